@@ -1,0 +1,140 @@
+/* spcsc.h -- C ABI of libspcsc.so, the B200-native convolutional sparse coding engine.
+ *
+ * The reference (bwohlberg/sporco, pure Python) has no FFI for this path; its extension
+ * contract is "subclass and override" (sporco/admm/admm.py:331-377 calls xstep, relax_AX,
+ * ystep, ustep, compute_residuals, update_rho; sporco/pgm/pgm.py:328-370 calls
+ * on_iteration_start, backtrack.update | xstep+ystep, compute_residuals) plus one real
+ * plug-in seam, the `sporco_cuda` import in sporco/cuda/__init__.py:6-18.  Each entry point
+ * below names the reference routine(s) it stands in for.  INTEGRATION.md shows the ctypes
+ * binding a sporco maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 (SPCSC_OK) or a negative spcsc_status; no C++ exception crosses
+ *    the ABI; spcsc_last_error() gives the message of the most recent failure;
+ *  - all array arguments are HOST pointers in the reference's own layouts, C order:
+ *      D  (hd, wd, Cd, M)     S  (N0, N1, C, K)     X/Y/U  (N0, N1, Cx, K, M), Cx = C-Cd+1
+ *      spectra Xf/Df/Sf as returned by sporco.fft.rfftn(..., axes=(0,1)):  (N0, N1/2+1, ...)
+ *    element type float or double according to spcsc_problem.dtype (complex = 2 reals);
+ *  - the caller owns host buffers (borrowed for the duration of the call); the library owns
+ *    all device memory of a handle; get_* calls copy out and synchronise;
+ *  - a handle is bound to one device and one stream and is not thread safe; distinct handles
+ *    are independent.
+ */
+#ifndef SPCSC_H_
+#define SPCSC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spcsc_handle spcsc_handle;
+
+typedef enum spcsc_status {
+    SPCSC_OK = 0,
+    SPCSC_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    SPCSC_ERR_CUDA = -2,         /* CUDA runtime error (sticky for the handle) */
+    SPCSC_ERR_NOMEM = -3,
+    SPCSC_ERR_UNSUPPORTED = -4,  /* valid for the reference but not implemented here */
+    SPCSC_ERR_STATE = -5,        /* call sequence error (e.g. iterate before set_dict) */
+    SPCSC_ERR_NCCL = -6
+} spcsc_status;
+
+enum { SPCSC_F32 = 0, SPCSC_F64 = 1 };
+
+/* Problem dimensions: what sporco/cnvrep.py:33-198 (CSC_ConvRepIndexing) infers. */
+typedef struct spcsc_problem {
+    int32_t N0, N1;        /* spatial size (both powers of two, N0 >= 2, N1 >= 4) */
+    int32_t C, Cd, K, M;   /* signal channels, dictionary channels, images, filters */
+    int32_t hd, wd;        /* filter support */
+    int32_t dtype;         /* SPCSC_F32 | SPCSC_F64 */
+    int32_t device;        /* CUDA device ordinal */
+} spcsc_problem;
+
+/* Options of the ADMM solver: sporco/admm/admm.py:148-161 + admm/cbpdn.py:127-134. */
+typedef struct spcsc_admm_opts {
+    double lmbda;          /* l1 weight                       admm/cbpdn.py:581 */
+    double mu;             /* l2,1 weight (joint only)        admm/cbpdn.py:780 */
+    double rlx;            /* RelaxParam                      admm/admm.py:877-885 */
+    double abs_tol, rel_tol;          /* AbsStopTol, RelStopTol      admm/admm.py:481-484 */
+    double ar_scaling;     /* AutoRho.Scaling (tau)           admm/admm.py:553 */
+    double ar_rsdl_ratio;  /* AutoRho.RsdlRatio (mu)          admm/admm.py:554 */
+    double ar_rsdl_target; /* AutoRho.RsdlTarget (xi), resolved by the caller  admm/cbpdn.py:588-593 */
+    int32_t ar_enabled, ar_period, ar_autoscaling, ar_std_residuals;
+    int32_t joint;         /* 1: ConvBPDNJoint prox (admm/cbpdn.py:785-794) */
+    int32_t nonneg;        /* NonNegCoef                      admm/cbpdn.py:306-307 */
+    int32_t no_bndry_cross;/* NoBndryCross                    admm/cbpdn.py:308-311 */
+    int32_t fast_solve;    /* FastSolve: skip objective       admm/admm.py:356 */
+    int32_t aux_var_obj;   /* AuxVarObj: objective on Y       admm/cbpdn.py:151-164 */
+    int32_t linsolve_check;/* LinSolveCheck                   admm/cbpdn.py:283-293 */
+} spcsc_admm_opts;
+
+/* One row of IterationStats (admm/admm.py:182-189, admm/cbpdn.py:512-514, 737-740). */
+typedef struct spcsc_itstat {
+    double iter, objfun, dfid, regl1, regl21, primal_rsdl, dual_rsdl, eps_primal, eps_dual,
+        rho, xslv_relres, reserved;
+} spcsc_itstat;
+
+typedef enum spcsc_array {
+    SPCSC_ARR_Y = 0, SPCSC_ARR_U = 1, SPCSC_ARR_X = 2,      /* real, (N0,N1,Cx,K,M) */
+    SPCSC_ARR_XF = 3,                                       /* complex, (N0,N1f,Cx,K,M) */
+    SPCSC_ARR_DF = 4,                                       /* complex, (N0,N1f,Cd,1,M) */
+    SPCSC_ARR_SF = 5                                        /* complex, (N0,N1f,C,K,1) */
+} spcsc_array;
+
+/* ---- library / device queries (stand-ins for sporco_cuda.util, docs/source/modules/sporco.cuda.rst:60-104) */
+int spcsc_version(void);
+int spcsc_device_count(void);
+int spcsc_device_name(int device, char* buf, int buflen);
+int spcsc_memory_info(int device, uint64_t* free_bytes, uint64_t* total_bytes);
+const char* spcsc_last_error(const spcsc_handle* h);   /* h may be NULL: last create() failure */
+
+/* ---- lifetime */
+int spcsc_create(const spcsc_problem* prob, spcsc_handle** out);
+int spcsc_destroy(spcsc_handle* h);
+int spcsc_synchronize(spcsc_handle* h);
+
+/* ---- problem data */
+/* GenericConvBPDN.setdict: Df = rfftn(D, Nv), Gram for the solve.   admm/cbpdn.py:242-256 */
+int spcsc_set_dict(spcsc_handle* h, const void* D);
+/* Sf = rfftn(S).                                                    admm/cbpdn.py:227-231 */
+int spcsc_set_signal(spcsc_handle* h, const void* S);
+/* L1Weight after cnvrep.l1Wshape: `shape` is its 5-D internal shape (each entry 1 or the full
+   extent of (N0,N1,Cx,K,M)).                                        admm/cbpdn.py:596-597 */
+int spcsc_set_l1_weight(spcsc_handle* h, const void* w, const int64_t shape[5]);
+/* L21Weight broadcast over (K, M): shape entries 1 or full.         admm/cbpdn.py:781 */
+int spcsc_set_l21_weight(spcsc_handle* h, const void* w, const int64_t shape[2]);
+
+/* ---- ADMM solver (ConvBPDN / ConvBPDNJoint) */
+int spcsc_admm_configure(spcsc_handle* h, const spcsc_admm_opts* opts);
+/* Y = U = 0 (or later set_array), k = 0, rho as given.              admm/admm.py:243-275 */
+int spcsc_admm_reset(spcsc_handle* h, double rho);
+int spcsc_admm_set_rho(spcsc_handle* h, double rho);
+/* Run up to n_iter iterations of admm/admm.py:331-377 on the device.  Stops early (device
+   side, no host round trip) once r < epri and s < edua.  `rows` (n_iter entries, may be NULL)
+   receives one spcsc_itstat per executed iteration.  Clears a previous stop flag on entry,
+   as re-entering ADMM.solve() does. */
+int spcsc_admm_iterate(spcsc_handle* h, int32_t n_iter, spcsc_itstat* rows, int32_t* n_done,
+                       int32_t* stopped);
+int spcsc_admm_get_scalars(spcsc_handle* h, double* rho, int32_t* k);
+
+/* ---- state access */
+int spcsc_get_array(spcsc_handle* h, int32_t which, void* host_out);
+int spcsc_set_array(spcsc_handle* h, int32_t which, const void* host_in);   /* Y or U */
+/* GenericConvBPDN.reconstruct: irfftn(sum_m Df * rfftn(X)); X == NULL means current Y.
+   out has shape (N0, N1, C, K).                                     admm/cbpdn.py:373-380 */
+int spcsc_reconstruct(spcsc_handle* h, const void* X, void* out);
+
+/* ---- level-1 entry points mirroring the reference's own unit-tested functions */
+/* sporco.fft.rfftn / irfftn over the last two axes of a (batch, N0, N1) array
+   (fft.py:257-314).  xf has shape (batch, N0, N1/2+1). */
+int spcsc_rfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1,
+                const void* x, void* xf);
+int spcsc_irfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1,
+                 const void* xf, void* x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPCSC_H_ */

@@ -1,0 +1,289 @@
+"""ctypes binding of libspcsc.so (the C ABI declared in include/spcsc.h).
+
+The library is the product: if it is missing, or if it reports no CUDA device, everything
+that needs it raises -- there is no CPU fallback in this package.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libspcsc.so')
+
+F32, F64 = 0, 1
+ARR_Y, ARR_U, ARR_X, ARR_XF, ARR_DF, ARR_SF = range(6)
+
+# every symbol include/spcsc.h declares (tests check the list against the header)
+SYMBOLS = (
+    'spcsc_version', 'spcsc_device_count', 'spcsc_device_name', 'spcsc_memory_info',
+    'spcsc_last_error', 'spcsc_create', 'spcsc_destroy', 'spcsc_synchronize',
+    'spcsc_set_dict', 'spcsc_set_signal', 'spcsc_set_l1_weight', 'spcsc_set_l21_weight',
+    'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_iterate',
+    'spcsc_admm_get_scalars', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
+    'spcsc_rfft2', 'spcsc_irfft2',
+)
+
+
+class SpcscError(RuntimeError):
+    """Error reported by libspcsc (status code in .status)."""
+
+    def __init__(self, status, msg):
+        RuntimeError.__init__(self, 'libspcsc error %d: %s' % (status, msg))
+        self.status = status
+
+
+class Problem(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ('N0', 'N1', 'C', 'Cd', 'K', 'M', 'hd', 'wd', 'dtype', 'device')]
+
+
+class AdmmOpts(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ('lmbda', 'mu', 'rlx', 'abs_tol', 'rel_tol', 'ar_scaling', 'ar_rsdl_ratio',
+                 'ar_rsdl_target')] + \
+               [(n, ctypes.c_int32) for n in
+                ('ar_enabled', 'ar_period', 'ar_autoscaling', 'ar_std_residuals', 'joint',
+                 'nonneg', 'no_bndry_cross', 'fast_solve', 'aux_var_obj', 'linsolve_check')]
+
+
+class ItStat(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ('iter', 'objfun', 'dfid', 'regl1', 'regl21', 'primal_rsdl', 'dual_rsdl',
+                 'eps_primal', 'eps_dual', 'rho', 'xslv_relres', 'reserved')]
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64p = ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)
+    lib.spcsc_version.restype = ctypes.c_int
+    lib.spcsc_device_count.restype = ctypes.c_int
+    lib.spcsc_device_name.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    lib.spcsc_memory_info.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint64),
+                                      ctypes.POINTER(ctypes.c_uint64)]
+    lib.spcsc_last_error.argtypes = [vp]
+    lib.spcsc_last_error.restype = ctypes.c_char_p
+    lib.spcsc_create.argtypes = [ctypes.POINTER(Problem), ctypes.POINTER(vp)]
+    lib.spcsc_destroy.argtypes = [vp]
+    lib.spcsc_synchronize.argtypes = [vp]
+    lib.spcsc_set_dict.argtypes = [vp, vp]
+    lib.spcsc_set_signal.argtypes = [vp, vp]
+    lib.spcsc_set_l1_weight.argtypes = [vp, vp, i64p]
+    lib.spcsc_set_l21_weight.argtypes = [vp, vp, i64p]
+    lib.spcsc_admm_configure.argtypes = [vp, ctypes.POINTER(AdmmOpts)]
+    lib.spcsc_admm_reset.argtypes = [vp, ctypes.c_double]
+    lib.spcsc_admm_set_rho.argtypes = [vp, ctypes.c_double]
+    lib.spcsc_admm_iterate.argtypes = [vp, i32, ctypes.POINTER(ItStat), ctypes.POINTER(i32),
+                                       ctypes.POINTER(i32)]
+    lib.spcsc_admm_get_scalars.argtypes = [vp, ctypes.POINTER(ctypes.c_double),
+                                           ctypes.POINTER(i32)]
+    lib.spcsc_get_array.argtypes = [vp, i32, vp]
+    lib.spcsc_set_array.argtypes = [vp, i32, vp]
+    lib.spcsc_reconstruct.argtypes = [vp, vp, vp]
+    lib.spcsc_rfft2.argtypes = [i32, i32, i32, i32, i32, vp, vp]
+    lib.spcsc_irfft2.argtypes = [i32, i32, i32, i32, i32, vp, vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name not in ('spcsc_version', 'spcsc_device_count'):
+            fn.restype = ctypes.c_int
+    return lib
+
+
+def load(path=None):
+    """Load (once) and return the ctypes library.  Raises if the extension is not built."""
+    global _lib
+    if path is None and _lib is not None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(
+            'libspcsc.so not found at %s -- build the CUDA extension first with '
+            '`python -m sporco_b200.build` (nvcc, sm_100a).  sporco_b200 has no CPU path.' % p)
+    lib = _declare(ctypes.CDLL(p))
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def use_library(lib):
+    """Install an already loaded library object as the process-wide binding.  Exists for
+    the test-suite's kernel emulation harness; product code never calls it."""
+    global _lib
+    _lib = lib
+
+
+def check(status, handle=None):
+    if status != 0:
+        msg = load().spcsc_last_error(handle)
+        raise SpcscError(status, msg.decode() if msg else 'unknown error')
+
+
+def dtype_code(dtype):
+    dt = np.dtype(dtype)
+    if dt == np.float32:
+        return F32
+    if dt == np.float64:
+        return F64
+    raise SpcscError(-4, 'unsupported data type %s (float32 and float64 only)' % dt)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def require_device():
+    lib = load()
+    n = lib.spcsc_device_count()
+    if n <= 0:
+        raise SpcscError(-2, 'no CUDA device visible: sporco_b200 runs on the GPU only')
+    return n
+
+
+class Handle(object):
+    """Thin object wrapper over a spcsc_handle."""
+
+    def __init__(self, N0, N1, C, Cd, K, M, hd, wd, dtype, device=0):
+        self.lib = load()
+        self.dtype = np.dtype(dtype)
+        self.cdtype = np.dtype(np.complex64 if self.dtype == np.float32 else np.complex128)
+        self.dims = dict(N0=N0, N1=N1, C=C, Cd=Cd, K=K, M=M, hd=hd, wd=wd)
+        self.Cx = C - Cd + 1
+        pb = Problem(N0, N1, C, Cd, K, M, hd, wd, dtype_code(dtype), device)
+        h = ctypes.c_void_p()
+        check(self.lib.spcsc_create(ctypes.byref(pb), ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.spcsc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _c(self, status):
+        check(status, self.h)
+
+    def _host(self, a, shape=None, complex_=False):
+        dt = self.cdtype if complex_ else self.dtype
+        a = np.ascontiguousarray(a, dtype=dt)
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError('array has shape %s, expected %s' % (a.shape, tuple(shape)))
+        return a
+
+    # shapes in the reference's layout
+    def xshape(self):
+        d = self.dims
+        return (d['N0'], d['N1'], self.Cx, d['K'], d['M'])
+
+    def set_dict(self, D):
+        d = self.dims
+        D = self._host(D, (d['hd'], d['wd'], d['Cd'], d['M']))
+        self._c(self.lib.spcsc_set_dict(self.h, _ptr(D)))
+
+    def set_signal(self, S):
+        d = self.dims
+        S = self._host(S, (d['N0'], d['N1'], d['C'], d['K']))
+        self._c(self.lib.spcsc_set_signal(self.h, _ptr(S)))
+
+    def set_l1_weight(self, W):
+        W = self._host(W)
+        if W.ndim != 5:
+            raise ValueError('l1 weight must be given in its 5-D internal shape')
+        shp = (ctypes.c_int64 * 5)(*W.shape)
+        self._c(self.lib.spcsc_set_l1_weight(self.h, _ptr(W), shp))
+
+    def set_l21_weight(self, W):
+        W = self._host(W)
+        if W.ndim != 2:
+            raise ValueError('l2,1 weight must be given with shape (K|1, M|1)')
+        shp = (ctypes.c_int64 * 2)(*W.shape)
+        self._c(self.lib.spcsc_set_l21_weight(self.h, _ptr(W), shp))
+
+    def admm_configure(self, **kw):
+        o = AdmmOpts()
+        for k, v in kw.items():
+            setattr(o, k, v)
+        self._c(self.lib.spcsc_admm_configure(self.h, ctypes.byref(o)))
+
+    def admm_reset(self, rho):
+        self._c(self.lib.spcsc_admm_reset(self.h, float(rho)))
+
+    def admm_set_rho(self, rho):
+        self._c(self.lib.spcsc_admm_set_rho(self.h, float(rho)))
+
+    def admm_iterate(self, n, want_rows=True):
+        rows = (ItStat * n)() if want_rows else None
+        nd = ctypes.c_int32(0)
+        st = ctypes.c_int32(0)
+        self._c(self.lib.spcsc_admm_iterate(self.h, n, rows, ctypes.byref(nd), ctypes.byref(st)))
+        return (rows, nd.value, bool(st.value))
+
+    def admm_scalars(self):
+        rho = ctypes.c_double(0)
+        k = ctypes.c_int32(0)
+        self._c(self.lib.spcsc_admm_get_scalars(self.h, ctypes.byref(rho), ctypes.byref(k)))
+        return rho.value, k.value
+
+    def get_array(self, which):
+        d = self.dims
+        N1f = d['N1'] // 2 + 1
+        if which in (ARR_Y, ARR_U, ARR_X):
+            out = np.empty(self.xshape(), dtype=self.dtype)
+        elif which == ARR_XF:
+            out = np.empty((d['N0'], N1f, self.Cx, d['K'], d['M']), dtype=self.cdtype)
+        elif which == ARR_DF:
+            out = np.empty((d['N0'], N1f, d['Cd'], 1, d['M']), dtype=self.cdtype)
+        elif which == ARR_SF:
+            out = np.empty((d['N0'], N1f, d['C'], d['K'], 1), dtype=self.cdtype)
+        else:
+            raise ValueError('unknown array id')
+        self._c(self.lib.spcsc_get_array(self.h, which, _ptr(out)))
+        return out
+
+    def set_array(self, which, a):
+        a = self._host(a, self.xshape())
+        self._c(self.lib.spcsc_set_array(self.h, which, _ptr(a)))
+
+    def reconstruct(self, X=None):
+        d = self.dims
+        out = np.empty((d['N0'], d['N1'], d['C'], d['K']), dtype=self.dtype)
+        if X is None:
+            self._c(self.lib.spcsc_reconstruct(self.h, None, _ptr(out)))
+        else:
+            X = self._host(X, self.xshape())
+            self._c(self.lib.spcsc_reconstruct(self.h, _ptr(X), _ptr(out)))
+        return out
+
+    def synchronize(self):
+        self._c(self.lib.spcsc_synchronize(self.h))
+
+
+def rfft2(x, device=0):
+    """rfftn over the last two axes of a (batch, N0, N1) real array, on the GPU."""
+    lib = load()
+    x = np.ascontiguousarray(x)
+    b, n0, n1 = x.shape
+    cdt = np.complex64 if x.dtype == np.float32 else np.complex128
+    out = np.empty((b, n0, n1 // 2 + 1), dtype=cdt)
+    check(lib.spcsc_rfft2(dtype_code(x.dtype), device, b, n0, n1, _ptr(x), _ptr(out)))
+    return out
+
+
+def irfft2(xf, n1, device=0):
+    """irfftn over the last two axes of a (batch, N0, N1/2+1) complex array, on the GPU."""
+    lib = load()
+    xf = np.ascontiguousarray(xf)
+    b, n0, n1f = xf.shape
+    if n1f != n1 // 2 + 1:
+        raise ValueError('inconsistent last-axis length')
+    rdt = np.float32 if xf.dtype == np.complex64 else np.float64
+    out = np.empty((b, n0, n1), dtype=rdt)
+    check(lib.spcsc_irfft2(dtype_code(rdt), device, b, n0, n1, _ptr(xf), _ptr(out)))
+    return out

@@ -1,0 +1,704 @@
+// kernels.cuh -- device kernels of the ConvBPDN hot path.
+//
+// Device data layout (all arrays dense, C order, spatial axis fastest):
+//   coefficient-shaped real arrays  Y, U           [K][Cx][M][N0][N1]
+//   row-spectrum / column slabs     Zt             [K][Cx][N1f][M][N0]   complex, N1f = N1/2+1
+//   dictionary spectrum             Df             [Cd][N1f][M][N0]      complex
+//   signal spectrum                 Sf             [K][C][N1f][N0]       complex
+//   Gram of the dictionary          G              [N1f][N0][Cd][Cd]     complex (Cd==1: real part = sum_m |Df|^2)
+// The reference keeps (N0,N1,C,K,M) with M fastest (sporco/cnvrep.py:104-198); conversion
+// happens once on upload / download (k_to_internal / k_from_internal).
+//
+// One ADMM iteration (sporco/admm/admm.py:331-377) is three data kernels + one scalar kernel:
+//   k_row_fwd       Y-U, real row FFT, transposed store         (admm/cbpdn.py:271-273, first half of rfftn)
+//   k_col           column FFT + Sherman-Morrison solve + column IFFT  (admm/cbpdn.py:273-281, linalg.py:232-297 / 370-444)
+//   k_row_inv_prox  row c2r IFFT + relax + prox + dual update + residual sums
+//                   (admm/admm.py:877-885, admm/cbpdn.py:614-620 / 785-794 / 297-311, admm/admm.py:434-437, 462-486)
+//   k_admm_scalars  residuals, stopping test, rho update  (admm/admm.py:462-486, 549-575)
+#pragma once
+
+#include "fft_core.cuh"
+
+namespace spcsc {
+
+// ------------------------------------------------------------------------------------
+// Device-resident solver scalars.
+// ------------------------------------------------------------------------------------
+enum { ACC_X2 = 0, ACC_Y2, ACC_U2, ACC_R2, ACC_S2, ACC_L1, ACC_L21, ACC_DFID,
+       ACC_AX2, ACC_B2, ACC_AXB2, ACC_N = 16 };
+
+template <typename T>
+struct AdmmState {
+    T rho;          // penalty parameter used by the next x-step
+    T udiv;         // pending dual rescale: U_effective = U_stored / udiv
+    int k;          // iterations completed
+    int stopped;    // 1 once the residual stopping test has fired
+};
+
+template <typename T>
+struct AdmmParams {
+    T lmbda, mu, rlx, tau, mur, xi;
+    double abs_tol, rel_tol, n_x;        // n_x = number of elements of X (== Nc)
+    double inv_n;                        // 1 / (N0*N1)
+    int autorho, period, autoscaling, stdres;
+    int need_rsdl, need_obj, joint, linsolve_check;
+};
+
+struct StatRow {
+    double k, obj, dfid, regl1, regl21, r, s, epri, edua, rho, xrrs, pad;
+};
+
+// l1 / l2,1 weight with numpy-style broadcasting over the internal index (k, c, m, n0, n1)
+template <typename T>
+struct WeightView {
+    const T* p;
+    long long sk, sc, sm, s0, s1;
+    int spatial_uniform;     // s0 == s1 == 0
+};
+
+// ------------------------------------------------------------------------------------
+// k_row_fwd:  Zt[b][wf][m][h] = rfft_row( A[b][m][h][:] - B[b][m][h][:] / udiv )
+//   A, B real [nb][M][N0][N1]; B may be null.  One CTA = TR consecutive rows of one (b,m).
+//   Real transform of length N1 = 2H done as a complex transform of length H on
+//   (even, odd) pairs followed by the usual split.
+// ------------------------------------------------------------------------------------
+template <typename T, int H>
+SPCSC_GLOBAL void k_row_fwd(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
+                            const AdmmState<T>* SPCSC_RESTRICT st, C2<T>* SPCSC_RESTRICT Zt,
+                            const C2<T>* SPCSC_RESTRICT tw, int N0, int M, int TR) {
+    if (st && st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);
+    constexpr int P = H + 1;
+    constexpr int TPF = fft_tpf<T, H>();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
+    const T udiv = (st && B) ? st->udiv : (T)1;
+
+    const size_t rowbase = (((size_t)b * M + m) * N0 + h0) * H;   // in C2 units
+    const C2<T>* A2 = reinterpret_cast<const C2<T>*>(A) + rowbase;
+    const C2<T>* B2 = B ? reinterpret_cast<const C2<T>*>(B) + rowbase : nullptr;
+    for (int e = tid; e < TR * H; e += nt) {
+        const int r = e / H, j = e - r * H;
+        C2<T> z = A2[e];
+        if (B2) {
+            C2<T> u = B2[e];
+            z.re -= u.re / udiv;
+            z.im -= u.im / udiv;
+        }
+        buf[r * P + j] = z;
+    }
+    __syncthreads();
+    {
+        const int row = tid / TPF, t = tid - row * TPF;
+        const bool active = row < TR;
+        fft_smem<T, H, false, 2>(buf + (active ? row : 0) * P, t, tw, active);
+    }
+    const int N1f = H + 1;
+    C2<T>* out = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
+    const size_t wstride = (size_t)M * N0;
+    for (int e = tid; e < TR * N1f; e += nt) {
+        const int wf = e / TR, r = e - wf * TR;
+        const C2<T> a = buf[r * P + (wf == H ? 0 : wf)];
+        const C2<T> bb = conj(buf[r * P + (wf == 0 ? 0 : H - wf)]);
+        const C2<T> w = tw[wf];
+        const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
+        out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Shared pieces of the row-inverse kernels: gather TR rows of one (b,m) from the slab
+// layout, undo the real-transform split, inverse complex FFT of length H.  Afterwards
+// buf[r*P + j] * scale = (x[h0+r][2j], x[h0+r][2j+1]).
+// ------------------------------------------------------------------------------------
+template <typename T, int H>
+SPCSC_DEV void row_inverse_to_smem(C2<T>* buf, const C2<T>* SPCSC_RESTRICT Zt,
+                                   const C2<T>* SPCSC_RESTRICT tw, int b, int m, int h0,
+                                   int N0, int M, int TR) {
+    constexpr int P = H + 1;
+    constexpr int TPF = fft_tpf<T, H>();
+    constexpr int N1f = H + 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const C2<T>* in = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
+    const size_t wstride = (size_t)M * N0;
+    for (int e = tid; e < TR * N1f; e += nt) {
+        const int wf = e / TR, r = e - wf * TR;
+        buf[r * P + wf] = in[wf * wstride + r];
+    }
+    __syncthreads();
+    constexpr int NP = H / 2 + 1;           // pairs (kk, H-kk), kk = 0..H/2
+    for (int e = tid; e < TR * NP; e += nt) {
+        const int r = e / NP, kk = e - r * NP;
+        C2<T>* row = buf + r * P;
+        if (kk == 0) {
+            const T a = row[0].re, c = row[H].re;    // c2r ignores the imaginary parts
+            row[0] = mk<T>(a + c, a - c);
+        } else {
+            const C2<T> Xa = row[kk], Xb = row[H - kk];
+            const C2<T> w = tw[kk];
+            // Z[kk]   = (Xa + conj Xb) + i conj(w) (Xa - conj Xb)
+            // Z[H-kk] = (Xb + conj Xa) - i w      (Xb - conj Xa)
+            const C2<T> s1 = Xa + conj(Xb), d1 = Xa - conj(Xb);
+            const C2<T> s2 = Xb + conj(Xa), d2 = Xb - conj(Xa);
+            row[kk] = s1 + mul_i(mulc(d1, w));
+            if (H - kk != kk) row[H - kk] = s2 - mul_i(d2 * w);
+        }
+    }
+    __syncthreads();
+    const int rowi = tid / TPF, t = tid - rowi * TPF;
+    const bool active = rowi < TR;
+    fft_smem<T, H, true, 2>(buf + (active ? rowi : 0) * P, t, tw, active);
+}
+
+// k_row_inv: X[b][m][h][:] = irfft_row(Zt) * scale   (plain inverse; used for get X,
+// reconstruction and the unit irfft2 entry point)
+template <typename T, int H>
+SPCSC_GLOBAL void k_row_inv(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT X,
+                            const C2<T>* SPCSC_RESTRICT tw, int N0, int M, int TR, T scale) {
+    SPCSC_DYN_SMEM(smem_raw);
+    C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);
+    constexpr int P = H + 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
+    row_inverse_to_smem<T, H>(buf, Zt, tw, b, m, h0, N0, M, TR);
+    C2<T>* X2 = reinterpret_cast<C2<T>*>(X) + (((size_t)b * M + m) * N0 + h0) * H;
+    for (int e = tid; e < TR * H; e += nt) {
+        const int r = e / H, j = e - r * H;
+        C2<T> z = buf[r * P + j];
+        X2[e] = mk<T>(z.re * scale, z.im * scale);
+    }
+}
+
+template <typename T>
+SPCSC_DEV T soft_threshold(T v, T thr) {
+    const T t = fabs(v) - thr;
+    return t > (T)0 ? copysign(t, v) : (T)0;
+}
+
+// ------------------------------------------------------------------------------------
+// k_row_inv_prox: for TR rows of one (k, m), all Cx channels:
+//   X = irfft_row(Zt)*scale ; AX = rlx X + (1-rlx) Y ; V = AX + U/udiv
+//   Y' = prox(V) (+NonNeg, +NoBndryCross) ; U' = U/udiv + (AX - Y') ; residual sums.
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int CX>
+SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y,
+                                 T* SPCSC_RESTRICT U, const AdmmState<T>* SPCSC_RESTRICT st,
+                                 AdmmParams<T> prm, WeightView<T> wl1, WeightView<T> wl21,
+                                 double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
+                                 int N0, int M, int TR, T scale, int nonneg,
+                                 int bnd0, int bnd1, int reg_on_y) {
+    if (st->stopped) return;
+    constexpr int Cx = CX;
+    SPCSC_DYN_SMEM(smem_raw);
+    C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);
+    constexpr int P = H + 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    const int N1 = 2 * H;
+    const size_t cbuf = (size_t)TR * P;
+
+    for (int c = 0; c < Cx; ++c)
+        row_inverse_to_smem<T, H>(buf + c * cbuf, Zt, tw, k * Cx + c, m, h0, N0, M, TR);
+    __syncthreads();
+
+    const T rho = st->rho, udiv = st->udiv;
+    const T lr = prm.lmbda / rho;
+    const T mr = prm.joint ? prm.mu / rho : (T)0;
+    const T rlx = prm.rlx;
+    double sums[7] = {0, 0, 0, 0, 0, 0, 0};
+
+    for (int e = tid; e < TR * H; e += nt) {
+        const int r = e / H, j = e - r * H;
+        const int h = h0 + r;
+        T a2[2] = {0, 0}, g2[2] = {0, 0};
+        T wv[CX][2], ax[CX][2], ue[CX][2], xv[CX][2], yp[CX][2];
+        SPCSC_UNROLL
+        for (int c = 0; c < Cx; ++c) {
+            const size_t off = ((((size_t)(k * Cx + c) * M + m) * N0 + h) * H + j);
+            const C2<T> z = buf[c * cbuf + r * P + j];
+            const C2<T> y2 = reinterpret_cast<const C2<T>*>(Y)[off];
+            const C2<T> u2 = reinterpret_cast<const C2<T>*>(U)[off];
+            const T xs[2] = {z.re * scale, z.im * scale};
+            const T ys[2] = {y2.re, y2.im};
+            const T us[2] = {u2.re / udiv, u2.im / udiv};
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                const T w1 = wl1.p[(size_t)k * wl1.sk + (size_t)c * wl1.sc + (size_t)m * wl1.sm +
+                                  (size_t)h * wl1.s0 + (size_t)(2 * j + q) * wl1.s1];
+                const T axv = (rlx == (T)1) ? xs[q] : rlx * xs[q] + ((T)1 - rlx) * ys[q];
+                const T v = axv + us[q];
+                const T w = soft_threshold(v, lr * w1);
+                xv[c][q] = xs[q];
+                yp[c][q] = ys[q];
+                ax[c][q] = axv;
+                ue[c][q] = us[q];
+                wv[c][q] = w;
+                a2[q] += w * w;
+                if (!reg_on_y) {
+                    sums[ACC_L1] += (double)fabs(w1 * xs[q]);
+                    g2[q] += xs[q] * xs[q];
+                }
+            }
+        }
+        T fac[2] = {1, 1};
+        T w21[2] = {1, 1};
+        if (prm.joint) {
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                w21[q] = wl21.p[(size_t)k * wl21.sk + (size_t)m * wl21.sm + (size_t)h * wl21.s0 +
+                                (size_t)(2 * j + q) * wl21.s1];
+                const T a = sqrt(a2[q]);
+                const T bq = fmax((T)0, a - mr * w21[q]);
+                fac[q] = (a != (T)0) ? bq / a : (T)0;
+            }
+        }
+        SPCSC_UNROLL
+        for (int c = 0; c < Cx; ++c) {
+            const size_t off = ((((size_t)(k * Cx + c) * M + m) * N0 + h) * H + j);
+            T yn[2], un[2];
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                T y = prm.joint ? fac[q] * wv[c][q] : wv[c][q];
+                if (nonneg && y < (T)0) y = (T)0;
+                if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+                const T u = ue[c][q] + (ax[c][q] - y);
+                yn[q] = y;
+                un[q] = u;
+                const T x = xv[c][q];
+                const T dr = x - y, ds = yp[c][q] - y;
+                sums[ACC_X2] += (double)x * x;
+                sums[ACC_Y2] += (double)y * y;
+                sums[ACC_U2] += (double)u * u;
+                sums[ACC_R2] += (double)dr * dr;
+                sums[ACC_S2] += (double)ds * ds;
+                if (reg_on_y) {
+                    const T w1 = wl1.p[(size_t)k * wl1.sk + (size_t)c * wl1.sc +
+                                      (size_t)m * wl1.sm + (size_t)h * wl1.s0 +
+                                      (size_t)(2 * j + q) * wl1.s1];
+                    sums[ACC_L1] += (double)fabs(w1 * y);
+                    g2[q] += y * y;
+                }
+            }
+            reinterpret_cast<C2<T>*>(Y)[off] = mk<T>(yn[0], yn[1]);
+            reinterpret_cast<C2<T>*>(U)[off] = mk<T>(un[0], un[1]);
+        }
+        if (prm.joint) {
+            sums[ACC_L21] += (double)(w21[0] * sqrt(g2[0])) + (double)(w21[1] * sqrt(g2[1]));
+        }
+    }
+    if (prm.need_rsdl || prm.need_obj) {
+        double* red = reinterpret_cast<double*>(smem_raw);
+        block_accumulate<7>(sums, red, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_col: one CTA per (wf, b) slab of M columns x N0.
+//   DO_FWD   : forward FFT along the column before the solve
+//   SOLVE    : 0 none, 1 ADMM  q = (rho I + G)^-1 (Sf - s),  2 gradient  q = (Sf - s)/L,
+//              3 sum only: write s_c = sum_m Df_c * col to `sumout` ([nb][Cd][N1f][N0])
+//   DO_INV   : inverse FFT (unnormalised) along the column after the update
+//   out = in + sum_c conj(Df_c) q_c       with s_c = sum_m Df_c[m] in[m]
+// The slab is processed in chunks of MC columns that fit shared memory; when the whole
+// slab fits (nchunk == 1) it stays resident between the reduction and the update.
+// ------------------------------------------------------------------------------------
+struct ColArgs {
+    int N0, M, Cd, Cs;     // Cs: channel count of Sf (C); b -> (k, c) = (b / Cx, b % Cx)
+    int Cx, N1f, MC, nchunk, parts;
+    int dfid_on, even_n1, check_on;
+};
+
+template <typename T, int MAXCD>
+SPCSC_DEV void hpd_solve(C2<T> (&A)[MAXCD][MAXCD], C2<T> (&bvec)[MAXCD], int n) {
+    // Gaussian elimination without pivoting on a Hermitian positive definite system.
+    for (int i = 0; i < n; ++i) {
+        const T inv = (T)1 / A[i][i].re;
+        for (int r = i + 1; r < n; ++r) {
+            const C2<T> f = inv * A[r][i];
+            for (int c = i; c < n; ++c) A[r][c] = A[r][c] - f * A[i][c];
+            bvec[r] = bvec[r] - f * bvec[i];
+        }
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        C2<T> s = bvec[i];
+        for (int c = i + 1; c < n; ++c) s = s - A[i][c] * bvec[c];
+        const T d = abs2(A[i][i]);
+        bvec[i] = mk<T>((s.re * A[i][i].re + s.im * A[i][i].im) / d,
+                        (s.im * A[i][i].re - s.re * A[i][i].im) / d);
+    }
+}
+
+template <typename T, int N0>
+SPCSC_DEV void col_load_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT src, int m0, int mc) {
+    for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) buf[e] = src[(size_t)m0 * N0 + e];
+    __syncthreads();
+}
+template <typename T, int N0, bool INV>
+SPCSC_DEV void col_fft_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT tw, int mc, int MC) {
+    constexpr int TPF = fft_tpf<T, N0>();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int cols_per_pass = nt / TPF > 0 ? nt / TPF : 1;
+    for (int c0 = 0; c0 < MC; c0 += cols_per_pass) {
+        const int col = c0 + tid / TPF, t = tid % TPF;
+        const bool active = (tid / TPF) < cols_per_pass && col < mc;
+        fft_smem<T, N0, INV, 1>(buf + (size_t)(active ? col : 0) * N0, t, tw, active);
+    }
+}
+
+template <typename T, int N0, bool DO_FWD, int SOLVE, bool DO_INV>
+SPCSC_GLOBAL void k_col(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out,
+                        const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
+                        const C2<T>* SPCSC_RESTRICT G, C2<T>* SPCSC_RESTRICT sumout,
+                        const AdmmState<T>* SPCSC_RESTRICT st, T Lstep,
+                        double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
+                        ColArgs a) {
+    if (st && st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    constexpr int MAXCD = 4;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int wf = blockIdx.x, b = blockIdx.y;
+    const int M = a.M, Cd = a.Cd, MC = a.MC;
+    C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);                 // [MC][N0]
+    C2<T>* spart = buf + (size_t)MC * N0;                             // [Cd][parts][N0]
+    const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
+    const C2<T>* src = in + slab;
+    C2<T>* dst = out ? out + slab : nullptr;
+    const bool resident = (a.nchunk == 1);
+    const T rho = (SOLVE == 1) ? st->rho : (T)0;
+
+    if (SOLVE != 0) {
+        // ---- phase A: s_c[h] = sum_m Df_c[m][h] * col[m][h]
+        const int parts = a.parts;
+        for (int e = tid; e < Cd * parts * N0; e += nt) spart[e] = mk<T>(0, 0);
+        __syncthreads();
+        for (int ch = 0; ch < a.nchunk; ++ch) {
+            const int m0 = ch * MC, mc = (M - m0 < MC) ? M - m0 : MC;
+            col_load_chunk<T, N0>(buf, src, m0, mc);
+            if (DO_FWD) col_fft_chunk<T, N0, false>(buf, tw, mc, MC);
+            for (int e = tid; e < parts * N0; e += nt) {
+                const int part = e / N0, h = e - part * N0;
+                for (int c = 0; c < Cd; ++c) {
+                    const C2<T>* dfc = Df + (((size_t)c * a.N1f + wf) * M + m0) * N0 + h;
+                    C2<T> s = mk<T>(0, 0);
+                    for (int mm = part; mm < mc; mm += parts)
+                        s = s + dfc[(size_t)mm * N0] * buf[(size_t)mm * N0 + h];
+                    C2<T>* sp = spart + ((size_t)c * parts + part) * N0 + h;
+                    *sp = *sp + s;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- q_c[h]
+        double dsum[1] = {0.0};
+        const int k = b / a.Cx, cx = b - k * a.Cx;
+        for (int h = tid; h < N0; h += nt) {
+            C2<T> d[MAXCD];
+            for (int c = 0; c < Cd; ++c) {
+                C2<T> s = mk<T>(0, 0);
+                for (int p = 0; p < parts; ++p) s = s + spart[((size_t)c * parts + p) * N0 + h];
+                if (SOLVE == 3) {
+                    d[c] = s;
+                } else {
+                    const int cs = (Cd > 1) ? c : cx;
+                    const C2<T> sf = Sf[(((size_t)k * a.Cs + cs) * a.N1f + wf) * N0 + h];
+                    d[c] = sf - s;
+                }
+            }
+            if (SOLVE == 1) {
+                if (Cd == 1) {
+                    const T g = G[(size_t)wf * N0 + h].re;
+                    const T den = g + rho;
+                    d[0] = mk<T>(d[0].re / den, d[0].im / den);
+                } else {
+                    C2<T> A[MAXCD][MAXCD];
+                    const C2<T>* Gp = G + ((size_t)wf * N0 + h) * Cd * Cd;
+                    for (int i = 0; i < Cd; ++i)
+                        for (int j = 0; j < Cd; ++j) {
+                            A[i][j] = Gp[i * Cd + j];
+                            if (i == j) A[i][j].re += rho;
+                        }
+                    hpd_solve<T, MAXCD>(A, d, Cd);
+                }
+                if (a.dfid_on) {
+                    const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+                    double q2 = 0.0;
+                    for (int c = 0; c < Cd; ++c) q2 += (double)abs2(d[c]);
+                    dsum[0] += wgt * q2;
+                }
+            } else if (SOLVE == 2) {
+                for (int c = 0; c < Cd; ++c) d[c] = mk<T>(d[c].re / Lstep, d[c].im / Lstep);
+            }
+            if (SOLVE == 3) {
+                for (int c = 0; c < Cd; ++c)
+                    sumout[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h] = d[c];
+            } else {
+                for (int c = 0; c < Cd; ++c) spart[((size_t)c * parts) * N0 + h] = d[c];
+            }
+        }
+        __syncthreads();
+        if (SOLVE == 1 && a.dfid_on) {
+            double* red = reinterpret_cast<double*>(spart + (size_t)Cd * parts * N0);
+            block_accumulate<1>(dsum, red, acc + ACC_DFID);
+        }
+        if (SOLVE == 3) return;
+    }
+
+    // ---- phase B: update, inverse transform, store
+    for (int ch = 0; ch < a.nchunk; ++ch) {
+        const int m0 = ch * MC, mc = (M - m0 < MC) ? M - m0 : MC;
+        if (!(resident && SOLVE != 0)) {
+            col_load_chunk<T, N0>(buf, src, m0, mc);
+            if (DO_FWD) col_fft_chunk<T, N0, false>(buf, tw, mc, MC);
+        }
+        if (SOLVE == 1 || SOLVE == 2) {
+            const int parts = a.parts;
+            for (int e = tid; e < mc * N0; e += nt) {
+                const int mm = e / N0, h = e - mm * N0;
+                C2<T> v = buf[e];
+                for (int c = 0; c < Cd; ++c) {
+                    const C2<T> df = Df[(((size_t)c * a.N1f + wf) * M + m0 + mm) * N0 + h];
+                    const C2<T> q = spart[((size_t)c * parts) * N0 + h];
+                    v = v + mulc(q, df);
+                }
+                buf[e] = v;
+            }
+            __syncthreads();
+        }
+        if (DO_INV) col_fft_chunk<T, N0, true>(buf, tw, mc, MC);
+        for (int e = tid; e < mc * N0; e += nt) dst[(size_t)m0 * N0 + e] = buf[e];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// LinSolveCheck (admm/cbpdn.py:283-293): relative residual of the x-step system, taken
+// honestly from the stored solution Xf (column-spectrum slab, before the inverse column
+// transform) -- a separate diagnostic kernel, only launched when the option is on.
+//   Zt holds Xf slabs; Zin holds the right-hand-side slabs rho*Z is formed from.
+// ------------------------------------------------------------------------------------
+template <typename T>
+SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* SPCSC_RESTRICT Zf,
+                                   const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
+                                   const AdmmState<T>* SPCSC_RESTRICT st,
+                                   double* SPCSC_RESTRICT acc, ColArgs a) {
+    // one CTA per (wf, b); thread per h (strided); loops over m twice.  Slow, diagnostic only.
+    if (st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int wf = blockIdx.x, b = blockIdx.y, N0 = a.N0, M = a.M, Cd = a.Cd;
+    const int k = b / a.Cx, cx = b - k * a.Cx;
+    const T rho = st->rho;
+    const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
+    double sums[3] = {0, 0, 0};
+    for (int h = tid; h < N0; h += nt) {
+        C2<T> e[4], sf[4];
+        for (int c = 0; c < Cd; ++c) {
+            C2<T> s = mk<T>(0, 0);
+            for (int m = 0; m < M; ++m)
+                s = s + Df[(((size_t)c * a.N1f + wf) * M + m) * N0 + h] * Xf[slab + (size_t)m * N0 + h];
+            e[c] = s;
+            const int cs = (Cd > 1) ? c : cx;
+            sf[c] = Sf[(((size_t)k * a.Cs + cs) * a.N1f + wf) * N0 + h];
+        }
+        for (int m = 0; m < M; ++m) {
+            const C2<T> x = Xf[slab + (size_t)m * N0 + h], z = Zf[slab + (size_t)m * N0 + h];
+            C2<T> ax = rho * x, bb = rho * z;
+            for (int c = 0; c < Cd; ++c) {
+                const C2<T> df = Df[(((size_t)c * a.N1f + wf) * M + m) * N0 + h];
+                ax = ax + mulc(e[c], df);
+                bb = bb + mulc(sf[c], df);
+            }
+            sums[0] += (double)abs2(ax);
+            sums[1] += (double)abs2(bb);
+            sums[2] += (double)abs2(ax - bb);
+        }
+    }
+    double* red = reinterpret_cast<double*>(smem_raw);
+    block_accumulate<3>(sums, red, acc + ACC_AX2);
+}
+
+// ------------------------------------------------------------------------------------
+// k_admm_scalars: one thread.  Replays admm/admm.py:462-486 (residuals, stopping
+// tolerances) and admm/admm.py:549-575 (rho update) in the working precision T from the
+// double-precision sums, writes one StatRow, advances k, clears the accumulators.
+// ------------------------------------------------------------------------------------
+template <typename T>
+SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
+                                 StatRow* rows, int k_base, int row_cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->stopped) return;
+    const int k = st->k;
+    T rho = st->rho;
+    T r = 0, s = 0;
+    double epri = 0, edua = 0;
+    if (p.need_rsdl) {
+        const T nX = (T)sqrt(acc[ACC_X2]), nY = (T)sqrt(acc[ACC_Y2]), nU = (T)sqrt(acc[ACC_U2]);
+        const T nR = (T)sqrt(acc[ACC_R2]), nS = rho * (T)sqrt(acc[ACC_S2]);
+        const T mx = nX > nY ? nX : nY;
+        if (p.stdres) {
+            r = nR;
+            s = nS;
+            epri = sqrt(p.n_x) * p.abs_tol + (double)mx * p.rel_tol;
+            edua = sqrt(p.n_x) * p.abs_tol + (double)(rho * nU) * p.rel_tol;
+        } else {
+            T rn = mx, sn = rho * nU;
+            if (rn == (T)0) rn = 1;
+            if (sn == (T)0) sn = 1;
+            r = nR / rn;
+            s = nS / sn;
+            epri = sqrt(p.n_x) * p.abs_tol / (double)rn + p.rel_tol;
+            edua = sqrt(p.n_x) * p.abs_tol / (double)sn + p.rel_tol;
+        }
+    }
+    if (rows && k - k_base >= 0 && k - k_base < row_cap) {
+        StatRow& o = rows[k - k_base];
+        o.k = k;
+        o.r = r; o.s = s; o.epri = epri; o.edua = edua; o.rho = rho;
+        o.dfid = o.regl1 = o.regl21 = o.obj = 0;
+        o.xrrs = -1.0;
+        if (p.need_obj) {
+            o.dfid = 0.5 * (double)rho * (double)rho * acc[ACC_DFID] * p.inv_n;
+            o.regl1 = acc[ACC_L1];
+            o.regl21 = acc[ACC_L21];
+            o.obj = o.dfid + (double)p.lmbda * o.regl1 + (p.joint ? (double)p.mu * o.regl21 : 0.0);
+        }
+        if (p.linsolve_check) {
+            const double na = sqrt(acc[ACC_AX2]), nb = sqrt(acc[ACC_B2]);
+            const double nm = na > nb ? na : nb;
+            o.xrrs = nm == 0.0 ? 0.0 : sqrt(acc[ACC_AXB2]) / nm;
+        }
+    }
+    T udiv = 1;
+    if (p.autorho && p.need_rsdl) {
+        if (k != 0 && ((k + 1) % p.period) == 0) {
+            T mlt;
+            if (p.autoscaling) {
+                if (s == (T)0 || r == (T)0) {
+                    mlt = p.tau;
+                } else {
+                    const T sx = s * p.xi;
+                    mlt = (T)sqrt(r > sx ? r / sx : sx / r);
+                    if (mlt > p.tau) mlt = p.tau;
+                }
+            } else {
+                mlt = p.tau;
+            }
+            T rsf = 1;
+            if (r > p.xi * p.mur * s) rsf = mlt;
+            else if (s > (p.mur / p.xi) * r) rsf = (T)1 / mlt;
+            rho = rho * rsf;
+            udiv = rsf;
+        }
+    }
+    st->rho = rho;
+    st->udiv = udiv;
+    st->k = k + 1;
+    if (p.need_rsdl && (double)r < epri && (double)s < edua) st->stopped = 1;
+    for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
+}
+
+// Fold a pending dual rescale into the stored U (used before U is read back).
+template <typename T>
+SPCSC_GLOBAL void k_apply_udiv(T* U, AdmmState<T>* st, size_t n) {
+    const T d = st->udiv;
+    if (d == (T)1) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        U[i] = U[i] / d;
+}
+template <typename T>
+SPCSC_GLOBAL void k_reset_udiv(AdmmState<T>* st) { st->udiv = 1; }
+
+// ------------------------------------------------------------------------------------
+// Layout conversion between the reference's (N0,N1,C,K,M) order and the device order
+// [K][C][M][N0*N1]: a tiled transpose of a (N0*N1) x (C*K*M) matrix with a row permutation.
+// ------------------------------------------------------------------------------------
+template <typename T>
+SPCSC_GLOBAL void k_to_internal(const T* SPCSC_RESTRICT ext, T* SPCSC_RESTRICT inr, int NP,
+                                int C, int K, int M) {
+    __shared__ T tile[32][33];
+    const int J = C * K * M;
+    const int p0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, j = j0 + tx;
+        if (p < NP && j < J) tile[i][tx] = ext[(size_t)p * J + j];
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int j = j0 + i, p = p0 + tx;
+        if (p < NP && j < J) {
+            const int m = j % M, kk = (j / M) % K, c = j / (M * K);
+            inr[(((size_t)kk * C + c) * M + m) * NP + p] = tile[tx][i];
+        }
+    }
+}
+
+template <typename T>
+SPCSC_GLOBAL void k_from_internal(const T* SPCSC_RESTRICT inr, T* SPCSC_RESTRICT ext, int NP,
+                                  int C, int K, int M) {
+    __shared__ T tile[32][33];
+    const int J = C * K * M;
+    const int p0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int j = j0 + i, p = p0 + tx;
+        if (p < NP && j < J) {
+            const int m = j % M, kk = (j / M) % K, c = j / (M * K);
+            tile[i][tx] = inr[(((size_t)kk * C + c) * M + m) * NP + p];
+        }
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, j = j0 + tx;
+        if (p < NP && j < J) ext[(size_t)p * J + j] = tile[tx][i];
+    }
+}
+
+// Zero-padded dictionary in device order [Cd][M][N0][N1] from the reference's (hd,wd,Cd,M).
+template <typename T>
+SPCSC_GLOBAL void k_pad_dict(const T* SPCSC_RESTRICT D, T* SPCSC_RESTRICT Dp, int hd, int wd,
+                             int Cd, int M, int N0, int N1) {
+    const size_t n = (size_t)Cd * M * N0 * N1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % N1), y = (int)((i / N1) % N0);
+        const int m = (int)((i / ((size_t)N1 * N0)) % M), c = (int)(i / ((size_t)N1 * N0 * M));
+        Dp[i] = (y < hd && x < wd) ? D[(((size_t)y * wd + x) * Cd + c) * M + m] : (T)0;
+    }
+}
+
+// Gram of the dictionary per frequency: G[wf][h][c][c'] = sum_m Df_c[m] conj(Df_c'[m]).
+template <typename T>
+SPCSC_GLOBAL void k_gram(const C2<T>* SPCSC_RESTRICT Df, C2<T>* SPCSC_RESTRICT G, int N1f, int N0,
+                         int M, int Cd) {
+    const size_t n = (size_t)N1f * N0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % N0), wf = (int)(i / N0);
+        for (int c = 0; c < Cd; ++c)
+            for (int d = 0; d < Cd; ++d) {
+                C2<T> s = mk<T>(0, 0);
+                for (int m = 0; m < M; ++m)
+                    s = s + mulc(Df[(((size_t)c * N1f + wf) * M + m) * N0 + h],
+                                 Df[(((size_t)d * N1f + wf) * M + m) * N0 + h]);
+                G[(i * Cd + c) * Cd + d] = s;
+            }
+    }
+}
+
+// out[b][h][wf] <-> in[b][wf][h]  (complex; unit-test entry points and Xf/Df/Sf read-back)
+template <typename T>
+SPCSC_GLOBAL void k_swap_last2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, int A, int B) {
+    // in [nb][A][B] -> out [nb][B][A]
+    const size_t n = (size_t)A * B;
+    const size_t base = (size_t)blockIdx.y * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int bb = (int)(i % B), aa = (int)(i / B);
+        out[base + (size_t)bb * A + aa] = in[base + i];
+    }
+}
+
+}  // namespace spcsc

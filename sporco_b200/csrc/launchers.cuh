@@ -1,0 +1,81 @@
+// launchers.cuh -- size-templated kernel launchers.  Each transform length is compiled in
+// its own translation unit (size_inst.cu with -DSPCSC_SIZE=n) so the library builds in
+// parallel; spcsc.cu dispatches on the runtime size.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace spcsc {
+
+constexpr size_t kSmemLimit = 220 * 1024;     // of the 227 KB a CTA may opt into on sm_100a
+
+template <typename T>
+struct RowArgs {
+    int N0, M, nb, TR;           // rows per image, filters, batch (K*Cx or Cd ...), rows per CTA
+    int Cx;                      // channels handled together by the prox kernel
+    const C2<T>* tw;             // exp(-2 pi i j / N1), j < N1
+    cudaStream_t stream;
+};
+
+template <typename T>
+struct ProxArgs {
+    AdmmParams<T> prm;
+    WeightView<T> wl1, wl21;
+    double* acc;
+    T scale;
+    int nonneg, bnd0, bnd1, reg_on_y;
+};
+
+enum ColMode {
+    COL_FWD = 0,        // forward column FFT only
+    COL_INV = 1,        // inverse column FFT only
+    COL_ADMM = 2,       // forward, Sherman-Morrison / Woodbury solve, inverse
+    COL_ADMM_NOFFT = 3, // solve only (input and output in the full 2-D frequency domain)
+    COL_GRAD_INV = 4,   // gradient step (q = (Sf - s)/L) then inverse   [PGM]
+    COL_FWD_SUM = 5,    // forward, write s_c = sum_m Df_c X
+    COL_SUM = 6         // write s_c = sum_m Df_c X (input already in frequency domain)
+};
+
+template <typename T>
+struct ColLaunch {
+    const C2<T>* in;
+    C2<T>* out;
+    const C2<T>* Df;
+    const C2<T>* Sf;
+    const C2<T>* G;
+    C2<T>* sumout;
+    const AdmmState<T>* st;
+    T Lstep;
+    double* acc;
+    const C2<T>* tw;             // exp(-2 pi i j / N0)
+    int nb;                      // slabs per frequency column (grid.y)
+    ColArgs a;                   // MC / nchunk / parts filled by the launcher
+    cudaStream_t stream;
+};
+
+// rows: H = N1/2
+template <typename T, int H>
+cudaError_t row_fwd_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
+                           C2<T>* Zt);
+template <typename T, int H>
+cudaError_t row_inv_launch(const RowArgs<T>& r, const C2<T>* Zt, T* X, T scale);
+template <typename T, int H>
+cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
+                                T* U, const AdmmState<T>* st);
+// columns
+template <typename T, int N0>
+cudaError_t col_launch(int mode, ColLaunch<T> c);
+
+// Rows per CTA for the row kernels (shared by launch code and memory planning).
+template <typename T>
+inline int row_tile(int H, int N0, int Cx) {
+    int e = H >= 64 ? 8 : (H >= 16 ? 4 : 2);
+    int tpf = H / e;
+    int tr = 256 / tpf;
+    if (tr < 1) tr = 1;
+    if (tr > N0) tr = N0;
+    while (tr > 1 && (size_t)Cx * tr * (H + 1) * sizeof(C2<T>) > 96 * 1024) tr >>= 1;
+    return tr;
+}
+
+}  // namespace spcsc

@@ -1,0 +1,105 @@
+// launchers_impl.cuh -- definitions of the size-templated launchers (see launchers.cuh).
+#pragma once
+
+#include "launchers.cuh"
+
+namespace spcsc {
+
+inline int round_up32(int n) { return (n + 31) / 32 * 32; }
+
+template <typename T, int H>
+cudaError_t row_fwd_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
+                           C2<T>* Zt) {
+    constexpr int TPF = fft_tpf<T, H>();
+    const int nt = round_up32(r.TR * TPF);
+    size_t smem = (size_t)r.TR * (H + 1) * sizeof(C2<T>);
+    dim3 grid(r.N0 / r.TR, r.M, r.nb);
+    return launch(k_row_fwd<T, H>, grid, dim3(nt), smem, r.stream, A, B, st, Zt, r.tw, r.N0, r.M,
+                  r.TR);
+}
+
+template <typename T, int H>
+cudaError_t row_inv_launch(const RowArgs<T>& r, const C2<T>* Zt, T* X, T scale) {
+    constexpr int TPF = fft_tpf<T, H>();
+    const int nt = round_up32(r.TR * TPF);
+    size_t smem = (size_t)r.TR * (H + 1) * sizeof(C2<T>);
+    dim3 grid(r.N0 / r.TR, r.M, r.nb);
+    return launch(k_row_inv<T, H>, grid, dim3(nt), smem, r.stream, Zt, X, r.tw, r.N0, r.M, r.TR,
+                  scale);
+}
+
+template <typename T, int H, int CX>
+static cudaError_t row_inv_prox_cx(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
+                                   T* U, const AdmmState<T>* st) {
+    constexpr int TPF = fft_tpf<T, H>();
+    const int nt = round_up32(r.TR * TPF);
+    size_t smem = (size_t)CX * r.TR * (H + 1) * sizeof(C2<T>);
+    if (smem < 7 * 32 * sizeof(double)) smem = 7 * 32 * sizeof(double);
+    dim3 grid(r.N0 / r.TR, r.M, r.nb / CX);
+    return launch(k_row_inv_prox<T, H, CX>, grid, dim3(nt), smem, r.stream, Zt, Y, U, st, p.prm,
+                  p.wl1, p.wl21, p.acc, r.tw, r.N0, r.M, r.TR, p.scale, p.nonneg, p.bnd0, p.bnd1,
+                  p.reg_on_y);
+}
+
+template <typename T, int H>
+cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
+                                T* U, const AdmmState<T>* st) {
+    switch (r.Cx) {
+        case 1: return row_inv_prox_cx<T, H, 1>(r, p, Zt, Y, U, st);
+        case 2: return row_inv_prox_cx<T, H, 2>(r, p, Zt, Y, U, st);
+        case 3: return row_inv_prox_cx<T, H, 3>(r, p, Zt, Y, U, st);
+        case 4: return row_inv_prox_cx<T, H, 4>(r, p, Zt, Y, U, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// Choose threads / chunking for the column kernel.
+template <typename T, int N0>
+inline void col_plan(ColArgs& a, int& nthreads, size_t& smem) {
+    constexpr int TPF = fft_tpf<T, N0>();
+    const int maxt = sizeof(T) == 4 ? 1024 : 512;
+    const size_t sz = sizeof(C2<T>);
+    int want = round_up32(a.M * TPF);
+    nthreads = want < maxt ? want : maxt;
+    if (nthreads < 32) nthreads = 32;
+    int parts = nthreads / N0;
+    if (parts < 1) parts = 1;
+    if (parts > 8) parts = 8;
+    if (parts > a.M) parts = a.M;
+    a.parts = parts;
+    const size_t fixed = (size_t)a.Cd * parts * N0 * sz + 64 * sizeof(double);
+    size_t room = kSmemLimit - fixed;
+    int mc = (int)(room / ((size_t)N0 * sz));
+    if (mc > a.M) mc = a.M;
+    if (mc < 1) mc = 1;
+    a.MC = mc;
+    a.nchunk = (a.M + mc - 1) / mc;
+    smem = (size_t)mc * N0 * sz + fixed;
+}
+
+template <typename T, int N0, bool F, int S, bool I>
+static cudaError_t col_go(ColLaunch<T>& c) {
+    int nt;
+    size_t smem;
+    col_plan<T, N0>(c.a, nt, smem);
+    dim3 grid(c.a.N1f, c.nb);
+    return launch(k_col<T, N0, F, S, I>, grid, dim3(nt), smem, c.stream, c.in, c.out, c.Df, c.Sf,
+                  c.G, c.sumout, c.st, c.Lstep, c.acc, c.tw, c.a);
+}
+
+template <typename T, int N0>
+cudaError_t col_launch(int mode, ColLaunch<T> c) {
+    c.a.N0 = N0;
+    switch (mode) {
+        case COL_FWD: return col_go<T, N0, true, 0, false>(c);
+        case COL_INV: return col_go<T, N0, false, 0, true>(c);
+        case COL_ADMM: return col_go<T, N0, true, 1, true>(c);
+        case COL_ADMM_NOFFT: return col_go<T, N0, false, 1, false>(c);
+        case COL_GRAD_INV: return col_go<T, N0, false, 2, true>(c);
+        case COL_FWD_SUM: return col_go<T, N0, true, 3, false>(c);
+        case COL_SUM: return col_go<T, N0, false, 3, false>(c);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace spcsc

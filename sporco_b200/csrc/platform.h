@@ -1,0 +1,114 @@
+// platform.h -- the one place where the kernels meet the toolchain.
+//
+// Product build: nvcc, sm_100a, real CUDA runtime.
+// SPCSC_EMU build: g++ only, used by tests/emu to execute the *same kernel source* on the
+// CPU (cooperative fibres stand in for CUDA threads) so index arithmetic and control
+// flow can be checked in a container without a GPU.  The emulation layer itself lives
+// under tests/emu/ and is never built into libspcsc.so.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <utility>
+
+#ifdef SPCSC_EMU
+#include "cuda_emu.h"            // tests/emu/cuda_emu.h (test infrastructure)
+#define SPCSC_HD
+#define SPCSC_DEV inline
+#define SPCSC_GLOBAL
+#define SPCSC_LAUNCH_BOUNDS(t)
+#define SPCSC_RESTRICT
+#define SPCSC_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#define SPCSC_UNROLL
+#else
+#include <cuda_runtime.h>
+#define SPCSC_HD __host__ __device__ __forceinline__
+#define SPCSC_DEV __device__ __forceinline__
+#define SPCSC_GLOBAL __global__
+#define SPCSC_LAUNCH_BOUNDS(t) __launch_bounds__(t)
+#define SPCSC_RESTRICT __restrict__
+#define SPCSC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define SPCSC_UNROLL _Pragma("unroll")
+#endif
+
+namespace spcsc {
+
+// ---- kernel launch -----------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          cudaStream_t stream, Args... args) {
+#ifdef SPCSC_EMU
+    (void)stream;
+    emu::launch(grid, block, smem, [=]() { kern(args...); });
+    return cudaSuccess;
+#else
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, block, smem, stream>>>(args...);
+    return cudaGetLastError();
+#endif
+}
+
+// ---- complex value type with natural vector alignment (8 B for float, 16 B for double)
+template <typename T>
+struct alignas(2 * sizeof(T)) C2 {
+    T re, im;
+};
+
+template <typename T> SPCSC_HD C2<T> mk(T a, T b) { C2<T> r; r.re = a; r.im = b; return r; }
+template <typename T> SPCSC_HD C2<T> operator+(C2<T> a, C2<T> b) { return mk<T>(a.re + b.re, a.im + b.im); }
+template <typename T> SPCSC_HD C2<T> operator-(C2<T> a, C2<T> b) { return mk<T>(a.re - b.re, a.im - b.im); }
+template <typename T> SPCSC_HD C2<T> operator*(C2<T> a, C2<T> b) {
+    return mk<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+template <typename T> SPCSC_HD C2<T> operator*(T s, C2<T> a) { return mk<T>(s * a.re, s * a.im); }
+template <typename T> SPCSC_HD C2<T> conj(C2<T> a) { return mk<T>(a.re, -a.im); }
+// a * conj(b)
+template <typename T> SPCSC_HD C2<T> mulc(C2<T> a, C2<T> b) {
+    return mk<T>(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im);
+}
+// multiply by +i / -i
+template <typename T> SPCSC_HD C2<T> mul_i(C2<T> a) { return mk<T>(-a.im, a.re); }
+template <typename T> SPCSC_HD C2<T> mul_mi(C2<T> a) { return mk<T>(a.im, -a.re); }
+template <typename T> SPCSC_HD T abs2(C2<T> a) { return a.re * a.re + a.im * a.im; }
+
+// ---- warp / block reductions (double accumulators) -------------------------------------
+SPCSC_DEV double warp_sum(double v) {
+    SPCSC_UNROLL
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum NV doubles per thread over the whole block, then one atomicAdd per value from
+// thread 0 into acc[0..NV).  `red` is block-shared scratch of at least NV*32 doubles.
+// All threads of the block must call this (blockDim.x a multiple of 32).
+template <int NV>
+SPCSC_DEV void block_accumulate(const double (&v)[NV], double* red, double* acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
+    double w[NV];
+    SPCSC_UNROLL
+    for (int i = 0; i < NV; ++i) w[i] = warp_sum(v[i]);
+    __syncthreads();                       // scratch may alias buffers used earlier
+    if (lane == 0) {
+        SPCSC_UNROLL
+        for (int i = 0; i < NV; ++i) red[i * 32 + warp] = w[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        SPCSC_UNROLL
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < nwarp) ? red[i * 32 + lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0 && x != 0.0) atomicAdd(acc + i, x);
+        }
+    }
+}
+
+}  // namespace spcsc

@@ -1,0 +1,784 @@
+// spcsc.cu -- host side of libspcsc.so: handle management, device memory, the per-iteration
+// launch schedule and the extern "C" entry points declared in include/spcsc.h.
+#include <spcsc.h>
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "launchers.cuh"
+
+namespace spcsc {
+
+// ---- dispatch on transform length -------------------------------------------------------
+#define SPCSC_FOR_SIZES(X) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
+
+#define SPCSC_DECL(n)                                                                           \
+    extern template cudaError_t row_fwd_launch<float, n>(const RowArgs<float>&, const float*,   \
+                                                         const float*, const AdmmState<float>*, \
+                                                         C2<float>*);                           \
+    extern template cudaError_t row_fwd_launch<double, n>(const RowArgs<double>&, const double*, \
+                                                          const double*,                         \
+                                                          const AdmmState<double>*, C2<double>*); \
+    extern template cudaError_t row_inv_launch<float, n>(const RowArgs<float>&, const C2<float>*, \
+                                                         float*, float);                        \
+    extern template cudaError_t row_inv_launch<double, n>(const RowArgs<double>&,                \
+                                                          const C2<double>*, double*, double);  \
+    extern template cudaError_t row_inv_prox_launch<float, n>(                                  \
+        const RowArgs<float>&, const ProxArgs<float>&, const C2<float>*, float*, float*,        \
+        const AdmmState<float>*);                                                               \
+    extern template cudaError_t row_inv_prox_launch<double, n>(                                 \
+        const RowArgs<double>&, const ProxArgs<double>&, const C2<double>*, double*, double*,   \
+        const AdmmState<double>*);                                                              \
+    extern template cudaError_t col_launch<float, n>(int, ColLaunch<float>);                    \
+    extern template cudaError_t col_launch<double, n>(int, ColLaunch<double>);
+SPCSC_FOR_SIZES(SPCSC_DECL)
+
+static bool supported_len(int n) { return n >= 2 && n <= 1024 && (n & (n - 1)) == 0; }
+
+template <typename T>
+static cudaError_t row_fwd(int H, const RowArgs<T>& r, const T* A, const T* B,
+                           const AdmmState<T>* st, C2<T>* Zt) {
+    switch (H) {
+#define X(n) case n: return row_fwd_launch<T, n>(r, A, B, st, Zt);
+        SPCSC_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T>
+static cudaError_t row_inv(int H, const RowArgs<T>& r, const C2<T>* Zt, T* Xo, T scale) {
+    switch (H) {
+#define X(n) case n: return row_inv_launch<T, n>(r, Zt, Xo, scale);
+        SPCSC_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T>
+static cudaError_t row_inv_prox(int H, const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
+                                T* Y, T* U, const AdmmState<T>* st) {
+    switch (H) {
+#define X(n) case n: return row_inv_prox_launch<T, n>(r, p, Zt, Y, U, st);
+        SPCSC_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T>
+static cudaError_t col(int N0, int mode, const ColLaunch<T>& c) {
+    switch (N0) {
+#define X(n) case n: return col_launch<T, n>(mode, c);
+        SPCSC_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+// complex spectra between device order [b][N1f][Mm][N0] (b = k*Cc + c) and the reference's
+// (N0, N1f, Cc, Kk, Mm)
+template <typename T>
+SPCSC_GLOBAL void k_freq_to_ext(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT ext, int N0,
+                                int N1f, int Cc, int Kk, int Mm) {
+    const size_t n = (size_t)N0 * N1f * Cc * Kk * Mm;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        size_t t = i;
+        const int m = (int)(t % Mm); t /= Mm;
+        const int k = (int)(t % Kk); t /= Kk;
+        const int c = (int)(t % Cc); t /= Cc;
+        const int wf = (int)(t % N1f); t /= N1f;
+        const int h = (int)t;
+        ext[i] = in[((((size_t)k * Cc + c) * N1f + wf) * Mm + m) * N0 + h];
+    }
+}
+
+}  // namespace spcsc
+
+using namespace spcsc;
+
+static thread_local std::string g_last_error;
+
+struct spcsc_handle {
+    std::string err;
+    bool poisoned = false;
+    virtual ~spcsc_handle() {}
+    virtual int set_dict(const void* D) = 0;
+    virtual int set_signal(const void* S) = 0;
+    virtual int set_l1_weight(const void* w, const int64_t* shape) = 0;
+    virtual int set_l21_weight(const void* w, const int64_t* shape) = 0;
+    virtual int admm_configure(const spcsc_admm_opts* o) = 0;
+    virtual int admm_reset(double rho) = 0;
+    virtual int admm_set_rho(double rho) = 0;
+    virtual int admm_iterate(int n, spcsc_itstat* rows, int* n_done, int* stopped) = 0;
+    virtual int admm_get_scalars(double* rho, int* k) = 0;
+    virtual int get_array(int which, void* out) = 0;
+    virtual int set_array(int which, const void* in) = 0;
+    virtual int reconstruct(const void* X, void* out) = 0;
+    virtual int synchronize() = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            poisoned = true;                                                             \
+            return SPCSC_ERR_CUDA;                                                       \
+        }                                                                                \
+    } while (0)
+
+#define FAIL(code, msg)        \
+    do {                       \
+        err = (msg);           \
+        return (code);         \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T>
+std::vector<C2<T>> twiddles(int n) {
+    std::vector<C2<T>> w(n);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int j = 0; j < n; ++j) {
+        const double a = -two_pi * (double)j / (double)n;
+        w[j] = mk<T>((T)std::cos(a), (T)std::sin(a));
+    }
+    return w;
+}
+
+template <typename T>
+class Engine : public spcsc_handle {
+  public:
+    spcsc_problem pb;
+    int N0, N1, H, N1f, C, Cd, Cx, K, M;
+    size_t nreal;       // K*Cx*M*N0*N1
+    size_t nslab;       // K*Cx*N1f*M*N0
+    cudaStream_t stream = nullptr;
+    DevBuf<T> Y, U, tmp_real, wl1_buf, wl21_buf, staging;
+    DevBuf<C2<T>> Zt, Zscratch, Xscratch, Df, Sf, G, tw_row, tw_col, sum_buf;
+    DevBuf<double> acc;
+    DevBuf<AdmmState<T>> st;
+    DevBuf<StatRow> rows;
+    WeightView<T> wl1, wl21;
+    AdmmParams<T> prm;
+    spcsc_admm_opts opts;
+    bool have_dict = false, have_signal = false, configured = false, have_x = false;
+
+    explicit Engine(const spcsc_problem& p) : pb(p) {
+        N0 = p.N0; N1 = p.N1; H = N1 / 2; N1f = H + 1;
+        C = p.C; Cd = p.Cd; K = p.K; M = p.M;
+        Cx = C - Cd + 1;
+        nreal = (size_t)K * Cx * M * N0 * N1;
+        nslab = (size_t)K * Cx * N1f * M * N0;
+        memset(&opts, 0, sizeof(opts));
+        memset(&prm, 0, sizeof(prm));
+    }
+    ~Engine() override {
+        cudaSetDevice(pb.device);
+        Y.release(); U.release(); tmp_real.release(); wl1_buf.release(); wl21_buf.release();
+        staging.release(); Zt.release(); Zscratch.release(); Xscratch.release(); Df.release();
+        Sf.release(); G.release(); tw_row.release(); tw_col.release(); sum_buf.release();
+        acc.release(); st.release(); rows.release();
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int init() {
+        CK(cudaSetDevice(pb.device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(Y.ensure(nreal));
+        CK(U.ensure(nreal));
+        CK(Zt.ensure(nslab));
+        CK(Df.ensure((size_t)Cd * N1f * M * N0));
+        CK(Sf.ensure((size_t)K * C * N1f * N0));
+        CK(G.ensure((size_t)N1f * N0 * Cd * Cd));
+        CK(acc.ensure(ACC_N));
+        CK(st.ensure(1));
+        CK(tw_row.ensure(N1));
+        CK(tw_col.ensure(N0));
+        auto wr = twiddles<T>(N1), wc = twiddles<T>(N0);
+        CK(cudaMemcpyAsync(tw_row.p, wr.data(), N1 * sizeof(C2<T>), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(tw_col.p, wc.data(), N0 * sizeof(C2<T>), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        // default weights: scalar 1
+        const T one = 1;
+        CK(wl1_buf.ensure(1));
+        CK(wl21_buf.ensure(1));
+        CK(cudaMemcpyAsync(wl1_buf.p, &one, sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(wl21_buf.p, &one, sizeof(T), cudaMemcpyHostToDevice, stream));
+        wl1 = WeightView<T>{wl1_buf.p, 0, 0, 0, 0, 0, 1};
+        wl21 = WeightView<T>{wl21_buf.p, 0, 0, 0, 0, 0, 1};
+        CK(cudaStreamSynchronize(stream));
+        return admm_reset(1.0);
+    }
+
+    RowArgs<T> rowargs(int m, int nb, int cx) const {
+        RowArgs<T> r;
+        r.N0 = N0; r.M = m; r.nb = nb; r.Cx = cx;
+        r.TR = row_tile<T>(H, N0, cx);
+        r.tw = tw_row.p;
+        r.stream = stream;
+        return r;
+    }
+    ColLaunch<T> colargs(int m, int nb) const {
+        ColLaunch<T> c;
+        memset(&c, 0, sizeof(c));
+        c.Df = Df.p; c.Sf = Sf.p; c.G = G.p;
+        c.tw = tw_col.p;
+        c.nb = nb;
+        c.a.N0 = N0; c.a.M = m; c.a.Cd = Cd; c.a.Cs = C; c.a.Cx = Cx; c.a.N1f = N1f;
+        c.a.even_n1 = 1;
+        c.stream = stream;
+        c.Lstep = 1;
+        return c;
+    }
+
+    // rfft2 of a real array in device order [nb][m][N0][N1] into slab order [nb][N1f][m][N0]
+    int forward2d(const T* real_in, C2<T>* out, int m, int nb) {
+        CK(row_fwd<T>(H, rowargs(m, nb, 1), real_in, (const T*)nullptr,
+                      (const AdmmState<T>*)nullptr, out));
+        ColLaunch<T> c = colargs(m, nb);
+        c.in = out; c.out = out;
+        c.a.Cd = 1;
+        CK(col<T>(N0, COL_FWD, c));
+        return SPCSC_OK;
+    }
+
+    int set_dict(const void* D) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        CK(cudaSetDevice(pb.device));
+        const size_t nd = (size_t)pb.hd * pb.wd * Cd * M;
+        CK(staging.ensure(nd));
+        CK(tmp_real.ensure((size_t)Cd * M * N0 * N1));
+        CK(cudaMemcpyAsync(staging.p, D, nd * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(launch(k_pad_dict<T>, dim3(1024), dim3(256), 0, stream, (const T*)staging.p, tmp_real.p,
+                  pb.hd, pb.wd, Cd, M, N0, N1));
+        int rc = forward2d(tmp_real.p, Df.p, M, Cd);
+        if (rc) return rc;
+        CK(launch(k_gram<T>, dim3(256), dim3(128), 0, stream, (const C2<T>*)Df.p, G.p, N1f, N0, M, Cd));
+        CK(cudaStreamSynchronize(stream));
+        have_dict = true;
+        return SPCSC_OK;
+    }
+
+    int to_internal(const void* host, T* dst, int c, int k, int m) {
+        const size_t n = (size_t)N0 * N1 * c * k * m;
+        CK(staging.ensure(n));
+        CK(cudaMemcpyAsync(staging.p, host, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        dim3 grid((N0 * N1 + 31) / 32, (c * k * m + 31) / 32);
+        CK(launch(k_to_internal<T>, grid, dim3(256), 0, stream, (const T*)staging.p, dst, N0 * N1, c, k, m));
+        return SPCSC_OK;
+    }
+    int from_internal(const T* src, void* host, int c, int k, int m) {
+        const size_t n = (size_t)N0 * N1 * c * k * m;
+        CK(staging.ensure(n));
+        dim3 grid((N0 * N1 + 31) / 32, (c * k * m + 31) / 32);
+        CK(launch(k_from_internal<T>, grid, dim3(256), 0, stream, src, staging.p, N0 * N1, c, k, m));
+        CK(cudaMemcpyAsync(host, staging.p, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+
+    int set_signal(const void* S) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        CK(cudaSetDevice(pb.device));
+        CK(tmp_real.ensure((size_t)K * C * N0 * N1));
+        int rc = to_internal(S, tmp_real.p, C, K, 1);
+        if (rc) return rc;
+        rc = forward2d(tmp_real.p, Sf.p, 1, K * C);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        have_signal = true;
+        return SPCSC_OK;
+    }
+
+    int set_weight(DevBuf<T>& buf, WeightView<T>& view, const void* w, const int64_t d[5]) {
+        const int64_t full[5] = {N0, N1, Cx, K, M};
+        size_t n = 1;
+        for (int i = 0; i < 5; ++i) {
+            if (d[i] != 1 && d[i] != full[i]) FAIL(SPCSC_ERR_INVALID, "weight shape is not broadcastable to (N0,N1,Cx,K,M)");
+            n *= (size_t)d[i];
+        }
+        CK(cudaSetDevice(pb.device));
+        CK(cudaStreamSynchronize(stream));
+        CK(buf.ensure(n));
+        CK(cudaMemcpyAsync(buf.p, w, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        long long s[5];
+        long long run = 1;
+        for (int i = 4; i >= 0; --i) {
+            s[i] = d[i] > 1 ? run : 0;
+            run *= d[i];
+        }
+        view.p = buf.p;
+        view.s0 = s[0]; view.s1 = s[1]; view.sc = s[2]; view.sk = s[3]; view.sm = s[4];
+        view.spatial_uniform = (s[0] == 0 && s[1] == 0);
+        return SPCSC_OK;
+    }
+    int set_l1_weight(const void* w, const int64_t* shape) override {
+        return set_weight(wl1_buf, wl1, w, shape);
+    }
+    int set_l21_weight(const void* w, const int64_t* shape) override {
+        const int64_t d[5] = {1, 1, 1, shape[0], shape[1]};
+        return set_weight(wl21_buf, wl21, w, d);
+    }
+
+    int admm_configure(const spcsc_admm_opts* o) override {
+        if (Cx > 4) FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 coefficient channels");
+        if (Cd > 4) FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 dictionary channels");
+        if (o->joint && Cd > 1) {
+            // Cx == 1: the l2 norm over the channel axis is |.|, handled by the same kernel
+        }
+        opts = *o;
+        prm.lmbda = (T)o->lmbda;
+        prm.mu = (T)o->mu;
+        prm.rlx = (T)o->rlx;
+        prm.tau = (T)o->ar_scaling;
+        prm.mur = (T)o->ar_rsdl_ratio;
+        prm.xi = (T)o->ar_rsdl_target;
+        prm.abs_tol = o->abs_tol;
+        prm.rel_tol = o->rel_tol;
+        prm.n_x = (double)nreal;
+        prm.inv_n = 1.0 / ((double)N0 * (double)N1);
+        prm.autorho = o->ar_enabled;
+        prm.period = o->ar_period > 0 ? o->ar_period : 1;
+        prm.autoscaling = o->ar_autoscaling;
+        prm.stdres = o->ar_std_residuals;
+        prm.need_rsdl = (o->ar_enabled || !o->fast_solve) ? 1 : 0;
+        prm.need_obj = o->fast_solve ? 0 : 1;
+        prm.joint = o->joint;
+        prm.linsolve_check = o->linsolve_check;
+        configured = true;
+        return SPCSC_OK;
+    }
+
+    int write_state(T rho, T udiv, int k, int stopped) {
+        AdmmState<T> s;
+        s.rho = rho; s.udiv = udiv; s.k = k; s.stopped = stopped;
+        CK(cudaMemcpyAsync(st.p, &s, sizeof(s), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+    int read_state(AdmmState<T>& s) {
+        CK(cudaMemcpyAsync(&s, st.p, sizeof(s), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+
+    int admm_reset(double rho) override {
+        CK(cudaSetDevice(pb.device));
+        CK(cudaMemsetAsync(Y.p, 0, nreal * sizeof(T), stream));
+        CK(cudaMemsetAsync(U.p, 0, nreal * sizeof(T), stream));
+        CK(cudaMemsetAsync(acc.p, 0, ACC_N * sizeof(double), stream));
+        have_x = false;
+        return write_state((T)rho, (T)1, 0, 0);
+    }
+    int admm_set_rho(double rho) override {
+        AdmmState<T> s;
+        int rc = read_state(s);
+        if (rc) return rc;
+        return write_state((T)rho, s.udiv, s.k, s.stopped);
+    }
+    int admm_get_scalars(double* rho, int* k) override {
+        AdmmState<T> s;
+        int rc = read_state(s);
+        if (rc) return rc;
+        if (rho) *rho = (double)s.rho;
+        if (k) *k = s.k;
+        return SPCSC_OK;
+    }
+
+    int admm_iterate(int n, spcsc_itstat* out_rows, int* n_done, int* stopped) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!have_dict || !have_signal || !configured)
+            FAIL(SPCSC_ERR_STATE, "admm_iterate before set_dict / set_signal / admm_configure");
+        if (n <= 0) FAIL(SPCSC_ERR_INVALID, "n_iter must be positive");
+        if (opts.aux_var_obj && !opts.fast_solve)
+            FAIL(SPCSC_ERR_UNSUPPORTED, "AuxVarObj objective evaluation");
+        CK(cudaSetDevice(pb.device));
+        AdmmState<T> s0;
+        int rc = read_state(s0);
+        if (rc) return rc;
+        if (s0.stopped) {
+            rc = write_state(s0.rho, s0.udiv, s0.k, 0);
+            if (rc) return rc;
+        }
+        CK(rows.ensure((size_t)n));
+        const bool check = opts.linsolve_check != 0;
+        if (check) {
+            CK(Zscratch.ensure(nslab));
+            CK(Xscratch.ensure(nslab));
+        }
+        RowArgs<T> rf = rowargs(M, K * Cx, 1);
+        RowArgs<T> rp = rowargs(M, K * Cx, Cx);
+        ProxArgs<T> pa;
+        pa.prm = prm;
+        pa.wl1 = wl1;
+        pa.wl21 = wl21;
+        pa.acc = acc.p;
+        pa.scale = (T)(1.0 / ((double)N0 * (double)N1));
+        pa.nonneg = opts.nonneg;
+        pa.bnd0 = N0;
+        pa.bnd1 = N1;
+        if (opts.no_bndry_cross) {       // Y[1-hd:, :] = 0, Y[:, 1-wd:] = 0 (a support of 1 zeroes everything)
+            pa.bnd0 = pb.hd == 1 ? 0 : N0 - (pb.hd - 1);
+            pa.bnd1 = pb.wd == 1 ? 0 : N1 - (pb.wd - 1);
+        }
+        pa.reg_on_y = opts.aux_var_obj;
+        ColLaunch<T> cs = colargs(M, K * Cx);
+        cs.st = st.p;
+        cs.acc = acc.p;
+        cs.a.dfid_on = prm.need_obj;
+        for (int it = 0; it < n; ++it) {
+            CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p));
+            if (!check) {
+                cs.in = Zt.p; cs.out = Zt.p;
+                CK(col<T>(N0, COL_ADMM, cs));
+            } else {
+                ColLaunch<T> c1 = cs;
+                c1.in = Zt.p; c1.out = Zscratch.p; c1.a.Cd = Cd;
+                CK(col<T>(N0, COL_FWD, c1));
+                ColLaunch<T> c2 = cs;
+                c2.in = Zscratch.p; c2.out = Xscratch.p;
+                CK(col<T>(N0, COL_ADMM_NOFFT, c2));
+                ColArgs ca = c2.a;
+                CK(launch(k_linsolve_check<T>, dim3(N1f, K * Cx), dim3(128), 3 * 32 * sizeof(double), stream,
+                          (const C2<T>*)Xscratch.p, (const C2<T>*)Zscratch.p, (const C2<T>*)Df.p,
+                          (const C2<T>*)Sf.p, (const AdmmState<T>*)st.p, acc.p, ca));
+                ColLaunch<T> c3 = cs;
+                c3.in = Xscratch.p; c3.out = Zt.p;
+                CK(col<T>(N0, COL_INV, c3));
+            }
+            CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p, (const AdmmState<T>*)st.p));
+            CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, s0.k, n));
+        }
+        AdmmState<T> s1;
+        rc = read_state(s1);
+        if (rc) return rc;
+        const int done = s1.k - s0.k;
+        have_x = have_x || done > 0;
+        if (out_rows && done > 0) {
+            std::vector<StatRow> hr(done);
+            CK(cudaMemcpyAsync(hr.data(), rows.p, done * sizeof(StatRow), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            for (int i = 0; i < done; ++i) {
+                spcsc_itstat& o = out_rows[i];
+                o.iter = hr[i].k; o.objfun = hr[i].obj; o.dfid = hr[i].dfid; o.regl1 = hr[i].regl1;
+                o.regl21 = hr[i].regl21; o.primal_rsdl = hr[i].r; o.dual_rsdl = hr[i].s;
+                o.eps_primal = hr[i].epri; o.eps_dual = hr[i].edua; o.rho = hr[i].rho;
+                o.xslv_relres = hr[i].xrrs; o.reserved = 0;
+            }
+        }
+        if (n_done) *n_done = done;
+        if (stopped) *stopped = s1.stopped;
+        return SPCSC_OK;
+    }
+
+    int fold_udiv() {
+        CK(launch(k_apply_udiv<T>, dim3(1184), dim3(256), 0, stream, U.p, st.p, nreal));
+        CK(launch(k_reset_udiv<T>, dim3(1), dim3(1), 0, stream, st.p));
+        return SPCSC_OK;
+    }
+
+    int freq_out(const C2<T>* src, void* host, int Cc, int Kk, int Mm) {
+        const size_t n = (size_t)N0 * N1f * Cc * Kk * Mm;
+        CK(staging.ensure(2 * n));
+        CK(launch(k_freq_to_ext<T>, dim3(1184), dim3(256), 0, stream, src,
+                  reinterpret_cast<C2<T>*>(staging.p), N0, N1f, Cc, Kk, Mm));
+        CK(cudaMemcpyAsync(host, staging.p, n * sizeof(C2<T>), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+
+    int get_array(int which, void* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        CK(cudaSetDevice(pb.device));
+        int rc;
+        switch (which) {
+            case SPCSC_ARR_Y: return from_internal(Y.p, out, Cx, K, M);
+            case SPCSC_ARR_U:
+                rc = fold_udiv();
+                if (rc) return rc;
+                return from_internal(U.p, out, Cx, K, M);
+            case SPCSC_ARR_X:
+            case SPCSC_ARR_XF: {
+                if (!have_x) FAIL(SPCSC_ERR_STATE, "X is not defined before the first iteration");
+                CK(tmp_real.ensure(nreal));
+                CK(row_inv<T>(H, rowargs(M, K * Cx, 1), (const C2<T>*)Zt.p, tmp_real.p,
+                              (T)(1.0 / ((double)N0 * (double)N1))));
+                if (which == SPCSC_ARR_X) return from_internal(tmp_real.p, out, Cx, K, M);
+                CK(Zscratch.ensure(nslab));
+                rc = forward2d(tmp_real.p, Zscratch.p, M, K * Cx);
+                if (rc) return rc;
+                return freq_out(Zscratch.p, out, Cx, K, M);
+            }
+            case SPCSC_ARR_DF:
+                if (!have_dict) FAIL(SPCSC_ERR_STATE, "no dictionary set");
+                return freq_out(Df.p, out, Cd, 1, M);
+            case SPCSC_ARR_SF:
+                if (!have_signal) FAIL(SPCSC_ERR_STATE, "no signal set");
+                return freq_out(Sf.p, out, C, K, 1);
+        }
+        FAIL(SPCSC_ERR_INVALID, "unknown array id");
+    }
+
+    int set_array(int which, const void* in) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        CK(cudaSetDevice(pb.device));
+        int rc;
+        if (which == SPCSC_ARR_Y) {
+            rc = to_internal(in, Y.p, Cx, K, M);
+        } else if (which == SPCSC_ARR_U) {
+            rc = to_internal(in, U.p, Cx, K, M);
+            if (rc) return rc;
+            CK(launch(k_reset_udiv<T>, dim3(1), dim3(1), 0, stream, st.p));
+        } else {
+            FAIL(SPCSC_ERR_INVALID, "only Y and U can be set");
+        }
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+
+    int reconstruct(const void* X, void* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!have_dict) FAIL(SPCSC_ERR_STATE, "no dictionary set");
+        CK(cudaSetDevice(pb.device));
+        size_t need = nreal > (size_t)K * C * N0 * N1 ? nreal : (size_t)K * C * N0 * N1;
+        CK(tmp_real.ensure(need));
+        const T* src = Y.p;
+        if (X) {
+            int rc = to_internal(X, tmp_real.p, Cx, K, M);
+            if (rc) return rc;
+            src = tmp_real.p;
+        }
+        CK(Zscratch.ensure(nslab));
+        CK(sum_buf.ensure((size_t)K * C * N1f * N0));
+        CK(row_fwd<T>(H, rowargs(M, K * Cx, 1), src, (const T*)nullptr, (const AdmmState<T>*)nullptr,
+                      Zscratch.p));
+        ColLaunch<T> c = colargs(M, K * Cx);
+        c.in = Zscratch.p; c.out = nullptr; c.sumout = sum_buf.p;
+        CK(col<T>(N0, COL_FWD_SUM, c));
+        // sum_buf is [K*Cx][Cd][N1f][N0] == [K][C][N1f][1][N0]: slabs with one column each
+        ColLaunch<T> ci = colargs(1, K * C);
+        ci.in = sum_buf.p; ci.out = sum_buf.p; ci.a.Cd = 1;
+        CK(col<T>(N0, COL_INV, ci));
+        T* rec = tmp_real.p;       // stream order: the forward pass has consumed tmp_real by now
+        CK(row_inv<T>(H, rowargs(1, K * C, 1), (const C2<T>*)sum_buf.p, rec,
+                      (T)(1.0 / ((double)N0 * (double)N1))));
+        return from_internal(rec, out, C, K, 1);
+    }
+
+    int synchronize() override {
+        CK(cudaSetDevice(pb.device));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+};
+
+int check_problem(const spcsc_problem* p, std::string& err) {
+    if (!p) { err = "null problem"; return SPCSC_ERR_INVALID; }
+    if (p->dtype != SPCSC_F32 && p->dtype != SPCSC_F64) { err = "dtype must be SPCSC_F32 or SPCSC_F64"; return SPCSC_ERR_INVALID; }
+    if (p->N0 < 1 || p->N1 < 1 || p->C < 1 || p->Cd < 1 || p->K < 1 || p->M < 1 || p->hd < 1 || p->wd < 1) {
+        err = "non-positive dimension"; return SPCSC_ERR_INVALID;
+    }
+    if (p->Cd > 1 && p->Cd != p->C) { err = "multi-channel dictionary needs C == Cd"; return SPCSC_ERR_INVALID; }
+    if (p->hd > p->N0 || p->wd > p->N1) { err = "filter support larger than the signal"; return SPCSC_ERR_INVALID; }
+    if (!supported_len(p->N0) || !supported_len(p->N1 / 2) || (p->N1 & 1)) {
+        err = "unsupported spatial size: N0 must be a power of two in [2,1024], N1 in [4,2048]";
+        return SPCSC_ERR_UNSUPPORTED;
+    }
+    return SPCSC_OK;
+}
+
+template <typename T>
+int unit_fft2(bool inverse, int device, int batch, int N0, int N1, const void* in, void* out,
+              std::string& err) {
+    spcsc_problem p;
+    memset(&p, 0, sizeof(p));
+    p.N0 = N0; p.N1 = N1; p.C = 1; p.Cd = 1; p.K = batch; p.M = 1; p.hd = 1; p.wd = 1;
+    p.dtype = sizeof(T) == 4 ? SPCSC_F32 : SPCSC_F64;
+    p.device = device;
+    int rc = check_problem(&p, err);
+    if (rc) return rc;
+    Engine<T> e(p);
+    rc = e.init();
+    if (rc) { err = e.err; return rc; }
+    const int N1f = N1 / 2 + 1;
+    const size_t nr = (size_t)batch * N0 * N1, nc = (size_t)batch * N0 * N1f;
+    bool poisoned = false;
+    DevBuf<C2<T>> sw;
+    cudaError_t ce = sw.ensure(nc);
+    if (ce != cudaSuccess) { err = cudaGetErrorString(ce); return SPCSC_ERR_NOMEM; }
+#define UCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); sw.release(); (void)poisoned; return SPCSC_ERR_CUDA; } } while (0)
+    if (!inverse) {
+        UCK(e.tmp_real.ensure(nr));
+        UCK(cudaMemcpyAsync(e.tmp_real.p, in, nr * sizeof(T), cudaMemcpyHostToDevice, e.stream));
+        rc = e.forward2d(e.tmp_real.p, e.Zt.p, 1, batch);
+        if (rc) { err = e.err; sw.release(); return rc; }
+        // [batch][N1f][N0] -> [batch][N0][N1f]
+        UCK(launch(k_swap_last2<T>, dim3(256, batch), dim3(256), 0, e.stream, (const C2<T>*)e.Zt.p, sw.p, N1f, N0));
+        UCK(cudaMemcpyAsync(out, sw.p, nc * sizeof(C2<T>), cudaMemcpyDeviceToHost, e.stream));
+        UCK(cudaStreamSynchronize(e.stream));
+    } else {
+        UCK(cudaMemcpyAsync(sw.p, in, nc * sizeof(C2<T>), cudaMemcpyHostToDevice, e.stream));
+        UCK(launch(k_swap_last2<T>, dim3(256, batch), dim3(256), 0, e.stream, (const C2<T>*)sw.p, e.Zt.p, N0, N1f));
+        ColLaunch<T> c = e.colargs(1, batch);
+        c.in = e.Zt.p; c.out = e.Zt.p; c.a.Cd = 1;
+        UCK(col<T>(N0, COL_INV, c));
+        UCK(e.tmp_real.ensure(nr));
+        UCK(row_inv<T>(N1 / 2, e.rowargs(1, batch, 1), (const C2<T>*)e.Zt.p, e.tmp_real.p,
+                       (T)(1.0 / ((double)N0 * (double)N1))));
+        UCK(cudaMemcpyAsync(out, e.tmp_real.p, nr * sizeof(T), cudaMemcpyDeviceToHost, e.stream));
+        UCK(cudaStreamSynchronize(e.stream));
+    }
+#undef UCK
+    sw.release();
+    return SPCSC_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int spcsc_version(void) { return 100; }
+
+int spcsc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int spcsc_device_name(int device, char* buf, int buflen) {
+    if (!buf || buflen <= 0) return SPCSC_ERR_INVALID;
+#ifdef SPCSC_EMU
+    snprintf(buf, buflen, "spcsc CPU emulation (test only)");
+    (void)device;
+    return SPCSC_OK;
+#else
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return SPCSC_ERR_CUDA; }
+    snprintf(buf, buflen, "%s", prop.name);
+    return SPCSC_OK;
+#endif
+}
+
+int spcsc_memory_info(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
+    size_t f = 0, t = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) {
+        g_last_error = "cudaMemGetInfo failed";
+        return SPCSC_ERR_CUDA;
+    }
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return SPCSC_OK;
+}
+
+const char* spcsc_last_error(const spcsc_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int spcsc_create(const spcsc_problem* prob, spcsc_handle** out) {
+    if (!out) { g_last_error = "null output pointer"; return SPCSC_ERR_INVALID; }
+    *out = nullptr;
+    int rc = check_problem(prob, g_last_error);
+    if (rc) return rc;
+    int ndev = spcsc_device_count();
+    if (ndev <= 0) { g_last_error = "no CUDA device available"; return SPCSC_ERR_CUDA; }
+    if (prob->device < 0 || prob->device >= ndev) { g_last_error = "device ordinal out of range"; return SPCSC_ERR_INVALID; }
+    spcsc_handle* h = nullptr;
+    int irc;
+    if (prob->dtype == SPCSC_F32) {
+        Engine<float>* e = new (std::nothrow) Engine<float>(*prob);
+        if (!e) { g_last_error = "out of host memory"; return SPCSC_ERR_NOMEM; }
+        irc = e->init();
+        h = e;
+    } else {
+        Engine<double>* e = new (std::nothrow) Engine<double>(*prob);
+        if (!e) { g_last_error = "out of host memory"; return SPCSC_ERR_NOMEM; }
+        irc = e->init();
+        h = e;
+    }
+    if (irc) {
+        g_last_error = h->err;
+        delete h;
+        return irc;
+    }
+    *out = h;
+    return SPCSC_OK;
+}
+
+int spcsc_destroy(spcsc_handle* h) {
+    delete h;
+    return SPCSC_OK;
+}
+
+#define H_CALL(expr)                                                   \
+    if (!h) { g_last_error = "null handle"; return SPCSC_ERR_INVALID; } \
+    return (expr)
+
+int spcsc_synchronize(spcsc_handle* h) { H_CALL(h->synchronize()); }
+int spcsc_set_dict(spcsc_handle* h, const void* D) { H_CALL(D ? h->set_dict(D) : SPCSC_ERR_INVALID); }
+int spcsc_set_signal(spcsc_handle* h, const void* S) { H_CALL(S ? h->set_signal(S) : SPCSC_ERR_INVALID); }
+int spcsc_set_l1_weight(spcsc_handle* h, const void* w, const int64_t shape[5]) {
+    H_CALL((w && shape) ? h->set_l1_weight(w, shape) : SPCSC_ERR_INVALID);
+}
+int spcsc_set_l21_weight(spcsc_handle* h, const void* w, const int64_t shape[2]) {
+    H_CALL((w && shape) ? h->set_l21_weight(w, shape) : SPCSC_ERR_INVALID);
+}
+int spcsc_admm_configure(spcsc_handle* h, const spcsc_admm_opts* o) {
+    H_CALL(o ? h->admm_configure(o) : SPCSC_ERR_INVALID);
+}
+int spcsc_admm_reset(spcsc_handle* h, double rho) { H_CALL(h->admm_reset(rho)); }
+int spcsc_admm_set_rho(spcsc_handle* h, double rho) { H_CALL(h->admm_set_rho(rho)); }
+int spcsc_admm_iterate(spcsc_handle* h, int32_t n_iter, spcsc_itstat* rows, int32_t* n_done,
+                       int32_t* stopped) {
+    H_CALL(h->admm_iterate(n_iter, rows, n_done, stopped));
+}
+int spcsc_admm_get_scalars(spcsc_handle* h, double* rho, int32_t* k) {
+    H_CALL(h->admm_get_scalars(rho, k));
+}
+int spcsc_get_array(spcsc_handle* h, int32_t which, void* out) {
+    H_CALL(out ? h->get_array(which, out) : SPCSC_ERR_INVALID);
+}
+int spcsc_set_array(spcsc_handle* h, int32_t which, const void* in) {
+    H_CALL(in ? h->set_array(which, in) : SPCSC_ERR_INVALID);
+}
+int spcsc_reconstruct(spcsc_handle* h, const void* X, void* out) {
+    H_CALL(out ? h->reconstruct(X, out) : SPCSC_ERR_INVALID);
+}
+
+int spcsc_rfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1, const void* x,
+                void* xf) {
+    if (!x || !xf || batch < 1) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
+    return dtype == SPCSC_F32 ? unit_fft2<float>(false, device, batch, N0, N1, x, xf, g_last_error)
+                              : unit_fft2<double>(false, device, batch, N0, N1, x, xf, g_last_error);
+}
+int spcsc_irfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1, const void* xf,
+                 void* x) {
+    if (!x || !xf || batch < 1) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
+    return dtype == SPCSC_F32 ? unit_fft2<float>(true, device, batch, N0, N1, xf, x, g_last_error)
+                              : unit_fft2<double>(true, device, batch, N0, N1, xf, x, g_last_error);
+}
+
+}  // extern "C"
