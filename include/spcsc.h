@@ -111,6 +111,8 @@ int spcsc_admm_configure(spcsc_handle* h, const spcsc_admm_opts* opts);
 /* Y = U = 0 (or later set_array), k = 0, rho as given.              admm/admm.py:243-275 */
 int spcsc_admm_reset(spcsc_handle* h, double rho);
 int spcsc_admm_set_rho(spcsc_handle* h, double rho);
+/* Set the iteration counter (restoring a pickled solver; admm/admm.py:331 resumes from self.k). */
+int spcsc_admm_set_iter(spcsc_handle* h, int32_t k);
 /* Run up to n_iter iterations of admm/admm.py:331-377 on the device.  Stops early (device
    side, no host round trip) once r < epri and s < edua.  `rows` (n_iter entries, may be NULL)
    receives one spcsc_itstat per executed iteration.  Clears a previous stop flag on entry,

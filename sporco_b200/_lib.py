@@ -20,7 +20,8 @@ SYMBOLS = (
     'spcsc_version', 'spcsc_device_count', 'spcsc_device_name', 'spcsc_memory_info',
     'spcsc_last_error', 'spcsc_create', 'spcsc_destroy', 'spcsc_synchronize',
     'spcsc_set_dict', 'spcsc_set_signal', 'spcsc_set_l1_weight', 'spcsc_set_l21_weight',
-    'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_iterate',
+    'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_set_iter',
+    'spcsc_admm_iterate',
     'spcsc_admm_get_scalars', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
     'spcsc_rfft2', 'spcsc_irfft2',
 )
@@ -76,6 +77,7 @@ def _declare(lib):
     lib.spcsc_admm_configure.argtypes = [vp, ctypes.POINTER(AdmmOpts)]
     lib.spcsc_admm_reset.argtypes = [vp, ctypes.c_double]
     lib.spcsc_admm_set_rho.argtypes = [vp, ctypes.c_double]
+    lib.spcsc_admm_set_iter.argtypes = [vp, i32]
     lib.spcsc_admm_iterate.argtypes = [vp, i32, ctypes.POINTER(ItStat), ctypes.POINTER(i32),
                                        ctypes.POINTER(i32)]
     lib.spcsc_admm_get_scalars.argtypes = [vp, ctypes.POINTER(ctypes.c_double),

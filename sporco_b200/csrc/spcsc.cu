@@ -110,6 +110,7 @@ struct spcsc_handle {
     virtual int admm_configure(const spcsc_admm_opts* o) = 0;
     virtual int admm_reset(double rho) = 0;
     virtual int admm_set_rho(double rho) = 0;
+    virtual int admm_set_iter(int k) = 0;
     virtual int admm_iterate(int n, spcsc_itstat* rows, int* n_done, int* stopped) = 0;
     virtual int admm_get_scalars(double* rho, int* k) = 0;
     virtual int get_array(int which, void* out) = 0;
@@ -398,6 +399,13 @@ class Engine : public spcsc_handle {
         int rc = read_state(s);
         if (rc) return rc;
         return write_state((T)rho, s.udiv, s.k, s.stopped);
+    }
+    int admm_set_iter(int k) override {
+        AdmmState<T> s;
+        int rc = read_state(s);
+        if (rc) return rc;
+        if (k > 0) have_x = false;
+        return write_state(s.rho, s.udiv, k, s.stopped);
     }
     int admm_get_scalars(double* rho, int* k) override {
         AdmmState<T> s;
@@ -751,6 +759,7 @@ int spcsc_admm_configure(spcsc_handle* h, const spcsc_admm_opts* o) {
 }
 int spcsc_admm_reset(spcsc_handle* h, double rho) { H_CALL(h->admm_reset(rho)); }
 int spcsc_admm_set_rho(spcsc_handle* h, double rho) { H_CALL(h->admm_set_rho(rho)); }
+int spcsc_admm_set_iter(spcsc_handle* h, int32_t k) { H_CALL(k >= 0 ? h->admm_set_iter(k) : SPCSC_ERR_INVALID); }
 int spcsc_admm_iterate(spcsc_handle* h, int32_t n_iter, spcsc_itstat* rows, int32_t* n_done,
                        int32_t* stopped) {
     H_CALL(h->admm_iterate(n_iter, rows, n_done, stopped));
