@@ -120,6 +120,13 @@ int spcsc_admm_set_iter(spcsc_handle* h, int32_t k);
 int spcsc_admm_iterate(spcsc_handle* h, int32_t n_iter, spcsc_itstat* rows, int32_t* n_done,
                        int32_t* stopped);
 int spcsc_admm_get_scalars(spcsc_handle* h, double* rho, int32_t* k);
+/* Device time (CUDA events on the handle's stream) of the kernels launched by the most recent
+   spcsc_admm_iterate call, in milliseconds, and the number of kernel launches it made. */
+int spcsc_admm_last_timing(spcsc_handle* h, float* elapsed_ms, int64_t* launches);
+/* Run n_iter iterations with a CUDA event between consecutive kernels and return the summed
+   device time per kernel, ms: [0] k_row_fwd, [1] k_col, [2] k_row_inv_prox, [3] k_admm_scalars.
+   Measurement aid for bench.py (same kernels, same stream as spcsc_admm_iterate). */
+int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]);
 
 /* ---- state access */
 int spcsc_get_array(spcsc_handle* h, int32_t which, void* host_out);

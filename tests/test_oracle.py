@@ -1,0 +1,83 @@
+"""The oracle against its pins: the committed golden vectors (any box) and the live
+reference (only where /root/reference exists, i.e. the build container)."""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import cbpdn_oracle as orc
+from tests import cases
+
+REF = '/root/reference'
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.ADMM_CASES))
+def test_oracle_reproduces_golden_admm(tag, sfx):
+    g = cases.load('%s_%s' % (tag, sfx))
+    opt, dimK, joint, _ = cases.ADMM_CASES[tag]
+    r = orc.admm_convbpdn(g['D'], g['S'], float(g['lmbda']),
+                          mu=float(g['mu']) if joint else None, opt=opt, dimK=dimK)
+    assert np.array_equal(r.Y, g['Y'])
+    assert np.array_equal(r.U, g['U'])
+    assert np.array_equal(r.X, g['X'])
+    rho_col = 9 if joint else 8
+    assert np.array_equal(np.array([row[rho_col] for row in r.itstat], dtype=np.float64), g['Rho'])
+    assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+def test_oracle_reproduces_golden_pgm(sfx):
+    g = cases.load('pgm_bt_' + sfx)
+    r = orc.pgm_convbpdn(g['D'], g['S'], float(g['lmbda']), dimK=1,
+                         opt={'MaxMainIter': 25, 'RelStopTol': 0.0, 'L': 10.0,
+                              'Backtrack': {'gamma_u': 1.3, 'maxiter': 8}})
+    assert np.array_equal(r.X, g['X'])
+    assert np.array_equal(np.array([row[8] for row in r.itstat], dtype=np.float64), g['L'])
+    assert np.array_equal(np.array([row[7] for row in r.itstat], dtype=np.float64), g['IterBTrack'])
+    g = cases.load('pgm_fixed_' + sfx)
+    r = orc.pgm_convbpdn(g['D'], g['S'], float(g['lmbda']), dimK=1,
+                         opt={'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0})
+    assert np.array_equal(r.X, g['X'])
+    assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
+
+
+def test_oracle_level1_known_answers():
+    g = cases.load('level1')
+    assert np.array_equal(orc.solvedbi_sm(g['ah'], 0.7, g['b'], 4), g['x'])
+    assert np.array_equal(orc.solvemdbi_ism(g['ah3'], 0.7, g['b3'], 4, 2), g['x3'])
+    assert np.array_equal(orc.prox_l1(g['v'], 0.4), g['prox_l1'])
+    assert np.array_equal(orc.prox_sl1l2(g['v'], 0.3, 0.25, axis=2), g['prox_sl1l2'])
+    assert orc.rfl2norm2(g['xf'], g['xr'].shape, axis=(0, 1)) == float(g['rfl2norm2'])
+    # algebraic pins used by the reference's own tests (tests/test_linalg.py:147-207)
+    a = np.conj(g['ah'])
+    lhs = a * orc.inner(g['ah'], g['x'], 4) + 0.7 * g['x']
+    assert orc.rrs(lhs, g['b']) < 1e-11
+
+
+def test_oracle_sharded_norms_match_unsharded():
+    """K-sharding with summed squared norms follows the single-object rho schedule."""
+    g = cases.load('admm_k3_f64')
+    opt = {'MaxMainIter': 12, 'RelStopTol': 0.0}
+    full = orc.admm_convbpdn(g['D'], g['S'], 0.1, opt=opt, dimK=1, norm_reduce=lambda v: v)
+    ref = orc.admm_convbpdn(g['D'], g['S'], 0.1, opt=opt, dimK=1)
+    assert cases.rel(full.Y, ref.Y) < 1e-10
+    assert cases.rel([r[8] for r in full.itstat], [r[8] for r in ref.itstat]) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present on this box')
+def test_oracle_matches_live_reference():
+    sys.path[:0] = [os.path.join(os.path.dirname(orc.__file__), 'shims'), REF]
+    warnings.filterwarnings('ignore')
+    from sporco.admm import cbpdn as rcbpdn
+    rng = np.random.default_rng(99)
+    D = rng.standard_normal((4, 4, 5)).astype(np.float32)
+    S = rng.standard_normal((16, 16, 2)).astype(np.float32)
+    opt = {'MaxMainIter': 15, 'RelStopTol': 0.0, 'L1Weight': np.linspace(0.5, 1.5, 5).astype(np.float32).reshape(1, 1, 1, 5)}
+    b = rcbpdn.ConvBPDN(D, S, 0.05, rcbpdn.ConvBPDN.Options(opt), dimK=1)
+    b.solve()
+    r = orc.admm_convbpdn(D, S, 0.05, opt=opt, dimK=1)
+    assert np.array_equal(b.Y, r.Y) and np.array_equal(b.U, r.U)
