@@ -347,7 +347,7 @@ SPCSC_DEV void col_fft_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT tw, int mc,
 }
 
 template <typename T, int N0, bool DO_FWD, int SOLVE, bool DO_INV>
-SPCSC_GLOBAL void k_col(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out,
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out,
                         const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
                         const C2<T>* SPCSC_RESTRICT G, C2<T>* SPCSC_RESTRICT sumout,
                         const AdmmState<T>* SPCSC_RESTRICT st, T Lstep,
