@@ -180,4 +180,121 @@ SPCSC_DEV void fft_smem(C2<T>* buf, int t, const C2<T>* SPCSC_RESTRICT tw, bool 
 template <typename T, int N>
 constexpr int fft_tpf() { return N / fft_elems<T>(N); }
 
+
+// =====================================================================================
+// Register-resident transform (kernel set v2).
+//
+// A length-N transform is done by TPF = N/E lanes of ONE warp (TPF <= 32), each holding E
+// elements in registers in the "strided" layout: slot p <-> element t + TPF*p.  The first
+// stage (radix E) works straight on the registers; later stages exchange data through a
+// per-transform shared-memory region of N elements with an XOR swizzle (conflict-free for
+// the radix-16 x 16 plan, at most 2-way otherwise) and only warp-level barriers.  Input and
+// output use the same strided layout, so forward -> pointwise -> inverse needs no shuffling.
+// Stage twiddles come from a small table laid out [r][k] per stage (consecutive lanes read
+// consecutive entries); make_stage_twiddles() on the host builds it with the same plan.
+// =====================================================================================
+SPCSC_HD int fft_swz(int i) { return i ^ ((i >> 4) & 15); }
+
+// total number of stage-twiddle entries of the (N, E) plan
+constexpr int stage_tw_len(int N, int E) {
+    int len = 0;
+    int Ns = (E < N ? E : N);
+    while (Ns < N) {
+        int R = (N / Ns >= E) ? E : N / Ns;
+        len += R * Ns;
+        Ns *= R;
+    }
+    return len;
+}
+
+template <typename T, int N, int E, bool INV, int Ns, int TWOFF>
+struct RegStage {
+    static constexpr int REM = N / Ns;
+    static constexpr int R = REM >= E ? E : REM;
+    static constexpr int NB = E / R;
+    static constexpr int TPF = N / E;
+    static constexpr bool LAST = (Ns * R >= N);
+
+    // v: E registers.  Ns == 1: strided input layout.  On return from the last stage v is
+    // again in strided layout (slot p <-> X[t + TPF*p]).
+    static SPCSC_DEV void run(C2<T>* v, C2<T>* buf, const C2<T>* SPCSC_RESTRICT stw, int t) {
+        if (Ns > 1) {
+            SPCSC_UNROLL
+            for (int i = 0; i < NB; ++i) {
+                const int j = t + i * TPF;
+                const int k = j & (Ns - 1);
+                SPCSC_UNROLL
+                for (int r = 0; r < R; ++r) {
+                    C2<T> x = buf[fft_swz(j + r * (N / R))];
+                    if (r > 0) {
+                        const C2<T> w = stw[TWOFF + r * Ns + k];
+                        x = INV ? mulc(x, w) : x * w;
+                    }
+                    v[i * R + r] = x;
+                }
+            }
+        }
+        SPCSC_UNROLL
+        for (int i = 0; i < NB; ++i) SmallDFT<T, R, INV>::run(v + i * R);
+        if constexpr (!LAST) {
+            if (Ns > 1) __syncwarp();          // everyone has read before anyone overwrites
+            SPCSC_UNROLL
+            for (int i = 0; i < NB; ++i) {
+                const int j = t + i * TPF;
+                const int k = j & (Ns - 1);
+                const int j0 = (j - k) * R + k;
+                SPCSC_UNROLL
+                for (int r = 0; r < R; ++r) buf[fft_swz(j0 + r * Ns)] = v[i * R + r];
+            }
+            __syncwarp();
+            RegStage<T, N, E, INV, Ns * R, TWOFF + (Ns > 1 ? R * Ns : 0)>::run(v, buf, stw, t);
+        } else {
+            // slot i*R + r holds X[t + TPF*(i + NB*r)]: rename registers into strided order
+            if (NB > 1) {
+                C2<T> o[E];
+                SPCSC_UNROLL
+                for (int i = 0; i < NB; ++i) {
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) o[i + NB * r] = v[i * R + r];
+                }
+                SPCSC_UNROLL
+                for (int p = 0; p < E; ++p) v[p] = o[p];
+            }
+        }
+    }
+};
+
+// v in strided layout -> transform -> v in strided layout.  `buf`: this transform's N-element
+// shared-memory region; `stw`: stage twiddle table of the (N, E) plan (forward sign).
+// All lanes of the warp must call it together.
+template <typename T, int N, int E, bool INV>
+SPCSC_DEV void fft_regs(C2<T>* v, C2<T>* buf, const C2<T>* SPCSC_RESTRICT stw, int t) {
+    static_assert(E <= N && (N / E) <= 32, "plan must fit in one warp");
+    RegStage<T, N, E, INV, 1, 0>::run(v, buf, stw, t);
+}
+
 }  // namespace spcsc
+
+#ifndef SPCSC_FFT_HOST_ONLY
+#include <vector>
+namespace spcsc {
+// Host: stage twiddle table of the (N, E) plan, forward sign, layout per stage [r][k].
+template <typename T>
+inline std::vector<C2<T>> make_stage_twiddles(int N, int E) {
+    std::vector<C2<T>> tab;
+    const double two_pi = 6.283185307179586476925286766559;
+    int Ns = (E < N ? E : N);
+    while (Ns < N) {
+        const int R = (N / Ns >= E) ? E : N / Ns;
+        for (int r = 0; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                const double a = -two_pi * (double)(r * k) / (double)(Ns * R);
+                tab.push_back(mk<T>((T)std::cos(a), (T)std::sin(a)));
+            }
+        Ns *= R;
+    }
+    if (tab.empty()) tab.push_back(mk<T>(1, 0));
+    return tab;
+}
+}  // namespace spcsc
+#endif

@@ -1,0 +1,353 @@
+// kernels2.cuh -- kernel set v2 for the ADMM iteration (single-channel dictionary, power-of-two
+// sizes that fit the one-warp register plans).  Same arithmetic as kernels.cuh, restructured
+// around what the v1 profile showed (profiles/r01_v1_ncu_summary.md):
+//   * transforms live in registers (fft_regs): first stage straight from global memory, later
+//     stages through a swizzled per-transform shared-memory region with warp-level barriers only;
+//   * the column kernel splits the M columns of a slab over a thread-block CLUSTER; each CTA keeps
+//     its columns' spectra in registers between the forward transform, the Sherman-Morrison
+//     update and the inverse transform; the per-frequency sums over M are combined through
+//     distributed shared memory.  Small CTAs (~40 KB smem) let several be resident per SM, so
+//     loads, transforms and stores of different slabs overlap without a hand-written pipeline;
+//   * per-thread float partial sums, no integer divisions by run-time values, U/udiv as a
+//     multiplication by a reciprocal that is exactly 1 when rho did not change.
+// kernels.cuh stays the general path (any supported size, Cd > 1, double) and the set-up path.
+#pragma once
+
+#include "kernels.cuh"
+
+#ifdef SPCSC_EMU
+#define SPCSC_LAUNCH_BOUNDS2(t, b)
+#else
+#define SPCSC_LAUNCH_BOUNDS2(t, b) __launch_bounds__(t, b)
+#endif
+
+namespace spcsc {
+
+// ------------------------------------------------------------------------------------
+// k_row_fwd2: TR = NT/TPF rows of one (b, m) per CTA; each row by TPF = H/E lanes.
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int E, int NT>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
+k_row_fwd2(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
+           const AdmmState<T>* SPCSC_RESTRICT st, C2<T>* SPCSC_RESTRICT Zt,
+           const C2<T>* SPCSC_RESTRICT tw, const C2<T>* SPCSC_RESTRICT stw, int N0, int M) {
+    if (st && st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
+    constexpr int TWLEN = stage_tw_len(H, E);
+    C2<T>* reg = reinterpret_cast<C2<T>*>(smem_raw);          // [TR][P]
+    C2<T>* stw_s = reg + TR * P;                               // [TWLEN]
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
+    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
+    const int g = tid / TPF, t = tid % TPF;
+    T uinv = 1;
+    if (st && B) {
+        const T ud = st->udiv;
+        if (ud != (T)1) uinv = (T)1 / ud;
+    }
+    const size_t rowbase = ((((size_t)b * M + m) * N0 + h0 + g) * H);
+    const C2<T>* A2 = reinterpret_cast<const C2<T>*>(A) + rowbase;
+    C2<T> v[E];
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) v[p] = A2[t + TPF * p];
+    if (B) {
+        const C2<T>* B2 = reinterpret_cast<const C2<T>*>(B) + rowbase;
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) {
+            const C2<T> u = B2[t + TPF * p];
+            v[p].re -= u.re * uinv;
+            v[p].im -= u.im * uinv;
+        }
+    }
+    __syncthreads();                                         // stage twiddles are in place
+    fft_regs<T, H, E, false>(v, reg + g * P, stw_s, t);
+    __syncwarp();
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) reg[g * P + t + TPF * p] = v[p];
+    __syncthreads();
+    C2<T>* out = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
+    const size_t wstride = (size_t)M * N0;
+    for (int e = tid; e < TR * N1f; e += NT) {
+        const int wf = e / TR, r = e % TR;
+        const C2<T> a = reg[r * P + (wf == H ? 0 : wf)];
+        const C2<T> bb = conj(reg[r * P + (wf == 0 ? 0 : H - wf)]);
+        const C2<T> w = tw[wf];
+        const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
+        out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_row_inv_prox2: inverse row transform + relaxation + prox + dual update + residual sums.
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int E, int CX, int NT>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (CX == 1 ? 2 : 1))
+k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RESTRICT U,
+                const AdmmState<T>* SPCSC_RESTRICT st, AdmmParams<T> prm, WeightView<T> wl1,
+                WeightView<T> wl21, double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
+                const C2<T>* SPCSC_RESTRICT stw, int N0, int M, T scale, int nonneg, int bnd0,
+                int bnd1, int reg_on_y) {
+    if (st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
+    constexpr int TWLEN = stage_tw_len(H, E);
+    C2<T>* reg = reinterpret_cast<C2<T>*>(smem_raw);          // [CX][TR][P]
+    C2<T>* stw_s = reg + CX * TR * P;
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
+    const size_t wstride = (size_t)M * N0;
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c) {
+        const C2<T>* in = Zt + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0;
+        for (int e = tid; e < TR * N1f; e += NT) {
+            const int wf = e / TR, r = e % TR;
+            reg[(c * TR + r) * P + wf] = in[wf * wstride + r];
+        }
+    }
+    __syncthreads();
+    const int g = tid / TPF, t = tid % TPF;
+    const int h = h0 + g;
+    C2<T> v[CX][E];
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c) {
+        C2<T>* row = reg + (c * TR + g) * P;
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) {
+            const int kk = t + TPF * p;
+            if (kk == 0) {
+                const T a = row[0].re, cc = row[H].re;       // c2r ignores the imaginary parts
+                v[c][p] = mk<T>(a + cc, a - cc);
+            } else {
+                const C2<T> Xa = row[kk], Xb = row[H - kk];
+                const C2<T> w = tw[kk];
+                const C2<T> s1 = Xa + conj(Xb), d1 = Xa - conj(Xb);
+                v[c][p] = s1 + mul_i(mulc(d1, w));
+            }
+        }
+        __syncwarp();
+        fft_regs<T, H, E, true>(v[c], row, stw_s, t);
+    }
+
+    const T rho = st->rho;
+    T uinv = 1;
+    {
+        const T ud = st->udiv;
+        if (ud != (T)1) uinv = (T)1 / ud;
+    }
+    const T lr = prm.lmbda / rho;
+    const T mr = prm.joint ? prm.mu / rho : (T)0;
+    const T rlx = prm.rlx;
+    const bool relax = rlx != (T)1;
+    const T rl1 = (T)1 - rlx;
+    T sums[7] = {0, 0, 0, 0, 0, 0, 0};
+    T w1u[CX];
+    const size_t wbase = (size_t)k * wl1.sk + (size_t)m * wl1.sm + (size_t)h * wl1.s0;
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c) w1u[c] = wl1.p[(size_t)k * wl1.sk + (size_t)c * wl1.sc + (size_t)m * wl1.sm];
+    const size_t w21base = (size_t)k * wl21.sk + (size_t)m * wl21.sm + (size_t)h * wl21.s0;
+
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) {
+        const int j = t + TPF * p;
+        T wv[CX][2], ax[CX][2], ue[CX][2], yp[CX][2];
+        T a2[2] = {0, 0}, g2[2] = {0, 0};
+        SPCSC_UNROLL
+        for (int c = 0; c < CX; ++c) {
+            const size_t off = ((((size_t)(k * CX + c) * M + m) * N0 + h) * H + j);
+            const C2<T> y2 = reinterpret_cast<const C2<T>*>(Y)[off];
+            const C2<T> u2 = reinterpret_cast<const C2<T>*>(U)[off];
+            const T xs[2] = {v[c][p].re * scale, v[c][p].im * scale};
+            const T ys[2] = {y2.re, y2.im};
+            const T us[2] = {u2.re * uinv, u2.im * uinv};
+            v[c][p] = mk<T>(xs[0], xs[1]);
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                const T w1 = wl1.spatial_uniform
+                                 ? w1u[c]
+                                 : wl1.p[wbase + (size_t)c * wl1.sc + (size_t)(2 * j + q) * wl1.s1];
+                const T axv = relax ? rlx * xs[q] + rl1 * ys[q] : xs[q];
+                const T vv = axv + us[q];
+                const T w = soft_threshold(vv, lr * w1);
+                yp[c][q] = ys[q];
+                ax[c][q] = axv;
+                ue[c][q] = us[q];
+                wv[c][q] = w;
+                a2[q] += w * w;
+                if (!reg_on_y) {
+                    sums[ACC_L1] += fabs(w1 * xs[q]);
+                    g2[q] += xs[q] * xs[q];
+                }
+            }
+        }
+        T fac[2] = {1, 1}, w21[2] = {1, 1};
+        if (prm.joint) {
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                w21[q] = wl21.p[w21base + (size_t)(2 * j + q) * wl21.s1];
+                const T a = sqrt(a2[q]);
+                const T bq = fmax((T)0, a - mr * w21[q]);
+                fac[q] = (a != (T)0) ? bq / a : (T)0;
+            }
+        }
+        SPCSC_UNROLL
+        for (int c = 0; c < CX; ++c) {
+            const size_t off = ((((size_t)(k * CX + c) * M + m) * N0 + h) * H + j);
+            T yn[2], un[2];
+            const T xs[2] = {v[c][p].re, v[c][p].im};
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                T y = prm.joint ? fac[q] * wv[c][q] : wv[c][q];
+                if (nonneg && y < (T)0) y = (T)0;
+                if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+                const T u = ue[c][q] + (ax[c][q] - y);
+                yn[q] = y;
+                un[q] = u;
+                const T x = xs[q];
+                const T dr = x - y, ds = yp[c][q] - y;
+                sums[ACC_X2] += x * x;
+                sums[ACC_Y2] += y * y;
+                sums[ACC_U2] += u * u;
+                sums[ACC_R2] += dr * dr;
+                sums[ACC_S2] += ds * ds;
+                if (reg_on_y) {
+                    const T w1 = wl1.spatial_uniform
+                                     ? w1u[c]
+                                     : wl1.p[wbase + (size_t)c * wl1.sc + (size_t)(2 * j + q) * wl1.s1];
+                    sums[ACC_L1] += fabs(w1 * y);
+                    g2[q] += y * y;
+                }
+            }
+            reinterpret_cast<C2<T>*>(Y)[off] = mk<T>(yn[0], yn[1]);
+            reinterpret_cast<C2<T>*>(U)[off] = mk<T>(un[0], un[1]);
+        }
+        if (prm.joint) sums[ACC_L21] += w21[0] * sqrt(g2[0]) + w21[1] * sqrt(g2[1]);
+    }
+    if (prm.need_rsdl || prm.need_obj) {
+        double d[7];
+        SPCSC_UNROLL
+        for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
+        double* red = reinterpret_cast<double*>(smem_raw);
+        block_accumulate<7>(d, red, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_col2: cluster of CS CTAs per (wf, b) slab; CTA `cr` owns columns
+//   m = (cr*G + g)*CPG + c,  g = group (TPF lanes) index, c < CPG, kept in registers.
+//   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (gradient)
+// ------------------------------------------------------------------------------------
+template <typename T, int N0, int E, int CPG, int NT, bool DO_FWD, int SOLVE, bool DO_INV>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
+k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
+       const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
+       const AdmmState<T>* SPCSC_RESTRICT st, T Lstep, double* SPCSC_RESTRICT acc,
+       const C2<T>* SPCSC_RESTRICT stw, ColArgs a) {
+    if (st && st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    constexpr int TPF = N0 / E, NG = NT / TPF;
+    constexpr int TWLEN = stage_tw_len(N0, E);
+    C2<T>* xbuf = reinterpret_cast<C2<T>*>(smem_raw);         // [NG][N0] exchange / partial sums
+    C2<T>* sloc = xbuf + NG * N0;                              // [N0]  this CTA's sum over its columns
+    C2<T>* qbuf = sloc + N0;                                   // [N0]
+    C2<T>* stw_s = qbuf + N0;                                  // [TWLEN]
+    double* red = reinterpret_cast<double*>(stw_s + TWLEN);    // [32]
+    const int tid = threadIdx.x;
+    const unsigned cr = cluster_rank(), cs = cluster_size();
+    const int wf = blockIdx.x / cs, b = blockIdx.y;
+    const int M = a.M;
+    const int g = tid / TPF, t = tid % TPF;
+    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
+    const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
+    const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
+
+    C2<T> v[CPG][E];
+    int mcol[CPG];
+    SPCSC_UNROLL
+    for (int c = 0; c < CPG; ++c) {
+        mcol[c] = ((int)cr * NG + g) * CPG + c;
+        if (mcol[c] < M) {
+            const C2<T>* src = in + slab + (size_t)mcol[c] * N0;
+            SPCSC_UNROLL
+            for (int p = 0; p < E; ++p) v[c][p] = src[t + TPF * p];
+        } else {
+            SPCSC_UNROLL
+            for (int p = 0; p < E; ++p) v[c][p] = mk<T>(0, 0);
+        }
+    }
+    __syncthreads();                                         // stage twiddles are in place
+    if (DO_FWD) {
+        SPCSC_UNROLL
+        for (int c = 0; c < CPG; ++c) {
+            fft_regs<T, N0, E, false>(v[c], xbuf + g * N0, stw_s, t);
+            __syncwarp();
+        }
+    }
+    // partial sums over this group's columns
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) {
+        const int h = t + TPF * p;
+        C2<T> s = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int c = 0; c < CPG; ++c)
+            if (mcol[c] < M) s = s + dfw[(size_t)mcol[c] * N0 + h] * v[c][p];
+        xbuf[g * N0 + h] = s;
+    }
+    __syncthreads();
+    for (int h = tid; h < N0; h += NT) {
+        C2<T> s = mk<T>(0, 0);
+        for (int gg = 0; gg < NG; ++gg) s = s + xbuf[gg * N0 + h];
+        sloc[h] = s;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const int k = b / a.Cx, cx = b - k * a.Cx;
+    const T rho = (SOLVE == 1) ? st->rho : (T)0;
+    double dsum[1] = {0.0};
+    for (int h = tid; h < N0; h += NT) {
+        C2<T> s = mk<T>(0, 0);
+        for (unsigned rk = 0; rk < cs; ++rk) {
+            const C2<T>* ps = (rk == cr) ? sloc : cluster_peer(sloc, rk);
+            s = s + ps[h];
+        }
+        const C2<T> sf = Sf[(((size_t)k * a.Cs + cx) * a.N1f + wf) * N0 + h];
+        C2<T> d = sf - s;
+        if (SOLVE == 1) {
+            const T den = G[(size_t)wf * N0 + h].re + rho;
+            d = mk<T>(d.re / den, d.im / den);
+            if (a.dfid_on && cr == 0) {
+                const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+                dsum[0] += wgt * (double)abs2(d);
+            }
+        } else {
+            d = mk<T>(d.re / Lstep, d.im / Lstep);
+        }
+        qbuf[h] = d;
+    }
+    cluster_arrive();                                        // done reading the peers' sums
+    __syncthreads();
+    if (SOLVE == 1 && a.dfid_on) block_accumulate<1>(dsum, red, acc + ACC_DFID);
+    SPCSC_UNROLL
+    for (int c = 0; c < CPG; ++c) {
+        if (mcol[c] < M) {
+            SPCSC_UNROLL
+            for (int p = 0; p < E; ++p) {
+                const int h = t + TPF * p;
+                v[c][p] = v[c][p] + mulc(qbuf[h], dfw[(size_t)mcol[c] * N0 + h]);
+            }
+        }
+        if (DO_INV) {
+            fft_regs<T, N0, E, true>(v[c], xbuf + g * N0, stw_s, t);
+            __syncwarp();
+        }
+        if (mcol[c] < M) {
+            C2<T>* dst = out + slab + (size_t)mcol[c] * N0;
+            SPCSC_UNROLL
+            for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[c][p];
+        }
+    }
+    cluster_wait();                                          // peers are done with my shared memory
+}
+
+}  // namespace spcsc

@@ -3,7 +3,7 @@
 // parallel; spcsc.cu dispatches on the runtime size.
 #pragma once
 
-#include "kernels.cuh"
+#include "kernels2.cuh"
 
 namespace spcsc {
 
@@ -65,6 +65,44 @@ cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const
 // columns
 template <typename T, int N0>
 cudaError_t col_launch(int mode, ColLaunch<T> c);
+
+// ---- kernel set v2 (kernels2.cuh): plans and eligibility ------------------------------
+constexpr int kRow2Threads = 256;
+constexpr int kCol2Threads = 256;
+constexpr int kCol2E = 16;
+constexpr int kCol2CPG = 2;
+
+// elements per lane of the v2 row plan (0: no v2 plan for this length)
+constexpr int row2_elems(int H, int Cx) {
+    int e = H >= 128 ? 16 : (H >= 32 ? 8 : 0);
+    if (Cx > 1 && e > 8) e = 8;
+    if (e != 0 && H / e > 32) e = 0;
+    return e;
+}
+constexpr int row2_tile(int H, int Cx) {
+    return row2_elems(H, Cx) == 0 ? 0 : kRow2Threads / (H / row2_elems(H, Cx));
+}
+template <typename T>
+inline bool row2_ok(int H, int N0, int Cx) {
+    if (sizeof(T) != 4) return false;
+    const int tr = row2_tile(H, Cx);
+    return tr > 0 && N0 % tr == 0 && Cx <= 4;
+}
+template <typename T>
+inline bool col2_ok(int N0, int M, int Cd) {
+    if (sizeof(T) != 4 || Cd != 1 || N0 < 32 || N0 > 512) return false;
+    const int per_cta = (kCol2Threads / (N0 / kCol2E)) * kCol2CPG;
+    return (M + per_cta - 1) / per_cta <= 8;
+}
+
+template <typename T, int H>
+cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
+                            C2<T>* Zt, const C2<T>* stw);
+template <typename T, int H>
+cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
+                                 T* U, const AdmmState<T>* st, const C2<T>* stw);
+template <typename T, int N0>
+cudaError_t col2_launch(int mode, ColLaunch<T> c, const C2<T>* stw);
 
 // Rows per CTA for the row kernels (shared by launch code and memory planning).
 template <typename T>

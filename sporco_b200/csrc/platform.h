@@ -16,7 +16,7 @@
 
 #ifdef SPCSC_EMU
 #include "cuda_emu.h"            // tests/emu/cuda_emu.h (test infrastructure)
-#define SPCSC_HD
+#define SPCSC_HD inline
 #define SPCSC_DEV inline
 #define SPCSC_GLOBAL
 #define SPCSC_LAUNCH_BOUNDS(t)
@@ -25,6 +25,7 @@
 #define SPCSC_UNROLL
 #else
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #define SPCSC_HD __host__ __device__ __forceinline__
 #define SPCSC_DEV __device__ __forceinline__
 #define SPCSC_GLOBAL __global__
@@ -54,6 +55,55 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
     return cudaGetLastError();
 #endif
 }
+
+// ---- thread-block clusters (distributed shared memory) ----------------------------------
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, unsigned cs,
+                                  size_t smem, cudaStream_t stream, Args... args) {
+#ifdef SPCSC_EMU
+    (void)stream;
+    emu::launch_cluster(grid, block, cs, smem, [=]() { kern(args...); });
+    return cudaSuccess;
+#else
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+#endif
+}
+
+#ifdef SPCSC_EMU
+inline unsigned cluster_rank() { return emu::cluster_rank(); }
+inline unsigned cluster_size() { return emu::cluster_size(); }
+inline void cluster_arrive() { emu::cluster_arrive(); }
+inline void cluster_wait() { emu::cluster_wait(); }
+template <typename P> inline P* cluster_peer(P* p, unsigned rank) {
+    return reinterpret_cast<P*>(emu::map_shared_rank((void*)p, rank));
+}
+#else
+SPCSC_DEV unsigned cluster_rank() { return cooperative_groups::this_cluster().block_rank(); }
+SPCSC_DEV unsigned cluster_size() { return cooperative_groups::this_cluster().num_blocks(); }
+SPCSC_DEV void cluster_arrive() { cooperative_groups::this_cluster().barrier_arrive(); }
+SPCSC_DEV void cluster_wait() { cooperative_groups::this_cluster().barrier_wait(); }
+template <typename P> SPCSC_DEV P* cluster_peer(P* p, unsigned rank) {
+    return cooperative_groups::this_cluster().map_shared_rank(p, rank);
+}
+#endif
 
 // ---- complex value type with natural vector alignment (8 B for float, 16 B for double)
 template <typename T>

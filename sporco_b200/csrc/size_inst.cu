@@ -20,4 +20,15 @@ namespace spcsc {
 SPCSC_INST(float)
 SPCSC_INST(double)
 
+// kernel set v2 (float only)
+template cudaError_t row_fwd2_launch<float, SPCSC_SIZE>(const RowArgs<float>&, const float*,
+                                                        const float*, const AdmmState<float>*,
+                                                        C2<float>*, const C2<float>*);
+template cudaError_t row_inv_prox2_launch<float, SPCSC_SIZE>(const RowArgs<float>&,
+                                                             const ProxArgs<float>&,
+                                                             const C2<float>*, float*, float*,
+                                                             const AdmmState<float>*,
+                                                             const C2<float>*);
+template cudaError_t col2_launch<float, SPCSC_SIZE>(int, ColLaunch<float>, const C2<float>*);
+
 }  // namespace spcsc

@@ -3,6 +3,7 @@
 #include <spcsc.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,43 @@ static cudaError_t col(int N0, int mode, const ColLaunch<T>& c) {
 #define X(n) case n: return col_launch<T, n>(mode, c);
         SPCSC_FOR_SIZES(X)
 #undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename T>
+static cudaError_t row_fwd2(int H, const RowArgs<T>& r, const T* A, const T* B,
+                            const AdmmState<T>* st, C2<T>* Zt, const C2<T>* stw) {
+    if constexpr (sizeof(T) == 4) {
+        switch (H) {
+#define X(n) case n: return row_fwd2_launch<T, n>(r, A, B, st, Zt, stw);
+            SPCSC_FOR_SIZES(X)
+#undef X
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T>
+static cudaError_t row_inv_prox2(int H, const RowArgs<T>& r, const ProxArgs<T>& p,
+                                 const C2<T>* Zt, T* Y, T* U, const AdmmState<T>* st,
+                                 const C2<T>* stw) {
+    if constexpr (sizeof(T) == 4) {
+        switch (H) {
+#define X(n) case n: return row_inv_prox2_launch<T, n>(r, p, Zt, Y, U, st, stw);
+            SPCSC_FOR_SIZES(X)
+#undef X
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T>
+static cudaError_t col2(int N0, int mode, const ColLaunch<T>& c, const C2<T>* stw) {
+    if constexpr (sizeof(T) == 4) {
+        switch (N0) {
+#define X(n) case n: return col2_launch<T, n>(mode, c, stw);
+            SPCSC_FOR_SIZES(X)
+#undef X
+        }
     }
     return cudaErrorInvalidValue;
 }
@@ -180,6 +218,8 @@ class Engine : public spcsc_handle {
     cudaStream_t stream = nullptr;
     DevBuf<T> Y, U, tmp_real, wl1_buf, wl21_buf, staging;
     DevBuf<C2<T>> Zt, Zscratch, Xscratch, Df, Sf, G, tw_row, tw_col, sum_buf;
+    DevBuf<C2<T>> stw_row1, stw_rowc, stw_col;     // stage twiddles of the v2 register plans
+    bool v2_rowf = false, v2_rowp = false, v2_col = false;
     DevBuf<double> acc;
     DevBuf<AdmmState<T>> st;
     DevBuf<StatRow> rows;
@@ -207,6 +247,7 @@ class Engine : public spcsc_handle {
         staging.release(); Zt.release(); Zscratch.release(); Xscratch.release(); Df.release();
         Sf.release(); G.release(); tw_row.release(); tw_col.release(); sum_buf.release();
         acc.release(); st.release(); rows.release();
+        stw_row1.release(); stw_rowc.release(); stw_col.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -232,6 +273,18 @@ class Engine : public spcsc_handle {
         CK(cudaMemcpyAsync(tw_row.p, wr.data(), N1 * sizeof(C2<T>), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(tw_col.p, wc.data(), N0 * sizeof(C2<T>), cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
+        // kernel set v2 eligibility (SPCSC_KERNELS=v1 forces the general kernels)
+        {
+            const char* force = getenv("SPCSC_KERNELS");
+            const bool allow2 = !(force && std::string(force) == "v1");
+            v2_rowf = allow2 && row2_ok<T>(H, N0, 1);
+            v2_rowp = allow2 && row2_ok<T>(H, N0, Cx);
+            v2_col = allow2 && col2_ok<T>(N0, M, Cd);
+            int rc;
+            if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1)))) return rc;
+            if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx)))) return rc;
+            if (v2_col && (rc = upload_stage_tw(stw_col, N0, kCol2E))) return rc;
+        }
         // default weights: scalar 1
         const T one = 1;
         CK(wl1_buf.ensure(1));
@@ -242,6 +295,14 @@ class Engine : public spcsc_handle {
         wl21 = WeightView<T>{wl21_buf.p, 0, 0, 0, 0, 0, 1};
         CK(cudaStreamSynchronize(stream));
         return admm_reset(1.0);
+    }
+
+    int upload_stage_tw(DevBuf<C2<T>>& buf, int n, int e) {
+        auto tab = make_stage_twiddles<T>(n, e);
+        CK(buf.ensure(tab.size()));
+        CK(cudaMemcpyAsync(buf.p, tab.data(), tab.size() * sizeof(C2<T>), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
     }
 
     RowArgs<T> rowargs(int m, int nb, int cx) const {
@@ -459,11 +520,18 @@ class Engine : public spcsc_handle {
         last_launches = 0;
         if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
         for (int it = 0; it < n; ++it) {
-            CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p));
+            if (v2_rowf)
+                CK(row_fwd2<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p,
+                               (const C2<T>*)stw_row1.p));
+            else
+                CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (!check) {
                 cs.in = Zt.p; cs.out = Zt.p;
-                CK(col<T>(N0, COL_ADMM, cs));
+                if (v2_col)
+                    CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
+                else
+                    CK(col<T>(N0, COL_ADMM, cs));
                 last_launches += 4;
             } else {
                 ColLaunch<T> c1 = cs;
@@ -482,7 +550,11 @@ class Engine : public spcsc_handle {
                 last_launches += 7;
             }
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
-            CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p, (const AdmmState<T>*)st.p));
+            if (v2_rowp)
+                CK(row_inv_prox2<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p,
+                                    (const AdmmState<T>*)st.p, (const C2<T>*)stw_rowc.p));
+            else
+                CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p, (const AdmmState<T>*)st.p));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));

@@ -74,3 +74,42 @@ def run_admm_case(tag, sfx):
         assert rel(its.RegL21, g['RegL21']) <= 10 * stol
     assert rel(b.reconstruct().reshape(g['recon'].shape), g['recon']) <= 4 * tol
     return b
+
+
+def run_fresh_case(N0, N1, M, K, C=None, mu=None, iters=8, extra=None, dt=np.float32, seed=1,
+                   tol=3e-4):
+    """Seeded random problem solved by sporco_b200 and by the oracle; sizes chosen so that the
+    register-plan (v2) kernels, including the cluster-split column kernel, are exercised."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(seed)
+    D = rng.standard_normal((5, 5, M)).astype(dt)
+    shp = (N0, N1) + ((C,) if C else ()) + ((K,) if K else ())
+    S = rng.standard_normal(shp).astype(dt)
+    o = {'MaxMainIter': iters, 'RelStopTol': 0.0}
+    o.update(extra or {})
+    dimK = None if (C and K) else (1 if K else 0)
+    if mu is None:
+        b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=dimK)
+    else:
+        b = cbpdn.ConvBPDNJoint(D, S, 0.1, mu, cbpdn.ConvBPDNJoint.Options(o), dimK=dimK)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, mu=mu, opt=o, dimK=dimK)
+    its = b.getitstat()
+    rc = 9 if mu is not None else 8
+    assert rel(Y, r.Y) < tol, 'Y %.3e' % rel(Y, r.Y)
+    assert rel(b.U, r.U) < 2 * tol
+    assert rel(its.Rho, [x[rc] for x in r.itstat]) < tol
+    assert rel(its.ObjFun, [x[1] for x in r.itstat]) < tol
+    return b, r
+
+
+FRESH_CASES = [
+    # N0, N1, M, K, C, mu, extra        (what it exercises)
+    (256, 64, 40, 2, None, None, None),                    # column cluster of 2 (ragged), rows E=8
+    (64, 256, 12, 2, None, None, None),                    # rows E=16
+    (128, 128, 70, 1, None, None, {'NonNegCoef': True}),   # cluster of 2, M not a multiple
+    (64, 64, 8, 2, 2, 0.05, None),                         # joint prox, CX=2
+    (32, 512, 5, 1, None, None, None),                     # long rows (H=256)
+    (512, 64, 9, 1, None, None, None),                     # long columns (full-warp plan)
+]

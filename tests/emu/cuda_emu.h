@@ -33,6 +33,12 @@ extern thread_local uint3 t_threadIdx, t_blockIdx;
 extern thread_local dim3 t_blockDim, t_gridDim;
 unsigned char* dyn_smem();
 void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> fn);
+void launch_cluster(dim3 grid, dim3 block, unsigned cs, size_t smem, std::function<void()> fn);
+unsigned cluster_rank();
+unsigned cluster_size();
+void cluster_arrive();
+void cluster_wait();
+void* map_shared_rank(void* p, unsigned rank);
 void sync_threads();
 void sync_warp();
 // exchange 16-byte payloads between lanes of the calling warp

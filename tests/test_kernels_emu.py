@@ -65,3 +65,14 @@ def test_resume_and_pickle():
     assert b.k == 30 and b2.k == 30
     assert cases.rel(b.Y, g['Y']) < 1e-9
     assert cases.rel(b2.Y, g['Y']) < 1e-9
+
+
+@pytest.mark.parametrize('case', cases.FRESH_CASES)
+def test_register_plan_kernels_vs_oracle(case):
+    N0, N1, M, K, C, mu, extra = case
+    cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
+
+
+def test_general_kernels_on_the_same_problem(monkeypatch):
+    monkeypatch.setenv('SPCSC_KERNELS', 'v1')
+    cases.run_fresh_case(256, 64, 40, 2)

@@ -110,3 +110,17 @@ def test_benchmark_size_properties():
     dfid = 0.5 * np.sum((rec[:, :, 0, :] - S) ** 2, dtype=np.float64)
     # DFid in itstat is evaluated on X, reconstruct on Y: same order of magnitude, and both finite
     assert np.isfinite(dfid) and dfid > 0
+
+
+@pytest.mark.parametrize('case', cases.FRESH_CASES)
+def test_register_plan_kernels_vs_oracle(case):
+    N0, N1, M, K, C, mu, extra = case
+    cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
+
+
+def test_kernel_sets_agree(monkeypatch):
+    """The general kernels (v1) and the register-plan kernels (v2) on the same problem."""
+    b2, r = cases.run_fresh_case(256, 256, 64, 2, iters=12)
+    monkeypatch.setenv('SPCSC_KERNELS', 'v1')
+    b1, _ = cases.run_fresh_case(256, 256, 64, 2, iters=12)
+    assert cases.rel(b1.Y, b2.Y) < 3e-4
