@@ -234,6 +234,132 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
 }
 
 // ------------------------------------------------------------------------------------
+// k_row_inv_prox3 (CX == 1): as k_row_inv_prox2, but every global read of the CTA -- the
+// transposed Zt tile and the contiguous Y and U tiles (TR rows x N1 reals each) -- is issued
+// up front as asynchronous global->shared copies (cp.async), so the memory system is kept
+// busy independently of the register budget; the transforms and the prox then run out of
+// shared memory.  (The v2 profile showed the kernel waiting on its own loads 60 % of the time.)
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int E, int NT>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
+k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RESTRICT U,
+                const AdmmState<T>* SPCSC_RESTRICT st, AdmmParams<T> prm, WeightView<T> wl1,
+                double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
+                const C2<T>* SPCSC_RESTRICT stw, int N0, int M, T scale, int nonneg, int bnd0,
+                int bnd1, int reg_on_y) {
+    if (st->stopped) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
+    constexpr int TWLEN = stage_tw_len(H, E);
+    constexpr int VEC = 16 / sizeof(C2<T>);                    // complex values per 16-byte copy
+    C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [TR][H]  (as complex pairs)
+    C2<T>* ubuf = ybuf + TR * H;                               // [TR][H]
+    C2<T>* reg = ubuf + TR * H;                                // [TR][P]
+    C2<T>* stw_s = reg + TR * P;
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    const size_t wstride = (size_t)M * N0;
+    {   // group 0: the Zt tile, transposed on the fly (one complex per copy)
+        const C2<T>* in = Zt + (((size_t)k * N1f) * M + m) * N0 + h0;
+        for (int e = tid; e < TR * N1f; e += NT) {
+            const int wf = e / TR, r = e % TR;
+            cp_async<sizeof(C2<T>)>(reg + r * P + wf, in + wf * wstride + r);
+        }
+        cp_async_commit();
+    }
+    const size_t tile = ((((size_t)k * M + m) * N0 + h0) * H);   // in complex-pair units
+    {   // group 1: the Y and U tiles, contiguous
+        const C2<T>* y2 = reinterpret_cast<const C2<T>*>(Y) + tile;
+        const C2<T>* u2 = reinterpret_cast<const C2<T>*>(U) + tile;
+        for (int e = tid * VEC; e < TR * H; e += NT * VEC) {
+            cp_async<16>(ybuf + e, y2 + e);
+            cp_async<16>(ubuf + e, u2 + e);
+        }
+        cp_async_commit();
+    }
+    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
+    const int g = tid / TPF, t = tid % TPF;
+    const int h = h0 + g;
+    cp_async_wait<1>();
+    __syncthreads();
+
+    C2<T> v[E];
+    {
+        C2<T>* row = reg + g * P;
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) {
+            const int kk = t + TPF * p;
+            if (kk == 0) {
+                const T a = row[0].re, cc = row[H].re;       // c2r ignores the imaginary parts
+                v[p] = mk<T>(a + cc, a - cc);
+            } else {
+                const C2<T> Xa = row[kk], Xb = row[H - kk];
+                const C2<T> w = tw[kk];
+                const C2<T> s1 = Xa + conj(Xb), d1 = Xa - conj(Xb);
+                v[p] = s1 + mul_i(mulc(d1, w));
+            }
+        }
+        __syncwarp();
+        fft_regs<T, H, E, true>(v, row, stw_s, t);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const T rho = st->rho;
+    T uinv = 1;
+    {
+        const T ud = st->udiv;
+        if (ud != (T)1) uinv = (T)1 / ud;
+    }
+    const T lr = prm.lmbda / rho;
+    const T rlx = prm.rlx;
+    const bool relax = rlx != (T)1;
+    const T rl1 = (T)1 - rlx;
+    T sums[7] = {0, 0, 0, 0, 0, 0, 0};
+    const T w1u = wl1.p[(size_t)k * wl1.sk + (size_t)m * wl1.sm];
+    const size_t wbase = (size_t)k * wl1.sk + (size_t)m * wl1.sm + (size_t)h * wl1.s0;
+    C2<T>* yg = reinterpret_cast<C2<T>*>(Y) + tile + (size_t)g * H;
+    C2<T>* ug = reinterpret_cast<C2<T>*>(U) + tile + (size_t)g * H;
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) {
+        const int j = t + TPF * p;
+        const C2<T> y2 = ybuf[g * H + j], u2 = ubuf[g * H + j];
+        const T xs[2] = {v[p].re * scale, v[p].im * scale};
+        const T ys[2] = {y2.re, y2.im};
+        const T us[2] = {u2.re * uinv, u2.im * uinv};
+        T yn[2], un[2];
+        SPCSC_UNROLL
+        for (int q = 0; q < 2; ++q) {
+            const T w1 = wl1.spatial_uniform ? w1u : wl1.p[wbase + (size_t)(2 * j + q) * wl1.s1];
+            const T axv = relax ? rlx * xs[q] + rl1 * ys[q] : xs[q];
+            T y = soft_threshold(axv + us[q], lr * w1);
+            if (nonneg && y < (T)0) y = (T)0;
+            if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+            const T u = us[q] + (axv - y);
+            yn[q] = y;
+            un[q] = u;
+            const T x = xs[q];
+            const T dr = x - y, ds = ys[q] - y;
+            sums[ACC_X2] += x * x;
+            sums[ACC_Y2] += y * y;
+            sums[ACC_U2] += u * u;
+            sums[ACC_R2] += dr * dr;
+            sums[ACC_S2] += ds * ds;
+            sums[ACC_L1] += fabs(w1 * (reg_on_y ? y : x));
+        }
+        yg[j] = mk<T>(yn[0], yn[1]);
+        ug[j] = mk<T>(un[0], un[1]);
+    }
+    if (prm.need_rsdl || prm.need_obj) {
+        double d[7];
+        SPCSC_UNROLL
+        for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
+        double* red = reinterpret_cast<double*>(smem_raw);
+        block_accumulate<7>(d, red, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // k_col2: cluster of CS CTAs per (wf, b) slab; CTA `cr` owns columns
 //   m = (cr*G + g)*CPG + c,  g = group (TPF lanes) index, c < CPG, kept in registers.
 //   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (gradient)

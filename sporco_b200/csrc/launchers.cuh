@@ -24,6 +24,7 @@ struct ProxArgs {
     double* acc;
     T scale;
     int nonneg, bnd0, bnd1, reg_on_y;
+    int use_v2_sync;             // 1: synchronous-load row kernel (k_row_inv_prox2) even when CX == 1
 };
 
 enum ColMode {
@@ -50,6 +51,7 @@ struct ColLaunch {
     const C2<T>* tw;             // exp(-2 pi i j / N0)
     int nb;                      // slabs per frequency column (grid.y)
     ColArgs a;                   // MC / nchunk / parts filled by the launcher
+    int cpg;                     // v2: columns kept in registers per lane group (1 or 2)
     cudaStream_t stream;
 };
 
@@ -92,7 +94,7 @@ template <typename T>
 inline bool col2_ok(int N0, int M, int Cd) {
     if (sizeof(T) != 4 || Cd != 1 || N0 < 32 || N0 > 512) return false;
     const int per_cta = (kCol2Threads / (N0 / kCol2E)) * kCol2CPG;
-    return (M + per_cta - 1) / per_cta <= 8;
+    return (M + per_cta - 1) / per_cta <= 4;     // so that the one-column variant needs <= 8 CTAs
 }
 
 template <typename T, int H>

@@ -134,10 +134,27 @@ static cudaError_t row_inv_prox2_cx(const RowArgs<T>& r, const ProxArgs<T>& p, c
 }
 
 template <typename T, int H>
+static cudaError_t row_inv_prox3_go(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
+                                    T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
+    if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
+        constexpr int E = row2_elems(H, 1), NT = kRow2Threads, TR = row2_tile(H, 1);
+        const size_t smem = ((size_t)TR * (3 * H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+        dim3 grid(r.N0 / TR, r.M, r.nb);
+        return launch(k_row_inv_prox3<T, H, E, NT>, grid, dim3(NT), smem, r.stream, Zt, Y, U, st,
+                      p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
+                      p.reg_on_y);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+}
+
+template <typename T, int H>
 cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
                                  T* U, const AdmmState<T>* st, const C2<T>* stw) {
     switch (r.Cx) {
-        case 1: return row_inv_prox2_cx<T, H, 1>(r, p, Zt, Y, U, st, stw);
+        case 1:
+            if (!p.prm.joint && !p.use_v2_sync) return row_inv_prox3_go<T, H>(r, p, Zt, Y, U, st, stw);
+            return row_inv_prox2_cx<T, H, 1>(r, p, Zt, Y, U, st, stw);
         case 2: return row_inv_prox2_cx<T, H, 2>(r, p, Zt, Y, U, st, stw);
         case 3: return row_inv_prox2_cx<T, H, 3>(r, p, Zt, Y, U, st, stw);
         case 4: return row_inv_prox2_cx<T, H, 4>(r, p, Zt, Y, U, st, stw);
@@ -145,22 +162,28 @@ cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, cons
     }
 }
 
+template <typename T, int N0, int CPG>
+static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
+    constexpr int E = kCol2E, NT = kCol2Threads;
+    constexpr int TPF = N0 / E, NG = NT / TPF;
+    const int per_cta = NG * CPG;
+    const unsigned cs = (unsigned)((c.a.M + per_cta - 1) / per_cta);
+    c.a.N0 = N0;
+    const size_t smem = ((size_t)NG * N0 + 2 * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
+                        32 * sizeof(double);
+    dim3 grid(c.a.N1f * cs, c.nb);
+    if (mode == COL_ADMM)
+        return launch_cluster(k_col2<T, N0, E, CPG, NT, true, 1, true>, grid, dim3(NT), cs, smem,
+                              c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw,
+                              c.a);
+    return cudaErrorInvalidValue;
+}
+
 template <typename T, int N0>
 cudaError_t col2_launch(int mode, ColLaunch<T> c, const C2<T>* stw) {
     if constexpr (sizeof(T) == 4 && N0 >= 32 && N0 <= 512) {
-        constexpr int E = kCol2E, NT = kCol2Threads, CPG = kCol2CPG;
-        constexpr int TPF = N0 / E, NG = NT / TPF;
-        const int per_cta = NG * CPG;
-        const unsigned cs = (unsigned)((c.a.M + per_cta - 1) / per_cta);
-        c.a.N0 = N0;
-        const size_t smem = ((size_t)NG * N0 + 2 * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
-                            32 * sizeof(double);
-        dim3 grid(c.a.N1f * cs, c.nb);
-        if (mode == COL_ADMM)
-            return launch_cluster(k_col2<T, N0, E, CPG, NT, true, 1, true>, grid, dim3(NT), cs, smem,
-                                  c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw,
-                                  c.a);
-        return cudaErrorInvalidValue;
+        if (c.cpg == 1) return col2_go<T, N0, 1>(mode, c, stw);
+        return col2_go<T, N0, 2>(mode, c, stw);
     } else {
         return cudaErrorInvalidValue;
     }

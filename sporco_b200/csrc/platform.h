@@ -26,6 +26,7 @@
 #else
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#include <cuda_pipeline.h>
 #define SPCSC_HD __host__ __device__ __forceinline__
 #define SPCSC_DEV __device__ __forceinline__
 #define SPCSC_GLOBAL __global__
@@ -103,6 +104,19 @@ SPCSC_DEV void cluster_wait() { cooperative_groups::this_cluster().barrier_wait(
 template <typename P> SPCSC_DEV P* cluster_peer(P* p, unsigned rank) {
     return cooperative_groups::this_cluster().map_shared_rank(p, rank);
 }
+#endif
+
+// ---- asynchronous global -> shared copies (LDGSTS) -------------------------------------
+#ifdef SPCSC_EMU
+template <int BYTES> inline void cp_async(void* dst, const void* src) { memcpy(dst, src, BYTES); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+#else
+template <int BYTES> SPCSC_DEV void cp_async(void* dst, const void* src) {
+    __pipeline_memcpy_async(dst, src, BYTES);
+}
+SPCSC_DEV void cp_async_commit() { __pipeline_commit(); }
+template <int N> SPCSC_DEV void cp_async_wait() { __pipeline_wait_prior(N); }
 #endif
 
 // ---- complex value type with natural vector alignment (8 B for float, 16 B for double)

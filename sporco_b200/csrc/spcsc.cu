@@ -220,6 +220,7 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> Zt, Zscratch, Xscratch, Df, Sf, G, tw_row, tw_col, sum_buf;
     DevBuf<C2<T>> stw_row1, stw_rowc, stw_col;     // stage twiddles of the v2 register plans
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
+    int col_cpg = kCol2CPG;
     DevBuf<double> acc;
     DevBuf<AdmmState<T>> st;
     DevBuf<StatRow> rows;
@@ -280,6 +281,7 @@ class Engine : public spcsc_handle {
             v2_rowf = allow2 && row2_ok<T>(H, N0, 1);
             v2_rowp = allow2 && row2_ok<T>(H, N0, Cx);
             v2_col = allow2 && col2_ok<T>(N0, M, Cd);
+            if (const char* e = getenv("SPCSC_COL_CPG")) col_cpg = (atoi(e) == 1) ? 1 : 2;
             int rc;
             if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1)))) return rc;
             if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx)))) return rc;
@@ -323,6 +325,7 @@ class Engine : public spcsc_handle {
         c.a.even_n1 = 1;
         c.stream = stream;
         c.Lstep = 1;
+        c.cpg = col_cpg;
         return c;
     }
 
@@ -512,6 +515,7 @@ class Engine : public spcsc_handle {
             pa.bnd1 = pb.wd == 1 ? 0 : N1 - (pb.wd - 1);
         }
         pa.reg_on_y = opts.aux_var_obj;
+        pa.use_v2_sync = (getenv("SPCSC_ROWPROX") && std::string(getenv("SPCSC_ROWPROX")) == "sync") ? 1 : 0;
         ColLaunch<T> cs = colargs(M, K * Cx);
         cs.st = st.p;
         cs.acc = acc.p;
