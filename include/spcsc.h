@@ -128,6 +128,17 @@ int spcsc_admm_last_timing(spcsc_handle* h, float* elapsed_ms, int64_t* launches
    Measurement aid for bench.py (same kernels, same stream as spcsc_admm_iterate). */
 int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]);
 
+/* ---- multi-GPU: images are sharded over ranks (one process per GPU); the only exchange of
+   the path is the all-reduce of the residual / objective sums that drive the shared rho and the
+   stopping test (admm/admm.py:462-486 are global over all K images).  NCCL is resolved at run
+   time from `nccl_lib` (path or soname of the libnccl the process already uses).
+   spcsc_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller broadcasts it.
+   spcsc_comm_init: collective over all ranks; `global_nx` = total number of coefficient
+   elements over all ranks (sets the AbsStopTol scaling, admm/admm.py:481-484). */
+int spcsc_comm_unique_id(const char* nccl_lib, void* id128);
+int spcsc_comm_init(spcsc_handle* h, const char* nccl_lib, const void* id128, int32_t rank,
+                    int32_t nranks, double global_nx);
+
 /* ---- state access */
 int spcsc_get_array(spcsc_handle* h, int32_t which, void* host_out);
 int spcsc_set_array(spcsc_handle* h, int32_t which, const void* host_in);   /* Y or U */

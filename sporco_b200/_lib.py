@@ -23,7 +23,7 @@ SYMBOLS = (
     'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_set_iter',
     'spcsc_admm_iterate',
     'spcsc_admm_get_scalars', 'spcsc_admm_last_timing', 'spcsc_admm_profile', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
-    'spcsc_rfft2', 'spcsc_irfft2',
+    'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_init',
 )
 
 
@@ -88,6 +88,8 @@ def _declare(lib):
     lib.spcsc_get_array.argtypes = [vp, i32, vp]
     lib.spcsc_set_array.argtypes = [vp, i32, vp]
     lib.spcsc_reconstruct.argtypes = [vp, vp, vp]
+    lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
+    lib.spcsc_comm_init.argtypes = [vp, ctypes.c_char_p, vp, i32, i32, ctypes.c_double]
     lib.spcsc_rfft2.argtypes = [i32, i32, i32, i32, i32, vp, vp]
     lib.spcsc_irfft2.argtypes = [i32, i32, i32, i32, i32, vp, vp]
     for name in SYMBOLS:
@@ -280,6 +282,11 @@ class Handle(object):
     def synchronize(self):
         self._c(self.lib.spcsc_synchronize(self.h))
 
+    def comm_init(self, nccl_lib, uid, rank, nranks, global_nx):
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(uid))
+        self._c(self.lib.spcsc_comm_init(self.h, nccl_lib.encode(), buf, rank, nranks,
+                                         float(global_nx)))
+
 
 def rfft2(x, device=0):
     """rfftn over the last two axes of a (batch, N0, N1) real array, on the GPU."""
@@ -303,3 +310,23 @@ def irfft2(xf, n1, device=0):
     out = np.empty((b, n0, n1), dtype=rdt)
     check(lib.spcsc_irfft2(dtype_code(rdt), device, b, n0, n1, _ptr(xf), _ptr(out)))
     return out
+
+
+def nccl_library_path():
+    """Path of the libnccl this process has loaded (torch's bundled copy when torch is
+    imported), else the bare soname for the dynamic loader to resolve."""
+    try:
+        with open('/proc/self/maps') as f:
+            for line in f:
+                if 'libnccl' in line and '.so' in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    return 'libnccl.so.2'
+
+
+def comm_unique_id(nccl_lib):
+    lib = load()
+    buf = (ctypes.c_char * 128)()
+    check(lib.spcsc_comm_unique_id(nccl_lib.encode(), buf))
+    return bytes(buf.raw)

@@ -203,6 +203,28 @@ class GenericConvBPDN(admm.ADMMEqual):
              rdt(row.rho), xr, t)
         return type(self).IterationStats(*tpl)
 
+    # ---- multi-GPU ---------------------------------------------------------------------
+    def attach_process_group(self, dist, group=None):
+        """Join the solvers of all ranks of a ``torch.distributed`` process group into one
+        batch-sharded problem: this rank keeps its own images (the `S` it was built with), and
+        the squared norms behind r, s, rho and the stopping test -- global over all images in
+        the reference (sporco/admm/admm.py:462-486) -- are summed over the ranks once per
+        iteration on the device.  Coefficient maps never leave their GPU.  ``torch.distributed``
+        only carries the 128-byte NCCL id and the element count."""
+        import torch
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        nccl_lib = _lib.nccl_library_path()
+        dev = torch.device('cuda', self._device)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(_lib.comm_unique_id(nccl_lib)),
+                                   dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, src=0, group=group)
+        nx = torch.tensor([float(self.Nx)], dtype=torch.float64, device=dev)
+        dist.all_reduce(nx, group=group)
+        self._h.comm_init(nccl_lib, bytes(uid.cpu().numpy().tobytes()), rank, world, float(nx.item()))
+        self._world = world
+
     # ---- pickling: device state travels as host arrays
     def __getstate__(self):
         st = {k: v for k, v in self.__dict__.items() if k not in ('_h', '_cache')}

@@ -9,6 +9,10 @@
 
 #include "launchers.cuh"
 
+#ifndef SPCSC_EMU
+#include <dlfcn.h>
+#endif
+
 namespace spcsc {
 
 // ---- dispatch on transform length -------------------------------------------------------
@@ -135,6 +139,43 @@ SPCSC_GLOBAL void k_freq_to_ext(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RES
 
 using namespace spcsc;
 
+// ---- NCCL, resolved at run time (no link-time dependency) ---------------------------------
+namespace {
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string err;
+};
+NcclApi& nccl_api(const char* libname) {
+    static NcclApi api;
+    if (api.ok) return api;
+#ifdef SPCSC_EMU
+    (void)libname;
+    api.err = "NCCL is not available in the CPU emulation build";
+#else
+    const char* name = (libname && libname[0]) ? libname : "libnccl.so.2";
+    void* hnd = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (!hnd) { api.err = std::string("dlopen failed: ") + dlerror(); return api; }
+    api.GetUniqueId = (int (*)(NcclApi::UniqueId*))dlsym(hnd, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclApi::UniqueId, int))dlsym(hnd, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(hnd, "ncclAllReduce");
+    api.CommDestroy = (int (*)(void*))dlsym(hnd, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(hnd, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+        api.err = "libnccl does not export the expected symbols";
+        return api;
+    }
+    api.ok = true;
+#endif
+    return api;
+}
+}  // namespace
+
 static thread_local std::string g_last_error;
 
 struct spcsc_handle {
@@ -157,6 +198,7 @@ struct spcsc_handle {
     virtual int set_array(int which, const void* in) = 0;
     virtual int reconstruct(const void* X, void* out) = 0;
     virtual int synchronize() = 0;
+    virtual int comm_init(const char* lib, const void* id, int rank, int nranks, double global_nx) = 0;
 };
 
 namespace {
@@ -229,6 +271,10 @@ class Engine : public spcsc_handle {
     spcsc_admm_opts opts;
     bool have_dict = false, have_signal = false, configured = false, have_x = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* nccl_comm = nullptr;
+    NcclApi* nccl = nullptr;
+    int nranks = 1;
+    double global_nx = 0.0;
     std::vector<cudaEvent_t> prof_ev;
     float last_ms = 0.f;
     int64_t last_launches = 0;
@@ -249,6 +295,7 @@ class Engine : public spcsc_handle {
         Sf.release(); G.release(); tw_row.release(); tw_col.release(); sum_buf.release();
         acc.release(); st.release(); rows.release();
         stw_row1.release(); stw_rowc.release(); stw_col.release();
+        if (nccl_comm && nccl) nccl->CommDestroy(nccl_comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -434,7 +481,7 @@ class Engine : public spcsc_handle {
         prm.xi = (T)o->ar_rsdl_target;
         prm.abs_tol = o->abs_tol;
         prm.rel_tol = o->rel_tol;
-        prm.n_x = (double)nreal;
+        prm.n_x = global_nx > 0.0 ? global_nx : (double)nreal;
         prm.inv_n = 1.0 / ((double)N0 * (double)N1);
         prm.autorho = o->ar_enabled;
         prm.period = o->ar_period > 0 ? o->ar_period : 1;
@@ -560,6 +607,15 @@ class Engine : public spcsc_handle {
             else
                 CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p, (const AdmmState<T>*)st.p));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
+                // the one exchange of the path: sum the residual / objective accumulators over ranks
+                int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
+                if (nr != 0) {
+                    err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr);
+                    poisoned = true;
+                    return SPCSC_ERR_NCCL;
+                }
+            }
             CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
         }
@@ -739,6 +795,24 @@ class Engine : public spcsc_handle {
         return from_internal(rec, out, C, K, 1);
     }
 
+    int comm_init(const char* lib, const void* id, int rank, int nr, double gnx) override {
+        if (nr < 1 || rank < 0 || rank >= nr) FAIL(SPCSC_ERR_INVALID, "bad rank / nranks");
+        NcclApi& api = nccl_api(lib);
+        if (!api.ok) FAIL(SPCSC_ERR_NCCL, api.err);
+        CK(cudaSetDevice(pb.device));
+        NcclApi::UniqueId uid;
+        memcpy(&uid, id, sizeof(uid));
+        void* comm = nullptr;
+        int r = api.CommInitRank(&comm, nr, uid, rank);
+        if (r != 0) FAIL(SPCSC_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+        nccl = &api;
+        nccl_comm = comm;
+        nranks = nr;
+        global_nx = gnx;
+        prm.n_x = gnx > 0.0 ? gnx : (double)nreal;
+        return SPCSC_OK;
+    }
+
     int synchronize() override {
         CK(cudaSetDevice(pb.device));
         CK(cudaStreamSynchronize(stream));
@@ -888,6 +962,20 @@ int spcsc_destroy(spcsc_handle* h) {
     return (expr)
 
 int spcsc_synchronize(spcsc_handle* h) { H_CALL(h->synchronize()); }
+int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {
+    if (!id128) { g_last_error = "null id buffer"; return SPCSC_ERR_INVALID; }
+    NcclApi& api = nccl_api(nccl_lib);
+    if (!api.ok) { g_last_error = api.err; return SPCSC_ERR_NCCL; }
+    NcclApi::UniqueId uid;
+    int r = api.GetUniqueId(&uid);
+    if (r != 0) { g_last_error = std::string("ncclGetUniqueId: ") + api.GetErrorString(r); return SPCSC_ERR_NCCL; }
+    memcpy(id128, &uid, sizeof(uid));
+    return SPCSC_OK;
+}
+int spcsc_comm_init(spcsc_handle* h, const char* nccl_lib, const void* id128, int32_t rank,
+                    int32_t nranks, double global_nx) {
+    H_CALL(id128 ? h->comm_init(nccl_lib, id128, rank, nranks, global_nx) : SPCSC_ERR_INVALID);
+}
 int spcsc_set_dict(spcsc_handle* h, const void* D) { H_CALL(D ? h->set_dict(D) : SPCSC_ERR_INVALID); }
 int spcsc_set_signal(spcsc_handle* h, const void* S) { H_CALL(S ? h->set_signal(S) : SPCSC_ERR_INVALID); }
 int spcsc_set_l1_weight(spcsc_handle* h, const void* w, const int64_t shape[5]) {

@@ -1,0 +1,50 @@
+"""Run under torchrun with 2 ranks (one GPU each): sporco_b200 with the batch sharded over
+the ranks against the single-object oracle on the whole batch."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rank = int(os.environ['RANK'])
+    world = int(os.environ['WORLD_SIZE'])
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rng = np.random.default_rng(77)
+    D = rng.standard_normal((8, 8, 16)).astype(np.float32)
+    S = rng.standard_normal((128, 128, 6)).astype(np.float32)
+    per = S.shape[2] // world
+    mine = list(range(rank * per, (rank + 1) * per))
+    opt = {'MaxMainIter': 20, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDN(D, S[:, :, mine], 0.1, cbpdn.ConvBPDN.Options(opt), dimK=1, device=local)
+    b.attach_process_group(dist)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=opt, dimK=1)
+    err = np.linalg.norm((Y - r.Y[:, :, :, mine, :]).ravel()) / np.linalg.norm(r.Y[:, :, :, mine, :].ravel())
+    rho = np.array(b.getitstat().Rho, dtype=np.float64)
+    rho_ref = np.array([row[8] for row in r.itstat], dtype=np.float64)
+    rho_err = np.abs(rho - rho_ref).max() / np.abs(rho_ref).max()
+    obj = np.array(b.getitstat().ObjFun, dtype=np.float64)
+    obj_ref = np.array([row[1] for row in r.itstat], dtype=np.float64)
+    obj_err = np.abs(obj - obj_ref).max() / np.abs(obj_ref).max()
+    ok = err < 3e-4 and rho_err < 1e-4 and obj_err < 1e-4
+    t = torch.tensor([1.0 if ok else 0.0], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    print('rank %d: Y err %.3e rho err %.3e obj err %.3e' % (rank, err, rho_err, obj_err), flush=True)
+    if rank == 0 and t.item() == 1.0:
+        print('MULTI_GPU_OK', flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == '__main__':
+    main()
