@@ -240,6 +240,17 @@ def run_b200(args):
             'kernels': kern}
 
     # ---- end to end through the public class: host arrays in, coefficient maps out
+    # (one untimed pass first: it fills the library's device / pinned allocation pools, which a
+    #  long-lived process pays for once)
+    wopt = dict(opt)
+    wopt['MaxMainIter'] = 3
+    bw = cbpdn.ConvBPDN(D, S, LMBDA, cbpdn.ConvBPDN.Options(wopt), dimK=1, device=local_rank)
+    if world > 1:
+        bw.attach_process_group(dist)
+    Yw = bw.solve()
+    del bw, Yw
+    import gc
+    gc.collect()
     barrier()
     t0 = time.perf_counter()
     b2 = cbpdn.ConvBPDN(D, S, LMBDA, cbpdn.ConvBPDN.Options(opt), dimK=1, device=local_rank)

@@ -80,8 +80,27 @@ typedef enum spcsc_array {
     SPCSC_ARR_Y = 0, SPCSC_ARR_U = 1, SPCSC_ARR_X = 2,      /* real, (N0,N1,Cx,K,M) */
     SPCSC_ARR_XF = 3,                                       /* complex, (N0,N1f,Cx,K,M) */
     SPCSC_ARR_DF = 4,                                       /* complex, (N0,N1f,Cd,1,M) */
-    SPCSC_ARR_SF = 5                                        /* complex, (N0,N1f,C,K,1) */
+    SPCSC_ARR_SF = 5,                                       /* complex, (N0,N1f,C,K,1) */
+    SPCSC_ARR_PGM_X = 6,                                    /* PGM iterate X, real (N0,N1,Cx,K,M) */
+    SPCSC_ARR_PGM_XF = 7, SPCSC_ARR_PGM_YF = 8              /* PGM Xf / Yf, complex (N0,N1f,Cx,K,M) */
 } spcsc_array;
+
+/* Options of the PGM/FISTA solver that reach the device (pgm/cbpdn.py:115-118, 288-298). */
+typedef struct spcsc_pgm_opts {
+    double lmbda;
+    int32_t nonneg, no_bndry_cross;
+} spcsc_pgm_opts;
+
+/* What one proximal-gradient trial reports (all sums over the stored half spectrum):
+   [0] F  = obfn_f(Xf)  = 1/2 sum |sum_m Df Xf - Sf|^2, unweighted     pgm/cbpdn.py:358-370
+   [1] FY = obfn_f(Yf)                                                  backtrack.py:93
+   [2] lin = sum Re(conj(Xf - Yf) gradY)                                pgm/pgm.py:886-894
+   [3] dxy2 = sum |Xf - Yf|^2                                           backtrack.py:95
+   [4] rsdl = rfl2norm2(Xf - Yf)  (Hermitian weights, 1/N)             pgm/cbpdn.py:314-318
+   [5] dfid = rfl2norm2(sum_m Df Xf - Sf)/2                             pgm/cbpdn.py:334-344
+   [6] regl1 = ||wl1 * X||_1                                            pgm/cbpdn.py:348-354 */
+enum { SPCSC_PGM_F = 0, SPCSC_PGM_FY = 1, SPCSC_PGM_LIN = 2, SPCSC_PGM_DXY2 = 3,
+       SPCSC_PGM_RSDL = 4, SPCSC_PGM_DFID = 5, SPCSC_PGM_REGL1 = 6, SPCSC_PGM_NOUT = 8 };
 
 /* ---- library / device queries (stand-ins for sporco_cuda.util, docs/source/modules/sporco.cuda.rst:60-104) */
 int spcsc_version(void);
@@ -128,16 +147,39 @@ int spcsc_admm_last_timing(spcsc_handle* h, float* elapsed_ms, int64_t* launches
    Measurement aid for bench.py (same kernels, same stream as spcsc_admm_iterate). */
 int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]);
 
+/* ---- PGM / FISTA solver (sporco.pgm.cbpdn.ConvBPDN).  The host keeps the scalar control flow
+   of pgm/pgm.py:328-370 and pgm/backtrack.py:74-107 (step size L, momentum t, F <= Q test);
+   each call below is one batch of kernels. */
+int spcsc_pgm_configure(spcsc_handle* h, const spcsc_pgm_opts* opts);
+/* X = X0 (NULL: zeros), Xf = Yf = rfftn(X).                           pgm/cbpdn.py:217-241 */
+int spcsc_pgm_reset(spcsc_handle* h, const void* X0);
+/* One proximal step from the current Yf with step 1/L (grad_f, PGMDFT.xstep): candidate X, Xf
+   are kept on the device, the sums needed for the stopping / backtracking tests come back. */
+int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]);
+/* Accept the candidate and take the momentum step Yf = Xf + coef (Xf - Xfprv)  (PGMDFT.ystep). */
+int spcsc_pgm_accept(spcsc_handle* h, double coef);
+
 /* ---- multi-GPU: images are sharded over ranks (one process per GPU); the only exchange of
    the path is the all-reduce of the residual / objective sums that drive the shared rho and the
    stopping test (admm/admm.py:462-486 are global over all K images).  NCCL is resolved at run
    time from `nccl_lib` (path or soname of the libnccl the process already uses).
    spcsc_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller broadcasts it.
-   spcsc_comm_init: collective over all ranks; `global_nx` = total number of coefficient
-   elements over all ranks (sets the AbsStopTol scaling, admm/admm.py:481-484). */
+   The caller broadcasts it and every rank creates its communicator from it. */
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128);
-int spcsc_comm_init(spcsc_handle* h, const char* nccl_lib, const void* id128, int32_t rank,
-                    int32_t nranks, double global_nx);
+typedef struct spcsc_comm spcsc_comm;
+/* Collective over all ranks (ncclCommInitRank); a communicator can serve any number of handles. */
+int spcsc_comm_create(const char* nccl_lib, const void* id128, int32_t rank, int32_t nranks,
+                      int32_t device, spcsc_comm** out);
+int spcsc_comm_destroy(spcsc_comm* c);
+/* `global_nx` = total number of coefficient elements over all ranks (sets the AbsStopTol
+   scaling, admm/admm.py:481-484).  `c` must outlive the handle's iterations. */
+int spcsc_attach_comm(spcsc_handle* h, spcsc_comm* c, double global_nx);
+
+/* ---- host memory: page-locked buffers for results (direct DMA on spcsc_get_array); device
+   and pinned allocations are pooled per process, spcsc_trim_pools() returns them to CUDA. */
+int spcsc_host_alloc(uint64_t bytes, void** out);
+int spcsc_host_free(void* p);
+int spcsc_trim_pools(void);
 
 /* ---- state access */
 int spcsc_get_array(spcsc_handle* h, int32_t which, void* host_out);

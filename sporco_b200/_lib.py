@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libspcsc.so')
 
 F32, F64 = 0, 1
-ARR_Y, ARR_U, ARR_X, ARR_XF, ARR_DF, ARR_SF = range(6)
+ARR_Y, ARR_U, ARR_X, ARR_XF, ARR_DF, ARR_SF, ARR_PGM_X, ARR_PGM_XF, ARR_PGM_YF = range(9)
 
 # every symbol include/spcsc.h declares (tests check the list against the header)
 SYMBOLS = (
@@ -23,7 +23,10 @@ SYMBOLS = (
     'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_set_iter',
     'spcsc_admm_iterate',
     'spcsc_admm_get_scalars', 'spcsc_admm_last_timing', 'spcsc_admm_profile', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
-    'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_init',
+    'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
+    'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
+    'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
+    'spcsc_pgm_accept',
 )
 
 
@@ -47,6 +50,11 @@ class AdmmOpts(ctypes.Structure):
                [(n, ctypes.c_int32) for n in
                 ('ar_enabled', 'ar_period', 'ar_autoscaling', 'ar_std_residuals', 'joint',
                  'nonneg', 'no_bndry_cross', 'fast_solve', 'aux_var_obj', 'linsolve_check')]
+
+
+class PgmOpts(ctypes.Structure):
+    _fields_ = [('lmbda', ctypes.c_double), ('nonneg', ctypes.c_int32),
+                ('no_bndry_cross', ctypes.c_int32)]
 
 
 class ItStat(ctypes.Structure):
@@ -88,8 +96,16 @@ def _declare(lib):
     lib.spcsc_get_array.argtypes = [vp, i32, vp]
     lib.spcsc_set_array.argtypes = [vp, i32, vp]
     lib.spcsc_reconstruct.argtypes = [vp, vp, vp]
+    lib.spcsc_pgm_configure.argtypes = [vp, ctypes.POINTER(PgmOpts)]
+    lib.spcsc_pgm_reset.argtypes = [vp, vp]
+    lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
     lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
-    lib.spcsc_comm_init.argtypes = [vp, ctypes.c_char_p, vp, i32, i32, ctypes.c_double]
+    lib.spcsc_comm_create.argtypes = [ctypes.c_char_p, vp, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.spcsc_comm_destroy.argtypes = [vp]
+    lib.spcsc_attach_comm.argtypes = [vp, vp, ctypes.c_double]
+    lib.spcsc_host_alloc.argtypes = [ctypes.c_uint64, ctypes.POINTER(vp)]
+    lib.spcsc_host_free.argtypes = [vp]
     lib.spcsc_rfft2.argtypes = [i32, i32, i32, i32, i32, vp, vp]
     lib.spcsc_irfft2.argtypes = [i32, i32, i32, i32, i32, vp, vp]
     for name in SYMBOLS:
@@ -252,9 +268,9 @@ class Handle(object):
     def get_array(self, which):
         d = self.dims
         N1f = d['N1'] // 2 + 1
-        if which in (ARR_Y, ARR_U, ARR_X):
-            out = np.empty(self.xshape(), dtype=self.dtype)
-        elif which == ARR_XF:
+        if which in (ARR_Y, ARR_U, ARR_X, ARR_PGM_X):
+            out = pinned_empty(self.xshape(), self.dtype)
+        elif which in (ARR_XF, ARR_PGM_XF, ARR_PGM_YF):
             out = np.empty((d['N0'], N1f, self.Cx, d['K'], d['M']), dtype=self.cdtype)
         elif which == ARR_DF:
             out = np.empty((d['N0'], N1f, d['Cd'], 1, d['M']), dtype=self.cdtype)
@@ -282,10 +298,61 @@ class Handle(object):
     def synchronize(self):
         self._c(self.lib.spcsc_synchronize(self.h))
 
-    def comm_init(self, nccl_lib, uid, rank, nranks, global_nx):
+    def pgm_configure(self, lmbda, nonneg, no_bndry_cross):
+        o = PgmOpts(float(lmbda), int(bool(nonneg)), int(bool(no_bndry_cross)))
+        self._c(self.lib.spcsc_pgm_configure(self.h, ctypes.byref(o)))
+
+    def pgm_reset(self, X0=None):
+        if X0 is None:
+            self._c(self.lib.spcsc_pgm_reset(self.h, None))
+        else:
+            X0 = self._host(X0, self.xshape())
+            self._c(self.lib.spcsc_pgm_reset(self.h, _ptr(X0)))
+
+    def pgm_trial(self, L):
+        out = (ctypes.c_double * 8)()
+        self._c(self.lib.spcsc_pgm_trial(self.h, float(L), out))
+        return [out[i] for i in range(8)]
+
+    def pgm_accept(self, coef):
+        self._c(self.lib.spcsc_pgm_accept(self.h, float(coef)))
+
+    def attach_comm(self, comm, global_nx):
+        self._comm = comm                      # keep the communicator alive
+        self._c(self.lib.spcsc_attach_comm(self.h, comm.c if comm is not None else None,
+                                           float(global_nx)))
+
+
+class Comm(object):
+    """An NCCL communicator owned by libspcsc (one per process group and device)."""
+
+    def __init__(self, nccl_lib, uid, rank, nranks, device):
+        self.lib = load()
         buf = (ctypes.c_char * 128).from_buffer_copy(bytes(uid))
-        self._c(self.lib.spcsc_comm_init(self.h, nccl_lib.encode(), buf, rank, nranks,
-                                         float(global_nx)))
+        c = ctypes.c_void_p()
+        check(self.lib.spcsc_comm_create(nccl_lib.encode(), buf, rank, nranks, device,
+                                         ctypes.byref(c)))
+        self.c = c
+        self.rank, self.nranks = rank, nranks
+
+    def close(self):
+        if getattr(self, 'c', None):
+            self.lib.spcsc_comm_destroy(self.c)
+            self.c = None
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory from the library's pool (returned to the pool
+    when the array is garbage collected)."""
+    import weakref
+    lib = load()
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    p = ctypes.c_void_p()
+    check(lib.spcsc_host_alloc(max(nbytes, 1), ctypes.byref(p)))
+    raw = (ctypes.c_byte * max(nbytes, 1)).from_address(p.value)
+    weakref.finalize(raw, lib.spcsc_host_free, ctypes.c_void_p(p.value))
+    return np.frombuffer(raw, dtype=dt, count=int(np.prod(shape))).reshape(shape)
 
 
 def rfft2(x, device=0):

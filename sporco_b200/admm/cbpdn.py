@@ -18,6 +18,9 @@ from .. import _lib, cnvrep as cr, common
 from . import admm
 
 
+_COMMS = {}     # (process group, device, world size) -> _lib.Comm, created once per process
+
+
 class GenericConvBPDN(admm.ADMMEqual):
     """Base of the convolutional BPDN solvers (mirror of sporco/admm/cbpdn.py:30-380)."""
 
@@ -213,16 +216,22 @@ class GenericConvBPDN(admm.ADMMEqual):
         only carries the 128-byte NCCL id and the element count."""
         import torch
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        nccl_lib = _lib.nccl_library_path()
         dev = torch.device('cuda', self._device)
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(_lib.comm_unique_id(nccl_lib)),
-                                   dtype=torch.uint8).to(dev)
-        dist.broadcast(uid, src=0, group=group)
+        key = (id(group), self._device, world)
+        comm = _COMMS.get(key)
+        if comm is None:
+            nccl_lib = _lib.nccl_library_path()
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(_lib.comm_unique_id(nccl_lib)),
+                                       dtype=torch.uint8).to(dev)
+            dist.broadcast(uid, src=0, group=group)
+            comm = _lib.Comm(nccl_lib, bytes(uid.cpu().numpy().tobytes()), rank, world,
+                             self._device)
+            _COMMS[key] = comm
         nx = torch.tensor([float(self.Nx)], dtype=torch.float64, device=dev)
         dist.all_reduce(nx, group=group)
-        self._h.comm_init(nccl_lib, bytes(uid.cpu().numpy().tobytes()), rank, world, float(nx.item()))
+        self._h.attach_comm(comm, float(nx.item()))
         self._world = world
 
     # ---- pickling: device state travels as host arrays

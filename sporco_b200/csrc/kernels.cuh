@@ -25,7 +25,8 @@ namespace spcsc {
 // Device-resident solver scalars.
 // ------------------------------------------------------------------------------------
 enum { ACC_X2 = 0, ACC_Y2, ACC_U2, ACC_R2, ACC_S2, ACC_L1, ACC_L21, ACC_DFID,
-       ACC_AX2, ACC_B2, ACC_AXB2, ACC_N = 16 };
+       ACC_AX2, ACC_B2, ACC_AXB2, ACC_PGM_FY, ACC_PGM_F, ACC_PGM_LIN, ACC_PGM_DXY2,
+       ACC_PGM_RSDL, ACC_N = 16 };
 
 template <typename T>
 struct AdmmState {
@@ -296,8 +297,12 @@ SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRI
 // ------------------------------------------------------------------------------------
 // k_col: one CTA per (wf, b) slab of M columns x N0.
 //   DO_FWD   : forward FFT along the column before the solve
-//   SOLVE    : 0 none, 1 ADMM  q = (rho I + G)^-1 (Sf - s),  2 gradient  q = (Sf - s)/L,
-//              3 sum only: write s_c = sum_m Df_c * col to `sumout` ([nb][Cd][N1f][N0])
+//   SOLVE    : 0 none, 1 ADMM  q = (rho I + G)^-1 (Sf - s),  2 gradient  q = (Sf - s)/L
+//              (PGM: also stores s in `sumout` and accumulates sum|Sf - s|^2),
+//              3 sum only: write s_c = sum_m Df_c * col to `sumout` ([nb][Cd][N1f][N0]),
+//              4 PGM evaluation of a candidate Xf: no update; accumulates sum|s - Sf|^2 (plain and
+//                Hermitian-weighted), sum Re(conj(s - sY)(sY - Sf)) with sY read from `sumin`,
+//                and sum|Xf - Yf|^2 (plain and weighted) against the slabs in `ref`
 //   DO_INV   : inverse FFT (unnormalised) along the column after the update
 //   out = in + sum_c conj(Df_c) q_c       with s_c = sum_m Df_c[m] in[m]
 // The slab is processed in chunks of MC columns that fit shared memory; when the whole
@@ -350,6 +355,7 @@ template <typename T, int N0, bool DO_FWD, int SOLVE, bool DO_INV>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out,
                         const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
                         const C2<T>* SPCSC_RESTRICT G, C2<T>* SPCSC_RESTRICT sumout,
+                        const C2<T>* SPCSC_RESTRICT sumin, const C2<T>* SPCSC_RESTRICT ref,
                         const AdmmState<T>* SPCSC_RESTRICT st, T Lstep,
                         double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
                         ColArgs a) {
@@ -391,6 +397,8 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
         }
         // ---- q_c[h]
         double dsum[1] = {0.0};
+        double psum[3] = {0.0, 0.0, 0.0};            // PGM: plain |s-Sf|^2, weighted, linear term
+        const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
         const int k = b / a.Cx, cx = b - k * a.Cx;
         for (int h = tid; h < N0; h += nt) {
             C2<T> d[MAXCD];
@@ -403,6 +411,18 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                     const int cs = (Cd > 1) ? c : cx;
                     const C2<T> sf = Sf[(((size_t)k * a.Cs + cs) * a.N1f + wf) * N0 + h];
                     d[c] = sf - s;
+                    if (SOLVE == 2 && sumout) {
+                        sumout[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h] = s;
+                        psum[0] += (double)abs2(d[c]);
+                    }
+                    if (SOLVE == 4) {
+                        const C2<T> sy = sumin[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h];
+                        const double e2 = (double)abs2(d[c]);
+                        psum[0] += e2;
+                        psum[1] += wgt * e2;
+                        const C2<T> dx = s - sy, gy = sy - sf;       // Re(conj(dx) * gy)
+                        psum[2] += (double)(dx.re * gy.re + dx.im * gy.im);
+                    }
                 }
             }
             if (SOLVE == 1) {
@@ -421,7 +441,6 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                     hpd_solve<T, MAXCD>(A, d, Cd);
                 }
                 if (a.dfid_on) {
-                    const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
                     double q2 = 0.0;
                     for (int c = 0; c < Cd; ++c) q2 += (double)abs2(d[c]);
                     dsum[0] += wgt * q2;
@@ -432,6 +451,8 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             if (SOLVE == 3) {
                 for (int c = 0; c < Cd; ++c)
                     sumout[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h] = d[c];
+            } else if (SOLVE == 4) {
+                // nothing to keep: the evaluation does not update the slab
             } else {
                 for (int c = 0; c < Cd; ++c) spart[((size_t)c * parts) * N0 + h] = d[c];
             }
@@ -440,6 +461,18 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
         if (SOLVE == 1 && a.dfid_on) {
             double* red = reinterpret_cast<double*>(spart + (size_t)Cd * parts * N0);
             block_accumulate<1>(dsum, red, acc + ACC_DFID);
+        }
+        if (SOLVE == 2 && sumout) {
+            double* red = reinterpret_cast<double*>(spart + (size_t)Cd * parts * N0);
+            double one[1] = {psum[0]};
+            block_accumulate<1>(one, red, acc + ACC_PGM_FY);
+        }
+        if (SOLVE == 4) {
+            double* red = reinterpret_cast<double*>(spart + (size_t)Cd * parts * N0);
+            double a1[1] = {psum[0]}, a2[1] = {psum[1]}, a3[1] = {psum[2]};
+            block_accumulate<1>(a1, red, acc + ACC_PGM_F);
+            block_accumulate<1>(a2, red, acc + ACC_DFID);
+            block_accumulate<1>(a3, red, acc + ACC_PGM_LIN);
         }
         if (SOLVE == 3) return;
     }
@@ -465,9 +498,91 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             }
             __syncthreads();
         }
+        if (SOLVE == 4) {
+            const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+            double dd[1] = {0.0};
+            const C2<T>* rs = ref + slab;
+            for (int e = tid; e < mc * N0; e += nt)
+                dd[0] += (double)abs2(buf[e] - rs[(size_t)m0 * N0 + e]);
+            double* red = reinterpret_cast<double*>(spart + (size_t)Cd * a.parts * N0);
+            block_accumulate<1>(dd, red, acc + ACC_PGM_DXY2);
+            dd[0] *= wgt;
+            block_accumulate<1>(dd, red, acc + ACC_PGM_RSDL);
+        }
         if (DO_INV) col_fft_chunk<T, N0, true>(buf, tw, mc, MC);
         for (int e = tid; e < mc * N0; e += nt) dst[(size_t)m0 * N0 + e] = buf[e];
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// PGM proximal step in the row domain (pgm/pgm.py:796-800, pgm/cbpdn.py:288-298):
+//   V = irfft_row(Vt)*scale ; X = prox_l1(V, (lmbda/L) wl1) [+NonNeg, NoBndryCross] ;
+//   Xt = rfft_row(X)   written over Vt;  X stored; RegL1 accumulated.
+// ------------------------------------------------------------------------------------
+template <typename T, int H>
+SPCSC_GLOBAL void k_row_inv_prox_fwd(C2<T>* SPCSC_RESTRICT Vt, T* SPCSC_RESTRICT X, T thr_scale,
+                                     WeightView<T> wl1, double* SPCSC_RESTRICT acc,
+                                     const C2<T>* SPCSC_RESTRICT tw, int N0, int M, int Cx, int TR,
+                                     T scale, int nonneg, int bnd0, int bnd1) {
+    SPCSC_DYN_SMEM(smem_raw);
+    C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);
+    constexpr int P = H + 1;
+    constexpr int TPF = fft_tpf<T, H>();
+    constexpr int N1f = H + 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
+    const int k = b / Cx, c = b - k * Cx;
+    row_inverse_to_smem<T, H>(buf, Vt, tw, b, m, h0, N0, M, TR);
+    __syncthreads();
+    double sums[1] = {0.0};
+    C2<T>* X2 = reinterpret_cast<C2<T>*>(X) + (((size_t)b * M + m) * N0 + h0) * H;
+    for (int e = tid; e < TR * H; e += nt) {
+        const int r = e / H, j = e - r * H;
+        const int h = h0 + r;
+        const C2<T> z = buf[r * P + j];
+        T xs[2] = {z.re * scale, z.im * scale};
+        SPCSC_UNROLL
+        for (int q = 0; q < 2; ++q) {
+            const T w1 = wl1.p[(size_t)k * wl1.sk + (size_t)c * wl1.sc + (size_t)m * wl1.sm +
+                              (size_t)h * wl1.s0 + (size_t)(2 * j + q) * wl1.s1];
+            T x = soft_threshold(xs[q], thr_scale * w1);
+            if (nonneg && x < (T)0) x = (T)0;
+            if (h >= bnd0 || (2 * j + q) >= bnd1) x = (T)0;
+            xs[q] = x;
+            sums[0] += (double)fabs(w1 * x);
+        }
+        X2[e] = mk<T>(xs[0], xs[1]);
+        buf[r * P + j] = mk<T>(xs[0], xs[1]);
+    }
+    __syncthreads();
+    {
+        const int row = tid / TPF, t = tid - row * TPF;
+        const bool active = row < TR;
+        fft_smem<T, H, false, 2>(buf + (active ? row : 0) * P, t, tw, active);
+    }
+    C2<T>* out = Vt + (((size_t)b * N1f) * M + m) * N0 + h0;
+    const size_t wstride = (size_t)M * N0;
+    for (int e = tid; e < TR * N1f; e += nt) {
+        const int wf = e / TR, r = e - wf * TR;
+        const C2<T> aa = buf[r * P + (wf == H ? 0 : wf)];
+        const C2<T> bb = conj(buf[r * P + (wf == 0 ? 0 : H - wf)]);
+        const C2<T> w = tw[wf];
+        const C2<T> sum = aa + bb, dif = mul_mi((aa - bb) * w);
+        out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+    }
+    double* red = reinterpret_cast<double*>(smem_raw);
+    block_accumulate<1>(sums, red, acc + ACC_L1);
+}
+
+// Momentum step in the frequency domain (pgm/pgm.py:815-831): Yf = Xf + coef (Xf - Xfprv).
+template <typename T>
+SPCSC_GLOBAL void k_pgm_momentum(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* SPCSC_RESTRICT Xfprv,
+                                 C2<T>* SPCSC_RESTRICT Yf, T coef, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const C2<T> x = Xf[i], p = Xfprv[i];
+        Yf[i] = mk<T>(x.re + coef * (x.re - p.re), x.im + coef * (x.im - p.im));
     }
 }
 

@@ -34,7 +34,8 @@ enum ColMode {
     COL_ADMM_NOFFT = 3, // solve only (input and output in the full 2-D frequency domain)
     COL_GRAD_INV = 4,   // gradient step (q = (Sf - s)/L) then inverse   [PGM]
     COL_FWD_SUM = 5,    // forward, write s_c = sum_m Df_c X
-    COL_SUM = 6         // write s_c = sum_m Df_c X (input already in frequency domain)
+    COL_SUM = 6,        // write s_c = sum_m Df_c X (input already in frequency domain)
+    COL_FWD_EVAL = 7    // forward, then PGM evaluation sums of the candidate (k_col SOLVE 4)
 };
 
 template <typename T>
@@ -45,6 +46,8 @@ struct ColLaunch {
     const C2<T>* Sf;
     const C2<T>* G;
     C2<T>* sumout;
+    const C2<T>* sumin;          // PGM: per-frequency sums of the current Yf
+    const C2<T>* ref;            // PGM: Yf slabs the candidate is compared with
     const AdmmState<T>* st;
     T Lstep;
     double* acc;
@@ -64,6 +67,16 @@ cudaError_t row_inv_launch(const RowArgs<T>& r, const C2<T>* Zt, T* X, T scale);
 template <typename T, int H>
 cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
                                 T* U, const AdmmState<T>* st);
+template <typename T>
+struct PgmRowArgs {
+    T thr_scale;                 // lmbda / L
+    WeightView<T> wl1;
+    double* acc;
+    T scale;
+    int nonneg, bnd0, bnd1;
+};
+template <typename T, int H>
+cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt, T* X);
 // columns
 template <typename T, int N0>
 cudaError_t col_launch(int mode, ColLaunch<T> c);

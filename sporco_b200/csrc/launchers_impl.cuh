@@ -53,6 +53,17 @@ cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const
     }
 }
 
+template <typename T, int H>
+cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt, T* X) {
+    constexpr int TPF = fft_tpf<T, H>();
+    const int nt = round_up32(r.TR * TPF);
+    size_t smem = (size_t)r.TR * (H + 1) * sizeof(C2<T>);
+    if (smem < 32 * sizeof(double)) smem = 32 * sizeof(double);
+    dim3 grid(r.N0 / r.TR, r.M, r.nb);
+    return launch(k_row_inv_prox_fwd<T, H>, grid, dim3(nt), smem, r.stream, Vt, X, p.thr_scale, p.wl1,
+                  p.acc, r.tw, r.N0, r.M, r.Cx, r.TR, p.scale, p.nonneg, p.bnd0, p.bnd1);
+}
+
 // Choose threads / chunking for the column kernel.
 template <typename T, int N0>
 inline void col_plan(ColArgs& a, int& nthreads, size_t& smem) {
@@ -84,7 +95,7 @@ static cudaError_t col_go(ColLaunch<T>& c) {
     col_plan<T, N0>(c.a, nt, smem);
     dim3 grid(c.a.N1f, c.nb);
     return launch(k_col<T, N0, F, S, I>, grid, dim3(nt), smem, c.stream, c.in, c.out, c.Df, c.Sf,
-                  c.G, c.sumout, c.st, c.Lstep, c.acc, c.tw, c.a);
+                  c.G, c.sumout, c.sumin, c.ref, c.st, c.Lstep, c.acc, c.tw, c.a);
 }
 
 template <typename T, int N0>
@@ -98,6 +109,7 @@ cudaError_t col_launch(int mode, ColLaunch<T> c) {
         case COL_GRAD_INV: return col_go<T, N0, false, 2, true>(c);
         case COL_FWD_SUM: return col_go<T, N0, true, 3, false>(c);
         case COL_SUM: return col_go<T, N0, false, 3, false>(c);
+        case COL_FWD_EVAL: return col_go<T, N0, true, 4, false>(c);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -15,6 +15,8 @@ namespace spcsc {
     template cudaError_t row_inv_prox_launch<T, SPCSC_SIZE>(const RowArgs<T>&,                 \
                                                             const ProxArgs<T>&, const C2<T>*,  \
                                                             T*, T*, const AdmmState<T>*);      \
+    template cudaError_t row_inv_prox_fwd_launch<T, SPCSC_SIZE>(const RowArgs<T>&,             \
+                                                                const PgmRowArgs<T>&, C2<T>*, T*); \
     template cudaError_t col_launch<T, SPCSC_SIZE>(int, ColLaunch<T>);
 
 SPCSC_INST(float)

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "launchers.cuh"
@@ -65,6 +66,16 @@ static cudaError_t row_inv_prox(int H, const RowArgs<T>& r, const ProxArgs<T>& p
                                 T* Y, T* U, const AdmmState<T>* st) {
     switch (H) {
 #define X(n) case n: return row_inv_prox_launch<T, n>(r, p, Zt, Y, U, st);
+        SPCSC_FOR_SIZES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T>
+static cudaError_t row_inv_prox_fwd(int H, const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt,
+                                    T* Xo) {
+    switch (H) {
+#define X(n) case n: return row_inv_prox_fwd_launch<T, n>(r, p, Vt, Xo);
         SPCSC_FOR_SIZES(X)
 #undef X
     }
@@ -139,6 +150,67 @@ SPCSC_GLOBAL void k_freq_to_ext(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RES
 
 using namespace spcsc;
 
+// ---- process-wide allocation pools ----------------------------------------------------
+// cudaMalloc / cudaHostAlloc of the 0.5 GB arrays of a solver cost tens of milliseconds; a
+// solver that is rebuilt (dictionary learning, repeated solves) gets its buffers back from here.
+#include <map>
+#include <mutex>
+namespace {
+struct MemPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_;          // size -> block
+    std::map<void*, std::pair<size_t, int>> live; // block -> (size, device)
+    bool host;
+    explicit MemPool(bool h) : host(h) {}
+    static size_t round(size_t n) {
+        const size_t g = n >= (1u << 20) ? (1u << 20) : 512;
+        return (n + g - 1) / g * g;
+    }
+    cudaError_t alloc(void** p, size_t bytes, int device) {
+        const size_t want = round(bytes ? bytes : 1);
+        {
+            std::lock_guard<std::mutex> l(mu);
+            for (auto it = free_.lower_bound(want); it != free_.end() && it->first <= want + want / 4; ++it) {
+                auto lv = live.find(it->second);
+                if (lv != live.end() && lv->second.second == device) {
+                    *p = it->second;
+                    free_.erase(it);
+                    return cudaSuccess;
+                }
+            }
+        }
+        void* q = nullptr;
+        cudaError_t e = host ? cudaMallocHost(&q, want) : cudaMalloc(&q, want);
+        if (e != cudaSuccess) {
+            trim();
+            e = host ? cudaMallocHost(&q, want) : cudaMalloc(&q, want);
+            if (e != cudaSuccess) return e;
+        }
+        std::lock_guard<std::mutex> l(mu);
+        live[q] = std::make_pair(want, device);
+        *p = q;
+        return cudaSuccess;
+    }
+    void release(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> l(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        free_.insert(std::make_pair(it->second.first, p));
+    }
+    void trim() {
+        std::lock_guard<std::mutex> l(mu);
+        for (auto& kv : free_) {
+            if (host) cudaFreeHost(kv.second); else cudaFree(kv.second);
+            live.erase(kv.second);
+        }
+        free_.clear();
+    }
+};
+MemPool& dev_pool() { static MemPool* p = new MemPool(false); return *p; }
+MemPool& host_pool() { static MemPool* p = new MemPool(true); return *p; }
+}  // namespace
+
 // ---- NCCL, resolved at run time (no link-time dependency) ---------------------------------
 namespace {
 struct NcclApi {
@@ -178,6 +250,12 @@ NcclApi& nccl_api(const char* libname) {
 
 static thread_local std::string g_last_error;
 
+struct spcsc_comm {
+    void* comm = nullptr;
+    NcclApi* api = nullptr;
+    int rank = 0, nranks = 1, device = 0;
+};
+
 struct spcsc_handle {
     std::string err;
     bool poisoned = false;
@@ -198,7 +276,11 @@ struct spcsc_handle {
     virtual int set_array(int which, const void* in) = 0;
     virtual int reconstruct(const void* X, void* out) = 0;
     virtual int synchronize() = 0;
-    virtual int comm_init(const char* lib, const void* id, int rank, int nranks, double global_nx) = 0;
+    virtual int attach_comm(spcsc_comm* c, double global_nx) = 0;
+    virtual int pgm_configure(const spcsc_pgm_opts* o) = 0;
+    virtual int pgm_reset(const void* X0) = 0;
+    virtual int pgm_trial(double L, double* out) = 0;
+    virtual int pgm_accept(double coef) = 0;
 };
 
 namespace {
@@ -225,15 +307,20 @@ struct DevBuf {
     size_t n = 0;
     cudaError_t ensure(size_t count) {
         if (count <= n) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        release();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        void* q = nullptr;
+        cudaError_t e = dev_pool().alloc(&q, count * sizeof(T), dev);
+        if (e == cudaSuccess) {
+            p = (T*)q;
+            n = count;
+        }
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaDeviceSynchronize();      // nothing in flight may still touch a pooled block
+        if (p) dev_pool().release(p);
         p = nullptr;
         n = 0;
     }
@@ -261,6 +348,9 @@ class Engine : public spcsc_handle {
     DevBuf<T> Y, U, tmp_real, wl1_buf, wl21_buf, staging;
     DevBuf<C2<T>> Zt, Zscratch, Xscratch, Df, Sf, G, tw_row, tw_col, sum_buf;
     DevBuf<C2<T>> stw_row1, stw_rowc, stw_col;     // stage twiddles of the v2 register plans
+    DevBuf<C2<T>> pgA, pgB;                         // PGM: accepted Xf (= Xfprv), Yf; Zt is the candidate
+    spcsc_pgm_opts popts;
+    bool pgm_ready = false, pgm_have_cand = false;
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
     int col_cpg = kCol2CPG;
     DevBuf<double> acc;
@@ -287,15 +377,17 @@ class Engine : public spcsc_handle {
         nslab = (size_t)K * Cx * N1f * M * N0;
         memset(&opts, 0, sizeof(opts));
         memset(&prm, 0, sizeof(prm));
+        memset(&popts, 0, sizeof(popts));
     }
     ~Engine() override {
         cudaSetDevice(pb.device);
+        if (stream) cudaStreamSynchronize(stream);
         Y.release(); U.release(); tmp_real.release(); wl1_buf.release(); wl21_buf.release();
         staging.release(); Zt.release(); Zscratch.release(); Xscratch.release(); Df.release();
         Sf.release(); G.release(); tw_row.release(); tw_col.release(); sum_buf.release();
         acc.release(); st.release(); rows.release();
         stw_row1.release(); stw_rowc.release(); stw_col.release();
-        if (nccl_comm && nccl) nccl->CommDestroy(nccl_comm);
+        pgA.release(); pgB.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -738,6 +830,15 @@ class Engine : public spcsc_handle {
                 if (rc) return rc;
                 return freq_out(Zscratch.p, out, Cx, K, M);
             }
+            case SPCSC_ARR_PGM_X:
+                if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "PGM state not initialised");
+                return from_internal(Y.p, out, Cx, K, M);
+            case SPCSC_ARR_PGM_XF:
+                if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "PGM state not initialised");
+                return freq_out(pgm_have_cand ? Zt.p : pgA.p, out, Cx, K, M);
+            case SPCSC_ARR_PGM_YF:
+                if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "PGM state not initialised");
+                return freq_out(pgB.p, out, Cx, K, M);
             case SPCSC_ARR_DF:
                 if (!have_dict) FAIL(SPCSC_ERR_STATE, "no dictionary set");
                 return freq_out(Df.p, out, Cd, 1, M);
@@ -795,21 +896,98 @@ class Engine : public spcsc_handle {
         return from_internal(rec, out, C, K, 1);
     }
 
-    int comm_init(const char* lib, const void* id, int rank, int nr, double gnx) override {
-        if (nr < 1 || rank < 0 || rank >= nr) FAIL(SPCSC_ERR_INVALID, "bad rank / nranks");
-        NcclApi& api = nccl_api(lib);
-        if (!api.ok) FAIL(SPCSC_ERR_NCCL, api.err);
+    int attach_comm(spcsc_comm* c, double gnx) override {
+        if (c && c->device != pb.device) FAIL(SPCSC_ERR_INVALID, "communicator belongs to another device");
+        nccl = c ? c->api : nullptr;
+        nccl_comm = c ? c->comm : nullptr;
+        nranks = c ? c->nranks : 1;
+        global_nx = c ? gnx : 0.0;
+        prm.n_x = global_nx > 0.0 ? global_nx : (double)nreal;
+        return SPCSC_OK;
+    }
+
+    // ---- PGM --------------------------------------------------------------------------
+    int pgm_configure(const spcsc_pgm_opts* o) override {
+        popts = *o;
+        return SPCSC_OK;
+    }
+    int pgm_reset(const void* X0) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!have_dict || !have_signal) FAIL(SPCSC_ERR_STATE, "pgm_reset before set_dict / set_signal");
+        if (Cd > 4) FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 dictionary channels");
         CK(cudaSetDevice(pb.device));
-        NcclApi::UniqueId uid;
-        memcpy(&uid, id, sizeof(uid));
-        void* comm = nullptr;
-        int r = api.CommInitRank(&comm, nr, uid, rank);
-        if (r != 0) FAIL(SPCSC_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
-        nccl = &api;
-        nccl_comm = comm;
-        nranks = nr;
-        global_nx = gnx;
-        prm.n_x = gnx > 0.0 ? gnx : (double)nreal;
+        CK(pgA.ensure(nslab));
+        CK(pgB.ensure(nslab));
+        CK(sum_buf.ensure((size_t)K * Cx * Cd * N1f * N0));
+        if (X0) {
+            int rc = to_internal(X0, Y.p, Cx, K, M);
+            if (rc) return rc;
+            rc = forward2d(Y.p, pgA.p, M, K * Cx);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(pgB.p, pgA.p, nslab * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
+        } else {
+            CK(cudaMemsetAsync(Y.p, 0, nreal * sizeof(T), stream));
+            CK(cudaMemsetAsync(pgA.p, 0, nslab * sizeof(C2<T>), stream));
+            CK(cudaMemsetAsync(pgB.p, 0, nslab * sizeof(C2<T>), stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        pgm_ready = true;
+        pgm_have_cand = false;
+        return SPCSC_OK;
+    }
+    int pgm_trial(double L, double* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "pgm_trial before pgm_reset");
+        if (!(L > 0.0)) FAIL(SPCSC_ERR_INVALID, "L must be positive");
+        CK(cudaSetDevice(pb.device));
+        CK(cudaMemsetAsync(acc.p, 0, ACC_N * sizeof(double), stream));
+        // gradient step + inverse column transform: Zt = icol( Yf - conj(Df)(sum_m Df Yf - Sf)/L )
+        ColLaunch<T> c1 = colargs(M, K * Cx);
+        c1.in = pgB.p; c1.out = Zt.p; c1.sumout = sum_buf.p; c1.acc = acc.p; c1.Lstep = (T)L;
+        CK(col<T>(N0, COL_GRAD_INV, c1));
+        // inverse rows, prox, forward rows
+        PgmRowArgs<T> pr;
+        pr.thr_scale = (T)popts.lmbda / (T)L;
+        pr.wl1 = wl1;
+        pr.acc = acc.p;
+        pr.scale = (T)(1.0 / ((double)N0 * (double)N1));
+        pr.nonneg = popts.nonneg;
+        pr.bnd0 = N0; pr.bnd1 = N1;
+        if (popts.no_bndry_cross) {
+            pr.bnd0 = pb.hd == 1 ? 0 : N0 - (pb.hd - 1);
+            pr.bnd1 = pb.wd == 1 ? 0 : N1 - (pb.wd - 1);
+        }
+        RowArgs<T> rr = rowargs(M, K * Cx, Cx);
+        rr.TR = row_tile<T>(H, N0, 1);
+        CK(row_inv_prox_fwd<T>(H, rr, pr, Zt.p, Y.p));
+        // forward columns + evaluation of the candidate against Yf
+        ColLaunch<T> c3 = colargs(M, K * Cx);
+        c3.in = Zt.p; c3.out = Zt.p; c3.sumin = sum_buf.p; c3.ref = pgB.p; c3.acc = acc.p;
+        CK(col<T>(N0, COL_FWD_EVAL, c3));
+        double hacc[ACC_N];
+        CK(cudaMemcpyAsync(hacc, acc.p, sizeof(hacc), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const double inv_n = 1.0 / ((double)N0 * (double)N1);
+        out[SPCSC_PGM_F] = 0.5 * hacc[ACC_PGM_F];
+        out[SPCSC_PGM_FY] = 0.5 * hacc[ACC_PGM_FY];
+        out[SPCSC_PGM_LIN] = hacc[ACC_PGM_LIN];
+        out[SPCSC_PGM_DXY2] = hacc[ACC_PGM_DXY2];
+        out[SPCSC_PGM_RSDL] = hacc[ACC_PGM_RSDL] * inv_n;
+        out[SPCSC_PGM_DFID] = 0.5 * hacc[ACC_DFID] * inv_n;
+        out[SPCSC_PGM_REGL1] = hacc[ACC_L1];
+        out[7] = 0.0;
+        pgm_have_cand = true;
+        return SPCSC_OK;
+    }
+    int pgm_accept(double coef) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!pgm_have_cand) FAIL(SPCSC_ERR_STATE, "pgm_accept without a candidate");
+        CK(cudaSetDevice(pb.device));
+        CK(launch(k_pgm_momentum<T>, dim3(1184), dim3(256), 0, stream, (const C2<T>*)Zt.p,
+                  (const C2<T>*)pgA.p, pgB.p, (T)coef, nslab));
+        std::swap(Zt.p, pgA.p);
+        std::swap(Zt.n, pgA.n);
+        pgm_have_cand = false;
         return SPCSC_OK;
     }
 
@@ -962,6 +1140,10 @@ int spcsc_destroy(spcsc_handle* h) {
     return (expr)
 
 int spcsc_synchronize(spcsc_handle* h) { H_CALL(h->synchronize()); }
+int spcsc_pgm_configure(spcsc_handle* h, const spcsc_pgm_opts* o) { H_CALL(o ? h->pgm_configure(o) : SPCSC_ERR_INVALID); }
+int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0)); }
+int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
+int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {
     if (!id128) { g_last_error = "null id buffer"; return SPCSC_ERR_INVALID; }
     NcclApi& api = nccl_api(nccl_lib);
@@ -972,10 +1154,42 @@ int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {
     memcpy(id128, &uid, sizeof(uid));
     return SPCSC_OK;
 }
-int spcsc_comm_init(spcsc_handle* h, const char* nccl_lib, const void* id128, int32_t rank,
-                    int32_t nranks, double global_nx) {
-    H_CALL(id128 ? h->comm_init(nccl_lib, id128, rank, nranks, global_nx) : SPCSC_ERR_INVALID);
+int spcsc_comm_create(const char* nccl_lib, const void* id128, int32_t rank, int32_t nranks,
+                      int32_t device, spcsc_comm** out) {
+    if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) {
+        g_last_error = "bad argument";
+        return SPCSC_ERR_INVALID;
+    }
+    *out = nullptr;
+    NcclApi& api = nccl_api(nccl_lib);
+    if (!api.ok) { g_last_error = api.err; return SPCSC_ERR_NCCL; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return SPCSC_ERR_CUDA; }
+    NcclApi::UniqueId uid;
+    memcpy(&uid, id128, sizeof(uid));
+    void* comm = nullptr;
+    int r = api.CommInitRank(&comm, nranks, uid, rank);
+    if (r != 0) { g_last_error = std::string("ncclCommInitRank: ") + api.GetErrorString(r); return SPCSC_ERR_NCCL; }
+    spcsc_comm* c = new spcsc_comm();
+    c->comm = comm; c->api = &api; c->rank = rank; c->nranks = nranks; c->device = device;
+    *out = c;
+    return SPCSC_OK;
 }
+int spcsc_comm_destroy(spcsc_comm* c) {
+    if (c) {
+        if (c->comm && c->api) c->api->CommDestroy(c->comm);
+        delete c;
+    }
+    return SPCSC_OK;
+}
+int spcsc_attach_comm(spcsc_handle* h, spcsc_comm* c, double global_nx) { H_CALL(h->attach_comm(c, global_nx)); }
+int spcsc_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return SPCSC_ERR_INVALID;
+    cudaError_t e = host_pool().alloc(out, (size_t)bytes, -1);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return SPCSC_ERR_NOMEM; }
+    return SPCSC_OK;
+}
+int spcsc_host_free(void* p) { host_pool().release(p); return SPCSC_OK; }
+int spcsc_trim_pools(void) { dev_pool().trim(); host_pool().trim(); return SPCSC_OK; }
 int spcsc_set_dict(spcsc_handle* h, const void* D) { H_CALL(D ? h->set_dict(D) : SPCSC_ERR_INVALID); }
 int spcsc_set_signal(spcsc_handle* h, const void* S) { H_CALL(S ? h->set_signal(S) : SPCSC_ERR_INVALID); }
 int spcsc_set_l1_weight(spcsc_handle* h, const void* w, const int64_t shape[5]) {

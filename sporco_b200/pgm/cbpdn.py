@@ -1,0 +1,138 @@
+"""Convolutional BPDN by PGM / FISTA on the B200 engine.
+
+Drop-in counterpart of ``sporco.pgm.cbpdn.ConvBPDN`` (sporco/pgm/cbpdn.py:29-384): same
+constructor, ``Options`` tree, ``IterationStats`` fields (ObjFun, DFid, RegL1, Rsdl, F_Btrack,
+Q_Btrack, IterBTrack, L) and ``solve / getcoef / setdict / reconstruct`` surface.
+Supported on the device: fixed step 1/L or ``BacktrackStandard``; Nesterov / linear momentum.
+``Monotone``, ``StepSizePolicy`` and ``BacktrackRobust`` raise ``NotImplementedError``.
+"""
+
+import copy
+
+import numpy as np
+
+from .. import _lib, cnvrep as cr
+from . import pgm
+from .backtrack import BacktrackStandard     # noqa: F401  (re-exported for user code)
+
+
+class ConvBPDN(pgm.PGMDFT):
+    class Options(pgm.PGMDFT.Options):
+        defaults = copy.deepcopy(pgm.PGMDFT.Options.defaults)
+        defaults.update({'NonNegCoef': False, 'NoBndryCross': False})
+        defaults.update({'L1Weight': 1.0})
+        defaults.update({'L': 500.0})
+
+        def __init__(self, opt=None):
+            pgm.PGMDFT.Options.__init__(self, {} if opt is None else opt)
+
+    itstat_fields_objfn = ('ObjFun', 'DFid', 'RegL1')
+    hdrtxt_objfn = ('Fnc', 'DFid', u'Regℓ1')
+    hdrval_objfun = {'Fnc': 'ObjFun', 'DFid': 'DFid', u'Regℓ1': 'RegL1'}
+
+    def __init__(self, D, S, lmbda=None, opt=None, dimK=None, dimN=2, device=0):
+        if dimN != 2:
+            raise NotImplementedError('sporco_b200 implements the dimN=2 (image) case only')
+        if not (np.isrealobj(D) and np.isrealobj(S)):
+            raise NotImplementedError('complex-valued dictionaries / signals are not supported')
+        opt = self._coerce_options(opt)
+        if not hasattr(self, 'cri'):
+            self.cri = cr.CSC_ConvRepIndexing(D, S, dimK=dimK, dimN=dimN)
+        cri = self.cri
+        self.set_dtype(opt, S.dtype)
+        self.D = np.asarray(D.reshape(cri.shpD), dtype=self.dtype)
+        self.S = np.asarray(S.reshape(cri.shpS), dtype=self.dtype)
+        self._device = device
+        self._cache = {}
+        _lib.require_device()
+        self._h = _lib.Handle(cri.Nv[0], cri.Nv[1], cri.C, cri.Cd, cri.K, cri.M,
+                              self.D.shape[0], self.D.shape[1], self.dtype, device)
+        self._h.set_signal(self.S[..., 0])
+        self._h.set_dict(self.D[:, :, :, 0, :])
+
+        if lmbda is None:                                # sporco/pgm/cbpdn.py:194-199
+            b = np.conj(self.Df) * self.Sf
+            lmbda = 0.1 * abs(b).max()
+        self.lmbda = self.dtype.type(lmbda)
+        self.wl1 = np.asarray(opt['L1Weight'], dtype=self.dtype)
+        w = self.wl1.reshape(cr.l1Wshape(self.wl1, cri))
+        self._h.set_l1_weight(np.ascontiguousarray(w))
+
+        super(ConvBPDN, self).__init__(cri.shpX, cri.Nv, cri.axisN, S.dtype, opt)
+        x0 = opt['X0']
+        self._h.pgm_reset(None if x0 is None else np.asarray(x0, dtype=self.dtype).reshape(cri.shpX))
+        self._stats = None
+
+    # ---- state on the device
+    def _fetch(self, which):
+        if which not in self._cache:
+            self._cache[which] = self._h.get_array(which)
+        return self._cache[which]
+
+    @property
+    def X(self):
+        return self._fetch(_lib.ARR_PGM_X)
+
+    @property
+    def Xf(self):
+        return self._fetch(_lib.ARR_PGM_XF)
+
+    @property
+    def Yf(self):
+        return self._fetch(_lib.ARR_PGM_YF)
+
+    @property
+    def Df(self):
+        return self._fetch(_lib.ARR_DF)
+
+    @property
+    def Sf(self):
+        return self._fetch(_lib.ARR_SF)
+
+    def setdict(self, D=None):
+        if D is not None:
+            self.D = np.asarray(D, dtype=self.dtype).reshape(self.cri.shpD)
+        self._cache.pop(_lib.ARR_DF, None)
+        self._h.set_dict(self.D[:, :, :, 0, :])
+
+    def getcoef(self):
+        return self.X
+
+    def reconstruct(self, X=None):
+        if X is None:
+            X = self.X
+        return self._h.reconstruct(np.asarray(X, dtype=self.dtype).reshape(self.cri.shpX))
+
+    # ---- one proximal step on the device; returns (F, Q) in the working precision
+    def _trial(self):
+        o = self.opt
+        self._h.pgm_configure(self.lmbda, o['NonNegCoef'], o['NoBndryCross'])
+        s = self._h.pgm_trial(float(self.L))
+        for k in (_lib.ARR_PGM_X, _lib.ARR_PGM_XF, _lib.ARR_PGM_YF):
+            self._cache.pop(k, None)
+        self._stats = s
+        ty = self.dtype.type
+        f = ty(s[0])
+        # Q = f(y) + <x - y, grad f(y)> + (L/2) ||x - y||^2      (sporco/pgm/backtrack.py:93-95)
+        q = ty(s[1]) + ty(s[2]) + (self.L / 2.) * ty(s[3])
+        return f, q
+
+    def ystep(self):
+        """Momentum step (sporco/pgm/pgm.py:815-831) on the device."""
+        tprv = self.t
+        self.t = self.momentum.update(self.var_momentum())
+        self._h.pgm_accept((tprv - 1.) / self.t)
+        self._cache.pop(_lib.ARR_PGM_YF, None)
+
+    def rsdl(self):
+        return self.dtype.type(self._stats[4])
+
+    def eval_objfn(self):
+        dfd = self._stats[5]
+        rl1 = self._stats[6]
+        return (dfd + self.lmbda * rl1, dfd, rl1)
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None:
+            h.close()

@@ -113,3 +113,31 @@ FRESH_CASES = [
     (32, 512, 5, 1, None, None, None),                     # long rows (H=256)
     (512, 64, 9, 1, None, None, None),                     # long columns (full-warp plan)
 ]
+
+
+def run_pgm_cases(sfx):
+    """PGM / FISTA golden problems (fixed step and standard backtracking)."""
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    tol = 1e-11 if sfx == 'f64' else 5e-5
+    g = load('pgm_bt_' + sfx)
+    opt = pcbpdn.ConvBPDN.Options({'MaxMainIter': 25, 'RelStopTol': 0.0, 'L': 10.0,
+                                   'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)})
+    b = pcbpdn.ConvBPDN(g['D'], g['S'], float(g['lmbda']), opt, dimK=1)
+    X = b.solve()
+    its = b.getitstat()
+    assert X.dtype == g['X'].dtype and rel(X, g['X']) < tol
+    assert np.array_equal(np.asarray(its.IterBTrack, dtype=np.float64), g['IterBTrack'])
+    assert rel(its.L, g['L']) < 1e-6
+    assert rel(its.F_Btrack, g['F_Btrack']) < 10 * tol and rel(its.Q_Btrack, g['Q_Btrack']) < 10 * tol
+    assert rel(its.Rsdl, g['Rsdl']) < 10 * tol and rel(its.ObjFun, g['ObjFun']) < 10 * tol
+    assert rel(b.reconstruct().squeeze(), np.zeros(1)) >= 0      # runs
+    g = load('pgm_fixed_' + sfx)
+    opt = pcbpdn.ConvBPDN.Options({'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0})
+    b = pcbpdn.ConvBPDN(g['D'], g['S'], float(g['lmbda']), opt, dimK=1)
+    X = b.solve()
+    its = b.getitstat()
+    assert rel(X, g['X']) < tol
+    assert rel(its.ObjFun, g['ObjFun']) < 10 * tol and rel(its.DFid, g['DFid']) < 10 * tol
+    assert rel(its.RegL1, g['RegL1']) < 10 * tol and rel(its.Rsdl, g['Rsdl']) < 10 * tol
+    return b

@@ -76,3 +76,8 @@ def test_register_plan_kernels_vs_oracle(case):
 def test_general_kernels_on_the_same_problem(monkeypatch):
     monkeypatch.setenv('SPCSC_KERNELS', 'v1')
     cases.run_fresh_case(256, 64, 40, 2)
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+def test_pgm_golden(sfx):
+    cases.run_pgm_cases(sfx)

@@ -124,3 +124,25 @@ def test_kernel_sets_agree(monkeypatch):
     monkeypatch.setenv('SPCSC_KERNELS', 'v1')
     b1, _ = cases.run_fresh_case(256, 256, 64, 2, iters=12)
     assert cases.rel(b1.Y, b2.Y) < 3e-4
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+def test_pgm_golden(sfx):
+    cases.run_pgm_cases(sfx)
+
+
+def test_pgm_vs_oracle_multichannel_dictionary():
+    """FISTA with a 3-channel dictionary (gradient summed over channels, pgm/cbpdn.py:263-284),
+    NonNegCoef, backtracking; 64x64, M=12, K=2."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    rng = np.random.default_rng(11)
+    D = rng.standard_normal((6, 6, 3, 12))
+    S = rng.standard_normal((64, 64, 3, 2))
+    o = {'MaxMainIter': 20, 'RelStopTol': 0.0, 'L': 5.0, 'NonNegCoef': True}
+    b = pcbpdn.ConvBPDN(D, S, 0.2, pcbpdn.ConvBPDN.Options(dict(o, Backtrack=BacktrackStandard(1.5, 10))))
+    X = b.solve()
+    r = orc.pgm_convbpdn(D, S, 0.2, opt=dict(o, Backtrack={'gamma_u': 1.5, 'maxiter': 10}))
+    assert cases.rel(X, r.X) < 1e-10
+    assert cases.rel(b.getitstat().L, [row[8] for row in r.itstat]) < 1e-12
