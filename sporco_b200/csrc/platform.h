@@ -126,8 +126,31 @@ struct alignas(2 * sizeof(T)) C2 {
 };
 
 template <typename T> SPCSC_HD C2<T> mk(T a, T b) { C2<T> r; r.re = a; r.im = b; return r; }
+#if defined(SPCSC_EMU) || defined(SPCSC_NO_F32X2)
 template <typename T> SPCSC_HD C2<T> operator+(C2<T> a, C2<T> b) { return mk<T>(a.re + b.re, a.im + b.im); }
 template <typename T> SPCSC_HD C2<T> operator-(C2<T> a, C2<T> b) { return mk<T>(a.re - b.re, a.im - b.im); }
+#else
+// Blackwell packed FP32 (FADD2 / FFMA2): one instruction per complex add / subtract.  The
+// results are bit-identical to the scalar forms (a - b as fma(b, -1, a) is exact).
+SPCSC_DEV float2 as_f2(C2<float> a) { return make_float2(a.re, a.im); }
+SPCSC_DEV C2<float> as_c2(float2 a) { C2<float> r; r.re = a.x; r.im = a.y; return r; }
+template <typename T> SPCSC_HD C2<T> operator+(C2<T> a, C2<T> b) { return mk<T>(a.re + b.re, a.im + b.im); }
+template <typename T> SPCSC_HD C2<T> operator-(C2<T> a, C2<T> b) { return mk<T>(a.re - b.re, a.im - b.im); }
+template <> SPCSC_HD C2<float> operator+<float>(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+    return as_c2(__fadd2_rn(as_f2(a), as_f2(b)));
+#else
+    return mk<float>(a.re + b.re, a.im + b.im);
+#endif
+}
+template <> SPCSC_HD C2<float> operator-<float>(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+    return as_c2(__ffma2_rn(as_f2(b), make_float2(-1.0f, -1.0f), as_f2(a)));
+#else
+    return mk<float>(a.re - b.re, a.im - b.im);
+#endif
+}
+#endif
 template <typename T> SPCSC_HD C2<T> operator*(C2<T> a, C2<T> b) {
     return mk<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
 }
