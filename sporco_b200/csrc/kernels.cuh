@@ -34,6 +34,8 @@ struct AdmmState {
     T udiv;         // pending dual rescale: U_effective = U_stored / udiv
     int k;          // iterations completed
     int stopped;    // 1 once the residual stopping test has fired
+    int zt_stale;   // 1: the pre-computed row spectra of (Y - U) do not match the current U scaling
+    int pad_;
 };
 
 template <typename T>
@@ -708,6 +710,7 @@ SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
     }
     st->rho = rho;
     st->udiv = udiv;
+    st->zt_stale = (udiv != (T)1) ? 1 : 0;
     st->k = k + 1;
     if (p.need_rsdl && (double)r < epri && (double)s < edua) st->stopped = 1;
     for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
@@ -723,7 +726,7 @@ SPCSC_GLOBAL void k_apply_udiv(T* U, AdmmState<T>* st, size_t n) {
         U[i] = U[i] / d;
 }
 template <typename T>
-SPCSC_GLOBAL void k_reset_udiv(AdmmState<T>* st) { st->udiv = 1; }
+SPCSC_GLOBAL void k_reset_udiv(AdmmState<T>* st) { st->udiv = 1; st->zt_stale = 1; }
 
 // ------------------------------------------------------------------------------------
 // Layout conversion between the reference's (N0,N1,C,K,M) order and the device order

@@ -30,15 +30,18 @@ template <typename T, int H, int E, int NT>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
 k_row_fwd2(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
            const AdmmState<T>* SPCSC_RESTRICT st, C2<T>* SPCSC_RESTRICT Zt,
-           const C2<T>* SPCSC_RESTRICT tw, const C2<T>* SPCSC_RESTRICT stw, int N0, int M) {
+           const C2<T>* SPCSC_RESTRICT tw, const C2<T>* SPCSC_RESTRICT stw, int N0, int M,
+           int nb, int gated) {
     if (st && st->stopped) return;
+    // `gated`: the previous iteration's prox kernel already produced these spectra; they are
+    // only stale (and this kernel only has work) when rho -- hence the scaling of U -- changed.
+    if (gated && st && !st->zt_stale) return;
     SPCSC_DYN_SMEM(smem_raw);
     constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
     constexpr int TWLEN = stage_tw_len(H, E);
     C2<T>* reg = reinterpret_cast<C2<T>*>(smem_raw);          // [TR][P]
     C2<T>* stw_s = reg + TR * P;                               // [TWLEN]
     const int tid = threadIdx.x;
-    const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
     for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
     const int g = tid / TPF, t = tid % TPF;
     T uinv = 1;
@@ -46,35 +49,42 @@ k_row_fwd2(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
         const T ud = st->udiv;
         if (ud != (T)1) uinv = (T)1 / ud;
     }
-    const size_t rowbase = ((((size_t)b * M + m) * N0 + h0 + g) * H);
-    const C2<T>* A2 = reinterpret_cast<const C2<T>*>(A) + rowbase;
-    C2<T> v[E];
-    SPCSC_UNROLL
-    for (int p = 0; p < E; ++p) v[p] = A2[t + TPF * p];
-    if (B) {
-        const C2<T>* B2 = reinterpret_cast<const C2<T>*>(B) + rowbase;
-        SPCSC_UNROLL
-        for (int p = 0; p < E; ++p) {
-            const C2<T> u = B2[t + TPF * p];
-            v[p].re -= u.re * uinv;
-            v[p].im -= u.im * uinv;
-        }
-    }
+    const int tiles_h = N0 / TR;
+    const long long ntiles = (long long)tiles_h * M * nb;
     __syncthreads();                                         // stage twiddles are in place
-    fft_regs<T, H, E, false>(v, reg + g * P, stw_s, t);
-    __syncwarp();
-    SPCSC_UNROLL
-    for (int p = 0; p < E; ++p) reg[g * P + t + TPF * p] = v[p];
-    __syncthreads();
-    C2<T>* out = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
-    const size_t wstride = (size_t)M * N0;
-    for (int e = tid; e < TR * N1f; e += NT) {
-        const int wf = e / TR, r = e % TR;
-        const C2<T> a = reg[r * P + (wf == H ? 0 : wf)];
-        const C2<T> bb = conj(reg[r * P + (wf == 0 ? 0 : H - wf)]);
-        const C2<T> w = tw[wf];
-        const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
-        out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int h0 = (int)(tile % tiles_h) * TR;
+        const int m = (int)((tile / tiles_h) % M), b = (int)(tile / ((long long)tiles_h * M));
+        const size_t rowbase = ((((size_t)b * M + m) * N0 + h0 + g) * H);
+        const C2<T>* A2 = reinterpret_cast<const C2<T>*>(A) + rowbase;
+        C2<T> v[E];
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) v[p] = A2[t + TPF * p];
+        if (B) {
+            const C2<T>* B2 = reinterpret_cast<const C2<T>*>(B) + rowbase;
+            SPCSC_UNROLL
+            for (int p = 0; p < E; ++p) {
+                const C2<T> u = B2[t + TPF * p];
+                v[p].re -= u.re * uinv;
+                v[p].im -= u.im * uinv;
+            }
+        }
+        fft_regs<T, H, E, false>(v, reg + g * P, stw_s, t);
+        __syncwarp();
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) reg[g * P + t + TPF * p] = v[p];
+        __syncthreads();
+        C2<T>* out = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
+        const size_t wstride = (size_t)M * N0;
+        for (int e = tid; e < TR * N1f; e += NT) {
+            const int wf = e / TR, r = e % TR;
+            const C2<T> a = reg[r * P + (wf == H ? 0 : wf)];
+            const C2<T> bb = conj(reg[r * P + (wf == 0 ? 0 : H - wf)]);
+            const C2<T> w = tw[wf];
+            const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
+            out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+        }
+        __syncthreads();                                     // reg is reused by the next tile
     }
 }
 
@@ -242,7 +252,8 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
 // ------------------------------------------------------------------------------------
 template <typename T, int H, int E, int NT>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
-k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RESTRICT U,
+k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* SPCSC_RESTRICT Y,
+                T* SPCSC_RESTRICT U,
                 const AdmmState<T>* SPCSC_RESTRICT st, AdmmParams<T> prm, WeightView<T> wl1,
                 double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
                 const C2<T>* SPCSC_RESTRICT stw, int N0, int M, T scale, int nonneg, int bnd0,
@@ -349,6 +360,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
         }
         yg[j] = mk<T>(yn[0], yn[1]);
         ug[j] = mk<T>(un[0], un[1]);
+        v[p] = mk<T>(yn[0] - un[0], yn[1] - un[1]);          // next x-step input, if rho stays
     }
     if (prm.need_rsdl || prm.need_obj) {
         double d[7];
@@ -356,6 +368,24 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
         for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
         double* red = reinterpret_cast<double*>(smem_raw);
         block_accumulate<7>(d, red, acc);
+    }
+    if (Znext) {
+        // Cross-iteration fusion: the row spectra of Y - U for the next iteration, valid as long
+        // as rho (hence the scaling of U) does not change; otherwise k_row_fwd2 redoes them.
+        fft_regs<T, H, E, false>(v, reg + g * P, stw_s, t);
+        __syncwarp();
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) reg[g * P + t + TPF * p] = v[p];
+        __syncthreads();
+        C2<T>* out = Znext + (((size_t)k * N1f) * M + m) * N0 + h0;
+        for (int e = tid; e < TR * N1f; e += NT) {
+            const int wf = e / TR, r = e % TR;
+            const C2<T> a = reg[r * P + (wf == H ? 0 : wf)];
+            const C2<T> bb = conj(reg[r * P + (wf == 0 ? 0 : H - wf)]);
+            const C2<T> w = tw[wf];
+            const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
+            out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+        }
     }
 }
 

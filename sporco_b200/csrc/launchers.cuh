@@ -25,6 +25,7 @@ struct ProxArgs {
     T scale;
     int nonneg, bnd0, bnd1, reg_on_y;
     int use_v2_sync;             // 1: synchronous-load row kernel (k_row_inv_prox2) even when CX == 1
+    void* znext;                 // fused forward output (C2<T>*), or null
 };
 
 enum ColMode {
@@ -112,7 +113,7 @@ inline bool col2_ok(int N0, int M, int Cd) {
 
 template <typename T, int H>
 cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
-                            C2<T>* Zt, const C2<T>* stw);
+                            C2<T>* Zt, const C2<T>* stw, int gated);
 template <typename T, int H>
 cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
                                  T* U, const AdmmState<T>* st, const C2<T>* stw);

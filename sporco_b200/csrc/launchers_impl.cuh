@@ -118,13 +118,16 @@ cudaError_t col_launch(int mode, ColLaunch<T> c) {
 // ---- kernel set v2 -----------------------------------------------------------------
 template <typename T, int H>
 cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
-                            C2<T>* Zt, const C2<T>* stw) {
+                            C2<T>* Zt, const C2<T>* stw, int gated) {
     if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
         constexpr int E = row2_elems(H, 1), NT = kRow2Threads, TR = row2_tile(H, 1);
         const size_t smem = ((size_t)TR * (H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
-        dim3 grid(r.N0 / TR, r.M, r.nb);
+        const long long ntiles = (long long)(r.N0 / TR) * r.M * r.nb;
+        // grid-stride over tiles: a gated launch that finds nothing to do retires in microseconds
+        const long long cap = 148LL * 24;
+        dim3 grid((unsigned)(ntiles < cap ? ntiles : cap));
         return launch(k_row_fwd2<T, H, E, NT>, grid, dim3(NT), smem, r.stream, A, B, st, Zt, r.tw,
-                      stw, r.N0, r.M);
+                      stw, r.N0, r.M, r.nb, gated);
     } else {
         return cudaErrorInvalidValue;
     }
@@ -152,7 +155,8 @@ static cudaError_t row_inv_prox3_go(const RowArgs<T>& r, const ProxArgs<T>& p, c
         constexpr int E = row2_elems(H, 1), NT = kRow2Threads, TR = row2_tile(H, 1);
         const size_t smem = ((size_t)TR * (3 * H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
         dim3 grid(r.N0 / TR, r.M, r.nb);
-        return launch(k_row_inv_prox3<T, H, E, NT>, grid, dim3(NT), smem, r.stream, Zt, Y, U, st,
+        return launch(k_row_inv_prox3<T, H, E, NT>, grid, dim3(NT), smem, r.stream, Zt,
+                      reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
                       p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
                       p.reg_on_y);
     } else {

@@ -25,7 +25,7 @@ SPCSC_INST(double)
 // kernel set v2 (float only)
 template cudaError_t row_fwd2_launch<float, SPCSC_SIZE>(const RowArgs<float>&, const float*,
                                                         const float*, const AdmmState<float>*,
-                                                        C2<float>*, const C2<float>*);
+                                                        C2<float>*, const C2<float>*, int);
 template cudaError_t row_inv_prox2_launch<float, SPCSC_SIZE>(const RowArgs<float>&,
                                                              const ProxArgs<float>&,
                                                              const C2<float>*, float*, float*,

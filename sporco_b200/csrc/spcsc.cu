@@ -93,10 +93,10 @@ static cudaError_t col(int N0, int mode, const ColLaunch<T>& c) {
 
 template <typename T>
 static cudaError_t row_fwd2(int H, const RowArgs<T>& r, const T* A, const T* B,
-                            const AdmmState<T>* st, C2<T>* Zt, const C2<T>* stw) {
+                            const AdmmState<T>* st, C2<T>* Zt, const C2<T>* stw, int gated) {
     if constexpr (sizeof(T) == 4) {
         switch (H) {
-#define X(n) case n: return row_fwd2_launch<T, n>(r, A, B, st, Zt, stw);
+#define X(n) case n: return row_fwd2_launch<T, n>(r, A, B, st, Zt, stw, gated);
             SPCSC_FOR_SIZES(X)
 #undef X
         }
@@ -353,6 +353,9 @@ class Engine : public spcsc_handle {
     bool pgm_ready = false, pgm_have_cand = false;
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
     int col_cpg = kCol2CPG;
+    bool fuse = false;          // prox kernel also emits the next iteration's row spectra
+    bool fused_batch = false, x_in_zt2 = false;
+    DevBuf<C2<T>> Zt2;          // ping-pong partner of Zt when fusing
     DevBuf<double> acc;
     DevBuf<AdmmState<T>> st;
     DevBuf<StatRow> rows;
@@ -387,7 +390,7 @@ class Engine : public spcsc_handle {
         Sf.release(); G.release(); tw_row.release(); tw_col.release(); sum_buf.release();
         acc.release(); st.release(); rows.release();
         stw_row1.release(); stw_rowc.release(); stw_col.release();
-        pgA.release(); pgB.release();
+        pgA.release(); pgB.release(); Zt2.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -421,6 +424,8 @@ class Engine : public spcsc_handle {
             v2_rowp = allow2 && row2_ok<T>(H, N0, Cx);
             v2_col = allow2 && col2_ok<T>(N0, M, Cd);
             if (const char* e = getenv("SPCSC_COL_CPG")) col_cpg = (atoi(e) == 1) ? 1 : 2;
+            const char* fz = getenv("SPCSC_FUSE");
+            fuse = v2_rowf && v2_rowp && Cx == 1 && !(fz && std::string(fz) == "0");
             int rc;
             if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1)))) return rc;
             if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx)))) return rc;
@@ -589,7 +594,7 @@ class Engine : public spcsc_handle {
 
     int write_state(T rho, T udiv, int k, int stopped) {
         AdmmState<T> s;
-        s.rho = rho; s.udiv = udiv; s.k = k; s.stopped = stopped;
+        s.rho = rho; s.udiv = udiv; s.k = k; s.stopped = stopped; s.zt_stale = 1; s.pad_ = 0;
         CK(cudaMemcpyAsync(st.p, &s, sizeof(s), cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
         return SPCSC_OK;
@@ -661,16 +666,25 @@ class Engine : public spcsc_handle {
         cs.a.dfid_on = prm.need_obj;
         int ne = 0;
         last_launches = 0;
+        C2<T>* zin = Zt.p;
+        C2<T>* zoth = nullptr;
+        fused_batch = false;
         if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
         for (int it = 0; it < n; ++it) {
+            const bool fuse_now = fuse && !check && !opts.joint && !pa.use_v2_sync;
+            if (fuse_now && !zoth) {
+                CK(Zt2.ensure(nslab));
+                zoth = Zt2.p;
+                fused_batch = true;
+            }
             if (v2_rowf)
-                CK(row_fwd2<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p,
-                               (const C2<T>*)stw_row1.p));
+                CK(row_fwd2<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, zin,
+                               (const C2<T>*)stw_row1.p, fuse_now ? 1 : 0));
             else
-                CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, Zt.p));
+                CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, zin));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (!check) {
-                cs.in = Zt.p; cs.out = Zt.p;
+                cs.in = zin; cs.out = zin;
                 if (v2_col)
                     CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
                 else
@@ -678,7 +692,7 @@ class Engine : public spcsc_handle {
                 last_launches += 4;
             } else {
                 ColLaunch<T> c1 = cs;
-                c1.in = Zt.p; c1.out = Zscratch.p; c1.a.Cd = Cd;
+                c1.in = zin; c1.out = Zscratch.p; c1.a.Cd = Cd;
                 CK(col<T>(N0, COL_FWD, c1));
                 ColLaunch<T> c2 = cs;
                 c2.in = Zscratch.p; c2.out = Xscratch.p;
@@ -688,16 +702,17 @@ class Engine : public spcsc_handle {
                           (const C2<T>*)Xscratch.p, (const C2<T>*)Zscratch.p, (const C2<T>*)Df.p,
                           (const C2<T>*)Sf.p, (const AdmmState<T>*)st.p, acc.p, ca));
                 ColLaunch<T> c3 = cs;
-                c3.in = Xscratch.p; c3.out = Zt.p;
+                c3.in = Xscratch.p; c3.out = zin;
                 CK(col<T>(N0, COL_INV, c3));
                 last_launches += 7;
             }
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            pa.znext = fuse_now ? (void*)zoth : nullptr;
             if (v2_rowp)
-                CK(row_inv_prox2<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p,
+                CK(row_inv_prox2<T>(H, rp, pa, (const C2<T>*)zin, Y.p, U.p,
                                     (const AdmmState<T>*)st.p, (const C2<T>*)stw_rowc.p));
             else
-                CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)Zt.p, Y.p, U.p, (const AdmmState<T>*)st.p));
+                CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)zin, Y.p, U.p, (const AdmmState<T>*)st.p));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
                 // the one exchange of the path: sum the residual / objective accumulators over ranks
@@ -710,8 +725,21 @@ class Engine : public spcsc_handle {
             }
             CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            if (fuse_now) std::swap(zin, zoth);        // the spectra just written feed the next x-step
         }
         return SPCSC_OK;
+    }
+
+    // After a fused batch of which `done` iterations actually executed (the device stops
+    // launching work once the stopping test fires), point Zt at the buffer holding the next
+    // x-step input and Zt2 at the one holding the last X row spectra.
+    void settle_pingpong(int done) {
+        if (!fused_batch) { x_in_zt2 = false; return; }
+        C2<T>* p0 = Zt.p;
+        C2<T>* p1 = Zt2.p;
+        if (done % 2 == 1) { Zt.p = p1; Zt2.p = p0; }
+        x_in_zt2 = done > 0 ? true : x_in_zt2;
+        if (done == 0) { /* nothing ran: roles unchanged */ }
     }
 
     int admm_prepare(int n, AdmmState<T>& s0) {
@@ -746,6 +774,7 @@ class Engine : public spcsc_handle {
         CK(cudaEventElapsedTime(&last_ms, ev0, ev1));
         const int done = s1.k - s0.k;
         have_x = have_x || done > 0;
+        settle_pingpong(done);
         if (out_rows && done > 0) {
             std::vector<StatRow> hr(done);
             CK(cudaMemcpyAsync(hr.data(), rows.p, done * sizeof(StatRow), cudaMemcpyDeviceToHost, stream));
@@ -789,6 +818,12 @@ class Engine : public spcsc_handle {
             ms4[i % 4] += ms;
         }
         have_x = true;
+        {
+            AdmmState<T> s1;
+            rc = read_state(s1);
+            if (rc) return rc;
+            settle_pingpong(s1.k - s0.k);
+        }
         return SPCSC_OK;
     }
 
@@ -822,7 +857,7 @@ class Engine : public spcsc_handle {
             case SPCSC_ARR_XF: {
                 if (!have_x) FAIL(SPCSC_ERR_STATE, "X is not defined before the first iteration");
                 CK(tmp_real.ensure(nreal));
-                CK(row_inv<T>(H, rowargs(M, K * Cx, 1), (const C2<T>*)Zt.p, tmp_real.p,
+                CK(row_inv<T>(H, rowargs(M, K * Cx, 1), (const C2<T>*)(x_in_zt2 ? Zt2.p : Zt.p), tmp_real.p,
                               (T)(1.0 / ((double)N0 * (double)N1))));
                 if (which == SPCSC_ARR_X) return from_internal(tmp_real.p, out, Cx, K, M);
                 CK(Zscratch.ensure(nslab));

@@ -141,3 +141,41 @@ def run_pgm_cases(sfx):
     assert rel(its.ObjFun, g['ObjFun']) < 10 * tol and rel(its.DFid, g['DFid']) < 10 * tol
     assert rel(its.RegL1, g['RegL1']) < 10 * tol and rel(its.Rsdl, g['Rsdl']) < 10 * tol
     return b
+
+
+def run_fusion_cases():
+    """The optimistic cross-iteration fusion (the prox kernel also emits the next iteration's
+    row spectra): consumed when rho is constant, redone when it changed; X must stay
+    retrievable; batches of odd/even length and a device-side stop inside a batch."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(21)
+    D = rng.standard_normal((5, 5, 12)).astype(np.float32)
+    S = rng.standard_normal((64, 256, 2)).astype(np.float32)
+    fixed = {'RelStopTol': 0.0, 'rho': 5.0, 'AutoRho': {'Enabled': False}}
+    # (a) constant rho: every fused spectrum is used
+    o = dict(fixed, MaxMainIter=13)
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=o, dimK=1)
+    assert rel(Y, r.Y) < 5e-5 and rel(b.X, r.X) < 5e-5 and rel(b.U, r.U) < 5e-5
+    # (b) the same in two calls of 7 + 6 iterations (odd, then even number of buffer swaps)
+    o1 = dict(fixed, MaxMainIter=7)
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o1), dimK=1)
+    b.solve()
+    x7 = b.X.copy()
+    r7 = orc.admm_convbpdn(D, S, 0.1, opt=o1, dimK=1)
+    assert rel(x7, r7.X) < 5e-5
+    b.opt['MaxMainIter'] = 6
+    Y = b.solve()
+    assert b.k == 13 and rel(Y, r.Y) < 5e-5 and rel(b.X, r.X) < 5e-5
+    # (c) AutoRho with a stop inside a batch
+    o = {'MaxMainIter': 60, 'RelStopTol': 3e-2}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=o, dimK=1)
+    assert 2 < r.k < 60, r.k
+    assert b.k == r.k and len(b.itstat) == r.k
+    assert rel(Y, r.Y) < 3e-4 and rel(b.X, r.X) < 3e-4
+    Y2 = b.solve()            # re-entering runs one more iteration, as the reference does
+    assert b.k == r.k + 1

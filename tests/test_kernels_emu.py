@@ -81,3 +81,7 @@ def test_general_kernels_on_the_same_problem(monkeypatch):
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
 def test_pgm_golden(sfx):
     cases.run_pgm_cases(sfx)
+
+
+def test_cross_iteration_fusion():
+    cases.run_fusion_cases()

@@ -146,3 +146,7 @@ def test_pgm_vs_oracle_multichannel_dictionary():
     r = orc.pgm_convbpdn(D, S, 0.2, opt=dict(o, Backtrack={'gamma_u': 1.5, 'maxiter': 10}))
     assert cases.rel(X, r.X) < 1e-10
     assert cases.rel(b.getitstat().L, [row[8] for row in r.itstat]) < 1e-12
+
+
+def test_cross_iteration_fusion():
+    cases.run_fusion_cases()
