@@ -146,6 +146,11 @@ int spcsc_admm_last_timing(spcsc_handle* h, float* elapsed_ms, int64_t* launches
    device time per kernel, ms: [0] k_row_fwd, [1] k_col, [2] k_row_inv_prox, [3] k_admm_scalars.
    Measurement aid for bench.py (same kernels, same stream as spcsc_admm_iterate). */
 int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]);
+/* Which kernel schedule the handle uses: info[0] register-plan row-forward kernel, [1] cluster
+   column kernel, [2] register-plan prox kernel, [3] cross-iteration fusion (the prox kernel also
+   emits the next x-step's row spectra; the row-forward launch is then a gated no-op unless rho
+   changed). */
+int spcsc_admm_schedule_info(spcsc_handle* h, int32_t info[4]);
 
 /* ---- PGM / FISTA solver (sporco.pgm.cbpdn.ConvBPDN).  The host keeps the scalar control flow
    of pgm/pgm.py:328-370 and pgm/backtrack.py:74-107 (step size L, momentum t, F <= Q test);

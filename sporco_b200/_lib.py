@@ -22,7 +22,7 @@ SYMBOLS = (
     'spcsc_set_dict', 'spcsc_set_signal', 'spcsc_set_l1_weight', 'spcsc_set_l21_weight',
     'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_set_iter',
     'spcsc_admm_iterate',
-    'spcsc_admm_get_scalars', 'spcsc_admm_last_timing', 'spcsc_admm_profile', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
+    'spcsc_admm_get_scalars', 'spcsc_admm_last_timing', 'spcsc_admm_profile', 'spcsc_admm_schedule_info', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
@@ -93,6 +93,7 @@ def _declare(lib):
     lib.spcsc_admm_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float),
                                            ctypes.POINTER(ctypes.c_int64)]
     lib.spcsc_admm_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
+    lib.spcsc_admm_schedule_info.argtypes = [vp, ctypes.POINTER(i32)]
     lib.spcsc_get_array.argtypes = [vp, i32, vp]
     lib.spcsc_set_array.argtypes = [vp, i32, vp]
     lib.spcsc_reconstruct.argtypes = [vp, vp, vp]
@@ -259,6 +260,12 @@ class Handle(object):
         n = ctypes.c_int64(0)
         self._c(self.lib.spcsc_admm_last_timing(self.h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def admm_schedule_info(self):
+        info = (ctypes.c_int32 * 4)()
+        self._c(self.lib.spcsc_admm_schedule_info(self.h, info))
+        return {'row_fwd_v2': bool(info[0]), 'col_v2': bool(info[1]), 'prox_v2': bool(info[2]),
+                'fused': bool(info[3])}
 
     def admm_profile(self, n):
         ms = (ctypes.c_float * 4)()

@@ -251,7 +251,7 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
 // shared memory.  (The v2 profile showed the kernel waiting on its own loads 60 % of the time.)
 // ------------------------------------------------------------------------------------
 template <typename T, int H, int E, int NT>
-SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? 4 : 2))
 k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* SPCSC_RESTRICT Y,
                 T* SPCSC_RESTRICT U,
                 const AdmmState<T>* SPCSC_RESTRICT st, AdmmParams<T> prm, WeightView<T> wl1,

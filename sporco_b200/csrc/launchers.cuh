@@ -26,6 +26,7 @@ struct ProxArgs {
     int nonneg, bnd0, bnd1, reg_on_y;
     int use_v2_sync;             // 1: synchronous-load row kernel (k_row_inv_prox2) even when CX == 1
     void* znext;                 // fused forward output (C2<T>*), or null
+    int prox_threads;            // 128 or 256 threads per CTA for k_row_inv_prox3
 };
 
 enum ColMode {

@@ -148,17 +148,31 @@ static cudaError_t row_inv_prox2_cx(const RowArgs<T>& r, const ProxArgs<T>& p, c
     }
 }
 
+template <typename T, int H, int NT>
+static cudaError_t row_inv_prox3_nt(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
+                                    T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
+    constexpr int E = row2_elems(H, 1), TR = NT / (H / E);
+    if (r.N0 % TR != 0) return cudaErrorInvalidValue;
+    const size_t smem = ((size_t)TR * (3 * H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+    dim3 grid(r.N0 / TR, r.M, r.nb);
+    return launch(k_row_inv_prox3<T, H, E, NT>, grid, dim3(NT), smem, r.stream, Zt,
+                  reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
+                  p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
+                  p.reg_on_y);
+}
+
 template <typename T, int H>
 static cudaError_t row_inv_prox3_go(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
     if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
-        constexpr int E = row2_elems(H, 1), NT = kRow2Threads, TR = row2_tile(H, 1);
-        const size_t smem = ((size_t)TR * (3 * H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
-        dim3 grid(r.N0 / TR, r.M, r.nb);
-        return launch(k_row_inv_prox3<T, H, E, NT>, grid, dim3(NT), smem, r.stream, Zt,
-                      reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
-                      p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
-                      p.reg_on_y);
+        constexpr int E = row2_elems(H, 1);
+        if constexpr ((H / E) <= 4) {
+            if (p.prox_threads == 128) return row_inv_prox3_nt<T, H, 128>(r, p, Zt, Y, U, st, stw);
+        } else {
+            if (p.prox_threads == 128 && r.N0 % (128 / (H / E)) == 0)
+                return row_inv_prox3_nt<T, H, 128>(r, p, Zt, Y, U, st, stw);
+        }
+        return row_inv_prox3_nt<T, H, kRow2Threads>(r, p, Zt, Y, U, st, stw);
     } else {
         return cudaErrorInvalidValue;
     }

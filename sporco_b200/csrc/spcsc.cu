@@ -272,6 +272,7 @@ struct spcsc_handle {
     virtual int admm_get_scalars(double* rho, int* k) = 0;
     virtual int admm_last_timing(float* ms, int64_t* launches) = 0;
     virtual int admm_profile(int n, float* ms4) = 0;
+    virtual int admm_schedule_info(int32_t* info) = 0;
     virtual int get_array(int which, void* out) = 0;
     virtual int set_array(int which, const void* in) = 0;
     virtual int reconstruct(const void* X, void* out) = 0;
@@ -659,6 +660,7 @@ class Engine : public spcsc_handle {
             pa.bnd1 = pb.wd == 1 ? 0 : N1 - (pb.wd - 1);
         }
         pa.reg_on_y = opts.aux_var_obj;
+        pa.prox_threads = (getenv("SPCSC_PROX_NT") && atoi(getenv("SPCSC_PROX_NT")) == 256) ? 256 : 128;
         pa.use_v2_sync = (getenv("SPCSC_ROWPROX") && std::string(getenv("SPCSC_ROWPROX")) == "sync") ? 1 : 0;
         ColLaunch<T> cs = colargs(M, K * Cx);
         cs.st = st.p;
@@ -798,6 +800,11 @@ class Engine : public spcsc_handle {
         return SPCSC_OK;
     }
 
+    int admm_schedule_info(int32_t* info) override {
+        info[0] = v2_rowf; info[1] = v2_col; info[2] = v2_rowp;
+        info[3] = (fuse && !opts.linsolve_check && !opts.joint) ? 1 : 0;
+        return SPCSC_OK;
+    }
     int admm_profile(int n, float* ms4) override {
         AdmmState<T> s0;
         int rc = admm_prepare(n, s0);
@@ -1249,6 +1256,7 @@ int spcsc_admm_get_scalars(spcsc_handle* h, double* rho, int32_t* k) {
 int spcsc_admm_last_timing(spcsc_handle* h, float* ms, int64_t* launches) {
     H_CALL(h->admm_last_timing(ms, launches));
 }
+int spcsc_admm_schedule_info(spcsc_handle* h, int32_t info[4]) { H_CALL(info ? h->admm_schedule_info(info) : SPCSC_ERR_INVALID); }
 int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]) {
     H_CALL(kernel_ms ? h->admm_profile(n_iter, kernel_ms) : SPCSC_ERR_INVALID);
 }
