@@ -45,6 +45,8 @@ struct AdmmParams {
     double inv_n;                        // 1 / (N0*N1)
     int autorho, period, autoscaling, stdres;
     int need_rsdl, need_obj, joint, linsolve_check;
+    int dfid_direct;                     // 1: ACC_DFID already holds the weighted |sum_m Df Yf - Sf|^2 (AuxVarObj)
+    int pad_;
 };
 
 struct StatRow {
@@ -418,12 +420,14 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                         psum[0] += (double)abs2(d[c]);
                     }
                     if (SOLVE == 4) {
-                        const C2<T> sy = sumin[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h];
                         const double e2 = (double)abs2(d[c]);
                         psum[0] += e2;
                         psum[1] += wgt * e2;
-                        const C2<T> dx = s - sy, gy = sy - sf;       // Re(conj(dx) * gy)
-                        psum[2] += (double)(dx.re * gy.re + dx.im * gy.im);
+                        if (sumin) {
+                            const C2<T> sy = sumin[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h];
+                            const C2<T> dx = s - sy, gy = sy - sf;   // Re(conj(dx) * gy)
+                            psum[2] += (double)(dx.re * gy.re + dx.im * gy.im);
+                        }
                     }
                 }
             }
@@ -500,7 +504,7 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             }
             __syncthreads();
         }
-        if (SOLVE == 4) {
+        if (SOLVE == 4 && ref) {
             const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
             double dd[1] = {0.0};
             const C2<T>* rs = ref + slab;
@@ -512,7 +516,8 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             block_accumulate<1>(dd, red, acc + ACC_PGM_RSDL);
         }
         if (DO_INV) col_fft_chunk<T, N0, true>(buf, tw, mc, MC);
-        for (int e = tid; e < mc * N0; e += nt) dst[(size_t)m0 * N0 + e] = buf[e];
+        if (dst)
+            for (int e = tid; e < mc * N0; e += nt) dst[(size_t)m0 * N0 + e] = buf[e];
         __syncthreads();
     }
 }
@@ -675,7 +680,8 @@ SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
         o.dfid = o.regl1 = o.regl21 = o.obj = 0;
         o.xrrs = -1.0;
         if (p.need_obj) {
-            o.dfid = 0.5 * (double)rho * (double)rho * acc[ACC_DFID] * p.inv_n;
+            o.dfid = p.dfid_direct ? 0.5 * acc[ACC_DFID] * p.inv_n
+                                   : 0.5 * (double)rho * (double)rho * acc[ACC_DFID] * p.inv_n;
             o.regl1 = acc[ACC_L1];
             o.regl21 = acc[ACC_L21];
             o.obj = o.dfid + (double)p.lmbda * o.regl1 + (p.joint ? (double)p.mu * o.regl21 : 0.0);

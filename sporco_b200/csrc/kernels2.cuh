@@ -395,7 +395,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
 //   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (gradient)
 // ------------------------------------------------------------------------------------
 template <typename T, int N0, int E, int CPG, int NT, bool DO_FWD, int SOLVE, bool DO_INV>
-SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (CPG == 1 ? 3 : 2))
 k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
        const AdmmState<T>* SPCSC_RESTRICT st, T Lstep, double* SPCSC_RESTRICT acc,

@@ -589,6 +589,7 @@ class Engine : public spcsc_handle {
         prm.need_obj = o->fast_solve ? 0 : 1;
         prm.joint = o->joint;
         prm.linsolve_check = o->linsolve_check;
+        prm.dfid_direct = (o->aux_var_obj && !o->fast_solve) ? 1 : 0;
         configured = true;
         return SPCSC_OK;
     }
@@ -665,7 +666,9 @@ class Engine : public spcsc_handle {
         ColLaunch<T> cs = colargs(M, K * Cx);
         cs.st = st.p;
         cs.acc = acc.p;
-        cs.a.dfid_on = prm.need_obj;
+        cs.a.dfid_on = (prm.need_obj && !prm.dfid_direct) ? 1 : 0;
+        const bool aux_eval = prm.need_obj && prm.dfid_direct;
+        if (aux_eval) CK(Zscratch.ensure(nslab));
         int ne = 0;
         last_launches = 0;
         C2<T>* zin = Zt.p;
@@ -716,6 +719,16 @@ class Engine : public spcsc_handle {
             else
                 CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)zin, Y.p, U.p, (const AdmmState<T>*)st.p));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            if (aux_eval) {
+                // AuxVarObj (admm/cbpdn.py:315-344 with fEvalX False): data fidelity of the
+                // auxiliary variable, 1/2 ||sum_m Df rfftn(Y) - Sf||^2, from a forward transform of Y
+                CK(row_fwd<T>(H, rowargs(M, K * Cx, 1), (const T*)Y.p, (const T*)nullptr,
+                              (const AdmmState<T>*)st.p, Zscratch.p));
+                ColLaunch<T> ce = colargs(M, K * Cx);
+                ce.in = Zscratch.p; ce.out = nullptr; ce.acc = acc.p; ce.st = st.p;
+                CK(col<T>(N0, COL_FWD_EVAL, ce));
+                last_launches += 2;
+            }
             if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
                 // the one exchange of the path: sum the residual / objective accumulators over ranks
                 int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
@@ -749,8 +762,6 @@ class Engine : public spcsc_handle {
         if (!have_dict || !have_signal || !configured)
             FAIL(SPCSC_ERR_STATE, "admm_iterate before set_dict / set_signal / admm_configure");
         if (n <= 0) FAIL(SPCSC_ERR_INVALID, "n_iter must be positive");
-        if (opts.aux_var_obj && !opts.fast_solve)
-            FAIL(SPCSC_ERR_UNSUPPORTED, "AuxVarObj objective evaluation");
         CK(cudaSetDevice(pb.device));
         int rc = read_state(s0);
         if (rc) return rc;

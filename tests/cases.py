@@ -179,3 +179,23 @@ def run_fusion_cases():
     assert rel(Y, r.Y) < 3e-4 and rel(b.X, r.X) < 3e-4
     Y2 = b.solve()            # re-entering runs one more iteration, as the reference does
     assert b.k == r.k + 1
+
+
+def run_auxvarobj_case(dt=np.float64):
+    """AuxVarObj=True: objective evaluated on the auxiliary variable Y (admm/cbpdn.py:151-164,
+    315-344): DFid from rfftn(Y), RegL1 on Y."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(8)
+    D = rng.standard_normal((4, 4, 5)).astype(dt)
+    S = rng.standard_normal((32, 64, 2)).astype(dt)
+    o = {'MaxMainIter': 12, 'RelStopTol': 0.0, 'AuxVarObj': True}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt={'MaxMainIter': 12, 'RelStopTol': 0.0, 'AuxVarObj': True}, dimK=1)
+    its = b.getitstat()
+    tol = 1e-9 if dt == np.float64 else 3e-4
+    assert rel(Y, r.Y) < tol
+    assert rel(its.DFid, [x[2] for x in r.itstat]) < 10 * tol
+    assert rel(its.RegL1, [x[3] for x in r.itstat]) < 10 * tol
+    assert rel(its.ObjFun, [x[1] for x in r.itstat]) < 10 * tol

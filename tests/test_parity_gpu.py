@@ -150,3 +150,8 @@ def test_pgm_vs_oracle_multichannel_dictionary():
 
 def test_cross_iteration_fusion():
     cases.run_fusion_cases()
+
+
+@pytest.mark.parametrize('dt', [np.float64, np.float32])
+def test_aux_var_obj(dt):
+    cases.run_auxvarobj_case(dt)
