@@ -70,6 +70,8 @@ def build(force=False, jobs=None, verbose=False, extra_flags=()):
         obj = os.path.join(BUILD, 'size_%d.o' % n)
         tasks.append((obj, [nvcc] + flags + ['-DSPCSC_SIZE=%d' % n, '-c',
                                             os.path.join(CSRC, 'size_inst.cu'), '-o', obj]))
+    obj = os.path.join(BUILD, 'gen.o')
+    tasks.append((obj, [nvcc] + flags + ['-c', os.path.join(CSRC, 'gen_inst.cu'), '-o', obj]))
     obj = os.path.join(BUILD, 'spcsc.o')
     tasks.append((obj, [nvcc] + flags + ['-c', os.path.join(CSRC, 'spcsc.cu'), '-o', obj]))
     jobs = jobs or min(len(tasks), os.cpu_count() or 4)

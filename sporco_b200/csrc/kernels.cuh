@@ -338,9 +338,29 @@ SPCSC_DEV void hpd_solve(C2<T> (&A)[MAXCD][MAXCD], C2<T> (&bvec)[MAXCD], int n) 
     }
 }
 
-template <typename T, int N0>
-SPCSC_DEV void col_load_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT src, int m0, int mc) {
+template <typename T>
+SPCSC_DEV void col_load_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT src, int m0, int mc, int N0) {
     for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) buf[e] = src[(size_t)m0 * N0 + e];
+    __syncthreads();
+}
+// Any-length column transform: direct DFT from the twiddle table into `buf2`, then copy back.
+template <typename T, bool INV>
+SPCSC_DEV void col_dft_chunk(C2<T>* buf, C2<T>* buf2, const C2<T>* SPCSC_RESTRICT tw, int mc, int N0) {
+    for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) {
+        const int col = e / N0, k = e - col * N0;
+        const C2<T>* x = buf + (size_t)col * N0;
+        C2<T> s = mk<T>(0, 0);
+        int idx = 0;
+        for (int n = 0; n < N0; ++n) {
+            const C2<T> w = tw[idx];
+            s = s + (INV ? mulc(x[n], w) : x[n] * w);
+            idx += k;
+            if (idx >= N0) idx -= N0;
+        }
+        buf2[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) buf[e] = buf2[e];
     __syncthreads();
 }
 template <typename T, int N0, bool INV>
@@ -355,7 +375,7 @@ SPCSC_DEV void col_fft_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT tw, int mc,
     }
 }
 
-template <typename T, int N0, bool DO_FWD, int SOLVE, bool DO_INV>
+template <typename T, int N0T, bool DO_FWD, int SOLVE, bool DO_INV>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out,
                         const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
                         const C2<T>* SPCSC_RESTRICT G, C2<T>* SPCSC_RESTRICT sumout,
@@ -365,12 +385,15 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                         ColArgs a) {
     if (st && st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
+    constexpr bool GEN = (N0T == 0);             // 0: run-time length, direct DFT (any size)
+    const int N0 = GEN ? a.N0 : N0T;
     constexpr int MAXCD = 4;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int wf = blockIdx.x, b = blockIdx.y;
     const int M = a.M, Cd = a.Cd, MC = a.MC;
     C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);                 // [MC][N0]
-    C2<T>* spart = buf + (size_t)MC * N0;                             // [Cd][parts][N0]
+    C2<T>* buf2 = buf + (size_t)MC * N0;                              // [MC][N0], direct-DFT path only
+    C2<T>* spart = buf + (size_t)MC * N0 * (GEN ? 2 : 1);             // [Cd][parts][N0]
     const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
     const C2<T>* src = in + slab;
     C2<T>* dst = out ? out + slab : nullptr;
@@ -384,8 +407,11 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
         __syncthreads();
         for (int ch = 0; ch < a.nchunk; ++ch) {
             const int m0 = ch * MC, mc = (M - m0 < MC) ? M - m0 : MC;
-            col_load_chunk<T, N0>(buf, src, m0, mc);
-            if (DO_FWD) col_fft_chunk<T, N0, false>(buf, tw, mc, MC);
+            col_load_chunk<T>(buf, src, m0, mc, N0);
+            if (DO_FWD) {
+                if constexpr (GEN) col_dft_chunk<T, false>(buf, buf2, tw, mc, N0);
+                else col_fft_chunk<T, N0T, false>(buf, tw, mc, MC);
+            }
             for (int e = tid; e < parts * N0; e += nt) {
                 const int part = e / N0, h = e - part * N0;
                 for (int c = 0; c < Cd; ++c) {
@@ -487,8 +513,11 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
     for (int ch = 0; ch < a.nchunk; ++ch) {
         const int m0 = ch * MC, mc = (M - m0 < MC) ? M - m0 : MC;
         if (!(resident && SOLVE != 0)) {
-            col_load_chunk<T, N0>(buf, src, m0, mc);
-            if (DO_FWD) col_fft_chunk<T, N0, false>(buf, tw, mc, MC);
+            col_load_chunk<T>(buf, src, m0, mc, N0);
+            if (DO_FWD) {
+                if constexpr (GEN) col_dft_chunk<T, false>(buf, buf2, tw, mc, N0);
+                else col_fft_chunk<T, N0T, false>(buf, tw, mc, MC);
+            }
         }
         if (SOLVE == 1 || SOLVE == 2) {
             const int parts = a.parts;
@@ -515,7 +544,10 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             dd[0] *= wgt;
             block_accumulate<1>(dd, red, acc + ACC_PGM_RSDL);
         }
-        if (DO_INV) col_fft_chunk<T, N0, true>(buf, tw, mc, MC);
+        if (DO_INV) {
+            if constexpr (GEN) col_dft_chunk<T, true>(buf, buf2, tw, mc, N0);
+            else col_fft_chunk<T, N0T, true>(buf, tw, mc, MC);
+        }
         if (dst)
             for (int e = tid; e < mc * N0; e += nt) dst[(size_t)m0 * N0 + e] = buf[e];
         __syncthreads();

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "kernels2.cuh"
+#include "kernels_gen.cuh"
 
 namespace spcsc {
 
@@ -13,6 +14,7 @@ template <typename T>
 struct RowArgs {
     int N0, M, nb, TR;           // rows per image, filters, batch (K*Cx or Cd ...), rows per CTA
     int Cx;                      // channels handled together by the prox kernel
+    int N1, gen;                 // gen: any-size direct-DFT path (N1 is then the real row length)
     const C2<T>* tw;             // exp(-2 pi i j / N1), j < N1
     cudaStream_t stream;
 };
@@ -57,6 +59,7 @@ struct ColLaunch {
     int nb;                      // slabs per frequency column (grid.y)
     ColArgs a;                   // MC / nchunk / parts filled by the launcher
     int cpg;                     // v2: columns kept in registers per lane group (1 or 2)
+    int gen;                     // any-size direct-DFT path (a.N0 holds the run-time length)
     cudaStream_t stream;
 };
 
@@ -82,6 +85,25 @@ cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p,
 // columns
 template <typename T, int N0>
 cudaError_t col_launch(int mode, ColLaunch<T> c);
+
+// ---- any-size path (kernels_gen.cuh, k_col<T, 0, ...>)
+template <typename T>
+struct GenRowArgs {
+    int N0, N1, M, nb, Cx, TR;
+    const C2<T>* tw;
+    cudaStream_t stream;
+};
+template <typename T>
+cudaError_t row_fwd_gen_launch(const GenRowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
+                               C2<T>* Zt);
+template <typename T>
+cudaError_t row_inv_gen_launch(const GenRowArgs<T>& r, const C2<T>* Zt, T* X, T scale);
+template <typename T>
+cudaError_t row_inv_prox_gen_launch(const GenRowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
+                                    T* Y, T* U, const AdmmState<T>* st);
+template <typename T>
+cudaError_t row_inv_prox_fwd_gen_launch(const GenRowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt,
+                                        T* X);
 
 // ---- kernel set v2 (kernels2.cuh): plans and eligibility ------------------------------
 constexpr int kRow2Threads = 256;

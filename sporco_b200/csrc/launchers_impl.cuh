@@ -65,9 +65,12 @@ cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p,
 }
 
 // Choose threads / chunking for the column kernel.
-template <typename T, int N0>
+template <typename T, int N0T>
 inline void col_plan(ColArgs& a, int& nthreads, size_t& smem) {
-    constexpr int TPF = fft_tpf<T, N0>();
+    constexpr bool GEN = (N0T == 0);
+    const int N0 = GEN ? a.N0 : N0T;
+    int TPF = 1;
+    if constexpr (!GEN) TPF = fft_tpf<T, N0T>();
     const int maxt = sizeof(T) == 4 ? 1024 : 512;
     const size_t sz = sizeof(C2<T>);
     int want = round_up32(a.M * TPF);
@@ -80,12 +83,12 @@ inline void col_plan(ColArgs& a, int& nthreads, size_t& smem) {
     a.parts = parts;
     const size_t fixed = (size_t)a.Cd * parts * N0 * sz + 64 * sizeof(double);
     size_t room = kSmemLimit - fixed;
-    int mc = (int)(room / ((size_t)N0 * sz));
+    int mc = (int)(room / ((size_t)N0 * sz * (GEN ? 2 : 1)));
     if (mc > a.M) mc = a.M;
     if (mc < 1) mc = 1;
     a.MC = mc;
     a.nchunk = (a.M + mc - 1) / mc;
-    smem = (size_t)mc * N0 * sz + fixed;
+    smem = (size_t)mc * N0 * sz * (GEN ? 2 : 1) + fixed;
 }
 
 template <typename T, int N0, bool F, int S, bool I>
@@ -100,7 +103,7 @@ static cudaError_t col_go(ColLaunch<T>& c) {
 
 template <typename T, int N0>
 cudaError_t col_launch(int mode, ColLaunch<T> c) {
-    c.a.N0 = N0;
+    if (N0 != 0) c.a.N0 = N0;
     switch (mode) {
         case COL_FWD: return col_go<T, N0, true, 0, false>(c);
         case COL_INV: return col_go<T, N0, false, 0, true>(c);
@@ -114,6 +117,62 @@ cudaError_t col_launch(int mode, ColLaunch<T> c) {
     }
 }
 
+
+// ---- any-size path --------------------------------------------------------------------
+template <typename T>
+inline int gen_threads(int work) {
+    int nt = round_up32(work);
+    return nt > 256 ? 256 : (nt < 32 ? 32 : nt);
+}
+template <typename T>
+cudaError_t row_fwd_gen_launch(const GenRowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
+                               C2<T>* Zt) {
+    const size_t smem = (size_t)r.TR * r.N1 * sizeof(T);
+    dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb);
+    return launch(k_row_fwd_gen<T>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream, A, B, st,
+                  Zt, r.tw, r.N0, r.N1, r.M, r.TR);
+}
+template <typename T>
+cudaError_t row_inv_gen_launch(const GenRowArgs<T>& r, const C2<T>* Zt, T* X, T scale) {
+    const int N1f = r.N1 / 2 + 1;
+    const size_t smem = (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)r.TR * r.N1 * sizeof(T);
+    dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb);
+    return launch(k_row_inv_gen<T>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream, Zt, X,
+                  r.tw, r.N0, r.N1, r.M, r.TR, scale);
+}
+template <typename T, int CX>
+static cudaError_t row_inv_prox_gen_cx(const GenRowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
+                                       T* Y, T* U, const AdmmState<T>* st) {
+    const int N1f = r.N1 / 2 + 1;
+    size_t smem = (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)CX * r.TR * r.N1 * sizeof(T);
+    if (smem < 7 * 32 * sizeof(double)) smem = 7 * 32 * sizeof(double);
+    dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb / CX);
+    return launch(k_row_inv_prox_gen<T, CX>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream,
+                  Zt, Y, U, st, p.prm, p.wl1, p.wl21, p.acc, r.tw, r.N0, r.N1, r.M, r.TR, p.scale,
+                  p.nonneg, p.bnd0, p.bnd1, p.reg_on_y);
+}
+template <typename T>
+cudaError_t row_inv_prox_gen_launch(const GenRowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
+                                    T* Y, T* U, const AdmmState<T>* st) {
+    switch (r.Cx) {
+        case 1: return row_inv_prox_gen_cx<T, 1>(r, p, Zt, Y, U, st);
+        case 2: return row_inv_prox_gen_cx<T, 2>(r, p, Zt, Y, U, st);
+        case 3: return row_inv_prox_gen_cx<T, 3>(r, p, Zt, Y, U, st);
+        case 4: return row_inv_prox_gen_cx<T, 4>(r, p, Zt, Y, U, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template <typename T>
+cudaError_t row_inv_prox_fwd_gen_launch(const GenRowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt,
+                                        T* X) {
+    const int N1f = r.N1 / 2 + 1;
+    size_t smem = (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)r.TR * r.N1 * sizeof(T);
+    if (smem < 32 * sizeof(double)) smem = 32 * sizeof(double);
+    dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb);
+    return launch(k_row_inv_prox_fwd_gen<T>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream,
+                  Vt, X, p.thr_scale, p.wl1, p.acc, r.tw, r.N0, r.N1, r.M, r.Cx, r.TR, p.scale,
+                  p.nonneg, p.bnd0, p.bnd1);
+}
 
 // ---- kernel set v2 -----------------------------------------------------------------
 template <typename T, int H>

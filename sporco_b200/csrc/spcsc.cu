@@ -43,8 +43,16 @@ SPCSC_FOR_SIZES(SPCSC_DECL)
 static bool supported_len(int n) { return n >= 2 && n <= 1024 && (n & (n - 1)) == 0; }
 
 template <typename T>
+static GenRowArgs<T> gen_args(const RowArgs<T>& r) {
+    GenRowArgs<T> g;
+    g.N0 = r.N0; g.N1 = r.N1; g.M = r.M; g.nb = r.nb; g.Cx = r.Cx; g.TR = r.TR; g.tw = r.tw;
+    g.stream = r.stream;
+    return g;
+}
+template <typename T>
 static cudaError_t row_fwd(int H, const RowArgs<T>& r, const T* A, const T* B,
                            const AdmmState<T>* st, C2<T>* Zt) {
+    if (r.gen) return row_fwd_gen_launch<T>(gen_args(r), A, B, st, Zt);
     switch (H) {
 #define X(n) case n: return row_fwd_launch<T, n>(r, A, B, st, Zt);
         SPCSC_FOR_SIZES(X)
@@ -54,6 +62,7 @@ static cudaError_t row_fwd(int H, const RowArgs<T>& r, const T* A, const T* B,
 }
 template <typename T>
 static cudaError_t row_inv(int H, const RowArgs<T>& r, const C2<T>* Zt, T* Xo, T scale) {
+    if (r.gen) return row_inv_gen_launch<T>(gen_args(r), Zt, Xo, scale);
     switch (H) {
 #define X(n) case n: return row_inv_launch<T, n>(r, Zt, Xo, scale);
         SPCSC_FOR_SIZES(X)
@@ -64,6 +73,7 @@ static cudaError_t row_inv(int H, const RowArgs<T>& r, const C2<T>* Zt, T* Xo, T
 template <typename T>
 static cudaError_t row_inv_prox(int H, const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                 T* Y, T* U, const AdmmState<T>* st) {
+    if (r.gen) return row_inv_prox_gen_launch<T>(gen_args(r), p, Zt, Y, U, st);
     switch (H) {
 #define X(n) case n: return row_inv_prox_launch<T, n>(r, p, Zt, Y, U, st);
         SPCSC_FOR_SIZES(X)
@@ -74,6 +84,7 @@ static cudaError_t row_inv_prox(int H, const RowArgs<T>& r, const ProxArgs<T>& p
 template <typename T>
 static cudaError_t row_inv_prox_fwd(int H, const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt,
                                     T* Xo) {
+    if (r.gen) return row_inv_prox_fwd_gen_launch<T>(gen_args(r), p, Vt, Xo);
     switch (H) {
 #define X(n) case n: return row_inv_prox_fwd_launch<T, n>(r, p, Vt, Xo);
         SPCSC_FOR_SIZES(X)
@@ -83,6 +94,7 @@ static cudaError_t row_inv_prox_fwd(int H, const RowArgs<T>& r, const PgmRowArgs
 }
 template <typename T>
 static cudaError_t col(int N0, int mode, const ColLaunch<T>& c) {
+    if (c.gen) return col_launch<T, 0>(mode, c);
     switch (N0) {
 #define X(n) case n: return col_launch<T, n>(mode, c);
         SPCSC_FOR_SIZES(X)
@@ -353,6 +365,7 @@ class Engine : public spcsc_handle {
     spcsc_pgm_opts popts;
     bool pgm_ready = false, pgm_have_cand = false;
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
+    bool gen_rows = false, gen_cols = false;   // any-size direct-DFT path for this axis
     int col_cpg = kCol2CPG;
     bool fuse = false;          // prox kernel also emits the next iteration's row spectra
     bool fused_batch = false, x_in_zt2 = false;
@@ -375,6 +388,8 @@ class Engine : public spcsc_handle {
 
     explicit Engine(const spcsc_problem& p) : pb(p) {
         N0 = p.N0; N1 = p.N1; H = N1 / 2; N1f = H + 1;
+        gen_rows = (N1 & 1) || !supported_len(N1 / 2);
+        gen_cols = !supported_len(N0);
         C = p.C; Cd = p.Cd; K = p.K; M = p.M;
         Cx = C - Cd + 1;
         nreal = (size_t)K * Cx * M * N0 * N1;
@@ -421,9 +436,9 @@ class Engine : public spcsc_handle {
         {
             const char* force = getenv("SPCSC_KERNELS");
             const bool allow2 = !(force && std::string(force) == "v1");
-            v2_rowf = allow2 && row2_ok<T>(H, N0, 1);
-            v2_rowp = allow2 && row2_ok<T>(H, N0, Cx);
-            v2_col = allow2 && col2_ok<T>(N0, M, Cd);
+            v2_rowf = allow2 && !gen_rows && row2_ok<T>(H, N0, 1);
+            v2_rowp = allow2 && !gen_rows && row2_ok<T>(H, N0, Cx);
+            v2_col = allow2 && !gen_cols && col2_ok<T>(N0, M, Cd);
             if (const char* e = getenv("SPCSC_COL_CPG")) col_cpg = (atoi(e) == 1) ? 1 : 2;
             const char* fz = getenv("SPCSC_FUSE");
             fuse = v2_rowf && v2_rowp && Cx == 1 && !(fz && std::string(fz) == "0");
@@ -455,7 +470,8 @@ class Engine : public spcsc_handle {
     RowArgs<T> rowargs(int m, int nb, int cx) const {
         RowArgs<T> r;
         r.N0 = N0; r.M = m; r.nb = nb; r.Cx = cx;
-        r.TR = row_tile<T>(H, N0, cx);
+        r.N1 = N1; r.gen = gen_rows ? 1 : 0;
+        r.TR = gen_rows ? (N0 < 8 ? N0 : 8) : row_tile<T>(H, N0, cx);
         r.tw = tw_row.p;
         r.stream = stream;
         return r;
@@ -471,6 +487,7 @@ class Engine : public spcsc_handle {
         c.stream = stream;
         c.Lstep = 1;
         c.cpg = col_cpg;
+        c.gen = gen_cols ? 1 : 0;
         return c;
     }
 
@@ -1011,7 +1028,7 @@ class Engine : public spcsc_handle {
             pr.bnd1 = pb.wd == 1 ? 0 : N1 - (pb.wd - 1);
         }
         RowArgs<T> rr = rowargs(M, K * Cx, Cx);
-        rr.TR = row_tile<T>(H, N0, 1);
+        if (!gen_rows) rr.TR = row_tile<T>(H, N0, 1);
         CK(row_inv_prox_fwd<T>(H, rr, pr, Zt.p, Y.p));
         // forward columns + evaluation of the candidate against Yf
         ColLaunch<T> c3 = colargs(M, K * Cx);
@@ -1059,8 +1076,8 @@ int check_problem(const spcsc_problem* p, std::string& err) {
     }
     if (p->Cd > 1 && p->Cd != p->C) { err = "multi-channel dictionary needs C == Cd"; return SPCSC_ERR_INVALID; }
     if (p->hd > p->N0 || p->wd > p->N1) { err = "filter support larger than the signal"; return SPCSC_ERR_INVALID; }
-    if (!supported_len(p->N0) || !supported_len(p->N1 / 2) || (p->N1 & 1)) {
-        err = "unsupported spatial size: N0 must be a power of two in [2,1024], N1 in [4,2048]";
+    if (p->N1 < 2 || p->N0 > 8192 || p->N1 > 8192) {
+        err = "unsupported spatial size (need N1 >= 2 and both axes <= 8192)";
         return SPCSC_ERR_UNSUPPORTED;
     }
     return SPCSC_OK;

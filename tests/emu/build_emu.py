@@ -51,6 +51,8 @@ def build(force=False):
         obj = os.path.join(BUILD, 'size_%d.o' % n)
         tasks.append((obj, ['g++'] + FLAGS + ['-DSPCSC_SIZE=%d' % n, '-c',
                                              os.path.join(CSRC, 'size_inst.cu'), '-o', obj]))
+    obj = os.path.join(BUILD, 'gen.o')
+    tasks.append((obj, ['g++'] + FLAGS + ['-c', os.path.join(CSRC, 'gen_inst.cu'), '-o', obj]))
     obj = os.path.join(BUILD, 'spcsc.o')
     tasks.append((obj, ['g++'] + FLAGS + ['-c', os.path.join(CSRC, 'spcsc.cu'), '-o', obj]))
     obj = os.path.join(BUILD, 'cuda_emu.o')
