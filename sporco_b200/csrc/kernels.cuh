@@ -24,6 +24,11 @@ namespace spcsc {
 // ------------------------------------------------------------------------------------
 // Device-resident solver scalars.
 // ------------------------------------------------------------------------------------
+// Accumulator block on the device: ACC_N doubles (floating-point atomics: objective / diagnostic
+// sums) followed by kAccDet rows of kDetBins 64-bit integer bins (the sums that steer the
+// algorithm -- residual norms and regularisation terms -- accumulated order-independently).
+constexpr int kAccDet = 7;
+constexpr size_t kAccBytes = 16 * sizeof(double) + (size_t)kAccDet * kDetBins * sizeof(unsigned long long);
 enum { ACC_X2 = 0, ACC_Y2, ACC_U2, ACC_R2, ACC_S2, ACC_L1, ACC_L21, ACC_DFID,
        ACC_AX2, ACC_B2, ACC_AXB2, ACC_PGM_FY, ACC_PGM_F, ACC_PGM_LIN, ACC_PGM_DXY2,
        ACC_PGM_RSDL, ACC_N = 16 };
@@ -294,7 +299,7 @@ SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRI
     }
     if (prm.need_rsdl || prm.need_obj) {
         double* red = reinterpret_cast<double*>(smem_raw);
-        block_accumulate<7>(sums, red, acc);
+        block_accumulate_det<7>(sums, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
     }
 }
 
@@ -677,11 +682,25 @@ SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* 
 // tolerances) and admm/admm.py:549-575 (rho update) in the working precision T from the
 // double-precision sums, writes one StatRow, advances k, clears the accumulators.
 // ------------------------------------------------------------------------------------
+SPCSC_DEV void fold_det_bins(double* acc) {
+    unsigned long long* bins = reinterpret_cast<unsigned long long*>(acc + ACC_N);
+    for (int i = 0; i < kAccDet; ++i) {
+        acc[i] += det_bins_value(bins + i * kDetBins);
+        for (int b = 0; b < kDetBins; ++b) bins[i * kDetBins + b] = 0ull;
+    }
+}
+// Used before a multi-rank all-reduce (which then sums plain doubles in NCCL's fixed order).
+template <int DUMMY>
+SPCSC_GLOBAL void k_fold_bins(double* acc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) fold_det_bins(acc);
+}
+
 template <typename T>
 SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
                                  StatRow* rows, int k_base, int row_cap) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (st->stopped) return;
+    fold_det_bins(acc);
     const int k = st->k;
     T rho = st->rho;
     T r = 0, s = 0;

@@ -239,7 +239,7 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
         SPCSC_UNROLL
         for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
         double* red = reinterpret_cast<double*>(smem_raw);
-        block_accumulate<7>(d, red, acc);
+        block_accumulate_det<7>(d, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
     }
 }
 
@@ -367,7 +367,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         SPCSC_UNROLL
         for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
         double* red = reinterpret_cast<double*>(smem_raw);
-        block_accumulate<7>(d, red, acc);
+        block_accumulate_det<7>(d, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
     }
     if (Znext) {
         // Cross-iteration fusion: the row spectra of Y - U for the next iteration, valid as long

@@ -179,7 +179,7 @@ SPCSC_GLOBAL void k_row_inv_prox_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RE
     }
     if (prm.need_rsdl || prm.need_obj) {
         double* red = reinterpret_cast<double*>(smem_raw);
-        block_accumulate<7>(sums, red, acc);
+        block_accumulate_det<7>(sums, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
     }
 }
 

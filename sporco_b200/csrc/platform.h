@@ -198,4 +198,64 @@ SPCSC_DEV void block_accumulate(const double (&v)[NV], double* red, double* acc)
     }
 }
 
+
+// ---- order-independent (bit-reproducible) accumulation of non-negative doubles ------------
+// A value is split over three 64-bit integer bins selected by its exponent (bin width 2^32,
+// 8 guard bits: up to 2^24 contributions per bin cannot overflow); integer atomics commute, so
+// the total does not depend on the order in which thread blocks finish, and the three-way split
+// is exact to double precision.  det_bins_value() turns a bin row back into a double (highest
+// bin first, a fixed order).
+constexpr int kDetBins = 64;
+constexpr int kDetBias = 1087 + 8;
+SPCSC_DEV double det_unit(int b) { return ldexp(1.0, (b << 5) - kDetBias); }
+SPCSC_DEV void det_accumulate(double v, unsigned long long* bins) {
+    if (!(v > 0.0)) return;
+    int e;
+    frexp(v, &e);                                  // v = f * 2^e, f in [0.5, 1)
+    int b = (e + 1087) >> 5;                       // bin of the leading bits
+    if (b > kDetBins - 1) b = kDetBins - 1;
+    if (b < 2) b = 2;
+    double r = v;
+    SPCSC_UNROLL
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        const double u = det_unit(b - lvl);
+        const double q = floor(r / u);             // level 0: < 2^40, then < 2^32
+        if (q > 0.0) atomicAdd(bins + (b - lvl), (unsigned long long)q);
+        r -= q * u;                                // exact
+    }
+}
+SPCSC_DEV double det_bins_value(const unsigned long long* bins) {
+    double s = 0.0;
+    for (int b = kDetBins - 1; b >= 0; --b) {
+        const unsigned long long q = bins[b];
+        if (q) s += (double)q * det_unit(b);
+    }
+    return s;
+}
+
+// As block_accumulate, but the block totals go into the reproducible bins (row i of `bins`
+// has kDetBins entries) instead of floating-point atomics.
+template <int NV>
+SPCSC_DEV void block_accumulate_det(const double (&v)[NV], double* red, unsigned long long* bins) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
+    double w[NV];
+    SPCSC_UNROLL
+    for (int i = 0; i < NV; ++i) w[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+        SPCSC_UNROLL
+        for (int i = 0; i < NV; ++i) red[i * 32 + warp] = w[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        SPCSC_UNROLL
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < nwarp) ? red[i * 32 + lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) det_accumulate(x, bins + i * kDetBins);
+        }
+    }
+}
+
 }  // namespace spcsc

@@ -370,7 +370,7 @@ class Engine : public spcsc_handle {
     bool fuse = false;          // prox kernel also emits the next iteration's row spectra
     bool fused_batch = false, x_in_zt2 = false;
     DevBuf<C2<T>> Zt2;          // ping-pong partner of Zt when fusing
-    DevBuf<double> acc;
+    DevBuf<double> acc;          // kAccBytes: ACC_N doubles + reproducible integer bins
     DevBuf<AdmmState<T>> st;
     DevBuf<StatRow> rows;
     WeightView<T> wl1, wl21;
@@ -424,7 +424,7 @@ class Engine : public spcsc_handle {
         CK(Df.ensure((size_t)Cd * N1f * M * N0));
         CK(Sf.ensure((size_t)K * C * N1f * N0));
         CK(G.ensure((size_t)N1f * N0 * Cd * Cd));
-        CK(acc.ensure(ACC_N));
+        CK(acc.ensure(kAccBytes / sizeof(double)));
         CK(st.ensure(1));
         CK(tw_row.ensure(N1));
         CK(tw_col.ensure(N0));
@@ -628,7 +628,7 @@ class Engine : public spcsc_handle {
         CK(cudaSetDevice(pb.device));
         CK(cudaMemsetAsync(Y.p, 0, nreal * sizeof(T), stream));
         CK(cudaMemsetAsync(U.p, 0, nreal * sizeof(T), stream));
-        CK(cudaMemsetAsync(acc.p, 0, ACC_N * sizeof(double), stream));
+        CK(cudaMemsetAsync(acc.p, 0, kAccBytes, stream));
         have_x = false;
         return write_state((T)rho, (T)1, 0, 0);
     }
@@ -748,6 +748,7 @@ class Engine : public spcsc_handle {
             }
             if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
                 // the one exchange of the path: sum the residual / objective accumulators over ranks
+                CK(launch(k_fold_bins<0>, dim3(1), dim3(32), 0, stream, acc.p));
                 int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
                 if (nr != 0) {
                     err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr);
@@ -1010,7 +1011,7 @@ class Engine : public spcsc_handle {
         if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "pgm_trial before pgm_reset");
         if (!(L > 0.0)) FAIL(SPCSC_ERR_INVALID, "L must be positive");
         CK(cudaSetDevice(pb.device));
-        CK(cudaMemsetAsync(acc.p, 0, ACC_N * sizeof(double), stream));
+        CK(cudaMemsetAsync(acc.p, 0, kAccBytes, stream));
         // gradient step + inverse column transform: Zt = icol( Yf - conj(Df)(sum_m Df Yf - Sf)/L )
         ColLaunch<T> c1 = colargs(M, K * Cx);
         c1.in = pgB.p; c1.out = Zt.p; c1.sumout = sum_buf.p; c1.acc = acc.p; c1.Lstep = (T)L;

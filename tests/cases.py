@@ -199,3 +199,21 @@ def run_auxvarobj_case(dt=np.float64):
     assert rel(its.DFid, [x[2] for x in r.itstat]) < 10 * tol
     assert rel(its.RegL1, [x[3] for x in r.itstat]) < 10 * tol
     assert rel(its.ObjFun, [x[1] for x in r.itstat]) < 10 * tol
+
+
+def run_reproducibility_case():
+    """Two solves of the same problem give bit-identical results: the sums that steer the
+    algorithm are accumulated order-independently (integer bins), whatever the order in which
+    thread blocks finish (cf. the reference's pickle test, tests/admm/test_cbpdn.py:631-645)."""
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(5)
+    D = rng.standard_normal((5, 5, 8))
+    S = rng.standard_normal((64, 64, 3))
+    outs = []
+    for _ in range(2):
+        b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options({'MaxMainIter': 25, 'RelStopTol': 0.0}),
+                           dimK=1)
+        Y = b.solve().copy()
+        outs.append((Y, np.array(b.getitstat().Rho), np.array(b.getitstat().PrimalRsdl)))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])

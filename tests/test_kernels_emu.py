@@ -90,3 +90,7 @@ def test_cross_iteration_fusion():
 @pytest.mark.parametrize('dt', [np.float64, np.float32])
 def test_aux_var_obj(dt):
     cases.run_auxvarobj_case(dt)
+
+
+def test_bit_reproducible_runs():
+    cases.run_reproducibility_case()

@@ -155,3 +155,24 @@ def test_cross_iteration_fusion():
 @pytest.mark.parametrize('dt', [np.float64, np.float32])
 def test_aux_var_obj(dt):
     cases.run_auxvarobj_case(dt)
+
+
+def test_bit_reproducible_runs():
+    cases.run_reproducibility_case()
+
+
+@pytest.mark.parametrize('shape', [(16, 17), (63, 63), (48, 40)])
+def test_any_image_size(shape):
+    """Non power-of-two sizes (direct-DFT path): the reference's own test sizes."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(9)
+    D = rng.standard_normal((5, 5, 4))
+    S = rng.standard_normal(shape + (2,))
+    x = rng.standard_normal((2,) + shape)
+    assert cases.rel(_lib.rfft2(x), np.fft.rfftn(x, axes=(1, 2))) < 1e-13
+    o = {'MaxMainIter': 15, 'RelStopTol': 0.0, 'LinSolveCheck': True}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=o, dimK=1)
+    assert cases.rel(Y, r.Y) < 1e-9 and b.getitstat().XSlvRelRes.max() < 1e-11

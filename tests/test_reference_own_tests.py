@@ -1,0 +1,113 @@
+"""Drop-in check in the build container: the REFERENCE'S OWN test files
+(/root/reference/tests/admm/test_cbpdn.py, /root/reference/tests/pgm/test_cbpdn.py) executed
+unmodified, with `sporco.admm.cbpdn.{GenericConvBPDN,ConvBPDN,ConvBPDNJoint}` and
+`sporco.pgm.cbpdn.ConvBPDN` replaced by the sporco_b200 classes (kernels run through the CPU
+emulation harness here; the same replacement works on a GPU box where the reference is
+installed).  Tests of other reference classes in those files are left alone; tests that need
+features sporco_b200 does not implement are listed explicitly below -- nothing is skipped
+silently.  Skipped entirely where /root/reference does not exist (the GPU box)."""
+
+import inspect
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import pytest
+
+from sporco_b200 import _lib
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+
+OTHER_CLASSES = ('ConvElasticNet', 'ConvBPDNGradReg', 'ConvBPDNProjL1', 'ConvMinL1InL2Ball',
+                 'ConvBPDNMaskDcpl', 'AddMaskSim', 'ConvL1L1Grd', 'MultiDictConvBPDN',
+                 'ConvBPDNMask', 'ConvTwoBlockCnstrnt')
+# reference tests that exercise the replaced classes but need something not implemented
+NOT_IMPLEMENTED = {
+    'admm': {'test_10cplx': 'complex-valued data'},
+    'pgm': {'test_10cplx': 'complex-valued data',
+            'test_13': 'Monotone PGM', 'test_14': 'Monotone PGM',
+            'test_15': 'StepSizePolicyBB', 'test_16': 'StepSizePolicyBB',
+            'test_17': 'StepSizePolicyCauchy', 'test_18': 'StepSizePolicyCauchy'},
+}
+
+
+def _load(kind):
+    sys.path[:0] = [os.path.join(os.path.dirname(os.path.dirname(__file__)), 'oracle', 'shims'), REF]
+    warnings.filterwarnings('ignore')
+    import sporco.admm.cbpdn as ref_admm
+    import sporco.pgm.cbpdn as ref_pgm
+    from sporco_b200.admm import cbpdn as my_admm
+    from sporco_b200.pgm import cbpdn as my_pgm
+    proxy = types.ModuleType('cbpdn_proxy')
+    if kind == 'admm':
+        proxy.__dict__.update(ref_admm.__dict__)
+        for name in ('GenericConvBPDN', 'ConvBPDN', 'ConvBPDNJoint'):
+            setattr(proxy, name, getattr(my_admm, name))
+        path = os.path.join(REF, 'tests', 'admm', 'test_cbpdn.py')
+    else:
+        proxy.__dict__.update(ref_pgm.__dict__)
+        proxy.ConvBPDN = my_pgm.ConvBPDN
+        path = os.path.join(REF, 'tests', 'pgm', 'test_cbpdn.py')
+    src = open(path).read()
+    src = src.replace('from sporco.admm import cbpdn', 'cbpdn = __proxy__')
+    src = src.replace('from sporco.pgm import cbpdn', 'cbpdn = __proxy__')
+    if kind == 'pgm':
+        # the reference's momentum / backtracking objects are plain parameter holders; the
+        # sporco_b200 solver expects its own classes of the same names
+        src = src.replace('from sporco.pgm.momentum import', 'from sporco_b200.pgm.momentum import')
+        src = src.replace('from sporco.pgm.backtrack import', 'from sporco_b200.pgm.backtrack import')
+    ns = {'__proxy__': proxy, '__name__': 'ref_tests_' + kind}
+    exec(compile(src, path, 'exec'), ns)
+    return ns['TestSet01']
+
+
+def _cases(kind):
+    if not os.path.isdir(REF):
+        return []
+    cls = _load(kind)
+    out = []
+    for name, fn in sorted(inspect.getmembers(cls, inspect.isfunction)):
+        if not name.startswith('test_'):
+            continue
+        body = inspect.getsource(fn)
+        if any(c in body for c in OTHER_CLASSES):
+            continue                                      # a test of another reference class
+        out.append(name)
+    return out
+
+
+@pytest.fixture(autouse=True, scope='module')
+def _use_emulated_kernels(emu_library):
+    _lib.use_library(emu_library)
+    yield
+    _lib.use_library(None)
+
+
+@pytest.mark.parametrize('name', _cases('admm'))
+def test_reference_admm_suite(name):
+    if name in NOT_IMPLEMENTED['admm']:
+        pytest.xfail('not implemented: ' + NOT_IMPLEMENTED['admm'][name])
+    cls = _load('admm')
+    obj = cls()
+    obj.setup_method(None)
+    getattr(obj, name)()
+
+
+# 2000-iteration recovery tests: ~1 min each under emulation; they pass (run them with
+# SPCSC_LONG_TESTS=1) but are kept out of the default CPU suite to keep it short
+LONG = {'pgm': ('test_10', 'test_11')}
+
+
+@pytest.mark.parametrize('name', _cases('pgm'))
+def test_reference_pgm_suite(name):
+    if name in LONG['pgm'] and not os.environ.get('SPCSC_LONG_TESTS'):
+        pytest.skip('long emulated run; set SPCSC_LONG_TESTS=1')
+    if name in NOT_IMPLEMENTED['pgm']:
+        pytest.xfail('not implemented: ' + NOT_IMPLEMENTED['pgm'][name])
+    cls = _load('pgm')
+    obj = cls()
+    obj.setup_method(None)
+    getattr(obj, name)()
