@@ -682,25 +682,34 @@ SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* 
 // tolerances) and admm/admm.py:549-575 (rho update) in the working precision T from the
 // double-precision sums, writes one StatRow, advances k, clears the accumulators.
 // ------------------------------------------------------------------------------------
+// Fold the integer bins into acc[0..kAccDet) and clear them: warp i handles sum i, lane l the bins
+// l and l+32; the butterfly reduction has a fixed order, so the result is reproducible.  Needs
+// blockDim.x >= 32*kAccDet; ends with a block barrier.
 SPCSC_DEV void fold_det_bins(double* acc) {
     unsigned long long* bins = reinterpret_cast<unsigned long long*>(acc + ACC_N);
-    for (int i = 0; i < kAccDet; ++i) {
-        acc[i] += det_bins_value(bins + i * kDetBins);
-        for (int b = 0; b < kDetBins; ++b) bins[i * kDetBins + b] = 0ull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < kAccDet) {
+        unsigned long long* row = bins + warp * kDetBins;
+        double x = det_bin_term(row, lane) + det_bin_term(row, lane + 32);
+        x = warp_sum(x);
+        row[lane] = 0ull;
+        row[lane + 32] = 0ull;
+        if (lane == 0) acc[warp] += x;
     }
+    __syncthreads();
 }
 // Used before a multi-rank all-reduce (which then sums plain doubles in NCCL's fixed order).
 template <int DUMMY>
 SPCSC_GLOBAL void k_fold_bins(double* acc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) fold_det_bins(acc);
+    fold_det_bins(acc);
 }
 
 template <typename T>
 SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
                                  StatRow* rows, int k_base, int row_cap) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (st->stopped) return;
+    if (st->stopped) return;                       // uniform over the (single) block
     fold_det_bins(acc);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int k = st->k;
     T rho = st->rho;
     T r = 0, s = 0;

@@ -207,34 +207,45 @@ SPCSC_DEV void block_accumulate(const double (&v)[NV], double* red, double* acc)
 // bin first, a fixed order).
 constexpr int kDetBins = 64;
 constexpr int kDetBias = 1087 + 8;
-SPCSC_DEV double det_unit(int b) { return ldexp(1.0, (b << 5) - kDetBias); }
+
+// 2^e as a double, built from the exponent bits (|e| within the normal range).
+SPCSC_DEV double det_pow2(int e) {
+    long long bits = (long long)(e + 1023) << 52;
+    double d;
+    memcpy(&d, &bits, sizeof(d));
+    return d;
+}
 SPCSC_DEV void det_accumulate(double v, unsigned long long* bins) {
     if (!(v > 0.0)) return;
-    int e;
-    frexp(v, &e);                                  // v = f * 2^e, f in [0.5, 1)
-    int b = (e + 1087) >> 5;                       // bin of the leading bits
+    long long bits;
+    memcpy(&bits, &v, sizeof(bits));
+    const int e = (int)((bits >> 52) & 0x7ff) - 1022;      // v = f * 2^e, f in [0.5, 1) (normal v)
+    int b = (e + 1087) >> 5;                               // bin of the leading bits
     if (b > kDetBins - 1) b = kDetBins - 1;
-    if (b < 2) b = 2;
+    if (b < 5) b = 5;                                      // keeps 2^(+-unit exponent) a normal double; terms < 2^-927 count as 0
     double r = v;
     SPCSC_UNROLL
     for (int lvl = 0; lvl < 3; ++lvl) {
-        const double u = det_unit(b - lvl);
-        const double q = floor(r / u);             // level 0: < 2^40, then < 2^32
+        const int ue = ((b - lvl) << 5) - kDetBias;        // unit = 2^ue
+        const double q = floor(r * det_pow2(-ue));         // level 0: < 2^40, then < 2^32 (exact scaling)
         if (q > 0.0) atomicAdd(bins + (b - lvl), (unsigned long long)q);
-        r -= q * u;                                // exact
+        r -= q * det_pow2(ue);                             // exact
     }
+}
+SPCSC_DEV double det_bin_term(const unsigned long long* bins, int b) {
+    const unsigned long long q = bins[b];
+    const int ue = (b << 5) - kDetBias;
+    if (q == 0ull || ue < -1022) return 0.0;
+    return (double)q * det_pow2(ue);
 }
 SPCSC_DEV double det_bins_value(const unsigned long long* bins) {
     double s = 0.0;
-    for (int b = kDetBins - 1; b >= 0; --b) {
-        const unsigned long long q = bins[b];
-        if (q) s += (double)q * det_unit(b);
-    }
+    for (int b = kDetBins - 1; b >= 0; --b) s += det_bin_term(bins, b);
     return s;
 }
 
 // As block_accumulate, but the block totals go into the reproducible bins (row i of `bins`
-// has kDetBins entries) instead of floating-point atomics.
+// has kDetBins entries) instead of floating-point atomics; lane i of warp 0 handles value i.
 template <int NV>
 SPCSC_DEV void block_accumulate_det(const double (&v)[NV], double* red, unsigned long long* bins) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,12 +260,14 @@ SPCSC_DEV void block_accumulate_det(const double (&v)[NV], double* red, unsigned
     }
     __syncthreads();
     if (warp == 0) {
+        double mine = 0.0;
         SPCSC_UNROLL
         for (int i = 0; i < NV; ++i) {
             double x = (lane < nwarp) ? red[i * 32 + lane] : 0.0;
             x = warp_sum(x);
-            if (lane == 0) det_accumulate(x, bins + i * kDetBins);
+            if (lane == i) mine = x;
         }
+        if (lane < NV) det_accumulate(mine, bins + lane * kDetBins);
     }
 }
 

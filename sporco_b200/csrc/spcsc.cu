@@ -748,7 +748,7 @@ class Engine : public spcsc_handle {
             }
             if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
                 // the one exchange of the path: sum the residual / objective accumulators over ranks
-                CK(launch(k_fold_bins<0>, dim3(1), dim3(32), 0, stream, acc.p));
+                CK(launch(k_fold_bins<0>, dim3(1), dim3(256), 0, stream, acc.p));
                 int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
                 if (nr != 0) {
                     err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr);
@@ -756,7 +756,7 @@ class Engine : public spcsc_handle {
                     return SPCSC_ERR_NCCL;
                 }
             }
-            CK(launch(k_admm_scalars<T>, dim3(1), dim3(32), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
+            CK(launch(k_admm_scalars<T>, dim3(1), dim3(256), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (fuse_now) std::swap(zin, zoth);        // the spectra just written feed the next x-step
         }
