@@ -193,7 +193,12 @@ constexpr int fft_tpf() { return N / fft_elems<T>(N); }
 // Stage twiddles come from a small table laid out [r][k] per stage (consecutive lanes read
 // consecutive entries); make_stage_twiddles() on the host builds it with the same plan.
 // =====================================================================================
-SPCSC_HD int fft_swz(int i) { return i ^ ((i >> 4) & 15); }
+// Exchange regions are padded by one element per 16 (index i lives at i + i/16): the radix-16
+// first-stage writes of a lane group (stride 16) then fall on distinct banks, and -- unlike an
+// XOR swizzle -- every access of a stage is "lane base + compile-time offset", so the exchanges
+// cost no integer arithmetic per element.  A region therefore needs fft_region(N) elements.
+SPCSC_HD int fft_pad(int i) { return i + (i >> 4); }
+constexpr int fft_region(int N) { return N + N / 16; }
 
 // total number of stage-twiddle entries of the (N, E) plan
 constexpr int stage_tw_len(int N, int E) {
@@ -214,6 +219,10 @@ struct RegStage {
     static constexpr int NB = E / R;
     static constexpr int TPF = N / E;
     static constexpr bool LAST = (Ns * R >= N);
+    static constexpr int RS = N / R;                         // read stride
+    static constexpr bool RD_FAST = (RS % 16 == 0);          // r*RS never carries into the pad term
+    static constexpr bool WR_FAST16 = (Ns % 16 == 0);
+    static constexpr bool WR_BLOCK = (!WR_FAST16 && Ns * R <= 16 && 16 % (Ns * R) == 0);
 
     // v: E registers.  Ns == 1: strided input layout.  On return from the last stage v is
     // again in strided layout (slot p <-> X[t + TPF*p]).
@@ -223,9 +232,10 @@ struct RegStage {
             for (int i = 0; i < NB; ++i) {
                 const int j = t + i * TPF;
                 const int k = j & (Ns - 1);
+                const C2<T>* rd = buf + fft_pad(j);
                 SPCSC_UNROLL
                 for (int r = 0; r < R; ++r) {
-                    C2<T> x = buf[fft_swz(j + r * (N / R))];
+                    C2<T> x = RD_FAST ? rd[r * (RS + RS / 16)] : buf[fft_pad(j + r * RS)];
                     if (r > 0) {
                         const C2<T> w = stw[TWOFF + r * Ns + k];
                         x = INV ? mulc(x, w) : x * w;
@@ -243,8 +253,19 @@ struct RegStage {
                 const int j = t + i * TPF;
                 const int k = j & (Ns - 1);
                 const int j0 = (j - k) * R + k;
-                SPCSC_UNROLL
-                for (int r = 0; r < R; ++r) buf[fft_swz(j0 + r * Ns)] = v[i * R + r];
+                if (WR_FAST16) {
+                    C2<T>* wr = buf + fft_pad(j0);
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) wr[r * (Ns + Ns / 16)] = v[i * R + r];
+                } else if (WR_BLOCK) {
+                    // j0 + r*Ns stays inside the 16-aligned block that contains j0 - k
+                    C2<T>* wr = buf + j0 + ((j0 - k) >> 4);
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) wr[r * Ns] = v[i * R + r];
+                } else {
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) buf[fft_pad(j0 + r * Ns)] = v[i * R + r];
+                }
             }
             __syncwarp();
             RegStage<T, N, E, INV, Ns * R, TWOFF + (Ns > 1 ? R * Ns : 0)>::run(v, buf, stw, t);

@@ -37,7 +37,7 @@ k_row_fwd2(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
     // only stale (and this kernel only has work) when rho -- hence the scaling of U -- changed.
     if (gated && st && !st->zt_stale) return;
     SPCSC_DYN_SMEM(smem_raw);
-    constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
+    constexpr int TPF = H / E, TR = NT / TPF, P = H + H / 16 + 1, N1f = H + 1;
     constexpr int TWLEN = stage_tw_len(H, E);
     C2<T>* reg = reinterpret_cast<C2<T>*>(smem_raw);          // [TR][P]
     C2<T>* stw_s = reg + TR * P;                               // [TWLEN]
@@ -100,7 +100,7 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
                 int bnd1, int reg_on_y) {
     if (st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
-    constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
+    constexpr int TPF = H / E, TR = NT / TPF, P = H + H / 16 + 1, N1f = H + 1;
     constexpr int TWLEN = stage_tw_len(H, E);
     C2<T>* reg = reinterpret_cast<C2<T>*>(smem_raw);          // [CX][TR][P]
     C2<T>* stw_s = reg + CX * TR * P;
@@ -250,7 +250,9 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
 // busy independently of the register budget; the transforms and the prox then run out of
 // shared memory.  (The v2 profile showed the kernel waiting on its own loads 60 % of the time.)
 // ------------------------------------------------------------------------------------
-template <typename T, int H, int E, int NT>
+// PLAIN: no NonNegCoef / NoBndryCross, spatially uniform l1 weight, regulariser evaluated on X --
+// the common configuration; the flag tests and per-element weight fetches then compile away.
+template <typename T, int H, int E, int NT, bool PLAIN>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? 4 : 2))
 k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* SPCSC_RESTRICT Y,
                 T* SPCSC_RESTRICT U,
@@ -260,7 +262,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
                 int bnd1, int reg_on_y) {
     if (st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
-    constexpr int TPF = H / E, TR = NT / TPF, P = H + 1, N1f = H + 1;
+    constexpr int TPF = H / E, TR = NT / TPF, P = H + H / 16 + 1, N1f = H + 1;
     constexpr int TWLEN = stage_tw_len(H, E);
     constexpr int VEC = 16 / sizeof(C2<T>);                    // complex values per 16-byte copy
     C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [TR][H]  (as complex pairs)
@@ -271,11 +273,12 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
     const size_t wstride = (size_t)M * N0;
     {   // group 0: the Zt tile, transposed on the fly (one complex per copy)
-        const C2<T>* in = Zt + (((size_t)k * N1f) * M + m) * N0 + h0;
-        for (int e = tid; e < TR * N1f; e += NT) {
-            const int wf = e / TR, r = e % TR;
-            cp_async<sizeof(C2<T>)>(reg + r * P + wf, in + wf * wstride + r);
-        }
+        constexpr int WSTEP = NT / TR;
+        const int r = tid % TR, wf0 = tid / TR;
+        const C2<T>* src = Zt + (((size_t)k * N1f) * M + m) * N0 + h0 + (size_t)wf0 * wstride + r;
+        C2<T>* dst = reg + r * P + wf0;
+        for (int wf = wf0; wf < N1f; wf += WSTEP, src += (size_t)WSTEP * wstride, dst += WSTEP)
+            cp_async<sizeof(C2<T>)>(dst, src);
         cp_async_commit();
     }
     const size_t tile = ((((size_t)k * M + m) * N0 + h0) * H);   // in complex-pair units
@@ -328,6 +331,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     const T rl1 = (T)1 - rlx;
     T sums[7] = {0, 0, 0, 0, 0, 0, 0};
     const T w1u = wl1.p[(size_t)k * wl1.sk + (size_t)m * wl1.sm];
+    const T thr_u = lr * w1u;
     const size_t wbase = (size_t)k * wl1.sk + (size_t)m * wl1.sm + (size_t)h * wl1.s0;
     C2<T>* yg = reinterpret_cast<C2<T>*>(Y) + tile + (size_t)g * H;
     C2<T>* ug = reinterpret_cast<C2<T>*>(U) + tile + (size_t)g * H;
@@ -341,11 +345,14 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         T yn[2], un[2];
         SPCSC_UNROLL
         for (int q = 0; q < 2; ++q) {
-            const T w1 = wl1.spatial_uniform ? w1u : wl1.p[wbase + (size_t)(2 * j + q) * wl1.s1];
+            const T w1 = (PLAIN || wl1.spatial_uniform) ? w1u
+                                                        : wl1.p[wbase + (size_t)(2 * j + q) * wl1.s1];
             const T axv = relax ? rlx * xs[q] + rl1 * ys[q] : xs[q];
-            T y = soft_threshold(axv + us[q], lr * w1);
-            if (nonneg && y < (T)0) y = (T)0;
-            if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+            T y = soft_threshold(axv + us[q], PLAIN ? thr_u : lr * w1);
+            if (!PLAIN) {
+                if (nonneg && y < (T)0) y = (T)0;
+                if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+            }
             const T u = us[q] + (axv - y);
             yn[q] = y;
             un[q] = u;
@@ -356,7 +363,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
             sums[ACC_U2] += u * u;
             sums[ACC_R2] += dr * dr;
             sums[ACC_S2] += ds * ds;
-            sums[ACC_L1] += fabs(w1 * (reg_on_y ? y : x));
+            sums[ACC_L1] += fabs(w1 * ((!PLAIN && reg_on_y) ? y : x));
         }
         yg[j] = mk<T>(yn[0], yn[1]);
         ug[j] = mk<T>(un[0], un[1]);
@@ -377,14 +384,16 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         SPCSC_UNROLL
         for (int p = 0; p < E; ++p) reg[g * P + t + TPF * p] = v[p];
         __syncthreads();
-        C2<T>* out = Znext + (((size_t)k * N1f) * M + m) * N0 + h0;
-        for (int e = tid; e < TR * N1f; e += NT) {
-            const int wf = e / TR, r = e % TR;
-            const C2<T> a = reg[r * P + (wf == H ? 0 : wf)];
-            const C2<T> bb = conj(reg[r * P + (wf == 0 ? 0 : H - wf)]);
+        constexpr int WSTEP = NT / TR;
+        const int r = tid % TR, wf0 = tid / TR;
+        const C2<T>* row = reg + r * P;
+        C2<T>* out = Znext + (((size_t)k * N1f) * M + m) * N0 + h0 + (size_t)wf0 * wstride + r;
+        for (int wf = wf0; wf < N1f; wf += WSTEP, out += (size_t)WSTEP * wstride) {
+            const C2<T> a = row[wf == H ? 0 : wf];
+            const C2<T> bb = conj(row[wf == 0 ? 0 : H - wf]);
             const C2<T> w = tw[wf];
             const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
-            out[wf * wstride + r] = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+            *out = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
         }
     }
 }
@@ -404,8 +413,9 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     SPCSC_DYN_SMEM(smem_raw);
     constexpr int TPF = N0 / E, NG = NT / TPF;
     constexpr int TWLEN = stage_tw_len(N0, E);
-    C2<T>* xbuf = reinterpret_cast<C2<T>*>(smem_raw);         // [NG][N0] exchange / partial sums
-    C2<T>* sloc = xbuf + NG * N0;                              // [N0]  this CTA's sum over its columns
+    constexpr int XP = fft_region(N0);                          // padded exchange region per lane group
+    C2<T>* xbuf = reinterpret_cast<C2<T>*>(smem_raw);         // [NG][XP] exchange / partial sums
+    C2<T>* sloc = xbuf + NG * XP;                              // [N0]  this CTA's sum over its columns
     C2<T>* qbuf = sloc + N0;                                   // [N0]
     C2<T>* stw_s = qbuf + N0;                                  // [TWLEN]
     double* red = reinterpret_cast<double*>(stw_s + TWLEN);    // [32]
@@ -436,7 +446,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     if (DO_FWD) {
         SPCSC_UNROLL
         for (int c = 0; c < CPG; ++c) {
-            fft_regs<T, N0, E, false>(v[c], xbuf + g * N0, stw_s, t);
+            fft_regs<T, N0, E, false>(v[c], xbuf + g * XP, stw_s, t);
             __syncwarp();
         }
     }
@@ -448,12 +458,12 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
         SPCSC_UNROLL
         for (int c = 0; c < CPG; ++c)
             if (mcol[c] < M) s = s + dfw[(size_t)mcol[c] * N0 + h] * v[c][p];
-        xbuf[g * N0 + h] = s;
+        xbuf[g * XP + h] = s;
     }
     __syncthreads();
     for (int h = tid; h < N0; h += NT) {
         C2<T> s = mk<T>(0, 0);
-        for (int gg = 0; gg < NG; ++gg) s = s + xbuf[gg * N0 + h];
+        for (int gg = 0; gg < NG; ++gg) s = s + xbuf[gg * XP + h];
         sloc[h] = s;
     }
     cluster_arrive();
@@ -494,7 +504,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             }
         }
         if (DO_INV) {
-            fft_regs<T, N0, E, true>(v[c], xbuf + g * N0, stw_s, t);
+            fft_regs<T, N0, E, true>(v[c], xbuf + g * XP, stw_s, t);
             __syncwarp();
         }
         if (mcol[c] < M) {

@@ -180,7 +180,7 @@ cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const A
                             C2<T>* Zt, const C2<T>* stw, int gated) {
     if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
         constexpr int E = row2_elems(H, 1), NT = kRow2Threads, TR = row2_tile(H, 1);
-        const size_t smem = ((size_t)TR * (H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+        const size_t smem = ((size_t)TR * (H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
         const long long ntiles = (long long)(r.N0 / TR) * r.M * r.nb;
         // grid-stride over tiles: a gated launch that finds nothing to do retires in microseconds
         const long long cap = 148LL * 24;
@@ -197,7 +197,7 @@ static cudaError_t row_inv_prox2_cx(const RowArgs<T>& r, const ProxArgs<T>& p, c
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
     if constexpr (sizeof(T) == 4 && row2_elems(H, CX) != 0) {
         constexpr int E = row2_elems(H, CX), NT = kRow2Threads, TR = row2_tile(H, CX);
-        const size_t smem = ((size_t)CX * TR * (H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+        const size_t smem = ((size_t)CX * TR * (H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
         dim3 grid(r.N0 / TR, r.M, r.nb / CX);
         return launch(k_row_inv_prox2<T, H, E, CX, NT>, grid, dim3(NT), smem, r.stream, Zt, Y, U, st,
                       p.prm, p.wl1, p.wl21, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0,
@@ -212,9 +212,16 @@ static cudaError_t row_inv_prox3_nt(const RowArgs<T>& r, const ProxArgs<T>& p, c
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
     constexpr int E = row2_elems(H, 1), TR = NT / (H / E);
     if (r.N0 % TR != 0) return cudaErrorInvalidValue;
-    const size_t smem = ((size_t)TR * (3 * H + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+    const size_t smem = ((size_t)TR * (3 * H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
     dim3 grid(r.N0 / TR, r.M, r.nb);
-    return launch(k_row_inv_prox3<T, H, E, NT>, grid, dim3(NT), smem, r.stream, Zt,
+    const bool plain = !p.nonneg && p.bnd0 >= r.N0 && p.bnd1 >= 2 * H && !p.reg_on_y &&
+                       p.wl1.spatial_uniform;
+    if (plain)
+        return launch(k_row_inv_prox3<T, H, E, NT, true>, grid, dim3(NT), smem, r.stream, Zt,
+                      reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
+                      p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
+                      p.reg_on_y);
+    return launch(k_row_inv_prox3<T, H, E, NT, false>, grid, dim3(NT), smem, r.stream, Zt,
                   reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
                   p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
                   p.reg_on_y);
@@ -258,7 +265,7 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     const int per_cta = NG * CPG;
     const unsigned cs = (unsigned)((c.a.M + per_cta - 1) / per_cta);
     c.a.N0 = N0;
-    const size_t smem = ((size_t)NG * N0 + 2 * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
+    const size_t smem = ((size_t)NG * fft_region(N0) + 2 * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
                         32 * sizeof(double);
     dim3 grid(c.a.N1f * cs, c.nb);
     if (mode == COL_ADMM)
