@@ -244,20 +244,22 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
 }
 
 // ------------------------------------------------------------------------------------
-// k_row_inv_prox3 (CX == 1): as k_row_inv_prox2, but every global read of the CTA -- the
-// transposed Zt tile and the contiguous Y and U tiles (TR rows x N1 reals each) -- is issued
-// up front as asynchronous global->shared copies (cp.async), so the memory system is kept
-// busy independently of the register budget; the transforms and the prox then run out of
-// shared memory.  (The v2 profile showed the kernel waiting on its own loads 60 % of the time.)
-// ------------------------------------------------------------------------------------
-// PLAIN: no NonNegCoef / NoBndryCross, spatially uniform l1 weight, regulariser evaluated on X --
+// k_row_inv_prox3: inverse row transform + relaxation + prox (l1, or l1 + l2,1 over the CX
+// coefficient channels) + dual update + residual sums + (optionally) the NEXT iteration's
+// Y - U row spectra.  Every global read of the CTA -- the transposed Zt tiles and the contiguous
+// Y and U tiles (TR rows x N1 reals per channel) -- is issued up front as asynchronous
+// global->shared copies (cp.async), so the memory system is kept busy independently of the
+// register budget; the transforms and the prox then run out of shared memory and registers.
+// (The v2 profile showed the synchronous-load version waiting on its own loads 60 % of the time.)
+// PLAIN: no NonNegCoef / NoBndryCross, spatially uniform weights, regulariser evaluated on X --
 // the common configuration; the flag tests and per-element weight fetches then compile away.
-template <typename T, int H, int E, int NT, bool PLAIN>
-SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? 4 : 2))
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int E, int CX, int NT, bool PLAIN>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? (CX == 1 ? 4 : 3) : 2))
 k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* SPCSC_RESTRICT Y,
                 T* SPCSC_RESTRICT U,
                 const AdmmState<T>* SPCSC_RESTRICT st, AdmmParams<T> prm, WeightView<T> wl1,
-                double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
+                WeightView<T> wl21, double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
                 const C2<T>* SPCSC_RESTRICT stw, int N0, int M, T scale, int nonneg, int bnd0,
                 int bnd1, int reg_on_y) {
     if (st->stopped) return;
@@ -265,56 +267,60 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     constexpr int TPF = H / E, TR = NT / TPF, P = H + H / 16 + 1, N1f = H + 1;
     constexpr int TWLEN = stage_tw_len(H, E);
     constexpr int VEC = 16 / sizeof(C2<T>);                    // complex values per 16-byte copy
-    C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [TR][H]  (as complex pairs)
-    C2<T>* ubuf = ybuf + TR * H;                               // [TR][H]
-    C2<T>* reg = ubuf + TR * H;                                // [TR][P]
-    C2<T>* stw_s = reg + TR * P;
+    constexpr int WSTEP = NT / TR;
+    C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [CX][TR][H]  (as complex pairs)
+    C2<T>* ubuf = ybuf + CX * TR * H;                          // [CX][TR][H]
+    C2<T>* reg = ubuf + CX * TR * H;                           // [CX][TR][P]
+    C2<T>* stw_s = reg + CX * TR * P;
     const int tid = threadIdx.x;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
     const size_t wstride = (size_t)M * N0;
-    {   // group 0: the Zt tile, transposed on the fly (one complex per copy)
-        constexpr int WSTEP = NT / TR;
-        const int r = tid % TR, wf0 = tid / TR;
-        const C2<T>* src = Zt + (((size_t)k * N1f) * M + m) * N0 + h0 + (size_t)wf0 * wstride + r;
-        C2<T>* dst = reg + r * P + wf0;
+    const int gr = tid % TR, wf0 = tid / TR;                   // this thread's row / first wf in tile loops
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c) {   // group 0: the Zt tiles, transposed on the fly
+        const C2<T>* src = Zt + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0 +
+                           (size_t)wf0 * wstride + gr;
+        C2<T>* dst = reg + (c * TR + gr) * P + wf0;
         for (int wf = wf0; wf < N1f; wf += WSTEP, src += (size_t)WSTEP * wstride, dst += WSTEP)
             cp_async<sizeof(C2<T>)>(dst, src);
-        cp_async_commit();
     }
-    const size_t tile = ((((size_t)k * M + m) * N0 + h0) * H);   // in complex-pair units
-    {   // group 1: the Y and U tiles, contiguous
+    cp_async_commit();
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c) {   // group 1: the Y and U tiles, contiguous
+        const size_t tile = ((((size_t)(k * CX + c) * M + m) * N0 + h0) * H);
         const C2<T>* y2 = reinterpret_cast<const C2<T>*>(Y) + tile;
         const C2<T>* u2 = reinterpret_cast<const C2<T>*>(U) + tile;
         for (int e = tid * VEC; e < TR * H; e += NT * VEC) {
-            cp_async<16>(ybuf + e, y2 + e);
-            cp_async<16>(ubuf + e, u2 + e);
+            cp_async<16>(ybuf + c * TR * H + e, y2 + e);
+            cp_async<16>(ubuf + c * TR * H + e, u2 + e);
         }
-        cp_async_commit();
     }
+    cp_async_commit();
     for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
     const int g = tid / TPF, t = tid % TPF;
     const int h = h0 + g;
     cp_async_wait<1>();
     __syncthreads();
 
-    C2<T> v[E];
-    {
-        C2<T>* row = reg + g * P;
+    C2<T> v[CX][E];
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c) {
+        C2<T>* row = reg + (c * TR + g) * P;
         SPCSC_UNROLL
         for (int p = 0; p < E; ++p) {
             const int kk = t + TPF * p;
             if (kk == 0) {
                 const T a = row[0].re, cc = row[H].re;       // c2r ignores the imaginary parts
-                v[p] = mk<T>(a + cc, a - cc);
+                v[c][p] = mk<T>(a + cc, a - cc);
             } else {
                 const C2<T> Xa = row[kk], Xb = row[H - kk];
                 const C2<T> w = tw[kk];
                 const C2<T> s1 = Xa + conj(Xb), d1 = Xa - conj(Xb);
-                v[p] = s1 + mul_i(mulc(d1, w));
+                v[c][p] = s1 + mul_i(mulc(d1, w));
             }
         }
         __syncwarp();
-        fft_regs<T, H, E, true>(v, row, stw_s, t);
+        fft_regs<T, H, E, true>(v[c], row, stw_s, t);
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -326,48 +332,89 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         if (ud != (T)1) uinv = (T)1 / ud;
     }
     const T lr = prm.lmbda / rho;
+    const T mr = prm.joint ? prm.mu / rho : (T)0;
     const T rlx = prm.rlx;
     const bool relax = rlx != (T)1;
     const T rl1 = (T)1 - rlx;
     T sums[7] = {0, 0, 0, 0, 0, 0, 0};
-    const T w1u = wl1.p[(size_t)k * wl1.sk + (size_t)m * wl1.sm];
-    const T thr_u = lr * w1u;
+    T w1u[CX];
+    SPCSC_UNROLL
+    for (int c = 0; c < CX; ++c)
+        w1u[c] = wl1.p[(size_t)k * wl1.sk + (size_t)c * wl1.sc + (size_t)m * wl1.sm];
+    const T w21u = prm.joint ? wl21.p[(size_t)k * wl21.sk + (size_t)m * wl21.sm] : (T)0;
+    // with a single coefficient channel the l2 norm over the channel axis is |.|, so
+    // S_2,beta(S_1,alpha(v)) = S_1,alpha+beta(v)  (prox/_l21.py:88 with a 1-element axis)
+    const T joint1 = (CX == 1) ? mr * w21u : (T)0;
     const size_t wbase = (size_t)k * wl1.sk + (size_t)m * wl1.sm + (size_t)h * wl1.s0;
-    C2<T>* yg = reinterpret_cast<C2<T>*>(Y) + tile + (size_t)g * H;
-    C2<T>* ug = reinterpret_cast<C2<T>*>(U) + tile + (size_t)g * H;
+    const size_t w21base = (size_t)k * wl21.sk + (size_t)m * wl21.sm + (size_t)h * wl21.s0;
     SPCSC_UNROLL
     for (int p = 0; p < E; ++p) {
         const int j = t + TPF * p;
-        const C2<T> y2 = ybuf[g * H + j], u2 = ubuf[g * H + j];
-        const T xs[2] = {v[p].re * scale, v[p].im * scale};
-        const T ys[2] = {y2.re, y2.im};
-        const T us[2] = {u2.re * uinv, u2.im * uinv};
-        T yn[2], un[2];
+        T wv[CX][2], ax[CX][2], ue[CX][2], yp[CX][2], w1s[CX][2];
+        T a2[2] = {0, 0};
         SPCSC_UNROLL
-        for (int q = 0; q < 2; ++q) {
-            const T w1 = (PLAIN || wl1.spatial_uniform) ? w1u
-                                                        : wl1.p[wbase + (size_t)(2 * j + q) * wl1.s1];
-            const T axv = relax ? rlx * xs[q] + rl1 * ys[q] : xs[q];
-            T y = soft_threshold(axv + us[q], PLAIN ? thr_u : lr * w1);
-            if (!PLAIN) {
-                if (nonneg && y < (T)0) y = (T)0;
-                if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+        for (int c = 0; c < CX; ++c) {
+            const C2<T> y2 = ybuf[(c * TR + g) * H + j], u2 = ubuf[(c * TR + g) * H + j];
+            const T xs[2] = {v[c][p].re * scale, v[c][p].im * scale};
+            const T ys[2] = {y2.re, y2.im};
+            const T us[2] = {u2.re * uinv, u2.im * uinv};
+            v[c][p] = mk<T>(xs[0], xs[1]);
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                const T w1 = (PLAIN || wl1.spatial_uniform)
+                                 ? w1u[c]
+                                 : wl1.p[wbase + (size_t)c * wl1.sc + (size_t)(2 * j + q) * wl1.s1];
+                const T axv = relax ? rlx * xs[q] + rl1 * ys[q] : xs[q];
+                const T w = soft_threshold(axv + us[q], lr * w1 + joint1);
+                yp[c][q] = ys[q];
+                ax[c][q] = axv;
+                ue[c][q] = us[q];
+                wv[c][q] = w;
+                w1s[c][q] = w1;
+                a2[q] += w * w;
             }
-            const T u = us[q] + (axv - y);
-            yn[q] = y;
-            un[q] = u;
-            const T x = xs[q];
-            const T dr = x - y, ds = ys[q] - y;
-            sums[ACC_X2] += x * x;
-            sums[ACC_Y2] += y * y;
-            sums[ACC_U2] += u * u;
-            sums[ACC_R2] += dr * dr;
-            sums[ACC_S2] += ds * ds;
-            sums[ACC_L1] += fabs(w1 * ((!PLAIN && reg_on_y) ? y : x));
         }
-        yg[j] = mk<T>(yn[0], yn[1]);
-        ug[j] = mk<T>(un[0], un[1]);
-        v[p] = mk<T>(yn[0] - un[0], yn[1] - un[1]);          // next x-step input, if rho stays
+        T fac[2] = {1, 1}, w21[2] = {w21u, w21u};
+        if (CX > 1 && prm.joint) {
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                if (!PLAIN && !wl21.spatial_uniform) w21[q] = wl21.p[w21base + (size_t)(2 * j + q) * wl21.s1];
+                const T a = sqrt(a2[q]);
+                const T bq = fmax((T)0, a - mr * w21[q]);
+                fac[q] = (a != (T)0) ? bq / a : (T)0;
+            }
+        }
+        T g2[2] = {0, 0};
+        SPCSC_UNROLL
+        for (int c = 0; c < CX; ++c) {
+            T yn[2], un[2];
+            SPCSC_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                T y = (CX > 1 && prm.joint) ? fac[q] * wv[c][q] : wv[c][q];
+                if (!PLAIN) {
+                    if (nonneg && y < (T)0) y = (T)0;
+                    if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+                }
+                const T u = ue[c][q] + (ax[c][q] - y);
+                yn[q] = y;
+                un[q] = u;
+                const T x = (q == 0) ? v[c][p].re : v[c][p].im;
+                const T dr = x - y, ds = yp[c][q] - y;
+                sums[ACC_X2] += x * x;
+                sums[ACC_Y2] += y * y;
+                sums[ACC_U2] += u * u;
+                sums[ACC_R2] += dr * dr;
+                sums[ACC_S2] += ds * ds;
+                const T gq = (!PLAIN && reg_on_y) ? y : x;
+                sums[ACC_L1] += fabs(w1s[c][q] * gq);
+                g2[q] += gq * gq;
+            }
+            const size_t off = ((((size_t)(k * CX + c) * M + m) * N0 + h) * H + j);
+            reinterpret_cast<C2<T>*>(Y)[off] = mk<T>(yn[0], yn[1]);
+            reinterpret_cast<C2<T>*>(U)[off] = mk<T>(un[0], un[1]);
+            v[c][p] = mk<T>(yn[0] - un[0], yn[1] - un[1]);   // next x-step input, if rho stays
+        }
+        if (prm.joint) sums[ACC_L21] += w21[0] * sqrt(g2[0]) + w21[1] * sqrt(g2[1]);
     }
     if (prm.need_rsdl || prm.need_obj) {
         double d[7];
@@ -379,21 +426,27 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     if (Znext) {
         // Cross-iteration fusion: the row spectra of Y - U for the next iteration, valid as long
         // as rho (hence the scaling of U) does not change; otherwise k_row_fwd2 redoes them.
-        fft_regs<T, H, E, false>(v, reg + g * P, stw_s, t);
-        __syncwarp();
         SPCSC_UNROLL
-        for (int p = 0; p < E; ++p) reg[g * P + t + TPF * p] = v[p];
+        for (int c = 0; c < CX; ++c) {
+            C2<T>* row = reg + (c * TR + g) * P;
+            fft_regs<T, H, E, false>(v[c], row, stw_s, t);
+            __syncwarp();
+            SPCSC_UNROLL
+            for (int p = 0; p < E; ++p) row[t + TPF * p] = v[c][p];
+        }
         __syncthreads();
-        constexpr int WSTEP = NT / TR;
-        const int r = tid % TR, wf0 = tid / TR;
-        const C2<T>* row = reg + r * P;
-        C2<T>* out = Znext + (((size_t)k * N1f) * M + m) * N0 + h0 + (size_t)wf0 * wstride + r;
-        for (int wf = wf0; wf < N1f; wf += WSTEP, out += (size_t)WSTEP * wstride) {
-            const C2<T> a = row[wf == H ? 0 : wf];
-            const C2<T> bb = conj(row[wf == 0 ? 0 : H - wf]);
-            const C2<T> w = tw[wf];
-            const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
-            *out = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+        SPCSC_UNROLL
+        for (int c = 0; c < CX; ++c) {
+            const C2<T>* row = reg + (c * TR + gr) * P;
+            C2<T>* out = Znext + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0 +
+                         (size_t)wf0 * wstride + gr;
+            for (int wf = wf0; wf < N1f; wf += WSTEP, out += (size_t)WSTEP * wstride) {
+                const C2<T> a = row[wf == H ? 0 : wf];
+                const C2<T> bb = conj(row[wf == 0 ? 0 : H - wf]);
+                const C2<T> w = tw[wf];
+                const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
+                *out = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+            }
         }
     }
 }
@@ -403,8 +456,8 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
 //   m = (cr*G + g)*CPG + c,  g = group (TPF lanes) index, c < CPG, kept in registers.
 //   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (gradient)
 // ------------------------------------------------------------------------------------
-template <typename T, int N0, int E, int CPG, int NT, bool DO_FWD, int SOLVE, bool DO_INV>
-SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (CPG == 1 ? 3 : 2))
+template <typename T, int N0, int E, int CPG, int NT, int CD, bool DO_FWD, int SOLVE, bool DO_INV>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
 k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
        const AdmmState<T>* SPCSC_RESTRICT st, T Lstep, double* SPCSC_RESTRICT acc,
@@ -415,9 +468,9 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     constexpr int TWLEN = stage_tw_len(N0, E);
     constexpr int XP = fft_region(N0);                          // padded exchange region per lane group
     C2<T>* xbuf = reinterpret_cast<C2<T>*>(smem_raw);         // [NG][XP] exchange / partial sums
-    C2<T>* sloc = xbuf + NG * XP;                              // [N0]  this CTA's sum over its columns
-    C2<T>* qbuf = sloc + N0;                                   // [N0]
-    C2<T>* stw_s = qbuf + N0;                                  // [TWLEN]
+    C2<T>* sloc = xbuf + NG * XP;                              // [CD][N0] this CTA's sums over its columns
+    C2<T>* qbuf = sloc + CD * N0;                              // [CD][N0]
+    C2<T>* stw_s = qbuf + CD * N0;                             // [TWLEN]
     double* red = reinterpret_cast<double*>(stw_s + TWLEN);    // [32]
     const int tid = threadIdx.x;
     const unsigned cr = cluster_rank(), cs = cluster_size();
@@ -426,6 +479,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     const int g = tid / TPF, t = tid % TPF;
     for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
     const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
+    const size_t dfc = (size_t)a.N1f * M * N0;                 // stride between dictionary channels
     const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
 
     C2<T> v[CPG][E];
@@ -450,21 +504,25 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             __syncwarp();
         }
     }
-    // partial sums over this group's columns
+    // s_d[h] = sum over this CTA's columns of Df_d[m][h] * col[m][h], one dictionary channel at a time
     SPCSC_UNROLL
-    for (int p = 0; p < E; ++p) {
-        const int h = t + TPF * p;
-        C2<T> s = mk<T>(0, 0);
+    for (int d = 0; d < CD; ++d) {
         SPCSC_UNROLL
-        for (int c = 0; c < CPG; ++c)
-            if (mcol[c] < M) s = s + dfw[(size_t)mcol[c] * N0 + h] * v[c][p];
-        xbuf[g * XP + h] = s;
-    }
-    __syncthreads();
-    for (int h = tid; h < N0; h += NT) {
-        C2<T> s = mk<T>(0, 0);
-        for (int gg = 0; gg < NG; ++gg) s = s + xbuf[gg * XP + h];
-        sloc[h] = s;
+        for (int p = 0; p < E; ++p) {
+            const int h = t + TPF * p;
+            C2<T> s = mk<T>(0, 0);
+            SPCSC_UNROLL
+            for (int c = 0; c < CPG; ++c)
+                if (mcol[c] < M) s = s + dfw[d * dfc + (size_t)mcol[c] * N0 + h] * v[c][p];
+            xbuf[g * XP + h] = s;
+        }
+        __syncthreads();
+        for (int h = tid; h < N0; h += NT) {
+            C2<T> s = mk<T>(0, 0);
+            for (int gg = 0; gg < NG; ++gg) s = s + xbuf[gg * XP + h];
+            sloc[d * N0 + h] = s;
+        }
+        if (d + 1 < CD) __syncthreads();
     }
     cluster_arrive();
     cluster_wait();
@@ -472,24 +530,47 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     const T rho = (SOLVE == 1) ? st->rho : (T)0;
     double dsum[1] = {0.0};
     for (int h = tid; h < N0; h += NT) {
-        C2<T> s = mk<T>(0, 0);
-        for (unsigned rk = 0; rk < cs; ++rk) {
-            const C2<T>* ps = (rk == cr) ? sloc : cluster_peer(sloc, rk);
-            s = s + ps[h];
+        C2<T> dv[CD];
+        SPCSC_UNROLL
+        for (int d = 0; d < CD; ++d) {
+            C2<T> s = mk<T>(0, 0);
+            for (unsigned rk = 0; rk < cs; ++rk) {
+                const C2<T>* ps = (rk == cr) ? sloc : cluster_peer(sloc, rk);
+                s = s + ps[d * N0 + h];
+            }
+            const int csig = (CD > 1) ? d : cx;
+            dv[d] = Sf[(((size_t)k * a.Cs + csig) * a.N1f + wf) * N0 + h] - s;
         }
-        const C2<T> sf = Sf[(((size_t)k * a.Cs + cx) * a.N1f + wf) * N0 + h];
-        C2<T> d = sf - s;
         if (SOLVE == 1) {
-            const T den = G[(size_t)wf * N0 + h].re + rho;
-            d = mk<T>(d.re / den, d.im / den);
+            if (CD == 1) {
+                const T den = G[(size_t)wf * N0 + h].re + rho;
+                dv[0] = mk<T>(dv[0].re / den, dv[0].im / den);
+            } else {
+                C2<T> A[CD][CD];
+                const C2<T>* Gp = G + ((size_t)wf * N0 + h) * CD * CD;
+                SPCSC_UNROLL
+                for (int i = 0; i < CD; ++i) {
+                    SPCSC_UNROLL
+                    for (int j = 0; j < CD; ++j) {
+                        A[i][j] = Gp[i * CD + j];
+                        if (i == j) A[i][j].re += rho;
+                    }
+                }
+                hpd_solve<T, CD>(A, dv, CD);
+            }
             if (a.dfid_on && cr == 0) {
                 const double wgt = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
-                dsum[0] += wgt * (double)abs2(d);
+                double q2 = 0.0;
+                SPCSC_UNROLL
+                for (int d = 0; d < CD; ++d) q2 += (double)abs2(dv[d]);
+                dsum[0] += wgt * q2;
             }
         } else {
-            d = mk<T>(d.re / Lstep, d.im / Lstep);
+            SPCSC_UNROLL
+            for (int d = 0; d < CD; ++d) dv[d] = mk<T>(dv[d].re / Lstep, dv[d].im / Lstep);
         }
-        qbuf[h] = d;
+        SPCSC_UNROLL
+        for (int d = 0; d < CD; ++d) qbuf[d * N0 + h] = dv[d];
     }
     cluster_arrive();                                        // done reading the peers' sums
     __syncthreads();
@@ -500,7 +581,11 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             SPCSC_UNROLL
             for (int p = 0; p < E; ++p) {
                 const int h = t + TPF * p;
-                v[c][p] = v[c][p] + mulc(qbuf[h], dfw[(size_t)mcol[c] * N0 + h]);
+                C2<T> x = v[c][p];
+                SPCSC_UNROLL
+                for (int d = 0; d < CD; ++d)
+                    x = x + mulc(qbuf[d * N0 + h], dfw[d * dfc + (size_t)mcol[c] * N0 + h]);
+                v[c][p] = x;
             }
         }
         if (DO_INV) {

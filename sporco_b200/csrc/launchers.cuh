@@ -58,7 +58,6 @@ struct ColLaunch {
     const C2<T>* tw;             // exp(-2 pi i j / N0)
     int nb;                      // slabs per frequency column (grid.y)
     ColArgs a;                   // MC / nchunk / parts filled by the launcher
-    int cpg;                     // v2: columns kept in registers per lane group (1 or 2)
     int gen;                     // any-size direct-DFT path (a.N0 holds the run-time length)
     cudaStream_t stream;
 };
@@ -129,7 +128,7 @@ inline bool row2_ok(int H, int N0, int Cx) {
 }
 template <typename T>
 inline bool col2_ok(int N0, int M, int Cd) {
-    if (sizeof(T) != 4 || Cd != 1 || N0 < 32 || N0 > 512) return false;
+    if (sizeof(T) != 4 || Cd < 1 || Cd > 4 || N0 < 32 || N0 > 512) return false;
     const int per_cta = (kCol2Threads / (N0 / kCol2E)) * kCol2CPG;
     return (M + per_cta - 1) / per_cta <= 4;     // so that the one-column variant needs <= 8 CTAs
 }

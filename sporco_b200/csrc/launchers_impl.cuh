@@ -207,38 +207,37 @@ static cudaError_t row_inv_prox2_cx(const RowArgs<T>& r, const ProxArgs<T>& p, c
     }
 }
 
-template <typename T, int H, int NT>
+template <typename T, int H, int CX, int NT>
 static cudaError_t row_inv_prox3_nt(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
-    constexpr int E = row2_elems(H, 1), TR = NT / (H / E);
+    constexpr int E = row2_elems(H, CX), TR = NT / (H / E);
     if (r.N0 % TR != 0) return cudaErrorInvalidValue;
-    const size_t smem = ((size_t)TR * (3 * H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
-    dim3 grid(r.N0 / TR, r.M, r.nb);
+    const size_t smem = ((size_t)CX * TR * (3 * H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+    dim3 grid(r.N0 / TR, r.M, r.nb / CX);
     const bool plain = !p.nonneg && p.bnd0 >= r.N0 && p.bnd1 >= 2 * H && !p.reg_on_y &&
-                       p.wl1.spatial_uniform;
+                       p.wl1.spatial_uniform && (!p.prm.joint || p.wl21.spatial_uniform);
     if (plain)
-        return launch(k_row_inv_prox3<T, H, E, NT, true>, grid, dim3(NT), smem, r.stream, Zt,
+        return launch(k_row_inv_prox3<T, H, E, CX, NT, true>, grid, dim3(NT), smem, r.stream, Zt,
                       reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
-                      p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
+                      p.prm, p.wl1, p.wl21, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
                       p.reg_on_y);
-    return launch(k_row_inv_prox3<T, H, E, NT, false>, grid, dim3(NT), smem, r.stream, Zt,
+    return launch(k_row_inv_prox3<T, H, E, CX, NT, false>, grid, dim3(NT), smem, r.stream, Zt,
                   reinterpret_cast<C2<T>*>(p.znext), Y, U, st,
-                  p.prm, p.wl1, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
+                  p.prm, p.wl1, p.wl21, p.acc, r.tw, stw, r.N0, r.M, p.scale, p.nonneg, p.bnd0, p.bnd1,
                   p.reg_on_y);
 }
 
-template <typename T, int H>
+// threads per CTA of the cp.async prox kernel: small CTAs (8-16 rows) give the best overlap
+template <typename T, int H, int CX>
 static cudaError_t row_inv_prox3_go(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
-    if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
-        constexpr int E = row2_elems(H, 1);
-        if constexpr ((H / E) <= 4) {
-            if (p.prox_threads == 128) return row_inv_prox3_nt<T, H, 128>(r, p, Zt, Y, U, st, stw);
-        } else {
-            if (p.prox_threads == 128 && r.N0 % (128 / (H / E)) == 0)
-                return row_inv_prox3_nt<T, H, 128>(r, p, Zt, Y, U, st, stw);
+    if constexpr (sizeof(T) == 4 && row2_elems(H, CX) != 0) {
+        constexpr int E = row2_elems(H, CX), TPF = H / E;
+        if constexpr (TPF <= 16) {
+            if (p.prox_threads == 128 && r.N0 % (128 / TPF) == 0)
+                return row_inv_prox3_nt<T, H, CX, 128>(r, p, Zt, Y, U, st, stw);
         }
-        return row_inv_prox3_nt<T, H, kRow2Threads>(r, p, Zt, Y, U, st, stw);
+        return row_inv_prox3_nt<T, H, CX, kRow2Threads>(r, p, Zt, Y, U, st, stw);
     } else {
         return cudaErrorInvalidValue;
     }
@@ -247,29 +246,37 @@ static cudaError_t row_inv_prox3_go(const RowArgs<T>& r, const ProxArgs<T>& p, c
 template <typename T, int H>
 cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt, T* Y,
                                  T* U, const AdmmState<T>* st, const C2<T>* stw) {
+    const bool async_ok = !p.use_v2_sync &&
+                          ((!p.prm.joint) || p.wl21.spatial_uniform || r.Cx > 1);
     switch (r.Cx) {
         case 1:
-            if (!p.prm.joint && !p.use_v2_sync) return row_inv_prox3_go<T, H>(r, p, Zt, Y, U, st, stw);
+            if (async_ok) return row_inv_prox3_go<T, H, 1>(r, p, Zt, Y, U, st, stw);
             return row_inv_prox2_cx<T, H, 1>(r, p, Zt, Y, U, st, stw);
-        case 2: return row_inv_prox2_cx<T, H, 2>(r, p, Zt, Y, U, st, stw);
-        case 3: return row_inv_prox2_cx<T, H, 3>(r, p, Zt, Y, U, st, stw);
-        case 4: return row_inv_prox2_cx<T, H, 4>(r, p, Zt, Y, U, st, stw);
+        case 2:
+            if (async_ok) return row_inv_prox3_go<T, H, 2>(r, p, Zt, Y, U, st, stw);
+            return row_inv_prox2_cx<T, H, 2>(r, p, Zt, Y, U, st, stw);
+        case 3:
+            if (async_ok) return row_inv_prox3_go<T, H, 3>(r, p, Zt, Y, U, st, stw);
+            return row_inv_prox2_cx<T, H, 3>(r, p, Zt, Y, U, st, stw);
+        case 4:
+            if (async_ok) return row_inv_prox3_go<T, H, 4>(r, p, Zt, Y, U, st, stw);
+            return row_inv_prox2_cx<T, H, 4>(r, p, Zt, Y, U, st, stw);
         default: return cudaErrorInvalidValue;
     }
 }
 
-template <typename T, int N0, int CPG>
+template <typename T, int N0, int CD>
 static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
-    constexpr int E = kCol2E, NT = kCol2Threads;
+    constexpr int E = kCol2E, NT = kCol2Threads, CPG = kCol2CPG;
     constexpr int TPF = N0 / E, NG = NT / TPF;
     const int per_cta = NG * CPG;
     const unsigned cs = (unsigned)((c.a.M + per_cta - 1) / per_cta);
     c.a.N0 = N0;
-    const size_t smem = ((size_t)NG * fft_region(N0) + 2 * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
+    const size_t smem = ((size_t)NG * fft_region(N0) + 2 * CD * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
                         32 * sizeof(double);
     dim3 grid(c.a.N1f * cs, c.nb);
     if (mode == COL_ADMM)
-        return launch_cluster(k_col2<T, N0, E, CPG, NT, true, 1, true>, grid, dim3(NT), cs, smem,
+        return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, true, 1, true>, grid, dim3(NT), cs, smem,
                               c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw,
                               c.a);
     return cudaErrorInvalidValue;
@@ -278,8 +285,13 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
 template <typename T, int N0>
 cudaError_t col2_launch(int mode, ColLaunch<T> c, const C2<T>* stw) {
     if constexpr (sizeof(T) == 4 && N0 >= 32 && N0 <= 512) {
-        if (c.cpg == 1) return col2_go<T, N0, 1>(mode, c, stw);
-        return col2_go<T, N0, 2>(mode, c, stw);
+        switch (c.a.Cd) {
+            case 1: return col2_go<T, N0, 1>(mode, c, stw);
+            case 2: return col2_go<T, N0, 2>(mode, c, stw);
+            case 3: return col2_go<T, N0, 3>(mode, c, stw);
+            case 4: return col2_go<T, N0, 4>(mode, c, stw);
+            default: return cudaErrorInvalidValue;
+        }
     } else {
         return cudaErrorInvalidValue;
     }

@@ -366,7 +366,6 @@ class Engine : public spcsc_handle {
     bool pgm_ready = false, pgm_have_cand = false;
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
     bool gen_rows = false, gen_cols = false;   // any-size direct-DFT path for this axis
-    int col_cpg = kCol2CPG;
     bool fuse = false;          // prox kernel also emits the next iteration's row spectra
     bool fused_batch = false, x_in_zt2 = false;
     DevBuf<C2<T>> Zt2;          // ping-pong partner of Zt when fusing
@@ -439,9 +438,8 @@ class Engine : public spcsc_handle {
             v2_rowf = allow2 && !gen_rows && row2_ok<T>(H, N0, 1);
             v2_rowp = allow2 && !gen_rows && row2_ok<T>(H, N0, Cx);
             v2_col = allow2 && !gen_cols && col2_ok<T>(N0, M, Cd);
-            if (const char* e = getenv("SPCSC_COL_CPG")) col_cpg = (atoi(e) == 1) ? 1 : 2;
             const char* fz = getenv("SPCSC_FUSE");
-            fuse = v2_rowf && v2_rowp && Cx == 1 && !(fz && std::string(fz) == "0");
+            fuse = v2_rowf && v2_rowp && !(fz && std::string(fz) == "0");
             int rc;
             if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1)))) return rc;
             if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx)))) return rc;
@@ -486,7 +484,6 @@ class Engine : public spcsc_handle {
         c.a.even_n1 = 1;
         c.stream = stream;
         c.Lstep = 1;
-        c.cpg = col_cpg;
         c.gen = gen_cols ? 1 : 0;
         return c;
     }
@@ -693,7 +690,8 @@ class Engine : public spcsc_handle {
         fused_batch = false;
         if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
         for (int it = 0; it < n; ++it) {
-            const bool fuse_now = fuse && !check && !opts.joint && !pa.use_v2_sync;
+            const bool fuse_now = fuse && !check && !pa.use_v2_sync &&
+                                  (!opts.joint || wl21.spatial_uniform || Cx > 1);
             if (fuse_now && !zoth) {
                 CK(Zt2.ensure(nslab));
                 zoth = Zt2.p;
@@ -831,7 +829,7 @@ class Engine : public spcsc_handle {
 
     int admm_schedule_info(int32_t* info) override {
         info[0] = v2_rowf; info[1] = v2_col; info[2] = v2_rowp;
-        info[3] = (fuse && !opts.linsolve_check && !opts.joint) ? 1 : 0;
+        info[3] = (fuse && !opts.linsolve_check && (!opts.joint || wl21.spatial_uniform || Cx > 1)) ? 1 : 0;
         return SPCSC_OK;
     }
     int admm_profile(int n, float* ms4) override {

@@ -217,3 +217,36 @@ def run_reproducibility_case():
         outs.append((Y, np.array(b.getitstat().Rho), np.array(b.getitstat().PrimalRsdl)))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+
+FRESH_CASES += [
+    (256, 64, 40, 2, 3, None, None),                       # 3-channel signal, Cd=1: CX=3 fused async prox
+    (64, 128, 10, 2, 3, 0.04, None),                       # joint l2,1 over 3 channels, fused
+]
+
+
+def run_multichannel_dict_cases():
+    """Multi-channel dictionary (Cd=3, Woodbury solve in the cluster column kernel), plain and
+    with the joint penalty, and the joint penalty with a single coefficient channel."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(2)
+    dt = np.float32
+    D3 = rng.standard_normal((5, 5, 3, 40)).astype(dt)
+    S3 = rng.standard_normal((256, 64, 3, 2)).astype(dt)
+    o = {'MaxMainIter': 8, 'RelStopTol': 0.0}
+    for mu in (None, 0.03):
+        if mu is None:
+            b = cbpdn.ConvBPDN(D3, S3, 0.1, cbpdn.ConvBPDN.Options(o))
+        else:
+            b = cbpdn.ConvBPDNJoint(D3, S3, 0.1, mu, cbpdn.ConvBPDNJoint.Options(o))
+        Y = b.solve()
+        r = orc.admm_convbpdn(D3, S3, 0.1, mu=mu, opt=o)
+        assert b._h.admm_schedule_info()['col_v2']
+        assert rel(Y, r.Y) < 3e-4 and rel(b.getitstat().ObjFun, [x[1] for x in r.itstat]) < 1e-4
+    D = rng.standard_normal((5, 5, 12)).astype(dt)
+    S = rng.standard_normal((64, 256, 2)).astype(dt)
+    o = {'MaxMainIter': 8, 'RelStopTol': 0.0, 'L21Weight': np.linspace(0.5, 1.5, 12).astype(dt)}
+    b = cbpdn.ConvBPDNJoint(D, S, 0.1, 0.05, cbpdn.ConvBPDNJoint.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, mu=0.05, opt=o, dimK=1)
+    assert rel(Y, r.Y) < 3e-4 and rel(b.getitstat().RegL21, [x[4] for x in r.itstat]) < 1e-4

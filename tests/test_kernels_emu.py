@@ -94,3 +94,7 @@ def test_aux_var_obj(dt):
 
 def test_bit_reproducible_runs():
     cases.run_reproducibility_case()
+
+
+def test_multichannel_dictionary_fast_path():
+    cases.run_multichannel_dict_cases()

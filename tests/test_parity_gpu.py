@@ -176,3 +176,7 @@ def test_any_image_size(shape):
     Y = b.solve()
     r = orc.admm_convbpdn(D, S, 0.1, opt=o, dimK=1)
     assert cases.rel(Y, r.Y) < 1e-9 and b.getitstat().XSlvRelRes.max() < 1e-11
+
+
+def test_multichannel_dictionary_fast_path():
+    cases.run_multichannel_dict_cases()
