@@ -250,3 +250,55 @@ def run_multichannel_dict_cases():
     Y = b.solve()
     r = orc.admm_convbpdn(D, S, 0.1, mu=0.05, opt=o, dimK=1)
     assert rel(Y, r.Y) < 3e-4 and rel(b.getitstat().RegL21, [x[4] for x in r.itstat]) < 1e-4
+
+
+def run_option_cases(capsys=None):
+    """Smaller option paths of the reference frame: StdResiduals, default lambda, Verbose status
+    table, Callback stop, AbsStopTol, AutoRho period / fixed scaling."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(31)
+    D = rng.standard_normal((4, 4, 6))
+    S = rng.standard_normal((32, 32, 2))
+    # StdResiduals + AbsStopTol (admm/admm.py:465-471)
+    o = {'MaxMainIter': 15, 'RelStopTol': 1e-4, 'AbsStopTol': 1e-6,
+         'AutoRho': {'StdResiduals': True, 'Period': 3, 'AutoScaling': False, 'Scaling': 2.0,
+                     'RsdlRatio': 5.0}}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=o, dimK=1)
+    its = b.getitstat()
+    assert len(its.Rho) == r.k
+    assert rel(Y, r.Y) < 1e-9 and rel(its.Rho, [x[8] for x in r.itstat]) < 1e-12
+    assert rel(its.PrimalRsdl, [x[4] for x in r.itstat]) < 1e-9
+    assert rel(its.EpsPrimal, [x[6] for x in r.itstat]) < 1e-9
+    assert rel(its.EpsDual, [x[7] for x in r.itstat]) < 1e-9
+    # default lambda = 0.1 max |D^H s| (admm/cbpdn.py:573-578) and default rho / rho_xi
+    o = {'MaxMainIter': 5, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDN(D, S, None, cbpdn.ConvBPDN.Options(o), dimK=1)
+    b.solve()
+    r = orc.admm_convbpdn(D, S, None, opt=o, dimK=1)
+    assert abs(float(b.lmbda) - float(r.lmbda)) < 1e-12 * float(r.lmbda)
+    assert rel(b.Y, r.Y) < 1e-9
+    # Callback: stop after 4 iterations (admm/admm.py:370-372); k counts like the reference
+    seen = []
+
+    def cb(obj):
+        seen.append(obj.k)
+        return len(seen) >= 4
+    o = {'MaxMainIter': 20, 'RelStopTol': 0.0, 'Callback': cb}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    b.solve()
+    assert seen == [0, 1, 2, 3] and b.k == 4 and len(b.itstat) == 4
+    # Verbose table: header, separator, one line per iteration (admm/admm.py:579-625)
+    if capsys is not None:
+        capsys.readouterr()
+        o = {'MaxMainIter': 3, 'RelStopTol': 0.0, 'Verbose': True}
+        b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+        b.solve()
+        out = capsys.readouterr().out.strip().splitlines()
+        assert out[0].split() == ['Itn', 'Fnc', 'DFid', u'Regℓ1', 'r', 's', u'ρ']
+        assert set(out[1]) == {'-'} and set(out[-1]) == {'-'} and len(out) == 6
+        assert out[2].split()[0] == '0' and len(out[2].split()) == 7
+    # timers exist and advanced
+    assert b.timer.elapsed('solve') > 0 and b.timer.elapsed('init') > 0

@@ -98,3 +98,7 @@ def test_bit_reproducible_runs():
 
 def test_multichannel_dictionary_fast_path():
     cases.run_multichannel_dict_cases()
+
+
+def test_option_paths(capsys):
+    cases.run_option_cases(capsys)

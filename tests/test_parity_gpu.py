@@ -180,3 +180,7 @@ def test_any_image_size(shape):
 
 def test_multichannel_dictionary_fast_path():
     cases.run_multichannel_dict_cases()
+
+
+def test_option_paths(capsys):
+    cases.run_option_cases(capsys)
