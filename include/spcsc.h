@@ -164,6 +164,26 @@ int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]);
 /* Accept the candidate and take the momentum step Yf = Xf + coef (Xf - Xfprv)  (PGMDFT.ystep). */
 int spcsc_pgm_accept(spcsc_handle* h, double coef);
 
+/* ---- dictionary update: sporco.pgm.ccmod.ConvCnstrMOD as the D step of
+   sporco.dictlrn.cbpdndl.ConvBPDNDictLearn (dictlrn/dictlrn.py:327-363), sharing the handle -- and
+   the device arrays -- of the X step.  Single-channel dictionary and signal.
+   out[] of spcsc_ccmod_step: [0] DFid = rfl2norm2(sum_m Zf Xf - Sf)/2 (pgm/ccmod.py:360-367),
+   [1] Cnstr = ||Pcn(X) - X|| (:370-376), [2] Rsdl = rfl2norm2(Xf - Yfprv) (:341-345), [3] obfn_f(Yf). */
+/* X = zero-padded D0 (already normalised by the caller, cbpdndl.py:448-454), Xf = Yf = rfftn(X). */
+int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zero_mean);
+/* setcoef: Zf = rfftn(Z) with Z the X step's current coefficient maps on this handle, device to
+   device (dictlrn.py:379-383 without the host round trip): the ADMM Y or the PGM iterate X ... */
+enum { SPCSC_COEF_ADMM_Y = 0, SPCSC_COEF_PGM_X = 1 };
+int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source);
+/* ... or from a host array Z (N0,N1,1,K,M).                                pgm/ccmod.py:264-281 */
+int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z);
+/* One PGM iteration with step 1/L and momentum coefficient coef = (t_prev - 1)/t  (pgm/pgm.py:779-831). */
+int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, double out[4]);
+/* getdict(crop=True): (hd, wd, Cd, M).                                     pgm/ccmod.py:283-291 */
+int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out);
+/* xstep.setdict(dstep.getdict()) on the device (dictlrn.py:386-389): Df <- Xf. */
+int spcsc_ccmod_push_dict(spcsc_handle* h);
+
 /* ---- multi-GPU: images are sharded over ranks (one process per GPU); the only exchange of
    the path is the all-reduce of the residual / objective sums that drive the shared rho and the
    stopping test (admm/admm.py:462-486 are global over all K images).  NCCL is resolved at run

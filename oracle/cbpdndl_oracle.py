@@ -1,0 +1,174 @@
+"""CPU oracle for convolutional dictionary learning -- TEST INFRASTRUCTURE, not product code.
+
+Restates, in numpy and in the reference's layout, ``sporco.dictlrn.cbpdndl.ConvBPDNDictLearn``
+with its default solvers: X-step = one ADMM ConvBPDN iteration per outer iteration
+(sporco/dictlrn/cbpdndl.py:49-55, admm/cbpdn.py), D-step = one PGM iteration of the
+constrained convolutional MOD problem (sporco/pgm/ccmod.py:28-404, pgm/pgm.py:328-370), the
+alternation of sporco/dictlrn/dictlrn.py:327-363 and the constraint-set projection
+``Pcn`` (sporco/cnvrep.py:868-1074: crop to the filter support, optional zero mean, unit
+norm).  Single-channel dictionary and signal (C = Cd = 1), one support size.
+Pinned bit-for-bit to the live reference by oracle/make_golden.py (fixture tests/golden/cdl_*.npz).
+"""
+
+import time
+
+import numpy as np
+
+from . import cbpdn_oracle as co
+
+
+def pcn(x, dsz, Nv, zm=False):
+    """normalise(zeromean(zpad(bcrop(x)))) for x of shape (N0, N1, 1, 1, M)  (cnvrep.py:953-1033)."""
+    h, w = dsz[0], dsz[1]
+    c = x[0:h, 0:w]
+    p = np.zeros(x.shape, dtype=x.dtype)
+    p[0:h, 0:w] = c
+    if zm:
+        p[0:h, 0:w] -= np.mean(p[0:h, 0:w], (0, 1))
+    vn = np.sqrt(np.sum(p ** 2, (0, 1, 2), keepdims=True))
+    vn[vn == 0] = 1.0
+    return np.asarray(p / vn, dtype=x.dtype)
+
+
+CDL_DEFAULTS = {
+    'MaxMainIter': 10,
+    'CBPDN': {'rho': None, 'RelaxParam': 1.8, 'NonNegCoef': False, 'NoBndryCross': False,
+              'AuxVarObj': False,
+              'AutoRho': {'Enabled': True, 'Period': 10, 'AutoScaling': False, 'RsdlRatio': 10.0,
+                          'Scaling': 2.0, 'RsdlTarget': 1.0, 'StdResiduals': False},
+              'RelStopTol': 1e-3, 'AbsStopTol': 0.0},
+    'CCMOD': {'L': None, 'ZeroMean': False},
+}
+
+
+def cbpdndl(D0, S, lmbda, opt=None, fft=None):
+    """Run ConvBPDNDictLearn(D0, S, lmbda, opt) with xmethod='admm', dmethod='pgm'.
+    Returns a dict with the learned dictionary (cropped), the coefficient maps and the
+    iteration statistics columns."""
+    fft = fft or co.FFTBackend()
+    o = {'MaxMainIter': 10, 'CBPDN': dict(CDL_DEFAULTS['CBPDN']), 'CCMOD': dict(CDL_DEFAULTS['CCMOD'])}
+    o['CBPDN']['AutoRho'] = dict(CDL_DEFAULTS['CBPDN']['AutoRho'])
+    for k, v in (opt or {}).items():
+        if k in ('CBPDN', 'CCMOD'):
+            for kk, vv in v.items():
+                if kk == 'AutoRho':
+                    o[k][kk].update(vv)
+                else:
+                    o[k][kk] = vv
+        else:
+            o[k] = v
+    xo, do = o['CBPDN'], o['CCMOD']
+    ar = xo['AutoRho']
+    dtype = np.dtype(S.dtype)
+    rdt = co._rdt(dtype)
+    dsz = D0.shape
+    N0, N1, K = S.shape[0], S.shape[1], S.shape[2]
+    M = D0.shape[-1]
+    Nv = (N0, N1)
+    axN, axK, axM = (0, 1), 3, 4
+
+    # ---- initial dictionary: cropped + normalised (cbpdndl.py:448-454)
+    Dn = np.zeros((dsz[0], dsz[1], 1, 1, M), dtype=D0.dtype)
+    Dn[...] = D0.reshape(dsz[0], dsz[1], 1, 1, M)
+    if do['ZeroMean']:
+        Dn = Dn - np.mean(Dn, (0, 1))
+    vn = np.sqrt(np.sum(Dn ** 2, (0, 1, 2), keepdims=True))
+    vn[vn == 0] = 1.0
+    Dn = np.asarray(Dn / vn, dtype=D0.dtype)
+    X0d = np.zeros((N0, N1, 1, 1, M), dtype=D0.dtype)
+    X0d[0:dsz[0], 0:dsz[1]] = Dn
+
+    # ---- X-step state (admm/cbpdn.py ctor)
+    Sm = np.asarray(S.reshape(N0, N1, 1, K, 1), dtype=dtype)
+    Sf = fft.rfftn(Sm, None, axN)
+    lm = rdt.type(lmbda)
+    rho = rdt.type(xo['rho']) if xo['rho'] is not None else rdt.type(50.0 * lm + 1.0)
+    tau, mur = rdt.type(ar['Scaling']), rdt.type(ar['RsdlRatio'])
+    xi = rdt.type(ar['RsdlTarget'])
+    rlx = rdt.type(xo['RelaxParam'])
+    Y = np.zeros((N0, N1, 1, K, M), dtype)
+    U = np.zeros((N0, N1, 1, K, M), dtype)
+    Dcur = np.asarray(Dn, dtype=dtype)
+    Nx = np.prod(np.array(Y.shape))
+    kx = 0
+
+    # ---- D-step state (pgm/ccmod.py ctor)
+    # NB: the reference means K*14 as default (pgm/ccmod.py:218) but PGM.__init__ has already set
+    # L = 1.0 (pgm/pgm.py:242) and set_attr does not overwrite it: the effective default is 1.0
+    L = dtype.type(do['L']) if do['L'] is not None else dtype.type(1.0)
+    Xd = X0d.astype(dtype, copy=True)
+    Xdf = fft.rfftn(Xd, None, axN)
+    Ydf = Xdf
+    t = 1
+
+    cols = {n: [] for n in ('ObjFun', 'DFid', 'RegL1', 'Cnstr', 'XPrRsdl', 'XDlRsdl', 'XRho',
+                            'D_L', 'D_Rsdl')}
+    t0 = time.perf_counter()
+    for j in range(o['MaxMainIter']):
+        # ================= X step: one ADMM iteration =================
+        Df = fft.rfftn(Dcur, Nv, axN)
+        DSf = np.conj(Df) * Sf
+        Yprev = Y.copy()
+        b = DSf + rho * fft.rfftn(Y - U, None, axN)
+        Xf = co.solvedbi_sm(Df, rho, b, axM)
+        X = fft.irfftn(Xf, Nv, axN)
+        AX = X if rlx == 1.0 else rlx * X + (1 - rlx) * Y
+        Y = co.prox_l1(AX + U, (lm / rho))
+        if xo['NonNegCoef']:
+            Y[Y < 0.0] = 0.0
+        U = U + (AX - Y)
+        nX, nY, nU = np.linalg.norm(X), np.linalg.norm(Y), np.linalg.norm(U)
+        rn = max(nX, nY)
+        rn = 1.0 if rn == 0.0 else rn
+        sn = rho * nU
+        sn = 1.0 if sn == 0.0 else sn
+        r = np.linalg.norm(X - Y) / rn
+        s = np.linalg.norm(rho * (Yprev - Y)) / sn
+        Ef = co.inner(Df, Xf, axM) - Sf
+        dfd = co.rfl2norm2(Ef, Sm.shape, axis=axN) / 2.0
+        rl1 = np.linalg.norm(X.ravel(), 1)
+        xrho = rho
+        if ar['Enabled'] and kx != 0 and np.mod(kx + 1, ar['Period']) == 0:
+            if ar['AutoScaling']:
+                if s == 0.0 or r == 0.0:
+                    mlt = tau
+                else:
+                    mlt = np.sqrt(r / (s * xi) if r > s * xi else (s * xi) / r)
+                    if mlt > tau:
+                        mlt = tau
+            else:
+                mlt = tau
+            rsf = 1.0
+            if r > xi * mur * s:
+                rsf = mlt
+            elif s > (mur / xi) * r:
+                rsf = 1.0 / mlt
+            rho = rho * rdt.type(rsf)
+            U = (U / rsf).astype(dtype, copy=False)
+        kx += 1
+        # ================= D step: one PGM iteration on the dictionary =================
+        Zf = fft.rfftn(Y, Nv, axN)                              # setcoef (pgm/ccmod.py:264-281)
+        Xdfprv = Xdf.copy()
+        Ydfprv = Ydf.copy()
+        Ryf = co.inner(Zf, Ydf, axM) - Sf
+        gradf = co.inner(np.conj(Zf), Ryf, axK)
+        Vf = Ydf - (1. / L) * gradf
+        V = fft.irfftn(Vf, Nv, axN)
+        Xd = pcn(V, dsz, Nv, zm=do['ZeroMean'])
+        Xdf = fft.rfftn(Xd, None, axN)
+        tprv = t
+        t = 0.5 * float(1. + np.sqrt(1. + 4. * t ** 2))
+        Ydf = Xdf + ((tprv - 1.) / t) * (Xdf - Xdfprv)
+        drsdl = co.rfl2norm2(Xdf - Ydfprv, Xd.shape, axis=axN)
+        cns = np.linalg.norm((pcn(Xd, dsz, Nv, zm=do['ZeroMean']) - Xd))
+        # ================= book-keeping (dictlrn/dictlrn.py:327-363) =================
+        Dcur = np.asarray(Xd[0:dsz[0], 0:dsz[1]], dtype=dtype)
+        for name, val in (('ObjFun', dfd + lm * rl1), ('DFid', dfd), ('RegL1', rl1), ('Cnstr', cns),
+                          ('XPrRsdl', r), ('XDlRsdl', s), ('XRho', xrho), ('D_L', L),
+                          ('D_Rsdl', drsdl)):
+            cols[name].append(float(val))
+    out = {k: np.array(v, dtype=np.float64) for k, v in cols.items()}
+    out['D'] = Dcur.reshape(dsz[0], dsz[1], M)
+    out['X'] = Y
+    out['time'] = time.perf_counter() - t0
+    return out

@@ -26,6 +26,8 @@ from sporco.pgm import cbpdn as rpgm             # noqa: E402
 from sporco.pgm.backtrack import BacktrackStandard  # noqa: E402
 from sporco import linalg as rlinalg, prox as rprox, fft as rfft   # noqa: E402
 from oracle import cbpdn_oracle as orc           # noqa: E402
+from oracle import cbpdndl_oracle as orcdl       # noqa: E402
+from sporco.dictlrn import cbpdndl as rcbpdndl   # noqa: E402
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
@@ -89,6 +91,49 @@ def pgm_case(tag, dt, D, S, lmbda, opt_ref, opt_orc, dimK=None):
     print('wrote', tag)
 
 
+CDL_FIELDS = ('ObjFun', 'DFid', 'RegL1', 'Cnstr', 'XPrRsdl', 'XDlRsdl', 'XRho', 'D_L', 'D_Rsdl')
+
+
+CDL_OPT = {'MaxMainIter': 25, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}}, 'CCMOD': {'L': 40.0}}
+CDL_OPT_ZM = {'MaxMainIter': 20, 'CBPDN': {'NonNegCoef': True},
+              'CCMOD': {'L': 60.0, 'ZeroMean': True}}
+
+
+CDL_OPT_PGMX = {'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}
+
+
+def cdl_case(tag, dt, D0, S, lmbda, opt):
+    """ConvBPDNDictLearn with its default solvers (ADMM X step, PGM D step)."""
+    b = rcbpdndl.ConvBPDNDictLearn(D0, S, lmbda, rcbpdndl.ConvBPDNDictLearn.Options(
+        opt, xmethod='admm', dmethod='pgm'), xmethod='admm', dmethod='pgm', dimK=1)
+    D1 = b.solve()
+    r = orcdl.cbpdndl(D0, S, lmbda, opt)
+    same(D1.squeeze(), r['D'], tag + ' D')            # the reference returns (hd, wd, 1, 1, M)
+    same(b.getcoef(), r['X'], tag + ' X')
+    its = b.getitstat()
+    for name in CDL_FIELDS:
+        same(stat(its, name), r[name], tag + ' ' + name)
+    out = dict(D0=D0, S=S, lmbda=np.float64(lmbda), D=D1, X=b.getcoef())
+    out.update({name: stat(its, name) for name in CDL_FIELDS})
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag)
+
+
+def cdl_ref_case(tag, dt, D0, S, lmbda, opt, xmethod):
+    """Variants the numpy oracle does not restate (PGM X step, AccurateDFid): the fixture holds
+    the reference's own outputs."""
+    b = rcbpdndl.ConvBPDNDictLearn(D0, S, lmbda, rcbpdndl.ConvBPDNDictLearn.Options(
+        opt, xmethod=xmethod, dmethod='pgm'), xmethod=xmethod, dmethod='pgm', dimK=1)
+    D1 = b.solve()
+    its = b.getitstat()
+    out = dict(D0=D0, S=S, lmbda=np.float64(lmbda), D=D1, X=b.getcoef())
+    for name in its._fields:
+        if name not in ('Iter', 'Time') and getattr(its, name)[0] is not None:
+            out[name] = stat(its, name)
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag, sorted(out))
+
+
 def level1():
     """Known-answer vectors for the level-1 functions from the reference itself."""
     rng = np.random.default_rng(7)
@@ -139,6 +184,12 @@ def main():
         pgm_case('pgm_fixed_' + sfx, dt, D, S, 0.1,
                  {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0},
                  {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0}, dimK=1)
+        D0 = rng.standard_normal((6, 6, 5)).astype(dt)
+        S4 = rng.standard_normal((32, 32, 4)).astype(dt)
+        cdl_case('cdl_' + sfx, dt, D0, S4, 0.1, CDL_OPT)
+        cdl_case('cdl_zm_' + sfx, dt, D0, S4, 0.2, CDL_OPT_ZM)
+        cdl_ref_case('cdl_accdfid_' + sfx, dt, D0, S4, 0.1, dict(CDL_OPT, AccurateDFid=True), 'admm')
+        cdl_ref_case('cdl_pgmx_' + sfx, dt, D0, S4, 0.1, CDL_OPT_PGMX, 'pgm')
 
 
 if __name__ == '__main__':

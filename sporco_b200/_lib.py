@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libspcsc.so')
 
 F32, F64 = 0, 1
 ARR_Y, ARR_U, ARR_X, ARR_XF, ARR_DF, ARR_SF, ARR_PGM_X, ARR_PGM_XF, ARR_PGM_YF = range(9)
+COEF_ADMM_Y, COEF_PGM_X = 0, 1
 
 # every symbol include/spcsc.h declares (tests check the list against the header)
 SYMBOLS = (
@@ -26,7 +27,8 @@ SYMBOLS = (
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
-    'spcsc_pgm_accept',
+    'spcsc_pgm_accept', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
+    'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
 )
 
 
@@ -101,6 +103,12 @@ def _declare(lib):
     lib.spcsc_pgm_reset.argtypes = [vp, vp]
     lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
+    lib.spcsc_ccmod_reset.argtypes = [vp, vp, i32]
+    lib.spcsc_ccmod_setcoef_device.argtypes = [vp, i32]
+    lib.spcsc_ccmod_setcoef.argtypes = [vp, vp]
+    lib.spcsc_ccmod_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    lib.spcsc_ccmod_get_dict.argtypes = [vp, vp]
+    lib.spcsc_ccmod_push_dict.argtypes = [vp]
     lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
     lib.spcsc_comm_create.argtypes = [ctypes.c_char_p, vp, i32, i32, i32, ctypes.POINTER(vp)]
     lib.spcsc_comm_destroy.argtypes = [vp]
@@ -323,6 +331,33 @@ class Handle(object):
 
     def pgm_accept(self, coef):
         self._c(self.lib.spcsc_pgm_accept(self.h, float(coef)))
+
+    # ---- dictionary update
+    def ccmod_reset(self, D0, zero_mean):
+        d = self.dims
+        D0 = self._host(D0, (d['hd'], d['wd'], d['Cd'], d['M']))
+        self._c(self.lib.spcsc_ccmod_reset(self.h, _ptr(D0), int(bool(zero_mean))))
+
+    def ccmod_setcoef_device(self, source):
+        self._c(self.lib.spcsc_ccmod_setcoef_device(self.h, int(source)))
+
+    def ccmod_setcoef(self, Z):
+        Z = self._host(Z, self.xshape())
+        self._c(self.lib.spcsc_ccmod_setcoef(self.h, _ptr(Z)))
+
+    def ccmod_step(self, L, coef):
+        out = (ctypes.c_double * 4)()
+        self._c(self.lib.spcsc_ccmod_step(self.h, float(L), float(coef), out))
+        return [out[i] for i in range(4)]
+
+    def ccmod_get_dict(self):
+        d = self.dims
+        out = np.empty((d['hd'], d['wd'], d['Cd'], d['M']), dtype=self.dtype)
+        self._c(self.lib.spcsc_ccmod_get_dict(self.h, _ptr(out)))
+        return out
+
+    def ccmod_push_dict(self):
+        self._c(self.lib.spcsc_ccmod_push_dict(self.h))
 
     def attach_comm(self, comm, global_nx):
         self._comm = comm                      # keep the communicator alive

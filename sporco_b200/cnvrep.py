@@ -60,3 +60,98 @@ def l1Wshape(W, cri):
     if W.ndim == cri.dimN + 3:
         return W.shape
     return W.shape[:-1] + (1,) * (2 - cri.dimC - cri.dimK) + W.shape[-1:]
+
+
+# ---- dictionary-update side (sporco/cnvrep.py:277-470, 868-1074), single filter-support size ----
+
+def _single_support(dsz, dimN):
+    if isinstance(dsz[0], (tuple, list)):
+        raise NotImplementedError('multi-scale dictionary size specifications are not supported')
+    if len(dsz) not in (dimN + 1, dimN + 2):
+        raise ValueError('dsz must have dimN+1 or dimN+2 entries')
+    return tuple(int(v) for v in dsz)
+
+
+class CDU_ConvRepIndexing(object):
+    """Array roles for the dictionary update: `dsz` is (hd, wd, M) or (hd, wd, Cd, M)."""
+
+    def __init__(self, dsz, S, dimK=None, dimN=2):
+        dsz = _single_support(dsz, dimN)
+        self.dsz = dsz
+        self.dimCd = len(dsz) - dimN - 1
+        self.Cd = dsz[dimN] if self.dimCd else 1
+        self.M = dsz[-1]
+        nd_extra = S.ndim - dimN
+        if dimK is None:
+            if nd_extra == 0:
+                dimC = dimK = 0
+            elif nd_extra == 1:
+                dimC = self.dimCd
+                dimK = 1 - dimC
+            else:
+                dimC = dimK = 1
+        else:
+            dimC = nd_extra - dimK
+        self.dimN, self.dimC, self.dimK = dimN, dimC, dimK
+        self.C = S.shape[dimN] if dimC == 1 else 1
+        self.Cx = self.C - self.Cd + 1
+        if self.Cd > 1 and self.C != self.Cd:
+            raise ValueError("Multi-channel dictionary with signal with mismatched number "
+                             "of channels (Cd=%d, C=%d)" % (self.Cd, self.C))
+        self.K = S.shape[dimN + dimC] if dimK == 1 else 1
+        self.Nv = tuple(S.shape[:dimN])
+        self.N = int(np.prod(self.Nv))
+        self.axisN = tuple(range(dimN))
+        self.axisC, self.axisK, self.axisM = dimN, dimN + 1, dimN + 2
+        self.shpD = self.Nv + (self.Cd, 1, self.M)
+        self.shpS = self.Nv + (self.C, self.K, 1)
+        self.shpX = self.Nv + (self.Cx, self.K, self.M)
+
+
+def stdformD(D, Cd, M, dimN=2):
+    """Dictionary with explicit channel and (singleton) signal axes (cnvrep.py:473-489)."""
+    return D.reshape(D.shape[0:dimN] + (Cd, 1, M))
+
+
+def zpad(x, Nv):
+    """Zero-pad the leading (spatial) axes of `x` to `Nv` (cnvrep.py:876-891)."""
+    out = np.zeros(tuple(Nv) + x.shape[len(Nv):], dtype=x.dtype)
+    out[tuple(slice(0, n) for n in x.shape[:len(Nv)])] = x
+    return out
+
+
+def bcrop(x, dsz, dimN=2):
+    """Crop the leading (spatial) axes to the filter support (cnvrep.py:894-932)."""
+    dsz = _single_support(dsz, dimN)
+    return x[tuple(slice(0, n) for n in dsz[:dimN])]
+
+
+def zeromean(v, dsz, dimN=2):
+    """Subtract, per filter and channel, the mean over the filter support (cnvrep.py:779-820)."""
+    dsz = _single_support(dsz, dimN)
+    vz = v.copy()
+    sl = tuple(slice(0, n) for n in dsz[:dimN])
+    vz[sl] -= np.mean(v[sl], axis=tuple(range(dimN)))
+    return vz
+
+
+def normalise(v, dimN=2):
+    """Scale every filter to unit l2 norm over its first `dimN` axes; zero filters stay zero
+    (cnvrep.py:823-848)."""
+    ax = tuple(range(dimN))
+    vn = np.sqrt(np.sum(v ** 2, ax, keepdims=True))
+    vn[vn == 0] = 1.0
+    return np.asarray(v / vn, dtype=v.dtype)
+
+
+def Pcn(x, dsz, Nv, dimN=2, dimC=1, crp=False, zm=False):
+    """Projection onto the constraint set: support `dsz`, optional zero mean, unit norm
+    (cnvrep.py:953-1033)."""
+    pad = (lambda a: a) if crp else (lambda a: zpad(a, Nv))
+    zmf = (lambda a: zeromean(a, dsz, dimN)) if zm else (lambda a: a)
+    return normalise(zmf(pad(bcrop(x, dsz, dimN))), dimN + dimC)
+
+
+def getPcn(dsz, Nv, dimN=2, dimC=1, crp=False, zm=False):
+    """Closure form of :func:`Pcn` (cnvrep.py:1036-1074)."""
+    return lambda x: Pcn(x, dsz, Nv, dimN, dimC, crp, zm)

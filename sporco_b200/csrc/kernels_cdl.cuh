@@ -1,0 +1,188 @@
+// kernels_cdl.cuh -- dictionary update (constrained convolutional MOD by PGM) on the device.
+//
+// Replaces the array work of sporco.pgm.ccmod.ConvCnstrMOD (sporco/pgm/ccmod.py:264-404) inside
+// the alternation of sporco.dictlrn.dictlrn.DictLearn.solve (dictlrn/dictlrn.py:327-363):
+//   setcoef     Zf = rfftn(Z)                                    -> forward2d of the ADMM Y
+//   grad_f      g_m = sum_k conj(Zf_km) (sum_m' Zf_km' Yf_m' - Sf_k)   -> k_ccmod_grad
+//   xstep       Vf = Yf - g/L ; V = irfftn(Vf) ; X = Pcn(V) ; Xf = rfftn(X)
+//   ystep       Yf = Xf + coef (Xf - Xfprv)
+//   rsdl / obfn rfl2norm2(Xf - Yfprv), rfl2norm2(sum_m Zf Xf - Sf)/2, ||Pcn(X) - X||
+// The dictionary iterate lives in the layout of Df ([Cd][N1f][M][N0] spectra, [Cd][M][N0][N1]
+// real), so handing the new dictionary to the X step is a device copy.  The coefficient spectra
+// Zf use the slab layout of the X step ([K][N1f][M][N0]); the only large traffic of a D step is
+// one read of Zf for the gradient and one for the data-fidelity value.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace spcsc {
+
+enum { ACC_CDL_F = 8, ACC_CDL_DFID = 9, ACC_CDL_RSDL = 10, ACC_CDL_CNS = 11 };
+
+// One CTA per (wf, tile of HT=32 frequencies h): threads = 32 h-lanes x 8 filter groups.
+// For every image k: R_k[h] = sum_m Zf[k][m][h] Yf[m][h] - Sf[k][h];  g[m][h] += conj(Zf[k][m][h]) R_k[h].
+// GRAD == false: only the (plain and Hermitian-weighted) sums of |R_k|^2 are accumulated.
+template <typename T, int MI, bool GRAD>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(256)
+k_ccmod_grad(const C2<T>* SPCSC_RESTRICT Zf, const C2<T>* SPCSC_RESTRICT Yf,
+             const C2<T>* SPCSC_RESTRICT Sf, C2<T>* SPCSC_RESTRICT gout, double* SPCSC_RESTRICT acc,
+             int K, int N1f, int M, int N0, int even_n1) {
+    __shared__ C2<T> red[8][33];
+    __shared__ double dred[2 * 32];
+    const int lane = threadIdx.x & 31, mg = threadIdx.x >> 5;
+    const int wf = blockIdx.x, h = blockIdx.y * 32 + lane;
+    const bool hv = h < N0;
+    C2<T> y[MI], g[MI];
+    SPCSC_UNROLL
+    for (int i = 0; i < MI; ++i) {
+        const int m = mg + 8 * i;
+        y[i] = (hv && m < M) ? Yf[((size_t)wf * M + m) * N0 + h] : mk<T>(0, 0);
+        g[i] = mk<T>(0, 0);
+    }
+    double fsum = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const C2<T>* zk = Zf + (((size_t)k * N1f + wf) * M) * N0;
+        C2<T> z[MI];
+        C2<T> part = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int i = 0; i < MI; ++i) {
+            const int m = mg + 8 * i;
+            z[i] = (hv && m < M) ? zk[(size_t)m * N0 + h] : mk<T>(0, 0);
+            part = part + z[i] * y[i];
+        }
+        red[mg][lane] = part;
+        __syncthreads();
+        C2<T> R = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int q = 0; q < 8; ++q) R = R + red[q][lane];
+        if (hv) R = R - Sf[((size_t)k * N1f + wf) * N0 + h];
+        __syncthreads();
+        if (GRAD) {
+            SPCSC_UNROLL
+            for (int i = 0; i < MI; ++i) g[i] = g[i] + mulc(R, z[i]);      // R * conj(z)
+        }
+        if (mg == 0 && hv) fsum += (double)abs2(R);
+    }
+    if (GRAD) {
+        SPCSC_UNROLL
+        for (int i = 0; i < MI; ++i) {
+            const int m = mg + 8 * i;
+            if (hv && m < M) gout[((size_t)wf * M + m) * N0 + h] = g[i];
+        }
+    }
+    const double wgt = (wf == 0 || (even_n1 && wf == N1f - 1)) ? 1.0 : 2.0;
+    double s1[1] = {fsum}, s2[1] = {fsum * wgt};
+    block_accumulate<1>(s1, dred, acc + ACC_CDL_F);
+    block_accumulate<1>(s2, dred, acc + ACC_CDL_DFID);
+}
+
+// Vf = Yf - g / L
+template <typename T>
+SPCSC_GLOBAL void k_ccmod_step(const C2<T>* SPCSC_RESTRICT Yf, const C2<T>* SPCSC_RESTRICT g,
+                               C2<T>* SPCSC_RESTRICT Vf, T L, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const C2<T> a = Yf[i], b = g[i];
+        const T inv = (T)1 / L;
+        Vf[i] = mk<T>(a.re - inv * b.re, a.im - inv * b.im);
+    }
+}
+
+// Constraint-set projection of one filter per CTA (sporco/cnvrep.py:953-1033):
+//   crop to the hd x wd support (all Cd channels), optional zero mean over the support of each
+//   channel, normalise to unit l2 norm (a zero filter stays zero), zero elsewhere.
+// V, X: real [Cd][M][N0][N1].  With `check` the squared distance ||Pcn(V) - V||^2 is accumulated
+// instead of writing X.
+template <typename T>
+SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* SPCSC_RESTRICT acc,
+                        int Cd, int M, int N0, int N1, int hd, int wd, int zero_mean, int check) {
+    __shared__ double red[4 * 32];
+    __shared__ double bc[8];
+    const int m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int ns = hd * wd;
+    // per-channel means over the support, then the norm of the (mean-free) support
+    double nrm2 = 0.0;
+    for (int c = 0; c < Cd; ++c) {
+        const T* v = V + ((size_t)c * M + m) * N0 * N1;
+        double mean = 0.0;
+        if (zero_mean) {
+            double s[1] = {0.0};
+            for (int e = tid; e < ns; e += nt) s[0] += (double)v[(size_t)(e / wd) * N1 + (e % wd)];
+            if (tid == 0) bc[0] = 0.0;
+            __syncthreads();
+            block_accumulate<1>(s, red, bc);
+            __syncthreads();
+            mean = bc[0] / (double)ns;
+            __syncthreads();
+        }
+        double s2[1] = {0.0};
+        for (int e = tid; e < ns; e += nt) {
+            const double x = (double)((T)((double)v[(size_t)(e / wd) * N1 + (e % wd)] - (T)mean));
+            s2[0] += x * x;
+        }
+        if (tid == 0) bc[1] = 0.0;
+        __syncthreads();
+        block_accumulate<1>(s2, red, bc + 1);
+        __syncthreads();
+        nrm2 += bc[1];
+        if (zero_mean && tid == 0) bc[2 + c] = mean;
+        __syncthreads();
+    }
+    T vn = (T)sqrt(nrm2);
+    if (vn == (T)0) vn = (T)1;
+    double d2[1] = {0.0};
+    for (int c = 0; c < Cd; ++c) {
+        const T mean = zero_mean ? (T)bc[2 + c] : (T)0;
+        const T* v = V + ((size_t)c * M + m) * N0 * N1;
+        T* x = X ? X + ((size_t)c * M + m) * N0 * N1 : nullptr;
+        for (int e = tid; e < N0 * N1; e += nt) {
+            const int r = e / N1, q = e - r * N1;
+            const T p = (r < hd && q < wd) ? (v[e] - mean) / vn : (T)0;
+            if (check) {
+                const double d = (double)(p - v[e]);
+                d2[0] += d * d;
+            } else {
+                x[e] = p;
+            }
+        }
+    }
+    if (check) {
+        __syncthreads();
+        block_accumulate<1>(d2, red, acc + ACC_CDL_CNS);
+    }
+}
+
+// Hermitian-weighted sum of |A - B|^2 over spectra in [nb][N1f][M][N0] order (rfl2norm2 weights).
+template <typename T>
+SPCSC_GLOBAL void k_spec_diffnorm(const C2<T>* SPCSC_RESTRICT A, const C2<T>* SPCSC_RESTRICT B,
+                                  double* SPCSC_RESTRICT acc, int nb, int N1f, size_t per_wf,
+                                  int even_n1) {
+    __shared__ double red[32];
+    const size_t n = (size_t)nb * N1f * per_wf;
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int wf = (int)((i / per_wf) % N1f);
+        const double wgt = (wf == 0 || (even_n1 && wf == N1f - 1)) ? 1.0 : 2.0;
+        s[0] += wgt * (double)abs2(A[i] - B[i]);
+    }
+    block_accumulate<1>(s, red, acc + ACC_CDL_RSDL);
+}
+
+// Cropped dictionary in the reference's order (hd, wd, Cd, M) from the device order [Cd][M][N0][N1].
+template <typename T>
+SPCSC_GLOBAL void k_crop_dict(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT D, int hd, int wd, int Cd,
+                              int M, int N0, int N1) {
+    const size_t n = (size_t)hd * wd * Cd * M;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        size_t t = i;
+        const int m = (int)(t % M); t /= M;
+        const int c = (int)(t % Cd); t /= Cd;
+        const int x = (int)(t % wd); t /= wd;
+        const int y = (int)t;
+        D[i] = X[(((size_t)c * M + m) * N0 + y) * N1 + x];
+    }
+}
+
+}  // namespace spcsc

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "launchers.cuh"
+#include "kernels_cdl.cuh"
 
 #ifndef SPCSC_EMU
 #include <dlfcn.h>
@@ -294,6 +295,12 @@ struct spcsc_handle {
     virtual int pgm_reset(const void* X0) = 0;
     virtual int pgm_trial(double L, double* out) = 0;
     virtual int pgm_accept(double coef) = 0;
+    virtual int ccmod_reset(const void* D0, int zero_mean) = 0;
+    virtual int ccmod_setcoef_device(int source) = 0;
+    virtual int ccmod_setcoef(const void* Z) = 0;
+    virtual int ccmod_step(double L, double coef, double* out) = 0;
+    virtual int ccmod_get_dict(void* out) = 0;
+    virtual int ccmod_push_dict() = 0;
 };
 
 namespace {
@@ -363,6 +370,11 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> stw_row1, stw_rowc, stw_col;     // stage twiddles of the v2 register plans
     DevBuf<C2<T>> pgA, pgB;                         // PGM: accepted Xf (= Xfprv), Yf; Zt is the candidate
     spcsc_pgm_opts popts;
+    DevBuf<T> cdX;                                  // CCMOD: dictionary iterate, real [Cd][M][N0][N1]
+    DevBuf<C2<T>> cdXf, cdYf, cdV, cdG;             // its spectrum, the momentum point, scratch, gradient
+    DevBuf<C2<T>> cdZf;                             // coefficient spectra, slab layout [K][N1f][M][N0]
+    bool cd_ready = false, cd_have_coef = false;
+    int cd_zero_mean = 0;
     bool pgm_ready = false, pgm_have_cand = false;
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
     bool gen_rows = false, gen_cols = false;   // any-size direct-DFT path for this axis
@@ -406,6 +418,7 @@ class Engine : public spcsc_handle {
         acc.release(); st.release(); rows.release();
         stw_row1.release(); stw_rowc.release(); stw_col.release();
         pgA.release(); pgB.release(); Zt2.release();
+        cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -975,6 +988,155 @@ class Engine : public spcsc_handle {
         return SPCSC_OK;
     }
 
+    // ---- dictionary update (CCMOD by PGM) --------------------------------------------------
+    int ccmod_check() {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (Cd != 1 || C != 1) FAIL(SPCSC_ERR_UNSUPPORTED, "dictionary update: single-channel dictionary and signal only");
+        if (M > 128) FAIL(SPCSC_ERR_UNSUPPORTED, "dictionary update: more than 128 filters");
+        if (!have_signal) FAIL(SPCSC_ERR_STATE, "dictionary update before set_signal");
+        return SPCSC_OK;
+    }
+    int ccmod_reset(const void* D0, int zero_mean) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        CK(cudaSetDevice(pb.device));
+        const size_t nd = (size_t)pb.hd * pb.wd * Cd * M, nsp = (size_t)Cd * N1f * M * N0;
+        CK(staging.ensure(nd));
+        CK(cdX.ensure((size_t)Cd * M * N0 * N1));
+        CK(cdXf.ensure(nsp)); CK(cdYf.ensure(nsp)); CK(cdV.ensure(nsp)); CK(cdG.ensure(nsp));
+        CK(cudaMemcpyAsync(staging.p, D0, nd * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(launch(k_pad_dict<T>, dim3(1024), dim3(256), 0, stream, (const T*)staging.p, cdX.p,
+                  pb.hd, pb.wd, Cd, M, N0, N1));
+        rc = forward2d(cdX.p, cdXf.p, M, Cd);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(cdYf.p, cdXf.p, nsp * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        cd_zero_mean = zero_mean;
+        cd_ready = true;
+        return SPCSC_OK;
+    }
+    int ccmod_setcoef_device(int source) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        CK(cudaSetDevice(pb.device));
+        CK(cdZf.ensure(nslab));
+        if (source == SPCSC_COEF_ADMM_Y) {
+            rc = forward2d(Y.p, cdZf.p, M, K * Cx);
+            if (rc) return rc;
+        } else if (source == SPCSC_COEF_PGM_X) {
+            if (!pgA.p) FAIL(SPCSC_ERR_STATE, "no PGM iterate on this handle");
+            CK(cudaMemcpyAsync(cdZf.p, pgA.p, nslab * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
+        } else {
+            FAIL(SPCSC_ERR_INVALID, "unknown coefficient source");
+        }
+        cd_have_coef = true;
+        return SPCSC_OK;
+    }
+    int ccmod_setcoef(const void* Z) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        CK(cudaSetDevice(pb.device));
+        CK(tmp_real.ensure(nreal));
+        CK(cdZf.ensure(nslab));
+        rc = to_internal(Z, tmp_real.p, Cx, K, M);
+        if (rc) return rc;
+        rc = forward2d(tmp_real.p, cdZf.p, M, K * Cx);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        cd_have_coef = true;
+        return SPCSC_OK;
+    }
+    template <bool GRAD>
+    cudaError_t launch_grad(const C2<T>* yf, C2<T>* g) {
+        dim3 grid(N1f, (N0 + 31) / 32);
+        if (M <= 64)
+            return launch(k_ccmod_grad<T, 8, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p,
+                          yf, (const C2<T>*)Sf.p, g, acc.p, K, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0);
+        return launch(k_ccmod_grad<T, 16, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p,
+                      yf, (const C2<T>*)Sf.p, g, acc.p, K, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0);
+    }
+    int ccmod_step(double L, double coef, double* out) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cd_ready || !cd_have_coef) FAIL(SPCSC_ERR_STATE, "ccmod_step before ccmod_reset / setcoef");
+        if (!(L > 0.0)) FAIL(SPCSC_ERR_INVALID, "L must be positive");
+        CK(cudaSetDevice(pb.device));
+        const size_t nsp = (size_t)Cd * N1f * M * N0;
+        const int even = (N1 % 2 == 0) ? 1 : 0;
+        double hF = 0.0;
+        CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+        // gradient at Yf (one pass over the coefficient spectra)
+        CK(launch_grad<true>((const C2<T>*)cdYf.p, cdG.p));
+        if (nccl_comm) {   // images are sharded over ranks: the gradient is a sum over all of them
+            int nr = nccl->AllReduce(cdG.p, cdG.p, 2 * nsp, sizeof(T) == 4 ? 7 : 8, 0, nccl_comm, stream);
+            if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+        }
+        CK(cudaMemcpyAsync(&hF, acc.p + ACC_CDL_F, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(launch(k_ccmod_step<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)cdYf.p,
+                  (const C2<T>*)cdG.p, cdV.p, (T)L, nsp));
+        // V = irfftn(Vf): inverse columns, inverse rows
+        ColLaunch<T> ci = colargs(M, Cd);
+        ci.in = cdV.p; ci.out = cdV.p; ci.a.Cd = 1;
+        CK(col<T>(N0, COL_INV, ci));
+        CK(tmp_real.ensure((size_t)Cd * M * N0 * N1));
+        CK(row_inv<T>(H, rowargs(M, Cd, 1), (const C2<T>*)cdV.p, tmp_real.p,
+                      (T)(1.0 / ((double)N0 * (double)N1))));
+        // X = Pcn(V) ; Xf = rfftn(X)  (into cdV, the old Xf stays in cdXf as Xfprv)
+        CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, cdX.p, acc.p, Cd, M,
+                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 0));
+        rc = forward2d(cdX.p, cdV.p, M, Cd);
+        if (rc) return rc;
+        // residual against Yfprv (= Yf before the momentum step), then the momentum step
+        CK(launch(k_spec_diffnorm<T>, dim3(296), dim3(256), 0, stream, (const C2<T>*)cdV.p,
+                  (const C2<T>*)cdYf.p, acc.p, Cd, N1f, (size_t)M * N0, even));
+        CK(launch(k_pgm_momentum<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)cdV.p,
+                  (const C2<T>*)cdXf.p, cdYf.p, (T)coef, nsp));
+        std::swap(cdXf.p, cdV.p);
+        std::swap(cdXf.n, cdV.n);
+        // objective terms of the new iterate: data fidelity (second pass over Zf), constraint violation
+        CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 2 * sizeof(double), stream));
+        CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
+        if (nccl_comm) {
+            int nr = nccl->AllReduce(acc.p + ACC_CDL_DFID, acc.p + ACC_CDL_DFID, 1, 8, 0, nccl_comm, stream);
+            if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+        }
+        CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
+                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
+        double ha[4];
+        CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const double inv_n = 1.0 / ((double)N0 * (double)N1);
+        out[0] = 0.5 * ha[1] * inv_n;
+        out[1] = std::sqrt(ha[3]);
+        out[2] = ha[2] * inv_n;
+        out[3] = 0.5 * hF;
+        return SPCSC_OK;
+    }
+    int ccmod_get_dict(void* out) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cd_ready) FAIL(SPCSC_ERR_STATE, "ccmod_get_dict before ccmod_reset");
+        CK(cudaSetDevice(pb.device));
+        const size_t nd = (size_t)pb.hd * pb.wd * Cd * M;
+        CK(staging.ensure(nd));
+        CK(launch(k_crop_dict<T>, dim3(64), dim3(256), 0, stream, (const T*)cdX.p, staging.p, pb.hd,
+                  pb.wd, Cd, M, N0, N1));
+        CK(cudaMemcpyAsync(out, staging.p, nd * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
+    int ccmod_push_dict() override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cd_ready) FAIL(SPCSC_ERR_STATE, "ccmod_push_dict before ccmod_reset");
+        CK(cudaSetDevice(pb.device));
+        const size_t nsp = (size_t)Cd * N1f * M * N0;
+        CK(cudaMemcpyAsync(Df.p, cdXf.p, nsp * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
+        CK(launch(k_gram<T>, dim3(256), dim3(128), 0, stream, (const C2<T>*)Df.p, G.p, N1f, N0, M, Cd));
+        have_dict = true;
+        return SPCSC_OK;
+    }
+
     // ---- PGM --------------------------------------------------------------------------
     int pgm_configure(const spcsc_pgm_opts* o) override {
         popts = *o;
@@ -1213,6 +1375,12 @@ int spcsc_pgm_configure(spcsc_handle* h, const spcsc_pgm_opts* o) { H_CALL(o ? h
 int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0)); }
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
 int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
+int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ? h->ccmod_reset(D0, zm) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source) { H_CALL(h->ccmod_setcoef_device(source)); }
+int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z) { H_CALL(Z ? h->ccmod_setcoef(Z) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, double out[4]) { H_CALL(out ? h->ccmod_step(L, coef, out) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {
     if (!id128) { g_last_error = "null id buffer"; return SPCSC_ERR_INVALID; }
     NcclApi& api = nccl_api(nccl_lib);

@@ -302,3 +302,101 @@ def run_option_cases(capsys=None):
         assert out[2].split()[0] == '0' and len(out[2].split()) == 7
     # timers exist and advanced
     assert b.timer.elapsed('solve') > 0 and b.timer.elapsed('init') > 0
+
+
+# ---- convolutional dictionary learning (tests/golden/cdl_*.npz, generated from the reference's
+# ConvBPDNDictLearn by oracle/make_golden.py)
+CDL_OPT = {'MaxMainIter': 25, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}}, 'CCMOD': {'L': 40.0}}
+CDL_CASES = {
+    # tag: (options, xmethod, lambda)
+    'cdl': (CDL_OPT, 'admm', 0.1),
+    'cdl_zm': ({'MaxMainIter': 20, 'CBPDN': {'NonNegCoef': True},
+                'CCMOD': {'L': 60.0, 'ZeroMean': True}}, 'admm', 0.2),
+    'cdl_accdfid': (dict(CDL_OPT, AccurateDFid=True), 'admm', 0.1),
+    'cdl_pgmx': ({'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}, 'pgm', 0.1),
+}
+
+
+def run_cdl_case(tag, sfx):
+    """Learn the golden dictionary with sporco_b200 and compare with the reference's outputs."""
+    from sporco_b200.dictlrn import cbpdndl
+    g = load('%s_%s' % (tag, sfx))
+    o, xmethod, lmbda = CDL_CASES[tag]
+    assert float(g['lmbda']) == lmbda
+    # float32: north_star's rtol 1e-4, except the PGM X step case, where the reference's own
+    # float32 and float64 runs drift apart by 2.1e-4 (D) over these 20 alternations
+    tol = 1e-10 if sfx == 'f64' else (1e-3 if tag == 'cdl_pgmx' else 1e-4)
+    opt = cbpdndl.ConvBPDNDictLearn.Options(o, xmethod=xmethod, dmethod='pgm')
+    b = cbpdndl.ConvBPDNDictLearn(g['D0'], g['S'], lmbda, opt, xmethod=xmethod, dmethod='pgm')
+    D = b.solve()
+    its = b.getitstat()
+    assert D.dtype == g['D'].dtype and D.shape == g['D'].shape
+    assert rel(D, g['D']) <= tol, 'D: %.3e' % rel(D, g['D'])
+    X = b.getcoef()
+    assert X.shape == g['X'].shape and rel(X, g['X']) <= 3 * tol, 'X: %.3e' % rel(X, g['X'])
+    names = [f for f in its._fields if f in g.files and f != 'Cnstr']
+    assert len(names) >= 6
+    for f in names:
+        assert len(getattr(its, f)) == len(g[f])
+        assert rel(getattr(its, f), g[f]) <= 10 * tol, '%s: %.3e' % (f, rel(getattr(its, f), g[f]))
+    # constraint violation of a projected iterate: rounding level in both implementations
+    lim = 1e-12 if sfx == 'f64' else 1e-5
+    assert np.max(np.abs(its.Cnstr)) < lim and np.max(np.abs(g['Cnstr'])) < lim
+    # learned filters: unit norm, support respected, dictionary handed to the X step
+    Dc = D.reshape(D.shape[0], D.shape[1], -1)
+    assert np.allclose(np.sqrt(np.sum(Dc.astype(np.float64) ** 2, (0, 1))), 1.0,
+                       atol=1e-12 if sfx == 'f64' else 1e-5)
+    full = b.getdict(crop=False)
+    assert full.shape[:2] == g['S'].shape[:2] and not np.any(full[D.shape[0]:]) \
+        and not np.any(full[:, D.shape[1]:])
+    rec = b.reconstruct()
+    assert rec.shape[:2] == g['S'].shape[:2]
+    assert rel(b.xstep.D.squeeze(), D.squeeze()) == 0.0
+    return b
+
+
+def run_ccmod_standalone(dt):
+    """sporco_b200.pgm.ccmod.ConvCnstrMOD on its own (coefficients from the host) against the
+    oracle's D-step algebra."""
+    from oracle import cbpdn_oracle as co
+    from oracle import cbpdndl_oracle as oc
+    from sporco_b200.pgm import ccmod
+    rng = np.random.default_rng(5)
+    N0, N1, K, M, hd, wd = 16, 32, 3, 5, 4, 6
+    S = rng.standard_normal((N0, N1, K)).astype(dt)
+    Z = (rng.standard_normal((N0, N1, 1, K, M)) * (rng.random((N0, N1, 1, K, M)) < 0.2)).astype(dt)
+    X0 = np.zeros((N0, N1, 1, 1, M), dt)
+    X0[:hd, :wd] = oc.pcn(rng.standard_normal((N0, N1, 1, 1, M)).astype(dt), (hd, wd, M),
+                          (N0, N1))[:hd, :wd]
+    L = 25.0
+    opt = ccmod.ConvCnstrMOD.Options({'MaxMainIter': 7, 'L': L, 'X0': X0, 'RelStopTol': 0.0})
+    c = ccmod.ConvCnstrMOD(Z, S, (hd, wd, M), opt)
+    c.solve()
+    its = c.getitstat()
+    # numpy restatement of pgm/pgm.py:328-370 + pgm/ccmod.py:295-376
+    fft = co.FFTBackend()
+    ax = (0, 1)
+    Sf = fft.rfftn(S.reshape(N0, N1, 1, K, 1), None, ax)
+    Zf = fft.rfftn(Z, None, ax)
+    Xd = X0.copy()
+    Xf = fft.rfftn(Xd, None, ax)
+    Yf = Xf
+    t = 1.0
+    dfd, rs = [], []
+    for _ in range(7):
+        Xfp, Yfp = Xf, Yf
+        g = co.inner(np.conj(Zf), co.inner(Zf, Yf, 4) - Sf, 3)
+        V = fft.irfftn(Yf - g / dt(L), (N0, N1), ax)
+        Xd = oc.pcn(V, (hd, wd, M), (N0, N1))
+        Xf = fft.rfftn(Xd, None, ax)
+        tp = t
+        t = 0.5 * (1. + np.sqrt(1. + 4. * t ** 2))
+        Yf = Xf + ((tp - 1.) / t) * (Xf - Xfp)
+        rs.append(co.rfl2norm2(Xf - Yfp, Xd.shape, axis=ax))
+        dfd.append(co.rfl2norm2(co.inner(Zf, Xf, 4) - Sf, (N0, N1, 1, K, 1), axis=ax) / 2.0)
+    tol = 1e-11 if dt == np.float64 else 3e-5
+    assert rel(c.getdict(crop=False), Xd) < tol
+    assert c.getdict().shape == (hd, wd, 1, 1, M)
+    assert rel(its.DFid, dfd) < 10 * tol and rel(its.Rsdl, rs) < 10 * tol
+    assert all(v == dt(L) for v in its.L)
+    return c

@@ -45,6 +45,19 @@ def test_oracle_reproduces_golden_pgm(sfx):
     assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
 
 
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', ['cdl', 'cdl_zm'])
+def test_oracle_reproduces_golden_dictionary_learning(tag, sfx):
+    from oracle import cbpdndl_oracle as ocdl
+    g = cases.load('%s_%s' % (tag, sfx))
+    o, _, lmbda = cases.CDL_CASES[tag]
+    r = ocdl.cbpdndl(g['D0'], g['S'], lmbda, o)
+    assert np.array_equal(r['D'], g['D'].squeeze())
+    assert np.array_equal(r['X'], g['X'])
+    for f in ('ObjFun', 'DFid', 'RegL1', 'Cnstr', 'XPrRsdl', 'XDlRsdl', 'XRho', 'D_L', 'D_Rsdl'):
+        assert np.array_equal(r[f], g[f]), f
+
+
 def test_oracle_level1_known_answers():
     g = cases.load('level1')
     assert np.array_equal(orc.solvedbi_sm(g['ah'], 0.7, g['b'], 4), g['x'])

@@ -184,3 +184,16 @@ def test_multichannel_dictionary_fast_path():
 
 def test_option_paths(capsys):
     cases.run_option_cases(capsys)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.CDL_CASES))
+def test_dictionary_learning_golden(tag, sfx):
+    cases.run_cdl_case(tag, sfx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dt', [np.float64, np.float32])
+def test_ccmod_standalone(dt):
+    cases.run_ccmod_standalone(dt)
