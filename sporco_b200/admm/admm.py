@@ -87,6 +87,12 @@ class ADMM(common.IterativeSolver):
 
     # ---- outer loop (sporco/admm/admm.py:293-389)
     def solve(self):
+        self.run()
+        return self.getmin()
+
+    def run(self):
+        """The body of :meth:`solve` without the final host copy of the minimiser: callers
+        that keep the result on the device (dictionary learning) use this."""
         fmtstr, nsep = self.display_start()
         self.timer.start(['solve', 'solve_wo_func', 'solve_wo_rsdl'])
         per_iter = self.opt['Verbose'] or self.opt['Callback'] is not None
@@ -116,7 +122,6 @@ class ADMM(common.IterativeSolver):
                 stop = True
         self.timer.stop(['solve', 'solve_wo_func', 'solve_wo_rsdl'])
         self.display_end(nsep)
-        return self.getmin()
 
     def getmin(self):
         return self.X

@@ -152,7 +152,14 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
             fmtmap={'It_X': '%4d', 'It_D': '%4d'})
         super(ConvBPDNDictLearn, self).__init__(xstep, dstep, opt, isc)
 
-    # ---- the two hand-overs stay on the device (dictlrn/dictlrn.py:379-389)
+    # ---- both steps run without copying their minimiser to the host ...
+    def run_xstep(self):
+        self.xstep.run()
+
+    def run_dstep(self):
+        self.dstep.run()
+
+    # ---- ... and the two hand-overs stay on the device (dictlrn/dictlrn.py:379-389)
     def post_xstep(self):
         self.dstep.setcoef_from_xstep(self._coef_source)
 

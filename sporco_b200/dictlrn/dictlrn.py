@@ -89,9 +89,9 @@ class DictLearn(object):
             self.isc.printheader()
         self.timer.start(['solve', 'solve_wo_eval'])
         for self.j in range(self.j, self.j + self.opt['MaxMainIter']):
-            self.xstep.solve()
+            self.run_xstep()
             self.post_xstep()
-            self.dstep.solve()
+            self.run_dstep()
             self.post_dstep()
             self.timer.stop('solve_wo_eval')
             evl = self.evaluate()
@@ -114,6 +114,12 @@ class DictLearn(object):
         if self.opt['Verbose'] and self.opt['StatusHeader']:
             self.isc.printseparator()
         return self.getdict()
+
+    def run_xstep(self):
+        self.xstep.solve()
+
+    def run_dstep(self):
+        self.dstep.solve()
 
     def post_xstep(self):
         self.dstep.setcoef(self.xstep.getcoef())

@@ -80,6 +80,11 @@ class PGM(common.IterativeSolver):
     # device-backed subclass provides _trial(), ystep(), _stats()
     def solve(self):
         """Outer loop of sporco/pgm/pgm.py:284-383."""
+        self.run()
+        return self.getmin()
+
+    def run(self):
+        """:meth:`solve` without the final host copy of the minimiser."""
         fmtstr, nsep = self.display_start()
         self.timer.start(['solve', 'solve_wo_func', 'solve_wo_rsdl', 'solve_wo_btrack'])
         for self.k in range(self.k, self.k + self.opt['MaxMainIter']):
@@ -107,7 +112,6 @@ class PGM(common.IterativeSolver):
         self.k += 1
         self.timer.stop(['solve', 'solve_wo_func', 'solve_wo_rsdl', 'solve_wo_btrack'])
         self.display_end(nsep)
-        return self.getmin()
 
     def getmin(self):
         return self.X

@@ -37,6 +37,23 @@ def main():
     obj_ref = np.array([row[1] for row in r.itstat], dtype=np.float64)
     obj_err = np.abs(obj - obj_ref).max() / np.abs(obj_ref).max()
     ok = err < 3e-4 and rho_err < 1e-4 and obj_err < 1e-4
+    # dictionary learning with the training images sharded: gradient summed over ranks on the device
+    from oracle import cbpdndl_oracle as ocdl
+    from sporco_b200.dictlrn import cbpdndl
+    D0 = rng.standard_normal((6, 6, 8)).astype(np.float32)
+    o = {'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}}, 'CCMOD': {'L': 60.0}}
+    dl = cbpdndl.ConvBPDNDictLearn(D0, S[:, :, mine], 0.1, cbpdndl.ConvBPDNDictLearn.Options(o),
+                                   device=local)
+    dl.attach_process_group(dist)
+    Dl = dl.solve().squeeze()
+    rd = ocdl.cbpdndl(D0, S, 0.1, o)
+    d_err = np.linalg.norm((Dl - rd['D']).ravel()) / np.linalg.norm(rd['D'].ravel())
+    its = dl.getitstat()
+    dobj_err = np.abs(np.array(its.ObjFun) - rd['ObjFun']).max() / np.abs(rd['ObjFun']).max()
+    drs_err = np.abs(np.array(its.D_Rsdl) - rd['D_Rsdl']).max() / np.abs(rd['D_Rsdl']).max()
+    print('rank %d: dictlearn D err %.3e obj err %.3e rsdl err %.3e' % (rank, d_err, dobj_err, drs_err),
+          flush=True)
+    ok = ok and d_err < 1e-4 and dobj_err < 1e-4 and drs_err < 1e-3
     t = torch.tensor([1.0 if ok else 0.0], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     print('rank %d: Y err %.3e rho err %.3e obj err %.3e' % (rank, err, rho_err, obj_err), flush=True)

@@ -55,6 +55,44 @@ def main():
         S = rng.standard_normal((256, 256, 8))
         o = cbpdn.ConvBPDN.Options({'RelStopTol': 0.0, 'FastSolve': True})
         admm('f64: ConvBPDN 256x256, 8x8x64, K=8, float64', cbpdn.ConvBPDN(D, S, 0.1, o, dimK=1), 50, 10)
+    if 'cfg5' in which:
+        from sporco_b200.dictlrn import cbpdndl
+        D0 = rng.standard_normal((8, 8, 64)).astype(np.float32)
+        S = rng.standard_normal((256, 256, 16)).astype(np.float32)
+        o = cbpdndl.ConvBPDNDictLearn.Options({'MaxMainIter': 20})
+        b = cbpdndl.ConvBPDNDictLearn(D0, S, 0.1, o)
+        b.solve()
+        b.opt['MaxMainIter'] = 100
+        b.xstep._h.synchronize()
+        t0 = time.perf_counter()
+        b.solve()
+        b.xstep._h.synchronize()
+        dt = time.perf_counter() - t0
+        # split: X step alone / D step alone, same sizes
+        h = b.xstep._h
+        t1 = time.perf_counter()
+        for _ in range(50):
+            b.run_xstep()
+        h.synchronize()
+        tx = (time.perf_counter() - t1) / 50
+        t1 = time.perf_counter()
+        for _ in range(50):
+            b.post_xstep()
+            b.run_dstep()
+            b.post_dstep()
+        h.synchronize()
+        td = (time.perf_counter() - t1) / 50
+        its = b.getitstat()
+        print(json.dumps({'config': 'cfg5: ConvBPDNDictLearn 256x256x16, 8x8x64, admm X / pgm D, f32',
+                          'ms_per_outer_iter': dt / 100 * 1e3, 'outer_it_per_s': 100 / dt,
+                          'ms_xstep': tx * 1e3, 'ms_dstep_incl_handover': td * 1e3,
+                          'ObjFun_first_last': [float(its.ObjFun[0]), float(its.ObjFun[-1])]}))
+        if 'cpu' in which:
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            from oracle import cbpdn_oracle as co, cbpdndl_oracle as ocdl
+            r = ocdl.cbpdndl(D0, S, 0.1, {'MaxMainIter': 2}, fft=co.FFTBackend('scipy', workers=os.cpu_count()))
+            print(json.dumps({'config': 'cfg5 CPU oracle (scipy.fft workers=all), 2 outer iterations',
+                              's_per_outer_iter': r['time'] / 2}))
     if 'cfg4' in which:
         D = unit(rng.standard_normal((12, 12, 128))).astype(np.float32)
         S = rng.standard_normal((512, 512)).astype(np.float32)
