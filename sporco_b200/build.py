@@ -57,7 +57,7 @@ def _run(cmd):
 
 def build(force=False, jobs=None, verbose=False, extra_flags=()):
     """Compile and link libspcsc.so; returns its path.  No-op when sources are unchanged."""
-    stamp = os.path.join(BUILD, 'stamp')
+    stamp = LIB + '.stamp'        # next to the library: objects need not travel with it
     digest = source_hash() + ' ' + ' '.join(extra_flags)
     if (not force and os.path.exists(LIB) and os.path.exists(stamp)
             and open(stamp).read() == digest):

@@ -254,6 +254,25 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
 // PLAIN: no NonNegCoef / NoBndryCross, spatially uniform weights, regulariser evaluated on X --
 // the common configuration; the flag tests and per-element weight fetches then compile away.
 // ------------------------------------------------------------------------------------
+// Shared-memory plan of k_row_inv_prox3.  A warp holds 32/TPF rows; 64-bit shared accesses are
+// served per half-warp, so with TPF = 8 two rows share a pass and must fall on complementary
+// halves of the 32 banks.  REMAP: lane groups 2i and 2i+1 take rows i and i+8 -- 8 rows of odd
+// stride P apart is 16 banks -- and rows >= 8 of the Y/U tiles are shifted by 8 elements for the
+// same reason (the profile of the unshifted layout showed every row access 2-way conflicted).
+template <typename T, int H, int E, int CX, int NT>
+struct Prox3Plan {
+    static constexpr int TPF = H / E, TR = NT / TPF, P = H + H / 16 + 1, N1f = H + 1;
+    static constexpr bool REMAP = (sizeof(C2<T>) == 8 && TPF == 8 && E == 16 && TR % 16 == 0);
+    static constexpr int YS = TR * H + (REMAP ? TR : 0);       // one channel of a Y / U tile
+    static constexpr int TWLEN = stage_tw_len(H, E);
+    static constexpr size_t smem_bytes =
+        ((size_t)CX * (2 * YS + TR * P) + TWLEN + N1f) * sizeof(C2<T>);
+    static SPCSC_HD int row_of_group(int gi) {
+        return REMAP ? ((gi & ~15) | ((gi & 1) << 3) | ((gi & 15) >> 1)) : gi;
+    }
+    static SPCSC_HD int yoff(int g) { return g * H + (REMAP ? 8 * (g >> 3) : 0); }
+};
+
 template <typename T, int H, int E, int CX, int NT, bool PLAIN>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? (CX == 1 ? 4 : 3) : 2))
 k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* SPCSC_RESTRICT Y,
@@ -264,14 +283,17 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
                 int bnd1, int reg_on_y) {
     if (st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
-    constexpr int TPF = H / E, TR = NT / TPF, P = H + H / 16 + 1, N1f = H + 1;
-    constexpr int TWLEN = stage_tw_len(H, E);
+    using PL = Prox3Plan<T, H, E, CX, NT>;
+    constexpr int TPF = PL::TPF, TR = PL::TR, P = PL::P, N1f = PL::N1f, YS = PL::YS;
+    constexpr int TWLEN = PL::TWLEN;
     constexpr int VEC = 16 / sizeof(C2<T>);                    // complex values per 16-byte copy
     constexpr int WSTEP = NT / TR;
-    C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [CX][TR][H]  (as complex pairs)
-    C2<T>* ubuf = ybuf + CX * TR * H;                          // [CX][TR][H]
-    C2<T>* reg = ubuf + CX * TR * H;                           // [CX][TR][P]
-    C2<T>* stw_s = reg + CX * TR * P;
+    constexpr int WIT = (N1f + WSTEP - 1) / WSTEP;             // wf iterations of the tile loops
+    C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [CX][YS]  (rows of H complex pairs)
+    C2<T>* ubuf = ybuf + CX * YS;                              // [CX][YS]
+    C2<T>* reg = ubuf + CX * YS;                               // [CX][TR][P]
+    C2<T>* stw_s = reg + CX * TR * P;                          // [TWLEN] stage twiddles
+    C2<T>* tw_s = stw_s + TWLEN;                               // [N1f] split twiddles
     const int tid = threadIdx.x;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
     const size_t wstride = (size_t)M * N0;
@@ -281,8 +303,10 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         const C2<T>* src = Zt + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0 +
                            (size_t)wf0 * wstride + gr;
         C2<T>* dst = reg + (c * TR + gr) * P + wf0;
-        for (int wf = wf0; wf < N1f; wf += WSTEP, src += (size_t)WSTEP * wstride, dst += WSTEP)
-            cp_async<sizeof(C2<T>)>(dst, src);
+        SPCSC_UNROLL
+        for (int it = 0; it < WIT; ++it)
+            if (wf0 + it * WSTEP < N1f)
+                cp_async<sizeof(C2<T>)>(dst + it * WSTEP, src + (size_t)it * WSTEP * wstride);
     }
     cp_async_commit();
     SPCSC_UNROLL
@@ -290,15 +314,19 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         const size_t tile = ((((size_t)(k * CX + c) * M + m) * N0 + h0) * H);
         const C2<T>* y2 = reinterpret_cast<const C2<T>*>(Y) + tile;
         const C2<T>* u2 = reinterpret_cast<const C2<T>*>(U) + tile;
+        SPCSC_UNROLL
         for (int e = tid * VEC; e < TR * H; e += NT * VEC) {
-            cp_async<16>(ybuf + c * TR * H + e, y2 + e);
-            cp_async<16>(ubuf + c * TR * H + e, u2 + e);
+            const int d = c * YS + e + (PL::REMAP ? 8 * (e / (8 * H)) : 0);
+            cp_async<16>(ybuf + d, y2 + e);
+            cp_async<16>(ubuf + d, u2 + e);
         }
     }
     cp_async_commit();
     for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
-    const int g = tid / TPF, t = tid % TPF;
+    for (int i = tid; i < N1f; i += NT) tw_s[i] = tw[i];
+    const int g = PL::row_of_group(tid / TPF), t = tid % TPF;
     const int h = h0 + g;
+    const int yrow = PL::yoff(g);
     cp_async_wait<1>();
     __syncthreads();
 
@@ -314,7 +342,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
                 v[c][p] = mk<T>(a + cc, a - cc);
             } else {
                 const C2<T> Xa = row[kk], Xb = row[H - kk];
-                const C2<T> w = tw[kk];
+                const C2<T> w = tw_s[kk];
                 const C2<T> s1 = Xa + conj(Xb), d1 = Xa - conj(Xb);
                 v[c][p] = s1 + mul_i(mulc(d1, w));
             }
@@ -354,7 +382,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         T a2[2] = {0, 0};
         SPCSC_UNROLL
         for (int c = 0; c < CX; ++c) {
-            const C2<T> y2 = ybuf[(c * TR + g) * H + j], u2 = ubuf[(c * TR + g) * H + j];
+            const C2<T> y2 = ybuf[c * YS + yrow + j], u2 = ubuf[c * YS + yrow + j];
             const T xs[2] = {v[c][p].re * scale, v[c][p].im * scale};
             const T ys[2] = {y2.re, y2.im};
             const T us[2] = {u2.re * uinv, u2.im * uinv};
@@ -440,12 +468,17 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
             const C2<T>* row = reg + (c * TR + gr) * P;
             C2<T>* out = Znext + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0 +
                          (size_t)wf0 * wstride + gr;
-            for (int wf = wf0; wf < N1f; wf += WSTEP, out += (size_t)WSTEP * wstride) {
-                const C2<T> a = row[wf == H ? 0 : wf];
-                const C2<T> bb = conj(row[wf == 0 ? 0 : H - wf]);
-                const C2<T> w = tw[wf];
-                const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
-                *out = mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+            SPCSC_UNROLL
+            for (int it = 0; it < WIT; ++it) {
+                const int wf = wf0 + it * WSTEP;
+                if (wf < N1f) {
+                    const C2<T> a = row[wf == H ? 0 : wf];
+                    const C2<T> bb = conj(row[wf == 0 ? 0 : H - wf]);
+                    const C2<T> w = tw_s[wf];
+                    const C2<T> sum = a + bb, dif = mul_mi((a - bb) * w);
+                    out[(size_t)it * WSTEP * wstride] =
+                        mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+                }
             }
         }
     }

@@ -212,7 +212,7 @@ static cudaError_t row_inv_prox3_nt(const RowArgs<T>& r, const ProxArgs<T>& p, c
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
     constexpr int E = row2_elems(H, CX), TR = NT / (H / E);
     if (r.N0 % TR != 0) return cudaErrorInvalidValue;
-    const size_t smem = ((size_t)CX * TR * (3 * H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
+    const size_t smem = Prox3Plan<T, H, E, CX, NT>::smem_bytes;
     dim3 grid(r.N0 / TR, r.M, r.nb / CX);
     const bool plain = !p.nonneg && p.bnd0 >= r.N0 && p.bnd1 >= 2 * H && !p.reg_on_y &&
                        p.wl1.spatial_uniform && (!p.prm.joint || p.wl21.spatial_uniform);
