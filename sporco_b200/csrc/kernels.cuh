@@ -321,6 +321,7 @@ struct ColArgs {
     int N0, M, Cd, Cs;     // Cs: channel count of Sf (C); b -> (k, c) = (b / Cx, b % Cx)
     int Cx, N1f, MC, nchunk, parts;
     int dfid_on, even_n1, check_on;
+    int ntiles;            // k_col2: number of (wf, b) slabs = N1f * nb
 };
 
 template <typename T, int MAXCD>

@@ -375,6 +375,45 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     const T joint1 = (CX == 1) ? mr * w21u : (T)0;
     const size_t wbase = (size_t)k * wl1.sk + (size_t)m * wl1.sm + (size_t)h * wl1.s0;
     const size_t w21base = (size_t)k * wl21.sk + (size_t)m * wl21.sm + (size_t)h * wl21.s0;
+    if constexpr (PLAIN && CX == 1) {
+        // The common configuration, on (re, im) pairs with packed arithmetic: threshold as
+        // v - clamp(v, -t, t); weights are uniform, so sum |w x| = |w| sum |x| (likewise l2,1).
+        const T thr = lr * w1u[0] + joint1;
+        C2<T> sx2 = mk<T>(0, 0), sy2 = sx2, su2 = sx2, sr2 = sx2, ss2 = sx2;
+        T sabs = 0;
+        const size_t tile = ((((size_t)k * M + m) * N0 + h) * H);
+        C2<T>* yg = reinterpret_cast<C2<T>*>(Y) + tile;
+        C2<T>* ug = reinterpret_cast<C2<T>*>(U) + tile;
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) {
+            const int j = t + TPF * p;
+            const C2<T> y2 = ybuf[yrow + j], u2 = ubuf[yrow + j];
+            const C2<T> xs = pmul(v[0][p], scale);
+            const C2<T> us = pmul(u2, uinv);
+            const C2<T> ax = relax ? pfma(xs, rlx, pmul(y2, rl1)) : xs;
+            const C2<T> vv = ax + us;
+            const C2<T> cl = mk<T>(fmin(fmax(vv.re, -thr), thr), fmin(fmax(vv.im, -thr), thr));
+            const C2<T> y = vv - cl;
+            const C2<T> u = us + (ax - y);
+            const C2<T> dr = xs - y, ds = y2 - y;
+            sx2 = pfma(xs, xs, sx2);
+            sy2 = pfma(y, y, sy2);
+            su2 = pfma(u, u, su2);
+            sr2 = pfma(dr, dr, sr2);
+            ss2 = pfma(ds, ds, ss2);
+            sabs += fabs(xs.re) + fabs(xs.im);
+            yg[j] = y;
+            ug[j] = u;
+            v[0][p] = y - u;                                   // next x-step input, if rho stays
+        }
+        sums[ACC_X2] = sx2.re + sx2.im;
+        sums[ACC_Y2] = sy2.re + sy2.im;
+        sums[ACC_U2] = su2.re + su2.im;
+        sums[ACC_R2] = sr2.re + sr2.im;
+        sums[ACC_S2] = ss2.re + ss2.im;
+        sums[ACC_L1] = fabs(w1u[0]) * sabs;
+        if (prm.joint) sums[ACC_L21] = w21u * sabs;
+    } else {
     SPCSC_UNROLL
     for (int p = 0; p < E; ++p) {
         const int j = t + TPF * p;
@@ -444,12 +483,24 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         }
         if (prm.joint) sums[ACC_L21] += w21[0] * sqrt(g2[0]) + w21[1] * sqrt(g2[1]);
     }
+    }
     if (prm.need_rsdl || prm.need_obj) {
-        double d[7];
-        SPCSC_UNROLL
-        for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
-        double* red = reinterpret_cast<double*>(smem_raw);
-        block_accumulate_det<7>(d, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
+#ifdef SPCSC_OLD_REDUCE
+        if constexpr (false) {
+#else
+        if constexpr (sizeof(T) == 4) {
+#endif
+            const float s8[8] = {(float)sums[0], (float)sums[1], (float)sums[2], (float)sums[3],
+                                 (float)sums[4], (float)sums[5], (float)sums[6], 0.f};
+            block_accumulate_det_f<7>(s8, reinterpret_cast<float*>(smem_raw),
+                                      reinterpret_cast<unsigned long long*>(acc + ACC_N));
+        } else {
+            double d[7];
+            SPCSC_UNROLL
+            for (int i = 0; i < 7; ++i) d[i] = (double)sums[i];
+            double* red = reinterpret_cast<double*>(smem_raw);
+            block_accumulate_det<7>(d, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
+        }
     }
     if (Znext) {
         // Cross-iteration fusion: the row spectra of Y - U for the next iteration, valid as long
@@ -489,7 +540,12 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
 //   m = (cr*G + g)*CPG + c,  g = group (TPF lanes) index, c < CPG, kept in registers.
 //   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (gradient)
 // ------------------------------------------------------------------------------------
-template <typename T, int N0, int E, int CPG, int NT, int CD, bool DO_FWD, int SOLVE, bool DO_INV>
+// BULK: persistent clusters (the grid is the number of clusters that fit on the GPU; each walks
+// over slabs with that stride) whose NEXT slab -- the CTA's NG*CPG columns are contiguous in
+// memory -- is fetched into shared memory by one bulk asynchronous copy (TMA) while the current
+// one is transformed, so the loads of a CTA are in flight during its whole lifetime.
+template <typename T, int N0, int E, int CPG, int NT, int CD, bool DO_FWD, int SOLVE, bool DO_INV,
+          bool BULK>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
 k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
@@ -505,31 +561,60 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     C2<T>* qbuf = sloc + CD * N0;                              // [CD][N0]
     C2<T>* stw_s = qbuf + CD * N0;                             // [TWLEN]
     double* red = reinterpret_cast<double*>(stw_s + TWLEN);    // [32]
+    mbar_t* bar = reinterpret_cast<mbar_t*>(red + 32);         // BULK: arrival of the prefetched slab
+    C2<T>* tbuf = reinterpret_cast<C2<T>*>(bar + 2);           // BULK: [NG*CPG][N0] prefetched columns
     const int tid = threadIdx.x;
     const unsigned cr = cluster_rank(), cs = cluster_size();
-    const int wf = blockIdx.x / cs, b = blockIdx.y;
     const int M = a.M;
     const int g = tid / TPF, t = tid % TPF;
     for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
-    const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
     const size_t dfc = (size_t)a.N1f * M * N0;                 // stride between dictionary channels
+    int mcol[CPG];
+    SPCSC_UNROLL
+    for (int c = 0; c < CPG; ++c) mcol[c] = ((int)cr * NG + g) * CPG + c;
+    // slabs of this cluster: tile, tile + tstep, ...   (BULK off: exactly one, from the grid)
+    const int tstep = BULK ? (int)(gridDim.x / cs) : a.ntiles;
+    int tile = BULK ? (int)(blockIdx.x / cs) : (int)(blockIdx.y * a.N1f + blockIdx.x / cs);
+    const int col0 = (int)cr * NG * CPG;                       // first column of this CTA
+    const int ncols = (M - col0 < NG * CPG) ? (M - col0) : NG * CPG;
+    const unsigned tbytes = ncols > 0 ? (unsigned)ncols * N0 * (unsigned)sizeof(C2<T>) : 0u;
+    unsigned parity = 0;
+    if (BULK && tid == 0) {
+        mbar_init(bar, 1);
+        if (tbytes && tile < a.ntiles) {
+            const int wf0 = tile % a.N1f, b0 = tile / a.N1f;
+            bulk_load(tbuf, in + (((size_t)b0 * a.N1f + wf0) * M + col0) * N0, tbytes, bar);
+        }
+    }
+    __syncthreads();                                         // stage twiddles / barrier are in place
+    for (; tile < a.ntiles; tile += tstep) {
+    const int wf = tile % a.N1f, b = tile / a.N1f;
+    const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
     const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
 
     C2<T> v[CPG][E];
-    int mcol[CPG];
-    SPCSC_UNROLL
-    for (int c = 0; c < CPG; ++c) {
-        mcol[c] = ((int)cr * NG + g) * CPG + c;
-        if (mcol[c] < M) {
-            const C2<T>* src = in + slab + (size_t)mcol[c] * N0;
+    if (BULK) {
+        if (tbytes) mbar_wait(bar, parity);
+        parity ^= 1u;
+        SPCSC_UNROLL
+        for (int c = 0; c < CPG; ++c) {
+            const C2<T>* src = tbuf + (size_t)(g * CPG + c) * N0;
             SPCSC_UNROLL
-            for (int p = 0; p < E; ++p) v[c][p] = src[t + TPF * p];
-        } else {
-            SPCSC_UNROLL
-            for (int p = 0; p < E; ++p) v[c][p] = mk<T>(0, 0);
+            for (int p = 0; p < E; ++p) v[c][p] = (mcol[c] < M) ? src[t + TPF * p] : mk<T>(0, 0);
+        }
+    } else {
+        SPCSC_UNROLL
+        for (int c = 0; c < CPG; ++c) {
+            if (mcol[c] < M) {
+                const C2<T>* src = in + slab + (size_t)mcol[c] * N0;
+                SPCSC_UNROLL
+                for (int p = 0; p < E; ++p) v[c][p] = src[t + TPF * p];
+            } else {
+                SPCSC_UNROLL
+                for (int p = 0; p < E; ++p) v[c][p] = mk<T>(0, 0);
+            }
         }
     }
-    __syncthreads();                                         // stage twiddles are in place
     if (DO_FWD) {
         SPCSC_UNROLL
         for (int c = 0; c < CPG; ++c) {
@@ -550,6 +635,13 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             xbuf[g * XP + h] = s;
         }
         __syncthreads();
+        // Every thread has by now USED what it read from the prefetch buffer (a barrier alone
+        // does not wait for shared-memory loads still in flight, and the bulk copy engine is
+        // not ordered behind them), so the buffer can be refilled with the cluster's next slab.
+        if (BULK && d == 0 && tid == 0 && tbytes && tile + tstep < a.ntiles) {
+            const int nt = tile + tstep, wf1 = nt % a.N1f, b1 = nt / a.N1f;
+            bulk_load(tbuf, in + (((size_t)b1 * a.N1f + wf1) * M + col0) * N0, tbytes, bar);
+        }
         for (int h = tid; h < N0; h += NT) {
             C2<T> s = mk<T>(0, 0);
             for (int gg = 0; gg < NG; ++gg) s = s + xbuf[gg * XP + h];
@@ -605,7 +697,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
         SPCSC_UNROLL
         for (int d = 0; d < CD; ++d) qbuf[d * N0 + h] = dv[d];
     }
-    cluster_arrive();                                        // done reading the peers' sums
+    cluster_arrive_relaxed();                                // done reading the peers' sums
     __syncthreads();
     if (SOLVE == 1 && a.dfid_on) block_accumulate<1>(dsum, red, acc + ACC_DFID);
     SPCSC_UNROLL
@@ -632,6 +724,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
         }
     }
     cluster_wait();                                          // peers are done with my shared memory
+    }
 }
 
 }  // namespace spcsc

@@ -59,6 +59,7 @@ struct ColLaunch {
     int nb;                      // slabs per frequency column (grid.y)
     ColArgs a;                   // MC / nchunk / parts filled by the launcher
     int gen;                     // any-size direct-DFT path (a.N0 holds the run-time length)
+    int bulk;                    // k_col2: persistent clusters with bulk-copy prefetch of the next slab
     cudaStream_t stream;
 };
 

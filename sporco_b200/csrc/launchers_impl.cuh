@@ -275,11 +275,24 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     const size_t smem = ((size_t)NG * fft_region(N0) + 2 * CD * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
                         32 * sizeof(double);
     dim3 grid(c.a.N1f * cs, c.nb);
-    if (mode == COL_ADMM)
-        return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, true, 1, true>, grid, dim3(NT), cs, smem,
-                              c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw,
-                              c.a);
-    return cudaErrorInvalidValue;
+    c.a.ntiles = c.a.N1f * c.nb;
+    if (mode != COL_ADMM) return cudaErrorInvalidValue;
+    if (c.bulk) {
+        // persistent clusters with the next slab prefetched by a bulk copy; in place is fine (a
+        // slab is in registers before the prefetch of the next one is issued, and stored after)
+        auto kern = k_col2<T, N0, E, CPG, NT, CD, true, 1, true, true>;
+        const size_t smem_b = smem + 2 * sizeof(mbar_t) + (size_t)per_cta * N0 * sizeof(C2<T>);
+        static int resident[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
+        if (cs < 8 && resident[cs] == 0) resident[cs] = max_active_clusters(kern, dim3(NT), cs, smem_b);
+        const int ncl = cs < 8 ? resident[cs] : 0;
+        if (ncl > 0) {
+            const int use = ncl < c.a.ntiles ? ncl : c.a.ntiles;
+            return launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem_b, c.stream, c.in, c.out,
+                                  c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a);
+        }
+    }
+    return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, true, 1, true, false>, grid, dim3(NT), cs, smem,
+                          c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a);
 }
 
 template <typename T, int N0>

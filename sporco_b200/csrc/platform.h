@@ -88,15 +88,47 @@ inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block,
 #endif
 }
 
+// number of clusters of `cs` CTAs that can be resident at once (persistent grids)
+template <typename... KArgs>
+inline int max_active_clusters(void (*kern)(KArgs...), dim3 block, unsigned cs, size_t smem) {
+#ifdef SPCSC_EMU
+    (void)kern; (void)block; (void)cs; (void)smem;
+    return 3;
+#else
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cs, 1, 1);
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+#endif
+}
+
 #ifdef SPCSC_EMU
 inline unsigned cluster_rank() { return emu::cluster_rank(); }
 inline unsigned cluster_size() { return emu::cluster_size(); }
 inline void cluster_arrive() { emu::cluster_arrive(); }
+inline void cluster_arrive_relaxed() { emu::cluster_arrive(); }
 inline void cluster_wait() { emu::cluster_wait(); }
 template <typename P> inline P* cluster_peer(P* p, unsigned rank) {
     return reinterpret_cast<P*>(emu::map_shared_rank((void*)p, rank));
 }
 #else
+// arrival that publishes nothing (the caller has only finished READING its peers' memory): no
+// release fence, which otherwise costs a GPU-scope MEMBAR + ERRBAR per arrival
+SPCSC_DEV void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 SPCSC_DEV unsigned cluster_rank() { return cooperative_groups::this_cluster().block_rank(); }
 SPCSC_DEV unsigned cluster_size() { return cooperative_groups::this_cluster().num_blocks(); }
 SPCSC_DEV void cluster_arrive() { cooperative_groups::this_cluster().barrier_arrive(); }
@@ -117,6 +149,39 @@ template <int BYTES> SPCSC_DEV void cp_async(void* dst, const void* src) {
 }
 SPCSC_DEV void cp_async_commit() { __pipeline_commit(); }
 template <int N> SPCSC_DEV void cp_async_wait() { __pipeline_wait_prior(N); }
+#endif
+
+// ---- bulk asynchronous copy global -> shared (TMA, 1-D) completing on an mbarrier ------------
+typedef unsigned long long mbar_t;
+#ifdef SPCSC_EMU
+inline void mbar_init(mbar_t*, unsigned) {}
+inline void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(mbar_t*, unsigned) {}
+#else
+SPCSC_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SPCSC_DEV void mbar_init(mbar_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: announce `bytes` on the barrier and start the copy (16-byte aligned, multiple of 16)
+SPCSC_DEV void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+SPCSC_DEV void mbar_wait(mbar_t* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
 #endif
 
 // ---- complex value type with natural vector alignment (8 B for float, 16 B for double)
@@ -160,6 +225,61 @@ template <typename T> SPCSC_HD C2<T> conj(C2<T> a) { return mk<T>(a.re, -a.im); 
 template <typename T> SPCSC_HD C2<T> mulc(C2<T> a, C2<T> b) {
     return mk<T>(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im);
 }
+// elementwise helpers on (re, im) used as a pair of reals: a*s, a*s + c, a*b + c (lane by lane)
+template <typename T> SPCSC_HD C2<T> pmul(C2<T> a, T s) { return mk<T>(a.re * s, a.im * s); }
+template <typename T> SPCSC_HD C2<T> pfma(C2<T> a, T s, C2<T> c) { return mk<T>(a.re * s + c.re, a.im * s + c.im); }
+template <typename T> SPCSC_HD C2<T> pfma(C2<T> a, C2<T> b, C2<T> c) {
+    return mk<T>(a.re * b.re + c.re, a.im * b.im + c.im);
+}
+#if !defined(SPCSC_EMU) && !defined(SPCSC_NO_F32X2)
+// Packed forms: FMUL2 takes a scalar broadcast operand and FFMA2 a lane-swapped, per-lane negated
+// one, so a complex product is two instructions (re = fma(-a.im, b.im, a.re*b.re), im =
+// fma(a.re, b.im, a.im*b.re)) instead of four.
+template <> SPCSC_HD C2<float> operator*<float>(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+    const float2 t = __fmul2_rn(as_f2(a), make_float2(b.re, b.re));
+    return as_c2(__ffma2_rn(make_float2(a.im, a.re), make_float2(-b.im, b.im), t));
+#else
+    return mk<float>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+#endif
+}
+template <> SPCSC_HD C2<float> operator*<float>(float s, C2<float> a) {
+#ifdef __CUDA_ARCH__
+    return as_c2(__fmul2_rn(as_f2(a), make_float2(s, s)));
+#else
+    return mk<float>(s * a.re, s * a.im);
+#endif
+}
+template <> SPCSC_HD C2<float> mulc<float>(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+    const float2 t = __fmul2_rn(as_f2(a), make_float2(b.re, b.re));
+    return as_c2(__ffma2_rn(make_float2(a.im, a.re), make_float2(b.im, -b.im), t));
+#else
+    return mk<float>(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im);
+#endif
+}
+template <> SPCSC_HD C2<float> pmul<float>(C2<float> a, float s) {
+#ifdef __CUDA_ARCH__
+    return as_c2(__fmul2_rn(as_f2(a), make_float2(s, s)));
+#else
+    return mk<float>(a.re * s, a.im * s);
+#endif
+}
+template <> SPCSC_HD C2<float> pfma<float>(C2<float> a, float s, C2<float> c) {
+#ifdef __CUDA_ARCH__
+    return as_c2(__ffma2_rn(as_f2(a), make_float2(s, s), as_f2(c)));
+#else
+    return mk<float>(a.re * s + c.re, a.im * s + c.im);
+#endif
+}
+template <> SPCSC_HD C2<float> pfma<float>(C2<float> a, C2<float> b, C2<float> c) {
+#ifdef __CUDA_ARCH__
+    return as_c2(__ffma2_rn(as_f2(a), as_f2(b), as_f2(c)));
+#else
+    return mk<float>(a.re * b.re + c.re, a.im * b.im + c.im);
+#endif
+}
+#endif
 // multiply by +i / -i
 template <typename T> SPCSC_HD C2<T> mul_i(C2<T> a) { return mk<T>(-a.im, a.re); }
 template <typename T> SPCSC_HD C2<T> mul_mi(C2<T> a) { return mk<T>(a.im, -a.re); }
@@ -268,6 +388,48 @@ SPCSC_DEV void block_accumulate_det(const double (&v)[NV], double* red, unsigned
             if (lane == i) mine = x;
         }
         if (lane < NV) det_accumulate(mine, bins + lane * kDetBins);
+    }
+}
+
+// Eight float values per lane summed over the warp with 9 shuffles (halving exchange: after the
+// steps with offsets 16, 8, 4 every lane carries one value, then two plain butterfly steps):
+// lane 4q ends up with the warp total of value q.  Fixed order, hence reproducible.
+SPCSC_DEV float warp_sum8(const float (&s)[8]) {
+    const int lane = threadIdx.x & 31;
+    float a[4], b[2];
+    const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+    SPCSC_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const float send = u16 ? s[i] : s[i + 4], keep = u16 ? s[i + 4] : s[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    SPCSC_UNROLL
+    for (int i = 0; i < 2; ++i) {
+        const float send = u8 ? a[i] : a[i + 2], keep = u8 ? a[i + 2] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float c = (u4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, u4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+
+// Block totals of up to eight float values per thread into the reproducible bins: warp totals by
+// warp_sum8, then lane i of warp 0 adds the per-warp partials of value i in warp order.
+// `red`: block-shared scratch of 8*32 floats.
+template <int NV>
+SPCSC_DEV void block_accumulate_det_f(const float (&v)[8], float* red, unsigned long long* bins) {
+    static_assert(NV <= 8, "at most eight values");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
+    const float c = warp_sum8(v);
+    __syncthreads();                       // scratch may alias buffers used earlier
+    if ((lane & 3) == 0) red[(lane >> 2) * 32 + warp] = c;
+    __syncthreads();
+    if (warp == 0 && lane < NV) {
+        double mine = 0.0;
+        for (int w = 0; w < nwarp; ++w) mine += (double)red[lane * 32 + w];
+        det_accumulate(mine, bins + lane * kDetBins);
     }
 }
 

@@ -498,6 +498,9 @@ class Engine : public spcsc_handle {
         c.stream = stream;
         c.Lstep = 1;
         c.gen = gen_cols ? 1 : 0;
+        // persistent clusters + bulk-copy prefetch: measured no faster than one slab per cluster
+        // (the kernel is issue-bound, not load-bound), so it stays opt-in
+        c.bulk = (getenv("SPCSC_COLBULK") && atoi(getenv("SPCSC_COLBULK")) == 1) ? 1 : 0;
         return c;
     }
 
