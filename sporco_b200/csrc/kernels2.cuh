@@ -608,7 +608,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             if (mcol[c] < M) {
                 const C2<T>* src = in + slab + (size_t)mcol[c] * N0;
                 SPCSC_UNROLL
-                for (int p = 0; p < E; ++p) v[c][p] = src[t + TPF * p];
+                for (int p = 0; p < E; ++p) v[c][p] = ld_stream(src + t + TPF * p);
             } else {
                 SPCSC_UNROLL
                 for (int p = 0; p < E; ++p) v[c][p] = mk<T>(0, 0);

@@ -285,6 +285,21 @@ template <typename T> SPCSC_HD C2<T> mul_i(C2<T> a) { return mk<T>(-a.im, a.re);
 template <typename T> SPCSC_HD C2<T> mul_mi(C2<T> a) { return mk<T>(a.im, -a.re); }
 template <typename T> SPCSC_HD T abs2(C2<T> a) { return a.re * a.re + a.im * a.im; }
 
+// Streaming (read-once) global load: evict-first in L1 so that re-used operands (dictionary
+// spectra) keep their lines.
+#ifdef SPCSC_EMU
+template <typename T> inline C2<T> ld_stream(const C2<T>* p) { return *p; }
+#else
+SPCSC_DEV C2<float> ld_stream(const C2<float>* p) {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    C2<float> r; r.re = v.x; r.im = v.y; return r;
+}
+SPCSC_DEV C2<double> ld_stream(const C2<double>* p) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    C2<double> r; r.re = v.x; r.im = v.y; return r;
+}
+#endif
+
 // ---- warp / block reductions (double accumulators) -------------------------------------
 SPCSC_DEV double warp_sum(double v) {
     SPCSC_UNROLL
