@@ -177,8 +177,11 @@ enum { SPCSC_COEF_ADMM_Y = 0, SPCSC_COEF_PGM_X = 1 };
 int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source);
 /* ... or from a host array Z (N0,N1,1,K,M).                                pgm/ccmod.py:264-281 */
 int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z);
-/* One PGM iteration with step 1/L and momentum coefficient coef = (t_prev - 1)/t  (pgm/pgm.py:779-831). */
-int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, double out[4]);
+/* One PGM iteration with step 1/L and momentum coefficient coef = (t_prev - 1)/t  (pgm/pgm.py:779-831).
+   flags select the statistics that cost a pass of their own (the reference computes both unless
+   FastSolve is set, pgm/pgm.py:347-356): out[0] needs SPCSC_CCMOD_DFID, out[1] SPCSC_CCMOD_CNSTR. */
+enum { SPCSC_CCMOD_DFID = 1, SPCSC_CCMOD_CNSTR = 2 };
+int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]);
 /* getdict(crop=True): (hd, wd, Cd, M).                                     pgm/ccmod.py:283-291 */
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out);
 /* xstep.setdict(dstep.getdict()) on the device (dictlrn.py:386-389): Df <- Xf. */

@@ -106,7 +106,7 @@ def _declare(lib):
     lib.spcsc_ccmod_reset.argtypes = [vp, vp, i32]
     lib.spcsc_ccmod_setcoef_device.argtypes = [vp, i32]
     lib.spcsc_ccmod_setcoef.argtypes = [vp, vp]
-    lib.spcsc_ccmod_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    lib.spcsc_ccmod_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, i32, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_ccmod_get_dict.argtypes = [vp, vp]
     lib.spcsc_ccmod_push_dict.argtypes = [vp]
     lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
@@ -345,9 +345,9 @@ class Handle(object):
         Z = self._host(Z, self.xshape())
         self._c(self.lib.spcsc_ccmod_setcoef(self.h, _ptr(Z)))
 
-    def ccmod_step(self, L, coef):
+    def ccmod_step(self, L, coef, flags=3):
         out = (ctypes.c_double * 4)()
-        self._c(self.lib.spcsc_ccmod_step(self.h, float(L), float(coef), out))
+        self._c(self.lib.spcsc_ccmod_step(self.h, float(L), float(coef), int(flags), out))
         return [out[i] for i in range(4)]
 
     def ccmod_get_dict(self):

@@ -622,6 +622,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             __syncwarp();
         }
     }
+    if constexpr (SOLVE != 0) {
     // s_d[h] = sum over this CTA's columns of Df_d[m][h] * col[m][h], one dictionary channel at a time
     SPCSC_UNROLL
     for (int d = 0; d < CD; ++d) {
@@ -700,6 +701,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     cluster_arrive_relaxed();                                // done reading the peers' sums
     __syncthreads();
     if (SOLVE == 1 && a.dfid_on) block_accumulate<1>(dsum, red, acc + ACC_DFID);
+    }
     SPCSC_UNROLL
     for (int c = 0; c < CPG; ++c) {
         if (mcol[c] < M) {
@@ -707,9 +709,11 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             for (int p = 0; p < E; ++p) {
                 const int h = t + TPF * p;
                 C2<T> x = v[c][p];
-                SPCSC_UNROLL
-                for (int d = 0; d < CD; ++d)
-                    x = x + mulc(qbuf[d * N0 + h], dfw[d * dfc + (size_t)mcol[c] * N0 + h]);
+                if constexpr (SOLVE != 0) {
+                    SPCSC_UNROLL
+                    for (int d = 0; d < CD; ++d)
+                        x = x + mulc(qbuf[d * N0 + h], dfw[d * dfc + (size_t)mcol[c] * N0 + h]);
+                }
                 v[c][p] = x;
             }
         }
@@ -723,7 +727,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[c][p];
         }
     }
-    cluster_wait();                                          // peers are done with my shared memory
+    if constexpr (SOLVE != 0) cluster_wait();                // peers are done with my shared memory
     }
 }
 

@@ -91,8 +91,8 @@ SPCSC_GLOBAL void k_ccmod_step(const C2<T>* SPCSC_RESTRICT Yf, const C2<T>* SPCS
 // Constraint-set projection of one filter per CTA (sporco/cnvrep.py:953-1033):
 //   crop to the hd x wd support (all Cd channels), optional zero mean over the support of each
 //   channel, normalise to unit l2 norm (a zero filter stays zero), zero elsewhere.
-// V, X: real [Cd][M][N0][N1].  With `check` the squared distance ||Pcn(V) - V||^2 is accumulated
-// instead of writing X.
+// V, X: real [Cd][M][N0][N1].  With `check` the squared distance ||Pcn(V) - V||^2 (over the
+// support) is accumulated instead of writing X.
 template <typename T>
 SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* SPCSC_RESTRICT acc,
                         int Cd, int M, int N0, int N1, int hd, int wd, int zero_mean, int check) {
@@ -130,19 +130,22 @@ SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* 
     }
     T vn = (T)sqrt(nrm2);
     if (vn == (T)0) vn = (T)1;
+    // Outside the support X is zero and stays zero (the buffer is cleared once, at reset), so only
+    // the support is written -- or, with `check`, compared: Pcn(V) - V vanishes elsewhere when V
+    // is itself a projected iterate, which is the only way the reference evaluates it.
     double d2[1] = {0.0};
     for (int c = 0; c < Cd; ++c) {
         const T mean = zero_mean ? (T)bc[2 + c] : (T)0;
         const T* v = V + ((size_t)c * M + m) * N0 * N1;
         T* x = X ? X + ((size_t)c * M + m) * N0 * N1 : nullptr;
-        for (int e = tid; e < N0 * N1; e += nt) {
-            const int r = e / N1, q = e - r * N1;
-            const T p = (r < hd && q < wd) ? (v[e] - mean) / vn : (T)0;
+        for (int e = tid; e < ns; e += nt) {
+            const size_t o = (size_t)(e / wd) * N1 + (e % wd);
+            const T p = (v[o] - mean) / vn;
             if (check) {
-                const double d = (double)(p - v[e]);
+                const double d = (double)(p - v[o]);
                 d2[0] += d * d;
             } else {
-                x[e] = p;
+                x[o] = p;
             }
         }
     }

@@ -276,6 +276,13 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
                         32 * sizeof(double);
     dim3 grid(c.a.N1f * cs, c.nb);
     c.a.ntiles = c.a.N1f * c.nb;
+    if (mode == COL_FWD) {
+        if constexpr (CD == 1)          // forward columns only (set-up transforms, coefficient spectra)
+            return launch_cluster(k_col2<T, N0, E, CPG, NT, 1, true, 0, false, false>, grid, dim3(NT), cs,
+                                  smem, c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw,
+                                  c.a);
+        return cudaErrorInvalidValue;
+    }
     if (mode != COL_ADMM) return cudaErrorInvalidValue;
     if (c.bulk) {
         // persistent clusters with the next slab prefetched by a bulk copy; in place is fine (a

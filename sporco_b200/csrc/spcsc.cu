@@ -298,7 +298,7 @@ struct spcsc_handle {
     virtual int ccmod_reset(const void* D0, int zero_mean) = 0;
     virtual int ccmod_setcoef_device(int source) = 0;
     virtual int ccmod_setcoef(const void* Z) = 0;
-    virtual int ccmod_step(double L, double coef, double* out) = 0;
+    virtual int ccmod_step(double L, double coef, int flags, double* out) = 0;
     virtual int ccmod_get_dict(void* out) = 0;
     virtual int ccmod_push_dict() = 0;
 };
@@ -506,11 +506,17 @@ class Engine : public spcsc_handle {
 
     // rfft2 of a real array in device order [nb][m][N0][N1] into slab order [nb][N1f][m][N0]
     int forward2d(const T* real_in, C2<T>* out, int m, int nb) {
-        CK(row_fwd<T>(H, rowargs(m, nb, 1), real_in, (const T*)nullptr,
-                      (const AdmmState<T>*)nullptr, out));
         ColLaunch<T> c = colargs(m, nb);
         c.in = out; c.out = out;
         c.a.Cd = 1;
+        if (v2_rowf && v2_col && col2_ok<T>(N0, m, 1)) {        // register-plan kernels
+            CK(row_fwd2<T>(H, rowargs(m, nb, 1), real_in, (const T*)nullptr,
+                           (const AdmmState<T>*)nullptr, out, (const C2<T>*)stw_row1.p, 0));
+            CK(col2<T>(N0, COL_FWD, c, (const C2<T>*)stw_col.p));
+            return SPCSC_OK;
+        }
+        CK(row_fwd<T>(H, rowargs(m, nb, 1), real_in, (const T*)nullptr,
+                      (const AdmmState<T>*)nullptr, out));
         CK(col<T>(N0, COL_FWD, c));
         return SPCSC_OK;
     }
@@ -1058,7 +1064,7 @@ class Engine : public spcsc_handle {
         return launch(k_ccmod_grad<T, 16, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p,
                       yf, (const C2<T>*)Sf.p, g, acc.p, K, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0);
     }
-    int ccmod_step(double L, double coef, double* out) override {
+    int ccmod_step(double L, double coef, int flags, double* out) override {
         int rc = ccmod_check();
         if (rc) return rc;
         if (!cd_ready || !cd_have_coef) FAIL(SPCSC_ERR_STATE, "ccmod_step before ccmod_reset / setcoef");
@@ -1098,13 +1104,14 @@ class Engine : public spcsc_handle {
         std::swap(cdXf.n, cdV.n);
         // objective terms of the new iterate: data fidelity (second pass over Zf), constraint violation
         CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 2 * sizeof(double), stream));
-        CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
-        if (nccl_comm) {
+        if (flags & SPCSC_CCMOD_DFID) CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
+        if (nccl_comm && (flags & SPCSC_CCMOD_DFID)) {
             int nr = nccl->AllReduce(acc.p + ACC_CDL_DFID, acc.p + ACC_CDL_DFID, 1, 8, 0, nccl_comm, stream);
             if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
         }
-        CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
-                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
+        if (flags & SPCSC_CCMOD_CNSTR)
+            CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
+                      N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
         double ha[4];
         CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1381,7 +1388,7 @@ int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef))
 int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ? h->ccmod_reset(D0, zm) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source) { H_CALL(h->ccmod_setcoef_device(source)); }
 int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z) { H_CALL(Z ? h->ccmod_setcoef(Z) : SPCSC_ERR_INVALID); }
-int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, double out[4]) { H_CALL(out ? h->ccmod_step(L, coef, out) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]) { H_CALL(out ? h->ccmod_step(L, coef, flags, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {

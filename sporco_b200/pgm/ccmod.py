@@ -111,7 +111,10 @@ class ConvCnstrMOD(pgm.PGMDFT):
     def ystep(self):
         tprv = self.t
         self.t = self.momentum.update(self.var_momentum())
-        self._stats = self._h.ccmod_step(float(self.L), (tprv - 1.) / self.t)
+        # FastSolve: no iteration record is built (pgm/pgm.py:347), so the two statistics that
+        # need a pass of their own are skipped
+        self._stats = self._h.ccmod_step(float(self.L), (tprv - 1.) / self.t,
+                                         0 if self.opt['FastSolve'] else 3)
         self._cache.clear()
 
     def rsdl(self):

@@ -161,6 +161,12 @@ def test_bit_reproducible_runs():
     cases.run_reproducibility_case()
 
 
+@pytest.mark.parametrize('bulk', ['0', '1'])
+def test_long_run_is_deterministic_and_settles(monkeypatch, bulk):
+    monkeypatch.setenv('SPCSC_COLBULK', bulk)        # both column-kernel schedules
+    cases.run_long_determinism_case()
+
+
 @pytest.mark.parametrize('shape', [(16, 17), (63, 63), (48, 40)])
 def test_any_image_size(shape):
     """Non power-of-two sizes (direct-DFT path): the reference's own test sizes."""
