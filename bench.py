@@ -238,12 +238,12 @@ def run_b200(args):
         kern[names[i]] = {'ms': kms[i], 'algorithmic_GB': alg_bytes[names[i]] / 1e9,
                           'GBps': gbs, 'frac': gbs / peak}
     kern['k_admm_scalars'] = {'ms': kms[3]}
-    traffic = {'k_row_inv_prox': 3.172e9, 'k_col': 1.101e9}.get(names[dom]) if sched['fused'] else None
+    traffic = {'k_row_inv_prox': 3.173e9, 'k_col': 1.076e9}.get(names[dom]) if sched['fused'] else None
     roof = {'bound': 'hbm', 'kernel': names[dom] + (' (fused with the next row-forward)' if sched['fused'] and dom == 2 else ''),
             'achieved': kern[names[dom]]['GBps'],
             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
             'frac': kern[names[dom]]['frac'], 'traffic': traffic,
-            'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_v3_ncu_summary.md',
+            'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_v6_ncu_summary.md',
             'schedule': sched,
             'iteration_algorithmic_GB': sum(alg_bytes.values()) / 1e9,
             'iteration_frac': sum(alg_bytes.values()) / 1e9 / (sum(kms) / 1000.0) / peak,
