@@ -68,6 +68,9 @@ typedef struct spcsc_admm_opts {
     int32_t fast_solve;    /* FastSolve: skip objective       admm/admm.py:356 */
     int32_t aux_var_obj;   /* AuxVarObj: objective on Y       admm/cbpdn.py:151-164 */
     int32_t linsolve_check;/* LinSolveCheck                   admm/cbpdn.py:283-293 */
+    double l2_weight;      /* ConvElasticNet mu: (mu/2)||x||^2, x-step diagonal mu + rho; 0 = plain
+                              ConvBPDN.  With it the regl21 column of the rows carries RegL2.
+                              admm/cbpdn.py:948-986 */
 } spcsc_admm_opts;
 
 /* One row of IterationStats (admm/admm.py:182-189, admm/cbpdn.py:512-514, 737-740). */

@@ -232,8 +232,10 @@ class ADMMResult(object):
 
 
 def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
-                  norm_reduce=None, record=False, timing=None):
-    """Run the ConvBPDN (mu is None) or ConvBPDNJoint (mu given) ADMM loop.
+                  norm_reduce=None, record=False, timing=None, enet_mu=None):
+    """Run the ConvBPDN (mu is None) or ConvBPDNJoint (mu given) ADMM loop; with `enet_mu` the
+    ConvElasticNet variant (admm/cbpdn.py:810-990: x-step with mu + rho on the diagonal, extra
+    (mu/2)||x||^2 term; rows then carry RegL2 where the joint solver has RegL21).
 
     `norm_reduce`, if given, maps a float64 vector of local sums to global sums; it is
     how the K-sharded multi-rank form of the algorithm is expressed (every rank then
@@ -281,6 +283,10 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
     if joint:
         mu_ = dtype.type(mu)
         wl21 = np.asarray(o['L21Weight'], dtype=dtype)
+    enet = enet_mu is not None
+    if enet:
+        assert not joint
+        emu = dtype.type(enet_mu)
 
     if o['U0'] is not None:
         U = o['U0'].astype(dtype, copy=True)
@@ -313,17 +319,18 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         # ---- xstep (admm/cbpdn.py:267-293)
         YU = Y - U
         b = DSf + rho * fft.rfftn(YU, None, axN)
+        rho_x = (emu + rho) if enet else rho           # admm/cbpdn.py:948-955
         if dims.Cd == 1:
-            Xf = solvedbi_sm(Df, rho, b, axM)
+            Xf = solvedbi_sm(Df, rho_x, b, axM)
         else:
-            Xf = solvemdbi_ism(Df, rho, b, axM, axC)
+            Xf = solvemdbi_ism(Df, rho_x, b, axM, axC)
         X = fft.irfftn(Xf, dims.Nv, axN)
         if o['LinSolveCheck']:
             dx = inner(Df, Xf, axM)
             if dims.Cd == 1:
-                ax = np.conj(Df) * dx + rho * Xf
+                ax = np.conj(Df) * dx + rho_x * Xf
             else:
-                ax = inner(np.conj(Df), dx, axC) + rho * Xf
+                ax = inner(np.conj(Df), dx, axC) + rho_x * Xf
             xrrs = rrs(ax, b)
         # ---- relaxation (admm/admm.py:877-885)
         if rlx == 1.0:
@@ -390,6 +397,13 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
                     rl21 = norm_reduce(np.array([rl21], dtype=np.float64))[0]
                 obj = dfd + (lmbda * rl1 + mu_ * rl21)
                 row = (k, obj, dfd, rl1, rl21, r, s, epri, edua, rho, xrrs,
+                       time.perf_counter() - t_start)
+            elif enet:                                  # admm/cbpdn.py:978-986
+                rl2 = 0.5 * np.linalg.norm(gvar) ** 2
+                if norm_reduce is not None:
+                    rl2 = norm_reduce(np.array([rl2], dtype=np.float64))[0]
+                obj = dfd + (lmbda * rl1 + emu * rl2)
+                row = (k, obj, dfd, rl1, rl2, r, s, epri, edua, rho, xrrs,
                        time.perf_counter() - t_start)
             else:
                 obj = dfd + lmbda * rl1

@@ -43,19 +43,21 @@ def stat(its, name):
     return np.asarray(getattr(its, name), dtype=np.float64)
 
 
-def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None):
-    if mu is None:
+def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None, enet_mu=None):
+    if enet_mu is not None:
+        b = rcbpdn.ConvElasticNet(D, S, lmbda, enet_mu, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    elif mu is None:
         b = rcbpdn.ConvBPDN(D, S, lmbda, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
     else:
         b = rcbpdn.ConvBPDNJoint(D, S, lmbda, mu, rcbpdn.ConvBPDNJoint.Options(opt), dimK=dimK)
     b.solve()
-    r = orc.admm_convbpdn(D, S, lmbda, mu=mu, opt=opt, dimK=dimK)
+    r = orc.admm_convbpdn(D, S, lmbda, mu=mu, opt=opt, dimK=dimK, enet_mu=enet_mu)
     same(b.Y, r.Y, tag + ' Y')
     same(b.U, r.U, tag + ' U')
     same(b.X, r.X, tag + ' X')
     its = b.getitstat()
     col = {'ObjFun': 1, 'DFid': 2, 'RegL1': 3}
-    off = 1 if mu is not None else 0
+    off = 1 if (mu is not None or enet_mu is not None) else 0
     col.update({'PrimalRsdl': 4 + off, 'DualRsdl': 5 + off, 'Rho': 8 + off})
     for name, c in col.items():
         same(stat(its, name), np.array([row[c] for row in r.itstat], dtype=np.float64),
@@ -68,6 +70,10 @@ def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None):
     if mu is not None:
         out['mu'] = np.float64(mu)
         out['RegL21'] = stat(its, 'RegL21')
+    if enet_mu is not None:
+        out['mu'] = np.float64(enet_mu)
+        out['RegL2'] = stat(its, 'RegL2')
+        same(out['RegL2'], np.array([row[4] for row in r.itstat], dtype=np.float64), tag + ' RegL2')
     np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
     print('wrote', tag, 'Y nnz', int(np.count_nonzero(b.Y)), 'final rho', float(b.rho))
 
@@ -176,6 +182,10 @@ def main():
                   {'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True})
         admm_case('joint_c3_' + sfx, dt, D, S3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0}, mu=0.05)
         admm_case('admm_stop_' + sfx, dt, D, S, 0.2, {'MaxMainIter': 200, 'RelStopTol': 5e-3}, dimK=1)
+        admm_case('enet_k3_' + sfx, dt, D, S, 0.1, {'MaxMainIter': 30, 'RelStopTol': 0.0}, dimK=1,
+                  enet_mu=0.3)
+        admm_case('enet_c3_' + sfx, dt, D3, S3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0,
+                                                      'AuxVarObj': True}, enet_mu=0.5)
         pgm_case('pgm_bt_' + sfx, dt, D, S, 0.1,
                  {'MaxMainIter': 25, 'RelStopTol': 0.0, 'L': 10.0,
                   'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)},

@@ -51,7 +51,8 @@ class AdmmOpts(ctypes.Structure):
                  'ar_rsdl_target')] + \
                [(n, ctypes.c_int32) for n in
                 ('ar_enabled', 'ar_period', 'ar_autoscaling', 'ar_std_residuals', 'joint',
-                 'nonneg', 'no_bndry_cross', 'fast_solve', 'aux_var_obj', 'linsolve_check')]
+                 'nonneg', 'no_bndry_cross', 'fast_solve', 'aux_var_obj', 'linsolve_check')] + \
+               [('l2_weight', ctypes.c_double)]
 
 
 class PgmOpts(ctypes.Structure):

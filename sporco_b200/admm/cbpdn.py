@@ -51,6 +51,7 @@ class GenericConvBPDN(admm.ADMMEqual):
     hdrval_objfun = {'Fnc': 'ObjFun', 'DFid': 'DFid', 'Reg': 'Reg'}
 
     _joint = False
+    _two_reg = False          # a second regularisation column in the rows (RegL2 of ConvElasticNet)
 
     def __init__(self, D, S, opt=None, dimK=None, dimN=2, device=0):
         if dimN != 2:
@@ -179,7 +180,8 @@ class GenericConvBPDN(admm.ADMMEqual):
             ar_std_residuals=int(bool(ar['StdResiduals'])), joint=int(self._joint),
             nonneg=int(bool(o['NonNegCoef'])), no_bndry_cross=int(bool(o['NoBndryCross'])),
             fast_solve=int(bool(o['FastSolve'])), aux_var_obj=int(bool(o['gEvalY'])),
-            linsolve_check=int(bool(o['LinSolveCheck'])))
+            linsolve_check=int(bool(o['LinSolveCheck'])),
+            l2_weight=float(getattr(self, '_l2_weight', 0.0)))
 
     def _device_iterate(self, n, want_rows):
         if bool(self.opt['gEvalY']) != (not bool(self.opt['fEvalX'])):
@@ -200,7 +202,7 @@ class GenericConvBPDN(admm.ADMMEqual):
     def _make_itstat(self, row, t):
         rdt = common.real_dtype(self.dtype).type
         xr = None if row.xslv_relres < 0 else row.xslv_relres
-        reg = (row.regl1, row.regl21) if self._joint else (row.regl1,)
+        reg = (row.regl1, row.regl21) if (self._joint or self._two_reg) else (row.regl1,)
         tpl = (int(row.iter), row.objfun, row.dfid) + reg + \
             (rdt(row.primal_rsdl), rdt(row.dual_rsdl), row.eps_primal, row.eps_dual,
              rdt(row.rho), xr, t)
@@ -355,3 +357,26 @@ class ConvBPDNJoint(ConvBPDN):
         if w.ndim != 2 or w.shape[0] not in (1, K) or w.shape[1] not in (1, M):
             raise NotImplementedError('L21Weight must broadcast over (K, M) only')
         self._h.set_l21_weight(np.ascontiguousarray(w))
+
+
+class ConvElasticNet(ConvBPDN):
+    """ADMM solver for the convolutional elastic net (mirror of sporco/admm/cbpdn.py:810-990)::
+
+        argmin_x (1/2) || sum_m d_m * x_m - s ||_2^2 + lambda sum_m || x_m ||_1
+                 + (mu/2) sum_m || x_m ||_2^2
+
+    Same iteration as :class:`ConvBPDN` with ``mu + rho`` on the diagonal of the x-step system
+    (admm/cbpdn.py:948-955) and the extra term in the objective; ``IterationStats`` gains ``RegL2``.
+    """
+
+    itstat_fields_objfn = ('ObjFun', 'DFid', 'RegL1', 'RegL2')
+    hdrtxt_objfn = ('Fnc', 'DFid', u'Regℓ1', u'Regℓ2')
+    hdrval_objfun = {'Fnc': 'ObjFun', 'DFid': 'DFid', u'Regℓ1': 'RegL1', u'Regℓ2': 'RegL2'}
+    _two_reg = True
+
+    def __init__(self, D, S, lmbda=None, mu=0.0, opt=None, dimK=None, dimN=2, device=0):
+        opt = self._coerce_options(opt)
+        self.set_dtype(opt, S.dtype)
+        self.mu = self.dtype.type(mu)
+        self._l2_weight = float(self.mu)
+        super(ConvElasticNet, self).__init__(D, S, lmbda, opt, dimK=dimK, dimN=dimN, device=device)

@@ -51,7 +51,8 @@ struct AdmmParams {
     int autorho, period, autoscaling, stdres;
     int need_rsdl, need_obj, joint, linsolve_check;
     int dfid_direct;                     // 1: ACC_DFID already holds the weighted |sum_m Df Yf - Sf|^2 (AuxVarObj)
-    int pad_;
+    int enet;                            // 1: ConvElasticNet: rows carry RegL2 = ||x||^2 / 2 in the regl21 column
+    T enet_mu;                           // its l2 weight: the x-step diagonal is enet_mu + rho
 };
 
 struct StatRow {
@@ -404,7 +405,11 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
     const C2<T>* src = in + slab;
     C2<T>* dst = out ? out + slab : nullptr;
     const bool resident = (a.nchunk == 1);
-    const T rho = (SOLVE == 1) ? st->rho : (T)0;
+    // SOLVE 1 with an l2 term (ConvElasticNet, admm/cbpdn.py:948-955; its weight arrives in Lstep):
+    // (D^H D + rho_x I) x = D^H s + rho z, rho_x = mu + rho, is the plain system for z' = (rho/rho_x) z
+    const T rho0 = (SOLVE == 1) ? st->rho : (T)0;
+    const T rho = (SOLVE == 1) ? rho0 + Lstep : (T)0;
+    const T zeta = (SOLVE == 1 && Lstep != (T)0) ? rho0 / rho : (T)1;
 
     if (SOLVE != 0) {
         // ---- phase A: s_c[h] = sum_m Df_c[m][h] * col[m][h]
@@ -417,6 +422,10 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             if (DO_FWD) {
                 if constexpr (GEN) col_dft_chunk<T, false>(buf, buf2, tw, mc, N0);
                 else col_fft_chunk<T, N0T, false>(buf, tw, mc, MC);
+            }
+            if (zeta != (T)1) {
+                for (int e = tid; e < mc * N0; e += nt) buf[e] = zeta * buf[e];
+                __syncthreads();
             }
             for (int e = tid; e < parts * N0; e += nt) {
                 const int part = e / N0, h = e - part * N0;
@@ -523,6 +532,10 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             if (DO_FWD) {
                 if constexpr (GEN) col_dft_chunk<T, false>(buf, buf2, tw, mc, N0);
                 else col_fft_chunk<T, N0T, false>(buf, tw, mc, MC);
+            }
+            if (zeta != (T)1) {
+                for (int e = tid; e < mc * N0; e += nt) buf[e] = zeta * buf[e];
+                __syncthreads();
             }
         }
         if (SOLVE == 1 || SOLVE == 2) {
@@ -641,7 +654,7 @@ template <typename T>
 SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* SPCSC_RESTRICT Zf,
                                    const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
                                    const AdmmState<T>* SPCSC_RESTRICT st,
-                                   double* SPCSC_RESTRICT acc, ColArgs a) {
+                                   double* SPCSC_RESTRICT acc, ColArgs a, T l2w) {
     // one CTA per (wf, b); thread per h (strided); loops over m twice.  Slow, diagnostic only.
     if (st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
@@ -663,7 +676,7 @@ SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* 
         }
         for (int m = 0; m < M; ++m) {
             const C2<T> x = Xf[slab + (size_t)m * N0 + h], z = Zf[slab + (size_t)m * N0 + h];
-            C2<T> ax = rho * x, bb = rho * z;
+            C2<T> ax = (rho + l2w) * x, bb = rho * z;
             for (int c = 0; c < Cd; ++c) {
                 const C2<T> df = Df[(((size_t)c * a.N1f + wf) * M + m) * N0 + h];
                 ax = ax + mulc(e[c], df);
@@ -741,11 +754,16 @@ SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
         o.dfid = o.regl1 = o.regl21 = o.obj = 0;
         o.xrrs = -1.0;
         if (p.need_obj) {
+            const double rho_x = (double)(T)(rho + (p.enet ? p.enet_mu : (T)0));
             o.dfid = p.dfid_direct ? 0.5 * acc[ACC_DFID] * p.inv_n
-                                   : 0.5 * (double)rho * (double)rho * acc[ACC_DFID] * p.inv_n;
+                                   : 0.5 * rho_x * rho_x * acc[ACC_DFID] * p.inv_n;
             o.regl1 = acc[ACC_L1];
             o.regl21 = acc[ACC_L21];
             o.obj = o.dfid + (double)p.lmbda * o.regl1 + (p.joint ? (double)p.mu * o.regl21 : 0.0);
+            if (p.enet) {                  // (mu/2)||x||^2 on the objective's variable (X, or Y with AuxVarObj)
+                o.regl21 = 0.5 * acc[p.dfid_direct ? ACC_Y2 : ACC_X2];
+                o.obj = o.dfid + ((double)p.lmbda * o.regl1 + (double)p.enet_mu * o.regl21);
+            }
         }
         if (p.linsolve_check) {
             const double na = sqrt(acc[ACC_AX2]), nb = sqrt(acc[ACC_B2]);

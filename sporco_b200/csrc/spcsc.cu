@@ -624,6 +624,8 @@ class Engine : public spcsc_handle {
         prm.need_rsdl = (o->ar_enabled || !o->fast_solve) ? 1 : 0;
         prm.need_obj = o->fast_solve ? 0 : 1;
         prm.joint = o->joint;
+        prm.enet = (o->l2_weight != 0.0) ? 1 : 0;
+        prm.enet_mu = (T)o->l2_weight;
         prm.linsolve_check = o->linsolve_check;
         prm.dfid_direct = (o->aux_var_obj && !o->fast_solve) ? 1 : 0;
         configured = true;
@@ -702,6 +704,7 @@ class Engine : public spcsc_handle {
         ColLaunch<T> cs = colargs(M, K * Cx);
         cs.st = st.p;
         cs.acc = acc.p;
+        cs.Lstep = prm.enet ? prm.enet_mu : (T)0;        // SOLVE 1 reads the elastic-net weight here
         cs.a.dfid_on = (prm.need_obj && !prm.dfid_direct) ? 1 : 0;
         const bool aux_eval = prm.need_obj && prm.dfid_direct;
         if (aux_eval) CK(Zscratch.ensure(nslab));
@@ -742,7 +745,7 @@ class Engine : public spcsc_handle {
                 ColArgs ca = c2.a;
                 CK(launch(k_linsolve_check<T>, dim3(N1f, K * Cx), dim3(128), 3 * 32 * sizeof(double), stream,
                           (const C2<T>*)Xscratch.p, (const C2<T>*)Zscratch.p, (const C2<T>*)Df.p,
-                          (const C2<T>*)Sf.p, (const AdmmState<T>*)st.p, acc.p, ca));
+                          (const C2<T>*)Sf.p, (const AdmmState<T>*)st.p, acc.p, ca, cs.Lstep));
                 ColLaunch<T> c3 = cs;
                 c3.in = Xscratch.p; c3.out = zin;
                 CK(col<T>(N0, COL_INV, c3));

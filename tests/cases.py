@@ -39,6 +39,9 @@ ADMM_CASES = {
                           'NoBndryCross': True}, None, False, 'auto'),
     'joint_c3': ({'MaxMainIter': 20, 'RelStopTol': 0.0}, None, True, 'auto'),
     'admm_stop': ({'MaxMainIter': 200, 'RelStopTol': 5e-3}, 1, False, 'auto'),
+    # ConvElasticNet (third field 'enet'): single- and multi-channel dictionary
+    'enet_k3': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, 1, 'enet', 'auto'),
+    'enet_c3': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'AuxVarObj': True}, None, 'enet', 'auto'),
 }
 
 
@@ -50,7 +53,12 @@ def run_admm_case(tag, sfx):
     opt, dimK, joint, kind = ADMM_CASES[tag]
     tol = TOL[(sfx, kind)]
     D, S = g['D'], g['S']
-    if joint:
+    enet = joint == 'enet'
+    joint = joint is True
+    if enet:
+        b = cbpdn.ConvElasticNet(D, S, float(g['lmbda']), float(g['mu']),
+                                 cbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    elif joint:
         b = cbpdn.ConvBPDNJoint(D, S, float(g['lmbda']), float(g['mu']),
                                 cbpdn.ConvBPDNJoint.Options(opt), dimK=dimK)
     else:
@@ -72,6 +80,8 @@ def run_admm_case(tag, sfx):
     assert rel(its.DualRsdl, g['DualRsdl']) <= 40 * stol
     if joint:
         assert rel(its.RegL21, g['RegL21']) <= 10 * stol
+    if enet:
+        assert rel(its.RegL2, g['RegL2']) <= 10 * stol
     assert rel(b.reconstruct().reshape(g['recon'].shape), g['recon']) <= 4 * tol
     return b
 

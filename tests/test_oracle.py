@@ -19,12 +19,15 @@ REF = '/root/reference'
 def test_oracle_reproduces_golden_admm(tag, sfx):
     g = cases.load('%s_%s' % (tag, sfx))
     opt, dimK, joint, _ = cases.ADMM_CASES[tag]
+    enet = joint == 'enet'
+    joint = joint is True
     r = orc.admm_convbpdn(g['D'], g['S'], float(g['lmbda']),
-                          mu=float(g['mu']) if joint else None, opt=opt, dimK=dimK)
+                          mu=float(g['mu']) if joint else None, opt=opt, dimK=dimK,
+                          enet_mu=float(g['mu']) if enet else None)
     assert np.array_equal(r.Y, g['Y'])
     assert np.array_equal(r.U, g['U'])
     assert np.array_equal(r.X, g['X'])
-    rho_col = 9 if joint else 8
+    rho_col = 9 if (joint or enet) else 8
     assert np.array_equal(np.array([row[rho_col] for row in r.itstat], dtype=np.float64), g['Rho'])
     assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
 
