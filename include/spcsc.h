@@ -71,6 +71,11 @@ typedef struct spcsc_admm_opts {
     double l2_weight;      /* ConvElasticNet mu: (mu/2)||x||^2, x-step diagonal mu + rho; 0 = plain
                               ConvBPDN.  With it the regl21 column of the rows carries RegL2.
                               admm/cbpdn.py:948-986 */
+    int32_t ams_maps;      /* AddMaskSim: the last ams_maps filters are the appended impulse(s); their
+                              coefficient maps are neither clipped (NonNegCoef, NoBndryCross) nor counted
+                              in RegL1, and the mask enters through the l1 weight (0 / huge).
+                              admm/cbpdn.py:2377-2409 */
+    int32_t reserved_;
 } spcsc_admm_opts;
 
 /* One row of IterationStats (admm/admm.py:182-189, admm/cbpdn.py:512-514, 737-740). */

@@ -231,11 +231,40 @@ class ADMMResult(object):
     pass
 
 
+def msk_shape(W, dims):
+    """Internal 5-D shape of a data-fidelity mask given in external form (cnvrep.py:553-605)."""
+    ck = W.ndim - 2
+    if ck >= 2:
+        return W.shape + (1,) if ck == 2 else W.shape
+    if ck == 1:
+        if dims.C == 1 and dims.K > 1:
+            return W.shape[0:2] + (1, W.shape[2]) + (1,)
+        return W.shape[0:2] + (W.shape[2], 1) + (1,)
+    return W.shape + (1,) * 3
+
+
+def admm_addmasksim(D, S, W, lmbda=None, opt=None, dimK=None, fft=None):
+    """AddMaskSim(ConvBPDN, D, S, W, lmbda, opt) (admm/cbpdn.py:2287-2485), single-channel
+    dictionary: an impulse filter is appended, its coefficient map is set to AX + U off the mask
+    and to zero on it, and is left out of the regulariser.  Returns the ADMMResult of the inner
+    solver (all M+1 maps) ."""
+    dims = Dims(D, S, dimK=dimK)
+    assert dims.Cd == 1
+    imp = np.zeros(D.shape[0:2] + (1,), dtype=D.dtype)
+    imp[0, 0] = 1.0
+    Di = np.concatenate((D, imp), axis=D.ndim - 1)
+    dtype = np.dtype(S.dtype) if (opt or {}).get('DataType') is None else np.dtype(opt['DataType'])
+    W5 = np.asarray(W.reshape(msk_shape(W, dims)), dtype=dtype)
+    return admm_convbpdn(Di, S, lmbda, opt=opt, dimK=dimK, fft=fft, ams=(W5, 1))
+
+
 def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
-                  norm_reduce=None, record=False, timing=None, enet_mu=None):
+                  norm_reduce=None, record=False, timing=None, enet_mu=None, ams=None):
     """Run the ConvBPDN (mu is None) or ConvBPDNJoint (mu given) ADMM loop; with `enet_mu` the
     ConvElasticNet variant (admm/cbpdn.py:810-990: x-step with mu + rho on the diagonal, extra
     (mu/2)||x||^2 term; rows then carry RegL2 where the joint solver has RegL21).
+    `ams` = (W5, Cd): the additive-mask hook of AddMaskSim (admm/cbpdn.py:2377-2409) for a
+    dictionary whose last Cd filters are the appended impulses; see :func:`admm_addmasksim`.
 
     `norm_reduce`, if given, maps a float64 vector of local sums to global sums; it is
     how the K-sharded multi-rank form of the algorithm is expressed (every rank then
@@ -347,6 +376,10 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         if o['NoBndryCross']:
             Y[1 - hD[0]:, :] = 0.0
             Y[:, 1 - hD[1]:] = 0.0
+        if ams is not None:                  # AddMaskSim.ystep: the impulse maps bypass the prox
+            Yi = AX[..., -ams[1]:] + U[..., -ams[1]:]
+            Yi[np.where(ams[0].astype(bool))] = 0.0
+            Y[..., -ams[1]:] = Yi
         # ---- ustep (admm/admm.py:434-437)
         U = U + (AX - Y)
         # ---- residuals (admm/admm.py:462-486, 959-983)
@@ -385,6 +418,9 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         if not o['FastSolve']:
             fvar = fft.rfftn(Y, None, axN) if o['AuxVarObj'] else Xf
             gvar = Y if o['AuxVarObj'] else X
+            if ams is not None:              # AddMaskSim.obfn_gvar: impulse maps do not count
+                gvar = gvar.copy()
+                gvar[..., -ams[1]:] = 0
             Ef = inner(Df, fvar, axM) - Sf
             dfd = rfl2norm2(Ef, Sm.shape, axis=axN) / 2.0
             rl1 = np.linalg.norm((wl1 * gvar).ravel(), 1)

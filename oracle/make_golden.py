@@ -78,6 +78,28 @@ def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None, enet_mu=None):
     print('wrote', tag, 'Y nnz', int(np.count_nonzero(b.Y)), 'final rho', float(b.rho))
 
 
+AMS_OPT = {'ams_gry': {'MaxMainIter': 30, 'RelStopTol': 0.0},
+           'ams_k3': {'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True,
+                      'AuxVarObj': True}}
+
+
+def ams_case(tag, dt, D, S, W, lmbda, opt, dimK=None):
+    """AddMaskSim about ConvBPDN (admm/cbpdn.py:2287-2485)."""
+    b = rcbpdn.AddMaskSim(rcbpdn.ConvBPDN, D, S, W, lmbda, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    X = b.solve()
+    r = orc.admm_addmasksim(D, S, W, lmbda, opt=opt, dimK=dimK)
+    same(b.cbpdn.Y, r.Y, tag + ' Y')
+    same(b.cbpdn.X, r.X, tag + ' X')
+    its = b.getitstat()
+    for name, c in (('ObjFun', 1), ('DFid', 2), ('RegL1', 3), ('PrimalRsdl', 4), ('DualRsdl', 5), ('Rho', 8)):
+        same(stat(its, name), np.array([row[c] for row in r.itstat], dtype=np.float64), tag + ' ' + name)
+    out = dict(D=D, S=S, W=W, lmbda=np.float64(lmbda), Y=b.cbpdn.Y, Xprimary=X, recon=b.reconstruct(),
+               Rho=stat(its, 'Rho'), ObjFun=stat(its, 'ObjFun'), DFid=stat(its, 'DFid'),
+               RegL1=stat(its, 'RegL1'), PrimalRsdl=stat(its, 'PrimalRsdl'), DualRsdl=stat(its, 'DualRsdl'))
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag)
+
+
 def pgm_case(tag, dt, D, S, lmbda, opt_ref, opt_orc, dimK=None):
     b = rpgm.ConvBPDN(D, S, lmbda, rpgm.ConvBPDN.Options(opt_ref), dimK=dimK)
     b.solve()
@@ -182,6 +204,10 @@ def main():
                   {'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True})
         admm_case('joint_c3_' + sfx, dt, D, S3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0}, mu=0.05)
         admm_case('admm_stop_' + sfx, dt, D, S, 0.2, {'MaxMainIter': 200, 'RelStopTol': 5e-3}, dimK=1)
+        Wm = (rng.random((32, 32)) > 0.3).astype(dt)
+        Wk = (rng.random((32, 32, 3)) > 0.3).astype(dt)
+        ams_case('ams_gry_' + sfx, dt, D, S[..., 0], Wm, 0.1, AMS_OPT['ams_gry'])
+        ams_case('ams_k3_' + sfx, dt, D, S, Wk, 0.1, AMS_OPT['ams_k3'], dimK=1)
         admm_case('enet_k3_' + sfx, dt, D, S, 0.1, {'MaxMainIter': 30, 'RelStopTol': 0.0}, dimK=1,
                   enet_mu=0.3)
         admm_case('enet_c3_' + sfx, dt, D3, S3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0,

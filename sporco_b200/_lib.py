@@ -52,7 +52,8 @@ class AdmmOpts(ctypes.Structure):
                [(n, ctypes.c_int32) for n in
                 ('ar_enabled', 'ar_period', 'ar_autoscaling', 'ar_std_residuals', 'joint',
                  'nonneg', 'no_bndry_cross', 'fast_solve', 'aux_var_obj', 'linsolve_check')] + \
-               [('l2_weight', ctypes.c_double)]
+               [('l2_weight', ctypes.c_double), ('ams_maps', ctypes.c_int32),
+                ('reserved_', ctypes.c_int32)]
 
 
 class PgmOpts(ctypes.Structure):

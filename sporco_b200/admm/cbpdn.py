@@ -181,7 +181,8 @@ class GenericConvBPDN(admm.ADMMEqual):
             nonneg=int(bool(o['NonNegCoef'])), no_bndry_cross=int(bool(o['NoBndryCross'])),
             fast_solve=int(bool(o['FastSolve'])), aux_var_obj=int(bool(o['gEvalY'])),
             linsolve_check=int(bool(o['LinSolveCheck'])),
-            l2_weight=float(getattr(self, '_l2_weight', 0.0)))
+            l2_weight=float(getattr(self, '_l2_weight', 0.0)),
+            ams_maps=int(getattr(self, '_ams_maps', 0)))
 
     def _device_iterate(self, n, want_rows):
         if bool(self.opt['gEvalY']) != (not bool(self.opt['fEvalX'])):
@@ -380,3 +381,86 @@ class ConvElasticNet(ConvBPDN):
         self.mu = self.dtype.type(mu)
         self._l2_weight = float(self.mu)
         super(ConvElasticNet, self).__init__(D, S, lmbda, opt, dimK=dimK, dimN=dimN, device=device)
+
+
+class AddMaskSim(object):
+    """Boundary / missing-data masking by additive mask simulation (mirror of
+    sporco/admm/cbpdn.py:2287-2485): a wrapper about a :class:`ConvBPDN` (or :class:`ConvElasticNet`)
+    object whose dictionary gets an impulse filter appended; the impulse's coefficient map absorbs
+    the signal where the mask `W` is zero.  Single-channel dictionaries.
+
+    On the device the hook the reference installs on ``ystep`` / ``obfn_gvar`` is a property of the
+    prox kernel: the mask enters as the l1 weight of the impulse map (0 where ``W == 0``: the map
+    is ``AX + U``; a huge weight elsewhere: the map is 0), and maps flagged as additive-mask maps are
+    neither clipped by ``NonNegCoef`` / ``NoBndryCross`` nor counted in ``RegL1``.
+    """
+
+    def __init__(self, cbpdnclass, D, S, W, *args, **kwargs):
+        dimK = kwargs.get('dimK', None)
+        dimN = kwargs.get('dimN', 2)
+        if not (isinstance(cbpdnclass, type) and issubclass(cbpdnclass, ConvBPDN)) or \
+                issubclass(cbpdnclass, ConvBPDNJoint):
+            raise NotImplementedError('AddMaskSim wraps sporco_b200 ConvBPDN / ConvElasticNet objects')
+        self.cri = cr.CSC_ConvRepIndexing(D, S, dimK=dimK, dimN=dimN)
+        if self.cri.Cd != 1:
+            raise NotImplementedError('AddMaskSim with a multi-channel dictionary is not supported')
+        self.imp = np.zeros(D.shape[0:dimN] + (1,))
+        self.imp[(0,) * dimN] = 1.0
+        Di = np.concatenate((D, self.imp.astype(D.dtype)), axis=D.ndim - 1)
+        self.cbpdn = cbpdnclass(Di, S, *args, **kwargs)
+        self.IterationStats = self.cbpdn.IterationStats
+        inner = self.cbpdn
+        self.W = np.asarray(np.asarray(W).reshape(cr.mskWshape(np.asarray(W), self.cri)),
+                            dtype=inner.dtype)
+        # positions of the impulse map that are forced to zero: exactly the reference's
+        # ``Yi[np.where(self.W.astype(bool))] = 0.0`` on Yi of shape (N0, N1, Cx, K, 1)
+        icri = inner.cri
+        kdim = icri.K if self.W.shape[icri.axisK] > 1 else 1
+        cdim = icri.shpX[icri.axisC] if self.W.shape[icri.axisC] > 1 else 1
+        on = np.zeros(icri.Nv + (cdim, kdim, 1), dtype=bool)
+        on[np.where(self.W.astype(bool))] = True
+        # combined l1 weight: the inner object's own weight on the primary maps ...
+        w1 = inner.wl1
+        shp = tuple(max(a, b) for a, b in zip(w1.shape[:4], on.shape[:4])) + (icri.M,)
+        wfull = np.empty(shp, dtype=inner.dtype)
+        wfull[...] = np.broadcast_to(w1, shp)
+        # ... and the mask on the impulse map
+        huge = inner.dtype.type(1e30 if inner.dtype == np.float32 else 1e300)
+        wfull[..., -1] = np.where(np.broadcast_to(on[..., 0], shp[:4]), huge, inner.dtype.type(0))
+        inner._ams_maps = 1
+        inner.wl1 = wfull
+        inner._after_open()
+        self.timer = inner.timer
+        self.itstat = inner.itstat
+
+    def solve(self):
+        """Solve with the inner object and strip the additive-mask map from the result."""
+        Xi = self.cbpdn.solve()
+        self.timer = self.cbpdn.timer
+        self.itstat = self.cbpdn.itstat
+        return Xi[self.index_primary()]
+
+    def setdict(self, D=None):
+        Di = np.concatenate((D, self.imp.astype(D.dtype)), axis=D.ndim - 1)
+        self.cbpdn.setdict(Di)
+
+    def getcoef(self):
+        return self.cbpdn.getcoef()[self.index_primary()]
+
+    def index_primary(self):
+        return np.s_[..., 0:-self.cri.Cd]
+
+    def index_addmsk(self):
+        return np.s_[..., -self.cri.Cd:]
+
+    def reconstruct(self, X=None):
+        """Reconstruction from the primary maps only (admm/cbpdn.py:2461-2475)."""
+        inner = self.cbpdn
+        if X is None:
+            X = inner.Y[self.index_primary()]
+        X = np.asarray(X, dtype=inner.dtype)
+        Xi = np.concatenate((X, np.zeros(X.shape[:-1] + (1,), dtype=inner.dtype)), axis=X.ndim - 1)
+        return inner.reconstruct(Xi)
+
+    def getitstat(self):
+        return self.cbpdn.getitstat()

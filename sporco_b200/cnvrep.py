@@ -155,3 +155,16 @@ def Pcn(x, dsz, Nv, dimN=2, dimC=1, crp=False, zm=False):
 def getPcn(dsz, Nv, dimN=2, dimC=1, crp=False, zm=False):
     """Closure form of :func:`Pcn` (cnvrep.py:1036-1074)."""
     return lambda x: Pcn(x, dsz, Nv, dimN, dimC, crp, zm)
+
+
+def mskWshape(W, cri):
+    """Internal 5-D (broadcastable) shape of a data-fidelity mask given in external form
+    (sporco/cnvrep.py:553-605)."""
+    ck = W.ndim - cri.dimN
+    if ck >= 2:
+        return W.shape + (1,) if ck == 2 else W.shape
+    if ck == 1:
+        if cri.C == 1 and cri.K > 1:
+            return W.shape[0:cri.dimN] + (1, W.shape[cri.dimN]) + (1,)
+        return W.shape[0:cri.dimN] + (W.shape[cri.dimN], 1) + (1,)
+    return W.shape + (1,) * (3 - ck)

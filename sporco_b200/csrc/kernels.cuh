@@ -53,6 +53,8 @@ struct AdmmParams {
     int dfid_direct;                     // 1: ACC_DFID already holds the weighted |sum_m Df Yf - Sf|^2 (AuxVarObj)
     int enet;                            // 1: ConvElasticNet: rows carry RegL2 = ||x||^2 / 2 in the regl21 column
     T enet_mu;                           // its l2 weight: the x-step diagonal is enet_mu + rho
+    int ams_m0;                          // AddMaskSim: filters m >= ams_m0 are the appended impulse maps (M: none)
+    int pad2_;
 };
 
 struct StatRow {
@@ -206,6 +208,7 @@ SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRI
     constexpr int P = H + 1;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
     const int N1 = 2 * H;
     const size_t cbuf = (size_t)TR * P;
 
@@ -247,7 +250,7 @@ SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRI
                 wv[c][q] = w;
                 a2[q] += w * w;
                 if (!reg_on_y) {
-                    sums[ACC_L1] += (double)fabs(w1 * xs[q]);
+                    sums[ACC_L1] += ams ? 0 : (double)fabs(w1 * xs[q]);
                     g2[q] += xs[q] * xs[q];
                 }
             }
@@ -271,8 +274,8 @@ SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRI
             SPCSC_UNROLL
             for (int q = 0; q < 2; ++q) {
                 T y = prm.joint ? fac[q] * wv[c][q] : wv[c][q];
-                if (nonneg && y < (T)0) y = (T)0;
-                if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+                if (nonneg && !ams && y < (T)0) y = (T)0;
+                if (!ams && (h >= bnd0 || (2 * j + q) >= bnd1)) y = (T)0;
                 const T u = ue[c][q] + (ax[c][q] - y);
                 yn[q] = y;
                 un[q] = u;
@@ -287,7 +290,7 @@ SPCSC_GLOBAL void k_row_inv_prox(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRI
                     const T w1 = wl1.p[(size_t)k * wl1.sk + (size_t)c * wl1.sc +
                                       (size_t)m * wl1.sm + (size_t)h * wl1.s0 +
                                       (size_t)(2 * j + q) * wl1.s1];
-                    sums[ACC_L1] += (double)fabs(w1 * y);
+                    sums[ACC_L1] += ams ? 0 : (double)fabs(w1 * y);
                     g2[q] += y * y;
                 }
             }

@@ -106,6 +106,7 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
     C2<T>* stw_s = reg + CX * TR * P;
     const int tid = threadIdx.x;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
     for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
     const size_t wstride = (size_t)M * N0;
     SPCSC_UNROLL
@@ -186,7 +187,7 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
                 wv[c][q] = w;
                 a2[q] += w * w;
                 if (!reg_on_y) {
-                    sums[ACC_L1] += fabs(w1 * xs[q]);
+                    sums[ACC_L1] += ams ? 0 : fabs(w1 * xs[q]);
                     g2[q] += xs[q] * xs[q];
                 }
             }
@@ -209,8 +210,8 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
             SPCSC_UNROLL
             for (int q = 0; q < 2; ++q) {
                 T y = prm.joint ? fac[q] * wv[c][q] : wv[c][q];
-                if (nonneg && y < (T)0) y = (T)0;
-                if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+                if (nonneg && !ams && y < (T)0) y = (T)0;
+                if (!ams && (h >= bnd0 || (2 * j + q) >= bnd1)) y = (T)0;
                 const T u = ue[c][q] + (ax[c][q] - y);
                 yn[q] = y;
                 un[q] = u;
@@ -225,7 +226,7 @@ k_row_inv_prox2(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT Y, T* SPCSC_RE
                     const T w1 = wl1.spatial_uniform
                                      ? w1u[c]
                                      : wl1.p[wbase + (size_t)c * wl1.sc + (size_t)(2 * j + q) * wl1.s1];
-                    sums[ACC_L1] += fabs(w1 * y);
+                    sums[ACC_L1] += ams ? 0 : fabs(w1 * y);
                     g2[q] += y * y;
                 }
             }
@@ -296,6 +297,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     C2<T>* tw_s = stw_s + TWLEN;                               // [N1f] split twiddles
     const int tid = threadIdx.x;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
     const size_t wstride = (size_t)M * N0;
     const int gr = tid % TR, wf0 = tid / TR;                   // this thread's row / first wf in tile loops
     SPCSC_UNROLL
@@ -459,8 +461,8 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
             for (int q = 0; q < 2; ++q) {
                 T y = (CX > 1 && prm.joint) ? fac[q] * wv[c][q] : wv[c][q];
                 if (!PLAIN) {
-                    if (nonneg && y < (T)0) y = (T)0;
-                    if (h >= bnd0 || (2 * j + q) >= bnd1) y = (T)0;
+                    if (nonneg && !ams && y < (T)0) y = (T)0;
+                    if (!ams && (h >= bnd0 || (2 * j + q) >= bnd1)) y = (T)0;
                 }
                 const T u = ue[c][q] + (ax[c][q] - y);
                 yn[q] = y;
@@ -473,7 +475,7 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
                 sums[ACC_R2] += dr * dr;
                 sums[ACC_S2] += ds * ds;
                 const T gq = (!PLAIN && reg_on_y) ? y : x;
-                sums[ACC_L1] += fabs(w1s[c][q] * gq);
+                sums[ACC_L1] += ams ? 0 : fabs(w1s[c][q] * gq);
                 g2[q] += gq * gq;
             }
             const size_t off = ((((size_t)(k * CX + c) * M + m) * N0 + h) * H + j);

@@ -116,6 +116,7 @@ SPCSC_GLOBAL void k_row_inv_prox_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RE
     C2<T>* zs = reinterpret_cast<C2<T>*>(smem_raw);                     // [TR][N1f]
     T* xs = reinterpret_cast<T*>(zs + (size_t)TR * N1f);                // [CX][TR][N1]
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
+    const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
     const int nrow = (N0 - h0) < TR ? (N0 - h0) : TR;
     for (int c = 0; c < CX; ++c)
         gen_rows_inverse<T>(zs, xs + (size_t)c * TR * N1, Zt, tw, k * CX + c, m, h0, nrow, N0, N1, M,
@@ -142,7 +143,7 @@ SPCSC_GLOBAL void k_row_inv_prox_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RE
             xv[c] = x; yp[c] = y; ax[c] = axv; ue[c] = u; wv[c] = w; w1s[c] = w1;
             a2 += w * w;
             if (!reg_on_y) {
-                sums[ACC_L1] += (double)fabs(w1 * x);
+                sums[ACC_L1] += ams ? 0 : (double)fabs(w1 * x);
                 g2 += x * x;
             }
         }
@@ -158,8 +159,8 @@ SPCSC_GLOBAL void k_row_inv_prox_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RE
         for (int c = 0; c < CX; ++c) {
             const size_t off = ((((size_t)(k * CX + c) * M + m) * N0 + h) * N1 + n);
             T y = prm.joint ? fac * wv[c] : wv[c];
-            if (nonneg && y < (T)0) y = (T)0;
-            if (h >= bnd0 || n >= bnd1) y = (T)0;
+            if (nonneg && !ams && y < (T)0) y = (T)0;
+            if (!ams && (h >= bnd0 || n >= bnd1)) y = (T)0;
             const T u = ue[c] + (ax[c] - y);
             const T x = xv[c];
             const T dr = x - y, ds = yp[c] - y;
@@ -169,7 +170,7 @@ SPCSC_GLOBAL void k_row_inv_prox_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RE
             sums[ACC_R2] += (double)dr * dr;
             sums[ACC_S2] += (double)ds * ds;
             if (reg_on_y) {
-                sums[ACC_L1] += (double)fabs(w1s[c] * y);
+                sums[ACC_L1] += ams ? 0 : (double)fabs(w1s[c] * y);
                 g2 += y * y;
             }
             Y[off] = y;

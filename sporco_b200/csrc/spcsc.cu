@@ -626,6 +626,10 @@ class Engine : public spcsc_handle {
         prm.joint = o->joint;
         prm.enet = (o->l2_weight != 0.0) ? 1 : 0;
         prm.enet_mu = (T)o->l2_weight;
+        prm.ams_m0 = M - (o->ams_maps > 0 ? o->ams_maps : 0);
+        prm.pad2_ = 0;
+        if (o->ams_maps < 0 || o->ams_maps >= M) FAIL(SPCSC_ERR_INVALID, "ams_maps out of range");
+        if (o->ams_maps > 0 && o->joint) FAIL(SPCSC_ERR_UNSUPPORTED, "AddMaskSim with the joint penalty");
         prm.linsolve_check = o->linsolve_check;
         prm.dfid_direct = (o->aux_var_obj && !o->fast_solve) ? 1 : 0;
         configured = true;

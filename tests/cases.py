@@ -434,3 +434,30 @@ def run_long_determinism_case(iters=400, K=8):
     rho, r, s = outs[0]
     assert np.all(rho[60:] == rho[60]), 'rho changed after settling: %s' % np.nonzero(np.diff(rho[60:]))[0][:5]
     assert np.all(np.diff(r[60:]) < 0) and np.all(np.diff(s[60:]) < 0)      # monotone decrease
+
+
+AMS_CASES = {'ams_gry': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, None),
+             'ams_k3': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True,
+                         'AuxVarObj': True}, 1)}
+
+
+def run_ams_case(tag, sfx):
+    """AddMaskSim about ConvBPDN against the reference's outputs (tests/golden/ams_*.npz)."""
+    from sporco_b200.admm import cbpdn
+    g = load('%s_%s' % (tag, sfx))
+    opt, dimK = AMS_CASES[tag]
+    tol = TOL[(sfx, 'auto')]
+    b = cbpdn.AddMaskSim(cbpdn.ConvBPDN, g['D'], g['S'], g['W'], float(g['lmbda']),
+                         cbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    X = b.solve()
+    its = b.getitstat()
+    assert X.shape == g['Xprimary'].shape and rel(X, g['Xprimary']) <= 4 * tol
+    assert rel(b.cbpdn.Y, g['Y']) <= tol, 'Y: %.3e' % rel(b.cbpdn.Y, g['Y'])
+    stol = max(tol, 1e-6 if sfx == 'f32' else 1e-11)
+    assert len(its.Rho) == len(g['Rho']) and rel(its.Rho, g['Rho']) <= 10 * stol
+    assert rel(its.ObjFun, g['ObjFun']) <= 10 * stol and rel(its.RegL1, g['RegL1']) <= 10 * stol
+    assert rel(its.DFid, g['DFid']) <= 40 * stol
+    assert rel(its.PrimalRsdl, g['PrimalRsdl']) <= 40 * stol and rel(its.DualRsdl, g['DualRsdl']) <= 40 * stol
+    assert rel(b.reconstruct().reshape(g['recon'].shape), g['recon']) <= 4 * tol
+    assert b.getcoef().shape == X.shape
+    return b

@@ -61,6 +61,17 @@ def test_oracle_reproduces_golden_dictionary_learning(tag, sfx):
         assert np.array_equal(r[f], g[f]), f
 
 
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.AMS_CASES))
+def test_oracle_reproduces_golden_addmasksim(tag, sfx):
+    g = cases.load('%s_%s' % (tag, sfx))
+    opt, dimK = cases.AMS_CASES[tag]
+    r = orc.admm_addmasksim(g['D'], g['S'], g['W'], float(g['lmbda']), opt=opt, dimK=dimK)
+    assert np.array_equal(r.Y, g['Y'])
+    assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
+    assert np.array_equal(np.array([row[8] for row in r.itstat], dtype=np.float64), g['Rho'])
+
+
 def test_oracle_level1_known_answers():
     g = cases.load('level1')
     assert np.array_equal(orc.solvedbi_sm(g['ah'], 0.7, g['b'], 4), g['x'])

@@ -203,3 +203,9 @@ def test_dictionary_learning_golden(tag, sfx):
 @pytest.mark.parametrize('dt', [np.float64, np.float32])
 def test_ccmod_standalone(dt):
     cases.run_ccmod_standalone(dt)
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.AMS_CASES))
+def test_additive_mask_simulation_golden(tag, sfx):
+    cases.run_ams_case(tag, sfx)
