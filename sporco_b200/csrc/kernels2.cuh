@@ -624,14 +624,6 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             __syncwarp();
         }
     }
-    if (SOLVE == 1 && Lstep != (T)0) {       // ConvElasticNet: z' = (rho / (mu + rho)) z, see k_col
-        const T r0 = st->rho, zeta = r0 / (r0 + Lstep);
-        SPCSC_UNROLL
-        for (int c = 0; c < CPG; ++c) {
-            SPCSC_UNROLL
-            for (int p = 0; p < E; ++p) v[c][p] = zeta * v[c][p];
-        }
-    }
     if constexpr (SOLVE != 0) {
     // s_d[h] = sum over this CTA's columns of Df_d[m][h] * col[m][h], one dictionary channel at a time
     SPCSC_UNROLL
@@ -663,7 +655,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     cluster_arrive();
     cluster_wait();
     const int k = b / a.Cx, cx = b - k * a.Cx;
-    const T rho = (SOLVE == 1) ? st->rho + Lstep : (T)0;      // Lstep: elastic-net weight (0: none)
+    const T rho = (SOLVE == 1) ? st->rho : (T)0;
     double dsum[1] = {0.0};
     for (int h = tid; h < N0; h += NT) {
         C2<T> dv[CD];

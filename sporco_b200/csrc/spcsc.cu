@@ -734,7 +734,7 @@ class Engine : public spcsc_handle {
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (!check) {
                 cs.in = zin; cs.out = zin;
-                if (v2_col)
+                if (v2_col && !prm.enet)         // the l2 term is handled by the general kernel only
                     CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
                 else
                     CK(col<T>(N0, COL_ADMM, cs));

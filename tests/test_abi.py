@@ -59,3 +59,29 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_hot_kernels_do_not_spill():
+    """The two kernels of the benchmarked iteration must fit their register budget without local
+    memory: a spill costs ~15 % of the column kernel (seen once, after an innocent-looking edit)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    from sporco_b200 import build
+    out = subprocess.run([cuobjdump, '-res-usage', build.build()], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, text=True).stdout.splitlines()
+    hot = {'k_col2IfLi256ELi16ELi2ELi256ELi1ELb1ELi1ELb1ELb0': 128,        # 2 CTAs of 256 threads per SM
+           'k_row_inv_prox3IfLi128ELi16ELi1ELi128ELb1': 128}               # 4 CTAs of 128 threads per SM
+    seen = set()
+    for i, line in enumerate(out):
+        for key, cap in hot.items():
+            if key in line and 'Function' in line:
+                use = out[i + 1]
+                regs = int(use.split('REG:')[1].split()[0])
+                stack = int(use.split('STACK:')[1].split()[0])
+                assert stack == 0, '%s spills %d bytes' % (key, stack)
+                assert regs <= cap, '%s uses %d registers' % (key, regs)
+                seen.add(key)
+    assert seen == set(hot), 'hot kernel instantiations not found: %s' % (set(hot) - seen)
