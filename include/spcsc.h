@@ -172,6 +172,12 @@ int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]);
 /* Accept the candidate and take the momentum step Yf = Xf + coef (Xf - Xfprv)  (PGMDFT.ystep). */
 int spcsc_pgm_accept(spcsc_handle* h, double coef);
 
+/* ConvBPDNGradReg (admm/cbpdn.py:993-1216): gradient regulariser (mu/2) sum_m w_m ||G x_m||^2 with weight
+   `mu` = spcsc_admm_opts.mu.  ghg: (N0, N1f) real, sum_i |G_i|^2 as signal.gradient_filters returns it;
+   wgrd: M reals (GradWeight).  The x-step solves with the diagonal mu w_m ghg + rho (linalg.solvedbd_sm);
+   the regl21 column of the rows carries RegGrad.  ghg == NULL switches it off. Single-channel dictionary. */
+int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd);
+
 /* ---- dictionary update: sporco.pgm.ccmod.ConvCnstrMOD as the D step of
    sporco.dictlrn.cbpdndl.ConvBPDNDictLearn (dictlrn/dictlrn.py:327-363), sharing the handle -- and
    the device arrays -- of the X step.  Single-channel dictionary and signal.

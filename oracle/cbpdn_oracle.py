@@ -130,6 +130,24 @@ def solvedbi_sm(ah, rho, b, axis=4):
     return (b - (a * inner(c, b, axis))) / rho
 
 
+def solvedbd_sm(ah, d, b, axis=4):
+    """(diag(d) + a a^H) x = b per frequency (linalg.py:301-366)."""
+    a = np.conj(ah)
+    c = (ah / d) / (inner(ah, (a / d), axis) + 1.0)
+    return (b - (a * inner(c, b, axis))) / d
+
+
+def gradient_filters(ndim, axes, axshp, dtype, fft):
+    """DFTs of the forward-difference filters and the sum of their squared magnitudes
+    (signal.py:196-240)."""
+    g = np.zeros([2 if k in axes else 1 for k in range(ndim)] + [len(axes), ], dtype)
+    for k in axes:
+        g[(0,) * k + (slice(None),) + (0,) * (g.ndim - 2 - k) + (k,)] = np.array([1, -1])
+    Gf = fft.rfftn(g, axshp, axes)
+    GHGf = np.sum(np.conj(Gf) * Gf, axis=-1).real
+    return Gf, GHGf
+
+
 def solvemdbi_ism(ah, rho, b, axisM, axisK):
     """(rho I + sum_k a_k a_k^H) x = b by iterated rank-one updates (linalg.py:370-444)."""
     nk = ah.shape[axisK]
@@ -203,7 +221,7 @@ ADMM_DEFAULTS = {
     'MaxMainIter': 1000, 'AbsStopTol': 0.0, 'RelStopTol': 1e-3, 'RelaxParam': 1.8,
     'rho': None, 'FastSolve': False, 'DataType': None, 'AuxVarObj': False,
     'LinSolveCheck': False, 'NonNegCoef': False, 'NoBndryCross': False,
-    'L1Weight': 1.0, 'L21Weight': 1.0, 'Y0': None, 'U0': None,
+    'L1Weight': 1.0, 'L21Weight': 1.0, 'GradWeight': 1.0, 'Y0': None, 'U0': None,
     'AutoRho': {'Enabled': True, 'Period': 1, 'Scaling': 1000.0, 'RsdlRatio': 1.2,
                 'RsdlTarget': None, 'AutoScaling': True, 'StdResiduals': False},
 }
@@ -243,7 +261,7 @@ def msk_shape(W, dims):
     return W.shape + (1,) * 3
 
 
-def admm_addmasksim(D, S, W, lmbda=None, opt=None, dimK=None, fft=None):
+def admm_addmasksim(D, S, W, lmbda=None, opt=None, dimK=None, fft=None, grad_mu=None):
     """AddMaskSim(ConvBPDN, D, S, W, lmbda, opt) (admm/cbpdn.py:2287-2485), single-channel
     dictionary: an impulse filter is appended, its coefficient map is set to AX + U off the mask
     and to zero on it, and is left out of the regulariser.  Returns the ADMMResult of the inner
@@ -255,14 +273,16 @@ def admm_addmasksim(D, S, W, lmbda=None, opt=None, dimK=None, fft=None):
     Di = np.concatenate((D, imp), axis=D.ndim - 1)
     dtype = np.dtype(S.dtype) if (opt or {}).get('DataType') is None else np.dtype(opt['DataType'])
     W5 = np.asarray(W.reshape(msk_shape(W, dims)), dtype=dtype)
-    return admm_convbpdn(Di, S, lmbda, opt=opt, dimK=dimK, fft=fft, ams=(W5, 1))
+    return admm_convbpdn(Di, S, lmbda, opt=opt, dimK=dimK, fft=fft, ams=(W5, 1), grad_mu=grad_mu)
 
 
 def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
-                  norm_reduce=None, record=False, timing=None, enet_mu=None, ams=None):
+                  norm_reduce=None, record=False, timing=None, enet_mu=None, ams=None,
+                  grad_mu=None):
     """Run the ConvBPDN (mu is None) or ConvBPDNJoint (mu given) ADMM loop; with `enet_mu` the
     ConvElasticNet variant (admm/cbpdn.py:810-990: x-step with mu + rho on the diagonal, extra
     (mu/2)||x||^2 term; rows then carry RegL2 where the joint solver has RegL21).
+    `grad_mu`: ConvBPDNGradReg (admm/cbpdn.py:993-1206; option GradWeight; rows carry RegGrad).
     `ams` = (W5, Cd): the additive-mask hook of AddMaskSim (admm/cbpdn.py:2377-2409) for a
     dictionary whose last Cd filters are the appended impulses; see :func:`admm_addmasksim`.
 
@@ -316,6 +336,17 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
     if enet:
         assert not joint
         emu = dtype.type(enet_mu)
+    grd = grad_mu is not None
+    if grd:
+        assert not joint and not enet and dims.Cd == 1
+        gmu = dtype.type(grad_mu)
+        gw = o.get('GradWeight', 1.0)
+        if hasattr(gw, 'ndim'):
+            Wgrd = np.asarray(gw.reshape((1,) * 4 + gw.shape), dtype=dtype)
+        else:
+            Wgrd = np.asarray(gw, dtype=dtype)
+        _, GHGf0 = gradient_filters(5, axN, dims.Nv, dtype, fft)
+        GHGf = Wgrd * GHGf0
 
     if o['U0'] is not None:
         U = o['U0'].astype(dtype, copy=True)
@@ -349,7 +380,10 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         YU = Y - U
         b = DSf + rho * fft.rfftn(YU, None, axN)
         rho_x = (emu + rho) if enet else rho           # admm/cbpdn.py:948-955
-        if dims.Cd == 1:
+        if grd:                                         # admm/cbpdn.py:1173-1201
+            rho_x = gmu * GHGf + rho
+            Xf = solvedbd_sm(Df, rho_x, b, axM)
+        elif dims.Cd == 1:
             Xf = solvedbi_sm(Df, rho_x, b, axM)
         else:
             Xf = solvemdbi_ism(Df, rho_x, b, axM, axC)
@@ -357,7 +391,7 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         if o['LinSolveCheck']:
             dx = inner(Df, Xf, axM)
             if dims.Cd == 1:
-                ax = np.conj(Df) * dx + rho_x * Xf
+                ax = np.conj(Df) * dx + rho_x * Xf          # rho_x: scalar, or the GradReg diagonal
             else:
                 ax = inner(np.conj(Df), dx, axC) + rho_x * Xf
             xrrs = rrs(ax, b)
@@ -433,6 +467,13 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
                     rl21 = norm_reduce(np.array([rl21], dtype=np.float64))[0]
                 obj = dfd + (lmbda * rl1 + mu_ * rl21)
                 row = (k, obj, dfd, rl1, rl21, r, s, epri, edua, rho, xrrs,
+                       time.perf_counter() - t_start)
+            elif grd:                                   # admm/cbpdn.py:1205-1216
+                rgr = rfl2norm2(np.sqrt(GHGf * np.conj(fvar) * fvar), dims.Nv, axis=axN) / 2.0
+                if norm_reduce is not None:
+                    rgr = norm_reduce(np.array([rgr], dtype=np.float64))[0]
+                obj = dfd + (lmbda * rl1 + gmu * rgr)
+                row = (k, obj, dfd, rl1, rgr, r, s, epri, edua, rho, xrrs,
                        time.perf_counter() - t_start)
             elif enet:                                  # admm/cbpdn.py:978-986
                 rl2 = 0.5 * np.linalg.norm(gvar) ** 2

@@ -43,21 +43,23 @@ def stat(its, name):
     return np.asarray(getattr(its, name), dtype=np.float64)
 
 
-def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None, enet_mu=None):
-    if enet_mu is not None:
+def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None, enet_mu=None, grad_mu=None):
+    if grad_mu is not None:
+        b = rcbpdn.ConvBPDNGradReg(D, S, lmbda, grad_mu, rcbpdn.ConvBPDNGradReg.Options(opt), dimK=dimK)
+    elif enet_mu is not None:
         b = rcbpdn.ConvElasticNet(D, S, lmbda, enet_mu, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
     elif mu is None:
         b = rcbpdn.ConvBPDN(D, S, lmbda, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
     else:
         b = rcbpdn.ConvBPDNJoint(D, S, lmbda, mu, rcbpdn.ConvBPDNJoint.Options(opt), dimK=dimK)
     b.solve()
-    r = orc.admm_convbpdn(D, S, lmbda, mu=mu, opt=opt, dimK=dimK, enet_mu=enet_mu)
+    r = orc.admm_convbpdn(D, S, lmbda, mu=mu, opt=opt, dimK=dimK, enet_mu=enet_mu, grad_mu=grad_mu)
     same(b.Y, r.Y, tag + ' Y')
     same(b.U, r.U, tag + ' U')
     same(b.X, r.X, tag + ' X')
     its = b.getitstat()
     col = {'ObjFun': 1, 'DFid': 2, 'RegL1': 3}
-    off = 1 if (mu is not None or enet_mu is not None) else 0
+    off = 1 if (mu is not None or enet_mu is not None or grad_mu is not None) else 0
     col.update({'PrimalRsdl': 4 + off, 'DualRsdl': 5 + off, 'Rho': 8 + off})
     for name, c in col.items():
         same(stat(its, name), np.array([row[c] for row in r.itstat], dtype=np.float64),
@@ -70,6 +72,10 @@ def admm_case(tag, dt, D, S, lmbda, opt, dimK=None, mu=None, enet_mu=None):
     if mu is not None:
         out['mu'] = np.float64(mu)
         out['RegL21'] = stat(its, 'RegL21')
+    if grad_mu is not None:
+        out['mu'] = np.float64(grad_mu)
+        out['RegGrad'] = stat(its, 'RegGrad')
+        same(out['RegGrad'], np.array([row[4] for row in r.itstat], dtype=np.float64), tag + ' RegGrad')
     if enet_mu is not None:
         out['mu'] = np.float64(enet_mu)
         out['RegL2'] = stat(its, 'RegL2')
@@ -83,15 +89,27 @@ AMS_OPT = {'ams_gry': {'MaxMainIter': 30, 'RelStopTol': 0.0},
                       'AuxVarObj': True}}
 
 
-def ams_case(tag, dt, D, S, W, lmbda, opt, dimK=None):
-    """AddMaskSim about ConvBPDN (admm/cbpdn.py:2287-2485)."""
-    b = rcbpdn.AddMaskSim(rcbpdn.ConvBPDN, D, S, W, lmbda, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
+GRD_OPT = {'grd_k3': lambda dt: {'MaxMainIter': 30, 'RelStopTol': 0.0},
+           'grd_aux': lambda dt: {'MaxMainIter': 20, 'RelStopTol': 0.0, 'AuxVarObj': True,
+                                  'LinSolveCheck': True,
+                                  'GradWeight': np.linspace(0.2, 2.0, 6).astype(dt)}}
+
+
+def ams_case(tag, dt, D, S, W, lmbda, opt, dimK=None, grad_mu=None):
+    """AddMaskSim about ConvBPDN or ConvBPDNGradReg (admm/cbpdn.py:2287-2485)."""
+    if grad_mu is None:
+        b = rcbpdn.AddMaskSim(rcbpdn.ConvBPDN, D, S, W, lmbda, rcbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    else:
+        b = rcbpdn.AddMaskSim(rcbpdn.ConvBPDNGradReg, D, S, W, lmbda, grad_mu,
+                              rcbpdn.ConvBPDNGradReg.Options(opt), dimK=dimK)
     X = b.solve()
-    r = orc.admm_addmasksim(D, S, W, lmbda, opt=opt, dimK=dimK)
+    r = orc.admm_addmasksim(D, S, W, lmbda, opt=opt, dimK=dimK, grad_mu=grad_mu)
     same(b.cbpdn.Y, r.Y, tag + ' Y')
     same(b.cbpdn.X, r.X, tag + ' X')
     its = b.getitstat()
-    for name, c in (('ObjFun', 1), ('DFid', 2), ('RegL1', 3), ('PrimalRsdl', 4), ('DualRsdl', 5), ('Rho', 8)):
+    o_ = 0 if grad_mu is None else 1
+    for name, c in (('ObjFun', 1), ('DFid', 2), ('RegL1', 3), ('PrimalRsdl', 4 + o_), ('DualRsdl', 5 + o_),
+                    ('Rho', 8 + o_)):
         same(stat(its, name), np.array([row[c] for row in r.itstat], dtype=np.float64), tag + ' ' + name)
     out = dict(D=D, S=S, W=W, lmbda=np.float64(lmbda), Y=b.cbpdn.Y, Xprimary=X, recon=b.reconstruct(),
                Rho=stat(its, 'Rho'), ObjFun=stat(its, 'ObjFun'), DFid=stat(its, 'DFid'),
@@ -208,6 +226,11 @@ def main():
         Wk = (rng.random((32, 32, 3)) > 0.3).astype(dt)
         ams_case('ams_gry_' + sfx, dt, D, S[..., 0], Wm, 0.1, AMS_OPT['ams_gry'])
         ams_case('ams_k3_' + sfx, dt, D, S, Wk, 0.1, AMS_OPT['ams_k3'], dimK=1)
+        gw7 = np.concatenate((np.linspace(0.2, 2.0, 6), [0.0])).astype(dt)
+        ams_case('ams_grd_' + sfx, dt, D, S[..., 0], Wm, 0.1,
+                 dict(AMS_OPT['ams_gry'], GradWeight=gw7, rho=3.0, AutoRho={'Enabled': False}), grad_mu=0.4)
+        admm_case('grd_k3_' + sfx, dt, D, S, 0.1, GRD_OPT['grd_k3'](dt), dimK=1, grad_mu=0.4)
+        admm_case('grd_aux_' + sfx, dt, D, S[..., 0], 0.1, GRD_OPT['grd_aux'](dt), grad_mu=0.2)
         admm_case('enet_k3_' + sfx, dt, D, S, 0.1, {'MaxMainIter': 30, 'RelStopTol': 0.0}, dimK=1,
                   enet_mu=0.3)
         admm_case('enet_c3_' + sfx, dt, D3, S3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0,

@@ -27,7 +27,7 @@ SYMBOLS = (
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
-    'spcsc_pgm_accept', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
+    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
 )
 
@@ -105,6 +105,7 @@ def _declare(lib):
     lib.spcsc_pgm_reset.argtypes = [vp, vp]
     lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
+    lib.spcsc_set_gradreg.argtypes = [vp, vp, vp]
     lib.spcsc_ccmod_reset.argtypes = [vp, vp, i32]
     lib.spcsc_ccmod_setcoef_device.argtypes = [vp, i32]
     lib.spcsc_ccmod_setcoef.argtypes = [vp, vp]
@@ -333,6 +334,15 @@ class Handle(object):
 
     def pgm_accept(self, coef):
         self._c(self.lib.spcsc_pgm_accept(self.h, float(coef)))
+
+    def set_gradreg(self, ghg, wgrd):
+        d = self.dims
+        if ghg is None:
+            self._c(self.lib.spcsc_set_gradreg(self.h, None, None))
+            return
+        ghg = self._host(ghg, (d['N0'], d['N1'] // 2 + 1))
+        wgrd = self._host(wgrd, (d['M'],))
+        self._c(self.lib.spcsc_set_gradreg(self.h, _ptr(ghg), _ptr(wgrd)))
 
     # ---- dictionary update
     def ccmod_reset(self, D0, zero_mean):

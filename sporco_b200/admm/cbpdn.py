@@ -383,6 +383,59 @@ class ConvElasticNet(ConvBPDN):
         super(ConvElasticNet, self).__init__(D, S, lmbda, opt, dimK=dimK, dimN=dimN, device=device)
 
 
+class ConvBPDNGradReg(ConvBPDN):
+    """ADMM solver for convolutional BPDN with an l2 penalty on the gradient of the coefficient
+    maps (mirror of sporco/admm/cbpdn.py:993-1216)::
+
+        argmin_x (1/2) || sum_m d_m * x_m - s ||_2^2 + lambda sum_m || x_m ||_1
+                 + (mu/2) sum_i sum_m w_m || G_i x_m ||_2^2
+
+    The x-step system has the diagonal ``mu w_m GHG + rho`` (linalg.solvedbd_sm) instead of
+    ``rho``; ``IterationStats`` gains ``RegGrad``.  Single-channel dictionaries.
+    """
+
+    class Options(ConvBPDN.Options):
+        defaults = copy.deepcopy(ConvBPDN.Options.defaults)
+        defaults.update({'GradWeight': 1.0})
+
+        def __init__(self, opt=None):
+            ConvBPDN.Options.__init__(self, {} if opt is None else opt)
+
+    itstat_fields_objfn = ('ObjFun', 'DFid', 'RegL1', 'RegGrad')
+    hdrtxt_objfn = ('Fnc', 'DFid', u'Regℓ1', u'Regℓ2∇')
+    hdrval_objfun = {'Fnc': 'ObjFun', 'DFid': 'DFid', u'Regℓ1': 'RegL1', u'Regℓ2∇': 'RegGrad'}
+    _two_reg = True
+
+    def __init__(self, D, S, lmbda=None, mu=0.0, opt=None, dimK=None, dimN=2, device=0):
+        opt = self._coerce_options(opt)
+        self.cri = cr.CSC_ConvRepIndexing(D, S, dimK=dimK, dimN=dimN)
+        if self.cri.Cd != 1:
+            raise NotImplementedError('ConvBPDNGradReg with a multi-channel dictionary is not supported')
+        self.set_dtype(opt, S.dtype)
+        self.mu = self.dtype.type(mu)
+        gw = opt['GradWeight']
+        wm = np.asarray(gw, dtype=self.dtype)
+        if wm.ndim > 1 or (wm.ndim == 1 and wm.size != self.cri.M):
+            raise ValueError('GradWeight must be a scalar or an M-vector')
+        self._wgrd = np.ascontiguousarray(np.broadcast_to(wm, (self.cri.M,)), dtype=self.dtype)
+        self.Wgrd = wm.reshape((1,) * (dimN + 2) + wm.shape) if wm.ndim else wm
+        super(ConvBPDNGradReg, self).__init__(D, S, lmbda, opt, dimK=dimK, dimN=dimN, device=device)
+
+    def _after_open(self):
+        # sum_i |G_i|^2 of the forward-difference filters, as signal.gradient_filters forms it
+        # (signal.py:196-240): transforms of the two 2-tap filters through the device FFT
+        N0, N1 = self.cri.Nv
+        g0 = np.zeros((N0, N1), dtype=self.dtype)
+        g1 = np.zeros((N0, N1), dtype=self.dtype)
+        g0[0, 0], g0[1 % N0, 0] = 1, -1
+        g1[0, 0], g1[0, 1 % N1] = 1, -1
+        gf = _lib.rfft2(np.stack((g0, g1)), device=self._device)
+        self._ghg = np.ascontiguousarray(np.sum((np.conj(gf) * gf).real, axis=0), dtype=self.dtype)
+        self.GHGf = self.Wgrd * self._ghg.reshape(self._ghg.shape + (1, 1, 1))
+        self._h.set_gradreg(self._ghg, self._wgrd)
+        super(ConvBPDNGradReg, self)._after_open()
+
+
 class AddMaskSim(object):
     """Boundary / missing-data masking by additive mask simulation (mirror of
     sporco/admm/cbpdn.py:2287-2485): a wrapper about a :class:`ConvBPDN` (or :class:`ConvElasticNet`)

@@ -32,6 +32,8 @@ constexpr size_t kAccBytes = 16 * sizeof(double) + (size_t)kAccDet * kDetBins * 
 enum { ACC_X2 = 0, ACC_Y2, ACC_U2, ACC_R2, ACC_S2, ACC_L1, ACC_L21, ACC_DFID,
        ACC_AX2, ACC_B2, ACC_AXB2, ACC_PGM_FY, ACC_PGM_F, ACC_PGM_LIN, ACC_PGM_DXY2,
        ACC_PGM_RSDL, ACC_N = 16 };
+// ConvBPDNGradReg (ADMM only, so the PGM slots are free): sum_m w_m GHG |x_m|^2, Hermitian-weighted
+enum { ACC_RGRAD = ACC_PGM_FY };   // (SOLVE 4 writes ACC_PGM_F / _LIN itself)
 
 template <typename T>
 struct AdmmState {
@@ -54,7 +56,7 @@ struct AdmmParams {
     int enet;                            // 1: ConvElasticNet: rows carry RegL2 = ||x||^2 / 2 in the regl21 column
     T enet_mu;                           // its l2 weight: the x-step diagonal is enet_mu + rho
     int ams_m0;                          // AddMaskSim: filters m >= ams_m0 are the appended impulse maps (M: none)
-    int pad2_;
+    int gradreg;                         // 1: ConvBPDNGradReg: DFid = |q|^2 sums without the rho^2 factor, rows carry RegGrad
 };
 
 struct StatRow {
@@ -326,6 +328,7 @@ struct ColArgs {
     int Cx, N1f, MC, nchunk, parts;
     int dfid_on, even_n1, check_on;
     int ntiles;            // k_col2: number of (wf, b) slabs = N1f * nb
+    int gradreg;           // k_col SOLVE 1 / 4: ConvBPDNGradReg (G.im = GHG, sumin[m] = (mu w_m, w_m))
 };
 
 template <typename T, int MAXCD>
@@ -417,7 +420,8 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
     if (SOLVE != 0) {
         // ---- phase A: s_c[h] = sum_m Df_c[m][h] * col[m][h]
         const int parts = a.parts;
-        for (int e = tid; e < Cd * parts * N0; e += nt) spart[e] = mk<T>(0, 0);
+        const int CdS = Cd + ((a.gradreg && SOLVE == 1) ? 1 : 0);     // + gamma pseudo-channel
+        for (int e = tid; e < CdS * parts * N0; e += nt) spart[e] = mk<T>(0, 0);
         __syncthreads();
         for (int ch = 0; ch < a.nchunk; ++ch) {
             const int m0 = ch * MC, mc = (M - m0 < MC) ? M - m0 : MC;
@@ -429,6 +433,39 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
             if (zeta != (T)1) {
                 for (int e = tid; e < mc * N0; e += nt) buf[e] = zeta * buf[e];
                 __syncthreads();
+            }
+            if (a.gradreg && SOLVE == 1) {
+                // diagonal d_m = mu w_m GHG + rho (admm/cbpdn.py:1173-1201, linalg.solvedbd_sm):
+                // sigma = sum_m Df z / d, gamma = sum_m |Df|^2 / d (kept as pseudo-channel 1)
+                for (int e = tid; e < parts * N0; e += nt) {
+                    const int part = e / N0, h = e - part * N0;
+                    const T ghg = G[(size_t)wf * N0 + h].im;
+                    const C2<T>* dfc = Df + ((size_t)wf * M + m0) * N0 + h;
+                    C2<T> s = mk<T>(0, 0);
+                    T gam = 0;
+                    for (int mm = part; mm < mc; mm += parts) {
+                        const C2<T> df = dfc[(size_t)mm * N0];
+                        const T inv = (T)1 / (sumin[m0 + mm].re * ghg + rho);
+                        s = s + inv * (df * buf[(size_t)mm * N0 + h]);
+                        gam += inv * abs2(df);
+                    }
+                    C2<T>* sp = spart + ((size_t)part) * N0 + h;
+                    *sp = *sp + s;
+                    C2<T>* gp = spart + ((size_t)parts + part) * N0 + h;
+                    gp->re += gam;
+                }
+                __syncthreads();
+                continue;
+            }
+            if (a.gradreg && SOLVE == 4) {   // RegGrad of the evaluated spectra (AuxVarObj)
+                const double wg = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+                double rg[1] = {0.0};
+                for (int e = tid; e < mc * N0; e += nt) {
+                    const int mm = e / N0, h = e - mm * N0;
+                    rg[0] += wg * (double)(sumin[m0 + mm].im * G[(size_t)wf * N0 + h].im * abs2(buf[e]));
+                }
+                double* red = reinterpret_cast<double*>(spart + (size_t)Cd * parts * N0);
+                block_accumulate<1>(rg, red, acc + ACC_RGRAD);
             }
             for (int e = tid; e < parts * N0; e += nt) {
                 const int part = e / N0, h = e - part * N0;
@@ -467,7 +504,7 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                         const double e2 = (double)abs2(d[c]);
                         psum[0] += e2;
                         psum[1] += wgt * e2;
-                        if (sumin) {
+                        if (sumin && !a.gradreg) {
                             const C2<T> sy = sumin[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h];
                             const C2<T> dx = s - sy, gy = sy - sf;   // Re(conj(dx) * gy)
                             psum[2] += (double)(dx.re * gy.re + dx.im * gy.im);
@@ -476,7 +513,20 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                 }
             }
             if (SOLVE == 1) {
-                if (Cd == 1) {
+                if (a.gradreg) {
+                    // q = (Sf - rho sigma) / (1 + gamma); then x_m = (rho z_m + conj(Df_m) q) / d_m
+                    // and sum_m Df_m x_m - Sf = -q
+                    T gam = 0;
+                    C2<T> sg = mk<T>(0, 0);
+                    for (int p = 0; p < parts; ++p) {
+                        sg = sg + spart[((size_t)p) * N0 + h];
+                        gam += spart[((size_t)parts + p) * N0 + h].re;
+                    }
+                    const C2<T> sf = Sf[(((size_t)k * a.Cs + cx) * a.N1f + wf) * N0 + h];
+                    const T den = (T)1 + gam;
+                    const C2<T> num = sf - rho * sg;
+                    d[0] = mk<T>(num.re / den, num.im / den);
+                } else if (Cd == 1) {
                     const T g = G[(size_t)wf * N0 + h].re;
                     const T den = g + rho;
                     d[0] = mk<T>(d[0].re / den, d[0].im / den);
@@ -509,7 +559,7 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
         }
         __syncthreads();
         if (SOLVE == 1 && a.dfid_on) {
-            double* red = reinterpret_cast<double*>(spart + (size_t)Cd * parts * N0);
+            double* red = reinterpret_cast<double*>(spart + (size_t)CdS * parts * N0);
             block_accumulate<1>(dsum, red, acc + ACC_DFID);
         }
         if (SOLVE == 2 && sumout) {
@@ -541,7 +591,27 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                 __syncthreads();
             }
         }
-        if (SOLVE == 1 || SOLVE == 2) {
+        if (SOLVE == 1 && a.gradreg) {
+            const int parts = a.parts;
+            const double wg = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+            double rg[1] = {0.0};
+            for (int e = tid; e < mc * N0; e += nt) {
+                const int mm = e / N0, h = e - mm * N0;
+                const T ghg = G[(size_t)wf * N0 + h].im;
+                const C2<T> gwm = sumin[m0 + mm];
+                const T inv = (T)1 / (gwm.re * ghg + rho);
+                const C2<T> df = Df[((size_t)wf * M + m0 + mm) * N0 + h];
+                const C2<T> q = spart[(size_t)h];
+                const C2<T> x = inv * (rho * buf[e] + mulc(q, df));
+                if (a.dfid_on) rg[0] += wg * (double)(gwm.im * ghg * abs2(x));
+                buf[e] = x;
+            }
+            __syncthreads();
+            if (a.dfid_on) {
+                double* red = reinterpret_cast<double*>(spart + (size_t)(Cd + 1) * parts * N0);
+                block_accumulate<1>(rg, red, acc + ACC_RGRAD);
+            }
+        } else if (SOLVE == 1 || SOLVE == 2) {
             const int parts = a.parts;
             for (int e = tid; e < mc * N0; e += nt) {
                 const int mm = e / N0, h = e - mm * N0;
@@ -657,7 +727,8 @@ template <typename T>
 SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* SPCSC_RESTRICT Zf,
                                    const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
                                    const AdmmState<T>* SPCSC_RESTRICT st,
-                                   double* SPCSC_RESTRICT acc, ColArgs a, T l2w) {
+                                   double* SPCSC_RESTRICT acc, ColArgs a, T l2w,
+                                   const C2<T>* SPCSC_RESTRICT G, const C2<T>* SPCSC_RESTRICT gw) {
     // one CTA per (wf, b); thread per h (strided); loops over m twice.  Slow, diagnostic only.
     if (st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
@@ -679,7 +750,9 @@ SPCSC_GLOBAL void k_linsolve_check(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* 
         }
         for (int m = 0; m < M; ++m) {
             const C2<T> x = Xf[slab + (size_t)m * N0 + h], z = Zf[slab + (size_t)m * N0 + h];
-            C2<T> ax = (rho + l2w) * x, bb = rho * z;
+            T dg = rho + l2w;
+            if (a.gradreg) dg = rho + gw[m].re * G[(size_t)wf * N0 + h].im;
+            C2<T> ax = dg * x, bb = rho * z;
             for (int c = 0; c < Cd; ++c) {
                 const C2<T> df = Df[(((size_t)c * a.N1f + wf) * M + m) * N0 + h];
                 ax = ax + mulc(e[c], df);
@@ -758,11 +831,15 @@ SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
         o.xrrs = -1.0;
         if (p.need_obj) {
             const double rho_x = (double)(T)(rho + (p.enet ? p.enet_mu : (T)0));
-            o.dfid = p.dfid_direct ? 0.5 * acc[ACC_DFID] * p.inv_n
-                                   : 0.5 * rho_x * rho_x * acc[ACC_DFID] * p.inv_n;
+            o.dfid = (p.dfid_direct || p.gradreg) ? 0.5 * acc[ACC_DFID] * p.inv_n
+                                                  : 0.5 * rho_x * rho_x * acc[ACC_DFID] * p.inv_n;
             o.regl1 = acc[ACC_L1];
             o.regl21 = acc[ACC_L21];
             o.obj = o.dfid + (double)p.lmbda * o.regl1 + (p.joint ? (double)p.mu * o.regl21 : 0.0);
+            if (p.gradreg) {               // (mu/2) sum_m w_m ||G x_m||^2, taken in the DFT domain
+                o.regl21 = 0.5 * acc[ACC_RGRAD] * p.inv_n;
+                o.obj = o.dfid + ((double)p.lmbda * o.regl1 + (double)p.mu * o.regl21);
+            }
             if (p.enet) {                  // (mu/2)||x||^2 on the objective's variable (X, or Y with AuxVarObj)
                 o.regl21 = 0.5 * acc[p.dfid_direct ? ACC_Y2 : ACC_X2];
                 o.obj = o.dfid + ((double)p.lmbda * o.regl1 + (double)p.enet_mu * o.regl21);
@@ -873,6 +950,14 @@ SPCSC_GLOBAL void k_pad_dict(const T* SPCSC_RESTRICT D, T* SPCSC_RESTRICT Dp, in
         const int m = (int)((i / ((size_t)N1 * N0)) % M), c = (int)(i / ((size_t)N1 * N0 * M));
         Dp[i] = (y < hd && x < wd) ? D[(((size_t)y * wd + x) * Cd + c) * M + m] : (T)0;
     }
+}
+
+// ConvBPDNGradReg: GHG[wf][h] rides in the (otherwise zero) imaginary part of the Cd = 1 Gram table.
+template <typename T>
+SPCSC_GLOBAL void k_set_ghg(C2<T>* SPCSC_RESTRICT G, const T* SPCSC_RESTRICT ghg, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        G[i].im = ghg[i];
 }
 
 // Gram of the dictionary per frequency: G[wf][h][c][c'] = sum_m Df_c[m] conj(Df_c'[m]).

@@ -81,7 +81,7 @@ inline void col_plan(ColArgs& a, int& nthreads, size_t& smem) {
     if (parts > 8) parts = 8;
     if (parts > a.M) parts = a.M;
     a.parts = parts;
-    const size_t fixed = (size_t)a.Cd * parts * N0 * sz + 64 * sizeof(double);
+    const size_t fixed = (size_t)(a.Cd + (a.gradreg ? 1 : 0)) * parts * N0 * sz + 64 * sizeof(double);
     size_t room = kSmemLimit - fixed;
     int mc = (int)(room / ((size_t)N0 * sz * (GEN ? 2 : 1)));
     if (mc > a.M) mc = a.M;

@@ -291,6 +291,7 @@ struct spcsc_handle {
     virtual int reconstruct(const void* X, void* out) = 0;
     virtual int synchronize() = 0;
     virtual int attach_comm(spcsc_comm* c, double global_nx) = 0;
+    virtual int set_gradreg(const void* ghg, const void* wgrd) = 0;
     virtual int pgm_configure(const spcsc_pgm_opts* o) = 0;
     virtual int pgm_reset(const void* X0) = 0;
     virtual int pgm_trial(double L, double* out) = 0;
@@ -372,6 +373,10 @@ class Engine : public spcsc_handle {
     spcsc_pgm_opts popts;
     DevBuf<T> cdX;                                  // CCMOD: dictionary iterate, real [Cd][M][N0][N1]
     DevBuf<C2<T>> cdXf, cdYf, cdV, cdG;             // its spectrum, the momentum point, scratch, gradient
+    DevBuf<T> ghg_buf;                              // ConvBPDNGradReg: GHG in device order [N1f][N0]
+    DevBuf<C2<T>> gw_buf;                           //   per filter (mu w_m, w_m)
+    std::vector<T> gr_w;                            //   host copy of w_m (mu arrives with admm_configure)
+    bool gradreg = false;
     DevBuf<C2<T>> cdZf;                             // coefficient spectra, slab layout [K][N1f][M][N0]
     bool cd_ready = false, cd_have_coef = false;
     int cd_zero_mean = 0;
@@ -418,7 +423,7 @@ class Engine : public spcsc_handle {
         acc.release(); st.release(); rows.release();
         stw_row1.release(); stw_rowc.release(); stw_col.release();
         pgA.release(); pgB.release(); Zt2.release();
-        cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release();
+        cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -533,6 +538,7 @@ class Engine : public spcsc_handle {
         int rc = forward2d(tmp_real.p, Df.p, M, Cd);
         if (rc) return rc;
         CK(launch(k_gram<T>, dim3(256), dim3(128), 0, stream, (const C2<T>*)Df.p, G.p, N1f, N0, M, Cd));
+        { int rg = install_ghg(); if (rg) return rg; }
         CK(cudaStreamSynchronize(stream));
         have_dict = true;
         return SPCSC_OK;
@@ -600,6 +606,30 @@ class Engine : public spcsc_handle {
         return set_weight(wl21_buf, wl21, w, d);
     }
 
+    int install_ghg() {
+        if (!gradreg) return SPCSC_OK;
+        CK(launch(k_set_ghg<T>, dim3(128), dim3(256), 0, stream, G.p, (const T*)ghg_buf.p, (size_t)N1f * N0));
+        return SPCSC_OK;
+    }
+    int set_gradreg(const void* ghg, const void* wgrd) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!ghg) { gradreg = false; return SPCSC_OK; }
+        if (Cd != 1) FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with a multi-channel dictionary");
+        if (!wgrd) FAIL(SPCSC_ERR_INVALID, "wgrd is NULL");
+        CK(cudaSetDevice(pb.device));
+        const T* g = (const T*)ghg;
+        std::vector<T> t((size_t)N1f * N0);                 // (N0, N1f) -> [N1f][N0]
+        for (int h = 0; h < N0; ++h)
+            for (int wf = 0; wf < N1f; ++wf) t[(size_t)wf * N0 + h] = g[(size_t)h * N1f + wf];
+        CK(ghg_buf.ensure(t.size()));
+        CK(cudaMemcpyAsync(ghg_buf.p, t.data(), t.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        gr_w.assign((const T*)wgrd, (const T*)wgrd + M);
+        gradreg = true;
+        if (have_dict) return install_ghg();
+        return SPCSC_OK;
+    }
+
     int admm_configure(const spcsc_admm_opts* o) override {
         if (Cx > 4) FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 coefficient channels");
         if (Cd > 4) FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 dictionary channels");
@@ -627,7 +657,15 @@ class Engine : public spcsc_handle {
         prm.enet = (o->l2_weight != 0.0) ? 1 : 0;
         prm.enet_mu = (T)o->l2_weight;
         prm.ams_m0 = M - (o->ams_maps > 0 ? o->ams_maps : 0);
-        prm.pad2_ = 0;
+        prm.gradreg = gradreg ? 1 : 0;
+        if (gradreg) {
+            if (o->joint || o->l2_weight != 0.0) FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with the joint or l2 penalty");
+            std::vector<C2<T>> gw(M);
+            for (int m = 0; m < M; ++m) gw[m] = mk<T>((T)o->mu * gr_w[m], gr_w[m]);
+            CK(gw_buf.ensure(M));
+            CK(cudaMemcpyAsync(gw_buf.p, gw.data(), M * sizeof(C2<T>), cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
         if (o->ams_maps < 0 || o->ams_maps >= M) FAIL(SPCSC_ERR_INVALID, "ams_maps out of range");
         if (o->ams_maps > 0 && o->joint) FAIL(SPCSC_ERR_UNSUPPORTED, "AddMaskSim with the joint penalty");
         prm.linsolve_check = o->linsolve_check;
@@ -709,6 +747,8 @@ class Engine : public spcsc_handle {
         cs.st = st.p;
         cs.acc = acc.p;
         cs.Lstep = prm.enet ? prm.enet_mu : (T)0;        // SOLVE 1 reads the elastic-net weight here
+        cs.a.gradreg = prm.gradreg;
+        if (prm.gradreg) cs.sumin = gw_buf.p;
         cs.a.dfid_on = (prm.need_obj && !prm.dfid_direct) ? 1 : 0;
         const bool aux_eval = prm.need_obj && prm.dfid_direct;
         if (aux_eval) CK(Zscratch.ensure(nslab));
@@ -734,7 +774,7 @@ class Engine : public spcsc_handle {
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (!check) {
                 cs.in = zin; cs.out = zin;
-                if (v2_col && !prm.enet)         // the l2 term is handled by the general kernel only
+                if (v2_col && !prm.enet && !prm.gradreg)   // l2 / gradient terms: general kernel only
                     CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
                 else
                     CK(col<T>(N0, COL_ADMM, cs));
@@ -749,7 +789,8 @@ class Engine : public spcsc_handle {
                 ColArgs ca = c2.a;
                 CK(launch(k_linsolve_check<T>, dim3(N1f, K * Cx), dim3(128), 3 * 32 * sizeof(double), stream,
                           (const C2<T>*)Xscratch.p, (const C2<T>*)Zscratch.p, (const C2<T>*)Df.p,
-                          (const C2<T>*)Sf.p, (const AdmmState<T>*)st.p, acc.p, ca, cs.Lstep));
+                          (const C2<T>*)Sf.p, (const AdmmState<T>*)st.p, acc.p, ca, cs.Lstep,
+                          (const C2<T>*)G.p, (const C2<T>*)gw_buf.p));
                 ColLaunch<T> c3 = cs;
                 c3.in = Xscratch.p; c3.out = zin;
                 CK(col<T>(N0, COL_INV, c3));
@@ -770,6 +811,8 @@ class Engine : public spcsc_handle {
                               (const AdmmState<T>*)st.p, Zscratch.p));
                 ColLaunch<T> ce = colargs(M, K * Cx);
                 ce.in = Zscratch.p; ce.out = nullptr; ce.acc = acc.p; ce.st = st.p;
+                ce.a.gradreg = prm.gradreg;
+                if (prm.gradreg) ce.sumin = gw_buf.p;
                 CK(col<T>(N0, COL_FWD_EVAL, ce));
                 last_launches += 2;
             }
@@ -1150,6 +1193,7 @@ class Engine : public spcsc_handle {
         const size_t nsp = (size_t)Cd * N1f * M * N0;
         CK(cudaMemcpyAsync(Df.p, cdXf.p, nsp * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
         CK(launch(k_gram<T>, dim3(256), dim3(128), 0, stream, (const C2<T>*)Df.p, G.p, N1f, N0, M, Cd));
+        { int rg = install_ghg(); if (rg) return rg; }
         have_dict = true;
         return SPCSC_OK;
     }
@@ -1392,6 +1436,7 @@ int spcsc_pgm_configure(spcsc_handle* h, const spcsc_pgm_opts* o) { H_CALL(o ? h
 int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0)); }
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
 int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
+int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd) { H_CALL(h->set_gradreg(ghg, wgrd)); }
 int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ? h->ccmod_reset(D0, zm) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source) { H_CALL(h->ccmod_setcoef_device(source)); }
 int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z) { H_CALL(Z ? h->ccmod_setcoef(Z) : SPCSC_ERR_INVALID); }

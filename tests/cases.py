@@ -42,7 +42,18 @@ ADMM_CASES = {
     # ConvElasticNet (third field 'enet'): single- and multi-channel dictionary
     'enet_k3': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, 1, 'enet', 'auto'),
     'enet_c3': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'AuxVarObj': True}, None, 'enet', 'auto'),
+    # ConvBPDNGradReg (third field 'grd'; GradWeight filled in by _grd_opt)
+    'grd_k3': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, 1, 'grd', 'auto'),
+    'grd_aux': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'AuxVarObj': True, 'LinSolveCheck': True,
+                 'GradWeight': 'linspace'}, None, 'grd', 'auto'),
 }
+
+
+def grd_opt(opt, dtype):
+    o = dict(opt)
+    if isinstance(o.get('GradWeight'), str):
+        o['GradWeight'] = np.linspace(0.2, 2.0, 6).astype(dtype)
+    return o
 
 
 def run_admm_case(tag, sfx):
@@ -53,9 +64,12 @@ def run_admm_case(tag, sfx):
     opt, dimK, joint, kind = ADMM_CASES[tag]
     tol = TOL[(sfx, kind)]
     D, S = g['D'], g['S']
-    enet = joint == 'enet'
+    enet, grd = joint == 'enet', joint == 'grd'
     joint = joint is True
-    if enet:
+    if grd:
+        b = cbpdn.ConvBPDNGradReg(D, S, float(g['lmbda']), float(g['mu']),
+                                  cbpdn.ConvBPDNGradReg.Options(grd_opt(opt, D.dtype)), dimK=dimK)
+    elif enet:
         b = cbpdn.ConvElasticNet(D, S, float(g['lmbda']), float(g['mu']),
                                  cbpdn.ConvBPDN.Options(opt), dimK=dimK)
     elif joint:
@@ -82,6 +96,10 @@ def run_admm_case(tag, sfx):
         assert rel(its.RegL21, g['RegL21']) <= 10 * stol
     if enet:
         assert rel(its.RegL2, g['RegL2']) <= 10 * stol
+    if grd:
+        assert rel(its.RegGrad, g['RegGrad']) <= 10 * stol
+        if opt.get('LinSolveCheck'):
+            assert max(its.XSlvRelRes) < (1e-10 if sfx == 'f64' else 1e-4)
     assert rel(b.reconstruct().reshape(g['recon'].shape), g['recon']) <= 4 * tol
     return b
 
@@ -437,6 +455,8 @@ def run_long_determinism_case(iters=400, K=8):
 
 
 AMS_CASES = {'ams_gry': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, None),
+             'ams_grd': ({'MaxMainIter': 30, 'RelStopTol': 0.0, 'rho': 3.0, 'AutoRho': {'Enabled': False},
+                          'GradWeight': 'ams7'}, None),
              'ams_k3': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True,
                          'AuxVarObj': True}, 1)}
 
@@ -447,8 +467,13 @@ def run_ams_case(tag, sfx):
     g = load('%s_%s' % (tag, sfx))
     opt, dimK = AMS_CASES[tag]
     tol = TOL[(sfx, 'auto')]
-    b = cbpdn.AddMaskSim(cbpdn.ConvBPDN, g['D'], g['S'], g['W'], float(g['lmbda']),
-                         cbpdn.ConvBPDN.Options(opt), dimK=dimK)
+    if tag == 'ams_grd':
+        o = dict(opt, GradWeight=np.concatenate((np.linspace(0.2, 2.0, 6), [0.0])).astype(g['D'].dtype))
+        b = cbpdn.AddMaskSim(cbpdn.ConvBPDNGradReg, g['D'], g['S'], g['W'], float(g['lmbda']), 0.4,
+                             cbpdn.ConvBPDNGradReg.Options(o), dimK=dimK)
+    else:
+        b = cbpdn.AddMaskSim(cbpdn.ConvBPDN, g['D'], g['S'], g['W'], float(g['lmbda']),
+                             cbpdn.ConvBPDN.Options(opt), dimK=dimK)
     X = b.solve()
     its = b.getitstat()
     assert X.shape == g['Xprimary'].shape and rel(X, g['Xprimary']) <= 4 * tol

@@ -19,15 +19,18 @@ REF = '/root/reference'
 def test_oracle_reproduces_golden_admm(tag, sfx):
     g = cases.load('%s_%s' % (tag, sfx))
     opt, dimK, joint, _ = cases.ADMM_CASES[tag]
-    enet = joint == 'enet'
+    enet, grd = joint == 'enet', joint == 'grd'
     joint = joint is True
+    if grd:
+        opt = cases.grd_opt(opt, g['D'].dtype)
     r = orc.admm_convbpdn(g['D'], g['S'], float(g['lmbda']),
                           mu=float(g['mu']) if joint else None, opt=opt, dimK=dimK,
-                          enet_mu=float(g['mu']) if enet else None)
+                          enet_mu=float(g['mu']) if enet else None,
+                          grad_mu=float(g['mu']) if grd else None)
     assert np.array_equal(r.Y, g['Y'])
     assert np.array_equal(r.U, g['U'])
     assert np.array_equal(r.X, g['X'])
-    rho_col = 9 if (joint or enet) else 8
+    rho_col = 9 if (joint or enet or grd) else 8
     assert np.array_equal(np.array([row[rho_col] for row in r.itstat], dtype=np.float64), g['Rho'])
     assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
 
@@ -66,10 +69,14 @@ def test_oracle_reproduces_golden_dictionary_learning(tag, sfx):
 def test_oracle_reproduces_golden_addmasksim(tag, sfx):
     g = cases.load('%s_%s' % (tag, sfx))
     opt, dimK = cases.AMS_CASES[tag]
-    r = orc.admm_addmasksim(g['D'], g['S'], g['W'], float(g['lmbda']), opt=opt, dimK=dimK)
+    gm = None
+    if tag == 'ams_grd':
+        gm = 0.4
+        opt = dict(opt, GradWeight=np.concatenate((np.linspace(0.2, 2.0, 6), [0.0])).astype(g['D'].dtype))
+    r = orc.admm_addmasksim(g['D'], g['S'], g['W'], float(g['lmbda']), opt=opt, dimK=dimK, grad_mu=gm)
     assert np.array_equal(r.Y, g['Y'])
     assert np.array_equal(np.array([row[1] for row in r.itstat], dtype=np.float64), g['ObjFun'])
-    assert np.array_equal(np.array([row[8] for row in r.itstat], dtype=np.float64), g['Rho'])
+    assert np.array_equal(np.array([row[9 if gm else 8] for row in r.itstat], dtype=np.float64), g['Rho'])
 
 
 def test_oracle_level1_known_answers():

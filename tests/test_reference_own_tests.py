@@ -1,6 +1,6 @@
 """Drop-in check in the build container: the REFERENCE'S OWN test files
 (/root/reference/tests/admm/test_cbpdn.py, /root/reference/tests/pgm/test_cbpdn.py) executed
-unmodified, with `sporco.admm.cbpdn.{GenericConvBPDN,ConvBPDN,ConvBPDNJoint,ConvElasticNet,AddMaskSim}` and
+unmodified, with `sporco.admm.cbpdn.{GenericConvBPDN,ConvBPDN,ConvBPDNJoint,ConvElasticNet,ConvBPDNGradReg,AddMaskSim}` and
 `sporco.pgm.cbpdn.ConvBPDN` replaced by the sporco_b200 classes (kernels run through the CPU
 emulation harness here; the same replacement works on a GPU box where the reference is
 installed).  Tests of other reference classes in those files are left alone; tests that need
@@ -21,7 +21,7 @@ from sporco_b200 import _lib
 REF = '/root/reference'
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
 
-OTHER_CLASSES = ('ConvBPDNGradReg', 'ConvBPDNProjL1', 'ConvMinL1InL2Ball',
+OTHER_CLASSES = ('ConvBPDNProjL1', 'ConvMinL1InL2Ball',
                  'ConvBPDNMaskDcpl', 'ConvL1L1Grd', 'MultiDictConvBPDN',
                  'ConvBPDNMask', 'ConvTwoBlockCnstrnt')
 # reference tests that exercise the replaced classes but need something not implemented
@@ -44,7 +44,8 @@ def _load(kind):
     proxy = types.ModuleType('cbpdn_proxy')
     if kind == 'admm':
         proxy.__dict__.update(ref_admm.__dict__)
-        for name in ('GenericConvBPDN', 'ConvBPDN', 'ConvBPDNJoint', 'ConvElasticNet', 'AddMaskSim'):
+        for name in ('GenericConvBPDN', 'ConvBPDN', 'ConvBPDNJoint', 'ConvElasticNet', 'ConvBPDNGradReg',
+                     'AddMaskSim'):
             setattr(proxy, name, getattr(my_admm, name))
         path = os.path.join(REF, 'tests', 'admm', 'test_cbpdn.py')
     else:
