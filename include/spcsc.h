@@ -238,6 +238,12 @@ int spcsc_rfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_
 int spcsc_irfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1,
                  const void* xf, void* x);
 
+/* sporco.signal.tikhonov_filter (signal.py:244-303), the highpass pre-processing step of the example
+   scripts: every image of s (batch, N0, N1) is padded symmetrically by npd, lowpass filtered by solving
+   (I + lmbda (Gr^T Gr + Gc^T Gc)) x = s in the DFT domain, cropped; sl = lowpass, sh = s - sl. */
+int spcsc_tikhonov_filter(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1,
+                          double lmbda, int32_t npd, const void* s, void* sl, void* sh);
+
 #ifdef __cplusplus
 }
 #endif

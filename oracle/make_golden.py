@@ -180,6 +180,27 @@ def cdl_ref_case(tag, dt, D0, S, lmbda, opt, xmethod):
     print('wrote', tag, sorted(out))
 
 
+def tikhonov():
+    """sporco.signal.tikhonov_filter on a few shapes (padded sizes: power of two, composite, odd)."""
+    from sporco import signal as rsignal
+    from oracle import signal_oracle as sorc
+    rng = np.random.default_rng(11)
+    out = {}
+    for dt, sfx in ((np.float64, 'f64'), (np.float32, 'f32')):
+        for i, (shape, lm, npd) in enumerate((((32, 32), 5.0, 16), ((40, 36, 3), 2.0, 16),
+                                              ((31, 33, 2, 2), 10.0, 8))):
+            s = rng.standard_normal(shape).astype(dt)
+            sl, sh = rsignal.tikhonov_filter(s, lm, npd)
+            ol, oh = sorc.tikhonov_filter(s, lm, npd)
+            same(sl, ol, 'tikhonov sl')
+            same(sh, oh, 'tikhonov sh')
+            out['s%d_%s' % (i, sfx)] = s
+            out['sl%d_%s' % (i, sfx)] = sl
+            out['sh%d_%s' % (i, sfx)] = sh
+    np.savez_compressed(os.path.join(OUT, 'tikhonov.npz'), **out)
+    print('wrote tikhonov')
+
+
 def level1():
     """Known-answer vectors for the level-1 functions from the reference itself."""
     rng = np.random.default_rng(7)
@@ -208,6 +229,7 @@ def level1():
 def main():
     os.makedirs(OUT, exist_ok=True)
     level1()
+    tikhonov()
     for dt, sfx in ((np.float64, 'f64'), (np.float32, 'f32')):
         rng = np.random.default_rng(12345)
         D = rng.standard_normal((5, 5, 6)).astype(dt)

@@ -27,7 +27,7 @@ SYMBOLS = (
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
-    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
+    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
 )
 
@@ -106,6 +106,7 @@ def _declare(lib):
     lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
     lib.spcsc_set_gradreg.argtypes = [vp, vp, vp]
+    lib.spcsc_tikhonov_filter.argtypes = [i32, i32, i32, i32, i32, ctypes.c_double, i32, vp, vp, vp]
     lib.spcsc_ccmod_reset.argtypes = [vp, vp, i32]
     lib.spcsc_ccmod_setcoef_device.argtypes = [vp, i32]
     lib.spcsc_ccmod_setcoef.argtypes = [vp, vp]
@@ -418,6 +419,18 @@ def rfft2(x, device=0):
     out = np.empty((b, n0, n1 // 2 + 1), dtype=cdt)
     check(lib.spcsc_rfft2(dtype_code(x.dtype), device, b, n0, n1, _ptr(x), _ptr(out)))
     return out
+
+
+def tikhonov_filter(x, lmbda, npd, device=0):
+    """Lowpass / highpass split of a (batch, N0, N1) real array on the GPU."""
+    lib = load()
+    x = np.ascontiguousarray(x)
+    b, n0, n1 = x.shape
+    sl = np.empty_like(x)
+    sh = np.empty_like(x)
+    check(lib.spcsc_tikhonov_filter(dtype_code(x.dtype), device, b, n0, n1, float(lmbda), int(npd),
+                                    _ptr(x), _ptr(sl), _ptr(sh)))
+    return sl, sh
 
 
 def irfft2(xf, n1, device=0):

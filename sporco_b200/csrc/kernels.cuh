@@ -952,6 +952,53 @@ SPCSC_GLOBAL void k_pad_dict(const T* SPCSC_RESTRICT D, T* SPCSC_RESTRICT Dp, in
     }
 }
 
+// ---- sporco.signal.tikhonov_filter (signal.py:244-303) ------------------------------------
+// symmetric padding by npd on every side of each image: index -1 -> 0, N -> N-1 (numpy 'symmetric')
+template <typename T>
+SPCSC_GLOBAL void k_pad_symmetric(const T* SPCSC_RESTRICT in, T* SPCSC_RESTRICT out, int batch, int N0,
+                                  int N1, int npd) {
+    const int P0 = N0 + 2 * npd, P1 = N1 + 2 * npd;
+    const size_t n = (size_t)batch * P0 * P1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % P1), y = (int)((i / P1) % P0), b = (int)(i / ((size_t)P0 * P1));
+        int sy = y - npd, sx = x - npd;
+        sy = sy < 0 ? -sy - 1 : (sy >= N0 ? 2 * N0 - 1 - sy : sy);
+        sx = sx < 0 ? -sx - 1 : (sx >= N1 ? 2 * N1 - 1 - sx : sx);
+        out[i] = in[((size_t)b * N0 + sy) * N1 + sx];
+    }
+}
+// slab spectra [batch][N1f][N0] divided by A = 1 + lmbda |Gr|^2 + lmbda |Gc|^2, the transfer function of
+// I + lmbda (Gr^T Gr + Gc^T Gc) for the periodic forward differences: |G(f)|^2 = 2 - 2 cos(2 pi f / N)
+template <typename T>
+SPCSC_GLOBAL void k_tikhonov_divide(C2<T>* SPCSC_RESTRICT Z, int batch, int N1f, int N0, int N1, T lmbda) {
+    const size_t n = (size_t)batch * N1f * N0;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % N0), wf = (int)((i / N0) % N1f);
+        const double gr = 2.0 - 2.0 * cos(two_pi * (double)h / (double)N0);
+        const double gc = 2.0 - 2.0 * cos(two_pi * (double)wf / (double)N1);
+        const T a = (T)1 + lmbda * (T)gr + lmbda * (T)gc;
+        Z[i] = mk<T>(Z[i].re / a, Z[i].im / a);
+    }
+}
+// sl = centre crop of the filtered padded image; sh = s - sl
+template <typename T>
+SPCSC_GLOBAL void k_crop_split(const T* SPCSC_RESTRICT padded, const T* SPCSC_RESTRICT s,
+                               T* SPCSC_RESTRICT sl, T* SPCSC_RESTRICT sh, int batch, int N0, int N1,
+                               int npd) {
+    const int P0 = N0 + 2 * npd, P1 = N1 + 2 * npd;
+    const size_t n = (size_t)batch * N0 * N1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % N1), y = (int)((i / N1) % N0), b = (int)(i / ((size_t)N0 * N1));
+        const T l = padded[((size_t)b * P0 + y + npd) * P1 + x + npd];
+        sl[i] = l;
+        sh[i] = s[i] - l;
+    }
+}
+
 // ConvBPDNGradReg: GHG[wf][h] rides in the (otherwise zero) imaginary part of the Cd = 1 Gram table.
 template <typename T>
 SPCSC_GLOBAL void k_set_ghg(C2<T>* SPCSC_RESTRICT G, const T* SPCSC_RESTRICT ghg, size_t n) {

@@ -1351,6 +1351,48 @@ int unit_fft2(bool inverse, int device, int batch, int N0, int N1, const void* i
     return SPCSC_OK;
 }
 
+template <typename T>
+int unit_tikhonov(int device, int batch, int N0, int N1, double lmbda, int npd, const void* in,
+                  void* sl, void* sh, std::string& err) {
+    if (npd < 0 || npd > N0 || npd > N1) { err = "npd must lie in [0, min(N0, N1)]"; return SPCSC_ERR_INVALID; }
+    const int P0 = N0 + 2 * npd, P1 = N1 + 2 * npd;
+    spcsc_problem p;
+    memset(&p, 0, sizeof(p));
+    p.N0 = P0; p.N1 = P1; p.C = 1; p.Cd = 1; p.K = batch; p.M = 1; p.hd = 1; p.wd = 1;
+    p.dtype = sizeof(T) == 4 ? SPCSC_F32 : SPCSC_F64;
+    p.device = device;
+    int rc = check_problem(&p, err);
+    if (rc) return rc;
+    Engine<T> e(p);
+    rc = e.init();
+    if (rc) { err = e.err; return rc; }
+    const size_t nr = (size_t)batch * N0 * N1, np_ = (size_t)batch * P0 * P1;
+    DevBuf<T> s_in, s_lo, s_hi;
+#define UCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); s_in.release(); s_lo.release(); s_hi.release(); return SPCSC_ERR_CUDA; } } while (0)
+    UCK(s_in.ensure(nr)); UCK(s_lo.ensure(nr)); UCK(s_hi.ensure(nr));
+    UCK(e.tmp_real.ensure(np_));
+    UCK(cudaMemcpyAsync(s_in.p, in, nr * sizeof(T), cudaMemcpyHostToDevice, e.stream));
+    UCK(launch(k_pad_symmetric<T>, dim3(592), dim3(256), 0, e.stream, (const T*)s_in.p, e.tmp_real.p, batch,
+               N0, N1, npd));
+    rc = e.forward2d(e.tmp_real.p, e.Zt.p, 1, batch);
+    if (rc) { err = e.err; s_in.release(); s_lo.release(); s_hi.release(); return rc; }
+    UCK(launch(k_tikhonov_divide<T>, dim3(592), dim3(256), 0, e.stream, e.Zt.p, batch, P1 / 2 + 1, P0, P1,
+               (T)lmbda));
+    ColLaunch<T> c = e.colargs(1, batch);
+    c.in = e.Zt.p; c.out = e.Zt.p; c.a.Cd = 1;
+    UCK(col<T>(P0, COL_INV, c));
+    UCK(row_inv<T>(P1 / 2, e.rowargs(1, batch, 1), (const C2<T>*)e.Zt.p, e.tmp_real.p,
+                   (T)(1.0 / ((double)P0 * (double)P1))));
+    UCK(launch(k_crop_split<T>, dim3(592), dim3(256), 0, e.stream, (const T*)e.tmp_real.p, (const T*)s_in.p,
+               s_lo.p, s_hi.p, batch, N0, N1, npd));
+    UCK(cudaMemcpyAsync(sl, s_lo.p, nr * sizeof(T), cudaMemcpyDeviceToHost, e.stream));
+    UCK(cudaMemcpyAsync(sh, s_hi.p, nr * sizeof(T), cudaMemcpyDeviceToHost, e.stream));
+    UCK(cudaStreamSynchronize(e.stream));
+#undef UCK
+    s_in.release(); s_lo.release(); s_hi.release();
+    return SPCSC_OK;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -1532,6 +1574,13 @@ int spcsc_rfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_
     if (!x || !xf || batch < 1) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
     return dtype == SPCSC_F32 ? unit_fft2<float>(false, device, batch, N0, N1, x, xf, g_last_error)
                               : unit_fft2<double>(false, device, batch, N0, N1, x, xf, g_last_error);
+}
+int spcsc_tikhonov_filter(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1, double lmbda,
+                          int32_t npd, const void* s, void* sl, void* sh) {
+    if (!s || !sl || !sh || batch < 1) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
+    return dtype == SPCSC_F32
+               ? unit_tikhonov<float>(device, batch, N0, N1, lmbda, npd, s, sl, sh, g_last_error)
+               : unit_tikhonov<double>(device, batch, N0, N1, lmbda, npd, s, sl, sh, g_last_error);
 }
 int spcsc_irfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1, const void* xf,
                  void* x) {

@@ -486,3 +486,20 @@ def run_ams_case(tag, sfx):
     assert rel(b.reconstruct().reshape(g['recon'].shape), g['recon']) <= 4 * tol
     assert b.getcoef().shape == X.shape
     return b
+
+
+TIKHONOV_CASES = (((32, 32), 5.0, 16), ((40, 36, 3), 2.0, 16), ((31, 33, 2, 2), 10.0, 8))
+
+
+def run_tikhonov_cases():
+    """sporco_b200.signal.tikhonov_filter against the reference's outputs."""
+    from sporco_b200 import signal
+    g = load('tikhonov')
+    for sfx, tol in (('f64', 1e-12), ('f32', 2e-6)):
+        for i, (shape, lm, npd) in enumerate(TIKHONOV_CASES):
+            s = g['s%d_%s' % (i, sfx)]
+            sl, sh = signal.tikhonov_filter(s, lm, npd)
+            assert sl.shape == s.shape and sl.dtype == s.dtype and sh.dtype == s.dtype
+            assert rel(sl, g['sl%d_%s' % (i, sfx)]) < tol, (sfx, i, rel(sl, g['sl%d_%s' % (i, sfx)]))
+            assert rel(sh, g['sh%d_%s' % (i, sfx)]) < 10 * tol
+            assert np.allclose(sl + sh, s, atol=1e-6 if sfx == 'f32' else 1e-14)

@@ -79,6 +79,15 @@ def test_oracle_reproduces_golden_addmasksim(tag, sfx):
     assert np.array_equal(np.array([row[9 if gm else 8] for row in r.itstat], dtype=np.float64), g['Rho'])
 
 
+def test_oracle_reproduces_golden_tikhonov():
+    from oracle import signal_oracle as sorc
+    g = cases.load('tikhonov')
+    for sfx in ('f64', 'f32'):
+        for i, (shape, lm, npd) in enumerate(cases.TIKHONOV_CASES):
+            sl, sh = sorc.tikhonov_filter(g['s%d_%s' % (i, sfx)], lm, npd)
+            assert np.array_equal(sl, g['sl%d_%s' % (i, sfx)]) and np.array_equal(sh, g['sh%d_%s' % (i, sfx)])
+
+
 def test_oracle_level1_known_answers():
     g = cases.load('level1')
     assert np.array_equal(orc.solvedbi_sm(g['ah'], 0.7, g['b'], 4), g['x'])

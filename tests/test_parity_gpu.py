@@ -209,3 +209,7 @@ def test_ccmod_standalone(dt):
 @pytest.mark.parametrize('tag', sorted(cases.AMS_CASES))
 def test_additive_mask_simulation_golden(tag, sfx):
     cases.run_ams_case(tag, sfx)
+
+
+def test_tikhonov_filter_golden():
+    cases.run_tikhonov_cases()
