@@ -172,6 +172,11 @@ int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]);
 /* Accept the candidate and take the momentum step Yf = Xf + coef (Xf - Xfprv)  (PGMDFT.ystep). */
 int spcsc_pgm_accept(spcsc_handle* h, double coef);
 
+/* pgm.cbpdn.ConvBPDNMask (pgm/cbpdn.py:387-508): data fidelity (1/2)||W (sum_m d_m * x_m - s)||^2.  W: real,
+   shape[4] = (N0|1, N1|1, C|1, K|1) broadcast against the signal; NULL switches the mask off.  Affects the
+   spcsc_pgm_* calls only.  Single-channel dictionary. */
+int spcsc_pgm_set_mask(spcsc_handle* h, const void* W, const int64_t shape[4]);
+
 /* ConvBPDNGradReg (admm/cbpdn.py:993-1216): gradient regulariser (mu/2) sum_m w_m ||G x_m||^2 with weight
    `mu` = spcsc_admm_opts.mu.  ghg: (N0, N1f) real, sum_i |G_i|^2 as signal.gradient_filters returns it;
    wgrd: M reals (GradWeight).  The x-step solves with the diagonal mu w_m ghg + rho (linalg.solvedbd_sm);

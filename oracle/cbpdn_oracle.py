@@ -542,8 +542,9 @@ PGM_DEFAULTS = {
 }
 
 
-def pgm_convbpdn(D, S, lmbda=None, opt=None, dimK=None, fft=None, timing=None):
-    """FISTA ConvBPDN with Nesterov momentum and optional standard backtracking."""
+def pgm_convbpdn(D, S, lmbda=None, opt=None, dimK=None, fft=None, timing=None, W=None):
+    """FISTA ConvBPDN with Nesterov momentum and optional standard backtracking; with `W` the
+    masked data fidelity of pgm.cbpdn.ConvBPDNMask (pgm/cbpdn.py:387-508)."""
     fft = fft or FFTBackend()
     o = _merge(PGM_DEFAULTS, opt)
     dims = Dims(D, S, dimK=dimK)
@@ -573,14 +574,32 @@ def pgm_convbpdn(D, S, lmbda=None, opt=None, dimK=None, fft=None, timing=None):
     def eval_Rf(Vf):
         return inner(Df, Vf, axM) - Sf
 
+    if W is not None:
+        W5 = np.asarray(W.reshape(msk_shape(W, dims)), dtype=dtype)
+
     def grad_f(Vf):
-        g = np.conj(Df) * eval_Rf(Vf)
+        if W is None:
+            g = np.conj(Df) * eval_Rf(Vf)
+        else:                                            # pgm/cbpdn.py:461-474
+            Ry = fft.irfftn(eval_Rf(Vf), dims.Nv, axN)
+            WRyf = fft.rfftn((W5 ** 2) * Ry, dims.Nv, axN)
+            g = np.conj(Df) * WRyf
         if dims.Cd > 1:
             g = np.sum(g, axis=axC, keepdims=True)
         return g
 
     def obfn_f(Vf):
-        return 0.5 * np.linalg.norm(eval_Rf(Vf).flatten(), 2) ** 2
+        if W is None:
+            return 0.5 * np.linalg.norm(eval_Rf(Vf).flatten(), 2) ** 2
+        R = fft.irfftn(eval_Rf(Vf), dims.Nv, axN)        # pgm/cbpdn.py:490-506
+        WRf = fft.rfftn(W5 * R, dims.Nv, axN)
+        return 0.5 * np.linalg.norm(WRf.flatten(), 2) ** 2
+
+    def obfn_dfd(Vf):
+        if W is None:
+            return rfl2norm2(eval_Rf(Vf), Sm.shape, axis=axN) / 2.0
+        E = fft.irfftn(eval_Rf(Vf), dims.Nv, axN)        # pgm/cbpdn.py:478-486
+        return (np.linalg.norm(W5 * E) ** 2) / 2.0
 
     def prox_g(V, Lc):
         Uo = prox_l1(V, (lmbda / Lc) * wl1)
@@ -632,7 +651,7 @@ def pgm_convbpdn(D, S, lmbda=None, opt=None, dimK=None, fft=None, timing=None):
             tol = o['RelStopTol']
             if o['AutoStop']['Enabled']:
                 tol = o['AutoStop']['Tau0'] / (1. + k)
-            dfd = rfl2norm2(eval_Rf(Xf), Sm.shape, axis=axN) / 2.0
+            dfd = obfn_dfd(Xf)
             rl1 = np.linalg.norm((wl1 * X).ravel(), 1)
             itstat.append((k, dfd + lmbda * rl1, dfd, rl1, frcxd, F, Q, itbt, L,
                            time.perf_counter() - t_start))

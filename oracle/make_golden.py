@@ -201,6 +201,22 @@ def tikhonov():
     print('wrote tikhonov')
 
 
+def pgm_mask_case(tag, dt, D, S, W, lmbda, opt_ref, opt_orc, dimK=None):
+    """pgm.cbpdn.ConvBPDNMask (pgm/cbpdn.py:387-508)."""
+    b = rpgm.ConvBPDNMask(D, S, lmbda, W, rpgm.ConvBPDNMask.Options(opt_ref), dimK=dimK)
+    b.solve()
+    r = orc.pgm_convbpdn(D, S, lmbda, opt=opt_orc, dimK=dimK, W=W)
+    same(b.X, r.X, tag + ' X')
+    its = b.getitstat()
+    same(stat(its, 'L'), np.array([row[8] for row in r.itstat], dtype=np.float64), tag + ' L')
+    same(stat(its, 'ObjFun'), np.array([row[1] for row in r.itstat], dtype=np.float64), tag + ' ObjFun')
+    out = dict(D=D, S=S, W=W, lmbda=np.float64(lmbda), X=b.X, L=stat(its, 'L'), Rsdl=stat(its, 'Rsdl'),
+               ObjFun=stat(its, 'ObjFun'), DFid=stat(its, 'DFid'), RegL1=stat(its, 'RegL1'),
+               IterBTrack=stat(its, 'IterBTrack'), F_Btrack=stat(its, 'F_Btrack'), Q_Btrack=stat(its, 'Q_Btrack'))
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag)
+
+
 def level1():
     """Known-answer vectors for the level-1 functions from the reference itself."""
     rng = np.random.default_rng(7)
@@ -248,6 +264,11 @@ def main():
         Wk = (rng.random((32, 32, 3)) > 0.3).astype(dt)
         ams_case('ams_gry_' + sfx, dt, D, S[..., 0], Wm, 0.1, AMS_OPT['ams_gry'])
         ams_case('ams_k3_' + sfx, dt, D, S, Wk, 0.1, AMS_OPT['ams_k3'], dimK=1)
+        pgm_mask_case('pgm_mask_' + sfx, dt, D, S, Wk, 0.1,
+                      {'MaxMainIter': 20, 'RelStopTol': 0.0, 'L': 5.0,
+                       'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)},
+                      {'MaxMainIter': 20, 'RelStopTol': 0.0, 'L': 5.0,
+                       'Backtrack': {'gamma_u': 1.3, 'maxiter': 8}}, dimK=1)
         gw7 = np.concatenate((np.linspace(0.2, 2.0, 6), [0.0])).astype(dt)
         ams_case('ams_grd_' + sfx, dt, D, S[..., 0], Wm, 0.1,
                  dict(AMS_OPT['ams_gry'], GradWeight=gw7, rho=3.0, AutoRho={'Enabled': False}), grad_mu=0.4)

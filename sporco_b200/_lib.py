@@ -27,7 +27,7 @@ SYMBOLS = (
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
-    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
+    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
 )
 
@@ -106,6 +106,7 @@ def _declare(lib):
     lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
     lib.spcsc_set_gradreg.argtypes = [vp, vp, vp]
+    lib.spcsc_pgm_set_mask.argtypes = [vp, vp, i64p]
     lib.spcsc_tikhonov_filter.argtypes = [i32, i32, i32, i32, i32, ctypes.c_double, i32, vp, vp, vp]
     lib.spcsc_ccmod_reset.argtypes = [vp, vp, i32]
     lib.spcsc_ccmod_setcoef_device.argtypes = [vp, i32]
@@ -335,6 +336,16 @@ class Handle(object):
 
     def pgm_accept(self, coef):
         self._c(self.lib.spcsc_pgm_accept(self.h, float(coef)))
+
+    def pgm_set_mask(self, W):
+        if W is None:
+            self._c(self.lib.spcsc_pgm_set_mask(self.h, None, None))
+            return
+        W = np.ascontiguousarray(W, dtype=self.dtype)
+        if W.ndim != 4:
+            raise ValueError('mask must be given as a 4-D (N0, N1, C, K) broadcastable array')
+        shp = (ctypes.c_int64 * 4)(*W.shape)
+        self._c(self.lib.spcsc_pgm_set_mask(self.h, _ptr(W), shp))
 
     def set_gradreg(self, ghg, wgrd):
         d = self.dims

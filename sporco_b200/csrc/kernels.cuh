@@ -329,6 +329,8 @@ struct ColArgs {
     int dfid_on, even_n1, check_on;
     int ntiles;            // k_col2: number of (wf, b) slabs = N1f * nb
     int gradreg;           // k_col SOLVE 1 / 4: ConvBPDNGradReg (G.im = GHG, sumin[m] = (mu w_m, w_m))
+    int pgm_mask;          // k_col SOLVE 2 / 4: masked data fidelity (pgm.ConvBPDNMask): the residual spectra
+                           // W^2-filtered in the signal domain arrive ready made (SOLVE 2: sumin, SOLVE 4: G)
 };
 
 template <typename T, int MAXCD>
@@ -496,6 +498,17 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
                     const int cs = (Cd > 1) ? c : cx;
                     const C2<T> sf = Sf[(((size_t)k * a.Cs + cs) * a.N1f + wf) * N0 + h];
                     d[c] = sf - s;
+                    if (a.pgm_mask) {
+                        const size_t si = (((size_t)b * Cd + c) * a.N1f + wf) * N0 + h;
+                        if (SOLVE == 2) {
+                            d[c] = mk<T>(-sumin[si].re, -sumin[si].im);        // - rfft(W^2 irfft(s_Y - Sf))
+                        } else if (SOLVE == 4) {
+                            sumout[si] = s;                                     // s_X, for the masked F / DFid
+                            const C2<T> dx = s - sumin[si], gy = G[si];
+                            psum[2] += (double)(dx.re * gy.re + dx.im * gy.im);
+                        }
+                        continue;
+                    }
                     if (SOLVE == 2 && sumout) {
                         sumout[(((size_t)b * Cd + c) * a.N1f + wf) * N0 + h] = s;
                         psum[0] += (double)abs2(d[c]);
@@ -950,6 +963,43 @@ SPCSC_GLOBAL void k_pad_dict(const T* SPCSC_RESTRICT D, T* SPCSC_RESTRICT Dp, in
         const int m = (int)((i / ((size_t)N1 * N0)) % M), c = (int)(i / ((size_t)N1 * N0 * M));
         Dp[i] = (y < hd && x < wd) ? D[(((size_t)y * wd + x) * Cd + c) * M + m] : (T)0;
     }
+}
+
+// ---- masked data fidelity of pgm.cbpdn.ConvBPDNMask (pgm/cbpdn.py:461-506) -----------------
+template <typename T>
+SPCSC_GLOBAL void k_spec_sub(const C2<T>* SPCSC_RESTRICT a, const C2<T>* SPCSC_RESTRICT b,
+                             C2<T>* SPCSC_RESTRICT out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = a[i] - b[i];
+}
+// o1 = W r, o2 = W^2 r (either may be null); optionally sum (W r)^2 * scale2 into acc_slot
+template <typename T>
+SPCSC_GLOBAL void k_mask_mul(const T* SPCSC_RESTRICT r, const T* SPCSC_RESTRICT W, T* SPCSC_RESTRICT o1,
+                             T* SPCSC_RESTRICT o2, double* SPCSC_RESTRICT acc_slot, double scale2, size_t n) {
+    __shared__ double red[32];
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const T w = W[i], wr = w * r[i];
+        if (o1) o1[i] = wr;
+        if (o2) o2[i] = w * wr;
+        s[0] += (double)wr * (double)wr;
+    }
+    if (acc_slot) {
+        s[0] *= scale2;
+        block_accumulate<1>(s, red, acc_slot);
+    }
+}
+// plain sum of |z|^2 over a spectrum buffer (the half-spectrum norm the backtracking test uses)
+template <typename T>
+SPCSC_GLOBAL void k_spec_sumsq(const C2<T>* SPCSC_RESTRICT z, double* SPCSC_RESTRICT acc_slot, size_t n) {
+    __shared__ double red[32];
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        s[0] += (double)abs2(z[i]);
+    block_accumulate<1>(s, red, acc_slot);
 }
 
 // ---- sporco.signal.tikhonov_filter (signal.py:244-303) ------------------------------------

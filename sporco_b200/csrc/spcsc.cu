@@ -292,6 +292,7 @@ struct spcsc_handle {
     virtual int synchronize() = 0;
     virtual int attach_comm(spcsc_comm* c, double global_nx) = 0;
     virtual int set_gradreg(const void* ghg, const void* wgrd) = 0;
+    virtual int pgm_set_mask(const void* W, const int64_t* shape) = 0;
     virtual int pgm_configure(const spcsc_pgm_opts* o) = 0;
     virtual int pgm_reset(const void* X0) = 0;
     virtual int pgm_trial(double L, double* out) = 0;
@@ -377,6 +378,9 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> gw_buf;                           //   per filter (mu w_m, w_m)
     std::vector<T> gr_w;                            //   host copy of w_m (mu arrives with admm_configure)
     bool gradreg = false;
+    DevBuf<T> mk_W, mk_r, mk_wr, mk_w2r;            // pgm.ConvBPDNMask: mask and signal-domain work planes [K][C][N0][N1]
+    DevBuf<C2<T>> mk_f, mk_grad, mk_sx;             //   spectra [K][C][N1f][N0]: work, rfft(W^2 R_Y), s_X
+    bool pgm_mask = false;
     DevBuf<C2<T>> cdZf;                             // coefficient spectra, slab layout [K][N1f][M][N0]
     bool cd_ready = false, cd_have_coef = false;
     int cd_zero_mean = 0;
@@ -424,6 +428,7 @@ class Engine : public spcsc_handle {
         stw_row1.release(); stw_rowc.release(); stw_col.release();
         pgA.release(); pgB.release(); Zt2.release();
         cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
+        mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
@@ -1199,6 +1204,45 @@ class Engine : public spcsc_handle {
     }
 
     // ---- PGM --------------------------------------------------------------------------
+    int pgm_set_mask(const void* W, const int64_t* shape) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!W) { pgm_mask = false; return SPCSC_OK; }
+        if (Cd != 1) FAIL(SPCSC_ERR_UNSUPPORTED, "masked PGM with a multi-channel dictionary");
+        const int64_t full[4] = {N0, N1, C, K};
+        for (int i = 0; i < 4; ++i)
+            if (shape[i] != 1 && shape[i] != full[i]) FAIL(SPCSC_ERR_INVALID, "mask shape is not broadcastable to (N0,N1,C,K)");
+        // expand on the host into device order [K][C][N0][N1] (set-up time, K*C planes)
+        const T* w = (const T*)W;
+        std::vector<T> t((size_t)K * C * N0 * N1);
+        const size_t s3 = 1, s2 = (size_t)shape[3], s1 = s2 * shape[2], s0 = s1 * shape[1];
+        for (int k = 0; k < K; ++k)
+            for (int c = 0; c < C; ++c)
+                for (int y = 0; y < N0; ++y)
+                    for (int x = 0; x < N1; ++x)
+                        t[(((size_t)k * C + c) * N0 + y) * N1 + x] =
+                            w[(shape[0] > 1 ? y : 0) * s0 + (shape[1] > 1 ? x : 0) * s1 +
+                              (shape[2] > 1 ? c : 0) * s2 + (shape[3] > 1 ? k : 0) * s3];
+        CK(cudaSetDevice(pb.device));
+        const size_t nr = t.size(), nc = (size_t)K * C * N1f * N0;
+        CK(mk_W.ensure(nr)); CK(mk_r.ensure(nr)); CK(mk_wr.ensure(nr)); CK(mk_w2r.ensure(nr));
+        CK(mk_f.ensure(nc)); CK(mk_grad.ensure(nc)); CK(mk_sx.ensure(nc));
+        CK(cudaMemcpyAsync(mk_W.p, t.data(), nr * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        pgm_mask = true;
+        return SPCSC_OK;
+    }
+    // signal-domain residual planes of a sum buffer: r = irfft2(s - Sf), [K*C][N0][N1]
+    int mask_residual(const C2<T>* sums) {
+        const int nb = K * C;
+        const size_t nc = (size_t)nb * N1f * N0;
+        CK(launch(k_spec_sub<T>, dim3(296), dim3(256), 0, stream, sums, (const C2<T>*)Sf.p, mk_f.p, nc));
+        ColLaunch<T> c = colargs(1, nb);
+        c.in = mk_f.p; c.out = mk_f.p; c.a.Cd = 1;
+        CK(col<T>(N0, COL_INV, c));
+        CK(row_inv<T>(H, rowargs(1, nb, 1), (const C2<T>*)mk_f.p, mk_r.p, (T)(1.0 / ((double)N0 * (double)N1))));
+        return SPCSC_OK;
+    }
+
     int pgm_configure(const spcsc_pgm_opts* o) override {
         popts = *o;
         return SPCSC_OK;
@@ -1236,6 +1280,25 @@ class Engine : public spcsc_handle {
         // gradient step + inverse column transform: Zt = icol( Yf - conj(Df)(sum_m Df Yf - Sf)/L )
         ColLaunch<T> c1 = colargs(M, K * Cx);
         c1.in = pgB.p; c1.out = Zt.p; c1.sumout = sum_buf.p; c1.acc = acc.p; c1.Lstep = (T)L;
+        const size_t mk_nr = (size_t)K * C * N0 * N1, mk_nc = (size_t)K * C * N1f * N0;
+        if (pgm_mask) {
+            // masked fidelity (pgm/cbpdn.py:461-506): the residual goes through the signal domain,
+            //   grad = conj(Df) rfft(W^2 irfft(s_Y - Sf)),  F(Yf) = ||rfft(W irfft(s_Y - Sf))||^2 / 2
+            ColLaunch<T> c0 = colargs(M, K * Cx);
+            c0.in = pgB.p; c0.out = nullptr; c0.sumout = sum_buf.p;
+            CK(col<T>(N0, COL_SUM, c0));
+            int rc = mask_residual((const C2<T>*)sum_buf.p);
+            if (rc) return rc;
+            CK(launch(k_mask_mul<T>, dim3(296), dim3(256), 0, stream, (const T*)mk_r.p, (const T*)mk_W.p,
+                      mk_wr.p, mk_w2r.p, (double*)nullptr, 0.0, mk_nr));
+            rc = forward2d(mk_wr.p, mk_f.p, 1, K * C);
+            if (rc) return rc;
+            CK(launch(k_spec_sumsq<T>, dim3(296), dim3(256), 0, stream, (const C2<T>*)mk_f.p,
+                      acc.p + ACC_PGM_FY, mk_nc));
+            rc = forward2d(mk_w2r.p, mk_grad.p, 1, K * C);
+            if (rc) return rc;
+            c1.sumout = nullptr; c1.sumin = mk_grad.p; c1.a.pgm_mask = 1;
+        }
         CK(col<T>(N0, COL_GRAD_INV, c1));
         // inverse rows, prox, forward rows
         PgmRowArgs<T> pr;
@@ -1255,7 +1318,19 @@ class Engine : public spcsc_handle {
         // forward columns + evaluation of the candidate against Yf
         ColLaunch<T> c3 = colargs(M, K * Cx);
         c3.in = Zt.p; c3.out = Zt.p; c3.sumin = sum_buf.p; c3.ref = pgB.p; c3.acc = acc.p;
+        if (pgm_mask) { c3.a.pgm_mask = 1; c3.G = mk_grad.p; c3.sumout = mk_sx.p; }
         CK(col<T>(N0, COL_FWD_EVAL, c3));
+        if (pgm_mask) {
+            // F(Xf) and DFid of the candidate, through the signal domain as well
+            int rc = mask_residual((const C2<T>*)mk_sx.p);
+            if (rc) return rc;
+            CK(launch(k_mask_mul<T>, dim3(296), dim3(256), 0, stream, (const T*)mk_r.p, (const T*)mk_W.p,
+                      mk_wr.p, (T*)nullptr, acc.p + ACC_DFID, (double)N0 * (double)N1, mk_nr));
+            rc = forward2d(mk_wr.p, mk_f.p, 1, K * C);
+            if (rc) return rc;
+            CK(launch(k_spec_sumsq<T>, dim3(296), dim3(256), 0, stream, (const C2<T>*)mk_f.p,
+                      acc.p + ACC_PGM_F, mk_nc));
+        }
         double hacc[ACC_N];
         CK(cudaMemcpyAsync(hacc, acc.p, sizeof(hacc), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1479,6 +1554,7 @@ int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0));
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
 int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
 int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd) { H_CALL(h->set_gradreg(ghg, wgrd)); }
+int spcsc_pgm_set_mask(spcsc_handle* h, const void* W, const int64_t shape[4]) { H_CALL((W && !shape) ? SPCSC_ERR_INVALID : h->pgm_set_mask(W, shape)); }
 int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ? h->ccmod_reset(D0, zm) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source) { H_CALL(h->ccmod_setcoef_device(source)); }
 int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z) { H_CALL(Z ? h->ccmod_setcoef(Z) : SPCSC_ERR_INVALID); }

@@ -136,3 +136,25 @@ class ConvBPDN(pgm.PGMDFT):
         h = getattr(self, '_h', None)
         if h is not None:
             h.close()
+
+
+class ConvBPDNMask(ConvBPDN):
+    """FISTA for convolutional BPDN with a spatial mask in the data fidelity term (mirror of
+    sporco/pgm/cbpdn.py:387-508)::
+
+        argmin_x (1/2) || W (sum_m d_m * x_m - s) ||_2^2 + lambda sum_m || x_m ||_1
+
+    The gradient, the backtracking functional and DFid take the residual through the signal
+    domain (``rfft(W^2 irfft(.))``); on the device these are transforms of the K*C residual
+    planes only, next to the M-times larger coefficient arrays.  Single-channel dictionaries.
+    """
+
+    def __init__(self, D, S, lmbda, W=None, opt=None, dimK=None, dimN=2, device=0):
+        super(ConvBPDNMask, self).__init__(D, S, lmbda, opt, dimK=dimK, dimN=dimN, device=device)
+        if self.cri.Cd != 1:
+            raise NotImplementedError('ConvBPDNMask with a multi-channel dictionary is not supported')
+        if W is None:
+            W = np.array([1.0], dtype=self.dtype)
+        W = np.asarray(W)
+        self.W = np.asarray(W.reshape(cr.mskWshape(W, self.cri)), dtype=self.dtype)
+        self._h.pgm_set_mask(np.ascontiguousarray(self.W[..., 0]))

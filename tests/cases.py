@@ -503,3 +503,23 @@ def run_tikhonov_cases():
             assert rel(sl, g['sl%d_%s' % (i, sfx)]) < tol, (sfx, i, rel(sl, g['sl%d_%s' % (i, sfx)]))
             assert rel(sh, g['sh%d_%s' % (i, sfx)]) < 10 * tol
             assert np.allclose(sl + sh, s, atol=1e-6 if sfx == 'f32' else 1e-14)
+
+
+def run_pgm_mask_case(sfx):
+    """pgm.cbpdn.ConvBPDNMask with backtracking against the reference's outputs."""
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    tol = 1e-11 if sfx == 'f64' else 5e-5
+    g = load('pgm_mask_' + sfx)
+    opt = pcbpdn.ConvBPDN.Options({'MaxMainIter': 20, 'RelStopTol': 0.0, 'L': 5.0,
+                                   'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)})
+    b = pcbpdn.ConvBPDNMask(g['D'], g['S'], float(g['lmbda']), g['W'], opt, dimK=1)
+    X = b.solve()
+    its = b.getitstat()
+    assert X.dtype == g['X'].dtype and rel(X, g['X']) < tol
+    assert np.array_equal(np.asarray(its.IterBTrack, dtype=np.float64), g['IterBTrack'])
+    assert rel(its.L, g['L']) < 1e-6
+    assert rel(its.F_Btrack, g['F_Btrack']) < 10 * tol and rel(its.Q_Btrack, g['Q_Btrack']) < 10 * tol
+    assert rel(its.ObjFun, g['ObjFun']) < 10 * tol and rel(its.DFid, g['DFid']) < 10 * tol
+    assert rel(its.Rsdl, g['Rsdl']) < 10 * tol
+    return b

@@ -88,6 +88,16 @@ def test_oracle_reproduces_golden_tikhonov():
             assert np.array_equal(sl, g['sl%d_%s' % (i, sfx)]) and np.array_equal(sh, g['sh%d_%s' % (i, sfx)])
 
 
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+def test_oracle_reproduces_golden_pgm_mask(sfx):
+    g = cases.load('pgm_mask_' + sfx)
+    r = orc.pgm_convbpdn(g['D'], g['S'], float(g['lmbda']), dimK=1, W=g['W'],
+                         opt={'MaxMainIter': 20, 'RelStopTol': 0.0, 'L': 5.0,
+                              'Backtrack': {'gamma_u': 1.3, 'maxiter': 8}})
+    assert np.array_equal(r.X, g['X'])
+    assert np.array_equal(np.array([row[8] for row in r.itstat], dtype=np.float64), g['L'])
+
+
 def test_oracle_level1_known_answers():
     g = cases.load('level1')
     assert np.array_equal(orc.solvedbi_sm(g['ah'], 0.7, g['b'], 4), g['x'])

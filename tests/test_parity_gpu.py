@@ -213,3 +213,8 @@ def test_additive_mask_simulation_golden(tag, sfx):
 
 def test_tikhonov_filter_golden():
     cases.run_tikhonov_cases()
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+def test_pgm_mask_golden(sfx):
+    cases.run_pgm_mask_case(sfx)

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree n
 
 OTHER_CLASSES = ('ConvBPDNProjL1', 'ConvMinL1InL2Ball',
                  'ConvBPDNMaskDcpl', 'ConvL1L1Grd', 'MultiDictConvBPDN',
-                 'ConvBPDNMask', 'ConvTwoBlockCnstrnt')
+                 'ConvTwoBlockCnstrnt')
 # reference tests that exercise the replaced classes but need something not implemented
 NOT_IMPLEMENTED = {
     'admm': {'test_10cplx': 'complex-valued data'},
@@ -51,6 +51,7 @@ def _load(kind):
     else:
         proxy.__dict__.update(ref_pgm.__dict__)
         proxy.ConvBPDN = my_pgm.ConvBPDN
+        proxy.ConvBPDNMask = my_pgm.ConvBPDNMask
         path = os.path.join(REF, 'tests', 'pgm', 'test_cbpdn.py')
     src = open(path).read()
     src = src.replace('from sporco.admm import cbpdn', 'cbpdn = __proxy__')
