@@ -172,6 +172,14 @@ int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]);
 /* Accept the candidate and take the momentum step Yf = Xf + coef (Xf - Xfprv)  (PGMDFT.ystep). */
 int spcsc_pgm_accept(spcsc_handle* h, double coef);
 
+/* Device-side all-reduce of the per-iteration accumulators over peer memory (NVLink / NVSwitch), replacing the
+   NCCL call on that path: every rank exports a small block (CUDA IPC, 64-byte handle), the handles of all
+   ranks are gathered by the caller and attached; the exchange then happens inside the scalar kernel.  Needs
+   an attached communicator (spcsc_attach_comm) first -- NCCL keeps serving the large dictionary-gradient
+   all-reduce -- and at most 8 ranks on one node.  If attaching fails the NCCL path simply stays in use. */
+int spcsc_p2p_export(spcsc_handle* h, void* handle64);
+int spcsc_p2p_attach(spcsc_handle* h, int32_t rank, int32_t nranks, const void* handles64);
+
 /* pgm.cbpdn.ConvBPDNMask (pgm/cbpdn.py:387-508): data fidelity (1/2)||W (sum_m d_m * x_m - s)||^2.  W: real,
    shape[4] = (N0|1, N1|1, C|1, K|1) broadcast against the signal; NULL switches the mask off.  Affects the
    spcsc_pgm_* calls only.  Single-channel dictionary. */

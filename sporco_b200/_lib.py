@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'libspcsc.so')
 F32, F64 = 0, 1
 ARR_Y, ARR_U, ARR_X, ARR_XF, ARR_DF, ARR_SF, ARR_PGM_X, ARR_PGM_XF, ARR_PGM_YF = range(9)
 COEF_ADMM_Y, COEF_PGM_X = 0, 1
+ERR_UNSUPPORTED = -4
 
 # every symbol include/spcsc.h declares (tests check the list against the header)
 SYMBOLS = (
@@ -27,7 +28,8 @@ SYMBOLS = (
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
-    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
+    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
+    'spcsc_p2p_attach', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
 )
 
@@ -106,6 +108,8 @@ def _declare(lib):
     lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
     lib.spcsc_set_gradreg.argtypes = [vp, vp, vp]
+    lib.spcsc_p2p_export.argtypes = [vp, vp]
+    lib.spcsc_p2p_attach.argtypes = [vp, i32, i32, vp]
     lib.spcsc_pgm_set_mask.argtypes = [vp, vp, i64p]
     lib.spcsc_tikhonov_filter.argtypes = [i32, i32, i32, i32, i32, ctypes.c_double, i32, vp, vp, vp]
     lib.spcsc_ccmod_reset.argtypes = [vp, vp, i32]
@@ -382,6 +386,23 @@ class Handle(object):
 
     def ccmod_push_dict(self):
         self._c(self.lib.spcsc_ccmod_push_dict(self.h))
+
+    def p2p_export(self):
+        buf = ctypes.create_string_buffer(64)
+        self._c(self.lib.spcsc_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, rank, nranks, handles):
+        """handles: nranks * 64 bytes.  Returns False when peer mapping is not possible here (the
+        NCCL all-reduce then stays in use)."""
+        rc = self.lib.spcsc_p2p_attach(self.h, int(rank), int(nranks), handles)
+        if rc == ERR_UNSUPPORTED:
+            return False
+        self._c(rc)
+        return True
+
+    def p2p_detach(self):
+        self._c(self.lib.spcsc_p2p_attach(self.h, 0, 0, b''))
 
     def attach_comm(self, comm, global_nx):
         self._comm = comm                      # keep the communicator alive

@@ -801,6 +801,64 @@ SPCSC_DEV void fold_det_bins(double* acc) {
     }
     __syncthreads();
 }
+// ---- all-reduce of the ACC_N accumulators over peer memory (NVLink / NVSwitch) --------------
+// Every rank owns one P2pSlots block; peers hold it mapped (CUDA IPC).  Rank r writes its ACC_N
+// doubles into slot [parity][r] of EVERY rank's block, fences, then raises flag [parity][r] there to
+// the sequence number of this exchange; each rank waits for all flags of its own block and adds the
+// slots in rank order -- the same order everywhere, so all ranks get bit-identical sums (they must:
+// the rho update and the stopping test branch on them).  Two parities: a rank can be at most one
+// exchange ahead of the slowest one (it cannot pass exchange n+1 without that rank's flag n+1, which
+// is raised only after exchange n was read), so buffer n+2 never overwrites unread data.
+constexpr int kP2pMaxRanks = 8;
+struct P2pSlots {
+    double vals[2][kP2pMaxRanks][ACC_N];
+    unsigned long long flag[2][kP2pMaxRanks];
+};
+struct P2pView {
+    P2pSlots* peer[kP2pMaxRanks];      // peer[r]: rank r's block as mapped here (peer[rank] = own block)
+    int nranks, rank;
+    unsigned long long seq;            // exchange number, counted identically on every rank; > 0
+};
+// All threads of the (single) block; blockDim.x >= ACC_N * nranks.  Returns false on time-out.
+SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
+#ifdef SPCSC_EMU
+    (void)pv; (void)acc;
+    return true;
+#else
+    __shared__ int timed_out;
+    const int tid = threadIdx.x, par = (int)(pv.seq & 1ull);
+    if (tid == 0) timed_out = 0;
+    if (tid < ACC_N * pv.nranks) {
+        const int r = tid / ACC_N, i = tid % ACC_N;
+        pv.peer[r]->vals[par][pv.rank][i] = acc[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pv.nranks) {
+        volatile unsigned long long* f = &pv.peer[tid]->flag[par][pv.rank];
+        *f = pv.seq;
+    }
+    if (tid < pv.nranks) {
+        volatile unsigned long long* f = &pv.peer[pv.rank]->flag[par][tid];
+        const long long t0 = clock64();
+        while (*f != pv.seq) {
+            if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }      // ~2 s
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (timed_out) return false;
+    if (tid < ACC_N) {
+        const volatile double* v = &pv.peer[pv.rank]->vals[par][0][tid];
+        double s = 0.0;
+        for (int r = 0; r < pv.nranks; ++r) s += v[(size_t)r * ACC_N];
+        acc[tid] = s;
+    }
+    __syncthreads();
+    return true;
+#endif
+}
+
 // Used before a multi-rank all-reduce (which then sums plain doubles in NCCL's fixed order).
 template <int DUMMY>
 SPCSC_GLOBAL void k_fold_bins(double* acc) {
@@ -809,9 +867,13 @@ SPCSC_GLOBAL void k_fold_bins(double* acc) {
 
 template <typename T>
 SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
-                                 StatRow* rows, int k_base, int row_cap) {
+                                 StatRow* rows, int k_base, int row_cap, P2pView pv) {
     if (st->stopped) return;                       // uniform over the (single) block
     fold_det_bins(acc);
+    if (pv.nranks > 1 && !p2p_allreduce(pv, acc)) {
+        if (threadIdx.x == 0) st->stopped = 2;     // a peer never arrived: stop, the host reports it
+        return;
+    }
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int k = st->k;
     T rho = st->rho;

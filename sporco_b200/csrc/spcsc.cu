@@ -291,6 +291,8 @@ struct spcsc_handle {
     virtual int reconstruct(const void* X, void* out) = 0;
     virtual int synchronize() = 0;
     virtual int attach_comm(spcsc_comm* c, double global_nx) = 0;
+    virtual int p2p_export(void* handle64) = 0;
+    virtual int p2p_attach(int rank, int nranks, const void* handles64) = 0;
     virtual int set_gradreg(const void* ghg, const void* wgrd) = 0;
     virtual int pgm_set_mask(const void* W, const int64_t* shape) = 0;
     virtual int pgm_configure(const spcsc_pgm_opts* o) = 0;
@@ -378,6 +380,9 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> gw_buf;                           //   per filter (mu w_m, w_m)
     std::vector<T> gr_w;                            //   host copy of w_m (mu arrives with admm_configure)
     bool gradreg = false;
+    P2pSlots* p2p_own = nullptr;                    // peer-memory all-reduce: own block (plain cudaMalloc: IPC needs it)
+    P2pView p2p{};                                  //   and the mapped blocks of all ranks
+    bool p2p_on = false;
     DevBuf<T> mk_W, mk_r, mk_wr, mk_w2r;            // pgm.ConvBPDNMask: mask and signal-domain work planes [K][C][N0][N1]
     DevBuf<C2<T>> mk_f, mk_grad, mk_sx;             //   spectra [K][C][N1f][N0]: work, rfft(W^2 R_Y), s_X
     bool pgm_mask = false;
@@ -821,7 +826,11 @@ class Engine : public spcsc_handle {
                 CK(col<T>(N0, COL_FWD_EVAL, ce));
                 last_launches += 2;
             }
-            if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
+            P2pView pv{};
+            if (p2p_on && (prm.need_rsdl || prm.need_obj)) {
+                pv = p2p;
+                pv.seq = ++p2p.seq;               // counted identically on every rank
+            } else if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
                 // the one exchange of the path: sum the residual / objective accumulators over ranks
                 CK(launch(k_fold_bins<0>, dim3(1), dim3(256), 0, stream, acc.p));
                 int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
@@ -831,7 +840,7 @@ class Engine : public spcsc_handle {
                     return SPCSC_ERR_NCCL;
                 }
             }
-            CK(launch(k_admm_scalars<T>, dim3(1), dim3(256), 0, stream, st.p, prm, acc.p, rows.p, k_base, n));
+            CK(launch(k_admm_scalars<T>, dim3(1), dim3(256), 0, stream, st.p, prm, acc.p, rows.p, k_base, n, pv));
             if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
             if (fuse_now) std::swap(zin, zoth);        // the spectra just written feed the next x-step
         }
@@ -878,6 +887,11 @@ class Engine : public spcsc_handle {
         rc = read_state(s1);
         if (rc) return rc;
         CK(cudaEventElapsedTime(&last_ms, ev0, ev1));
+        if (s1.stopped == 2) {
+            err = "peer-memory all-reduce timed out: a rank of the group did not reach the exchange";
+            poisoned = true;
+            return SPCSC_ERR_NCCL;
+        }
         const int done = s1.k - s0.k;
         have_x = have_x || done > 0;
         settle_pingpong(done);
@@ -1042,6 +1056,55 @@ class Engine : public spcsc_handle {
         return from_internal(rec, out, C, K, 1);
     }
 
+    int p2p_export(void* handle64) override {
+#ifdef SPCSC_EMU
+        (void)handle64;
+        FAIL(SPCSC_ERR_UNSUPPORTED, "peer-memory all-reduce needs real devices");
+#else
+        if (poisoned) return SPCSC_ERR_CUDA;
+        CK(cudaSetDevice(pb.device));
+        if (!p2p_own) {
+            CK(cudaMalloc((void**)&p2p_own, sizeof(P2pSlots)));
+            CK(cudaMemset(p2p_own, 0, sizeof(P2pSlots)));
+        }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t hnd;
+        CK(cudaIpcGetMemHandle(&hnd, p2p_own));
+        memcpy(handle64, &hnd, 64);
+        return SPCSC_OK;
+#endif
+    }
+    int p2p_attach(int rank, int nr, const void* handles64) override {
+#ifdef SPCSC_EMU
+        (void)rank; (void)nr; (void)handles64;
+        FAIL(SPCSC_ERR_UNSUPPORTED, "peer-memory all-reduce needs real devices");
+#else
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (nr == 0) { p2p_on = false; return SPCSC_OK; }      // detach
+        if (!p2p_own) FAIL(SPCSC_ERR_STATE, "p2p_attach before p2p_export");
+        if (nr < 2 || nr > kP2pMaxRanks || rank < 0 || rank >= nr) FAIL(SPCSC_ERR_INVALID, "rank / nranks out of range");
+        if (!nccl_comm || nr != nranks) FAIL(SPCSC_ERR_STATE, "attach the communicator of the same group first");
+        CK(cudaSetDevice(pb.device));
+        P2pView v{};
+        v.nranks = nr; v.rank = rank; v.seq = 0;
+        for (int r = 0; r < nr; ++r) {
+            if (r == rank) { v.peer[r] = p2p_own; continue; }
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, (const char*)handles64 + 64 * (size_t)r, 64);
+            void* q = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&q, hnd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {          // not fatal: the NCCL path stays in use
+                cudaGetLastError();
+                err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+                return SPCSC_ERR_UNSUPPORTED;
+            }
+            v.peer[r] = (P2pSlots*)q;
+        }
+        p2p = v;
+        p2p_on = true;
+        return SPCSC_OK;
+#endif
+    }
     int attach_comm(spcsc_comm* c, double gnx) override {
         if (c && c->device != pb.device) FAIL(SPCSC_ERR_INVALID, "communicator belongs to another device");
         nccl = c ? c->api : nullptr;
@@ -1553,6 +1616,8 @@ int spcsc_pgm_configure(spcsc_handle* h, const spcsc_pgm_opts* o) { H_CALL(o ? h
 int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0)); }
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
 int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
+int spcsc_p2p_export(spcsc_handle* h, void* handle64) { H_CALL(handle64 ? h->p2p_export(handle64) : SPCSC_ERR_INVALID); }
+int spcsc_p2p_attach(spcsc_handle* h, int32_t rank, int32_t nranks, const void* handles64) { H_CALL(handles64 ? h->p2p_attach(rank, nranks, handles64) : SPCSC_ERR_INVALID); }
 int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd) { H_CALL(h->set_gradreg(ghg, wgrd)); }
 int spcsc_pgm_set_mask(spcsc_handle* h, const void* W, const int64_t shape[4]) { H_CALL((W && !shape) ? SPCSC_ERR_INVALID : h->pgm_set_mask(W, shape)); }
 int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ? h->ccmod_reset(D0, zm) : SPCSC_ERR_INVALID); }
