@@ -842,7 +842,7 @@ SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
         volatile unsigned long long* f = &pv.peer[pv.rank]->flag[par][tid];
         const long long t0 = clock64();
         while (*f != pv.seq) {
-            if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }      // ~2 s
+            if (clock64() - t0 > 60000000000LL) { timed_out = 1; break; }     // ~30 s: ranks may start far apart
         }
     }
     __threadfence_system();
