@@ -1,4 +1,4 @@
-"""Run under torchrun with 2 ranks (one GPU each): sporco_b200 with the batch sharded over
+"""Run under torchrun with 2 (or more) ranks (one GPU each): sporco_b200 with the batch sharded over
 the ranks against the single-object oracle on the whole batch."""
 import os
 import sys
@@ -21,7 +21,7 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     rng = np.random.default_rng(77)
     D = rng.standard_normal((8, 8, 16)).astype(np.float32)
-    S = rng.standard_normal((128, 128, 6)).astype(np.float32)
+    S = rng.standard_normal((128, 128, 3 * world if world <= 2 else 2 * world)).astype(np.float32)
     per = S.shape[2] // world
     mine = list(range(rank * per, (rank + 1) * per))
     opt = {'MaxMainIter': 20, 'RelStopTol': 0.0}
