@@ -562,7 +562,9 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     C2<T>* sloc = xbuf + NG * XP;                              // [CD][N0] this CTA's sums over its columns
     C2<T>* qbuf = sloc + CD * N0;                              // [CD][N0]
     C2<T>* stw_s = qbuf + CD * N0;                             // [TWLEN]
-    double* red = reinterpret_cast<double*>(stw_s + TWLEN);    // [32]
+    C2<T>* pre = stw_s + TWLEN;                                // [2][N0] CD == 1: Sf and G rows of this slab,
+                                                               //   fetched asynchronously at slab entry
+    double* red = reinterpret_cast<double*>(pre + 2 * N0);     // [32]
     mbar_t* bar = reinterpret_cast<mbar_t*>(red + 32);         // BULK: arrival of the prefetched slab
     C2<T>* tbuf = reinterpret_cast<C2<T>*>(bar + 2);           // BULK: [NG*CPG][N0] prefetched columns
     const int tid = threadIdx.x;
@@ -593,6 +595,16 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     const int wf = tile % a.N1f, b = tile / a.N1f;
     const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
     const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
+    if constexpr (SOLVE == 1 && CD == 1) {
+        // the solve needs one signal and one Gram value per frequency: start fetching them now, so
+        // that their L2 latency is not exposed between the two cluster barriers
+        const int kk = b / a.Cx, cxx = b - kk * a.Cx;
+        for (int h = tid; h < N0; h += NT) {
+            cp_async<sizeof(C2<T>)>(pre + h, Sf + (((size_t)kk * a.Cs + cxx) * a.N1f + wf) * N0 + h);
+            cp_async<sizeof(C2<T>)>(pre + N0 + h, G + (size_t)wf * N0 + h);
+        }
+        cp_async_commit();
+    }
 
     C2<T> v[CPG][E];
     if (BULK) {
@@ -634,7 +646,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             C2<T> s = mk<T>(0, 0);
             SPCSC_UNROLL
             for (int c = 0; c < CPG; ++c)
-                if (mcol[c] < M) s = s + dfw[d * dfc + (size_t)mcol[c] * N0 + h] * v[c][p];
+                if (mcol[c] < M) s = s + ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h) * v[c][p];
             xbuf[g * XP + h] = s;
         }
         __syncthreads();
@@ -657,6 +669,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     const int k = b / a.Cx, cx = b - k * a.Cx;
     const T rho = (SOLVE == 1) ? st->rho : (T)0;
     double dsum[1] = {0.0};
+    if constexpr (SOLVE == 1 && CD == 1) cp_async_wait<0>();   // own copies only: same h as below
     for (int h = tid; h < N0; h += NT) {
         C2<T> dv[CD];
         SPCSC_UNROLL
@@ -667,11 +680,14 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 s = s + ps[d * N0 + h];
             }
             const int csig = (CD > 1) ? d : cx;
-            dv[d] = Sf[(((size_t)k * a.Cs + csig) * a.N1f + wf) * N0 + h] - s;
+            if constexpr (SOLVE == 1 && CD == 1)
+                dv[d] = pre[h] - s;
+            else
+                dv[d] = Sf[(((size_t)k * a.Cs + csig) * a.N1f + wf) * N0 + h] - s;
         }
         if (SOLVE == 1) {
             if (CD == 1) {
-                const T den = G[(size_t)wf * N0 + h].re + rho;
+                const T den = pre[N0 + h].re + rho;
                 dv[0] = mk<T>(dv[0].re / den, dv[0].im / den);
             } else {
                 C2<T> A[CD][CD];
@@ -714,7 +730,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 if constexpr (SOLVE != 0) {
                     SPCSC_UNROLL
                     for (int d = 0; d < CD; ++d)
-                        x = x + mulc(qbuf[d * N0 + h], dfw[d * dfc + (size_t)mcol[c] * N0 + h]);
+                        x = x + mulc(qbuf[d * N0 + h], ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h));
                 }
                 v[c][p] = x;
             }

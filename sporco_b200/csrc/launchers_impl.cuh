@@ -272,7 +272,7 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     const int per_cta = NG * CPG;
     const unsigned cs = (unsigned)((c.a.M + per_cta - 1) / per_cta);
     c.a.N0 = N0;
-    const size_t smem = ((size_t)NG * fft_region(N0) + 2 * CD * N0 + stage_tw_len(N0, E)) * sizeof(C2<T>) +
+    const size_t smem = ((size_t)NG * fft_region(N0) + 2 * CD * N0 + stage_tw_len(N0, E) + 2 * N0) * sizeof(C2<T>) +
                         32 * sizeof(double);
     dim3 grid(c.a.N1f * cs, c.nb);
     c.a.ntiles = c.a.N1f * c.nb;
@@ -298,6 +298,18 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
                                   c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a);
         }
     }
+#ifndef SPCSC_EMU
+    {   // two CTAs of this kernel per SM need 2 x smem of shared memory; leave the rest of the unified
+        // array to L1, which serves the second read of the dictionary slice
+        static bool carved = false;
+        if (!carved) {
+            const int pct = (int)((2 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+            cudaFuncSetAttribute(k_col2<T, N0, E, CPG, NT, CD, true, 1, true, false>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+            carved = true;
+        }
+    }
+#endif
     return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, true, 1, true, false>, grid, dim3(NT), cs, smem,
                           c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a);
 }

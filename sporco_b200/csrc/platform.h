@@ -300,6 +300,19 @@ SPCSC_DEV C2<double> ld_stream(const C2<double>* p) {
 }
 #endif
 
+// Re-used read-only operand (dictionary spectra, read twice per slab by the same thread): ask L1 to
+// keep the line (evict-last), the counterpart of ld_stream.
+#ifdef SPCSC_EMU
+template <typename T> inline C2<T> ld_keep(const C2<T>* p) { return *p; }
+#else
+SPCSC_DEV C2<float> ld_keep(const C2<float>* p) {
+    C2<float> r;
+    asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(r.re), "=f"(r.im) : "l"(p));
+    return r;
+}
+SPCSC_DEV C2<double> ld_keep(const C2<double>* p) { return *p; }
+#endif
+
 // ---- warp / block reductions (double accumulators) -------------------------------------
 SPCSC_DEV double warp_sum(double v) {
     SPCSC_UNROLL
