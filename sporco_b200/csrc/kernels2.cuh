@@ -538,9 +538,113 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
 }
 
 // ------------------------------------------------------------------------------------
+// k_row_prox_fwd3: the PGM proximal step in the row domain (pgm/pgm.py:796-800, pgm/cbpdn.py:288-298)
+// on the register plans: V = irfft_row(Vt)*scale ; X = prox_l1(V, (lmbda/L) wl1) [+NonNeg,
+// NoBndryCross] stored; Xt = rfft_row(X) written over Vt (the CTA owns its TR rows of every wf);
+// RegL1 accumulated.  Same tile flow and conflict-free row mapping as k_row_inv_prox3.
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int E, int NT>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? 4 : 2))
+k_row_prox_fwd3(C2<T>* SPCSC_RESTRICT Vt, T* SPCSC_RESTRICT X, T thr_scale, WeightView<T> wl1,
+                double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw,
+                const C2<T>* SPCSC_RESTRICT stw, int N0, int M, int Cx, T scale, int nonneg, int bnd0,
+                int bnd1) {
+    SPCSC_DYN_SMEM(smem_raw);
+    using PL = Prox3Plan<T, H, E, 1, NT>;
+    constexpr int TPF = PL::TPF, TR = PL::TR, P = PL::P, N1f = PL::N1f, TWLEN = PL::TWLEN;
+    constexpr int WSTEP = NT / TR, WIT = (N1f + WSTEP - 1) / WSTEP;
+    C2<T>* reg = reinterpret_cast<C2<T>*>(smem_raw);           // [TR][P]
+    C2<T>* stw_s = reg + TR * P;                               // [TWLEN]
+    C2<T>* tw_s = stw_s + TWLEN;                               // [N1f]
+    double* red = reinterpret_cast<double*>(tw_s + N1f + (N1f & 1));   // [32]
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
+    const int k = b / Cx, c = b - k * Cx;
+    const size_t wstride = (size_t)M * N0;
+    const int gr = tid % TR, wf0 = tid / TR;
+    C2<T>* tile = Vt + (((size_t)b * N1f) * M + m) * N0 + h0 + (size_t)wf0 * wstride + gr;
+    {
+        C2<T>* dst = reg + gr * P + wf0;
+        SPCSC_UNROLL
+        for (int it = 0; it < WIT; ++it)
+            if (wf0 + it * WSTEP < N1f)
+                cp_async<sizeof(C2<T>)>(dst + it * WSTEP, tile + (size_t)it * WSTEP * wstride);
+    }
+    cp_async_commit();
+    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
+    for (int i = tid; i < N1f; i += NT) tw_s[i] = tw[i];
+    const int g = PL::row_of_group(tid / TPF), t = tid % TPF;
+    const int h = h0 + g;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    C2<T> v[E];
+    C2<T>* row = reg + g * P;
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) {
+        const int kk = t + TPF * p;
+        if (kk == 0) {
+            const T a0 = row[0].re, cc = row[H].re;            // c2r ignores the imaginary parts
+            v[p] = mk<T>(a0 + cc, a0 - cc);
+        } else {
+            const C2<T> Xa = row[kk], Xb = row[H - kk];
+            const C2<T> s1 = Xa + conj(Xb), d1 = Xa - conj(Xb);
+            v[p] = s1 + mul_i(mulc(d1, tw_s[kk]));
+        }
+    }
+    __syncwarp();
+    fft_regs<T, H, E, true>(v, row, stw_s, t);
+
+    const size_t wbase = (size_t)k * wl1.sk + (size_t)c * wl1.sc + (size_t)m * wl1.sm + (size_t)h * wl1.s0;
+    C2<T>* xg = reinterpret_cast<C2<T>*>(X) + (((size_t)b * M + m) * N0 + h) * H;
+    double sums[1] = {0.0};
+    T sabs = 0;
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) {
+        const int j = t + TPF * p;
+        T xs[2] = {v[p].re * scale, v[p].im * scale};
+        SPCSC_UNROLL
+        for (int q = 0; q < 2; ++q) {
+            const T w1 = wl1.spatial_uniform ? wl1.p[wbase] : wl1.p[wbase + (size_t)(2 * j + q) * wl1.s1];
+            T x = soft_threshold(xs[q], thr_scale * w1);
+            if (nonneg && x < (T)0) x = (T)0;
+            if (h >= bnd0 || (2 * j + q) >= bnd1) x = (T)0;
+            xs[q] = x;
+            sabs += fabs(w1 * x);
+        }
+        v[p] = mk<T>(xs[0], xs[1]);
+        xg[j] = v[p];
+    }
+    sums[0] = (double)sabs;
+    fft_regs<T, H, E, false>(v, row, stw_s, t);
+    __syncwarp();
+    SPCSC_UNROLL
+    for (int p = 0; p < E; ++p) row[t + TPF * p] = v[p];
+    __syncthreads();
+    {
+        const C2<T>* rrow = reg + gr * P;
+        SPCSC_UNROLL
+        for (int it = 0; it < WIT; ++it) {
+            const int wf = wf0 + it * WSTEP;
+            if (wf < N1f) {
+                const C2<T> aa = rrow[wf == H ? 0 : wf];
+                const C2<T> bb = conj(rrow[wf == 0 ? 0 : H - wf]);
+                const C2<T> sum = aa + bb, dif = mul_mi((aa - bb) * tw_s[wf]);
+                tile[(size_t)it * WSTEP * wstride] =
+                    mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+            }
+        }
+    }
+    block_accumulate<1>(sums, red, acc + ACC_L1);
+}
+
+// ------------------------------------------------------------------------------------
 // k_col2: cluster of CS CTAs per (wf, b) slab; CTA `cr` owns columns
 //   m = (cr*G + g)*CPG + c,  g = group (TPF lanes) index, c < CPG, kept in registers.
-//   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (gradient)
+//   SOLVE 1: q = (Sf - s)/(g + rho)   (ADMM, Cd == 1)      SOLVE 2: q = (Sf - s)/L  (PGM gradient step;
+//   also stores s and sums |Sf - s|^2)      SOLVE 4: no update: PGM evaluation of the transformed
+//   slab against Sf, the sums `sumin` of the momentum point and its slabs `ref` (F, DFid, linear
+//   term, |X - Y|^2)
 // ------------------------------------------------------------------------------------
 // BULK: persistent clusters (the grid is the number of clusters that fit on the GPU; each walks
 // over slabs with that stride) whose NEXT slab -- the CTA's NG*CPG columns are contiguous in
@@ -552,7 +656,8 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
 k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
        const AdmmState<T>* SPCSC_RESTRICT st, T Lstep, double* SPCSC_RESTRICT acc,
-       const C2<T>* SPCSC_RESTRICT stw, ColArgs a) {
+       const C2<T>* SPCSC_RESTRICT stw, ColArgs a, C2<T>* SPCSC_RESTRICT sumout,
+       const C2<T>* SPCSC_RESTRICT sumin, const C2<T>* SPCSC_RESTRICT ref) {
     if (st && st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
     constexpr int TPF = N0 / E, NG = NT / TPF;
@@ -595,13 +700,13 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     const int wf = tile % a.N1f, b = tile / a.N1f;
     const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
     const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
-    if constexpr (SOLVE == 1 && CD == 1) {
+    if constexpr (SOLVE != 0 && CD == 1) {
         // the solve needs one signal and one Gram value per frequency: start fetching them now, so
         // that their L2 latency is not exposed between the two cluster barriers
         const int kk = b / a.Cx, cxx = b - kk * a.Cx;
         for (int h = tid; h < N0; h += NT) {
             cp_async<sizeof(C2<T>)>(pre + h, Sf + (((size_t)kk * a.Cs + cxx) * a.N1f + wf) * N0 + h);
-            cp_async<sizeof(C2<T>)>(pre + N0 + h, G + (size_t)wf * N0 + h);
+            if (SOLVE == 1) cp_async<sizeof(C2<T>)>(pre + N0 + h, G + (size_t)wf * N0 + h);
         }
         cp_async_commit();
     }
@@ -669,7 +774,9 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     const int k = b / a.Cx, cx = b - k * a.Cx;
     const T rho = (SOLVE == 1) ? st->rho : (T)0;
     double dsum[1] = {0.0};
-    if constexpr (SOLVE == 1 && CD == 1) cp_async_wait<0>();   // own copies only: same h as below
+    if constexpr (SOLVE != 0 && CD == 1) cp_async_wait<0>();   // own copies only: same h as below
+    double psum[3] = {0.0, 0.0, 0.0};                          // PGM: plain |s - Sf|^2, weighted, linear term
+    const double wgt_wf = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
     for (int h = tid; h < N0; h += NT) {
         C2<T> dv[CD];
         SPCSC_UNROLL
@@ -680,10 +787,26 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 s = s + ps[d * N0 + h];
             }
             const int csig = (CD > 1) ? d : cx;
-            if constexpr (SOLVE == 1 && CD == 1)
-                dv[d] = pre[h] - s;
+            C2<T> sfv;
+            if constexpr (SOLVE != 0 && CD == 1)
+                sfv = pre[h];
             else
-                dv[d] = Sf[(((size_t)k * a.Cs + csig) * a.N1f + wf) * N0 + h] - s;
+                sfv = Sf[(((size_t)k * a.Cs + csig) * a.N1f + wf) * N0 + h];
+            dv[d] = sfv - s;
+            if ((SOLVE == 2 || SOLVE == 4) && cr == 0) {
+                const size_t si = (((size_t)b * CD + d) * a.N1f + wf) * N0 + h;
+                const double e2 = (double)abs2(dv[d]);
+                psum[0] += e2;
+                if (SOLVE == 2 && sumout) sumout[si] = s;
+                if (SOLVE == 4) {
+                    psum[1] += wgt_wf * e2;
+                    if (sumin) {
+                        const C2<T> sy = sumin[si];
+                        const C2<T> dx = s - sy, gy = sy - sfv;          // Re(conj(dx) * gy)
+                        psum[2] += (double)(dx.re * gy.re + dx.im * gy.im);
+                    }
+                }
+            }
         }
         if (SOLVE == 1) {
             if (CD == 1) {
@@ -719,7 +842,18 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     cluster_arrive_relaxed();                                // done reading the peers' sums
     __syncthreads();
     if (SOLVE == 1 && a.dfid_on) block_accumulate<1>(dsum, red, acc + ACC_DFID);
+    if (SOLVE == 2 && sumout) {
+        double one[1] = {psum[0]};
+        block_accumulate<1>(one, red, acc + ACC_PGM_FY);
     }
+    if (SOLVE == 4) {
+        double a1[1] = {psum[0]}, a2[1] = {psum[1]}, a3[1] = {psum[2]};
+        block_accumulate<1>(a1, red, acc + ACC_PGM_F);
+        block_accumulate<1>(a2, red, acc + ACC_DFID);
+        block_accumulate<1>(a3, red, acc + ACC_PGM_LIN);
+    }
+    }
+    double dxy[1] = {0.0};
     SPCSC_UNROLL
     for (int c = 0; c < CPG; ++c) {
         if (mcol[c] < M) {
@@ -727,10 +861,13 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             for (int p = 0; p < E; ++p) {
                 const int h = t + TPF * p;
                 C2<T> x = v[c][p];
-                if constexpr (SOLVE != 0) {
+                if constexpr (SOLVE == 1 || SOLVE == 2) {
                     SPCSC_UNROLL
                     for (int d = 0; d < CD; ++d)
                         x = x + mulc(qbuf[d * N0 + h], ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h));
+                }
+                if constexpr (SOLVE == 4) {
+                    if (ref) dxy[0] += (double)abs2(x - ld_stream(ref + slab + (size_t)mcol[c] * N0 + h));
                 }
                 v[c][p] = x;
             }
@@ -743,6 +880,14 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             C2<T>* dst = out + slab + (size_t)mcol[c] * N0;
             SPCSC_UNROLL
             for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[c][p];
+        }
+    }
+    if constexpr (SOLVE == 4) {
+        if (ref) {
+            __syncthreads();
+            block_accumulate<1>(dxy, red, acc + ACC_PGM_DXY2);
+            dxy[0] *= (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+            block_accumulate<1>(dxy, red, acc + ACC_PGM_RSDL);
         }
     }
     if constexpr (SOLVE != 0) cluster_wait();                // peers are done with my shared memory

@@ -79,6 +79,7 @@ struct PgmRowArgs {
     double* acc;
     T scale;
     int nonneg, bnd0, bnd1;
+    const C2<T>* stw;            // stage twiddles of the register plan (null: general kernel)
 };
 template <typename T, int H>
 cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt, T* X);
@@ -131,7 +132,7 @@ template <typename T>
 inline bool col2_ok(int N0, int M, int Cd) {
     if (sizeof(T) != 4 || Cd < 1 || Cd > 4 || N0 < 32 || N0 > 512) return false;
     const int per_cta = (kCol2Threads / (N0 / kCol2E)) * kCol2CPG;
-    return (M + per_cta - 1) / per_cta <= 4;     // so that the one-column variant needs <= 8 CTAs
+    return (M + per_cta - 1) / per_cta <= 8;     // portable cluster size
 }
 
 template <typename T, int H>

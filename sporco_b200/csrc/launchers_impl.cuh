@@ -55,6 +55,18 @@ cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const
 
 template <typename T, int H>
 cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt, T* X) {
+    if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
+        // register-plan kernel: float32, power-of-two row length, 128-thread CTAs
+        constexpr int E = row2_elems(H, 1), TPF2 = H / E, NT2 = 128, TR2 = NT2 / TPF2;
+        if (p.stw && TPF2 <= 16 && r.N0 % TR2 == 0) {
+            using PL = Prox3Plan<T, H, E, 1, NT2>;
+            const size_t smem2 = ((size_t)TR2 * PL::P + PL::TWLEN + PL::N1f + (PL::N1f & 1)) * sizeof(C2<T>) +
+                                 32 * sizeof(double);
+            dim3 grid2(r.N0 / TR2, r.M, r.nb);
+            return launch(k_row_prox_fwd3<T, H, E, NT2>, grid2, dim3(NT2), smem2, r.stream, Vt, X, p.thr_scale,
+                          p.wl1, p.acc, r.tw, p.stw, r.N0, r.M, r.Cx, p.scale, p.nonneg, p.bnd0, p.bnd1);
+        }
+    }
     constexpr int TPF = fft_tpf<T, H>();
     const int nt = round_up32(r.TR * TPF);
     size_t smem = (size_t)r.TR * (H + 1) * sizeof(C2<T>);
@@ -280,9 +292,17 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
         if constexpr (CD == 1)          // forward columns only (set-up transforms, coefficient spectra)
             return launch_cluster(k_col2<T, N0, E, CPG, NT, 1, true, 0, false, false>, grid, dim3(NT), cs,
                                   smem, c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw,
-                                  c.a);
+                                  c.a, c.sumout, c.sumin, c.ref);
         return cudaErrorInvalidValue;
     }
+    if (mode == COL_GRAD_INV)       // PGM gradient step on slabs already in the frequency domain
+        return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, false, 2, true, false>, grid, dim3(NT), cs, smem,
+                              c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a,
+                              c.sumout, c.sumin, c.ref);
+    if (mode == COL_FWD_EVAL)       // PGM: forward columns + evaluation of the candidate
+        return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, true, 4, false, false>, grid, dim3(NT), cs, smem,
+                              c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a,
+                              c.sumout, c.sumin, c.ref);
     if (mode != COL_ADMM) return cudaErrorInvalidValue;
     if (c.bulk) {
         // persistent clusters with the next slab prefetched by a bulk copy; in place is fine (a
@@ -295,7 +315,7 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
         if (ncl > 0) {
             const int use = ncl < c.a.ntiles ? ncl : c.a.ntiles;
             return launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem_b, c.stream, c.in, c.out,
-                                  c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a);
+                                  c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a, c.sumout, c.sumin, c.ref);
         }
     }
 #ifndef SPCSC_EMU
@@ -311,7 +331,7 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     }
 #endif
     return launch_cluster(k_col2<T, N0, E, CPG, NT, CD, true, 1, true, false>, grid, dim3(NT), cs, smem,
-                          c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a);
+                          c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a, c.sumout, c.sumin, c.ref);
 }
 
 template <typename T, int N0>

@@ -1362,7 +1362,9 @@ class Engine : public spcsc_handle {
             if (rc) return rc;
             c1.sumout = nullptr; c1.sumin = mk_grad.p; c1.a.pgm_mask = 1;
         }
-        CK(col<T>(N0, COL_GRAD_INV, c1));
+        const bool pgm_v2 = v2_col && !pgm_mask;       // cluster column kernel (register plans)
+        if (pgm_v2) CK(col2<T>(N0, COL_GRAD_INV, c1, (const C2<T>*)stw_col.p));
+        else CK(col<T>(N0, COL_GRAD_INV, c1));
         // inverse rows, prox, forward rows
         PgmRowArgs<T> pr;
         pr.thr_scale = (T)popts.lmbda / (T)L;
@@ -1370,6 +1372,7 @@ class Engine : public spcsc_handle {
         pr.acc = acc.p;
         pr.scale = (T)(1.0 / ((double)N0 * (double)N1));
         pr.nonneg = popts.nonneg;
+        pr.stw = (v2_rowf && !pgm_mask) ? (const C2<T>*)stw_row1.p : nullptr;
         pr.bnd0 = N0; pr.bnd1 = N1;
         if (popts.no_bndry_cross) {
             pr.bnd0 = pb.hd == 1 ? 0 : N0 - (pb.hd - 1);
@@ -1382,7 +1385,8 @@ class Engine : public spcsc_handle {
         ColLaunch<T> c3 = colargs(M, K * Cx);
         c3.in = Zt.p; c3.out = Zt.p; c3.sumin = sum_buf.p; c3.ref = pgB.p; c3.acc = acc.p;
         if (pgm_mask) { c3.a.pgm_mask = 1; c3.G = mk_grad.p; c3.sumout = mk_sx.p; }
-        CK(col<T>(N0, COL_FWD_EVAL, c3));
+        if (pgm_v2) CK(col2<T>(N0, COL_FWD_EVAL, c3, (const C2<T>*)stw_col.p));
+        else CK(col<T>(N0, COL_FWD_EVAL, c3));
         if (pgm_mask) {
             // F(Xf) and DFid of the candidate, through the signal domain as well
             int rc = mask_residual((const C2<T>*)mk_sx.p);

@@ -218,3 +218,30 @@ def test_tikhonov_filter_golden():
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
 def test_pgm_mask_golden(sfx):
     cases.run_pgm_mask_case(sfx)
+
+
+def test_eight_cta_clusters_admm_and_pgm():
+    """512 rows x 120 filters: the cluster column kernel runs with 8 CTAs per cluster (16 columns
+    each) -- ADMM x-step and both PGM modes -- against the oracle."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    rng = np.random.default_rng(8)
+    D = rng.standard_normal((6, 6, 120)).astype(np.float32)
+    S = rng.standard_normal((512, 64)).astype(np.float32)
+    opt = {'MaxMainIter': 12, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(opt))
+    Y = b.solve()
+    assert b._h.admm_schedule_info()[1] == 1                   # the cluster kernel is in use
+    r = orc.admm_convbpdn(D, S, 0.1, opt=opt)
+    assert cases.rel(Y, r.Y) < 3e-4
+    assert cases.rel(b.getitstat().ObjFun, [row[1] for row in r.itstat]) < 1e-4
+    po = {'MaxMainIter': 10, 'RelStopTol': 0.0, 'L': 20.0}
+    p = pcbpdn.ConvBPDN(D, S, 0.1, pcbpdn.ConvBPDN.Options(dict(po, Backtrack=BacktrackStandard(maxiter=10))))
+    X = p.solve()
+    rp = orc.pgm_convbpdn(D, S, 0.1, opt=dict(po, Backtrack={'gamma_u': 1.2, 'maxiter': 10}))
+    assert cases.rel(X, rp.X) < 1e-4
+    its = p.getitstat()
+    assert cases.rel(its.ObjFun, [row[1] for row in rp.itstat]) < 1e-4
+    assert np.array_equal(np.asarray(its.IterBTrack, dtype=float), np.array([row[7] for row in rp.itstat], dtype=float))
