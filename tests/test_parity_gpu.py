@@ -233,7 +233,7 @@ def test_eight_cta_clusters_admm_and_pgm():
     opt = {'MaxMainIter': 12, 'RelStopTol': 0.0}
     b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(opt))
     Y = b.solve()
-    assert b._h.admm_schedule_info()[1] == 1                   # the cluster kernel is in use
+    assert b._h.admm_schedule_info()['col_v2']                   # the cluster kernel is in use
     r = orc.admm_convbpdn(D, S, 0.1, opt=opt)
     assert cases.rel(Y, r.Y) < 3e-4
     assert cases.rel(b.getitstat().ObjFun, [row[1] for row in r.itstat]) < 1e-4
