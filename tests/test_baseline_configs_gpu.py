@@ -1,0 +1,80 @@
+"""BASELINE.json's configurations at their own sizes (batch / iteration counts reduced so that the
+numpy oracle finishes in seconds): parity of the device path with the oracle, float32, rtol 1e-4
+(north_star).  cfg1 (dense BPDN) is CPU plumbing of the reference and out of scope."""
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(D):
+    return (D / np.sqrt(np.sum(D ** 2, axis=(0, 1), keepdims=True))).astype(np.float32)
+
+
+def test_cfg2_single_image_256_dict_8x8x32():
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(12345)
+    D = _unit(rng.standard_normal((8, 8, 32)))
+    S = rng.standard_normal((256, 256)).astype(np.float32)
+    opt = {'MaxMainIter': 60, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(opt))
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=opt, fft=orc.FFTBackend('scipy', 16))
+    assert cases.rel(Y, r.Y) < 1e-4
+    assert cases.rel(b.getitstat().ObjFun, [row[1] for row in r.itstat]) < 1e-4
+    assert cases.rel(b.getitstat().Rho, [row[8] for row in r.itstat]) < 1e-4
+
+
+@pytest.mark.parametrize('multichannel_dict', [False, True])
+def test_cfg3_joint_colour_256(multichannel_dict):
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(12345)
+    D = _unit(rng.standard_normal((8, 8, 3, 64) if multichannel_dict else (8, 8, 64)))
+    S = rng.standard_normal((256, 256, 3, 2)).astype(np.float32)           # 2 of the 32 images
+    opt = {'MaxMainIter': 15, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDNJoint(D, S, 0.1, 0.01, cbpdn.ConvBPDNJoint.Options(opt))
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, mu=0.01, opt=opt, fft=orc.FFTBackend('scipy', 16))
+    assert cases.rel(Y, r.Y) < 1e-4
+    its = b.getitstat()
+    assert cases.rel(its.ObjFun, [row[1] for row in r.itstat]) < 1e-4
+    assert cases.rel(its.RegL21, [row[4] for row in r.itstat]) < 1e-4
+
+
+def test_cfg4_fista_512_dict_12x12x128_backtracking():
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    rng = np.random.default_rng(12345)
+    D = _unit(rng.standard_normal((12, 12, 128)))
+    S = rng.standard_normal((512, 512)).astype(np.float32)
+    po = {'MaxMainIter': 8, 'RelStopTol': 0.0, 'L': 1.0}
+    p = pcbpdn.ConvBPDN(D, S, 0.05, pcbpdn.ConvBPDN.Options(dict(po, Backtrack=BacktrackStandard(maxiter=15))))
+    X = p.solve()
+    r = orc.pgm_convbpdn(D, S, 0.05, opt=dict(po, Backtrack={'gamma_u': 1.2, 'maxiter': 15}),
+                         fft=orc.FFTBackend('scipy', 16))
+    its = p.getitstat()
+    assert np.array_equal(np.asarray(its.IterBTrack, dtype=float), np.array([row[7] for row in r.itstat], dtype=float))
+    assert cases.rel(its.L, [row[8] for row in r.itstat]) < 1e-6
+    assert cases.rel(X, r.X) < 1e-4
+    assert cases.rel(its.ObjFun, [row[1] for row in r.itstat]) < 1e-4
+
+
+def test_cfg5_dictionary_learning_16_images_256():
+    from oracle import cbpdn_oracle as orc, cbpdndl_oracle as ocdl
+    from sporco_b200.dictlrn import cbpdndl
+    rng = np.random.default_rng(12345)
+    D0 = rng.standard_normal((8, 8, 64)).astype(np.float32)
+    S = rng.standard_normal((256, 256, 16)).astype(np.float32)
+    o = {'MaxMainIter': 4}
+    d = cbpdndl.ConvBPDNDictLearn(D0, S, 0.1, cbpdndl.ConvBPDNDictLearn.Options(o))
+    D1 = d.solve()
+    r = ocdl.cbpdndl(D0, S, 0.1, o, fft=orc.FFTBackend('scipy', 16))
+    assert cases.rel(D1.squeeze(), r['D']) < 1e-4
+    its = d.getitstat()
+    assert cases.rel(its.ObjFun, r['ObjFun']) < 1e-4 and cases.rel(its.D_Rsdl, r['D_Rsdl']) < 1e-3
