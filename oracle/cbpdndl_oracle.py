@@ -41,10 +41,13 @@ CDL_DEFAULTS = {
 }
 
 
-def cbpdndl(D0, S, lmbda, opt=None, fft=None):
+def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
     """Run ConvBPDNDictLearn(D0, S, lmbda, opt) with xmethod='admm', dmethod='pgm'.
     Returns a dict with the learned dictionary (cropped), the coefficient maps and the
-    iteration statistics columns."""
+    iteration statistics columns.  `reduce`, if given, maps a float64 array of local sums to
+    global sums: the form of the algorithm with the training images sharded over ranks (every
+    rank codes its own images; squared norms, objective terms and the dictionary gradient are
+    summed), which must reproduce the unsharded run."""
     fft = fft or co.FFTBackend()
     o = {'MaxMainIter': 10, 'CBPDN': dict(CDL_DEFAULTS['CBPDN']), 'CCMOD': dict(CDL_DEFAULTS['CCMOD'])}
     o['CBPDN']['AutoRho'] = dict(CDL_DEFAULTS['CBPDN']['AutoRho'])
@@ -117,16 +120,24 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None):
         if xo['NonNegCoef']:
             Y[Y < 0.0] = 0.0
         U = U + (AX - Y)
-        nX, nY, nU = np.linalg.norm(X), np.linalg.norm(Y), np.linalg.norm(U)
+        if reduce is None:
+            nX, nY, nU = np.linalg.norm(X), np.linalg.norm(Y), np.linalg.norm(U)
+            nR, nS = np.linalg.norm(X - Y), np.linalg.norm(rho * (Yprev - Y))
+        else:
+            g = reduce(np.array([np.sum(a.astype(np.float64) ** 2) for a in (X, Y, U, X - Y, Yprev - Y)]))
+            nX, nY, nU, nR = [rdt.type(np.sqrt(v)) for v in g[0:4]]
+            nS = rho * rdt.type(np.sqrt(g[4]))
         rn = max(nX, nY)
         rn = 1.0 if rn == 0.0 else rn
         sn = rho * nU
         sn = 1.0 if sn == 0.0 else sn
-        r = np.linalg.norm(X - Y) / rn
-        s = np.linalg.norm(rho * (Yprev - Y)) / sn
+        r = nR / rn
+        s = nS / sn
         Ef = co.inner(Df, Xf, axM) - Sf
         dfd = co.rfl2norm2(Ef, Sm.shape, axis=axN) / 2.0
         rl1 = np.linalg.norm(X.ravel(), 1)
+        if reduce is not None:
+            dfd, rl1 = reduce(np.array([dfd, rl1], dtype=np.float64))
         xrho = rho
         if ar['Enabled'] and kx != 0 and np.mod(kx + 1, ar['Period']) == 0:
             if ar['AutoScaling']:
@@ -152,6 +163,9 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None):
         Ydfprv = Ydf.copy()
         Ryf = co.inner(Zf, Ydf, axM) - Sf
         gradf = co.inner(np.conj(Zf), Ryf, axK)
+        if reduce is not None:                                   # sum of the shards' gradients
+            gradf = (reduce(gradf.real.astype(np.float64)) + 1j * reduce(gradf.imag.astype(np.float64))
+                     ).astype(gradf.dtype)
         Vf = Ydf - (1. / L) * gradf
         V = fft.irfftn(Vf, Nv, axN)
         Xd = pcn(V, dsz, Nv, zm=do['ZeroMean'])

@@ -51,6 +51,49 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_cdl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import cbpdndl_oracle as ocdl
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = cases.load('cdl_f64')
+    S = g['S']                                   # (32, 32, 4): four training images
+    mine = [0] if rank == 0 else [1, 2, 3]       # uneven shards on purpose
+
+    def reduce(v):
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
+        dist.all_reduce(t)
+        return t.numpy()
+
+    o, _, lmbda = cases.CDL_CASES['cdl']
+    r = ocdl.cbpdndl(g['D0'], S[:, :, mine], lmbda, o, reduce=reduce)
+    q.put((rank, cases.rel(r['D'], g['D'].squeeze()), cases.rel(r['X'], g['X'][:, :, :, mine, :]),
+           cases.rel(r['ObjFun'], g['ObjFun']), cases.rel(r['XRho'], g['XRho']),
+           cases.rel(r['D_Rsdl'], g['D_Rsdl'])))
+    dist.destroy_process_group()
+
+
+def test_sharded_dictionary_learning_gloo_world2():
+    """Dictionary learning with the training images sharded over two ranks (gradient, norms and
+    objective terms summed over ranks) follows the single-object reference trajectory."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_cdl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, d_err, x_err, obj_err, rho_err, rs_err in res:
+        assert d_err < 1e-9 and x_err < 1e-8, (rank, d_err, x_err)
+        assert obj_err < 1e-10 and rho_err < 1e-12 and rs_err < 1e-8
+
+
 def test_sharded_algorithm_gloo_world2():
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
