@@ -109,30 +109,34 @@ cudaError_t row_inv_prox_fwd_gen_launch(const GenRowArgs<T>& r, const PgmRowArgs
 // ---- kernel set v2 (kernels2.cuh): plans and eligibility ------------------------------
 constexpr int kRow2Threads = 256;
 constexpr int kCol2Threads = 256;
-constexpr int kCol2E = 16;
-constexpr int kCol2CPG = 2;
+// column kernel: elements per lane and columns per lane group.  float32: 16 x 2 (32 complex values =
+// 64 registers of payload per thread); float64: 8 x 1 (the same 32 registers of payload as one
+// float32 column)
+template <typename T> constexpr int col2_elems() { return sizeof(T) == 4 ? 16 : 8; }
+template <typename T> constexpr int col2_cpg() { return sizeof(T) == 4 ? 2 : 1; }
 
-// elements per lane of the v2 row plan (0: no v2 plan for this length)
-constexpr int row2_elems(int H, int Cx) {
+// elements per lane of the v2 row plan (0: no v2 plan for this length); esz = sizeof(T)
+constexpr int row2_elems(int H, int Cx, int esz) {
     int e = H >= 128 ? 16 : (H >= 32 ? 8 : 0);
-    if (Cx > 1 && e > 8) e = 8;
+    if ((Cx > 1 || esz == 8) && e > 8) e = 8;
     if (e != 0 && H / e > 32) e = 0;
     return e;
 }
-constexpr int row2_tile(int H, int Cx) {
-    return row2_elems(H, Cx) == 0 ? 0 : kRow2Threads / (H / row2_elems(H, Cx));
+constexpr int row2_tile(int H, int Cx, int esz) {
+    return row2_elems(H, Cx, esz) == 0 ? 0 : kRow2Threads / (H / row2_elems(H, Cx, esz));
 }
 template <typename T>
 inline bool row2_ok(int H, int N0, int Cx) {
-    if (sizeof(T) != 4) return false;
-    const int tr = row2_tile(H, Cx);
-    return tr > 0 && N0 % tr == 0 && Cx <= 4;
+    const int tr = row2_tile(H, Cx, (int)sizeof(T));
+    const int tr128 = tr / 2;                      // the 128-thread prox kernel
+    return tr > 0 && N0 % tr == 0 && (tr128 == 0 || N0 % tr128 == 0) && Cx <= 4;
 }
 template <typename T>
 inline bool col2_ok(int N0, int M, int Cd) {
-    if (sizeof(T) != 4 || Cd < 1 || Cd > 4 || N0 < 32 || N0 > 512) return false;
-    const int per_cta = (kCol2Threads / (N0 / kCol2E)) * kCol2CPG;
-    return (M + per_cta - 1) / per_cta <= 8;     // portable cluster size
+    if (Cd < 1 || Cd > 4 || N0 < 32 || N0 > 512 || N0 / col2_elems<T>() > 32) return false;
+    if (sizeof(T) == 8 && Cd > 1) return false;    // the Woodbury variants stay float32 for now
+    const int per_cta = (kCol2Threads / (N0 / col2_elems<T>())) * col2_cpg<T>();
+    return (M + per_cta - 1) / per_cta <= 8;       // portable cluster size
 }
 
 template <typename T, int H>

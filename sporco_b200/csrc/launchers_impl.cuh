@@ -55,9 +55,9 @@ cudaError_t row_inv_prox_launch(const RowArgs<T>& r, const ProxArgs<T>& p, const
 
 template <typename T, int H>
 cudaError_t row_inv_prox_fwd_launch(const RowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt, T* X) {
-    if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
+    if constexpr (row2_elems(H, 1, (int)sizeof(T)) != 0) {
         // register-plan kernel: float32, power-of-two row length, 128-thread CTAs
-        constexpr int E = row2_elems(H, 1), TPF2 = H / E, NT2 = 128, TR2 = NT2 / TPF2;
+        constexpr int E = row2_elems(H, 1, (int)sizeof(T)), TPF2 = H / E, NT2 = 128, TR2 = NT2 / TPF2;
         if (p.stw && TPF2 <= 16 && r.N0 % TR2 == 0) {
             using PL = Prox3Plan<T, H, E, 1, NT2>;
             const size_t smem2 = ((size_t)TR2 * PL::P + PL::TWLEN + PL::N1f + (PL::N1f & 1)) * sizeof(C2<T>) +
@@ -190,8 +190,8 @@ cudaError_t row_inv_prox_fwd_gen_launch(const GenRowArgs<T>& r, const PgmRowArgs
 template <typename T, int H>
 cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
                             C2<T>* Zt, const C2<T>* stw, int gated) {
-    if constexpr (sizeof(T) == 4 && row2_elems(H, 1) != 0) {
-        constexpr int E = row2_elems(H, 1), NT = kRow2Threads, TR = row2_tile(H, 1);
+    if constexpr (row2_elems(H, 1, (int)sizeof(T)) != 0) {
+        constexpr int E = row2_elems(H, 1, (int)sizeof(T)), NT = kRow2Threads, TR = row2_tile(H, 1, (int)sizeof(T));
         const size_t smem = ((size_t)TR * (H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
         const long long ntiles = (long long)(r.N0 / TR) * r.M * r.nb;
         // grid-stride over tiles: a gated launch that finds nothing to do retires in microseconds
@@ -207,8 +207,8 @@ cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const A
 template <typename T, int H, int CX>
 static cudaError_t row_inv_prox2_cx(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
-    if constexpr (sizeof(T) == 4 && row2_elems(H, CX) != 0) {
-        constexpr int E = row2_elems(H, CX), NT = kRow2Threads, TR = row2_tile(H, CX);
+    if constexpr (row2_elems(H, CX, (int)sizeof(T)) != 0) {
+        constexpr int E = row2_elems(H, CX, (int)sizeof(T)), NT = kRow2Threads, TR = row2_tile(H, CX, (int)sizeof(T));
         const size_t smem = ((size_t)CX * TR * (H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
         dim3 grid(r.N0 / TR, r.M, r.nb / CX);
         return launch(k_row_inv_prox2<T, H, E, CX, NT>, grid, dim3(NT), smem, r.stream, Zt, Y, U, st,
@@ -222,7 +222,7 @@ static cudaError_t row_inv_prox2_cx(const RowArgs<T>& r, const ProxArgs<T>& p, c
 template <typename T, int H, int CX, int NT>
 static cudaError_t row_inv_prox3_nt(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
-    constexpr int E = row2_elems(H, CX), TR = NT / (H / E);
+    constexpr int E = row2_elems(H, CX, (int)sizeof(T)), TR = NT / (H / E);
     if (r.N0 % TR != 0) return cudaErrorInvalidValue;
     const size_t smem = Prox3Plan<T, H, E, CX, NT>::smem_bytes;
     dim3 grid(r.N0 / TR, r.M, r.nb / CX);
@@ -243,8 +243,8 @@ static cudaError_t row_inv_prox3_nt(const RowArgs<T>& r, const ProxArgs<T>& p, c
 template <typename T, int H, int CX>
 static cudaError_t row_inv_prox3_go(const RowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                     T* Y, T* U, const AdmmState<T>* st, const C2<T>* stw) {
-    if constexpr (sizeof(T) == 4 && row2_elems(H, CX) != 0) {
-        constexpr int E = row2_elems(H, CX), TPF = H / E;
+    if constexpr (row2_elems(H, CX, (int)sizeof(T)) != 0) {
+        constexpr int E = row2_elems(H, CX, (int)sizeof(T)), TPF = H / E;
         if constexpr (TPF <= 16) {
             if (p.prox_threads == 128 && r.N0 % (128 / TPF) == 0)
                 return row_inv_prox3_nt<T, H, CX, 128>(r, p, Zt, Y, U, st, stw);
@@ -279,7 +279,7 @@ cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, cons
 
 template <typename T, int N0, int CD>
 static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
-    constexpr int E = kCol2E, NT = kCol2Threads, CPG = kCol2CPG;
+    constexpr int E = col2_elems<T>(), NT = kCol2Threads, CPG = col2_cpg<T>();
     constexpr int TPF = N0 / E, NG = NT / TPF;
     const int per_cta = NG * CPG;
     const unsigned cs = (unsigned)((c.a.M + per_cta - 1) / per_cta);
@@ -336,7 +336,11 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
 
 template <typename T, int N0>
 cudaError_t col2_launch(int mode, ColLaunch<T> c, const C2<T>* stw) {
-    if constexpr (sizeof(T) == 4 && N0 >= 32 && N0 <= 512) {
+    if constexpr (N0 >= 32 && N0 <= 512 && N0 / col2_elems<T>() <= 32) {
+        if constexpr (sizeof(T) == 8) {        // float64: single-channel dictionaries only
+            if (c.a.Cd != 1) return cudaErrorInvalidValue;
+            return col2_go<T, N0, 1>(mode, c, stw);
+        }
         switch (c.a.Cd) {
             case 1: return col2_go<T, N0, 1>(mode, c, stw);
             case 2: return col2_go<T, N0, 2>(mode, c, stw);

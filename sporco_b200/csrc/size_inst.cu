@@ -22,15 +22,18 @@ namespace spcsc {
 SPCSC_INST(float)
 SPCSC_INST(double)
 
-// kernel set v2 (float only)
-template cudaError_t row_fwd2_launch<float, SPCSC_SIZE>(const RowArgs<float>&, const float*,
-                                                        const float*, const AdmmState<float>*,
-                                                        C2<float>*, const C2<float>*, int);
-template cudaError_t row_inv_prox2_launch<float, SPCSC_SIZE>(const RowArgs<float>&,
-                                                             const ProxArgs<float>&,
-                                                             const C2<float>*, float*, float*,
-                                                             const AdmmState<float>*,
-                                                             const C2<float>*);
-template cudaError_t col2_launch<float, SPCSC_SIZE>(int, ColLaunch<float>, const C2<float>*);
+// kernel set v2 (register plans; float64 with half the elements per lane)
+#define SPCSC_INST2(T)                                                                         \
+    template cudaError_t row_fwd2_launch<T, SPCSC_SIZE>(const RowArgs<T>&, const T*, const T*, \
+                                                        const AdmmState<T>*, C2<T>*,           \
+                                                        const C2<T>*, int);                    \
+    template cudaError_t row_inv_prox2_launch<T, SPCSC_SIZE>(const RowArgs<T>&,                \
+                                                             const ProxArgs<T>&, const C2<T>*, \
+                                                             T*, T*, const AdmmState<T>*,      \
+                                                             const C2<T>*);                    \
+    template cudaError_t col2_launch<T, SPCSC_SIZE>(int, ColLaunch<T>, const C2<T>*);
+
+SPCSC_INST2(float)
+SPCSC_INST2(double)
 
 }  // namespace spcsc

@@ -107,7 +107,7 @@ static cudaError_t col(int N0, int mode, const ColLaunch<T>& c) {
 template <typename T>
 static cudaError_t row_fwd2(int H, const RowArgs<T>& r, const T* A, const T* B,
                             const AdmmState<T>* st, C2<T>* Zt, const C2<T>* stw, int gated) {
-    if constexpr (sizeof(T) == 4) {
+    {
         switch (H) {
 #define X(n) case n: return row_fwd2_launch<T, n>(r, A, B, st, Zt, stw, gated);
             SPCSC_FOR_SIZES(X)
@@ -120,7 +120,7 @@ template <typename T>
 static cudaError_t row_inv_prox2(int H, const RowArgs<T>& r, const ProxArgs<T>& p,
                                  const C2<T>* Zt, T* Y, T* U, const AdmmState<T>* st,
                                  const C2<T>* stw) {
-    if constexpr (sizeof(T) == 4) {
+    {
         switch (H) {
 #define X(n) case n: return row_inv_prox2_launch<T, n>(r, p, Zt, Y, U, st, stw);
             SPCSC_FOR_SIZES(X)
@@ -131,7 +131,7 @@ static cudaError_t row_inv_prox2(int H, const RowArgs<T>& r, const ProxArgs<T>& 
 }
 template <typename T>
 static cudaError_t col2(int N0, int mode, const ColLaunch<T>& c, const C2<T>* stw) {
-    if constexpr (sizeof(T) == 4) {
+    {
         switch (N0) {
 #define X(n) case n: return col2_launch<T, n>(mode, c, stw);
             SPCSC_FOR_SIZES(X)
@@ -469,9 +469,9 @@ class Engine : public spcsc_handle {
             const char* fz = getenv("SPCSC_FUSE");
             fuse = v2_rowf && v2_rowp && !(fz && std::string(fz) == "0");
             int rc;
-            if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1)))) return rc;
-            if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx)))) return rc;
-            if (v2_col && (rc = upload_stage_tw(stw_col, N0, kCol2E))) return rc;
+            if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1, (int)sizeof(T))))) return rc;
+            if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx, (int)sizeof(T))))) return rc;
+            if (v2_col && (rc = upload_stage_tw(stw_col, N0, col2_elems<T>()))) return rc;
         }
         // default weights: scalar 1
         const T one = 1;

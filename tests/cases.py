@@ -143,6 +143,14 @@ FRESH_CASES = [
 ]
 
 
+FRESH_CASES_F64 = [
+    # float64 on the register plans: 8 elements per lane, one column per lane group
+    (64, 128, 12, 2, None, None, None),                    # rows H=64, 8-column CTAs: cluster of 2
+    (256, 256, 20, 1, None, None, {'NonNegCoef': True}),   # the benchmark's transform sizes, cluster of 3
+    (128, 64, 6, 2, 2, 0.05, None),                        # joint prox, CX=2
+]
+
+
 def run_pgm_cases(sfx):
     """PGM / FISTA golden problems (fixed step and standard backtracking)."""
     from sporco_b200.pgm import cbpdn as pcbpdn

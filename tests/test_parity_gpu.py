@@ -118,6 +118,14 @@ def test_register_plan_kernels_vs_oracle(case):
     cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
 
 
+@pytest.mark.parametrize('case', cases.FRESH_CASES_F64)
+def test_register_plan_kernels_float64_vs_oracle(case):
+    N0, N1, M, K, C, mu, extra = case
+    b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra, dt=np.float64, tol=1e-9)
+    info = b._h.admm_schedule_info()
+    assert info['col_v2'] and info['prox_v2']
+
+
 def test_kernel_sets_agree(monkeypatch):
     """The general kernels (v1) and the register-plan kernels (v2) on the same problem."""
     b2, r = cases.run_fresh_case(256, 256, 64, 2, iters=12)
