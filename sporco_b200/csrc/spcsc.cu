@@ -434,6 +434,12 @@ class Engine : public spcsc_handle {
         pgA.release(); pgB.release(); Zt2.release();
         cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
+#ifndef SPCSC_EMU
+        if (p2p_on)
+            for (int r = 0; r < p2p.nranks; ++r)
+                if (r != p2p.rank && p2p.peer[r]) cudaIpcCloseMemHandle(p2p.peer[r]);
+        if (p2p_own) cudaFree(p2p_own);
+#endif
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : prof_ev) cudaEventDestroy(e);
