@@ -14,7 +14,6 @@ import hashlib
 import os
 import shutil
 import subprocess
-import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)

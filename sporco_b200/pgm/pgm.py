@@ -8,11 +8,9 @@ the sums entering F, Q and the residual) is a batch of CUDA kernels behind
 
 import copy
 
-import numpy as np
-
 from .. import cdict, common, util
-from .momentum import MomentumNesterov, MomentumBase
-from .backtrack import BacktrackStandard, BacktrackRobust
+from .momentum import MomentumNesterov
+from .backtrack import BacktrackRobust
 
 
 class PGM(common.IterativeSolver):

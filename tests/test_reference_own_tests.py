@@ -13,7 +13,6 @@ import sys
 import types
 import warnings
 
-import numpy as np
 import pytest
 
 from sporco_b200 import _lib
