@@ -415,6 +415,60 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         sums[ACC_S2] = ss2.re + ss2.im;
         sums[ACC_L1] = fabs(w1u[0]) * sabs;
         if (prm.joint) sums[ACC_L21] = w21u * sabs;
+    } else if constexpr (PLAIN && CX > 1) {
+        // Several coefficient channels, common configuration: the same packed (re, im)-pair arithmetic;
+        // the l2 shrinkage over the channel axis (prox_sl1l2) is one factor per pixel.
+        C2<T> sx2 = mk<T>(0, 0), sy2 = sx2, su2 = sx2, sr2 = sx2, ss2 = sx2;
+        T sl1 = 0, sl21 = 0;
+        const T mrw = mr * w21u;
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) {
+            const int j = t + TPF * p;
+            C2<T> xs[CX], ax[CX], us[CX], yp[CX], w[CX];
+            C2<T> a2 = mk<T>(0, 0), g2 = mk<T>(0, 0);
+            SPCSC_UNROLL
+            for (int c = 0; c < CX; ++c) {
+                yp[c] = ybuf[c * YS + yrow + j];
+                xs[c] = pmul(v[c][p], scale);
+                us[c] = pmul(ubuf[c * YS + yrow + j], uinv);
+                ax[c] = relax ? pfma(xs[c], rlx, pmul(yp[c], rl1)) : xs[c];
+                const C2<T> vv = ax[c] + us[c];
+                const T thr = lr * w1u[c];
+                w[c] = vv - mk<T>(fmin(fmax(vv.re, -thr), thr), fmin(fmax(vv.im, -thr), thr));
+                a2 = pfma(w[c], w[c], a2);
+                g2 = pfma(xs[c], xs[c], g2);
+                sl1 += fabs(w1u[c]) * (fabs(xs[c].re) + fabs(xs[c].im));
+            }
+            C2<T> fac = mk<T>(1, 1);
+            if (prm.joint) {
+                const T a0 = sqrt(a2.re), a1 = sqrt(a2.im);
+                fac = mk<T>(a0 != (T)0 ? fmax((T)0, a0 - mrw) / a0 : (T)0,
+                            a1 != (T)0 ? fmax((T)0, a1 - mrw) / a1 : (T)0);
+                sl21 += w21u * (sqrt(g2.re) + sqrt(g2.im));
+            }
+            SPCSC_UNROLL
+            for (int c = 0; c < CX; ++c) {
+                const C2<T> y = prm.joint ? pfma(w[c], fac, mk<T>(0, 0)) : w[c];
+                const C2<T> u = us[c] + (ax[c] - y);
+                const C2<T> dr = xs[c] - y, ds = yp[c] - y;
+                sx2 = pfma(xs[c], xs[c], sx2);
+                sy2 = pfma(y, y, sy2);
+                su2 = pfma(u, u, su2);
+                sr2 = pfma(dr, dr, sr2);
+                ss2 = pfma(ds, ds, ss2);
+                const size_t off = ((((size_t)(k * CX + c) * M + m) * N0 + h) * H + j);
+                reinterpret_cast<C2<T>*>(Y)[off] = y;
+                reinterpret_cast<C2<T>*>(U)[off] = u;
+                v[c][p] = y - u;                               // next x-step input, if rho stays
+            }
+        }
+        sums[ACC_X2] = sx2.re + sx2.im;
+        sums[ACC_Y2] = sy2.re + sy2.im;
+        sums[ACC_U2] = su2.re + su2.im;
+        sums[ACC_R2] = sr2.re + sr2.im;
+        sums[ACC_S2] = ss2.re + ss2.im;
+        sums[ACC_L1] = sl1;
+        sums[ACC_L21] = sl21;
     } else {
     SPCSC_UNROLL
     for (int p = 0; p < E; ++p) {
