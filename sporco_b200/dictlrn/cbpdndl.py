@@ -210,6 +210,8 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
         """Shard the training images over the ranks of a ``torch.distributed`` group: every rank
         codes its own images; the dictionary gradient and the data-fidelity value are summed
         over ranks on the device (NCCL), so all ranks hold the same dictionary."""
+        if self.xmethod != 'admm':
+            raise NotImplementedError('sharding over GPUs is implemented for the ADMM X step')
         self.xstep.attach_process_group(dist, group)
 
 
