@@ -6,7 +6,9 @@ with its default solvers: X-step = one ADMM ConvBPDN iteration per outer iterati
 constrained convolutional MOD problem (sporco/pgm/ccmod.py:28-404, pgm/pgm.py:328-370), the
 alternation of sporco/dictlrn/dictlrn.py:327-363 and the constraint-set projection
 ``Pcn`` (sporco/cnvrep.py:868-1074: crop to the filter support, optional zero mean, unit
-norm).  Single-channel dictionary and signal (C = Cd = 1), one support size.
+norm).  Greyscale, single-channel dictionary with multi-channel signals (the channels then act as
+further images in the D step, pgm/ccmod.py:232-237, 264-281) and multi-channel dictionaries; one
+support size.  Signals are given as (N0, N1, K) or (N0, N1, C, K).
 Pinned bit-for-bit to the live reference by oracle/make_golden.py (fixture tests/golden/cdl_*.npz).
 """
 
@@ -18,7 +20,7 @@ from . import cbpdn_oracle as co
 
 
 def pcn(x, dsz, Nv, zm=False):
-    """normalise(zeromean(zpad(bcrop(x)))) for x of shape (N0, N1, 1, 1, M)  (cnvrep.py:953-1033)."""
+    """normalise(zeromean(zpad(bcrop(x)))) for x of shape (N0, N1, Cd, 1, M)  (cnvrep.py:953-1033)."""
     h, w = dsz[0], dsz[1]
     c = x[0:h, 0:w]
     p = np.zeros(x.shape, dtype=x.dtype)
@@ -65,32 +67,38 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
     dtype = np.dtype(S.dtype)
     rdt = co._rdt(dtype)
     dsz = D0.shape
-    N0, N1, K = S.shape[0], S.shape[1], S.shape[2]
+    Cd = D0.shape[2] if D0.ndim == 4 else 1
+    C = S.shape[2] if S.ndim == 4 else 1
+    N0, N1, K = S.shape[0], S.shape[1], S.shape[-1]
     M = D0.shape[-1]
+    Cx = C - Cd + 1
     Nv = (N0, N1)
-    axN, axK, axM = (0, 1), 3, 4
+    axN, axC, axK, axM = (0, 1), 2, 3, 4
 
     # ---- initial dictionary: cropped + normalised (cbpdndl.py:448-454)
-    Dn = np.zeros((dsz[0], dsz[1], 1, 1, M), dtype=D0.dtype)
-    Dn[...] = D0.reshape(dsz[0], dsz[1], 1, 1, M)
+    Dn = np.zeros((dsz[0], dsz[1], Cd, 1, M), dtype=D0.dtype)
+    Dn[...] = D0.reshape(dsz[0], dsz[1], Cd, 1, M)
     if do['ZeroMean']:
         Dn = Dn - np.mean(Dn, (0, 1))
     vn = np.sqrt(np.sum(Dn ** 2, (0, 1, 2), keepdims=True))
     vn[vn == 0] = 1.0
     Dn = np.asarray(Dn / vn, dtype=D0.dtype)
-    X0d = np.zeros((N0, N1, 1, 1, M), dtype=D0.dtype)
+    X0d = np.zeros((N0, N1, Cd, 1, M), dtype=D0.dtype)
     X0d[0:dsz[0], 0:dsz[1]] = Dn
 
     # ---- X-step state (admm/cbpdn.py ctor)
-    Sm = np.asarray(S.reshape(N0, N1, 1, K, 1), dtype=dtype)
+    Sm = np.asarray(S.reshape(N0, N1, C, K, 1), dtype=dtype)
     Sf = fft.rfftn(Sm, None, axN)
+    # D step: with a single-channel dictionary the channels of the signal count as images
+    Sd = Sm.reshape(N0, N1, 1, C * K, 1) if (Cd == 1 and C > 1) else Sm
+    Sdf = fft.rfftn(Sd, None, axN)
     lm = rdt.type(lmbda)
     rho = rdt.type(xo['rho']) if xo['rho'] is not None else rdt.type(50.0 * lm + 1.0)
     tau, mur = rdt.type(ar['Scaling']), rdt.type(ar['RsdlRatio'])
     xi = rdt.type(ar['RsdlTarget'])
     rlx = rdt.type(xo['RelaxParam'])
-    Y = np.zeros((N0, N1, 1, K, M), dtype)
-    U = np.zeros((N0, N1, 1, K, M), dtype)
+    Y = np.zeros((N0, N1, Cx, K, M), dtype)
+    U = np.zeros((N0, N1, Cx, K, M), dtype)
     Dcur = np.asarray(Dn, dtype=dtype)
     Nx = np.prod(np.array(Y.shape))
     kx = 0
@@ -111,9 +119,14 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
         # ================= X step: one ADMM iteration =================
         Df = fft.rfftn(Dcur, Nv, axN)
         DSf = np.conj(Df) * Sf
+        if Cd > 1:
+            DSf = np.sum(DSf, axis=axC, keepdims=True)
         Yprev = Y.copy()
         b = DSf + rho * fft.rfftn(Y - U, None, axN)
-        Xf = co.solvedbi_sm(Df, rho, b, axM)
+        if Cd == 1:
+            Xf = co.solvedbi_sm(Df, rho, b, axM)
+        else:
+            Xf = co.solvemdbi_ism(Df, rho, b, axM, axC)
         X = fft.irfftn(Xf, Nv, axN)
         AX = X if rlx == 1.0 else rlx * X + (1 - rlx) * Y
         Y = co.prox_l1(AX + U, (lm / rho))
@@ -158,10 +171,11 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
             U = (U / rsf).astype(dtype, copy=False)
         kx += 1
         # ================= D step: one PGM iteration on the dictionary =================
-        Zf = fft.rfftn(Y, Nv, axN)                              # setcoef (pgm/ccmod.py:264-281)
+        Zc = Y.reshape(N0, N1, 1, Cx * K, M) if (Cd == 1 and C > 1) else Y
+        Zf = fft.rfftn(Zc, Nv, axN)                             # setcoef (pgm/ccmod.py:264-281)
         Xdfprv = Xdf.copy()
         Ydfprv = Ydf.copy()
-        Ryf = co.inner(Zf, Ydf, axM) - Sf
+        Ryf = co.inner(Zf, Ydf, axM) - Sdf
         gradf = co.inner(np.conj(Zf), Ryf, axK)
         if reduce is not None:                                   # sum of the shards' gradients
             gradf = (reduce(gradf.real.astype(np.float64)) + 1j * reduce(gradf.imag.astype(np.float64))
@@ -182,7 +196,7 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
                           ('D_Rsdl', drsdl)):
             cols[name].append(float(val))
     out = {k: np.array(v, dtype=np.float64) for k, v in cols.items()}
-    out['D'] = Dcur.reshape(dsz[0], dsz[1], M)
+    out['D'] = Dcur.reshape(dsz)
     out['X'] = Y
     out['time'] = time.perf_counter() - t0
     return out

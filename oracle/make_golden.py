@@ -145,6 +145,8 @@ CDL_OPT_ZM = {'MaxMainIter': 20, 'CBPDN': {'NonNegCoef': True},
               'CCMOD': {'L': 60.0, 'ZeroMean': True}}
 
 
+CDL_OPT_CLR = {'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}},
+               'CCMOD': {'L': 60.0, 'ZeroMean': True}}
 CDL_OPT_PGMX = {'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}
 
 
@@ -290,6 +292,10 @@ def main():
         S4 = rng.standard_normal((32, 32, 4)).astype(dt)
         cdl_case('cdl_' + sfx, dt, D0, S4, 0.1, CDL_OPT)
         cdl_case('cdl_zm_' + sfx, dt, D0, S4, 0.2, CDL_OPT_ZM)
+        Sc = rng.standard_normal((32, 32, 3, 2)).astype(dt)
+        D0c = rng.standard_normal((6, 6, 3, 5)).astype(dt)
+        cdl_case('cdl_clr1_' + sfx, dt, D0, Sc, 0.1, CDL_OPT_CLR)      # greyscale dictionary, colour signals
+        cdl_case('cdl_clr3_' + sfx, dt, D0c, Sc, 0.1, CDL_OPT_CLR)     # colour dictionary
         cdl_ref_case('cdl_accdfid_' + sfx, dt, D0, S4, 0.1, dict(CDL_OPT, AccurateDFid=True), 'admm')
         cdl_ref_case('cdl_pgmx_' + sfx, dt, D0, S4, 0.1, CDL_OPT_PGMX, 'pgm')
 

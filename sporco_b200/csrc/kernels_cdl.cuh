@@ -22,11 +22,14 @@ enum { ACC_CDL_F = 8, ACC_CDL_DFID = 9, ACC_CDL_RSDL = 10, ACC_CDL_CNS = 11 };
 // One CTA per (wf, tile of HT=32 frequencies h): threads = 32 h-lanes x 8 filter groups.
 // For every image k: R_k[h] = sum_m Zf[k][m][h] Yf[m][h] - Sf[k][h];  g[m][h] += conj(Zf[k][m][h]) R_k[h].
 // GRAD == false: only the (plain and Hermitian-weighted) sums of |R_k|^2 are accumulated.
+// Sf holds sfs channel planes per image; this launch uses plane sfc (multi-channel dictionaries
+// run one launch per channel; with a single-channel dictionary the K "images" are all
+// (image, channel) pairs and sfs = 1).
 template <typename T, int MI, bool GRAD>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(256)
 k_ccmod_grad(const C2<T>* SPCSC_RESTRICT Zf, const C2<T>* SPCSC_RESTRICT Yf,
              const C2<T>* SPCSC_RESTRICT Sf, C2<T>* SPCSC_RESTRICT gout, double* SPCSC_RESTRICT acc,
-             int K, int N1f, int M, int N0, int even_n1) {
+             int K, int N1f, int M, int N0, int even_n1, int sfs, int sfc) {
     __shared__ C2<T> red[8][33];
     __shared__ double dred[2 * 32];
     const int lane = threadIdx.x & 31, mg = threadIdx.x >> 5;
@@ -55,7 +58,7 @@ k_ccmod_grad(const C2<T>* SPCSC_RESTRICT Zf, const C2<T>* SPCSC_RESTRICT Yf,
         C2<T> R = mk<T>(0, 0);
         SPCSC_UNROLL
         for (int q = 0; q < 8; ++q) R = R + red[q][lane];
-        if (hv) R = R - Sf[((size_t)k * N1f + wf) * N0 + h];
+        if (hv) R = R - Sf[(((size_t)k * sfs + sfc) * N1f + wf) * N0 + h];      // image k, channel sfc of sfs
         __syncthreads();
         if (GRAD) {
             SPCSC_UNROLL

@@ -1124,7 +1124,8 @@ class Engine : public spcsc_handle {
     // ---- dictionary update (CCMOD by PGM) --------------------------------------------------
     int ccmod_check() {
         if (poisoned) return SPCSC_ERR_CUDA;
-        if (Cd != 1 || C != 1) FAIL(SPCSC_ERR_UNSUPPORTED, "dictionary update: single-channel dictionary and signal only");
+        // Cd == 1: the channels of the signal act as further images (pgm/ccmod.py:232-237);
+        // Cd == C > 1: every dictionary channel has its own gradient against the shared coefficients
         if (M > 128) FAIL(SPCSC_ERR_UNSUPPORTED, "dictionary update: more than 128 filters");
         if (!have_signal) FAIL(SPCSC_ERR_STATE, "dictionary update before set_signal");
         return SPCSC_OK;
@@ -1182,11 +1183,22 @@ class Engine : public spcsc_handle {
     template <bool GRAD>
     cudaError_t launch_grad(const C2<T>* yf, C2<T>* g) {
         dim3 grid(N1f, (N0 + 31) / 32);
-        if (M <= 64)
-            return launch(k_ccmod_grad<T, 8, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p,
-                          yf, (const C2<T>*)Sf.p, g, acc.p, K, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0);
-        return launch(k_ccmod_grad<T, 16, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p,
-                      yf, (const C2<T>*)Sf.p, g, acc.p, K, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0);
+        const int nimg = K * Cx;                                  // Cd == 1: (image, channel) pairs
+        const size_t plane = (size_t)N1f * M * N0;
+        for (int c = 0; c < Cd; ++c) {
+            const C2<T>* yc = yf + (size_t)c * plane;
+            C2<T>* gc = g ? g + (size_t)c * plane : nullptr;
+            const int sfs = (Cd > 1) ? C : 1, sfc = (Cd > 1) ? c : 0;
+            cudaError_t e;
+            if (M <= 64)
+                e = launch(k_ccmod_grad<T, 8, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p, yc,
+                           (const C2<T>*)Sf.p, gc, acc.p, nimg, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0, sfs, sfc);
+            else
+                e = launch(k_ccmod_grad<T, 16, GRAD>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p, yc,
+                           (const C2<T>*)Sf.p, gc, acc.p, nimg, N1f, M, N0, (N1 % 2 == 0) ? 1 : 0, sfs, sfc);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
     }
     int ccmod_step(double L, double coef, int flags, double* out) override {
         int rc = ccmod_check();

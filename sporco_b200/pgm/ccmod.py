@@ -9,8 +9,8 @@ sequence, as the reference does.  When the object is built by
 :class:`sporco_b200.dictlrn.cbpdndl.ConvBPDNDictLearn` it shares the X step's handle, so
 coefficient maps and dictionary pass between the two steps without leaving the GPU.
 
-Supported: single-channel dictionary and signal, one filter-support size, fixed step 1/L with
-Nesterov (or linear) momentum.  Backtracking, ``Monotone`` and ``StepSizePolicy`` raise
+Supported: greyscale and multi-channel signals with a single-channel or a multi-channel
+dictionary, one filter-support size, fixed step 1/L with Nesterov (or linear) momentum.  Backtracking, ``Monotone`` and ``StepSizePolicy`` raise
 ``NotImplementedError``.
 """
 
@@ -40,9 +40,6 @@ class ConvCnstrMOD(pgm.PGMDFT):
         opt = self._coerce_options(opt)
         self.cri = cr.CDU_ConvRepIndexing(dsz, S, dimK=dimK, dimN=dimN)
         cri = self.cri
-        if cri.Cd != 1 or cri.C != 1:
-            raise NotImplementedError('the device dictionary update handles single-channel '
-                                      'dictionaries and signals')
         if opt['Backtrack'] is not None:
             raise NotImplementedError('backtracking is not implemented for the device '
                                       'dictionary update')

@@ -349,6 +349,10 @@ CDL_CASES = {
     'cdl_zm': ({'MaxMainIter': 20, 'CBPDN': {'NonNegCoef': True},
                 'CCMOD': {'L': 60.0, 'ZeroMean': True}}, 'admm', 0.2),
     'cdl_accdfid': (dict(CDL_OPT, AccurateDFid=True), 'admm', 0.1),
+    'cdl_clr1': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}},
+                  'CCMOD': {'L': 60.0, 'ZeroMean': True}}, 'admm', 0.1),       # colour signals, greyscale dictionary
+    'cdl_clr3': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}},
+                  'CCMOD': {'L': 60.0, 'ZeroMean': True}}, 'admm', 0.1),       # colour dictionary
     'cdl_pgmx': ({'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}, 'pgm', 0.1),
 }
 
@@ -379,8 +383,7 @@ def run_cdl_case(tag, sfx):
     lim = 1e-12 if sfx == 'f64' else 1e-5
     assert np.max(np.abs(its.Cnstr)) < lim and np.max(np.abs(g['Cnstr'])) < lim
     # learned filters: unit norm, support respected, dictionary handed to the X step
-    Dc = D.reshape(D.shape[0], D.shape[1], -1)
-    assert np.allclose(np.sqrt(np.sum(Dc.astype(np.float64) ** 2, (0, 1))), 1.0,
+    assert np.allclose(np.sqrt(np.sum(D.astype(np.float64) ** 2, (0, 1, 2))), 1.0,      # over support and channels
                        atol=1e-12 if sfx == 'f64' else 1e-5)
     full = b.getdict(crop=False)
     assert full.shape[:2] == g['S'].shape[:2] and not np.any(full[D.shape[0]:]) \

@@ -52,7 +52,7 @@ def test_oracle_reproduces_golden_pgm(sfx):
 
 
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
-@pytest.mark.parametrize('tag', ['cdl', 'cdl_zm'])
+@pytest.mark.parametrize('tag', ['cdl', 'cdl_zm', 'cdl_clr1', 'cdl_clr3'])
 def test_oracle_reproduces_golden_dictionary_learning(tag, sfx):
     from oracle import cbpdndl_oracle as ocdl
     g = cases.load('%s_%s' % (tag, sfx))
