@@ -193,7 +193,8 @@ int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd);
 
 /* ---- dictionary update: sporco.pgm.ccmod.ConvCnstrMOD as the D step of
    sporco.dictlrn.cbpdndl.ConvBPDNDictLearn (dictlrn/dictlrn.py:327-363), sharing the handle -- and
-   the device arrays -- of the X step.  Single-channel dictionary and signal.
+   the device arrays -- of the X step.  Greyscale; colour signals with a single-channel dictionary (the
+   channels then count as further images, pgm/ccmod.py:232-237); multi-channel dictionaries (Cd == C).
    out[] of spcsc_ccmod_step: [0] DFid = rfl2norm2(sum_m Zf Xf - Sf)/2 (pgm/ccmod.py:360-367),
    [1] Cnstr = ||Pcn(X) - X|| (:370-376), [2] Rsdl = rfl2norm2(Xf - Yfprv) (:341-345), [3] obfn_f(Yf). */
 /* X = zero-padded D0 (already normalised by the caller, cbpdndl.py:448-454), Xf = Yf = rfftn(X). */
