@@ -88,3 +88,67 @@ def test_iterationstats_fields():
         'Iter', 'ObjFun', 'DFid', 'RegL1', 'PrimalRsdl', 'DualRsdl', 'EpsPrimal', 'EpsDual',
         'Rho', 'XSlvRelRes', 'Time')
     assert cbpdn.ConvBPDNJoint.IterationStats._fields[3:5] == ('RegL1', 'RegL21')
+
+
+# ---- host helpers added with the dictionary-learning / sibling classes -------------------------
+def test_cnvrep_dictionary_helpers_match_the_oracle():
+    from oracle import cbpdndl_oracle as ocdl, cbpdn_oracle as orc
+    from sporco_b200 import cnvrep as cr
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((16, 12, 3, 1, 4))
+    for zm in (False, True):
+        a = cr.Pcn(x, (5, 4, 3, 4), (16, 12), dimN=2, dimC=1, crp=False, zm=zm)
+        assert np.allclose(a, ocdl.pcn(x, (5, 4, 3, 4), (16, 12), zm=zm), atol=1e-15)
+        c = cr.Pcn(x, (5, 4, 3, 4), (16, 12), dimN=2, dimC=1, crp=True, zm=zm)
+        assert c.shape == (5, 4, 3, 1, 4) and np.allclose(cr.zpad(c, (16, 12)), a)
+    assert np.allclose(np.sum(a ** 2, (0, 1, 2)), 1.0)
+    cri = cr.CDU_ConvRepIndexing((5, 4, 3, 4), np.zeros((16, 12, 3, 7)), dimK=1)
+    assert (cri.Cd, cri.C, cri.Cx, cri.K, cri.M) == (3, 3, 1, 7, 4) and cri.shpD == (16, 12, 3, 1, 4)
+    cri = cr.CDU_ConvRepIndexing((5, 4, 4), np.zeros((16, 12, 3, 7)), dimK=1)
+    assert (cri.Cd, cri.C, cri.Cx) == (1, 3, 3) and cri.shpX == (16, 12, 3, 7, 4)
+    with pytest.raises(NotImplementedError):
+        cr.CDU_ConvRepIndexing(((5, 5, 2), (3, 3, 2)), np.zeros((16, 12, 7)))
+    # mask shapes: same decisions as the oracle's restatement of cnvrep.mskWshape
+    for S, W in ((np.zeros((8, 8)), np.zeros((8, 8))), (np.zeros((8, 8, 3)), np.zeros((8, 8, 3))),
+                 (np.zeros((8, 8, 3, 2)), np.zeros((8, 8, 1, 2))), (np.zeros((8, 8, 3, 2)), np.zeros((8, 8, 3)))):
+        for dimK in ((None,) if S.ndim != 3 else (0, 1)):
+            c = cr.CSC_ConvRepIndexing(np.zeros((3, 3, 2)), S, dimK=dimK)
+            d = orc.Dims(np.zeros((3, 3, 2)), S, dimK=dimK)
+            assert cr.mskWshape(W, c) == orc.msk_shape(W, d)
+
+
+def test_dictionary_learning_options_tree():
+    from sporco_b200 import cdict
+    from sporco_b200.dictlrn import cbpdndl
+    from sporco_b200.admm import cbpdn
+    from sporco_b200.pgm import ccmod
+    o = cbpdndl.ConvBPDNDictLearn.Options({'CBPDN': {'AuxVarObj': True}, 'CCMOD': {'ZeroMean': True}})
+    assert isinstance(o['CBPDN'], cbpdn.ConvBPDN.Options) and isinstance(o['CCMOD'], ccmod.ConvCnstrMOD.Options)
+    assert o['CBPDN', 'MaxMainIter'] == 1 and o['CCMOD', 'MaxMainIter'] == 1
+    assert o['CBPDN', 'AutoRho', 'Period'] == 10 and o['CBPDN', 'AutoRho', 'Enabled'] is True
+    assert o['CBPDN', 'gEvalY'] is True and o['CBPDN', 'fEvalX'] is False       # AuxVarObj took effect
+    with pytest.raises(cdict.UnknownKeyError):
+        o['CCMOD', 'NoSuchKey'] = 1
+    p = cbpdndl.ConvBPDNDictLearn.Options(xmethod='pgm')
+    assert p.xmethod == 'pgm' and 'Backtrack' in p['CBPDN'] and 'AutoRho' not in p['CBPDN']
+    with pytest.raises(NotImplementedError):
+        cbpdndl.ccmod_class_label_lookup('cns')
+    from sporco_b200.dictlrn import common as dc
+    assert dc.isfld('admm', 'pgm', o) == ['Iter', 'ObjFun', 'DFid', 'RegL1', 'Cnstr', 'XPrRsdl', 'XDlRsdl',
+                                          'XRho', 'D_L', 'D_Rsdl', 'Time']
+    assert dc.isfld('pgm', 'pgm', p) == ['Iter', 'ObjFun', 'DFid', 'RegL1', 'Cnstr', 'X_L', 'X_Rsdl', 'D_L',
+                                         'D_Rsdl', 'Time']
+
+
+def test_momentum_rules_and_weight_extension():
+    from sporco_b200.pgm.momentum import MomentumNesterov, MomentumLinear, MomentumGenLinear
+    t = 1
+    for _ in range(6):
+        nxt = MomentumNesterov().update(t)
+        assert nxt == 0.5 * float(1. + np.sqrt(1. + 4. * t ** 2))             # the reference's expression
+        t = nxt
+    assert MomentumLinear(2.).update(3) == 2.5 and MomentumGenLinear(50., 2.).update(4) == 27.0
+    from sporco_cuda.cbpdn import _extend
+    assert _extend(1.0, 4, 0.0).shape == ()
+    w = _extend(np.arange(4, dtype=np.float32).reshape(1, 1, 4), 4, 0.0)
+    assert w.shape == (1, 1, 5) and w[0, 0, -1] == 0.0 and w[0, 0, 2] == 2.0
