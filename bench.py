@@ -12,8 +12,11 @@ Own arm: `value` = K iterations / device time (CUDA events on the library's stre
 resident in HBM, max over ranks); `e2e` = the same through the public class with host
 arrays in and the coefficient maps back out; `roofline` = the dominant kernel's algorithmic
 bytes / its event-timed duration against MEASURED_PEAKS.json; `cpu_baseline` = the numpy
-oracle (a restatement of the reference, bit-identical to it here) on a bounded sample.
-Reference arm (`--impl reference`): the oracle on the host cores, on a bounded sample.
+oracle (a restatement of the reference, bit-identical to it here) on the full 32-image batch for a
+few iterations; `configs` = short runs of BASELINE.json's other configurations; at N > 1
+`parity_check` = a small sharded solve against the oracle on the whole batch (the run fails if
+it disagrees).  Reference arm (`--impl reference`): the oracle on the host cores, full batch, the
+same warm-up / timed iterations of one solve as the device arm.
 """
 
 import argparse
@@ -37,6 +40,8 @@ HD = 8
 LMBDA = 0.1
 METRIC = 'ConvBPDN ADMM iterations/sec (256x256, M=64 filters, batch=32 images per GPU, float32)'
 OPT_BENCH = {'RelStopTol': 0.0, 'FastSolve': True, 'AutoRho': {'Enabled': True}}
+WORKLOAD = ('admm.cbpdn.ConvBPDN 256x256, 8x8x64 dict, 32 images per GPU, lambda=0.1, AutoRho on (period 1), '
+            'RelaxParam 1.8, FastSolve (mode B)')
 
 
 def make_inputs(k_images, seed=12345):
@@ -110,55 +115,109 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_sample(k_s, iters, kind, workers):
-    """Time the oracle on k_s images; returns it/s scaled to the 32-image workload."""
+def cpu_solve(k_images, warm, steps, kind, workers):
+    """Time the oracle (oracle/cbpdn_oracle.py: numpy restatement of the reference, pinned bit for bit to
+    it) on `k_images` images of the metric workload: ONE solve of warm + steps iterations with a time stamp
+    after every iteration; returns seconds per iteration over the last `steps` of them -- the same
+    iterations of the same solve that the device arm times."""
     from oracle import cbpdn_oracle as orc
-    D, S = make_inputs(k_s)
+    D, S = make_inputs(k_images)
     tm = {}
     opt = dict(OPT_BENCH)
-    opt['MaxMainIter'] = iters
+    opt['MaxMainIter'] = warm + steps
     orc.admm_convbpdn(D, S, LMBDA, opt=opt, dimK=1, fft=orc.FFTBackend(kind, workers), timing=tm)
-    per_iter = tm['solve'] / tm['iters']
-    return (1.0 / per_iter) * (float(k_s) / K_PER_GPU), per_iter
+    te = tm['iter_end']
+    assert len(te) == warm + steps
+    t0 = te[warm - 1] if warm > 0 else 0.0
+    return (te[-1] - t0) / steps
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (the oracle port; sporco itself is pure Python
+    over numpy / pyfftw and cannot travel to the GPU box) on the host cores, FULL metric workload:
+    32 images, `warmup` untimed + `steps` timed iterations of one solve."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    k_s = 1
-    iters = args.warmup + args.steps
-    from oracle import cbpdn_oracle as orc
-    D, S = make_inputs(k_s)
-    opt = dict(OPT_BENCH)
-    fft = orc.FFTBackend('scipy', cores)
-    # warm-up iterations are separate short solves so that K timed steps are exact
-    opt['MaxMainIter'] = max(args.warmup, 1)
-    orc.admm_convbpdn(D, S, LMBDA, opt=opt, dimK=1, fft=fft)
-    tm = {}
-    opt['MaxMainIter'] = args.steps
-    orc.admm_convbpdn(D, S, LMBDA, opt=opt, dimK=1, fft=fft, timing=tm)
-    per_iter = tm['solve'] / tm['iters']
-    value = (1.0 / per_iter) * (float(k_s) / K_PER_GPU)
-    sample = ('oracle (numpy restatement of sporco.admm.cbpdn.ConvBPDN, bit-identical to the '
-              'reference in the build container) with scipy.fft workers=%d standing in for '
-              "the reference's multi-threaded pyfftw; %d image of the %d-image batch, %d iterations; "
-              'iterations/sec scaled by %d/%d (CPU cost is at least linear in the batch)'
-              % (cores, k_s, K_PER_GPU, tm['iters'], k_s, K_PER_GPU))
+    # whole job at N GPUs = N batches of 32 images (weak scaling); the CPU arm runs them as one
+    # ConvBPDN object of 32 N images, capped at 64 images (N <= 2 exact; beyond, the 64-image time per
+    # batch is used for the remaining batches and the line says so)
+    n_batches = max(1, args.gpus)
+    run_batches = min(n_batches, 2)
+    t_wall = time.perf_counter()
+    per_iter = cpu_solve(K_PER_GPU * run_batches, args.warmup, args.steps, 'scipy', cores)
+    t_wall = time.perf_counter() - t_wall
+    value = run_batches / per_iter          # batch-iterations per second, as the device arm counts them
+    per_iter = per_iter / run_batches * n_batches
+    sample = ('oracle (numpy restatement of sporco.admm.cbpdn.ConvBPDN, bit-identical to the reference in '
+              'the build container) with scipy.fft workers=%d standing in for the reference\'s multi-threaded '
+              'pyfftw; %d images (%s), %d warm-up + %d timed iterations of one solve (%.1f s wall clock in all)'
+              % (cores, K_PER_GPU * run_batches,
+                 'the full job' if run_batches == n_batches else
+                 'of the %d of the %d-GPU job; per-batch rate assumed the same for the rest' % (K_PER_GPU * n_batches, n_batches),
+                 args.warmup, args.steps, t_wall))
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'iterations/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1000.0 / value, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': 1000.0 * per_iter, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'admm.cbpdn.ConvBPDN 256x256, 8x8x64 dict, 32 images, lambda=0.1, '
-                               'AutoRho on, FastSolve (mode B)', 'sample_images': k_s},
+        'config': {'workload': WORKLOAD, 'sample_images': K_PER_GPU * run_batches,
+                   'images_total': K_PER_GPU * n_batches, 'same_config': run_batches == n_batches},
         'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(out))
+
+
+def multi_gpu_parity(dist, rank, world, device):
+    """Untimed check run by `bench.py --gpus N>1`: a small problem sharded over the ranks (2 images each)
+    against the oracle on the WHOLE batch -- the coefficient maps of this rank's images, the rho
+    trajectory and the iteration at which the (global) stopping test fires must agree
+    (sporco/admm/admm.py:462-486: the norms are global over all images)."""
+    import torch
+    from sporco_b200.admm import cbpdn
+    from oracle import cbpdn_oracle as orc
+    rng = np.random.default_rng(77)
+    Dp = rng.standard_normal((6, 6, 8)).astype(np.float32)
+    Sp = rng.standard_normal((64, 64, 2 * world)).astype(np.float32)
+    opt = {'MaxMainIter': 60, 'RelStopTol': 4e-3, 'AutoRho': {'Enabled': True}}
+    b = cbpdn.ConvBPDN(Dp, np.ascontiguousarray(Sp[:, :, 2 * rank:2 * rank + 2]), 0.05,
+                       cbpdn.ConvBPDN.Options(opt), dimK=1, device=device)
+    b.attach_process_group(dist)
+    Y = b.solve()
+    its = b.getitstat()
+    r = orc.admm_convbpdn(Dp, Sp, 0.05, opt=opt, dimK=1)
+    Yr = r.Y[:, :, :, 2 * rank:2 * rank + 2, :].reshape(Y.shape)
+    rel_y = float(np.linalg.norm((Y - Yr).ravel()) / max(np.linalg.norm(Yr.ravel()), 1e-30))
+    rho_ref = np.array([row[8] for row in r.itstat], dtype=np.float64)
+    rho_own = np.asarray(its.Rho, dtype=np.float64)
+    same_n = len(rho_own) == len(rho_ref)
+    rho_rel = float(np.max(np.abs(rho_own - rho_ref) / rho_ref)) if same_n else float('inf')
+    t = torch.tensor([rel_y, rho_rel, 0.0 if same_n else 1.0], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rel_y, rho_rel, bad_n = (float(x) for x in t.tolist())
+    ok = bool(rel_y < 1e-4 and rho_rel < 1e-4 and bad_n == 0.0)
+    del b
+    return {'n': world, 'problem': '64x64, 6x6x8 dictionary, %d images (2 per rank), AutoRho, stop at RelStopTol 4e-3'
+            % (2 * world), 'iterations': int(len(rho_ref)), 'stop_iteration_equal': bad_n == 0.0,
+            'rel_Y': rel_y, 'rho_rel': rho_rel, 'tol': 1e-4, 'ok': ok}
+
+
+def recorded_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r02_traffic.json,
+    written by tools/ncu_summary.py from `ncu --set full`: dram__bytes_read.sum + dram__bytes_write.sum)."""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    try:
+        rec = json.load(open(p))
+    except Exception:
+        return None, None
+    for name, v in rec.get('kernels', {}).items():
+        if name.startswith(kernel):
+            return float(v['dram_bytes']), 'profiles/r02_traffic.json (%s; %s)' % (name, rec.get('source', ''))
+    return None, None
 
 
 def run_b200(args):
@@ -238,16 +297,25 @@ def run_b200(args):
         kern[names[i]] = {'ms': kms[i], 'algorithmic_GB': alg_bytes[names[i]] / 1e9,
                           'GBps': gbs, 'frac': gbs / peak}
     kern['k_admm_scalars'] = {'ms': kms[3]}
-    traffic = {'k_row_inv_prox': 3.173e9, 'k_col': 1.076e9}.get(names[dom]) if sched['fused'] else None
+    traffic, traffic_src = recorded_traffic(names[dom])
+    ms_step = ms_max / args.steps
+    iter_gb = sum(alg_bytes.values()) / 1e9
     roof = {'bound': 'hbm', 'kernel': names[dom] + (' (fused with the next row-forward)' if sched['fused'] and dom == 2 else ''),
             'achieved': kern[names[dom]]['GBps'],
             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
             'frac': kern[names[dom]]['frac'], 'traffic': traffic,
-            'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_v6_ncu_summary.md',
+            'traffic_source': traffic_src,
             'schedule': sched,
-            'iteration_algorithmic_GB': sum(alg_bytes.values()) / 1e9,
-            'iteration_frac': sum(alg_bytes.values()) / 1e9 / (sum(kms) / 1000.0) / peak,
+            'iteration_algorithmic_GB': iter_gb,
+            # of the timed loop itself (ms_per_step); iterations in which rho changed redo the row-forward
+            # pass, which the algorithmic bytes do not credit
+            'iteration_frac': iter_gb / (ms_step / 1000.0) / peak,
+            'iteration_frac_profiled_phase': iter_gb / (sum(kms) / 1000.0) / peak,
             'kernels': kern}
+
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(dist, rank, world, local_rank)
 
     # ---- end to end through the public class: host arrays in, coefficient maps out
     # (one untimed pass first: it fills the library's device / pinned allocation pools, which a
@@ -286,27 +354,39 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    if parity is not None and not parity['ok']:
+        print(json.dumps({'error': 'multi-GPU parity check failed', 'parity_check': parity}))
+        raise SystemExit(3)
+
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v_np, per_np = cpu_sample(2, 6, 'numpy', 1)
-        v_sp, per_sp = cpu_sample(2, 8, 'scipy', cores)
-        best = max(v_np, v_sp)
-        cpu = {'value': best, 'unit': 'iterations/s', 'cores': cores if v_sp >= v_np else 1,
-               'kind': 'port',
-               'sample': ('oracle (numpy restatement of the reference, bit-identical to it) on 2 of '
-                          'the 32 images, scaled by 2/32: numpy.fft as the reference runs without '
-                          'pyfftw: %.4f it/s (6 iterations, %.2f s/iter on the sample); scipy.fft '
-                          'workers=%d as a multi-threaded FFTW stand-in: %.4f it/s (8 iterations, '
-                          '%.2f s/iter)' % (v_np, per_np, cores, v_sp, per_sp))}
+        cw, cs_ = 3, 5
+        per = cpu_solve(K_PER_GPU, cw, cs_, 'scipy', cores)
+        cpu = {'value': 1.0 / per, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
+               'sample': ('oracle (numpy restatement of the reference, bit-identical to it in the build '
+                          'container) on the full 32-image batch, scipy.fft workers=%d standing in for the '
+                          "reference's multi-threaded pyfftw: %d warm-up + %d timed iterations of one solve, "
+                          '%.2f s per iteration' % (cores, cw, cs_, per))}
+
+    cfgs = None
+    if world == 1 and not args.no_configs:
+        # the other BASELINE.json configurations, short untimed-by-the-headline runs (tools/bench_configs.py)
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import bench_configs
+        cfgs = {}
+        for name in ('cfg2', 'cfg3a', 'cfg3b', 'cfg4', 'cfg5'):
+            try:
+                cfgs[name] = bench_configs.measure(name, peak, quick=True)
+            except Exception as e:        # a configuration must not take the headline line down
+                cfgs[name] = {'error': '%s: %s' % (type(e).__name__, e)}
 
     out = {
         'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'admm.cbpdn.ConvBPDN 256x256, 8x8x64 dict, 32 images per GPU, '
-                               'lambda=0.1, AutoRho on (period 1), RelaxParam 1.8, FastSolve (mode B)',
+        'config': {'workload': WORKLOAD,
                    'images_total': world * K_PER_GPU,
                    'image_iterations_per_s': img_iter_per_s,
                    'parallelism': 'images sharded %d per GPU; one allreduce of 5 doubles per iteration'
@@ -318,6 +398,10 @@ def run_b200(args):
     }
     if cpu is not None:
         out['cpu_baseline'] = cpu
+    if parity is not None:
+        out['parity_check'] = parity
+    if cfgs is not None:
+        out['configs'] = cfgs
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -330,6 +414,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-configs', action='store_true', help='skip the configs block (cfg2..cfg5)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

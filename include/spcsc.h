@@ -175,8 +175,10 @@ int spcsc_pgm_accept(spcsc_handle* h, double coef);
 /* Device-side all-reduce of the per-iteration accumulators over peer memory (NVLink / NVSwitch), replacing the
    NCCL call on that path: every rank exports a small block (CUDA IPC, 64-byte handle), the handles of all
    ranks are gathered by the caller and attached; the exchange then happens inside the scalar kernel.  Needs
-   an attached communicator (spcsc_attach_comm) first -- NCCL keeps serving the large dictionary-gradient
-   all-reduce -- and at most 8 ranks on one node.  If attaching fails the NCCL path simply stays in use. */
+   an attached communicator (spcsc_attach_comm) first and at most 8 ranks on one node.  The blocks belong to the
+   communicator: once one solver has attached them, further solvers on the same communicator pass
+   handles64 = NULL and need no exchange of handles.  nranks = 0 detaches.  If exporting or attaching fails
+   (SPCSC_ERR_UNSUPPORTED, the handle stays usable) the NCCL path simply stays in use. */
 int spcsc_p2p_export(spcsc_handle* h, void* handle64);
 int spcsc_p2p_attach(spcsc_handle* h, int32_t rank, int32_t nranks, const void* handles64);
 

@@ -510,6 +510,8 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
                 rho = rho * rdt.type(rsf)
                 U = U / rsf
                 U = U.astype(dtype, copy=False)
+        if timing is not None:
+            timing.setdefault('iter_end', []).append(time.perf_counter() - t_start)
         if need_rsdl and r < epri and s < edua:
             break
     if timing is not None:

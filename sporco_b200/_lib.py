@@ -421,6 +421,7 @@ class Comm(object):
                                          ctypes.byref(c)))
         self.c = c
         self.rank, self.nranks = rank, nranks
+        self.p2p = None        # None: peer blocks not exchanged yet; True / False: the group's decision
 
     def close(self):
         if getattr(self, 'c', None):

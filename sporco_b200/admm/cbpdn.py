@@ -242,19 +242,38 @@ class GenericConvBPDN(admm.ADMMEqual):
         # take the same decision, hence the all-reduce of the outcome
         self._p2p = False
         if 1 < world <= 8 and os.environ.get('SPCSC_P2P', '1') != '0':
+            if comm.p2p is not None:
+                # an earlier solver of this group has settled it (the blocks live with the communicator):
+                # no handle exchange, no collective
+                if comm.p2p:
+                    self._p2p = bool(self._h.p2p_attach(rank, world, None))
+                return
+            # every rank takes part in every collective below, whatever happened locally: a rank
+            # whose export failed sends a zero handle and votes "no"
+            ok = True
             try:
-                mine = torch.frombuffer(bytearray(self._h.p2p_export()), dtype=torch.uint8).to(dev)
-                allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
-                dist.all_gather(allh, mine, group=group)
-                blob = b''.join(bytes(t.cpu().numpy().tobytes()) for t in allh)
-                ok = self._h.p2p_attach(rank, world, blob)
+                raw = bytearray(self._h.p2p_export())
             except _lib.SpcscError:
+                raw, ok = bytearray(64), False
+            mine = torch.frombuffer(raw, dtype=torch.uint8).to(dev)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine, group=group)
+            flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if flag.item() == 1.0:
+                blob = b''.join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+                try:
+                    ok = bool(self._h.p2p_attach(rank, world, blob))
+                except _lib.SpcscError:
+                    ok = False
+            else:
                 ok = False
             flag = torch.tensor([1.0 if ok else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             if flag.item() != 1.0 and ok:
                 self._h.p2p_detach()
             self._p2p = bool(flag.item() == 1.0)
+            comm.p2p = self._p2p
 
     # ---- pickling: device state travels as host arrays
     def __getstate__(self):

@@ -817,7 +817,8 @@ struct P2pSlots {
 struct P2pView {
     P2pSlots* peer[kP2pMaxRanks];      // peer[r]: rank r's block as mapped here (peer[rank] = own block)
     int nranks, rank;
-    unsigned long long seq;            // exchange number, counted identically on every rank; > 0
+    unsigned long long* seq_dev;       // own exchange counter (device memory): the number of exchanges executed
+                                       // so far; every rank executes the same ones, so the counters agree
 };
 // All threads of the (single) block; blockDim.x >= ACC_N * nranks.  Returns false on time-out.
 SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
@@ -826,8 +827,15 @@ SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
     return true;
 #else
     __shared__ int timed_out;
-    const int tid = threadIdx.x, par = (int)(pv.seq & 1ull);
-    if (tid == 0) timed_out = 0;
+    __shared__ unsigned long long seq_s;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        timed_out = 0;
+        seq_s = ++(*pv.seq_dev);           // > 0; advanced only by exchanges that execute
+    }
+    __syncthreads();
+    const unsigned long long seq = seq_s;
+    const int par = (int)(seq & 1ull);
     if (tid < ACC_N * pv.nranks) {
         const int r = tid / ACC_N, i = tid % ACC_N;
         pv.peer[r]->vals[par][pv.rank][i] = acc[i];
@@ -836,12 +844,12 @@ SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
     __syncthreads();
     if (tid < pv.nranks) {
         volatile unsigned long long* f = &pv.peer[tid]->flag[par][pv.rank];
-        *f = pv.seq;
+        *f = seq;
     }
     if (tid < pv.nranks) {
         volatile unsigned long long* f = &pv.peer[pv.rank]->flag[par][tid];
         const long long t0 = clock64();
-        while (*f != pv.seq) {
+        while (*f != seq) {
             if (clock64() - t0 > 60000000000LL) { timed_out = 1; break; }     // ~30 s: ranks may start far apart
         }
     }
@@ -967,6 +975,8 @@ SPCSC_GLOBAL void k_apply_udiv(T* U, AdmmState<T>* st, size_t n) {
 }
 template <typename T>
 SPCSC_GLOBAL void k_reset_udiv(AdmmState<T>* st) { st->udiv = 1; st->zt_stale = 1; }
+template <typename T>
+SPCSC_GLOBAL void k_mark_stale(AdmmState<T>* st) { st->zt_stale = 1; }
 
 // ------------------------------------------------------------------------------------
 // Layout conversion between the reference's (N0,N1,C,K,M) order and the device order

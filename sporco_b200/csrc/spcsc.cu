@@ -267,6 +267,12 @@ struct spcsc_comm {
     void* comm = nullptr;
     NcclApi* api = nullptr;
     int rank = 0, nranks = 1, device = 0;
+    // peer-memory all-reduce (kernels.cuh, p2p_allreduce): this rank's block -- plain cudaMalloc, IPC needs
+    // it -- and the mapped blocks of all ranks.  They belong to the communicator, so every solver that
+    // attaches it shares them and only the first attachment pays for the handle exchange.
+    void* p2p_own = nullptr;
+    void* p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool p2p_ready = false;
 };
 
 struct spcsc_handle {
@@ -380,8 +386,8 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> gw_buf;                           //   per filter (mu w_m, w_m)
     std::vector<T> gr_w;                            //   host copy of w_m (mu arrives with admm_configure)
     bool gradreg = false;
-    P2pSlots* p2p_own = nullptr;                    // peer-memory all-reduce: own block (plain cudaMalloc: IPC needs it)
-    P2pView p2p{};                                  //   and the mapped blocks of all ranks
+    spcsc_comm* comm_obj = nullptr;                 // attached communicator (owns the peer-memory blocks)
+    P2pView p2p{};                                  // peer-memory all-reduce: view of the communicator's blocks
     bool p2p_on = false;
     DevBuf<T> mk_W, mk_r, mk_wr, mk_w2r;            // pgm.ConvBPDNMask: mask and signal-domain work planes [K][C][N0][N1]
     DevBuf<C2<T>> mk_f, mk_grad, mk_sx;             //   spectra [K][C][N1f][N0]: work, rfft(W^2 R_Y), s_X
@@ -408,6 +414,16 @@ class Engine : public spcsc_handle {
     int nranks = 1;
     double global_nx = 0.0;
     std::vector<cudaEvent_t> prof_ev;
+    // wavefront schedule: groups of wave_g images run row-forward -> column -> row-inverse/prox back to
+    // back, through a small scratch that stays in L2, round-robin over wave_s streams
+    int wave_g = 0, wave_s = 1;
+    bool wave_keep = true;                          // the column kernel stores the X spectra in Zt (get_array(X))
+    bool wave_batch = false, wave_persist_set = false;
+    bool wave_fused = false;                        // groups through column + prox only, cross-iteration fusion kept
+    std::vector<cudaStream_t> wstreams;             // [0] is `stream`
+    std::vector<cudaEvent_t> wjoin;
+    cudaEvent_t wfork = nullptr;
+    DevBuf<C2<T>> wscratch;
     float last_ms = 0.f;
     int64_t last_launches = 0;
 
@@ -435,13 +451,13 @@ class Engine : public spcsc_handle {
         cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
 #ifndef SPCSC_EMU
-        if (p2p_on)
-            for (int r = 0; r < p2p.nranks; ++r)
-                if (r != p2p.rank && p2p.peer[r]) cudaIpcCloseMemHandle(p2p.peer[r]);
-        if (p2p_own) cudaFree(p2p_own);
 #endif
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        wscratch.release();
+        for (size_t i = 1; i < wstreams.size(); ++i) cudaStreamDestroy(wstreams[i]);
+        for (auto e : wjoin) cudaEventDestroy(e);
+        if (wfork) cudaEventDestroy(wfork);
         for (auto e : prof_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -474,6 +490,15 @@ class Engine : public spcsc_handle {
             v2_col = allow2 && !gen_cols && col2_ok<T>(N0, M, Cd);
             const char* fz = getenv("SPCSC_FUSE");
             fuse = v2_rowf && v2_rowp && !(fz && std::string(fz) == "0");
+            if (const char* wv = getenv("SPCSC_WAVE")) {
+                int g = 0, ns = 1;
+                if (sscanf(wv, "%d,%d", &g, &ns) >= 1 && g > 0) {
+                    wave_g = g < K ? g : K;
+                    wave_s = ns < 1 ? 1 : (ns > 8 ? 8 : ns);
+                }
+            }
+            if (const char* wk = getenv("SPCSC_WAVE_KEEP")) wave_keep = atoi(wk) != 0;
+            if (const char* wf = getenv("SPCSC_WAVE_FUSED")) wave_fused = atoi(wf) != 0;
             int rc;
             if (v2_rowf && (rc = upload_stage_tw(stw_row1, H, row2_elems(H, 1, (int)sizeof(T))))) return rc;
             if (v2_rowp && (rc = upload_stage_tw(stw_rowc, H, row2_elems(H, Cx, (int)sizeof(T))))) return rc;
@@ -733,6 +758,170 @@ class Engine : public spcsc_handle {
         return SPCSC_OK;
     }
 
+    std::vector<int> prof_kind;                     // kind of the interval that ends at prof_ev[i] (-1: start)
+    cudaError_t prof_mark(int kind) {
+        const size_t i = prof_kind.size();
+        while (prof_ev.size() <= i) {
+            cudaEvent_t e;
+            cudaError_t ce = cudaEventCreate(&e);
+            if (ce != cudaSuccess) return ce;
+            prof_ev.push_back(e);
+        }
+        prof_kind.push_back(kind);
+        return cudaEventRecord(prof_ev[i], stream);
+    }
+
+    // Wavefront schedule (register-plan kernels): the batch is cut into groups of wave_g images; a group runs
+    // row-forward -> column -> row-inverse/prox back to back through a scratch of one group's row spectra, which
+    // therefore lives in L2: per iteration DRAM sees Y and U read twice and written once (6 B_r; 7 B_r when the
+    // X spectra are kept for get_array(X)) instead of the 8.03 B_r of the cross-iteration-fused schedule, and a
+    // change of rho costs nothing because the row spectra of Y - U are formed after the scalar kernel.  Groups
+    // go round-robin over wave_s streams (each with its own scratch) so that the tail of one group's kernel
+    // overlaps the next group's.
+    int wave_setup() {
+        const size_t gslab = (size_t)wave_g * Cx * N1f * M * N0;
+        CK(wscratch.ensure(gslab * wave_s));
+        if (wstreams.empty()) wstreams.push_back(stream);
+        while ((int)wstreams.size() < wave_s) {
+            cudaStream_t s2;
+            CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            wstreams.push_back(s2);
+        }
+        while ((int)wjoin.size() < wave_s) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            wjoin.push_back(e);
+        }
+        if (!wfork) CK(cudaEventCreateWithFlags(&wfork, cudaEventDisableTiming));
+#ifndef SPCSC_EMU
+        if (!wave_persist_set) {
+            wave_persist_set = true;
+            const char* wp = getenv("SPCSC_WAVE_PERSIST");
+            if (wp && atoi(wp) > 0) {
+                // optional: pin each stream's scratch in the persisting part of L2
+                cudaDeviceProp prop;
+                CK(cudaGetDeviceProperties(&prop, pb.device));
+                size_t want = gslab * sizeof(C2<T>) * wave_s;
+                if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+                CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+                for (int si = 0; si < wave_s; ++si) {
+                    cudaStreamAttrValue av;
+                    memset(&av, 0, sizeof(av));
+                    size_t bytes = gslab * sizeof(C2<T>);
+                    if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+                    av.accessPolicyWindow.base_ptr = (void*)(wscratch.p + gslab * si);
+                    av.accessPolicyWindow.num_bytes = bytes;
+                    av.accessPolicyWindow.hitRatio = 1.0f;
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    CK(cudaStreamSetAttribute(wstreams[si], cudaStreamAttributeAccessPolicyWindow, &av));
+                }
+            }
+        }
+#endif
+        return SPCSC_OK;
+    }
+
+    int launch_wave(int n, int k_base, bool prof, const ProxArgs<T>& pa0, const ColLaunch<T>& cs0) {
+        int rc = wave_setup();
+        if (rc) return rc;
+        const int ns = prof ? 1 : wave_s;
+        const size_t gslab = (size_t)wave_g * Cx * N1f * M * N0;
+        const size_t img_r = (size_t)Cx * M * N0 * N1, img_z = (size_t)Cx * N1f * M * N0;
+        const int ngroups = (K + wave_g - 1) / wave_g;
+        C2<T>* zin = Zt.p;
+        C2<T>* zoth = nullptr;
+        if (wave_fused) {
+            CK(Zt2.ensure(nslab));
+            zoth = Zt2.p;
+            fused_batch = true;
+        } else {
+            wave_batch = true;
+        }
+        if (prof) CK(prof_mark(-1));
+        for (int it = 0; it < n; ++it) {
+            if (wave_fused) {       // the spectra the prox kernel wrote are stale only when rho changed
+                CK(row_fwd2<T>(H, rowargs(M, K * Cx, 1), (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p,
+                               zin, (const C2<T>*)stw_row1.p, 1));
+                if (prof) CK(prof_mark(0));
+                last_launches += 1;
+            }
+            if (ns > 1) {
+                CK(cudaEventRecord(wfork, stream));
+                for (int s = 1; s < ns; ++s) CK(cudaStreamWaitEvent(wstreams[s], wfork, 0));
+            }
+            for (int j = 0; j < ngroups; ++j) {
+                const int k0 = j * wave_g, gk = (K - k0 < wave_g) ? (K - k0) : wave_g;
+                const int si = j % ns;
+                cudaStream_t sq = wstreams[si];
+                C2<T>* zs = wscratch.p + gslab * si;
+                T* yg = Y.p + img_r * k0;
+                T* ug = U.p + img_r * k0;
+                ColLaunch<T> cs = cs0;
+                cs.stream = sq;
+                cs.nb = gk * Cx;
+                cs.Sf = Sf.p + (size_t)k0 * C * N1f * N0;
+                ProxArgs<T> pa = pa0;
+                pa.znext = nullptr;
+                if (wave_fused) {
+                    cs.in = zin + img_z * k0;
+                    cs.out = zin + img_z * k0;
+                    pa.znext = (void*)(zoth + img_z * k0);
+                } else {
+                    RowArgs<T> rf = rowargs(M, gk * Cx, 1);
+                    rf.stream = sq;
+                    CK(row_fwd2<T>(H, rf, (const T*)yg, (const T*)ug, (const AdmmState<T>*)st.p, zs,
+                                   (const C2<T>*)stw_row1.p, 0));
+                    if (prof) CK(prof_mark(0));
+                    last_launches += 1;
+                    cs.in = zs;
+                    cs.out = wave_keep ? Zt.p + img_z * k0 : zs;
+                }
+                CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
+                if (prof) CK(prof_mark(1));
+                RowArgs<T> rp = rowargs(M, gk * Cx, Cx);
+                rp.stream = sq;
+                pa.wl1.p += (size_t)k0 * pa.wl1.sk;
+                pa.wl21.p += (size_t)k0 * pa.wl21.sk;
+                CK(row_inv_prox2<T>(H, rp, pa, (const C2<T>*)cs.out, yg, ug, (const AdmmState<T>*)st.p,
+                                    (const C2<T>*)stw_rowc.p));
+                if (prof) CK(prof_mark(2));
+                last_launches += 2;
+            }
+            if (ns > 1) {
+                for (int s = 1; s < ns; ++s) {
+                    CK(cudaEventRecord(wjoin[s], wstreams[s]));
+                    CK(cudaStreamWaitEvent(stream, wjoin[s], 0));
+                }
+            }
+            rc = launch_scalars(k_base, n);
+            if (rc) return rc;
+            last_launches += 1;
+            if (prof) CK(prof_mark(3));
+            if (wave_fused) std::swap(zin, zoth);
+        }
+        return SPCSC_OK;
+    }
+
+    // the exchange of the residual / objective sums (multi-GPU) and the scalar kernel
+    int launch_scalars(int k_base, int n) {
+        P2pView pv{};
+        if (p2p_on && (prm.need_rsdl || prm.need_obj)) {
+            pv = p2p;
+        } else if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
+            // the one exchange of the path: sum the residual / objective accumulators over ranks
+            CK(launch(k_fold_bins<0>, dim3(1), dim3(256), 0, stream, acc.p));
+            int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
+            if (nr != 0) {
+                err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr);
+                poisoned = true;
+                return SPCSC_ERR_NCCL;
+            }
+        }
+        CK(launch(k_admm_scalars<T>, dim3(1), dim3(256), 0, stream, st.p, prm, acc.p, rows.p, k_base, n, pv));
+        return SPCSC_OK;
+    }
+
     // Launch n iterations on the stream.  With `prof` set, an event is recorded after every
     // kernel (prof_ev holds 4*n+1 events).
     int launch_iterations(int n, int k_base, bool prof) {
@@ -768,12 +957,17 @@ class Engine : public spcsc_handle {
         cs.a.dfid_on = (prm.need_obj && !prm.dfid_direct) ? 1 : 0;
         const bool aux_eval = prm.need_obj && prm.dfid_direct;
         if (aux_eval) CK(Zscratch.ensure(nslab));
-        int ne = 0;
         last_launches = 0;
         C2<T>* zin = Zt.p;
         C2<T>* zoth = nullptr;
         fused_batch = false;
-        if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+        wave_batch = false;
+        prof_kind.clear();
+        const bool wave = wave_g > 0 && v2_rowf && v2_rowp && v2_col && !check && !aux_eval && !prm.enet &&
+                          !prm.gradreg && !pa.use_v2_sync && (!opts.joint || wl21.spatial_uniform || Cx > 1) &&
+                          (!wave_fused || fuse);
+        if (wave) return launch_wave(n, k_base, prof, pa, cs);
+        if (prof) CK(prof_mark(-1));
         for (int it = 0; it < n; ++it) {
             const bool fuse_now = fuse && !check && !pa.use_v2_sync &&
                                   (!opts.joint || wl21.spatial_uniform || Cx > 1);
@@ -787,7 +981,7 @@ class Engine : public spcsc_handle {
                                (const C2<T>*)stw_row1.p, fuse_now ? 1 : 0));
             else
                 CK(row_fwd<T>(H, rf, (const T*)Y.p, (const T*)U.p, (const AdmmState<T>*)st.p, zin));
-            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            if (prof) CK(prof_mark(0));
             if (!check) {
                 cs.in = zin; cs.out = zin;
                 if (v2_col && !prm.enet && !prm.gradreg)   // l2 / gradient terms: general kernel only
@@ -812,14 +1006,14 @@ class Engine : public spcsc_handle {
                 CK(col<T>(N0, COL_INV, c3));
                 last_launches += 7;
             }
-            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            if (prof) CK(prof_mark(1));
             pa.znext = fuse_now ? (void*)zoth : nullptr;
             if (v2_rowp)
                 CK(row_inv_prox2<T>(H, rp, pa, (const C2<T>*)zin, Y.p, U.p,
                                     (const AdmmState<T>*)st.p, (const C2<T>*)stw_rowc.p));
             else
                 CK(row_inv_prox<T>(H, rp, pa, (const C2<T>*)zin, Y.p, U.p, (const AdmmState<T>*)st.p));
-            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            if (prof) CK(prof_mark(2));
             if (aux_eval) {
                 // AuxVarObj (admm/cbpdn.py:315-344 with fEvalX False): data fidelity of the
                 // auxiliary variable, 1/2 ||sum_m Df rfftn(Y) - Sf||^2, from a forward transform of Y
@@ -832,22 +1026,8 @@ class Engine : public spcsc_handle {
                 CK(col<T>(N0, COL_FWD_EVAL, ce));
                 last_launches += 2;
             }
-            P2pView pv{};
-            if (p2p_on && (prm.need_rsdl || prm.need_obj)) {
-                pv = p2p;
-                pv.seq = ++p2p.seq;               // counted identically on every rank
-            } else if (nccl_comm && (prm.need_rsdl || prm.need_obj)) {
-                // the one exchange of the path: sum the residual / objective accumulators over ranks
-                CK(launch(k_fold_bins<0>, dim3(1), dim3(256), 0, stream, acc.p));
-                int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
-                if (nr != 0) {
-                    err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr);
-                    poisoned = true;
-                    return SPCSC_ERR_NCCL;
-                }
-            }
-            CK(launch(k_admm_scalars<T>, dim3(1), dim3(256), 0, stream, st.p, prm, acc.p, rows.p, k_base, n, pv));
-            if (prof) CK(cudaEventRecord(prof_ev[ne++], stream));
+            { int rs = launch_scalars(k_base, n); if (rs) return rs; }
+            if (prof) CK(prof_mark(3));
             if (fuse_now) std::swap(zin, zoth);        // the spectra just written feed the next x-step
         }
         return SPCSC_OK;
@@ -900,6 +1080,7 @@ class Engine : public spcsc_handle {
         }
         const int done = s1.k - s0.k;
         have_x = have_x || done > 0;
+        if (wave_batch && !wave_keep && done > 0) have_x = false;   // the X spectra only ever lived in the L2 scratch
         settle_pingpong(done);
         if (out_rows && done > 0) {
             std::vector<StatRow> hr(done);
@@ -934,21 +1115,16 @@ class Engine : public spcsc_handle {
         int rc = admm_prepare(n, s0);
         if (rc) return rc;
         if (opts.linsolve_check) FAIL(SPCSC_ERR_INVALID, "profile with LinSolveCheck off");
-        while ((int)prof_ev.size() < 4 * n + 1) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e));
-            prof_ev.push_back(e);
-        }
         rc = launch_iterations(n, s0.k, true);
         if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
         for (int j = 0; j < 4; ++j) ms4[j] = 0.f;
-        for (int i = 0; i < 4 * n; ++i) {
+        for (size_t i = 1; i < prof_kind.size(); ++i) {
             float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
-            ms4[i % 4] += ms;
+            CK(cudaEventElapsedTime(&ms, prof_ev[i - 1], prof_ev[i]));
+            if (prof_kind[i] >= 0 && prof_kind[i] < 4) ms4[prof_kind[i]] += ms;
         }
-        have_x = true;
+        have_x = !(wave_batch && !wave_keep);
         {
             AdmmState<T> s1;
             rc = read_state(s1);
@@ -1021,6 +1197,9 @@ class Engine : public spcsc_handle {
         int rc;
         if (which == SPCSC_ARR_Y) {
             rc = to_internal(in, Y.p, Cx, K, M);
+            if (rc) return rc;
+            // the row spectra of Y - U that the last prox kernel wrote no longer match Y
+            CK(launch(k_mark_stale<T>, dim3(1), dim3(1), 0, stream, st.p));
         } else if (which == SPCSC_ARR_U) {
             rc = to_internal(in, U.p, Cx, K, M);
             if (rc) return rc;
@@ -1068,18 +1247,34 @@ class Engine : public spcsc_handle {
         FAIL(SPCSC_ERR_UNSUPPORTED, "peer-memory all-reduce needs real devices");
 #else
         if (poisoned) return SPCSC_ERR_CUDA;
+        if (!comm_obj) FAIL(SPCSC_ERR_STATE, "p2p_export before attach_comm");
         CK(cudaSetDevice(pb.device));
-        if (!p2p_own) {
-            CK(cudaMalloc((void**)&p2p_own, sizeof(P2pSlots)));
-            CK(cudaMemset(p2p_own, 0, sizeof(P2pSlots)));
+        // failures here are not fatal (the NCCL all-reduce stays in use): report, do not poison the handle
+        if (!comm_obj->p2p_own) {
+            void* q = nullptr;
+            cudaError_t e = cudaMalloc(&q, sizeof(P2pSlots) + sizeof(unsigned long long));
+            if (e == cudaSuccess) e = cudaMemset(q, 0, sizeof(P2pSlots) + sizeof(unsigned long long));
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                if (q) cudaFree(q);
+                err = std::string("peer block allocation: ") + cudaGetErrorString(e);
+                return SPCSC_ERR_UNSUPPORTED;
+            }
+            comm_obj->p2p_own = q;
         }
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         cudaIpcMemHandle_t hnd;
-        CK(cudaIpcGetMemHandle(&hnd, p2p_own));
+        cudaError_t e = cudaIpcGetMemHandle(&hnd, comm_obj->p2p_own);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+            return SPCSC_ERR_UNSUPPORTED;
+        }
         memcpy(handle64, &hnd, 64);
         return SPCSC_OK;
 #endif
     }
+    // handles64 == NULL: use the mapping the communicator already holds (a solver attached earlier)
     int p2p_attach(int rank, int nr, const void* handles64) override {
 #ifdef SPCSC_EMU
         (void)rank; (void)nr; (void)handles64;
@@ -1087,25 +1282,38 @@ class Engine : public spcsc_handle {
 #else
         if (poisoned) return SPCSC_ERR_CUDA;
         if (nr == 0) { p2p_on = false; return SPCSC_OK; }      // detach
-        if (!p2p_own) FAIL(SPCSC_ERR_STATE, "p2p_attach before p2p_export");
+        if (!comm_obj || !nccl_comm || nr != nranks) FAIL(SPCSC_ERR_STATE, "attach the communicator of the same group first");
         if (nr < 2 || nr > kP2pMaxRanks || rank < 0 || rank >= nr) FAIL(SPCSC_ERR_INVALID, "rank / nranks out of range");
-        if (!nccl_comm || nr != nranks) FAIL(SPCSC_ERR_STATE, "attach the communicator of the same group first");
         CK(cudaSetDevice(pb.device));
-        P2pView v{};
-        v.nranks = nr; v.rank = rank; v.seq = 0;
-        for (int r = 0; r < nr; ++r) {
-            if (r == rank) { v.peer[r] = p2p_own; continue; }
-            cudaIpcMemHandle_t hnd;
-            memcpy(&hnd, (const char*)handles64 + 64 * (size_t)r, 64);
-            void* q = nullptr;
-            cudaError_t e = cudaIpcOpenMemHandle(&q, hnd, cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) {          // not fatal: the NCCL path stays in use
-                cudaGetLastError();
-                err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        if (!comm_obj->p2p_ready) {
+            if (!handles64) {
+                err = "the communicator holds no peer mapping yet";
                 return SPCSC_ERR_UNSUPPORTED;
             }
-            v.peer[r] = (P2pSlots*)q;
+            if (!comm_obj->p2p_own) FAIL(SPCSC_ERR_STATE, "p2p_attach before p2p_export");
+            for (int r = 0; r < nr; ++r) {
+                if (r == rank) { comm_obj->p2p_peer[r] = comm_obj->p2p_own; continue; }
+                if (comm_obj->p2p_peer[r]) continue;
+                cudaIpcMemHandle_t hnd;
+                memcpy(&hnd, (const char*)handles64 + 64 * (size_t)r, 64);
+                void* q = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&q, hnd, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {          // not fatal: the NCCL path stays in use
+                    cudaGetLastError();
+                    err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+                    return SPCSC_ERR_UNSUPPORTED;
+                }
+                comm_obj->p2p_peer[r] = q;
+            }
+            comm_obj->p2p_ready = true;
         }
+        P2pView v{};
+        v.nranks = nr; v.rank = rank;
+        // exchange counter: lives on the device (behind the own block), is zeroed with the block at allocation
+        // and advances only when an exchange really executes -- launches skipped after the stopping test fired
+        // do not count, and flags left in the peers' blocks by earlier solvers never match a new number
+        v.seq_dev = reinterpret_cast<unsigned long long*>(reinterpret_cast<P2pSlots*>(comm_obj->p2p_own) + 1);
+        for (int r = 0; r < nr; ++r) v.peer[r] = reinterpret_cast<P2pSlots*>(comm_obj->p2p_peer[r]);
         p2p = v;
         p2p_on = true;
         return SPCSC_OK;
@@ -1113,6 +1321,8 @@ class Engine : public spcsc_handle {
     }
     int attach_comm(spcsc_comm* c, double gnx) override {
         if (c && c->device != pb.device) FAIL(SPCSC_ERR_INVALID, "communicator belongs to another device");
+        comm_obj = c;
+        if (!c) p2p_on = false;
         nccl = c ? c->api : nullptr;
         nccl_comm = c ? c->comm : nullptr;
         nranks = c ? c->nranks : 1;
@@ -1250,6 +1460,9 @@ class Engine : public spcsc_handle {
                       N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
         double ha[4];
         CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        // slots ACC_CDL_* alias ADMM accumulators (ACC_AX2 ...: LinSolveCheck sums of the X step that shares
+        // this handle): leave them clean
+        CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
         CK(cudaStreamSynchronize(stream));
         const double inv_n = 1.0 / ((double)N0 * (double)N1);
         out[0] = 0.5 * ha[1] * inv_n;
@@ -1639,7 +1852,7 @@ int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0));
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
 int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
 int spcsc_p2p_export(spcsc_handle* h, void* handle64) { H_CALL(handle64 ? h->p2p_export(handle64) : SPCSC_ERR_INVALID); }
-int spcsc_p2p_attach(spcsc_handle* h, int32_t rank, int32_t nranks, const void* handles64) { H_CALL(handles64 ? h->p2p_attach(rank, nranks, handles64) : SPCSC_ERR_INVALID); }
+int spcsc_p2p_attach(spcsc_handle* h, int32_t rank, int32_t nranks, const void* handles64) { H_CALL(h->p2p_attach(rank, nranks, handles64)); }
 int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd) { H_CALL(h->set_gradreg(ghg, wgrd)); }
 int spcsc_pgm_set_mask(spcsc_handle* h, const void* W, const int64_t shape[4]) { H_CALL((W && !shape) ? SPCSC_ERR_INVALID : h->pgm_set_mask(W, shape)); }
 int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ? h->ccmod_reset(D0, zm) : SPCSC_ERR_INVALID); }
@@ -1680,6 +1893,13 @@ int spcsc_comm_create(const char* nccl_lib, const void* id128, int32_t rank, int
 }
 int spcsc_comm_destroy(spcsc_comm* c) {
     if (c) {
+#ifndef SPCSC_EMU
+        cudaSetDevice(c->device);
+        for (int r = 0; r < 8; ++r)
+            if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_own) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+        if (c->p2p_own) cudaFree(c->p2p_own);
+        cudaGetLastError();
+#endif
         if (c->comm && c->api) c->api->CommDestroy(c->comm);
         delete c;
     }

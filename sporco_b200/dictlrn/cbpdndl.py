@@ -131,6 +131,7 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
             raise ValueError('Parameters xmethod and dmethod must have the same values used to '
                              'initialise the Options object')
         self.opt = opt
+        self._dist = None
         self.xmethod, self.dmethod = xmethod, dmethod
         dsz = D0.shape if opt['DictSize'] is None else opt['DictSize']
         cri = cr.CDU_ConvRepIndexing(dsz, S, dimK, dimN)
@@ -204,6 +205,11 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
         X = self.xstep.getcoef() if self.xmethod == 'pgm' else self.xstep.var_y()
         dfd = self.dstep._stats[0]
         rl1 = float(np.sum(np.abs(X), dtype=np.float64))
+        if self._dist is not None:       # sharded images: DFid is already global, RegL1 is not
+            import torch
+            t = torch.tensor([rl1], dtype=torch.float64, device=torch.device('cuda', self.xstep._device))
+            self._dist[0].all_reduce(t, group=self._dist[1])
+            rl1 = float(t.item())
         return dict(DFid=dfd, RegL1=rl1, ObjFun=dfd + self.xstep.lmbda * rl1)
 
     def attach_process_group(self, dist, group=None):
@@ -213,6 +219,7 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
         if self.xmethod != 'admm':
             raise NotImplementedError('sharding over GPUs is implemented for the ADMM X step')
         self.xstep.attach_process_group(dist, group)
+        self._dist = (dist, group)
 
 
 def _rebuild_options(content, xmethod, dmethod):

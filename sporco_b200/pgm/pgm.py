@@ -115,7 +115,12 @@ class PGM(common.IterativeSolver):
         return self.X
 
     def var_momentum(self):
-        return self.t if isinstance(self.momentum, MomentumNesterov) else self.k
+        # sporco/pgm/pgm.py:662-668: the Nesterov rule takes t, the linear rules the iteration count.
+        # Decided by the rule's class name so that a rule object built by the reference package
+        # (sporco.pgm.momentum.MomentumNesterov) is recognised as well.
+        nesterov = isinstance(self.momentum, MomentumNesterov) or any(
+            c.__name__ == 'MomentumNesterov' for c in type(self.momentum).__mro__)
+        return self.t if nesterov else self.k
 
     def iteration_stats(self, k, frcxd):
         tk = self.timer.elapsed(self.opt['IterTimer'])

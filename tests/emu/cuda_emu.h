@@ -119,5 +119,6 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0);
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)1 << 34; return cudaSuccess; }

@@ -78,3 +78,26 @@ def test_cfg5_dictionary_learning_16_images_256():
     assert cases.rel(D1.squeeze(), r['D']) < 1e-4
     its = d.getitstat()
     assert cases.rel(its.ObjFun, r['ObjFun']) < 1e-4 and cases.rel(its.D_Rsdl, r['D_Rsdl']) < 1e-3
+
+
+def test_metric_configuration_k32_against_oracle():
+    """The literal BASELINE.json metric configuration -- 256x256, 8x8x64 dictionary, 32 images, lambda 0.1,
+    AutoRho on, float32 -- for 10 iterations against the oracle (scipy FFT workers; about half a minute of
+    host time): coefficient maps to north_star's rtol 1e-4, and the rho trajectory."""
+    import os
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(12345)
+    D = _unit(rng.standard_normal((8, 8, 64)))
+    S = rng.standard_normal((256, 256, 32)).astype(np.float32)
+    opt = {'MaxMainIter': 10, 'RelStopTol': 0.0, 'AutoRho': {'Enabled': True}}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(opt), dimK=1)
+    Y = b.solve()
+    its = b.getitstat()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=opt, dimK=1, fft=orc.FFTBackend('scipy', os.cpu_count() or 8))
+    assert cases.rel(Y, r.Y) < 1e-4
+    assert cases.rel(its.Rho, [row[8] for row in r.itstat]) < 1e-4
+    assert cases.rel(its.PrimalRsdl, [row[4] for row in r.itstat]) < 1e-4
+    assert cases.rel(its.DualRsdl, [row[5] for row in r.itstat]) < 1e-4
+    assert cases.rel(its.ObjFun, [row[1] for row in r.itstat]) < 1e-4
+    assert len(set(np.round(np.asarray(its.Rho), 6))) > 3          # rho really moved in these iterations

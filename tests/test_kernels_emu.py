@@ -136,3 +136,58 @@ def test_tikhonov_filter_golden():
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
 def test_pgm_mask_golden(sfx):
     cases.run_pgm_mask_case(sfx)
+
+
+@pytest.mark.parametrize('wave', ['1,1', '2,2', '2,1'])
+@pytest.mark.parametrize('keep', ['0', '1', 'fused'])
+def test_wavefront_schedule_vs_oracle(wave, keep, monkeypatch):
+    """The wavefront schedule (groups of images through an L2-sized scratch, SPCSC_WAVE=g,s): ragged
+    last group, several streams, X retrievable only when the X spectra are kept."""
+    monkeypatch.setenv('SPCSC_WAVE', wave)
+    if keep == 'fused':       # groups through column + prox kernels only, cross-iteration fusion kept
+        monkeypatch.setenv('SPCSC_WAVE_FUSED', '1')
+        keep = '1'
+    monkeypatch.setenv('SPCSC_WAVE_KEEP', keep)
+    from sporco_b200 import _lib as L
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(7)
+    D = rng.standard_normal((5, 5, 12)).astype(np.float32)
+    S = rng.standard_normal((64, 64, 3)).astype(np.float32)
+    o = {'MaxMainIter': 9, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o), dimK=1)
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=o, dimK=1)
+    assert cases.rel(Y, r.Y) < 3e-4 and cases.rel(b.U, r.U) < 6e-4
+    its = b.getitstat()
+    assert cases.rel(its.Rho, [x[8] for x in r.itstat]) < 3e-4
+    assert cases.rel(its.ObjFun, [x[1] for x in r.itstat]) < 3e-4
+    if keep == '1':
+        assert cases.rel(b.X, r.X) < 6e-4
+    else:
+        with pytest.raises(L.SpcscError):
+            b.X
+
+
+def test_setting_y_between_solves_is_seen_by_the_fused_schedule():
+    """Warm start: `b.Y = ...` between two solve() calls.  With the cross-iteration fusion the next x-step
+    would otherwise reuse the row spectra of the OLD Y - U that the last prox kernel wrote."""
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(11)
+    D = rng.standard_normal((4, 4, 4)).astype(np.float32)
+    S = rng.standard_normal((64, 64, 2)).astype(np.float32)
+    opt = {'MaxMainIter': 4, 'RelStopTol': 0.0, 'rho': 3.0, 'AutoRho': {'Enabled': False}}
+    sol = []
+    Ynew = None
+    for touch_u in (False, True):
+        b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(opt), dimK=1)
+        assert b._h.admm_schedule_info()['fused']
+        b.solve()
+        if Ynew is None:
+            Ynew = (b.Y + rng.standard_normal(b.Y.shape)).astype(np.float32)
+        b.Y = Ynew
+        if touch_u:
+            b.U = b.U.copy()          # setting U has always invalidated the spectra
+        sol.append(b.solve().copy())
+    assert np.abs(sol[0]).max() > 0
+    assert np.array_equal(sol[0], sol[1])
