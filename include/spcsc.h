@@ -157,8 +157,10 @@ int spcsc_admm_profile(spcsc_handle* h, int32_t n_iter, float kernel_ms[4]);
 /* Which kernel schedule the handle uses: info[0] register-plan row-forward kernel, [1] cluster
    column kernel, [2] register-plan prox kernel, [3] cross-iteration fusion (the prox kernel also
    emits the next x-step's row spectra; the row-forward launch is then a gated no-op unless rho
-   changed). */
-int spcsc_admm_schedule_info(spcsc_handle* h, int32_t info[4]);
+   changed), [4] column kernel of the last batch (0 general, 2 k_col2 clusters, 3 k_col3 persistent clusters
+   with pushed sums), [5] images per wavefront group (0: whole batch per launch), [6] streams of the
+   wavefront schedule, [7] reserved. */
+int spcsc_admm_schedule_info(spcsc_handle* h, int32_t info[8]);
 
 /* ---- PGM / FISTA solver (sporco.pgm.cbpdn.ConvBPDN).  The host keeps the scalar control flow
    of pgm/pgm.py:328-370 and pgm/backtrack.py:74-107 (step size L, momentum t, F <= Q test);

@@ -279,10 +279,11 @@ class Handle(object):
         return ms.value, n.value
 
     def admm_schedule_info(self):
-        info = (ctypes.c_int32 * 4)()
+        info = (ctypes.c_int32 * 8)()
         self._c(self.lib.spcsc_admm_schedule_info(self.h, info))
         return {'row_fwd_v2': bool(info[0]), 'col_v2': bool(info[1]), 'prox_v2': bool(info[2]),
-                'fused': bool(info[3])}
+                'fused': bool(info[3]), 'col_kernel': int(info[4]), 'wave_group': int(info[5]),
+                'wave_streams': int(info[6])}
 
     def admm_profile(self, n):
         ms = (ctypes.c_float * 4)()

@@ -3,7 +3,7 @@
 // parallel; spcsc.cu dispatches on the runtime size.
 #pragma once
 
-#include "kernels2.cuh"
+#include "kernels3.cuh"
 #include "kernels_gen.cuh"
 
 namespace spcsc {
@@ -60,6 +60,7 @@ struct ColLaunch {
     ColArgs a;                   // MC / nchunk / parts filled by the launcher
     int gen;                     // any-size direct-DFT path (a.N0 holds the run-time length)
     int bulk;                    // k_col2: persistent clusters with bulk-copy prefetch of the next slab
+    int push;                    // COL_ADMM: k_col3 (persistent clusters, sums pushed over DSMEM) instead of k_col2
     cudaStream_t stream;
 };
 

@@ -6,6 +6,7 @@
 namespace spcsc {
 
 inline int round_up32(int n) { return (n + 31) / 32 * 32; }
+extern int g_col_variant;      // spcsc.cu: which cluster column kernel the last COL_ADMM launch used
 
 template <typename T, int H>
 cudaError_t row_fwd_launch(const RowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
@@ -304,6 +305,37 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
                               c.stream, c.in, c.out, c.Df, c.Sf, c.G, c.st, c.Lstep, c.acc, stw, c.a,
                               c.sumout, c.sumin, c.ref);
     if (mode != COL_ADMM) return cudaErrorInvalidValue;
+    g_col_variant = 2;
+    if (c.push && !c.bulk) {
+        // k_col3: persistent clusters over (frequency column, run of images) items; the per-frequency sums
+        // travel by st.async pushes instead of cluster barriers
+        auto kern = k_col3<T, N0, E, CPG, NT, CD>;
+        const size_t smem3 = col3_smem_bytes<T, N0, E, NT, CD>((int)cs);
+        if (smem3 <= kSmemLimit) {
+            static int resident3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
+            if (resident3[cs] == 0) {
+#ifndef SPCSC_EMU
+                // leave what two CTAs per SM do not need of the unified array to L1: it holds the dictionary slice
+                const int pct = (int)((2 * (smem3 + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+#endif
+                resident3[cs] = max_active_clusters(kern, dim3(NT), cs, smem3);
+                if (resident3[cs] <= 0) resident3[cs] = -1;
+            }
+            const int ncl = resident3[cs];
+            if (ncl > 0) {
+                // runs of images per item: about six rounds of items per resident cluster
+                int chunk = (int)(((long long)c.a.N1f * c.nb) / (6LL * ncl));
+                if (chunk < 1) chunk = 1;
+                if (chunk > c.nb) chunk = c.nb;
+                const int nitems = c.a.N1f * ((c.nb + chunk - 1) / chunk);
+                const int use = ncl < nitems ? ncl : nitems;
+                g_col_variant = 3;
+                return launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem3, c.stream, c.in, c.out, c.Df,
+                                      c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, chunk);
+            }
+        }
+    }
     if (c.bulk) {
         // persistent clusters with the next slab prefetched by a bulk copy; in place is fine (a
         // slab is in registers before the prefetch of the next one is issued, and stored after)

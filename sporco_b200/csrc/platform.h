@@ -154,19 +154,47 @@ template <int N> SPCSC_DEV void cp_async_wait() { __pipeline_wait_prior(N); }
 // ---- bulk asynchronous copy global -> shared (TMA, 1-D) completing on an mbarrier ------------
 typedef unsigned long long mbar_t;
 #ifdef SPCSC_EMU
-inline void mbar_init(mbar_t*, unsigned) {}
-inline void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t*) { memcpy(dst, src, bytes); }
-inline void mbar_wait(mbar_t*, unsigned) {}
+// emulated mbarrier: transaction count, pending arrivals, arrival count per phase, phase parity.  A
+// cluster runs as cooperative fibres on one OS thread, so plain fields suffice.
+struct EmuBar { int tx; unsigned short pending; unsigned char init, phase; };
+static_assert(sizeof(EmuBar) == sizeof(mbar_t), "emulated barrier must fit the real one");
+inline void emu_bar_check(EmuBar* b) {
+    if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->init; }
+}
+inline void mbar_init(mbar_t* bar, unsigned count) {
+    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+    b->tx = 0; b->pending = (unsigned short)count; b->init = (unsigned char)count; b->phase = 0;
+}
+inline void mbar_expect_tx(mbar_t* bar, unsigned bytes) {
+    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+    b->tx += (int)bytes; b->pending -= 1; emu_bar_check(b);
+}
+inline void mbar_complete_tx(mbar_t* bar, unsigned bytes) {
+    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+    b->tx -= (int)bytes; emu_bar_check(b);
+}
+inline void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
+    mbar_expect_tx(bar, bytes);
+    memcpy(dst, src, bytes);
+    mbar_complete_tx(bar, bytes);
+}
+inline void mbar_wait(mbar_t* bar, unsigned parity) {
+    while (reinterpret_cast<EmuBar*>(bar)->phase == (unsigned char)parity) emu::yield();
+}
 #else
 SPCSC_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 SPCSC_DEV void mbar_init(mbar_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// one thread: announce `bytes` on the barrier and start the copy (16-byte aligned, multiple of 16)
-SPCSC_DEV void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
+// one thread: arrive on the barrier and announce `bytes` of asynchronous writes for the current phase
+SPCSC_DEV void mbar_expect_tx(mbar_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
                  : "memory");
+}
+// one thread: announce `bytes` on the barrier and start the copy (16-byte aligned, multiple of 16)
+SPCSC_DEV void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
+    mbar_expect_tx(bar, bytes);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_addr(dst)),
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
@@ -182,6 +210,30 @@ SPCSC_DEV void mbar_wait(mbar_t* bar, unsigned parity) {
             : "memory");
     }
 }
+#endif
+
+// ---- pushing values into a peer CTA's shared memory (st.async over distributed shared memory) ---------
+// The store completes `sizeof(value)` transaction bytes on an mbarrier of the RECEIVING CTA, which waits on
+// its own barrier: no cluster-wide barrier, hence none of the cluster-scope fences (and the L1 invalidation)
+// that barrier.cluster.arrive.release / wait.acquire bring along.
+#ifdef SPCSC_EMU
+typedef unsigned char* rptr_t;                       // address in a peer's shared memory
+template <typename P> inline rptr_t cluster_remote(P* p, unsigned rank) {
+    return reinterpret_cast<rptr_t>(emu::map_shared_rank((void*)p, rank));
+}
+inline rptr_t rptr_add(rptr_t r, size_t bytes) { return r + bytes; }
+template <typename V> inline void push_remote(rptr_t dst, V v, rptr_t bar) {
+    memcpy(dst, &v, sizeof(V));
+    mbar_complete_tx(reinterpret_cast<mbar_t*>(bar), (unsigned)sizeof(V));
+}
+#else
+typedef unsigned rptr_t;                             // shared::cluster address
+template <typename P> SPCSC_DEV rptr_t cluster_remote(P* p, unsigned rank) {
+    rptr_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(p)), "r"(rank));
+    return r;
+}
+SPCSC_DEV rptr_t rptr_add(rptr_t r, size_t bytes) { return r + (unsigned)bytes; }
 #endif
 
 // ---- complex value type with natural vector alignment (8 B for float, 16 B for double)
@@ -311,6 +363,19 @@ SPCSC_DEV C2<float> ld_keep(const C2<float>* p) {
     return r;
 }
 SPCSC_DEV C2<double> ld_keep(const C2<double>* p) { return *p; }
+#endif
+
+#ifndef SPCSC_EMU
+SPCSC_DEV void push_remote(rptr_t dst, C2<float> v, rptr_t bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(dst),
+                 "f"(v.re), "f"(v.im), "r"(bar)
+                 : "memory");
+}
+SPCSC_DEV void push_remote(rptr_t dst, C2<double> v, rptr_t bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst),
+                 "d"(v.re), "d"(v.im), "r"(bar)
+                 : "memory");
+}
 #endif
 
 // ---- warp / block reductions (double accumulators) -------------------------------------

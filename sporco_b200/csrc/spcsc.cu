@@ -129,6 +129,7 @@ static cudaError_t row_inv_prox2(int H, const RowArgs<T>& r, const ProxArgs<T>& 
     }
     return cudaErrorInvalidValue;
 }
+int g_col_variant = 0;      // set by the cluster column launchers: 2 k_col2, 3 k_col3
 template <typename T>
 static cudaError_t col2(int N0, int mode, const ColLaunch<T>& c, const C2<T>* stw) {
     {
@@ -426,6 +427,7 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> wscratch;
     float last_ms = 0.f;
     int64_t last_launches = 0;
+    int last_col_kernel = 0;
 
     explicit Engine(const spcsc_problem& p) : pb(p) {
         N0 = p.N0; N1 = p.N1; H = N1 / 2; N1f = H + 1;
@@ -547,6 +549,7 @@ class Engine : public spcsc_handle {
         // persistent clusters + bulk-copy prefetch: measured no faster than one slab per cluster
         // (the kernel is issue-bound, not load-bound), so it stays opt-in
         c.bulk = (getenv("SPCSC_COLBULK") && atoi(getenv("SPCSC_COLBULK")) == 1) ? 1 : 0;
+        c.push = (getenv("SPCSC_COL3") && atoi(getenv("SPCSC_COL3")) == 1) ? 1 : 0;
         return c;
     }
 
@@ -878,6 +881,7 @@ class Engine : public spcsc_handle {
                     cs.out = wave_keep ? Zt.p + img_z * k0 : zs;
                 }
                 CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
+                last_col_kernel = g_col_variant;
                 if (prof) CK(prof_mark(1));
                 RowArgs<T> rp = rowargs(M, gk * Cx, Cx);
                 rp.stream = sq;
@@ -984,10 +988,13 @@ class Engine : public spcsc_handle {
             if (prof) CK(prof_mark(0));
             if (!check) {
                 cs.in = zin; cs.out = zin;
-                if (v2_col && !prm.enet && !prm.gradreg)   // l2 / gradient terms: general kernel only
+                if (v2_col && !prm.enet && !prm.gradreg) {  // l2 / gradient terms: general kernel only
                     CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
-                else
+                    last_col_kernel = g_col_variant;
+                } else {
                     CK(col<T>(N0, COL_ADMM, cs));
+                    last_col_kernel = 0;
+                }
                 last_launches += 4;
             } else {
                 ColLaunch<T> c1 = cs;
@@ -1108,6 +1115,9 @@ class Engine : public spcsc_handle {
     int admm_schedule_info(int32_t* info) override {
         info[0] = v2_rowf; info[1] = v2_col; info[2] = v2_rowp;
         info[3] = (fuse && !opts.linsolve_check && (!opts.joint || wl21.spatial_uniform || Cx > 1)) ? 1 : 0;
+        if (wave_g > 0 && !wave_fused) info[3] = 0;
+        info[4] = last_col_kernel;
+        info[5] = wave_g; info[6] = wave_g > 0 ? wave_s : 0; info[7] = 0;
         return SPCSC_OK;
     }
     int admm_profile(int n, float* ms4) override {

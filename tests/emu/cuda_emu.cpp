@@ -254,6 +254,8 @@ void warp_exchange(const void* mine, void* out, int src_lane, size_t nbytes) {
     warp_barrier(ws);
 }
 
+void yield() { yield_to_sched(); }
+
 unsigned cluster_rank() { return (unsigned)t_worker->cur_blk; }
 unsigned cluster_size() { return (unsigned)t_worker->cs; }
 

@@ -39,6 +39,7 @@ unsigned cluster_size();
 void cluster_arrive();
 void cluster_wait();
 void* map_shared_rank(void* p, unsigned rank);
+void yield();                        // let the other fibres of the cluster run (used by emulated waits)
 void sync_threads();
 void sync_warp();
 // exchange 16-byte payloads between lanes of the calling warp

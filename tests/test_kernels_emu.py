@@ -191,3 +191,31 @@ def test_setting_y_between_solves_is_seen_by_the_fused_schedule():
         sol.append(b.solve().copy())
     assert np.abs(sol[0]).max() > 0
     assert np.array_equal(sol[0], sol[1])
+
+
+@pytest.mark.parametrize('case', cases.FRESH_CASES + [(64, 64, 8, 5, None, None, None)])
+def test_push_exchange_column_kernel_vs_oracle(case, monkeypatch):
+    """k_col3 (SPCSC_COL3=1): persistent clusters over (frequency column, run of images) items, the
+    per-frequency sums pushed into the peers' shared memory and awaited on an mbarrier."""
+    monkeypatch.setenv('SPCSC_COL3', '1')
+    N0, N1, M, K, C, mu, extra = case
+    b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
+    assert b._h.admm_schedule_info()['col_kernel'] == 3
+
+
+def test_push_exchange_column_kernel_float64_and_colour_dictionary(monkeypatch):
+    monkeypatch.setenv('SPCSC_COL3', '1')
+    N0, N1, M, K, C, mu, extra = cases.FRESH_CASES_F64[0]
+    cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra, dt=np.float64, tol=1e-9)
+    # multi-channel dictionary (Woodbury solve), cluster of 2
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(9)
+    D = rng.standard_normal((5, 5, 3, 40)).astype(np.float32)
+    S = rng.standard_normal((64, 64, 3, 2)).astype(np.float32)
+    o = {'MaxMainIter': 6, 'RelStopTol': 0.0}
+    b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(o))
+    Y = b.solve()
+    r = orc.admm_convbpdn(D, S, 0.1, opt=o)
+    assert cases.rel(Y, r.Y) < 3e-4
+    assert cases.rel(b.getitstat().ObjFun, [x[1] for x in r.itstat]) < 3e-4

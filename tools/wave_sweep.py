@@ -17,7 +17,7 @@ from sporco_b200.admm import cbpdn            # noqa: E402
 
 
 def run(D, S, env):
-    for k in ('SPCSC_WAVE', 'SPCSC_WAVE_KEEP', 'SPCSC_WAVE_PERSIST', 'SPCSC_FUSE', 'SPCSC_WAVE_FUSED'):
+    for k in [k for k in os.environ if k.startswith('SPCSC_')]:
         os.environ.pop(k, None)
     os.environ.update(env)
     o = cbpdn.ConvBPDN.Options({'RelStopTol': 0.0, 'FastSolve': True, 'AutoRho': {'Enabled': True}})
@@ -32,7 +32,7 @@ def run(D, S, env):
     ms_st, launches = h.admm_last_timing()
     rho = float(b.rho)
     ysum = float(np.abs(b.Y[:, :, 0, 0, :4]).sum()) if hasattr(b, 'Y') else 0.0
-    out = {'env': env, 'driver_ms': ms_drv / 20, 'driver_its': 20e3 / ms_drv, 'steady_ms': ms_st / 200,
+    out = {'env': env, 'sched': h.admm_schedule_info(), 'driver_ms': ms_drv / 20, 'driver_its': 20e3 / ms_drv, 'steady_ms': ms_st / 200,
            'steady_its': 200e3 / ms_st, 'rho': rho, 'ysum': ysum, 'launches_per_iter': launches / 200}
     if os.environ.get('WAVE_SWEEP_PROFILE'):
         out['kernel_ms'] = [round(x / 20, 4) for x in h.admm_profile(20)]
@@ -56,6 +56,8 @@ def main():
             print(json.dumps(run(D, S, {})), flush=True)
         elif v == 'nofuse':
             print(json.dumps(run(D, S, {'SPCSC_FUSE': '0'})), flush=True)
+        elif v.startswith('env:'):          # env:KEY=VAL,KEY=VAL
+            print(json.dumps(run(D, S, dict(kv.split('=') for kv in v[4:].split(',')))), flush=True)
         elif v.startswith('f:'):
             print(json.dumps(run(D, S, {'SPCSC_WAVE': v[2:], 'SPCSC_WAVE_FUSED': '1'})), flush=True)
         else:
