@@ -173,6 +173,22 @@ int spcsc_pgm_reset(spcsc_handle* h, const void* X0);
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]);
 /* Accept the candidate and take the momentum step Yf = Xf + coef (Xf - Xfprv)  (PGMDFT.ystep). */
 int spcsc_pgm_accept(spcsc_handle* h, double coef);
+/* Scalars for the step-size policies and the monotone variant, at the current state (two passes over the
+   spectra that only form per-frequency sums):
+     out[0] = ||grad f(Yf)||^2, out[1] = <grad, Hess grad>               StepSizePolicyCauchy, pgm/stepsize.py:50-87
+     out[2] = ||grad - grad_prev||^2, out[3] = <Xf - Xf_prev, grad - grad_prev>   StepSizePolicyBB, :90-145
+     out[4] = DFid of the accepted Xf, out[5] = RegL1 of the X last produced      eval_objfn, pgm/cbpdn.py:320-356
+   (plain sums over the stored half spectrum for [0..3], like np.sum over rfftn output).  store != 0 afterwards
+   remembers the current gradient / iterate as "previous" (StepSizePolicyBB.store_prev_state). */
+int spcsc_pgm_policy_stats(spcsc_handle* h, int32_t store, double out[8]);
+/* Robust backtracking (pgm/backtrack.py:110-210): Yf = a Xf + b Z with the auxiliary sequence Z (set to Xf on
+   first use); save_prev != 0 first keeps the old Yf for the residual of the iteration. */
+int spcsc_pgm_combine_y(spcsc_handle* h, double a, double b, int32_t save_prev);
+/* Ends an iteration other than by spcsc_pgm_accept.  SPCSC_PGM_FINISH_REJECT (monotone FISTA, pgm/pgm.py:802-831,
+   the candidate Z raised the objective): Xf stays, Yf = Xf + c0 (Zf - Xf).  SPCSC_PGM_FINISH_ROBUST: Z += c0 (Xf_new
+   - Yf), the candidate is accepted, Yf untouched.  out[0] = rfl2norm2(Xf - Yfprv), the residual of pgm/cbpdn.py:314-318. */
+enum { SPCSC_PGM_FINISH_REJECT = 1, SPCSC_PGM_FINISH_ROBUST = 2 };
+int spcsc_pgm_finish(spcsc_handle* h, int32_t mode, double c0, double out[2]);
 
 /* Device-side all-reduce of the per-iteration accumulators over peer memory (NVLink / NVSwitch), replacing the
    NCCL call on that path: every rank exports a small block (CUDA IPC, 64-byte handle), the handles of all

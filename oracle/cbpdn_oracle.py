@@ -540,6 +540,9 @@ PGM_DEFAULTS = {
     'DataType': None, 'NonNegCoef': False, 'NoBndryCross': False, 'L1Weight': 1.0,
     'X0': None,
     'Backtrack': None,      # None | {'gamma_u': 1.2, 'maxiter': 50}  (BacktrackStandard)
+                            #      | {'kind': 'robust', 'gamma_d': 0.9, 'gamma_u': 2.0, 'maxiter': 50}
+    'StepSizePolicy': None,  # None | 'cauchy' | 'bb'   (pgm/stepsize.py; ignored with Backtrack)
+    'Monotone': False,       # pgm/pgm.py:802-831 (without backtracking)
     'AutoStop': {'Enabled': False, 'Tau0': 1e-2},
 }
 
@@ -618,16 +621,65 @@ def pgm_convbpdn(D, S, lmbda=None, opt=None, dimK=None, fft=None, timing=None, W
         Xn = prox_g(V, Lc)
         return Xn, fft.rfftn(Xn, None, axN)
 
+    def hessian_f(V):                                    # pgm/cbpdn.py:302-310
+        h = np.conj(Df) * inner(Df, V, axM)
+        if dims.Cd > 1:
+            h = np.sum(h, axis=axC, keepdims=True)
+        return h
+
+    def eval_objfn(Xf_, X_):                             # pgm/cbpdn.py:320-356
+        dfd_ = obfn_dfd(Xf_)
+        rl1_ = np.linalg.norm((wl1 * X_).ravel(), 1)
+        return (dfd_ + lmbda * rl1_, dfd_, rl1_)
+
+    robust = bt is not None and bt.get('kind') == 'robust'
+    policy = o['StepSizePolicy'] if bt is None else None   # pgm/pgm.py:236-239
+    mono = bool(o['Monotone'])
+    if mono and bt is not None:
+        raise NotImplementedError('oracle: Monotone together with backtracking')
+    Tk, Zrb = 0., None                                   # BacktrackRobust state (pgm/backtrack.py:150-151)
+    bb_xprv, bb_gprv = 0.0, 0.0                          # StepSizePolicyBB state (pgm/stepsize.py:108-109)
+    objfn = objfn_prev = None
+    ZZf = None
+
     res = ADMMResult()
     itstat = []
     F = Q = itbt = None
     k = 0
     t_start = time.perf_counter()
     for k in range(0, o['MaxMainIter']):
+        # on_iteration_start (pgm/pgm.py:835-846)
         Xfprv = Xf.copy()
-        if not o['FastSolve']:
+        if not o['FastSolve'] or robust:
             Yfprv = Yf.copy()
-        if bt is not None:                               # pgm/backtrack.py:74-107
+        if mono:
+            if k == 0:
+                objfn = eval_objfn(Xf, X)
+            objfn_prev = objfn
+        if robust:                                       # pgm/backtrack.py:153-210
+            if Zrb is None:
+                Zrb = Xf.copy()
+            L = L * bt.get('gamma_d', 0.9)
+            itbt = 0
+            search = True
+            while search and itbt < bt.get('maxiter', 50):
+                tt = float(1. + np.sqrt(1. + 4. * L * Tk)) / (2. * L)
+                T = Tk + tt
+                Yf = (Tk * Xfprv + tt * Zrb) / T
+                gradY = grad_f(Yf)
+                X, Xf = xstep(gradY, L)
+                F = obfn_f(Xf)
+                Dxy = Xf - Yf
+                Q = obfn_f(Yf) + np.sum(np.real(np.conj(Dxy) * gradY)) + \
+                    (L / 2.) * np.linalg.norm(Dxy.flatten(), 2) ** 2
+                if F <= Q:
+                    search = False
+                else:
+                    L = L * bt.get('gamma_u', 2.0)
+                itbt += 1
+            Tk = T
+            Zrb = Zrb + (tt * L * (Xf - Yf))
+        elif bt is not None:                             # pgm/backtrack.py:74-107
             gradY = grad_f(Yf)
             itbt = 0
             search = True
@@ -642,20 +694,51 @@ def pgm_convbpdn(D, S, lmbda=None, opt=None, dimK=None, fft=None, timing=None, W
                 else:
                     L = L * dtype.type(bt.get('gamma_u', 1.2))
                 itbt += 1
-        else:
-            X, Xf = xstep(grad_f(Yf), L)
-        # momentum (pgm/pgm.py:815-831, pgm/momentum.py:45-48)
-        tprv = t
-        t = 0.5 * float(1. + np.sqrt(1. + 4. * t ** 2))
-        Yf = Xf + ((tprv - 1.) / t) * (Xf - Xfprv)
+        else:                                            # PGMDFT.xstep (pgm/pgm.py:779-811)
+            gradf = grad_f(Yf)
+            if policy is not None:
+                if k > 1:
+                    if policy == 'cauchy':               # pgm/stepsize.py:68-87
+                        den = np.sum(np.real(np.conj(gradf) * gradf))
+                        num = np.sum(np.real(np.conj(gradf) * hessian_f(gradf)))
+                        L = num / den
+                    else:                                # Barzilai-Borwein, pgm/stepsize.py:125-145
+                        dx = Xf - bb_xprv
+                        dg = gradf - bb_gprv
+                        den = np.sum(np.real(np.conj(dx) * dg))
+                        num = np.sum(np.real(np.conj(dg) * dg))
+                        Lbb = num / den
+                        if not Lbb < 0.:
+                            L = Lbb
+                if policy == 'bb':
+                    bb_xprv, bb_gprv = Xf, gradf
+            X, Xf = xstep(gradf, L)
+            if mono and k > 0:
+                ZZf = Xf.copy()
+                objfn = eval_objfn(Xf, X)
+                if objfn_prev[0] < objfn[0]:
+                    Xf = Xfprv.copy()
+                    objfn = objfn_prev
+        if not robust:
+            # momentum (pgm/pgm.py:815-831, pgm/momentum.py:45-48)
+            tprv = t
+            t = 0.5 * float(1. + np.sqrt(1. + 4. * t ** 2))
+            if mono and k > 0:
+                Yf = Xf + (tprv / t) * (ZZf - Xf) + ((tprv - 1.) / t) * (Xf - Xfprv)
+            else:
+                Yf = Xf + ((tprv - 1.) / t) * (Xf - Xfprv)
         if not o['FastSolve']:
             frcxd = rfl2norm2(Xf - Yfprv, X.shape, axis=axN)
             tol = o['RelStopTol']
             if o['AutoStop']['Enabled']:
                 tol = o['AutoStop']['Tau0'] / (1. + k)
-            dfd = obfn_dfd(Xf)
-            rl1 = np.linalg.norm((wl1 * X).ravel(), 1)
-            itstat.append((k, dfd + lmbda * rl1, dfd, rl1, frcxd, F, Q, itbt, L,
+            if mono:                                     # pgm/pgm.py:546-549: the tracked objective
+                obj, dfd, rl1 = objfn
+            else:
+                dfd = obfn_dfd(Xf)
+                rl1 = np.linalg.norm((wl1 * X).ravel(), 1)
+                obj = dfd + lmbda * rl1
+            itstat.append((k, obj, dfd, rl1, frcxd, F, Q, itbt, L,
                            time.perf_counter() - t_start))
             if frcxd < tol:
                 break

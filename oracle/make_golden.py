@@ -23,7 +23,8 @@ warnings.filterwarnings('ignore')
 
 from sporco.admm import cbpdn as rcbpdn          # noqa: E402
 from sporco.pgm import cbpdn as rpgm             # noqa: E402
-from sporco.pgm.backtrack import BacktrackStandard  # noqa: E402
+from sporco.pgm.backtrack import BacktrackStandard, BacktrackRobust  # noqa: E402
+from sporco.pgm.stepsize import StepSizePolicyBB, StepSizePolicyCauchy  # noqa: E402
 from sporco import linalg as rlinalg, prox as rprox, fft as rfft   # noqa: E402
 from oracle import cbpdn_oracle as orc           # noqa: E402
 from oracle import cbpdndl_oracle as orcdl       # noqa: E402
@@ -288,6 +289,18 @@ def main():
         pgm_case('pgm_fixed_' + sfx, dt, D, S, 0.1,
                  {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0},
                  {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0}, dimK=1)
+        # row a17: step-size policies, monotone FISTA, robust backtracking
+        pb = {'MaxMainIter': 25, 'RelStopTol': 0.0}
+        pgm_case('pgm_cauchy_' + sfx, dt, D, S, 0.1, dict(pb, L=50.0, StepSizePolicy=StepSizePolicyCauchy()),
+                 dict(pb, L=50.0, StepSizePolicy='cauchy'), dimK=1)
+        pgm_case('pgm_bb_' + sfx, dt, D, S, 0.1, dict(pb, L=50.0, StepSizePolicy=StepSizePolicyBB()),
+                 dict(pb, L=50.0, StepSizePolicy='bb'), dimK=1)
+        pgm_case('pgm_mono_' + sfx, dt, D, S, 0.1, dict(pb, L=150.0, Monotone=True),
+                 dict(pb, L=150.0, Monotone=True), dimK=1)
+        pgm_case('pgm_robust_' + sfx, dt, D, S, 0.1,
+                 dict(pb, L=5.0, Backtrack=BacktrackRobust(gamma_d=0.95, gamma_u=1.8, maxiter=10)),
+                 dict(pb, L=5.0, Backtrack={'kind': 'robust', 'gamma_d': 0.95, 'gamma_u': 1.8, 'maxiter': 10}),
+                 dimK=1)
         D0 = rng.standard_normal((6, 6, 5)).astype(dt)
         S4 = rng.standard_normal((32, 32, 4)).astype(dt)
         cdl_case('cdl_' + sfx, dt, D0, S4, 0.1, CDL_OPT)

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libspcsc.so')
 
 F32, F64 = 0, 1
 ARR_Y, ARR_U, ARR_X, ARR_XF, ARR_DF, ARR_SF, ARR_PGM_X, ARR_PGM_XF, ARR_PGM_YF = range(9)
+PGM_FINISH_REJECT, PGM_FINISH_ROBUST = 1, 2
 COEF_ADMM_Y, COEF_PGM_X = 0, 1
 ERR_UNSUPPORTED = -4
 
@@ -28,7 +29,7 @@ SYMBOLS = (
     'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
-    'spcsc_pgm_accept', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
+    'spcsc_pgm_accept', 'spcsc_pgm_policy_stats', 'spcsc_pgm_combine_y', 'spcsc_pgm_finish', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
     'spcsc_p2p_attach', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
 )
@@ -107,6 +108,9 @@ def _declare(lib):
     lib.spcsc_pgm_reset.argtypes = [vp, vp]
     lib.spcsc_pgm_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_pgm_accept.argtypes = [vp, ctypes.c_double]
+    lib.spcsc_pgm_policy_stats.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.spcsc_pgm_combine_y.argtypes = [vp, ctypes.c_double, ctypes.c_double, i32]
+    lib.spcsc_pgm_finish.argtypes = [vp, i32, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_set_gradreg.argtypes = [vp, vp, vp]
     lib.spcsc_p2p_export.argtypes = [vp, vp]
     lib.spcsc_p2p_attach.argtypes = [vp, i32, i32, vp]
@@ -341,6 +345,19 @@ class Handle(object):
 
     def pgm_accept(self, coef):
         self._c(self.lib.spcsc_pgm_accept(self.h, float(coef)))
+
+    def pgm_policy_stats(self, store=False):
+        out = (ctypes.c_double * 8)()
+        self._c(self.lib.spcsc_pgm_policy_stats(self.h, 1 if store else 0, out))
+        return [out[i] for i in range(8)]
+
+    def pgm_combine_y(self, a, b, save_prev):
+        self._c(self.lib.spcsc_pgm_combine_y(self.h, float(a), float(b), 1 if save_prev else 0))
+
+    def pgm_finish(self, mode, c0):
+        out = (ctypes.c_double * 2)()
+        self._c(self.lib.spcsc_pgm_finish(self.h, int(mode), float(c0), out))
+        return out[0]
 
     def pgm_set_mask(self, W):
         if W is None:

@@ -730,6 +730,120 @@ SPCSC_GLOBAL void k_pgm_momentum(const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* SP
     }
 }
 
+// out = a X + b Y  (spectra; robust backtracking: y = (T_k x_prev + t z) / T, pgm/backtrack.py:176-178;
+// monotone FISTA after a rejected step: y = x + (t_prev / t)(z - x), pgm/pgm.py:826-828)
+template <typename T>
+SPCSC_GLOBAL void k_spec_axpby(const C2<T>* SPCSC_RESTRICT X, const C2<T>* SPCSC_RESTRICT Y,
+                               C2<T>* SPCSC_RESTRICT out, T a, T b, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const C2<T> x = X[i], y = Y[i];
+        out[i] = mk<T>(a * x.re + b * y.re, a * x.im + b * y.im);
+    }
+}
+// Z += c (X - Y)   (robust backtracking: z += t L (x - y), pgm/backtrack.py:203)
+template <typename T>
+SPCSC_GLOBAL void k_spec_add_diff(C2<T>* SPCSC_RESTRICT Z, const C2<T>* SPCSC_RESTRICT X,
+                                  const C2<T>* SPCSC_RESTRICT Y, T c, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const C2<T> z = Z[i], x = X[i], y = Y[i];
+        Z[i] = mk<T>(z.re + c * (x.re - y.re), z.im + c * (x.im - y.im));
+    }
+}
+// Hermitian-weighted squared distance of two spectra in slab order [nb][N1f][per_wf], i.e. N times
+// rfl2norm2(A - B) (fft.py:449-484), added to *slot.
+template <typename T>
+SPCSC_GLOBAL void k_spec_wdist2(const C2<T>* SPCSC_RESTRICT A, const C2<T>* SPCSC_RESTRICT B,
+                                double* SPCSC_RESTRICT slot, int nb, int N1f, size_t per_wf, int even_n1) {
+    __shared__ double red[32];
+    const size_t n = (size_t)nb * N1f * per_wf;
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int wf = (int)((i / per_wf) % N1f);
+        const double wgt = (wf == 0 || (even_n1 && wf == N1f - 1)) ? 1.0 : 2.0;
+        s[0] += wgt * (double)abs2(A[i] - B[i]);
+    }
+    block_accumulate<1>(s, red, slot);
+}
+// sum |w x| over a real array in device order [K][Cx][M][N0][N1] with the broadcast weight view
+template <typename T>
+SPCSC_GLOBAL void k_l1_sum(const T* SPCSC_RESTRICT X, WeightView<T> w, double* SPCSC_RESTRICT slot, int K,
+                           int Cx, int M, int N0, int N1) {
+    __shared__ double red[32];
+    const size_t n = (size_t)K * Cx * M * N0 * N1;
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        size_t t = i;
+        const int n1 = (int)(t % N1); t /= N1;
+        const int n0 = (int)(t % N0); t /= N0;
+        const int m = (int)(t % M); t /= M;
+        const int c = (int)(t % Cx);
+        const int k = (int)(t / Cx);
+        const T wv = w.p[(size_t)k * w.sk + (size_t)c * w.sc + (size_t)m * w.sm + (size_t)n0 * w.s0 +
+                         (size_t)n1 * w.s1];
+        s[0] += (double)fabs(wv * X[i]);
+    }
+    block_accumulate<1>(s, red, slot);
+}
+// Scalars of the step-size policies (pgm/stepsize.py:50-145) and of the objective, from the per-frequency
+// sums only.  With R = sY - Sf (residual spectrum at the auxiliary point, Cd-vector per frequency; gradient
+// A R with A = [conj(Df_c,m)]) and G = A^H A:
+//   out[0] = sum R^H G R = ||grad||^2                 out[1] = sum |G R|^2 = <grad, Hess grad>      (Cauchy)
+//   out[2] = sum dR^H G dR = ||grad - grad_prev||^2   out[3] = sum Re(dsX^H dR) = <x - x_prev, dgrad>   (BB)
+//   out[4] = Hermitian-weighted sum |sX - Sf|^2  (N times 2 DFid of the accepted iterate)
+// Plain sums over the stored half spectrum for [0..3], as np.sum over rfftn output does.  With `store` the
+// current R and sX replace the remembered ones afterwards (StepSizePolicyBB.store_prev_state).
+// Layout of sY, sX, Sf, Rprev, sXprev: [nb][CD][N1f][N0]; G: [N1f][N0][CD][CD].
+template <typename T, int CD>
+SPCSC_GLOBAL void k_pgm_policy(const C2<T>* SPCSC_RESTRICT sY, const C2<T>* SPCSC_RESTRICT sX,
+                               const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
+                               C2<T>* SPCSC_RESTRICT Rprev, C2<T>* SPCSC_RESTRICT sXprev,
+                               double* SPCSC_RESTRICT out, int nb, int N1f, int N0, int even_n1, int store) {
+    __shared__ double red[5 * 32];
+    const size_t nf = (size_t)N1f * N0, n = (size_t)nb * nf;
+    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / nf, f = i - b * nf;
+        const int wf = (int)(f / N0);
+        const double wgt = (wf == 0 || (even_n1 && wf == N1f - 1)) ? 1.0 : 2.0;
+        C2<T> R[CD], dR[CD], dS[CD];
+        SPCSC_UNROLL
+        for (int d = 0; d < CD; ++d) {
+            const size_t j = (b * CD + d) * nf + f;
+            const C2<T> sf = Sf[j], sy = sY[j], sx = sX[j];
+            R[d] = sy - sf;
+            dR[d] = R[d] - Rprev[j];
+            dS[d] = sx - sXprev[j];
+            s[4] += wgt * (double)abs2(sx - sf);
+            if (store) {
+                Rprev[j] = R[d];
+                sXprev[j] = sx;
+            }
+        }
+        const C2<T>* Gp = G + f * CD * CD;
+        SPCSC_UNROLL
+        for (int r = 0; r < CD; ++r) {
+            C2<T> y = mk<T>(0, 0), dy = mk<T>(0, 0);
+            SPCSC_UNROLL
+            for (int c = 0; c < CD; ++c) {
+                C2<T> g = Gp[r * CD + c];
+                if (CD == 1) g.im = 0;           // the imaginary part may carry another table (GHG)
+                y = y + g * R[c];
+                dy = dy + g * dR[c];
+            }
+            s[0] += (double)(R[r].re * y.re + R[r].im * y.im);
+            s[1] += (double)abs2(y);
+            s[2] += (double)(dR[r].re * dy.re + dR[r].im * dy.im);
+            s[3] += (double)(dS[r].re * dR[r].re + dS[r].im * dR[r].im);
+        }
+    }
+    block_accumulate<5>(s, red, out);
+}
+
 // ------------------------------------------------------------------------------------
 // LinSolveCheck (admm/cbpdn.py:283-293): relative residual of the x-step system, taken
 // honestly from the stored solution Xf (column-spectrum slab, before the inverse column

@@ -306,6 +306,9 @@ struct spcsc_handle {
     virtual int pgm_reset(const void* X0) = 0;
     virtual int pgm_trial(double L, double* out) = 0;
     virtual int pgm_accept(double coef) = 0;
+    virtual int pgm_policy_stats(int store, double* out) = 0;
+    virtual int pgm_combine_y(double a, double b, int save_prev) = 0;
+    virtual int pgm_finish(int mode, double c0, double* out) = 0;
     virtual int ccmod_reset(const void* D0, int zero_mean) = 0;
     virtual int ccmod_setcoef_device(int source) = 0;
     virtual int ccmod_setcoef(const void* Z) = 0;
@@ -380,6 +383,9 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> Zt, Zscratch, Xscratch, Df, Sf, G, tw_row, tw_col, sum_buf;
     DevBuf<C2<T>> stw_row1, stw_rowc, stw_col;     // stage twiddles of the v2 register plans
     DevBuf<C2<T>> pgA, pgB;                         // PGM: accepted Xf (= Xfprv), Yf; Zt is the candidate
+    DevBuf<C2<T>> pgZ, pgYp;                        //   robust backtracking: auxiliary sequence z, Yf of the previous iteration
+    DevBuf<C2<T>> pg_sx, pg_rprev, pg_sxprev;       //   step-size policies: sum_m Df Xf, remembered residual / iterate sums
+    bool pg_z_init = false, pg_pol_init = false;
     spcsc_pgm_opts popts;
     DevBuf<T> cdX;                                  // CCMOD: dictionary iterate, real [Cd][M][N0][N1]
     DevBuf<C2<T>> cdXf, cdYf, cdV, cdG;             // its spectrum, the momentum point, scratch, gradient
@@ -450,6 +456,7 @@ class Engine : public spcsc_handle {
         acc.release(); st.release(); rows.release();
         stw_row1.release(); stw_rowc.release(); stw_col.release();
         pgA.release(); pgB.release(); Zt2.release();
+        pgZ.release(); pgYp.release(); pg_sx.release(); pg_rprev.release(); pg_sxprev.release();
         cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
 #ifndef SPCSC_EMU
@@ -1573,6 +1580,106 @@ class Engine : public spcsc_handle {
         CK(cudaStreamSynchronize(stream));
         pgm_ready = true;
         pgm_have_cand = false;
+        pg_z_init = false;
+        pg_pol_init = false;
+        return SPCSC_OK;
+    }
+
+    // ---- step-size policies, monotone and robust variants (pgm/stepsize.py, pgm/pgm.py:413-440 / 802-831,
+    //      pgm/backtrack.py:110-210): a few passes over the state and scalars for the host's control flow
+    template <int CD>
+    cudaError_t policy_launch(int store) {
+        return launch(k_pgm_policy<T, CD>, dim3(296), dim3(256), 0, stream, (const C2<T>*)sum_buf.p,
+                      (const C2<T>*)pg_sx.p, (const C2<T>*)Sf.p, (const C2<T>*)G.p, pg_rprev.p, pg_sxprev.p, acc.p,
+                      K * Cx, N1f, N0, 1 - (N1 & 1), store);
+    }
+    int pgm_policy_stats(int store, double* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "pgm_policy_stats before pgm_reset");
+        if (pgm_mask) FAIL(SPCSC_ERR_UNSUPPORTED, "step-size policies / monotone steps with a masked data fidelity");
+        CK(cudaSetDevice(pb.device));
+        const size_t ns = (size_t)K * Cx * Cd * N1f * N0;
+        CK(sum_buf.ensure(ns));
+        CK(pg_sx.ensure(ns));
+        CK(pg_rprev.ensure(ns));
+        CK(pg_sxprev.ensure(ns));
+        if (!pg_pol_init) {
+            // StepSizePolicyBB starts from xprv = gradprv = 0 (stepsize.py:108-109): grad = 0 means R = 0
+            CK(cudaMemsetAsync(pg_rprev.p, 0, ns * sizeof(C2<T>), stream));
+            CK(cudaMemsetAsync(pg_sxprev.p, 0, ns * sizeof(C2<T>), stream));
+            pg_pol_init = true;
+        }
+        ColLaunch<T> cy = colargs(M, K * Cx);
+        cy.in = pgB.p; cy.out = nullptr; cy.sumout = sum_buf.p;
+        CK(col<T>(N0, COL_SUM, cy));
+        ColLaunch<T> cx = colargs(M, K * Cx);
+        cx.in = pgA.p; cx.out = nullptr; cx.sumout = pg_sx.p;
+        CK(col<T>(N0, COL_SUM, cx));
+        CK(cudaMemsetAsync(acc.p, 0, kAccBytes, stream));
+        switch (Cd) {
+            case 1: CK(policy_launch<1>(store)); break;
+            case 2: CK(policy_launch<2>(store)); break;
+            case 3: CK(policy_launch<3>(store)); break;
+            case 4: CK(policy_launch<4>(store)); break;
+            default: FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 dictionary channels");
+        }
+        CK(launch(k_l1_sum<T>, dim3(592), dim3(256), 0, stream, (const T*)Y.p, wl1, acc.p + 5, K, Cx, M, N0, N1));
+        double ha[6];
+        CK(cudaMemcpyAsync(ha, acc.p, sizeof(ha), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (int i = 0; i < 4; ++i) out[i] = ha[i];
+        out[4] = 0.5 * ha[4] / ((double)N0 * (double)N1);      // DFid of the accepted iterate
+        out[5] = ha[5];                                         // RegL1 of the X in the real buffer
+        out[6] = out[7] = 0.0;
+        return SPCSC_OK;
+    }
+    int pgm_combine_y(double a, double b, int save_prev) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!pgm_ready) FAIL(SPCSC_ERR_STATE, "pgm_combine_y before pgm_reset");
+        CK(cudaSetDevice(pb.device));
+        CK(pgZ.ensure(nslab));
+        CK(pgYp.ensure(nslab));
+        if (!pg_z_init) {          // z_0 = x_0   (pgm/backtrack.py:163-164)
+            CK(cudaMemcpyAsync(pgZ.p, pgA.p, nslab * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
+            pg_z_init = true;
+        }
+        if (save_prev)             // Yfprv of the residual (pgm/pgm.py:838-841)
+            CK(cudaMemcpyAsync(pgYp.p, pgB.p, nslab * sizeof(C2<T>), cudaMemcpyDeviceToDevice, stream));
+        CK(launch(k_spec_axpby<T>, dim3(1184), dim3(256), 0, stream, (const C2<T>*)pgA.p, (const C2<T>*)pgZ.p,
+                  pgB.p, (T)a, (T)b, nslab));
+        return SPCSC_OK;
+    }
+    int pgm_finish(int mode, double c0, double* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!pgm_have_cand) FAIL(SPCSC_ERR_STATE, "pgm_finish without a candidate");
+        CK(cudaSetDevice(pb.device));
+        const int even = 1 - (N1 & 1);
+        const double inv_n = 1.0 / ((double)N0 * (double)N1);
+        double hv = 0.0;
+        CK(cudaMemsetAsync(acc.p, 0, sizeof(double), stream));
+        if (mode == SPCSC_PGM_FINISH_REJECT) {
+            // monotone FISTA, objective went up: Xf stays, Yf = Xf + c0 (Zf - Xf); the residual is taken
+            // between the kept Xf and the old Yf
+            CK(launch(k_spec_wdist2<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)pgA.p, (const C2<T>*)pgB.p,
+                      acc.p, K * Cx, N1f, (size_t)M * N0, even));
+            CK(launch(k_spec_axpby<T>, dim3(1184), dim3(256), 0, stream, (const C2<T>*)pgA.p, (const C2<T>*)Zt.p,
+                      pgB.p, (T)(1.0 - c0), (T)c0, nslab));
+        } else if (mode == SPCSC_PGM_FINISH_ROBUST) {
+            if (!pg_z_init) FAIL(SPCSC_ERR_STATE, "robust finish without pgm_combine_y");
+            // z += c0 (x - y); x accepted; y untouched; residual against the previous iteration's y
+            CK(launch(k_spec_add_diff<T>, dim3(1184), dim3(256), 0, stream, pgZ.p, (const C2<T>*)Zt.p,
+                      (const C2<T>*)pgB.p, (T)c0, nslab));
+            CK(launch(k_spec_wdist2<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)Zt.p, (const C2<T>*)pgYp.p,
+                      acc.p, K * Cx, N1f, (size_t)M * N0, even));
+            std::swap(Zt.p, pgA.p);
+            std::swap(Zt.n, pgA.n);
+        } else {
+            FAIL(SPCSC_ERR_INVALID, "unknown finish mode");
+        }
+        CK(cudaMemcpyAsync(&hv, acc.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (out) { out[0] = hv * inv_n; out[1] = 0.0; }
+        pgm_have_cand = false;
         return SPCSC_OK;
     }
     int pgm_trial(double L, double* out) override {
@@ -1861,6 +1968,9 @@ int spcsc_pgm_configure(spcsc_handle* h, const spcsc_pgm_opts* o) { H_CALL(o ? h
 int spcsc_pgm_reset(spcsc_handle* h, const void* X0) { H_CALL(h->pgm_reset(X0)); }
 int spcsc_pgm_trial(spcsc_handle* h, double L, double out[8]) { H_CALL(out ? h->pgm_trial(L, out) : SPCSC_ERR_INVALID); }
 int spcsc_pgm_accept(spcsc_handle* h, double coef) { H_CALL(h->pgm_accept(coef)); }
+int spcsc_pgm_policy_stats(spcsc_handle* h, int32_t store, double out[8]) { H_CALL(out ? h->pgm_policy_stats(store, out) : SPCSC_ERR_INVALID); }
+int spcsc_pgm_combine_y(spcsc_handle* h, double a, double b, int32_t save_prev) { H_CALL(h->pgm_combine_y(a, b, save_prev)); }
+int spcsc_pgm_finish(spcsc_handle* h, int32_t mode, double c0, double out[2]) { H_CALL(h->pgm_finish(mode, c0, out)); }
 int spcsc_p2p_export(spcsc_handle* h, void* handle64) { H_CALL(handle64 ? h->p2p_export(handle64) : SPCSC_ERR_INVALID); }
 int spcsc_p2p_attach(spcsc_handle* h, int32_t rank, int32_t nranks, const void* handles64) { H_CALL(h->p2p_attach(rank, nranks, handles64)); }
 int spcsc_set_gradreg(spcsc_handle* h, const void* ghg, const void* wgrd) { H_CALL(h->set_gradreg(ghg, wgrd)); }

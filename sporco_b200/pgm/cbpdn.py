@@ -3,8 +3,8 @@
 Drop-in counterpart of ``sporco.pgm.cbpdn.ConvBPDN`` (sporco/pgm/cbpdn.py:29-384): same
 constructor, ``Options`` tree, ``IterationStats`` fields (ObjFun, DFid, RegL1, Rsdl, F_Btrack,
 Q_Btrack, IterBTrack, L) and ``solve / getcoef / setdict / reconstruct`` surface.
-Supported on the device: fixed step 1/L or ``BacktrackStandard``; Nesterov / linear momentum.
-``Monotone``, ``StepSizePolicy`` and ``BacktrackRobust`` raise ``NotImplementedError``.
+Supported on the device: fixed step 1/L, ``BacktrackStandard`` / ``BacktrackRobust``,
+``StepSizePolicyCauchy`` / ``StepSizePolicyBB``, ``Monotone``; Nesterov / linear momentum.
 """
 
 import copy
@@ -13,7 +13,7 @@ import numpy as np
 
 from .. import _lib, cnvrep as cr
 from . import pgm
-from .backtrack import BacktrackStandard     # noqa: F401  (re-exported for user code)
+from .backtrack import BacktrackStandard, BacktrackRobust     # noqa: F401  (re-exported for user code)
 
 
 class ConvBPDN(pgm.PGMDFT):
@@ -59,9 +59,13 @@ class ConvBPDN(pgm.PGMDFT):
         self._h.set_l1_weight(np.ascontiguousarray(w))
 
         super(ConvBPDN, self).__init__(cri.shpX, cri.Nv, cri.axisN, S.dtype, opt)
+        if opt['Monotone'] and opt['Backtrack'] is not None:
+            raise NotImplementedError('Monotone together with backtracking is not supported on the device')
         x0 = opt['X0']
         self._h.pgm_reset(None if x0 is None else np.asarray(x0, dtype=self.dtype).reshape(cri.shpX))
         self._stats = None
+        self._rsdl = None
+        self._rejected = False
 
     # ---- state on the device
     def _fetch(self, which):
@@ -111,23 +115,76 @@ class ConvBPDN(pgm.PGMDFT):
         for k in (_lib.ARR_PGM_X, _lib.ARR_PGM_XF, _lib.ARR_PGM_YF):
             self._cache.pop(k, None)
         self._stats = s
+        self._rsdl = s[4]
         ty = self.dtype.type
         f = ty(s[0])
         # Q = f(y) + <x - y, grad f(y)> + (L/2) ||x - y||^2      (sporco/pgm/backtrack.py:93-95)
         q = ty(s[1]) + ty(s[2]) + (self.L / 2.) * ty(s[3])
         return f, q
 
+    def policy_stats(self, store=False):
+        """Scalars of the step-size policies / objective at the current state (spcsc_pgm_policy_stats)."""
+        return self._h.pgm_policy_stats(store)
+
+    def on_iteration_start(self):
+        """sporco/pgm/pgm.py:835-846: with ``Monotone`` the objective of the previous iterate is what
+        the next proximal step is compared with (the reference takes it from the initial state
+        for the first TWO iterations: its ``objfn`` is only refreshed by steps with k > 0)."""
+        self._rejected = False
+        if self.opt['Monotone']:
+            if self.k == 0:
+                st = self.policy_stats()
+                self.objfn = (st[4] + self.lmbda * st[5], st[4], st[5])
+            self.objfn_prev = self.objfn
+
+    def xstep(self):
+        """Proximal step of sporco/pgm/pgm.py:779-811 with its optional step-size policy and the
+        monotone safeguard: the policy sets L from the gradient at the auxiliary point before the step;
+        a step that raises the objective is taken back (Xf only, as in the reference)."""
+        if self.stepsizepolicy is not None:
+            from .stepsize import StepSizePolicyBB
+            bb = isinstance(self.stepsizepolicy, StepSizePolicyBB) or any(
+                c.__name__ == 'StepSizePolicyBB' for c in type(self.stepsizepolicy).__mro__)
+            st = self.policy_stats(store=bb)
+            if self.k > 1:
+                self.L = self.stepsizepolicy.update(self, st)
+        self._trial()
+        if self.opt['Monotone'] and self.k > 0:
+            s = self._stats
+            objfn = (s[5] + self.lmbda * s[6], s[5], s[6])
+            if self.objfn_prev[0] < objfn[0]:
+                self._rejected = True
+                self.objfn = self.objfn_prev
+            else:
+                self.objfn = objfn
+
+    def _combine_y(self, a, b, first):
+        self._h.pgm_combine_y(a, b, first)
+        self._cache.pop(_lib.ARR_PGM_YF, None)
+
+    def _finish_robust(self, c0):
+        self._rsdl = self._h.pgm_finish(_lib.PGM_FINISH_ROBUST, c0)
+        for k in (_lib.ARR_PGM_XF,):
+            self._cache.pop(k, None)
+
     def ystep(self):
         """Momentum step (sporco/pgm/pgm.py:815-831) on the device."""
         tprv = self.t
         self.t = self.momentum.update(self.var_momentum())
-        self._h.pgm_accept((tprv - 1.) / self.t)
+        if self._rejected:
+            # monotone: Xf = Xfprv, so Yf = Xf + (tprv / t)(ZZf - Xf)
+            self._rsdl = self._h.pgm_finish(_lib.PGM_FINISH_REJECT, tprv / self.t)
+            self._cache.pop(_lib.ARR_PGM_XF, None)
+        else:
+            self._h.pgm_accept((tprv - 1.) / self.t)
         self._cache.pop(_lib.ARR_PGM_YF, None)
 
     def rsdl(self):
-        return self.dtype.type(self._stats[4])
+        return self.dtype.type(self._rsdl)
 
     def eval_objfn(self):
+        if self.opt['Monotone']:         # the record carries the tracked objective (sporco/pgm/pgm.py:546-549)
+            return self.objfn
         dfd = self._stats[5]
         rl1 = self._stats[6]
         return (dfd + self.lmbda * rl1, dfd, rl1)

@@ -43,6 +43,9 @@ class ConvCnstrMOD(pgm.PGMDFT):
         if opt['Backtrack'] is not None:
             raise NotImplementedError('backtracking is not implemented for the device '
                                       'dictionary update')
+        if opt['Monotone'] or opt['StepSizePolicy'] is not None:
+            raise NotImplementedError('Monotone / StepSizePolicy are not implemented for the device '
+                                      'dictionary update')
         super(ConvCnstrMOD, self).__init__(cri.shpD, cri.Nv, cri.axisN, S.dtype, opt)
         # NB the reference passes dval = 14 K here (pgm/ccmod.py:218) but PGM.__init__ has already
         # set L = 1 (pgm/pgm.py:242) and set_attr keeps a value that is set: the effective

@@ -10,7 +10,6 @@ import copy
 
 from .. import cdict, common, util
 from .momentum import MomentumNesterov
-from .backtrack import BacktrackRobust
 
 
 class PGM(common.IterativeSolver):
@@ -57,13 +56,10 @@ class PGM(common.IterativeSolver):
         self.set_dtype(self.opt, dtype)
         self.set_attr('L', self.opt['L'], dval=1.0, dtype=self.dtype)
         o = self.opt
-        if o['Monotone']:
-            raise NotImplementedError('Monotone PGM is not implemented on the device')
-        if o['StepSizePolicy'] is not None and o['Backtrack'] is None:
-            raise NotImplementedError('StepSizePolicy is not implemented on the device')
-        if isinstance(o['Backtrack'], BacktrackRobust):
-            raise NotImplementedError('BacktrackRobust is not implemented on the device')
-        self.stepsizepolicy = None
+        # step-size policy is switched off when backtracking is enabled (sporco/pgm/pgm.py:236-239)
+        self.stepsizepolicy = o['StepSizePolicy']
+        if o['Backtrack'] is not None:
+            self.stepsizepolicy = None
         self.momentum = o['Momentum']
         if o['AutoStop', 'Enabled']:
             self.tau0 = o['AutoStop', 'Tau0']
@@ -86,12 +82,13 @@ class PGM(common.IterativeSolver):
         fmtstr, nsep = self.display_start()
         self.timer.start(['solve', 'solve_wo_func', 'solve_wo_rsdl', 'solve_wo_btrack'])
         for self.k in range(self.k, self.k + self.opt['MaxMainIter']):
+            self.on_iteration_start()
             if self.backtrack is not None:
                 self.timer.stop('solve_wo_btrack')
                 self.backtrack.update(self)
                 self.timer.start('solve_wo_btrack')
             else:
-                self._trial()
+                self.xstep()
                 self.ystep()
             if not self.opt['FastSolve']:
                 frcxd = self.rsdl()
@@ -113,6 +110,14 @@ class PGM(common.IterativeSolver):
 
     def getmin(self):
         return self.X
+
+    def on_iteration_start(self):
+        """Hook at the top of an iteration (sporco/pgm/pgm.py:835-846); the copies of the previous
+        iterates the reference makes here are implicit on the device."""
+
+    def xstep(self):
+        """One proximal step at the current L."""
+        self._trial()
 
     def var_momentum(self):
         # sporco/pgm/pgm.py:662-668: the Nesterov rule takes t, the linear rules the iteration count.

@@ -179,6 +179,38 @@ def run_pgm_cases(sfx):
     return b
 
 
+PGM_VARIANTS = ('cauchy', 'bb', 'mono', 'robust')
+
+
+def run_pgm_variant_case(name, sfx):
+    """Row a17: StepSizePolicyCauchy / StepSizePolicyBB, Monotone, BacktrackRobust against the reference's
+    stored outputs (fixtures pgm_<name>_<sfx>, generated from the imported reference)."""
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackRobust
+    from sporco_b200.pgm.stepsize import StepSizePolicyBB, StepSizePolicyCauchy
+    g = load('pgm_%s_%s' % (name, sfx))
+    extra = {'cauchy': {'L': 50.0, 'StepSizePolicy': StepSizePolicyCauchy()},
+             'bb': {'L': 50.0, 'StepSizePolicy': StepSizePolicyBB()},
+             'mono': {'L': 150.0, 'Monotone': True},
+             'robust': {'L': 5.0, 'Backtrack': BacktrackRobust(gamma_d=0.95, gamma_u=1.8, maxiter=10)}}[name]
+    opt = pcbpdn.ConvBPDN.Options(dict({'MaxMainIter': 25, 'RelStopTol': 0.0}, **extra))
+    b = pcbpdn.ConvBPDN(g['D'], g['S'], float(g['lmbda']), opt, dimK=1)
+    X = b.solve()
+    its = b.getitstat()
+    # the Barzilai-Borwein quotient amplifies rounding (its denominator is a difference of nearly equal
+    # sums), so float32 trajectories of that policy are compared more loosely
+    tol = 1e-10 if sfx == 'f64' else (2e-3 if name == 'bb' else 1e-4)
+    assert X.dtype == g['X'].dtype
+    assert rel(its.L, g['L']) < tol, 'L %.3e' % rel(its.L, g['L'])
+    assert rel(X, g['X']) < tol, 'X %.3e' % rel(X, g['X'])
+    assert rel(its.ObjFun, g['ObjFun']) < tol and rel(its.DFid, g['DFid']) < 4 * tol
+    assert rel(its.RegL1, g['RegL1']) < tol and rel(its.Rsdl, g['Rsdl']) < 10 * tol
+    if name == 'robust':
+        assert np.array_equal(np.asarray(its.IterBTrack, dtype=np.float64), g['IterBTrack'])
+        assert rel(its.F_Btrack, g['F_Btrack']) < 10 * tol and rel(its.Q_Btrack, g['Q_Btrack']) < 10 * tol
+    return b
+
+
 def run_fusion_cases():
     """The optimistic cross-iteration fusion (the prox kernel also emits the next iteration's
     row spectra): consumed when rho is constant, redone when it changed; X must stay

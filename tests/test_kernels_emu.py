@@ -219,3 +219,9 @@ def test_push_exchange_column_kernel_float64_and_colour_dictionary(monkeypatch):
     r = orc.admm_convbpdn(D, S, 0.1, opt=o)
     assert cases.rel(Y, r.Y) < 3e-4
     assert cases.rel(b.getitstat().ObjFun, [x[1] for x in r.itstat]) < 3e-4
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('name', cases.PGM_VARIANTS)
+def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
+    cases.run_pgm_variant_case(name, sfx)

@@ -139,6 +139,31 @@ def test_pgm_golden(sfx):
     cases.run_pgm_cases(sfx)
 
 
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('name', cases.PGM_VARIANTS)
+def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
+    cases.run_pgm_variant_case(name, sfx)
+
+
+@pytest.mark.parametrize('case', [cases.FRESH_CASES[0], cases.FRESH_CASES[2], (64, 64, 8, 5, None, None, None)])
+def test_push_exchange_column_kernel_vs_oracle(case, monkeypatch):
+    """k_col3 (persistent clusters, sums pushed over DSMEM) against the oracle and against k_col2."""
+    monkeypatch.setenv('SPCSC_COL3', '1')
+    N0, N1, M, K, C, mu, extra = case
+    b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
+    assert b._h.admm_schedule_info()['col_kernel'] == 3
+
+
+@pytest.mark.parametrize('wave', ['2,2', 'f:2,2'])
+def test_wavefront_schedules_vs_oracle(wave, monkeypatch):
+    """The opt-in wavefront schedules (groups of images per launch, several streams)."""
+    if wave.startswith('f:'):
+        monkeypatch.setenv('SPCSC_WAVE_FUSED', '1')
+        wave = wave[2:]
+    monkeypatch.setenv('SPCSC_WAVE', wave)
+    cases.run_fresh_case(64, 256, 12, 5)
+
+
 def test_pgm_vs_oracle_multichannel_dictionary():
     """FISTA with a 3-channel dictionary (gradient summed over channels, pgm/cbpdn.py:263-284),
     NonNegCoef, backtracking; 64x64, M=12, K=2."""

@@ -26,10 +26,7 @@ OTHER_CLASSES = ('ConvBPDNProjL1', 'ConvMinL1InL2Ball',
 # reference tests that exercise the replaced classes but need something not implemented
 NOT_IMPLEMENTED = {
     'admm': {'test_10cplx': 'complex-valued data'},
-    'pgm': {'test_10cplx': 'complex-valued data',
-            'test_13': 'Monotone PGM', 'test_14': 'Monotone PGM',
-            'test_15': 'StepSizePolicyBB', 'test_16': 'StepSizePolicyBB',
-            'test_17': 'StepSizePolicyCauchy', 'test_18': 'StepSizePolicyCauchy'},
+    'pgm': {'test_10cplx': 'complex-valued data'},
 }
 
 
@@ -60,6 +57,7 @@ def _load(kind):
         # sporco_b200 solver expects its own classes of the same names
         src = src.replace('from sporco.pgm.momentum import', 'from sporco_b200.pgm.momentum import')
         src = src.replace('from sporco.pgm.backtrack import', 'from sporco_b200.pgm.backtrack import')
+        src = src.replace('from sporco.pgm.stepsize import', 'from sporco_b200.pgm.stepsize import')
     ns = {'__proxy__': proxy, '__name__': 'ref_tests_' + kind}
     exec(compile(src, path, 'exec'), ns)
     return ns['TestSet01']
