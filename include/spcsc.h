@@ -272,6 +272,21 @@ int spcsc_rfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_
 int spcsc_irfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1,
                  const void* xf, void* x);
 
+/* sporco.linalg.solvedbi_sm (linalg.py:232-297; Cd == 1) and solvemdbi_ism (linalg.py:370-444; Cd > 1):
+   x solves (rho I + sum_c a_c a_c^H) x = b with a_c = conj(ah_c), independently for each of the nf positions and
+   nk right-hand sides, the inner products running over the last axis (M).  Host arrays, complex of `dtype`:
+   ah (nf, Cd, M), b and x (nf, nk, M) -- the reference's (N0, N1f, C, K, M) arrays with the leading axes flattened.
+   The arithmetic is the one inside the fused column kernels (k_col / k_col2 / k_col3).   tests/test_linalg.py:147-207 */
+int spcsc_solvedbi_sm(int32_t dtype, int32_t device, int64_t nf, int32_t nk, int32_t Cd, int32_t M, double rho,
+                      const void* ah, const void* b, void* x);
+/* sporco.prox.prox_l1 (prox/_lp.py:144-183): out = sign(v) max(|v| - alpha w, 0); v, out real (n); w: weights of the
+   same shape or NULL (w = 1).                                                         tests/test_prox.py:77-96 */
+int spcsc_prox_l1(int32_t dtype, int32_t device, int64_t n, double alpha, const void* w, const void* v, void* out);
+/* sporco.prox.prox_sl1l2 (prox/_l21.py:51-88): prox_l1 with alpha, then the l2 shrinkage by beta of the vectors
+   along the middle axis of v (n_outer, C, n_inner).                                   tests/test_prox.py:130-139 */
+int spcsc_prox_sl1l2(int32_t dtype, int32_t device, int64_t n_outer, int32_t C, int64_t n_inner, double alpha,
+                     double beta, const void* v, void* out);
+
 /* sporco.signal.tikhonov_filter (signal.py:244-303), the highpass pre-processing step of the example
    scripts: every image of s (batch, N0, N1) is padded symmetrically by npd, lowpass filtered by solving
    (I + lmbda (Gr^T Gr + Gc^T Gc)) x = s in the DFT domain, cropped; sl = lowpass, sh = s - sl. */

@@ -26,7 +26,7 @@ SYMBOLS = (
     'spcsc_admm_configure', 'spcsc_admm_reset', 'spcsc_admm_set_rho', 'spcsc_admm_set_iter',
     'spcsc_admm_iterate',
     'spcsc_admm_get_scalars', 'spcsc_admm_last_timing', 'spcsc_admm_profile', 'spcsc_admm_schedule_info', 'spcsc_get_array', 'spcsc_set_array', 'spcsc_reconstruct',
-    'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
+    'spcsc_rfft2', 'spcsc_irfft2', 'spcsc_solvedbi_sm', 'spcsc_prox_l1', 'spcsc_prox_sl1l2', 'spcsc_comm_unique_id', 'spcsc_comm_create',
     'spcsc_comm_destroy', 'spcsc_attach_comm', 'spcsc_host_alloc', 'spcsc_host_free',
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
     'spcsc_pgm_accept', 'spcsc_pgm_policy_stats', 'spcsc_pgm_combine_y', 'spcsc_pgm_finish', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
@@ -101,6 +101,10 @@ def _declare(lib):
                                            ctypes.POINTER(ctypes.c_int64)]
     lib.spcsc_admm_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     lib.spcsc_admm_schedule_info.argtypes = [vp, ctypes.POINTER(i32)]
+    i64 = ctypes.c_int64
+    lib.spcsc_solvedbi_sm.argtypes = [i32, i32, i64, i32, i32, i32, ctypes.c_double, vp, vp, vp]
+    lib.spcsc_prox_l1.argtypes = [i32, i32, i64, ctypes.c_double, vp, vp, vp]
+    lib.spcsc_prox_sl1l2.argtypes = [i32, i32, i64, i32, i64, ctypes.c_double, ctypes.c_double, vp, vp]
     lib.spcsc_get_array.argtypes = [vp, i32, vp]
     lib.spcsc_set_array.argtypes = [vp, i32, vp]
     lib.spcsc_reconstruct.argtypes = [vp, vp, vp]
@@ -469,6 +473,58 @@ def rfft2(x, device=0):
     cdt = np.complex64 if x.dtype == np.float32 else np.complex128
     out = np.empty((b, n0, n1 // 2 + 1), dtype=cdt)
     check(lib.spcsc_rfft2(dtype_code(x.dtype), device, b, n0, n1, _ptr(x), _ptr(out)))
+    return out
+
+
+def solvedbi_sm(ah, rho, b, c=None, axis=4, device=0):
+    """``sporco.linalg.solvedbi_sm`` (single-channel ``ah``) / ``solvemdbi_ism`` (``ah`` with several
+    channels on axis 2) on the GPU: arrays in the reference's (N0, N1f, C, K, M) layout, the system
+    solved along the last axis.  `c` (the reference's cached component) is accepted and ignored."""
+    lib = load()
+    if axis not in (4, -1) or ah.ndim != 5 or b.ndim != 5:
+        raise ValueError('expected 5-d arrays (N0, N1f, C, K, M) and axis=4')
+    cdt = np.complex64 if np.dtype(b.dtype) == np.complex64 else np.complex128
+    n0, n1f, cd, ka, m = ah.shape
+    nk = b.shape[3]
+    if ka != 1 or b.shape[2] != 1 or b.shape[:2] != (n0, n1f) or b.shape[4] != m:
+        raise ValueError('ah must be (N0, N1f, Cd, 1, M) and b (N0, N1f, 1, K, M)')
+    ahc = np.ascontiguousarray(ah[:, :, :, 0, :], dtype=cdt)
+    bc = np.ascontiguousarray(b[:, :, 0, :, :], dtype=cdt)
+    out = np.empty_like(bc)
+    code = dtype_code(np.float32 if cdt == np.complex64 else np.float64)
+    check(lib.spcsc_solvedbi_sm(code, device, n0 * n1f, nk, cd, m, float(rho), _ptr(ahc), _ptr(bc), _ptr(out)))
+    return out.reshape(b.shape)
+
+
+def prox_l1(v, alpha, device=0):
+    """``sporco.prox.prox_l1`` on the GPU; `alpha` a scalar or an array broadcastable to `v`."""
+    lib = load()
+    v = np.ascontiguousarray(v)
+    out = np.empty_like(v)
+    w = None
+    a = alpha
+    if np.ndim(alpha) > 0:
+        w = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=v.dtype), v.shape))
+        a = 1.0
+    check(lib.spcsc_prox_l1(dtype_code(v.dtype), device, v.size, float(a), None if w is None else _ptr(w),
+                            _ptr(v), _ptr(out)))
+    return out
+
+
+def prox_sl1l2(v, alpha, beta, axis=None, device=0):
+    """``sporco.prox.prox_sl1l2`` on the GPU, the l2 norm taken along one `axis` (all axes if None)."""
+    lib = load()
+    v = np.ascontiguousarray(v)
+    if axis is None:
+        outer, c, inner = 1, v.size, 1
+    else:
+        axis = axis % v.ndim
+        outer = int(np.prod(v.shape[:axis], dtype=np.int64))
+        c = v.shape[axis]
+        inner = int(np.prod(v.shape[axis + 1:], dtype=np.int64))
+    out = np.empty_like(v)
+    check(lib.spcsc_prox_sl1l2(dtype_code(v.dtype), device, outer, c, inner, float(alpha), float(beta),
+                               _ptr(v), _ptr(out)))
     return out
 
 

@@ -1188,6 +1188,95 @@ SPCSC_GLOBAL void k_spec_sumsq(const C2<T>* SPCSC_RESTRICT z, double* SPCSC_REST
     block_accumulate<1>(s, red, acc_slot);
 }
 
+// ---- level-1 entry points (stand-alone launches of the arithmetic the fused kernels use) ---------------
+// linalg.solvedbi_sm / solvemdbi_ism (linalg.py:232-297, 370-444): (rho I + sum_c a_c a_c^H) x = b with
+// a_c = conj(ah_c), per position f and right-hand side k, reduction over the M axis.
+//   ah [nf][CD][M], b and x [nf][nk][M].  One warp per (f, k): lanes stride over M.
+template <typename T, int CD>
+SPCSC_GLOBAL void k_solvedbi(const C2<T>* SPCSC_RESTRICT ah, const C2<T>* SPCSC_RESTRICT b,
+                             C2<T>* SPCSC_RESTRICT x, long long nf, int nk, int M, T rho) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp; w < nf * nk; w += nwarp) {
+        const long long f = w / nk;
+        const C2<T>* a = ah + (size_t)f * CD * M;
+        const C2<T>* bb = b + (size_t)w * M;
+        // s_c = sum_m ah_c,m b_m ;  G_ij = sum_m ah_i,m conj(ah_j,m)
+        C2<T> sv[CD], A[CD][CD];
+        SPCSC_UNROLL
+        for (int i = 0; i < CD; ++i) {
+            sv[i] = mk<T>(0, 0);
+            SPCSC_UNROLL
+            for (int j = 0; j < CD; ++j) A[i][j] = mk<T>(0, 0);
+        }
+        for (int m = lane; m < M; m += 32) {
+            const C2<T> bm = bb[m];
+            C2<T> am[CD];
+            SPCSC_UNROLL
+            for (int i = 0; i < CD; ++i) am[i] = a[(size_t)i * M + m];
+            SPCSC_UNROLL
+            for (int i = 0; i < CD; ++i) {
+                sv[i] = sv[i] + am[i] * bm;
+                SPCSC_UNROLL
+                for (int j = 0; j < CD; ++j) A[i][j] = A[i][j] + mulc(am[i], am[j]);
+            }
+        }
+        SPCSC_UNROLL
+        for (int i = 0; i < CD; ++i) {
+            SPCSC_UNROLL
+            for (int o = 16; o > 0; o >>= 1) {
+                sv[i].re += __shfl_xor_sync(0xffffffffu, sv[i].re, o);
+                sv[i].im += __shfl_xor_sync(0xffffffffu, sv[i].im, o);
+            }
+            SPCSC_UNROLL
+            for (int j = 0; j < CD; ++j) {
+                SPCSC_UNROLL
+                for (int o = 16; o > 0; o >>= 1) {
+                    A[i][j].re += __shfl_xor_sync(0xffffffffu, A[i][j].re, o);
+                    A[i][j].im += __shfl_xor_sync(0xffffffffu, A[i][j].im, o);
+                }
+            }
+            A[i][i].re += rho;
+        }
+        if (CD == 1) {
+            sv[0] = mk<T>(sv[0].re / A[0][0].re, sv[0].im / A[0][0].re);
+        } else {
+            hpd_solve<T, CD>(A, sv, CD);
+        }
+        for (int m = lane; m < M; m += 32) {
+            C2<T> v = bb[m];
+            SPCSC_UNROLL
+            for (int i = 0; i < CD; ++i) v = v - mulc(sv[i], a[(size_t)i * M + m]);   // conj(ah) * y
+            x[(size_t)w * M + m] = mk<T>(v.re / rho, v.im / rho);
+        }
+    }
+}
+// prox_l1 (prox/_lp.py:144-183) and prox_sl1l2 (prox/_l21.py:51-88, the l2 shrinkage over the middle axis of
+// [n_outer][C][n_inner]); w: optional weights of the l1 term, same shape as v
+template <typename T>
+SPCSC_GLOBAL void k_prox_l1l2(const T* SPCSC_RESTRICT v, const T* SPCSC_RESTRICT w, T* SPCSC_RESTRICT out,
+                              long long n_outer, int C, long long n_inner, T alpha, T beta, int joint) {
+    const long long n = n_outer * n_inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long o = i / n_inner, r = i - o * n_inner;
+        const size_t base = (size_t)o * C * n_inner + r;
+        T a2 = 0;
+        for (int c = 0; c < C; ++c) {
+            const size_t j = base + (size_t)c * n_inner;
+            const T t = soft_threshold(v[j], alpha * (w ? w[j] : (T)1));
+            out[j] = t;
+            a2 += t * t;
+        }
+        if (joint) {
+            const T a = sqrt(a2);
+            const T fac = (a != (T)0) ? fmax((T)0, a - beta) / a : (T)0;
+            for (int c = 0; c < C; ++c) out[base + (size_t)c * n_inner] *= fac;
+        }
+    }
+}
+
 // ---- sporco.signal.tikhonov_filter (signal.py:244-303) ------------------------------------
 // symmetric padding by npd on every side of each image: index -1 -> 0, N -> N-1 (numpy 'symmetric')
 template <typename T>

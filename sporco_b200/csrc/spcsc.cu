@@ -1841,6 +1841,52 @@ int unit_fft2(bool inverse, int device, int batch, int N0, int N1, const void* i
     return SPCSC_OK;
 }
 
+// level-1 entry points on plain host arrays: stage, launch, copy back
+struct TmpDev {
+    void* p = nullptr;
+    ~TmpDev() { if (p) cudaFree(p); }
+    cudaError_t get(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+#define LCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError(); err = std::string(#call) + ": " + cudaGetErrorString(e_); return SPCSC_ERR_CUDA; } } while (0)
+template <typename T>
+int unit_solvedbi(int device, long long nf, int nk, int Cd, int M, double rho, const void* ah, const void* b,
+                  void* x, std::string& err) {
+    if (nf < 1 || nk < 1 || M < 1 || Cd < 1 || Cd > 4 || !(rho > 0.0)) { err = "bad argument (need nf, nk, M >= 1, 1 <= Cd <= 4, rho > 0)"; return SPCSC_ERR_INVALID; }
+    LCK(cudaSetDevice(device));
+    const size_t na = (size_t)nf * Cd * M * sizeof(C2<T>), nb = (size_t)nf * nk * M * sizeof(C2<T>);
+    TmpDev da, db, dx;
+    LCK(da.get(na)); LCK(db.get(nb)); LCK(dx.get(nb));
+    LCK(cudaMemcpy(da.p, ah, na, cudaMemcpyHostToDevice));
+    LCK(cudaMemcpy(db.p, b, nb, cudaMemcpyHostToDevice));
+    long long warps = nf * nk;
+    int blocks = (int)((warps + 7) / 8 < 1184 ? (warps + 7) / 8 : 1184);
+    const C2<T>* pa = (const C2<T>*)da.p; const C2<T>* pb = (const C2<T>*)db.p; C2<T>* px = (C2<T>*)dx.p;
+    switch (Cd) {
+        case 1: LCK(launch(k_solvedbi<T, 1>, dim3(blocks), dim3(256), 0, (cudaStream_t)0, pa, pb, px, nf, nk, M, (T)rho)); break;
+        case 2: LCK(launch(k_solvedbi<T, 2>, dim3(blocks), dim3(256), 0, (cudaStream_t)0, pa, pb, px, nf, nk, M, (T)rho)); break;
+        case 3: LCK(launch(k_solvedbi<T, 3>, dim3(blocks), dim3(256), 0, (cudaStream_t)0, pa, pb, px, nf, nk, M, (T)rho)); break;
+        default: LCK(launch(k_solvedbi<T, 4>, dim3(blocks), dim3(256), 0, (cudaStream_t)0, pa, pb, px, nf, nk, M, (T)rho)); break;
+    }
+    LCK(cudaMemcpy(x, dx.p, nb, cudaMemcpyDeviceToHost));
+    return SPCSC_OK;
+}
+template <typename T>
+int unit_prox(int device, long long n_outer, int C, long long n_inner, double alpha, double beta, int joint,
+              const void* w, const void* v, void* out, std::string& err) {
+    if (n_outer < 1 || C < 1 || n_inner < 1) { err = "bad argument"; return SPCSC_ERR_INVALID; }
+    LCK(cudaSetDevice(device));
+    const size_t nbytes = (size_t)n_outer * C * n_inner * sizeof(T);
+    TmpDev dv, dw, dout;
+    LCK(dv.get(nbytes)); LCK(dout.get(nbytes));
+    LCK(cudaMemcpy(dv.p, v, nbytes, cudaMemcpyHostToDevice));
+    if (w) { LCK(dw.get(nbytes)); LCK(cudaMemcpy(dw.p, w, nbytes, cudaMemcpyHostToDevice)); }
+    LCK(launch(k_prox_l1l2<T>, dim3(592), dim3(256), 0, (cudaStream_t)0, (const T*)dv.p, (const T*)dw.p, (T*)dout.p,
+               n_outer, C, n_inner, (T)alpha, (T)beta, joint));
+    LCK(cudaMemcpy(out, dout.p, nbytes, cudaMemcpyDeviceToHost));
+    return SPCSC_OK;
+}
+#undef LCK
+
 template <typename T>
 int unit_tikhonov(int device, int batch, int N0, int N1, double lmbda, int npd, const void* in,
                   void* sl, void* sh, std::string& err) {
@@ -2084,6 +2130,23 @@ int spcsc_tikhonov_filter(int32_t dtype, int32_t device, int32_t batch, int32_t 
     return dtype == SPCSC_F32
                ? unit_tikhonov<float>(device, batch, N0, N1, lmbda, npd, s, sl, sh, g_last_error)
                : unit_tikhonov<double>(device, batch, N0, N1, lmbda, npd, s, sl, sh, g_last_error);
+}
+int spcsc_solvedbi_sm(int32_t dtype, int32_t device, int64_t nf, int32_t nk, int32_t Cd, int32_t M, double rho,
+                      const void* ah, const void* b, void* x) {
+    if (!ah || !b || !x) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
+    return dtype == SPCSC_F32 ? unit_solvedbi<float>(device, nf, nk, Cd, M, rho, ah, b, x, g_last_error)
+                              : unit_solvedbi<double>(device, nf, nk, Cd, M, rho, ah, b, x, g_last_error);
+}
+int spcsc_prox_l1(int32_t dtype, int32_t device, int64_t n, double alpha, const void* w, const void* v, void* out) {
+    if (!v || !out) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
+    return dtype == SPCSC_F32 ? unit_prox<float>(device, 1, 1, n, alpha, 0.0, 0, w, v, out, g_last_error)
+                              : unit_prox<double>(device, 1, 1, n, alpha, 0.0, 0, w, v, out, g_last_error);
+}
+int spcsc_prox_sl1l2(int32_t dtype, int32_t device, int64_t n_outer, int32_t C, int64_t n_inner, double alpha,
+                     double beta, const void* v, void* out) {
+    if (!v || !out) { g_last_error = "bad argument"; return SPCSC_ERR_INVALID; }
+    return dtype == SPCSC_F32 ? unit_prox<float>(device, n_outer, C, n_inner, alpha, beta, 1, nullptr, v, out, g_last_error)
+                              : unit_prox<double>(device, n_outer, C, n_inner, alpha, beta, 1, nullptr, v, out, g_last_error);
 }
 int spcsc_irfft2(int32_t dtype, int32_t device, int32_t batch, int32_t N0, int32_t N1, const void* xf,
                  void* x) {

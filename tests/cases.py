@@ -179,6 +179,31 @@ def run_pgm_cases(sfx):
     return b
 
 
+def run_level1_cases():
+    """The level-1 entry points (spcsc_solvedbi_sm, spcsc_prox_l1, spcsc_prox_sl1l2) against the
+    reference's own outputs in tests/golden/level1.npz, both precisions, and the algebraic pins of
+    the reference's unit tests (tests/test_linalg.py:147-207)."""
+    from sporco_b200 import linalg, prox
+    g = load('level1')
+    for cdt, tol in ((np.complex128, 1e-13), (np.complex64, 2e-6)):
+        rdt = np.float64 if cdt == np.complex128 else np.float32
+        x = linalg.solvedbi_sm(g['ah'].astype(cdt), 0.7, g['b'].astype(cdt))
+        assert x.dtype == cdt and rel(x, g['x']) < tol
+        a = np.conj(g['ah'])
+        lhs = a * np.sum(g['ah'] * x, axis=4, keepdims=True) + 0.7 * x
+        assert rel(lhs, g['b']) < 10 * tol                       # (rho I + a a^H) x = b
+        x3 = linalg.solvemdbi_ism(g['ah3'].astype(cdt), 0.7, g['b3'].astype(cdt), 4, 2)
+        assert rel(x3, g['x3']) < tol
+        p1 = prox.prox_l1(g['v'].astype(rdt), 0.4)
+        assert p1.dtype == rdt and rel(p1, g['prox_l1']) < tol
+        w = np.linspace(0.2, 1.0, 4).astype(rdt)
+        pw = prox.prox_l1(g['v'].astype(rdt), 0.4 * w)
+        vv = g['v']
+        assert rel(pw, np.sign(vv) * np.maximum(np.abs(vv) - 0.4 * w, 0)) < tol
+        p21 = prox.prox_sl1l2(g['v'].astype(rdt), 0.3, 0.25, axis=2)
+        assert rel(p21, g['prox_sl1l2']) < tol
+
+
 PGM_VARIANTS = ('cauchy', 'bb', 'mono', 'robust')
 
 

@@ -225,3 +225,7 @@ def test_push_exchange_column_kernel_float64_and_colour_dictionary(monkeypatch):
 @pytest.mark.parametrize('name', cases.PGM_VARIANTS)
 def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
     cases.run_pgm_variant_case(name, sfx)
+
+
+def test_level1_entry_points():
+    cases.run_level1_cases()

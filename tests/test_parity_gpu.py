@@ -278,3 +278,7 @@ def test_eight_cta_clusters_admm_and_pgm():
     its = p.getitstat()
     assert cases.rel(its.ObjFun, [row[1] for row in rp.itstat]) < 1e-4
     assert np.array_equal(np.asarray(its.IterBTrack, dtype=float), np.array([row[7] for row in rp.itstat], dtype=float))
+
+
+def test_level1_entry_points():
+    cases.run_level1_cases()
