@@ -19,7 +19,6 @@ from .. import _lib, cnvrep as cr, common
 from . import admm
 
 
-_COMMS = {}     # (process group, device, world size) -> _lib.Comm, created once per process
 
 
 class GenericConvBPDN(admm.ADMMEqual):
@@ -217,63 +216,9 @@ class GenericConvBPDN(admm.ADMMEqual):
         the squared norms behind r, s, rho and the stopping test -- global over all images in
         the reference (sporco/admm/admm.py:462-486) -- are summed over the ranks once per
         iteration on the device.  Coefficient maps never leave their GPU.  ``torch.distributed``
-        only carries the 128-byte NCCL id and the element count."""
-        import torch
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-        dev = torch.device('cuda', self._device)
-        key = (id(group), self._device, world)
-        comm = _COMMS.get(key)
-        if comm is None:
-            nccl_lib = _lib.nccl_library_path()
-            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-            if rank == 0:
-                uid = torch.frombuffer(bytearray(_lib.comm_unique_id(nccl_lib)),
-                                       dtype=torch.uint8).to(dev)
-            dist.broadcast(uid, src=0, group=group)
-            comm = _lib.Comm(nccl_lib, bytes(uid.cpu().numpy().tobytes()), rank, world,
-                             self._device)
-            _COMMS[key] = comm
-        nx = torch.tensor([float(self.Nx)], dtype=torch.float64, device=dev)
-        dist.all_reduce(nx, group=group)
-        self._h.attach_comm(comm, float(nx.item()))
-        self._world = world
-        # the per-iteration all-reduce of the 16 accumulators over peer memory instead of NCCL,
-        # where the ranks can map each other's memory (one node, <= 8 ranks); every rank must
-        # take the same decision, hence the all-reduce of the outcome
-        self._p2p = False
-        if 1 < world <= 8 and os.environ.get('SPCSC_P2P', '1') != '0':
-            if comm.p2p is not None:
-                # an earlier solver of this group has settled it (the blocks live with the communicator):
-                # no handle exchange, no collective
-                if comm.p2p:
-                    self._p2p = bool(self._h.p2p_attach(rank, world, None))
-                return
-            # every rank takes part in every collective below, whatever happened locally: a rank
-            # whose export failed sends a zero handle and votes "no"
-            ok = True
-            try:
-                raw = bytearray(self._h.p2p_export())
-            except _lib.SpcscError:
-                raw, ok = bytearray(64), False
-            mine = torch.frombuffer(raw, dtype=torch.uint8).to(dev)
-            allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
-            dist.all_gather(allh, mine, group=group)
-            flag = torch.tensor([1.0 if ok else 0.0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if flag.item() == 1.0:
-                blob = b''.join(bytes(t.cpu().numpy().tobytes()) for t in allh)
-                try:
-                    ok = bool(self._h.p2p_attach(rank, world, blob))
-                except _lib.SpcscError:
-                    ok = False
-            else:
-                ok = False
-            flag = torch.tensor([1.0 if ok else 0.0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if flag.item() != 1.0 and ok:
-                self._h.p2p_detach()
-            self._p2p = bool(flag.item() == 1.0)
-            comm.p2p = self._p2p
+        only carries the 128-byte NCCL id, the peer-memory handles and the element count."""
+        from .. import _dist
+        self._world, self._p2p = _dist.attach(self._h, self._device, float(self.Nx), dist, group)
 
     # ---- pickling: device state travels as host arrays
     def __getstate__(self):

@@ -924,15 +924,23 @@ SPCSC_DEV void fold_det_bins(double* acc) {
 // exchange ahead of the slowest one (it cannot pass exchange n+1 without that rank's flag n+1, which
 // is raised only after exchange n was read), so buffer n+2 never overwrites unread data.
 constexpr int kP2pMaxRanks = 8;
+constexpr int kP2pVecMax = 16384;      // largest vector (elements) the peer-memory vector all-reduce takes
 struct P2pSlots {
     double vals[2][kP2pMaxRanks][ACC_N];
     unsigned long long flag[2][kP2pMaxRanks];
 };
+// The block every rank allocates and its peers map: the accumulator slots, this rank's exchange counters
+// (advanced only by exchanges that execute), and the slots of the vector all-reduce (dictionary learning:
+// the cropped dictionary gradient, h*w*Cd*M values, pgm/ccmod.py + cnvrep.py:953-981).
+struct P2pBlock {
+    P2pSlots slots;
+    unsigned long long seq, vseq;
+    unsigned long long vflag[2][kP2pMaxRanks];
+    double vec[2][kP2pMaxRanks][kP2pVecMax];
+};
 struct P2pView {
-    P2pSlots* peer[kP2pMaxRanks];      // peer[r]: rank r's block as mapped here (peer[rank] = own block)
+    P2pBlock* peer[kP2pMaxRanks];      // peer[r]: rank r's block as mapped here (peer[rank] = own block)
     int nranks, rank;
-    unsigned long long* seq_dev;       // own exchange counter (device memory): the number of exchanges executed
-                                       // so far; every rank executes the same ones, so the counters agree
 };
 // All threads of the (single) block; blockDim.x >= ACC_N * nranks.  Returns false on time-out.
 SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
@@ -945,23 +953,23 @@ SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         timed_out = 0;
-        seq_s = ++(*pv.seq_dev);           // > 0; advanced only by exchanges that execute
+        seq_s = ++pv.peer[pv.rank]->seq;           // > 0; advanced only by exchanges that execute
     }
     __syncthreads();
     const unsigned long long seq = seq_s;
     const int par = (int)(seq & 1ull);
     if (tid < ACC_N * pv.nranks) {
         const int r = tid / ACC_N, i = tid % ACC_N;
-        pv.peer[r]->vals[par][pv.rank][i] = acc[i];
+        pv.peer[r]->slots.vals[par][pv.rank][i] = acc[i];
     }
     __threadfence_system();
     __syncthreads();
     if (tid < pv.nranks) {
-        volatile unsigned long long* f = &pv.peer[tid]->flag[par][pv.rank];
+        volatile unsigned long long* f = &pv.peer[tid]->slots.flag[par][pv.rank];
         *f = seq;
     }
     if (tid < pv.nranks) {
-        volatile unsigned long long* f = &pv.peer[pv.rank]->flag[par][tid];
+        volatile unsigned long long* f = &pv.peer[pv.rank]->slots.flag[par][tid];
         const long long t0 = clock64();
         while (*f != seq) {
             if (clock64() - t0 > 60000000000LL) { timed_out = 1; break; }     // ~30 s: ranks may start far apart
@@ -971,7 +979,7 @@ SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
     __syncthreads();
     if (timed_out) return false;
     if (tid < ACC_N) {
-        const volatile double* v = &pv.peer[pv.rank]->vals[par][0][tid];
+        const volatile double* v = &pv.peer[pv.rank]->slots.vals[par][0][tid];
         double s = 0.0;
         for (int r = 0; r < pv.nranks; ++r) s += v[(size_t)r * ACC_N];
         acc[tid] = s;
@@ -979,6 +987,77 @@ SPCSC_DEV bool p2p_allreduce(const P2pView& pv, double* acc) {
     __syncthreads();
     return true;
 #endif
+}
+
+// All-reduce (sum) of a vector of n <= kP2pVecMax values over the ranks, same protocol as p2p_allreduce with
+// its own counter, flags and slots; sums in double, in rank order, so every rank ends with identical values.
+// One block; any number of threads.  On time-out *status is set to 2.
+template <typename T>
+SPCSC_GLOBAL void k_p2p_allreduce_vec(P2pView pv, T* SPCSC_RESTRICT data, int n, int* SPCSC_RESTRICT status) {
+#ifndef SPCSC_EMU
+    __shared__ int timed_out;
+    __shared__ unsigned long long seq_s;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        timed_out = 0;
+        seq_s = ++pv.peer[pv.rank]->vseq;
+    }
+    __syncthreads();
+    const unsigned long long seq = seq_s;
+    const int par = (int)(seq & 1ull);
+    for (int r = 0; r < pv.nranks; ++r) {
+        double* dst = pv.peer[r]->vec[par][pv.rank];
+        for (int i = tid; i < n; i += nt) dst[i] = (double)data[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pv.nranks) {
+        volatile unsigned long long* f = &pv.peer[tid]->vflag[par][pv.rank];
+        *f = seq;
+    }
+    if (tid < pv.nranks) {
+        volatile unsigned long long* f = &pv.peer[pv.rank]->vflag[par][tid];
+        const long long t0 = clock64();
+        while (*f != seq) {
+            if (clock64() - t0 > 60000000000LL) { timed_out = 1; break; }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (timed_out) {
+        if (tid == 0 && status) *status = 2;
+        return;
+    }
+    for (int i = tid; i < n; i += nt) {
+        double s = 0.0;
+        for (int r = 0; r < pv.nranks; ++r) {
+            const volatile double* v = pv.peer[pv.rank]->vec[par][r];
+            s += v[i];
+        }
+        data[i] = (T)s;
+    }
+#else
+    (void)pv; (void)data; (void)n; (void)status;
+#endif
+}
+// the accumulator all-reduce as a kernel of its own (dictionary learning: the data fidelity of the new iterate)
+template <int DUMMY>
+SPCSC_GLOBAL void k_p2p_allreduce_acc(P2pView pv, double* acc, int* status) {
+    if (!p2p_allreduce(pv, acc) && threadIdx.x == 0 && status) *status = 2;
+}
+// gather / scatter of the filter supports (top-left hd x wd of every [Cd*M] plane of N0 x N1)
+template <typename T>
+SPCSC_GLOBAL void k_support_copy(T* SPCSC_RESTRICT full, T* SPCSC_RESTRICT compact, int planes, int N0, int N1,
+                                 int hd, int wd, int scatter) {
+    const size_t n = (size_t)planes * hd * wd;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % wd), y = (int)((i / wd) % hd);
+        const size_t pl = i / ((size_t)hd * wd);
+        const size_t o = (pl * N0 + y) * N1 + x;
+        if (scatter) full[o] = compact[i];
+        else compact[i] = full[o];
+    }
 }
 
 // Used before a multi-rank all-reduce (which then sums plain doubles in NCCL's fixed order).

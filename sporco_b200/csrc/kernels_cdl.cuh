@@ -79,15 +79,19 @@ k_ccmod_grad(const C2<T>* SPCSC_RESTRICT Zf, const C2<T>* SPCSC_RESTRICT Yf,
     block_accumulate<1>(s2, dred, acc + ACC_CDL_DFID);
 }
 
-// Vf = Yf - g / L
+// Vf = ys Yf - g / L   (ys = 1; with images sharded over R ranks ys = 1/R, so that the rank sum of the
+// inverse transforms is irfftn(Yf - sum_r g_r / L))
 template <typename T>
 SPCSC_GLOBAL void k_ccmod_step(const C2<T>* SPCSC_RESTRICT Yf, const C2<T>* SPCSC_RESTRICT g,
-                               C2<T>* SPCSC_RESTRICT Vf, T L, size_t n) {
+                               C2<T>* SPCSC_RESTRICT Vf, T L, T ys, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const C2<T> a = Yf[i], b = g[i];
         const T inv = (T)1 / L;
-        Vf[i] = mk<T>(a.re - inv * b.re, a.im - inv * b.im);
+        if (ys == (T)1)
+            Vf[i] = mk<T>(a.re - inv * b.re, a.im - inv * b.im);
+        else
+            Vf[i] = mk<T>(ys * a.re - inv * b.re, ys * a.im - inv * b.im);
     }
 }
 

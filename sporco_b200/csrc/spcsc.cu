@@ -389,6 +389,7 @@ class Engine : public spcsc_handle {
     spcsc_pgm_opts popts;
     DevBuf<T> cdX;                                  // CCMOD: dictionary iterate, real [Cd][M][N0][N1]
     DevBuf<C2<T>> cdXf, cdYf, cdV, cdG;             // its spectrum, the momentum point, scratch, gradient
+    DevBuf<T> cd_supp;                              //   filter supports of V (sharded: what is exchanged)
     DevBuf<T> ghg_buf;                              // ConvBPDNGradReg: GHG in device order [N1f][N0]
     DevBuf<C2<T>> gw_buf;                           //   per filter (mu w_m, w_m)
     std::vector<T> gr_w;                            //   host copy of w_m (mu arrives with admm_configure)
@@ -457,7 +458,7 @@ class Engine : public spcsc_handle {
         stw_row1.release(); stw_rowc.release(); stw_col.release();
         pgA.release(); pgB.release(); Zt2.release();
         pgZ.release(); pgYp.release(); pg_sx.release(); pg_rprev.release(); pg_sxprev.release();
-        cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
+        cd_supp.release(); cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
 #ifndef SPCSC_EMU
 #endif
@@ -914,6 +915,22 @@ class Engine : public spcsc_handle {
         return SPCSC_OK;
     }
 
+    // sum the ACC_N accumulators over the ranks (PGM trial sums, policy scalars, dictionary-update terms)
+    int reduce_acc_over_ranks() {
+        if (!nccl_comm) return SPCSC_OK;
+        if (p2p_on) {
+            CK(launch(k_p2p_allreduce_acc<0>, dim3(1), dim3(256), 0, stream, p2p, acc.p, &st.p->stopped));
+        } else {
+            int nr = nccl->AllReduce(acc.p, acc.p, ACC_N, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, stream);
+            if (nr != 0) {
+                err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr);
+                poisoned = true;
+                return SPCSC_ERR_NCCL;
+            }
+        }
+        return SPCSC_OK;
+    }
+
     // the exchange of the residual / objective sums (multi-GPU) and the scalar kernel
     int launch_scalars(int k_base, int n) {
         P2pView pv{};
@@ -1269,8 +1286,8 @@ class Engine : public spcsc_handle {
         // failures here are not fatal (the NCCL all-reduce stays in use): report, do not poison the handle
         if (!comm_obj->p2p_own) {
             void* q = nullptr;
-            cudaError_t e = cudaMalloc(&q, sizeof(P2pSlots) + sizeof(unsigned long long));
-            if (e == cudaSuccess) e = cudaMemset(q, 0, sizeof(P2pSlots) + sizeof(unsigned long long));
+            cudaError_t e = cudaMalloc(&q, sizeof(P2pBlock));
+            if (e == cudaSuccess) e = cudaMemset(q, 0, sizeof(P2pBlock));
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 if (q) cudaFree(q);
@@ -1326,11 +1343,10 @@ class Engine : public spcsc_handle {
         }
         P2pView v{};
         v.nranks = nr; v.rank = rank;
-        // exchange counter: lives on the device (behind the own block), is zeroed with the block at allocation
-        // and advances only when an exchange really executes -- launches skipped after the stopping test fired
-        // do not count, and flags left in the peers' blocks by earlier solvers never match a new number
-        v.seq_dev = reinterpret_cast<unsigned long long*>(reinterpret_cast<P2pSlots*>(comm_obj->p2p_own) + 1);
-        for (int r = 0; r < nr; ++r) v.peer[r] = reinterpret_cast<P2pSlots*>(comm_obj->p2p_peer[r]);
+        // the exchange counters live in the block itself (zeroed with it at allocation) and advance only when an
+        // exchange really executes -- launches skipped after the stopping test fired do not count, and flags
+        // left in the peers' blocks by earlier solvers never match a new number
+        for (int r = 0; r < nr; ++r) v.peer[r] = reinterpret_cast<P2pBlock*>(comm_obj->p2p_peer[r]);
         p2p = v;
         p2p_on = true;
         return SPCSC_OK;
@@ -1439,13 +1455,21 @@ class Engine : public spcsc_handle {
         CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
         // gradient at Yf (one pass over the coefficient spectra)
         CK(launch_grad<true>((const C2<T>*)cdYf.p, cdG.p));
-        if (nccl_comm) {   // images are sharded over ranks: the gradient is a sum over all of them
+        // Images sharded over ranks: the gradient is a sum over all of them.  Pcn only looks at the filter
+        // supports and cropping is linear (cnvrep.py:953-981), so instead of all-reducing the 2 N0 N1f Cd M values of
+        // the spectral gradient every rank forms V_r = irfftn(Yf / R - g_r / L), and only the hd x wd supports of
+        // V = sum_r V_r are exchanged (hd wd Cd M values: 16 KB at 8x8x64) -- over the peer-memory block when the
+        // ranks have mapped each other, else by one small NCCL call.
+        const int nsupp = pb.hd * pb.wd * Cd * M;
+        const bool crop_reduce = nccl_comm && (p2p_on ? nsupp <= kP2pVecMax : true) &&
+                                 !(getenv("SPCSC_CDL_FULLREDUCE") && atoi(getenv("SPCSC_CDL_FULLREDUCE")) == 1);
+        if (nccl_comm && !crop_reduce) {
             int nr = nccl->AllReduce(cdG.p, cdG.p, 2 * nsp, sizeof(T) == 4 ? 7 : 8, 0, nccl_comm, stream);
             if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
         }
         CK(cudaMemcpyAsync(&hF, acc.p + ACC_CDL_F, sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(launch(k_ccmod_step<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)cdYf.p,
-                  (const C2<T>*)cdG.p, cdV.p, (T)L, nsp));
+                  (const C2<T>*)cdG.p, cdV.p, (T)L, crop_reduce ? (T)(1.0 / (double)nranks) : (T)1, nsp));
         // V = irfftn(Vf): inverse columns, inverse rows
         ColLaunch<T> ci = colargs(M, Cd);
         ci.in = cdV.p; ci.out = cdV.p; ci.a.Cd = 1;
@@ -1453,6 +1477,20 @@ class Engine : public spcsc_handle {
         CK(tmp_real.ensure((size_t)Cd * M * N0 * N1));
         CK(row_inv<T>(H, rowargs(M, Cd, 1), (const C2<T>*)cdV.p, tmp_real.p,
                       (T)(1.0 / ((double)N0 * (double)N1))));
+        if (crop_reduce) {
+            CK(cd_supp.ensure((size_t)nsupp + 4));
+            CK(launch(k_support_copy<T>, dim3(64), dim3(256), 0, stream, tmp_real.p, cd_supp.p, Cd * M, N0, N1,
+                      pb.hd, pb.wd, 0));
+            if (p2p_on) {
+                CK(launch(k_p2p_allreduce_vec<T>, dim3(1), dim3(1024), 0, stream, p2p, cd_supp.p, nsupp,
+                          &st.p->stopped));
+            } else {
+                int nr = nccl->AllReduce(cd_supp.p, cd_supp.p, (size_t)nsupp, sizeof(T) == 4 ? 7 : 8, 0, nccl_comm, stream);
+                if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+            }
+            CK(launch(k_support_copy<T>, dim3(64), dim3(256), 0, stream, tmp_real.p, cd_supp.p, Cd * M, N0, N1,
+                      pb.hd, pb.wd, 1));
+        }
         // X = Pcn(V) ; Xf = rfftn(X)  (into cdV, the old Xf stays in cdXf as Xfprv)
         CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, cdX.p, acc.p, Cd, M,
                   N0, N1, pb.hd, pb.wd, cd_zero_mean, 0));
@@ -1469,8 +1507,12 @@ class Engine : public spcsc_handle {
         CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 2 * sizeof(double), stream));
         if (flags & SPCSC_CCMOD_DFID) CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
         if (nccl_comm && (flags & SPCSC_CCMOD_DFID)) {
-            int nr = nccl->AllReduce(acc.p + ACC_CDL_DFID, acc.p + ACC_CDL_DFID, 1, 8, 0, nccl_comm, stream);
-            if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+            if (p2p_on) {       // the 16 accumulators over the peer block, as in the ADMM iteration
+                CK(launch(k_p2p_allreduce_acc<0>, dim3(1), dim3(256), 0, stream, p2p, acc.p, &st.p->stopped));
+            } else {
+                int nr = nccl->AllReduce(acc.p + ACC_CDL_DFID, acc.p + ACC_CDL_DFID, 1, 8, 0, nccl_comm, stream);
+                if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+            }
         }
         if (flags & SPCSC_CCMOD_CNSTR)
             CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
@@ -1624,6 +1666,7 @@ class Engine : public spcsc_handle {
             default: FAIL(SPCSC_ERR_UNSUPPORTED, "more than 4 dictionary channels");
         }
         CK(launch(k_l1_sum<T>, dim3(592), dim3(256), 0, stream, (const T*)Y.p, wl1, acc.p + 5, K, Cx, M, N0, N1));
+        { int rr = reduce_acc_over_ranks(); if (rr) return rr; }
         double ha[6];
         CK(cudaMemcpyAsync(ha, acc.p, sizeof(ha), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1675,6 +1718,11 @@ class Engine : public spcsc_handle {
             std::swap(Zt.n, pgA.n);
         } else {
             FAIL(SPCSC_ERR_INVALID, "unknown finish mode");
+        }
+        if (nccl_comm) {
+            CK(cudaMemsetAsync(acc.p + 1, 0, (ACC_N - 1) * sizeof(double), stream));
+            int rr = reduce_acc_over_ranks();
+            if (rr) return rr;
         }
         CK(cudaMemcpyAsync(&hv, acc.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1746,6 +1794,7 @@ class Engine : public spcsc_handle {
             CK(launch(k_spec_sumsq<T>, dim3(296), dim3(256), 0, stream, (const C2<T>*)mk_f.p,
                       acc.p + ACC_PGM_F, mk_nc));
         }
+        { int rr = reduce_acc_over_ranks(); if (rr) return rr; }     // images sharded over ranks
         double hacc[ACC_N];
         CK(cudaMemcpyAsync(hacc, acc.p, sizeof(hacc), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));

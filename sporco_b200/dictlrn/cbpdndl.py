@@ -214,10 +214,10 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
 
     def attach_process_group(self, dist, group=None):
         """Shard the training images over the ranks of a ``torch.distributed`` group: every rank
-        codes its own images; the dictionary gradient and the data-fidelity value are summed
-        over ranks on the device (NCCL), so all ranks hold the same dictionary."""
-        if self.xmethod != 'admm':
-            raise NotImplementedError('sharding over GPUs is implemented for the ADMM X step')
+        codes its own images (ADMM or PGM X step); of the dictionary gradient only the filter supports of
+        the gradient step are summed over ranks (crop before reduce: h w Cd M values), together with the
+        data-fidelity value, on the device over peer memory (NCCL where peers cannot be mapped), so all
+        ranks hold the same dictionary."""
         self.xstep.attach_process_group(dist, group)
         self._dist = (dist, group)
 

@@ -99,6 +99,13 @@ class ConvBPDN(pgm.PGMDFT):
         self._cache.pop(_lib.ARR_DF, None)
         self._h.set_dict(self.D[:, :, :, 0, :])
 
+    def attach_process_group(self, dist, group=None):
+        """Shard the images over the ranks of a ``torch.distributed`` group: every rank keeps the images it
+        was built with; the sums behind F, Q, the residual and the objective of every proximal step are
+        reduced over the ranks on the device, so all ranks take the same backtracking / stopping decisions."""
+        from .. import _dist
+        self._world, self._p2p = _dist.attach(self._h, self._device, float(self.cri.K), dist, group)
+
     def getcoef(self):
         return self.X
 

@@ -54,6 +54,27 @@ def main():
     print('rank %d: dictlearn D err %.3e obj err %.3e rsdl err %.3e' % (rank, d_err, dobj_err, drs_err),
           flush=True)
     ok = ok and d_err < 1e-4 and dobj_err < 1e-4 and drs_err < 1e-3
+    # PGM / FISTA with backtracking, images sharded: the sums behind F <= Q, the residual and the objective are
+    # reduced over the ranks, so every rank takes the same backtracking decisions as the single-object solver
+    from sporco_b200.pgm import cbpdn as pcbpdn
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    po = {'MaxMainIter': 15, 'RelStopTol': 0.0, 'L': 5.0}
+    pb = pcbpdn.ConvBPDN(D, S[:, :, mine], 0.1,
+                         pcbpdn.ConvBPDN.Options(dict(po, Backtrack=BacktrackStandard(gamma_u=1.3, maxiter=10))),
+                         dimK=1, device=local)
+    pb.attach_process_group(dist)
+    Xp = pb.solve()
+    rp = orc.pgm_convbpdn(D, S, 0.1, opt=dict(po, Backtrack={'gamma_u': 1.3, 'maxiter': 10}), dimK=1)
+    pits = pb.getitstat()
+    x_err = np.linalg.norm((Xp - rp.X[:, :, :, mine, :]).ravel()) / np.linalg.norm(rp.X[:, :, :, mine, :].ravel())
+    bt_same = np.array_equal(np.asarray(pits.IterBTrack, dtype=float), np.array([row[7] for row in rp.itstat], dtype=float))
+    l_err = np.abs(np.array(pits.L, dtype=np.float64) - np.array([row[8] for row in rp.itstat])).max()
+    pobj_err = np.abs(np.array(pits.ObjFun) - np.array([row[1] for row in rp.itstat])).max() / \
+        np.abs(np.array([row[1] for row in rp.itstat])).max()
+    print('rank %d: pgm X err %.3e backtracking counts equal %s L err %.3e obj err %.3e'
+          % (rank, x_err, bt_same, l_err, pobj_err), flush=True)
+    ok = ok and x_err < 1e-4 and bt_same and l_err < 1e-4 and pobj_err < 1e-4
+    print('rank %d: schedule %s, peer-memory exchange %s' % (rank, b._h.admm_schedule_info(), b._p2p), flush=True)
     t = torch.tensor([1.0 if ok else 0.0], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     print('rank %d: Y err %.3e rho err %.3e obj err %.3e' % (rank, err, rho_err, obj_err), flush=True)
