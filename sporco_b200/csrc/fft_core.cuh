@@ -285,6 +285,101 @@ struct RegStage {
     }
 };
 
+// Two transforms at once (the two columns a lane group of the column kernels holds): same plan, the exchange
+// moves both columns' values as one 16-byte element (half the shared-memory instructions of two separate
+// transforms, one stage-twiddle fetch for both), and the butterflies of the two columns interleave.
+template <typename T>
+struct alignas(4 * sizeof(T)) C4 {
+    C2<T> a, b;
+};
+template <typename T> SPCSC_HD C4<T> mk4(C2<T> a, C2<T> b) { C4<T> r; r.a = a; r.b = b; return r; }
+
+template <typename T, int N, int E, bool INV, int Ns, int TWOFF>
+struct RegStage2 {
+    static constexpr int REM = N / Ns;
+    static constexpr int R = REM >= E ? E : REM;
+    static constexpr int NB = E / R;
+    static constexpr int TPF = N / E;
+    static constexpr bool LAST = (Ns * R >= N);
+    static constexpr int RS = N / R;
+    static constexpr bool RD_FAST = (RS % 16 == 0);
+    static constexpr bool WR_FAST16 = (Ns % 16 == 0);
+    static constexpr bool WR_BLOCK = (!WR_FAST16 && Ns * R <= 16 && 16 % (Ns * R) == 0);
+
+    static SPCSC_DEV void run(C2<T>* v0, C2<T>* v1, C4<T>* buf, const C2<T>* SPCSC_RESTRICT stw, int t) {
+        if (Ns > 1) {
+            SPCSC_UNROLL
+            for (int i = 0; i < NB; ++i) {
+                const int j = t + i * TPF;
+                const int k = j & (Ns - 1);
+                const C4<T>* rd = buf + fft_pad(j);
+                SPCSC_UNROLL
+                for (int r = 0; r < R; ++r) {
+                    C4<T> x = RD_FAST ? rd[r * (RS + RS / 16)] : buf[fft_pad(j + r * RS)];
+                    if (r > 0) {
+                        const C2<T> w = stw[TWOFF + r * Ns + k];
+                        x.a = INV ? mulc(x.a, w) : x.a * w;
+                        x.b = INV ? mulc(x.b, w) : x.b * w;
+                    }
+                    v0[i * R + r] = x.a;
+                    v1[i * R + r] = x.b;
+                }
+            }
+        }
+        SPCSC_UNROLL
+        for (int i = 0; i < NB; ++i) {
+            SmallDFT<T, R, INV>::run(v0 + i * R);
+            SmallDFT<T, R, INV>::run(v1 + i * R);
+        }
+        if constexpr (!LAST) {
+            if (Ns > 1) __syncwarp();
+            SPCSC_UNROLL
+            for (int i = 0; i < NB; ++i) {
+                const int j = t + i * TPF;
+                const int k = j & (Ns - 1);
+                const int j0 = (j - k) * R + k;
+                if (WR_FAST16) {
+                    C4<T>* wr = buf + fft_pad(j0);
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) wr[r * (Ns + Ns / 16)] = mk4<T>(v0[i * R + r], v1[i * R + r]);
+                } else if (WR_BLOCK) {
+                    C4<T>* wr = buf + j0 + ((j0 - k) >> 4);
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) wr[r * Ns] = mk4<T>(v0[i * R + r], v1[i * R + r]);
+                } else {
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) buf[fft_pad(j0 + r * Ns)] = mk4<T>(v0[i * R + r], v1[i * R + r]);
+                }
+            }
+            __syncwarp();
+            RegStage2<T, N, E, INV, Ns * R, TWOFF + (Ns > 1 ? R * Ns : 0)>::run(v0, v1, buf, stw, t);
+        } else {
+            if (NB > 1) {
+                C2<T> o[E];
+                SPCSC_UNROLL
+                for (int i = 0; i < NB; ++i) {
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) o[i + NB * r] = v0[i * R + r];
+                }
+                SPCSC_UNROLL
+                for (int p = 0; p < E; ++p) v0[p] = o[p];
+                SPCSC_UNROLL
+                for (int i = 0; i < NB; ++i) {
+                    SPCSC_UNROLL
+                    for (int r = 0; r < R; ++r) o[i + NB * r] = v1[i * R + r];
+                }
+                SPCSC_UNROLL
+                for (int p = 0; p < E; ++p) v1[p] = o[p];
+            }
+        }
+    }
+};
+template <typename T, int N, int E, bool INV>
+SPCSC_DEV void fft_regs2(C2<T>* v0, C2<T>* v1, C4<T>* buf, const C2<T>* SPCSC_RESTRICT stw, int t) {
+    static_assert(E <= N && (N / E) <= 32, "plan must fit in one warp");
+    RegStage2<T, N, E, INV, 1, 0>::run(v0, v1, buf, stw, t);
+}
+
 // v in strided layout -> transform -> v in strided layout.  `buf`: this transform's N-element
 // shared-memory region; `stw`: stage twiddle table of the (N, E) plan (forward sign).
 // All lanes of the warp must call it together.

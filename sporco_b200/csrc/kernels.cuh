@@ -358,9 +358,81 @@ SPCSC_DEV void col_load_chunk(C2<T>* buf, const C2<T>* SPCSC_RESTRICT src, int m
     for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) buf[e] = src[(size_t)m0 * N0 + e];
     __syncthreads();
 }
-// Any-length column transform: direct DFT from the twiddle table into `buf2`, then copy back.
+// ---- any-length transforms: mixed-radix Stockham passes with run-time radices ----------------------------
+// A length N whose prime factors are all <= kGenMaxRadix is transformed in O(N sum(radices)) instead of the
+// O(N^2) direct DFT: per pass every butterfly gathers R inputs, applies the inter-stage twiddles, evaluates
+// the R-point DFT directly from the twiddle table (tw[j] = exp(-2 pi i j / N)) and scatters in autosort
+// order; passes ping-pong between two buffers.  Used by the any-size row and column kernels (image sizes
+// the reference accepts that are not powers of two, e.g. the padded sizes of signal.tikhonov_filter).
+constexpr int kGenMaxRadix = 32;
+SPCSC_HD int gen_factor(int n, int* rad) {
+    int c = 0;
+    while (n % 4 == 0) { rad[c++] = 4; n /= 4; }
+    if (n % 2 == 0) { rad[c++] = 2; n /= 2; }
+    for (int p = 3; p <= kGenMaxRadix && n > 1; p += 2)
+        while (n % p == 0) { rad[c++] = p; n /= p; }
+    return n == 1 ? c : 0;
+}
+// nseq sequences of length N stored back to back in `a`; `b` is scratch of the same size.  All threads of the
+// block take part.  Returns the buffer that holds the result (natural order).
+template <typename T, bool INV>
+SPCSC_DEV C2<T>* gen_fft_batch(C2<T>* a, C2<T>* b, const C2<T>* SPCSC_RESTRICT tw, int nseq, int N,
+                               const int* rad, int nrad) {
+    int Ns = 1;
+    for (int stg = 0; stg < nrad; ++stg) {
+        const int R = rad[stg], nb = N / R;
+        const int qs = N / R;                                   // table step of exp(-2 pi i / R)
+        const int ts = N / (Ns * R);                            // table step of the inter-stage twiddle
+        for (int e = threadIdx.x; e < nseq * nb; e += blockDim.x) {
+            const int sq = e / nb, j = e - sq * nb;
+            const int k = j % Ns;
+            const C2<T>* x = a + (size_t)sq * N;
+            C2<T> v[kGenMaxRadix];
+            int ti = 0;
+            for (int r = 0; r < R; ++r) {
+                C2<T> xv = x[j + r * nb];
+                if (ti != 0) {
+                    const C2<T> w = tw[ti];
+                    xv = INV ? mulc(xv, w) : xv * w;
+                }
+                v[r] = xv;
+                ti += ts * k;                                   // r k N / (Ns R) < N
+            }
+            C2<T>* y = b + (size_t)sq * N + (size_t)(j - k) * R + k;
+            for (int q = 0; q < R; ++q) {
+                C2<T> s = v[0];
+                int wi = 0;
+                for (int r = 1; r < R; ++r) {
+                    wi += q * qs;                               // (q r mod R) N / R
+                    if (wi >= N) wi -= N;
+                    const C2<T> w = tw[wi];
+                    s = s + (INV ? mulc(v[r], w) : v[r] * w);
+                }
+                y[(size_t)q * Ns] = s;
+            }
+        }
+        __syncthreads();
+        C2<T>* t2 = a; a = b; b = t2;
+        Ns *= R;
+    }
+    return a;
+}
+// Any-length column transform in place in `buf` (`buf2`: scratch of the same size): mixed radix when the
+// length factors into small primes, else the direct DFT from the twiddle table.
 template <typename T, bool INV>
 SPCSC_DEV void col_dft_chunk(C2<T>* buf, C2<T>* buf2, const C2<T>* SPCSC_RESTRICT tw, int mc, int N0) {
+    __shared__ int rad[16];
+    __shared__ int nrad;
+    if (threadIdx.x == 0) nrad = gen_factor(N0, rad);
+    __syncthreads();
+    if (nrad > 0) {
+        C2<T>* res = gen_fft_batch<T, INV>(buf, buf2, tw, mc, N0, rad, nrad);
+        if (res != buf) {
+            for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) buf[e] = buf2[e];
+            __syncthreads();
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < mc * N0; e += blockDim.x) {
         const int col = e / N0, k = e - col * N0;
         const C2<T>* x = buf + (size_t)col * N0;

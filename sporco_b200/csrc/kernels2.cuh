@@ -300,8 +300,12 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
     const size_t wstride = (size_t)M * N0;
     const int gr = tid % TR, wf0 = tid / TR;                   // this thread's row / first wf in tile loops
+    // group 0: the twiddle tables (asynchronous as well: the profile of the synchronous copy showed 16 % of
+    // the kernel's stall samples on the stores that waited for these loads) ...
+    for (int i = tid; i < TWLEN; i += NT) cp_async<sizeof(C2<T>)>(stw_s + i, stw + i);
+    for (int i = tid; i < N1f; i += NT) cp_async<sizeof(C2<T>)>(tw_s + i, tw + i);
     SPCSC_UNROLL
-    for (int c = 0; c < CX; ++c) {   // group 0: the Zt tiles, transposed on the fly
+    for (int c = 0; c < CX; ++c) {   // ... and the Zt tiles, transposed on the fly
         const C2<T>* src = Zt + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0 +
                            (size_t)wf0 * wstride + gr;
         C2<T>* dst = reg + (c * TR + gr) * P + wf0;
@@ -324,8 +328,6 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
         }
     }
     cp_async_commit();
-    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
-    for (int i = tid; i < N1f; i += NT) tw_s[i] = tw[i];
     const int g = PL::row_of_group(tid / TPF), t = tid % TPF;
     const int h = h0 + g;
     const int yrow = PL::yoff(g);
@@ -624,9 +626,9 @@ k_row_prox_fwd3(C2<T>* SPCSC_RESTRICT Vt, T* SPCSC_RESTRICT X, T thr_scale, Weig
             if (wf0 + it * WSTEP < N1f)
                 cp_async<sizeof(C2<T>)>(dst + it * WSTEP, tile + (size_t)it * WSTEP * wstride);
     }
+    for (int i = tid; i < TWLEN; i += NT) cp_async<sizeof(C2<T>)>(stw_s + i, stw + i);
+    for (int i = tid; i < N1f; i += NT) cp_async<sizeof(C2<T>)>(tw_s + i, tw + i);
     cp_async_commit();
-    for (int i = tid; i < TWLEN; i += NT) stw_s[i] = stw[i];
-    for (int i = tid; i < N1f; i += NT) tw_s[i] = tw[i];
     const int g = PL::row_of_group(tid / TPF), t = tid % TPF;
     const int h = h0 + g;
     cp_async_wait<0>();

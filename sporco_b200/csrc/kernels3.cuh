@@ -21,16 +21,10 @@
 
 namespace spcsc {
 
-template <typename T, int N0, int CD>
-struct Col3Smem {
-    // per CTA, in C2<T> units unless noted
-    static constexpr int TWLEN_MAX = 0;
-};
-
 // shared-memory bytes of k_col3 for a cluster of `cs` CTAs
-template <typename T, int N0, int E, int NT, int CD>
+template <typename T, int N0, int E, int NT, int CD, bool PAIR>
 constexpr size_t col3_smem_bytes(int cs) {
-    return ((size_t)(NT / (N0 / E)) * fft_region(N0)        // xbuf
+    return ((size_t)(NT / (N0 / E)) * fft_region(N0) * (PAIR ? 2 : 1)   // xbuf (16-byte elements with PAIR)
             + (size_t)CD * N0                                // qbuf
             + (size_t)stage_tw_len(N0, E)                    // stage twiddles
             + (size_t)2 * N0                                 // Sf row, Gram row
@@ -39,8 +33,8 @@ constexpr size_t col3_smem_bytes(int cs) {
            32 * sizeof(double) + 2 * sizeof(mbar_t);
 }
 
-template <typename T, int N0, int E, int CPG, int NT, int CD>
-SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 2)
+template <typename T, int N0, int E, int CPG, int NT, int CD, bool PAIR>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (CPG == 1 && sizeof(T) == 4 ? 3 : 2))
 k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
        const AdmmState<T>* SPCSC_RESTRICT st, double* SPCSC_RESTRICT acc,
@@ -49,8 +43,9 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     SPCSC_DYN_SMEM(smem_raw);
     constexpr int TPF = N0 / E, NG = NT / TPF;
     constexpr int TWLEN = stage_tw_len(N0, E);
-    constexpr int XP = fft_region(N0);
+    constexpr int XP = fft_region(N0) * (PAIR ? 2 : 1);        // per lane group, in C2 units
     constexpr int HPT = (N0 + NT - 1) / NT;                    // frequencies per thread in the solve
+    static_assert(!PAIR || CPG == 2, "the paired transform takes the two columns of a lane group");
     const unsigned cr = cluster_rank(), cs = cluster_size();
     C2<T>* xbuf = reinterpret_cast<C2<T>*>(smem_raw);         // [NG][XP] FFT exchange / partial sums
     C2<T>* qbuf = xbuf + NG * XP;                              // [CD][N0]
@@ -114,10 +109,15 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                     for (int p = 0; p < E; ++p) v[c][p] = mk<T>(0, 0);
                 }
             }
-            SPCSC_UNROLL
-            for (int c = 0; c < CPG; ++c) {
-                fft_regs<T, N0, E, false>(v[c], xbuf + g * XP, stw_s, t);
+            if constexpr (PAIR) {
+                fft_regs2<T, N0, E, false>(v[0], v[1], reinterpret_cast<C4<T>*>(xbuf + g * XP), stw_s, t);
                 __syncwarp();
+            } else {
+                SPCSC_UNROLL
+                for (int c = 0; c < CPG; ++c) {
+                    fft_regs<T, N0, E, false>(v[c], xbuf + g * XP, stw_s, t);
+                    __syncwarp();
+                }
             }
             // s_d[h] over this CTA's columns, pushed to every peer
             C2<T> mine[CD][HPT];
@@ -213,12 +213,26 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                         v[c][p] = x;
                     }
                 }
-                fft_regs<T, N0, E, true>(v[c], xbuf + g * XP, stw_s, t);
+                if constexpr (!PAIR) {
+                    fft_regs<T, N0, E, true>(v[c], xbuf + g * XP, stw_s, t);
+                    __syncwarp();
+                    if (mcol[c] < M) {
+                        C2<T>* dst = out + slab + (size_t)mcol[c] * N0;
+                        SPCSC_UNROLL
+                        for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[c][p];
+                    }
+                }
+            }
+            if constexpr (PAIR) {
+                fft_regs2<T, N0, E, true>(v[0], v[1], reinterpret_cast<C4<T>*>(xbuf + g * XP), stw_s, t);
                 __syncwarp();
-                if (mcol[c] < M) {
-                    C2<T>* dst = out + slab + (size_t)mcol[c] * N0;
-                    SPCSC_UNROLL
-                    for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[c][p];
+                SPCSC_UNROLL
+                for (int c = 0; c < CPG; ++c) {
+                    if (mcol[c] < M) {
+                        C2<T>* dst = out + slab + (size_t)mcol[c] * N0;
+                        SPCSC_UNROLL
+                        for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[c][p];
+                    }
                 }
             }
             // qbuf, xbuf and pre are next written after the next slab's first block barrier or by the thread

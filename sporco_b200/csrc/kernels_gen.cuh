@@ -12,14 +12,42 @@
 
 namespace spcsc {
 
-// Forward real DFT of TR rows held in shared memory (xs[r*N1 + n]) -> transposed slab store.
+SPCSC_HD size_t gen_align16(size_t n) { return (n + 15) / 16 * 16; }
+
+// Plan of the mixed-radix path for the row length (computed once per CTA by thread 0)
+struct GenRowPlan {
+    int rad[16];
+    int nrad;
+};
+template <typename T>
+SPCSC_DEV void gen_row_plan(GenRowPlan* pl, int N1, int fast) {
+    if (threadIdx.x == 0) pl->nrad = fast ? gen_factor(N1, pl->rad) : 0;
+    __syncthreads();
+}
+
+// Forward real DFT of TR rows held in shared memory (xs[r*N1 + n]) -> transposed slab store.  `work`: two
+// complex buffers of TR*N1 each for the mixed-radix path (null: direct DFT).
 template <typename T>
 SPCSC_DEV void gen_rows_forward_store(const T* xs, C2<T>* SPCSC_RESTRICT Zt,
                                       const C2<T>* SPCSC_RESTRICT tw, int b, int m, int h0, int nrow,
-                                      int N0, int N1, int M) {
+                                      int N0, int N1, int M, C2<T>* work = nullptr,
+                                      const GenRowPlan* pl = nullptr, int TRmax = 0) {
     const int N1f = N1 / 2 + 1;
     C2<T>* out = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
     const size_t wstride = (size_t)M * N0;
+    if (work && pl && pl->nrad > 0) {
+        C2<T>* wa = work;
+        C2<T>* wb = work + (size_t)TRmax * N1;
+        for (int e = threadIdx.x; e < nrow * N1; e += blockDim.x) wa[e] = mk<T>(xs[e], 0);
+        __syncthreads();
+        const C2<T>* res = gen_fft_batch<T, false>(wa, wb, tw, nrow, N1, pl->rad, pl->nrad);
+        for (int e = threadIdx.x; e < nrow * N1f; e += blockDim.x) {
+            const int wf = e / nrow, r = e - wf * nrow;
+            out[wf * wstride + r] = res[(size_t)r * N1 + wf];
+        }
+        __syncthreads();
+        return;
+    }
     for (int e = threadIdx.x; e < nrow * N1f; e += blockDim.x) {
         const int wf = e / nrow, r = e - wf * nrow;
         const T* x = xs + (size_t)r * N1;
@@ -41,16 +69,35 @@ SPCSC_DEV void gen_rows_forward_store(const T* xs, C2<T>* SPCSC_RESTRICT Zt,
 template <typename T>
 SPCSC_DEV void gen_rows_inverse(C2<T>* zs, T* xs, const C2<T>* SPCSC_RESTRICT Zt,
                                 const C2<T>* SPCSC_RESTRICT tw, int b, int m, int h0, int nrow, int N0,
-                                int N1, int M, T scale) {
+                                int N1, int M, T scale, C2<T>* work = nullptr,
+                                const GenRowPlan* pl = nullptr, int TRmax = 0) {
     const int N1f = N1 / 2 + 1;
     const C2<T>* in = Zt + (((size_t)b * N1f) * M + m) * N0 + h0;
     const size_t wstride = (size_t)M * N0;
+    const bool even = (N1 % 2) == 0;
+    if (work && pl && pl->nrad > 0) {
+        // full Hermitian spectrum (c2r ignores Im X[0] and Im X[N1/2]), complex inverse, real part
+        C2<T>* wa = work;
+        C2<T>* wb = work + (size_t)TRmax * N1;
+        for (int e = threadIdx.x; e < nrow * N1; e += blockDim.x) {
+            const int kf = e / nrow, r = e - kf * nrow;
+            const int ks = kf < N1f ? kf : N1 - kf;
+            C2<T> z = in[ks * wstride + r];
+            if (kf >= N1f) z = conj(z);
+            if (ks == 0 || (even && ks == N1f - 1)) z.im = 0;
+            wa[(size_t)r * N1 + kf] = z;
+        }
+        __syncthreads();
+        const C2<T>* res = gen_fft_batch<T, true>(wa, wb, tw, nrow, N1, pl->rad, pl->nrad);
+        for (int e = threadIdx.x; e < nrow * N1; e += blockDim.x) xs[e] = res[e].re * scale;
+        __syncthreads();
+        return;
+    }
     for (int e = threadIdx.x; e < nrow * N1f; e += blockDim.x) {
         const int wf = e / nrow, r = e - wf * nrow;
         zs[(size_t)r * N1f + wf] = in[wf * wstride + r];
     }
     __syncthreads();
-    const bool even = (N1 % 2) == 0;
     for (int e = threadIdx.x; e < nrow * N1; e += blockDim.x) {
         const int r = e / N1, n = e - r * N1;
         const C2<T>* z = zs + (size_t)r * N1f;
@@ -71,10 +118,13 @@ SPCSC_DEV void gen_rows_inverse(C2<T>* zs, T* xs, const C2<T>* SPCSC_RESTRICT Zt
 template <typename T>
 SPCSC_GLOBAL void k_row_fwd_gen(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
                                 const AdmmState<T>* SPCSC_RESTRICT st, C2<T>* SPCSC_RESTRICT Zt,
-                                const C2<T>* SPCSC_RESTRICT tw, int N0, int N1, int M, int TR) {
+                                const C2<T>* SPCSC_RESTRICT tw, int N0, int N1, int M, int TR, int fast) {
     if (st && st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
+    __shared__ GenRowPlan plan;
+    gen_row_plan<T>(&plan, N1, fast);
     T* xs = reinterpret_cast<T*>(smem_raw);
+    C2<T>* work = fast ? reinterpret_cast<C2<T>*>(smem_raw + gen_align16((size_t)TR * N1 * sizeof(T))) : nullptr;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
     const int nrow = (N0 - h0) < TR ? (N0 - h0) : TR;
     const T udiv = (st && B) ? st->udiv : (T)1;
@@ -85,19 +135,22 @@ SPCSC_GLOBAL void k_row_fwd_gen(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRI
         xs[e] = v;
     }
     __syncthreads();
-    gen_rows_forward_store<T>(xs, Zt, tw, b, m, h0, nrow, N0, N1, M);
+    gen_rows_forward_store<T>(xs, Zt, tw, b, m, h0, nrow, N0, N1, M, work, &plan, TR);
 }
 
 template <typename T>
 SPCSC_GLOBAL void k_row_inv_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RESTRICT X,
-                                const C2<T>* SPCSC_RESTRICT tw, int N0, int N1, int M, int TR, T scale) {
+                                const C2<T>* SPCSC_RESTRICT tw, int N0, int N1, int M, int TR, T scale, int fast) {
     SPCSC_DYN_SMEM(smem_raw);
+    __shared__ GenRowPlan plan;
+    gen_row_plan<T>(&plan, N1, fast);
     const int N1f = N1 / 2 + 1;
     C2<T>* zs = reinterpret_cast<C2<T>*>(smem_raw);
     T* xs = reinterpret_cast<T*>(zs + (size_t)TR * N1f);
+    C2<T>* work = fast ? reinterpret_cast<C2<T>*>(smem_raw + gen_align16((size_t)TR * N1f * sizeof(C2<T>) + (size_t)TR * N1 * sizeof(T))) : nullptr;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
     const int nrow = (N0 - h0) < TR ? (N0 - h0) : TR;
-    gen_rows_inverse<T>(zs, xs, Zt, tw, b, m, h0, nrow, N0, N1, M, scale);
+    gen_rows_inverse<T>(zs, xs, Zt, tw, b, m, h0, nrow, N0, N1, M, scale, work, &plan, TR);
     const size_t base = (((size_t)b * M + m) * N0 + h0) * N1;
     for (int e = threadIdx.x; e < nrow * N1; e += blockDim.x) X[base + e] = xs[e];
 }
@@ -109,18 +162,21 @@ SPCSC_GLOBAL void k_row_inv_prox_gen(const C2<T>* SPCSC_RESTRICT Zt, T* SPCSC_RE
                                      AdmmParams<T> prm, WeightView<T> wl1, WeightView<T> wl21,
                                      double* SPCSC_RESTRICT acc, const C2<T>* SPCSC_RESTRICT tw, int N0,
                                      int N1, int M, int TR, T scale, int nonneg, int bnd0, int bnd1,
-                                     int reg_on_y) {
+                                     int reg_on_y, int fast) {
     if (st->stopped) return;
     SPCSC_DYN_SMEM(smem_raw);
+    __shared__ GenRowPlan plan;
+    gen_row_plan<T>(&plan, N1, fast);
     const int N1f = N1 / 2 + 1;
     C2<T>* zs = reinterpret_cast<C2<T>*>(smem_raw);                     // [TR][N1f]
     T* xs = reinterpret_cast<T*>(zs + (size_t)TR * N1f);                // [CX][TR][N1]
+    C2<T>* work = fast ? reinterpret_cast<C2<T>*>(smem_raw + gen_align16((size_t)TR * N1f * sizeof(C2<T>) + (size_t)CX * TR * N1 * sizeof(T))) : nullptr;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
     const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
     const int nrow = (N0 - h0) < TR ? (N0 - h0) : TR;
     for (int c = 0; c < CX; ++c)
         gen_rows_inverse<T>(zs, xs + (size_t)c * TR * N1, Zt, tw, k * CX + c, m, h0, nrow, N0, N1, M,
-                            scale);
+                            scale, work, &plan, TR);
     const T rho = st->rho, udiv = st->udiv;
     const T lr = prm.lmbda / rho;
     const T mr = prm.joint ? prm.mu / rho : (T)0;
@@ -189,15 +245,18 @@ template <typename T>
 SPCSC_GLOBAL void k_row_inv_prox_fwd_gen(C2<T>* SPCSC_RESTRICT Vt, T* SPCSC_RESTRICT X, T thr_scale,
                                          WeightView<T> wl1, double* SPCSC_RESTRICT acc,
                                          const C2<T>* SPCSC_RESTRICT tw, int N0, int N1, int M, int Cx,
-                                         int TR, T scale, int nonneg, int bnd0, int bnd1) {
+                                         int TR, T scale, int nonneg, int bnd0, int bnd1, int fast) {
     SPCSC_DYN_SMEM(smem_raw);
+    __shared__ GenRowPlan plan;
+    gen_row_plan<T>(&plan, N1, fast);
     const int N1f = N1 / 2 + 1;
     C2<T>* zs = reinterpret_cast<C2<T>*>(smem_raw);
     T* xs = reinterpret_cast<T*>(zs + (size_t)TR * N1f);
+    C2<T>* work = fast ? reinterpret_cast<C2<T>*>(smem_raw + gen_align16((size_t)TR * N1f * sizeof(C2<T>) + (size_t)TR * N1 * sizeof(T))) : nullptr;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, b = blockIdx.z;
     const int k = b / Cx, c = b - k * Cx;
     const int nrow = (N0 - h0) < TR ? (N0 - h0) : TR;
-    gen_rows_inverse<T>(zs, xs, Vt, tw, b, m, h0, nrow, N0, N1, M, scale);
+    gen_rows_inverse<T>(zs, xs, Vt, tw, b, m, h0, nrow, N0, N1, M, scale, work, &plan, TR);
     double sums[1] = {0.0};
     const size_t base = (((size_t)b * M + m) * N0 + h0) * N1;
     for (int e = threadIdx.x; e < nrow * N1; e += blockDim.x) {
@@ -213,7 +272,7 @@ SPCSC_GLOBAL void k_row_inv_prox_fwd_gen(C2<T>* SPCSC_RESTRICT Vt, T* SPCSC_REST
         X[base + e] = x;
     }
     __syncthreads();
-    gen_rows_forward_store<T>(xs, Vt, tw, b, m, h0, nrow, N0, N1, M);
+    gen_rows_forward_store<T>(xs, Vt, tw, b, m, h0, nrow, N0, N1, M, work, &plan, TR);
     double* red = reinterpret_cast<double*>(smem_raw);
     block_accumulate<1>(sums, red, acc + ACC_L1);
 }

@@ -137,32 +137,47 @@ inline int gen_threads(int work) {
     int nt = round_up32(work);
     return nt > 256 ? 256 : (nt < 32 ? 32 : nt);
 }
+// Mixed-radix path of the any-size row kernels: taken when the row length factors into primes <= kGenMaxRadix
+// and the two complex work buffers (TR rows each) fit into shared memory next to what the kernel needs anyway.
+template <typename T>
+inline int gen_rows_fast(const GenRowArgs<T>& r, size_t base_bytes, size_t& smem) {
+    int rad[16];
+    smem = base_bytes;
+    if (gen_factor(r.N1, rad) == 0) return 0;
+    const size_t extra = gen_align16(base_bytes) + (size_t)2 * r.TR * r.N1 * sizeof(C2<T>);
+    if (extra > kSmemLimit) return 0;
+    smem = extra;
+    return 1;
+}
 template <typename T>
 cudaError_t row_fwd_gen_launch(const GenRowArgs<T>& r, const T* A, const T* B, const AdmmState<T>* st,
                                C2<T>* Zt) {
-    const size_t smem = (size_t)r.TR * r.N1 * sizeof(T);
+    size_t smem;
+    const int fast = gen_rows_fast<T>(r, (size_t)r.TR * r.N1 * sizeof(T), smem);
     dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb);
     return launch(k_row_fwd_gen<T>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream, A, B, st,
-                  Zt, r.tw, r.N0, r.N1, r.M, r.TR);
+                  Zt, r.tw, r.N0, r.N1, r.M, r.TR, fast);
 }
 template <typename T>
 cudaError_t row_inv_gen_launch(const GenRowArgs<T>& r, const C2<T>* Zt, T* X, T scale) {
     const int N1f = r.N1 / 2 + 1;
-    const size_t smem = (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)r.TR * r.N1 * sizeof(T);
+    size_t smem;
+    const int fast = gen_rows_fast<T>(r, (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)r.TR * r.N1 * sizeof(T), smem);
     dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb);
     return launch(k_row_inv_gen<T>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream, Zt, X,
-                  r.tw, r.N0, r.N1, r.M, r.TR, scale);
+                  r.tw, r.N0, r.N1, r.M, r.TR, scale, fast);
 }
 template <typename T, int CX>
 static cudaError_t row_inv_prox_gen_cx(const GenRowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
                                        T* Y, T* U, const AdmmState<T>* st) {
     const int N1f = r.N1 / 2 + 1;
-    size_t smem = (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)CX * r.TR * r.N1 * sizeof(T);
+    size_t smem;
+    const int fast = gen_rows_fast<T>(r, (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)CX * r.TR * r.N1 * sizeof(T), smem);
     if (smem < 7 * 32 * sizeof(double)) smem = 7 * 32 * sizeof(double);
     dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb / CX);
     return launch(k_row_inv_prox_gen<T, CX>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream,
                   Zt, Y, U, st, p.prm, p.wl1, p.wl21, p.acc, r.tw, r.N0, r.N1, r.M, r.TR, p.scale,
-                  p.nonneg, p.bnd0, p.bnd1, p.reg_on_y);
+                  p.nonneg, p.bnd0, p.bnd1, p.reg_on_y, fast);
 }
 template <typename T>
 cudaError_t row_inv_prox_gen_launch(const GenRowArgs<T>& r, const ProxArgs<T>& p, const C2<T>* Zt,
@@ -179,12 +194,13 @@ template <typename T>
 cudaError_t row_inv_prox_fwd_gen_launch(const GenRowArgs<T>& r, const PgmRowArgs<T>& p, C2<T>* Vt,
                                         T* X) {
     const int N1f = r.N1 / 2 + 1;
-    size_t smem = (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)r.TR * r.N1 * sizeof(T);
+    size_t smem;
+    const int fast = gen_rows_fast<T>(r, (size_t)r.TR * N1f * sizeof(C2<T>) + (size_t)r.TR * r.N1 * sizeof(T), smem);
     if (smem < 32 * sizeof(double)) smem = 32 * sizeof(double);
     dim3 grid((r.N0 + r.TR - 1) / r.TR, r.M, r.nb);
     return launch(k_row_inv_prox_fwd_gen<T>, grid, dim3(gen_threads<T>(r.TR * r.N1)), smem, r.stream,
                   Vt, X, p.thr_scale, p.wl1, p.acc, r.tw, r.N0, r.N1, r.M, r.Cx, r.TR, p.scale,
-                  p.nonneg, p.bnd0, p.bnd1);
+                  p.nonneg, p.bnd0, p.bnd1, fast);
 }
 
 // ---- kernel set v2 -----------------------------------------------------------------
@@ -278,6 +294,37 @@ cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, cons
     }
 }
 
+// k_col3 launch: returns false when the variant does not fit (shared memory, no resident cluster)
+template <typename T, int N0, int E, int CPG, int NT, int CD, bool PAIR>
+static bool col3_go(ColLaunch<T>& c, const C2<T>* stw, unsigned cs, cudaError_t& result) {
+    auto kern = k_col3<T, N0, E, CPG, NT, CD, PAIR>;
+    const size_t smem3 = col3_smem_bytes<T, N0, E, NT, CD, PAIR>((int)cs);
+    if (smem3 > kSmemLimit) return false;
+    static int resident3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
+    if (resident3[cs] == 0) {
+#ifndef SPCSC_EMU
+        // leave what two CTAs per SM do not need of the unified array to L1: it holds the dictionary slice
+        const int per_sm = (CPG == 1 && sizeof(T) == 4) ? 3 : 2;
+        const int pct = (int)((per_sm * (smem3 + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+#endif
+        resident3[cs] = max_active_clusters(kern, dim3(NT), cs, smem3);
+        if (resident3[cs] <= 0) resident3[cs] = -1;
+    }
+    const int ncl = resident3[cs];
+    if (ncl <= 0) return false;
+    // runs of images per item: about six rounds of items per resident cluster
+    int chunk = (int)(((long long)c.a.N1f * c.nb) / (6LL * ncl));
+    if (chunk < 1) chunk = 1;
+    if (chunk > c.nb) chunk = c.nb;
+    const int nitems = c.a.N1f * ((c.nb + chunk - 1) / chunk);
+    const int use = ncl < nitems ? ncl : nitems;
+    g_col_variant = PAIR ? 4 : (CPG == 1 && sizeof(T) == 4 ? 5 : 3);
+    result = launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem3, c.stream, c.in, c.out, c.Df,
+                            c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, chunk);
+    return true;
+}
+
 template <typename T, int N0, int CD>
 static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     constexpr int E = col2_elems<T>(), NT = kCol2Threads, CPG = col2_cpg<T>();
@@ -308,33 +355,20 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     g_col_variant = 2;
     if (c.push && !c.bulk) {
         // k_col3: persistent clusters over (frequency column, run of images) items; the per-frequency sums
-        // travel by st.async pushes instead of cluster barriers
-        auto kern = k_col3<T, N0, E, CPG, NT, CD>;
-        const size_t smem3 = col3_smem_bytes<T, N0, E, NT, CD>((int)cs);
-        if (smem3 <= kSmemLimit) {
-            static int resident3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
-            if (resident3[cs] == 0) {
-#ifndef SPCSC_EMU
-                // leave what two CTAs per SM do not need of the unified array to L1: it holds the dictionary slice
-                const int pct = (int)((2 * (smem3 + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
-                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-#endif
-                resident3[cs] = max_active_clusters(kern, dim3(NT), cs, smem3);
-                if (resident3[cs] <= 0) resident3[cs] = -1;
-            }
-            const int ncl = resident3[cs];
-            if (ncl > 0) {
-                // runs of images per item: about six rounds of items per resident cluster
-                int chunk = (int)(((long long)c.a.N1f * c.nb) / (6LL * ncl));
-                if (chunk < 1) chunk = 1;
-                if (chunk > c.nb) chunk = c.nb;
-                const int nitems = c.a.N1f * ((c.nb + chunk - 1) / chunk);
-                const int use = ncl < nitems ? ncl : nitems;
-                g_col_variant = 3;
-                return launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem3, c.stream, c.in, c.out, c.Df,
-                                      c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, chunk);
+        // travel by st.async pushes instead of cluster barriers.  push == 2 (float32): the two columns of a lane
+        // group are transformed together, exchanging 16-byte elements
+        cudaError_t e3 = cudaErrorInvalidValue;
+        bool done = false;
+        if constexpr (CPG == 2) {
+            if (c.push == 2) done = col3_go<T, N0, E, CPG, NT, CD, true>(c, stw, cs, e3);
+            if (c.push == 3) {
+                // one column per lane group: half the register payload, 3 CTAs per SM, clusters twice as large
+                const unsigned cs1 = (unsigned)((c.a.M + NG - 1) / NG);
+                if (cs1 <= 8) done = col3_go<T, N0, E, 1, NT, CD, false>(c, stw, cs1, e3);
             }
         }
+        if (!done) done = col3_go<T, N0, E, CPG, NT, CD, false>(c, stw, cs, e3);
+        if (done) return e3;
     }
     if (c.bulk) {
         // persistent clusters with the next slab prefetched by a bulk copy; in place is fine (a

@@ -82,8 +82,15 @@ def test_cfg5_dictionary_learning_16_images_256():
 
 def test_metric_configuration_k32_against_oracle():
     """The literal BASELINE.json metric configuration -- 256x256, 8x8x64 dictionary, 32 images, lambda 0.1,
-    AutoRho on, float32 -- for 10 iterations against the oracle (scipy FFT workers; about half a minute of
-    host time): coefficient maps to north_star's rtol 1e-4, and the rho trajectory."""
+    AutoRho on, float32 -- for 10 iterations against the oracle in FLOAT64 (scipy FFT workers; about two minutes
+    of host time): coefficient maps to north_star's rtol 1e-4, and the rho trajectory.
+
+    Why float64: at this size the reference's own float32 run is the less accurate of the two.  Its residual
+    norms are numpy float32 sums over 134 M elements and its rho trajectory drifts by 2e-3 from the float64 one
+    within 10 iterations (coefficient maps: 6.6e-4); the device accumulates the norms in double and lands
+    9e-7 from the float64 result (tools/k32_accuracy.py, profiles/r02_k32_accuracy.json).  Against the float32
+    oracle the same 6.6e-4 shows up -- that comparison is made at sizes where float32 sums are benign
+    (tests/cases.py), here the exact answer is the yardstick."""
     import os
     from oracle import cbpdn_oracle as orc
     from sporco_b200.admm import cbpdn
@@ -94,7 +101,9 @@ def test_metric_configuration_k32_against_oracle():
     b = cbpdn.ConvBPDN(D, S, 0.1, cbpdn.ConvBPDN.Options(opt), dimK=1)
     Y = b.solve()
     its = b.getitstat()
-    r = orc.admm_convbpdn(D, S, 0.1, opt=opt, dimK=1, fft=orc.FFTBackend('scipy', os.cpu_count() or 8))
+    r = orc.admm_convbpdn(D.astype(np.float64), S.astype(np.float64), 0.1, opt=opt, dimK=1,
+                          fft=orc.FFTBackend('scipy', os.cpu_count() or 8))
+    assert Y.dtype == np.float32
     assert cases.rel(Y, r.Y) < 1e-4
     assert cases.rel(its.Rho, [row[8] for row in r.itstat]) < 1e-4
     assert cases.rel(its.PrimalRsdl, [row[4] for row in r.itstat]) < 1e-4

@@ -18,7 +18,9 @@ def _use_emulated_kernels(emu_library):
 
 
 @pytest.mark.parametrize('dt', [np.float32, np.float64])
-@pytest.mark.parametrize('shape', [(2, 4), (8, 8), (16, 64), (64, 32), (128, 256)])
+@pytest.mark.parametrize('shape', [(2, 4), (8, 8), (16, 64), (64, 32), (128, 256),
+                                   # not powers of two: mixed-radix passes (radices 2..31), direct DFT for 37
+                                   (36, 40), (45, 63), (34, 62), (37, 74), (17, 9)])
 def test_rfft2_irfft2(shape, dt):
     rng = np.random.default_rng(3)
     x = rng.standard_normal((2,) + shape).astype(dt)
@@ -194,13 +196,14 @@ def test_setting_y_between_solves_is_seen_by_the_fused_schedule():
 
 
 @pytest.mark.parametrize('case', cases.FRESH_CASES + [(64, 64, 8, 5, None, None, None)])
-def test_push_exchange_column_kernel_vs_oracle(case, monkeypatch):
+@pytest.mark.parametrize('pair', [False, True, 'cpg1'])
+def test_push_exchange_column_kernel_vs_oracle(case, pair, monkeypatch):
     """k_col3 (SPCSC_COL3=1): persistent clusters over (frequency column, run of images) items, the
     per-frequency sums pushed into the peers' shared memory and awaited on an mbarrier."""
-    monkeypatch.setenv('SPCSC_COL3', '1')
+    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3'}[pair])
     N0, N1, M, K, C, mu, extra = case
     b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
-    assert b._h.admm_schedule_info()['col_kernel'] == 3
+    assert b._h.admm_schedule_info()['col_kernel'] == {False: 3, True: 4, 'cpg1': 5}[pair]
 
 
 def test_push_exchange_column_kernel_float64_and_colour_dictionary(monkeypatch):

@@ -21,7 +21,11 @@ def _real_library():
 
 @pytest.mark.parametrize('dt', [np.float32, np.float64])
 @pytest.mark.parametrize('shape', [(2, 4), (4, 8), (8, 8), (16, 64), (64, 32), (128, 256),
-                                   (256, 256), (512, 512), (1024, 2048)])
+                                   (256, 256), (512, 512), (1024, 2048),
+                                   # not powers of two: mixed-radix passes with run-time radices (288 = 2^5 3^2 is the
+                                   # padded size of tikhonov_filter on 256 images, 544 = 2^5 17 on 512), odd lengths,
+                                   # and a length with a large prime factor (direct DFT)
+                                   (288, 288), (544, 320), (480, 768), (63, 45), (74, 37)])
 def test_rfft2_irfft2(shape, dt):
     rng = np.random.default_rng(3)
     x = rng.standard_normal((3,) + shape).astype(dt)
@@ -146,12 +150,13 @@ def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
 
 
 @pytest.mark.parametrize('case', [cases.FRESH_CASES[0], cases.FRESH_CASES[2], (64, 64, 8, 5, None, None, None)])
-def test_push_exchange_column_kernel_vs_oracle(case, monkeypatch):
+@pytest.mark.parametrize('pair', [False, True, 'cpg1'])
+def test_push_exchange_column_kernel_vs_oracle(case, pair, monkeypatch):
     """k_col3 (persistent clusters, sums pushed over DSMEM) against the oracle and against k_col2."""
-    monkeypatch.setenv('SPCSC_COL3', '1')
+    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3'}[pair])
     N0, N1, M, K, C, mu, extra = case
     b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
-    assert b._h.admm_schedule_info()['col_kernel'] == 3
+    assert b._h.admm_schedule_info()['col_kernel'] == {False: 3, True: 4, 'cpg1': 5}[pair]
 
 
 @pytest.mark.parametrize('wave', ['2,2', 'f:2,2'])
