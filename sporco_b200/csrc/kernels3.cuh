@@ -22,9 +22,10 @@
 namespace spcsc {
 
 // shared-memory bytes of k_col3 for a cluster of `cs` CTAs
-template <typename T, int N0, int E, int NT, int CD, bool PAIR>
+template <typename T, int N0, int E, int NT, int CD, bool PAIR, int DFCOLS = 0>
 constexpr size_t col3_smem_bytes(int cs) {
     return ((size_t)(NT / (N0 / E)) * fft_region(N0) * (PAIR ? 2 : 1)   // xbuf (16-byte elements with PAIR)
+            + (size_t)DFCOLS * N0                            // staged dictionary columns of this CTA
             + (size_t)CD * N0                                // qbuf
             + (size_t)stage_tw_len(N0, E)                    // stage twiddles
             + (size_t)2 * N0                                 // Sf row, Gram row
@@ -33,12 +34,14 @@ constexpr size_t col3_smem_bytes(int cs) {
            32 * sizeof(double) + 2 * sizeof(mbar_t);
 }
 
-template <typename T, int N0, int E, int CPG, int NT, int CD, bool PAIR>
+// DFS: the CTA's columns of the dictionary slice are copied into shared memory once per work item and read from
+// there in both the sum and the correction phase (single-channel dictionaries).
+template <typename T, int N0, int E, int CPG, int NT, int CD, bool PAIR, bool DFS = false>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (CPG == 1 && sizeof(T) == 4 ? 3 : 2))
 k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
        const AdmmState<T>* SPCSC_RESTRICT st, double* SPCSC_RESTRICT acc,
-       const C2<T>* SPCSC_RESTRICT stw, ColArgs a, int nb, int chunk) {
+       const C2<T>* SPCSC_RESTRICT stw, ColArgs a, int nb, int chunk, int pf) {
     if (st->stopped) return;                                   // same value in every CTA of the cluster
     SPCSC_DYN_SMEM(smem_raw);
     constexpr int TPF = N0 / E, NG = NT / TPF;
@@ -52,7 +55,9 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     C2<T>* stw_s = qbuf + CD * N0;                             // [TWLEN]
     C2<T>* pre = stw_s + TWLEN;                                // [2][N0] Sf row of the slab, Gram row of the item
     C2<T>* recv = pre + 2 * N0;                                // [2][cs][CD][N0] sums pushed by the peers
-    double* red = reinterpret_cast<double*>(recv + (size_t)2 * cs * CD * N0);   // [32]
+    C2<T>* dfs = recv + (size_t)2 * cs * CD * N0;              // DFS: [NG*CPG][N0] this CTA's dictionary columns
+    double* red = reinterpret_cast<double*>(dfs + (DFS ? (size_t)NG * CPG * N0 : 0));   // [32]
+    static_assert(!DFS || CD == 1, "dictionary staging is for single-channel dictionaries");
     mbar_t* bar = reinterpret_cast<mbar_t*>(red + 32);         // [2]
     const int tid = threadIdx.x;
     const int M = a.M;
@@ -82,6 +87,15 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
         const int b1 = (b0 + chunk < nb) ? b0 + chunk : nb;
         const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
         const double wgt_wf = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
+        if constexpr (DFS) {
+            __syncthreads();                                   // everyone is done with the previous item's columns
+            const int col0 = (int)cr * NG * CPG;
+            const int ncol = (M - col0 < NG * CPG) ? (M - col0) : NG * CPG;
+            constexpr int VEC = 16 / (int)sizeof(C2<T>);
+            const C2<T>* srcd = dfw + (size_t)col0 * N0;
+            for (int e = tid * VEC; e < ncol * N0; e += NT * VEC) cp_async<16>(dfs + e, srcd + e);
+            cp_async_commit();
+        }
         for (int b = b0; b < b1; ++b, ++slab_no) {
             const unsigned par = slab_no & 1u, ph = (slab_no >> 1) & 1u;
             const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
@@ -109,6 +123,24 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                     for (int p = 0; p < E; ++p) v[c][p] = mk<T>(0, 0);
                 }
             }
+            if (pf) {
+                // the cluster's next slab: ask L2 for its lines now (lane t takes line t of each column; TPF
+                // lanes x sizeof(C2) = one line), so that the loads at the top of the next pass find them there
+                int bn = b + 1, wfn = wf;
+                bool have = true;
+                if (bn >= b1) {
+                    const int itn = item + ncl;
+                    have = itn < nitems;
+                    wfn = itn / nchunks;
+                    bn = (itn - wfn * nchunks) * chunk;
+                }
+                if (have && t < E) {
+                    const C2<T>* nxt = in + (((size_t)bn * a.N1f + wfn) * M) * N0 + TPF * t;
+                    SPCSC_UNROLL
+                    for (int c = 0; c < CPG; ++c)
+                        if (mcol[c] < M) prefetch_l2(nxt + (size_t)mcol[c] * N0);
+                }
+            }
             if constexpr (PAIR) {
                 fft_regs2<T, N0, E, false>(v[0], v[1], reinterpret_cast<C4<T>*>(xbuf + g * XP), stw_s, t);
                 __syncwarp();
@@ -117,6 +149,12 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 for (int c = 0; c < CPG; ++c) {
                     fft_regs<T, N0, E, false>(v[c], xbuf + g * XP, stw_s, t);
                     __syncwarp();
+                }
+            }
+            if constexpr (DFS) {
+                if (b == b0) {                                 // the item's dictionary columns have landed
+                    cp_async_wait<0>();
+                    __syncthreads();
                 }
             }
             // s_d[h] over this CTA's columns, pushed to every peer
@@ -128,8 +166,13 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                     const int h = t + TPF * p;
                     C2<T> s = mk<T>(0, 0);
                     SPCSC_UNROLL
-                    for (int c = 0; c < CPG; ++c)
-                        if (mcol[c] < M) s = s + ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h) * v[c][p];
+                    for (int c = 0; c < CPG; ++c) {
+                        if (mcol[c] < M) {
+                            const C2<T> dv = DFS ? dfs[(size_t)(g * CPG + c) * N0 + h]
+                                                 : ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h);
+                            s = s + dv * v[c][p];
+                        }
+                    }
                     xbuf[g * XP + h] = s;
                 }
                 __syncthreads();
@@ -208,8 +251,11 @@ k_col3(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                         const int h = t + TPF * p;
                         C2<T> x = v[c][p];
                         SPCSC_UNROLL
-                        for (int d = 0; d < CD; ++d)
-                            x = x + mulc(qbuf[d * N0 + h], ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h));
+                        for (int d = 0; d < CD; ++d) {
+                            const C2<T> dv = DFS ? dfs[(size_t)(g * CPG + c) * N0 + h]
+                                                 : ld_keep(dfw + d * dfc + (size_t)mcol[c] * N0 + h);
+                            x = x + mulc(qbuf[d * N0 + h], dv);
+                        }
                         v[c][p] = x;
                     }
                 }

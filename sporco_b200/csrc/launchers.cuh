@@ -61,6 +61,7 @@ struct ColLaunch {
     int gen;                     // any-size direct-DFT path (a.N0 holds the run-time length)
     int bulk;                    // k_col2: persistent clusters with bulk-copy prefetch of the next slab
     int push;                    // COL_ADMM: k_col3 (persistent clusters, sums pushed over DSMEM) instead of k_col2
+    int prefetch;                // k_col3: L2 prefetch of the cluster's next slab
     cudaStream_t stream;
 };
 

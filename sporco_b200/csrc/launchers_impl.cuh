@@ -295,10 +295,10 @@ cudaError_t row_inv_prox2_launch(const RowArgs<T>& r, const ProxArgs<T>& p, cons
 }
 
 // k_col3 launch: returns false when the variant does not fit (shared memory, no resident cluster)
-template <typename T, int N0, int E, int CPG, int NT, int CD, bool PAIR>
+template <typename T, int N0, int E, int CPG, int NT, int CD, bool PAIR, bool DFS = false>
 static bool col3_go(ColLaunch<T>& c, const C2<T>* stw, unsigned cs, cudaError_t& result) {
-    auto kern = k_col3<T, N0, E, CPG, NT, CD, PAIR>;
-    const size_t smem3 = col3_smem_bytes<T, N0, E, NT, CD, PAIR>((int)cs);
+    auto kern = k_col3<T, N0, E, CPG, NT, CD, PAIR, DFS>;
+    const size_t smem3 = col3_smem_bytes<T, N0, E, NT, CD, PAIR, (DFS ? (NT / (N0 / E)) * CPG : 0)>((int)cs);
     if (smem3 > kSmemLimit) return false;
     static int resident3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
     if (resident3[cs] == 0) {
@@ -319,9 +319,9 @@ static bool col3_go(ColLaunch<T>& c, const C2<T>* stw, unsigned cs, cudaError_t&
     if (chunk > c.nb) chunk = c.nb;
     const int nitems = c.a.N1f * ((c.nb + chunk - 1) / chunk);
     const int use = ncl < nitems ? ncl : nitems;
-    g_col_variant = PAIR ? 4 : (CPG == 1 && sizeof(T) == 4 ? 5 : 3);
+    g_col_variant = (PAIR ? 4 : (CPG == 1 && sizeof(T) == 4 ? 5 : 3)) + (DFS ? 10 : 0);
     result = launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem3, c.stream, c.in, c.out, c.Df,
-                            c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, chunk);
+                            c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, chunk, c.prefetch);
     return true;
 }
 
@@ -359,6 +359,12 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
         // group are transformed together, exchanging 16-byte elements
         cudaError_t e3 = cudaErrorInvalidValue;
         bool done = false;
+        if constexpr (CD == 1) {    // + 10: the CTA's dictionary columns staged in shared memory
+            if (c.push == 11) done = col3_go<T, N0, E, CPG, NT, CD, false, true>(c, stw, cs, e3);
+            if constexpr (CPG == 2) {
+                if (c.push == 12) done = col3_go<T, N0, E, CPG, NT, CD, true, true>(c, stw, cs, e3);
+            }
+        }
         if constexpr (CPG == 2) {
             if (c.push == 2) done = col3_go<T, N0, E, CPG, NT, CD, true>(c, stw, cs, e3);
             if (c.push == 3) {

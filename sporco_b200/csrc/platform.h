@@ -352,6 +352,13 @@ SPCSC_DEV C2<double> ld_stream(const C2<double>* p) {
 }
 #endif
 
+// Bring a line into L2 ahead of its use (the next slab of a persistent CTA).
+#ifdef SPCSC_EMU
+inline void prefetch_l2(const void*) {}
+#else
+SPCSC_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // Re-used read-only operand (dictionary spectra, read twice per slab by the same thread): ask L1 to
 // keep the line (evict-last), the counterpart of ld_stream.
 #ifdef SPCSC_EMU

@@ -558,6 +558,7 @@ class Engine : public spcsc_handle {
         // (the kernel is issue-bound, not load-bound), so it stays opt-in
         c.bulk = (getenv("SPCSC_COLBULK") && atoi(getenv("SPCSC_COLBULK")) == 1) ? 1 : 0;
         c.push = getenv("SPCSC_COL3") ? atoi(getenv("SPCSC_COL3")) : 0;     // 1: k_col3, 2: with paired transforms
+        c.prefetch = getenv("SPCSC_COL3_PF") ? atoi(getenv("SPCSC_COL3_PF")) : 0;
         return c;
     }
 
