@@ -594,6 +594,102 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
 }
 
 // ------------------------------------------------------------------------------------
+// k_row_fwd3: Zt = row spectra of A - B / udiv, as k_row_fwd2, with the tile flow of k_row_inv_prox3: the
+// contiguous A and B tiles (TR rows x N1 reals) arrive by 16-byte asynchronous copies in the conflict-free
+// row layout of Prox3Plan, and -- the CTAs walk over tiles with a grid stride -- the copies of the NEXT tile are
+// issued as soon as every thread holds its values of the current one, so they overlap the transform and the
+// transposed stores.  This is the kernel that redoes the row spectra when rho changed (`gated`), i.e. in
+// every other iteration of the first ~25 of an AutoRho run.
+// ------------------------------------------------------------------------------------
+template <typename T, int H, int E, int NT>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, (NT <= 128 ? 4 : 2))
+k_row_fwd3(const T* SPCSC_RESTRICT A, const T* SPCSC_RESTRICT B,
+           const AdmmState<T>* SPCSC_RESTRICT st, C2<T>* SPCSC_RESTRICT Zt,
+           const C2<T>* SPCSC_RESTRICT tw, const C2<T>* SPCSC_RESTRICT stw, int N0, int M,
+           int nb, int gated) {
+    if (st && st->stopped) return;
+    if (gated && st && !st->zt_stale) return;
+    SPCSC_DYN_SMEM(smem_raw);
+    using PL = Prox3Plan<T, H, E, 1, NT>;
+    constexpr int TPF = PL::TPF, TR = PL::TR, P = PL::P, N1f = PL::N1f, YS = PL::YS, TWLEN = PL::TWLEN;
+    constexpr int VEC = 16 / sizeof(C2<T>);
+    constexpr int WSTEP = NT / TR, WIT = (N1f + WSTEP - 1) / WSTEP;
+    C2<T>* abuf = reinterpret_cast<C2<T>*>(smem_raw);          // [YS]
+    C2<T>* bbuf = abuf + YS;                                   // [YS]
+    C2<T>* reg = bbuf + YS;                                    // [TR][P]
+    C2<T>* stw_s = reg + TR * P;                               // [TWLEN]
+    C2<T>* tw_s = stw_s + TWLEN;                               // [N1f]
+    const int tid = threadIdx.x;
+    T uinv = 1;
+    if (st && B) {
+        const T ud = st->udiv;
+        if (ud != (T)1) uinv = (T)1 / ud;
+    }
+    const int tiles_h = N0 / TR;
+    const long long ntiles = (long long)tiles_h * M * nb;
+    const int g = PL::row_of_group(tid / TPF), t = tid % TPF;
+    const int yrow = PL::yoff(g);
+    const int gr = tid % TR, wf0 = tid / TR;
+    const size_t wstride = (size_t)M * N0;
+    auto issue = [&](long long tile) {
+        const int h0 = (int)(tile % tiles_h) * TR;
+        const int m = (int)((tile / tiles_h) % M), b = (int)(tile / ((long long)tiles_h * M));
+        const size_t base = ((((size_t)b * M + m) * N0 + h0) * H);
+        const C2<T>* a2 = reinterpret_cast<const C2<T>*>(A) + base;
+        const C2<T>* b2 = B ? reinterpret_cast<const C2<T>*>(B) + base : nullptr;
+        SPCSC_UNROLL
+        for (int e = tid * VEC; e < TR * H; e += NT * VEC) {
+            const int d = e + (PL::REMAP ? 8 * (e / (8 * H)) : 0);
+            cp_async<16>(abuf + d, a2 + e);
+            if (b2) cp_async<16>(bbuf + d, b2 + e);
+        }
+    };
+    for (int i = tid; i < TWLEN; i += NT) cp_async<sizeof(C2<T>)>(stw_s + i, stw + i);
+    for (int i = tid; i < N1f; i += NT) cp_async<sizeof(C2<T>)>(tw_s + i, tw + i);
+    if ((long long)blockIdx.x < ntiles) issue(blockIdx.x);
+    cp_async_commit();
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int h0 = (int)(tile % tiles_h) * TR;
+        const int m = (int)((tile / tiles_h) % M), b = (int)(tile / ((long long)tiles_h * M));
+        cp_async_wait<0>();
+        __syncthreads();
+        C2<T> v[E];
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) {
+            const int j = t + TPF * p;
+            C2<T> a = abuf[yrow + j];
+            if (B) a = a - pmul(bbuf[yrow + j], uinv);
+            v[p] = a;
+        }
+        __syncthreads();                                     // the tile buffers are free: fetch the next tile now
+        if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
+        cp_async_commit();
+        C2<T>* row = reg + g * P;
+        fft_regs<T, H, E, false>(v, row, stw_s, t);
+        __syncwarp();
+        SPCSC_UNROLL
+        for (int p = 0; p < E; ++p) row[t + TPF * p] = v[p];
+        __syncthreads();
+        {
+            const C2<T>* rrow = reg + gr * P;
+            C2<T>* out = Zt + (((size_t)b * N1f) * M + m) * N0 + h0 + (size_t)wf0 * wstride + gr;
+            SPCSC_UNROLL
+            for (int it = 0; it < WIT; ++it) {
+                const int wf = wf0 + it * WSTEP;
+                if (wf < N1f) {
+                    const C2<T> aa = rrow[wf == H ? 0 : wf];
+                    const C2<T> bb = conj(rrow[wf == 0 ? 0 : H - wf]);
+                    const C2<T> sum = aa + bb, dif = mul_mi((aa - bb) * tw_s[wf]);
+                    out[(size_t)it * WSTEP * wstride] =
+                        mk<T>((T)0.5 * (sum.re + dif.re), (T)0.5 * (sum.im + dif.im));
+                }
+            }
+        }
+        // reg is next written after the barrier that follows the wait at the top of the loop
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // k_row_prox_fwd3: the PGM proximal step in the row domain (pgm/pgm.py:796-800, pgm/cbpdn.py:288-298)
 // on the register plans: V = irfft_row(Vt)*scale ; X = prox_l1(V, (lmbda/L) wl1) [+NonNeg,
 // NoBndryCross] stored; Xt = rfft_row(X) written over Vt (the CTA owns its TR rows of every wf);

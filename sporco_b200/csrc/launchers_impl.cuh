@@ -3,6 +3,9 @@
 
 #include "launchers.cuh"
 
+#include <cstdlib>
+#include <string>
+
 namespace spcsc {
 
 inline int round_up32(int n) { return (n + 31) / 32 * 32; }
@@ -209,6 +212,20 @@ cudaError_t row_fwd2_launch(const RowArgs<T>& r, const T* A, const T* B, const A
                             C2<T>* Zt, const C2<T>* stw, int gated) {
     if constexpr (row2_elems(H, 1, (int)sizeof(T)) != 0) {
         constexpr int E = row2_elems(H, 1, (int)sizeof(T)), NT = kRow2Threads, TR = row2_tile(H, 1, (int)sizeof(T));
+        if constexpr (H / E <= 16) {
+            // asynchronous-copy tile flow (as the prox kernel): 128-thread CTAs, next tile prefetched
+            constexpr int NT3 = 128, TR3 = NT3 / (H / E);
+            const bool use3 = !(getenv("SPCSC_ROWFWD") && std::string(getenv("SPCSC_ROWFWD")) == "2");
+            if (use3 && r.N0 % TR3 == 0) {
+                using PL = Prox3Plan<T, H, E, 1, NT3>;
+                const size_t smem3 = ((size_t)2 * PL::YS + (size_t)TR3 * PL::P + PL::TWLEN + PL::N1f) * sizeof(C2<T>);
+                const long long ntiles3 = (long long)(r.N0 / TR3) * r.M * r.nb;
+                const long long cap3 = 148LL * 4 * 4;
+                dim3 grid3((unsigned)(ntiles3 < cap3 ? ntiles3 : cap3));
+                return launch(k_row_fwd3<T, H, E, NT3>, grid3, dim3(NT3), smem3, r.stream, A, B, st, Zt, r.tw,
+                              stw, r.N0, r.M, r.nb, gated);
+            }
+        }
         const size_t smem = ((size_t)TR * (H + H / 16 + 1) + stage_tw_len(H, E)) * sizeof(C2<T>);
         const long long ntiles = (long long)(r.N0 / TR) * r.M * r.nb;
         // grid-stride over tiles: a gated launch that finds nothing to do retires in microseconds
