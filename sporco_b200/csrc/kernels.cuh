@@ -41,8 +41,8 @@ struct AdmmState {
     T udiv;         // pending dual rescale: U_effective = U_stored / udiv
     int k;          // iterations completed
     int stopped;    // 1 once the residual stopping test has fired
-    int zt_stale;   // 1: the pre-computed row spectra of (Y - U) do not match the current U scaling
-    int pad_;
+    int zt_stale;   // 1: the pre-computed row spectra of (Y - U) do not match the current U scaling (or were not made)
+    int emit;       // 1: this iteration's prox kernel also produces the next x-step's row spectra (fused schedule)
 };
 
 template <typename T>
@@ -57,6 +57,9 @@ struct AdmmParams {
     T enet_mu;                           // its l2 weight: the x-step diagonal is enet_mu + rho
     int ams_m0;                          // AddMaskSim: filters m >= ams_m0 are the appended impulse maps (M: none)
     int gradreg;                         // 1: ConvBPDNGradReg: DFid = |q|^2 sums without the rho^2 factor, rows carry RegGrad
+    int emit_policy;                     // cross-iteration fusion: 0 always emit the next row spectra, 1 skip it in the
+                                         // iteration after a change of rho (changes come in runs; a skipped emission
+                                         // costs one row-forward pass, a wasted one costs that pass AND the emission)
 };
 
 struct StatRow {
@@ -1223,7 +1226,10 @@ SPCSC_GLOBAL void k_admm_scalars(AdmmState<T>* st, AdmmParams<T> p, double* acc,
     }
     st->rho = rho;
     st->udiv = udiv;
-    st->zt_stale = (udiv != (T)1) ? 1 : 0;
+    // the spectra the prox kernel may have written for the next x-step are unusable when rho changed (U is
+    // rescaled), and absent when the kernel was told not to write them
+    st->zt_stale = (udiv != (T)1 || !st->emit) ? 1 : 0;
+    st->emit = (p.emit_policy == 0 || udiv == (T)1) ? 1 : 0;
     st->k = k + 1;
     if (p.need_rsdl && (double)r < epri && (double)s < edua) st->stopped = 1;
     for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;

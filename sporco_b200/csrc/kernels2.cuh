@@ -560,9 +560,10 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
             block_accumulate_det<7>(d, red, reinterpret_cast<unsigned long long*>(acc + ACC_N));
         }
     }
-    if (Znext) {
+    if (Znext && st->emit) {
         // Cross-iteration fusion: the row spectra of Y - U for the next iteration, valid as long
-        // as rho (hence the scaling of U) does not change; otherwise k_row_fwd2 redoes them.
+        // as rho (hence the scaling of U) does not change; otherwise k_row_fwd3 redoes them.  Skipped
+        // (st->emit, set by the scalar kernel) in the iteration after a change of rho.
         SPCSC_UNROLL
         for (int c = 0; c < CX; ++c) {
             C2<T>* row = reg + (c * TR + g) * P;

@@ -711,6 +711,7 @@ class Engine : public spcsc_handle {
         prm.enet_mu = (T)o->l2_weight;
         prm.ams_m0 = M - (o->ams_maps > 0 ? o->ams_maps : 0);
         prm.gradreg = gradreg ? 1 : 0;
+        prm.emit_policy = (getenv("SPCSC_EMIT") && atoi(getenv("SPCSC_EMIT")) == 0) ? 0 : 1;
         if (gradreg) {
             if (o->joint || o->l2_weight != 0.0) FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with the joint or l2 penalty");
             std::vector<C2<T>> gw(M);
@@ -729,7 +730,7 @@ class Engine : public spcsc_handle {
 
     int write_state(T rho, T udiv, int k, int stopped) {
         AdmmState<T> s;
-        s.rho = rho; s.udiv = udiv; s.k = k; s.stopped = stopped; s.zt_stale = 1; s.pad_ = 0;
+        s.rho = rho; s.udiv = udiv; s.k = k; s.stopped = stopped; s.zt_stale = 1; s.emit = 0;
         CK(cudaMemcpyAsync(st.p, &s, sizeof(s), cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
         return SPCSC_OK;
