@@ -262,18 +262,25 @@ def msk_shape(W, dims):
 
 
 def admm_addmasksim(D, S, W, lmbda=None, opt=None, dimK=None, fft=None, grad_mu=None):
-    """AddMaskSim(ConvBPDN, D, S, W, lmbda, opt) (admm/cbpdn.py:2287-2485), single-channel
-    dictionary: an impulse filter is appended, its coefficient map is set to AX + U off the mask
-    and to zero on it, and is left out of the regulariser.  Returns the ADMMResult of the inner
-    solver (all M+1 maps) ."""
+    """AddMaskSim(ConvBPDN, D, S, W, lmbda, opt) (admm/cbpdn.py:2287-2485): impulse filters are appended
+    (one for a single-channel dictionary, one per channel -- each non-zero in its own channel -- for a
+    multi-channel one, :2337-2345), their coefficient maps are set to AX + U off the mask and to zero on it,
+    and are left out of the regulariser.  A mask with a channel axis moves that axis onto the filter axis of
+    the impulse maps (:2361-2362).  Returns the ADMMResult of the inner solver (all M + Cd maps)."""
     dims = Dims(D, S, dimK=dimK)
-    assert dims.Cd == 1
-    imp = np.zeros(D.shape[0:2] + (1,), dtype=D.dtype)
-    imp[0, 0] = 1.0
+    if dims.Cd == 1:
+        imp = np.zeros(D.shape[0:2] + (1,), dtype=D.dtype)
+        imp[0, 0] = 1.0
+    else:
+        imp = np.zeros(D.shape[0:2] + (dims.Cd,) * 2, dtype=D.dtype)
+        for c in range(dims.Cd):
+            imp[0, 0, c, c] = 1.0
     Di = np.concatenate((D, imp), axis=D.ndim - 1)
     dtype = np.dtype(S.dtype) if (opt or {}).get('DataType') is None else np.dtype(opt['DataType'])
     W5 = np.asarray(W.reshape(msk_shape(W, dims)), dtype=dtype)
-    return admm_convbpdn(Di, S, lmbda, opt=opt, dimK=dimK, fft=fft, ams=(W5, 1), grad_mu=grad_mu)
+    if dims.Cd > 1 and W5.shape[2] > 1:
+        W5 = np.swapaxes(W5, dims.axisC, dims.axisM)
+    return admm_convbpdn(Di, S, lmbda, opt=opt, dimK=dimK, fft=fft, ams=(W5, dims.Cd), grad_mu=grad_mu)
 
 
 def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,

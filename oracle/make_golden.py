@@ -289,6 +289,16 @@ def main():
         pgm_case('pgm_fixed_' + sfx, dt, D, S, 0.1,
                  {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0},
                  {'MaxMainIter': 30, 'RelStopTol': 0.0, 'L': 400.0}, dimK=1)
+        # multi-channel dictionaries in AddMaskSim (one impulse per channel, channel mask on the impulse maps) and
+        # in the masked PGM solver; own generator so that the cases above keep their inputs
+        rng3 = np.random.default_rng(4321)
+        W3 = (rng3.random((32, 32, 3, 2)) > 0.3).astype(dt)
+        ams_case('ams_c3_' + sfx, dt, D3, S3, W3, 0.1, {'MaxMainIter': 20, 'RelStopTol': 0.0})
+        pgm_mask_case('pgm_mask_c3_' + sfx, dt, D3, S3, W3, 0.1,
+                      {'MaxMainIter': 15, 'RelStopTol': 0.0, 'L': 5.0,
+                       'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)},
+                      {'MaxMainIter': 15, 'RelStopTol': 0.0, 'L': 5.0,
+                       'Backtrack': {'gamma_u': 1.3, 'maxiter': 8}})
         # row a17: step-size policies, monotone FISTA, robust backtracking
         pb = {'MaxMainIter': 25, 'RelStopTol': 0.0}
         pgm_case('pgm_cauchy_' + sfx, dt, D, S, 0.1, dict(pb, L=50.0, StepSizePolicy=StepSizePolicyCauchy()),

@@ -423,7 +423,7 @@ class AddMaskSim(object):
     """Boundary / missing-data masking by additive mask simulation (mirror of
     sporco/admm/cbpdn.py:2287-2485): a wrapper about a :class:`ConvBPDN` (or :class:`ConvElasticNet`)
     object whose dictionary gets an impulse filter appended; the impulse's coefficient map absorbs
-    the signal where the mask `W` is zero.  Single-channel dictionaries.
+    the signal where the mask `W` is zero (one impulse filter per channel for a multi-channel dictionary).
 
     On the device the hook the reference installs on ``ystep`` / ``obfn_gvar`` is a property of the
     prox kernel: the mask enters as the l1 weight of the impulse map (0 where ``W == 0``: the map
@@ -438,32 +438,48 @@ class AddMaskSim(object):
                 issubclass(cbpdnclass, ConvBPDNJoint):
             raise NotImplementedError('AddMaskSim wraps sporco_b200 ConvBPDN / ConvElasticNet objects')
         self.cri = cr.CSC_ConvRepIndexing(D, S, dimK=dimK, dimN=dimN)
-        if self.cri.Cd != 1:
-            raise NotImplementedError('AddMaskSim with a multi-channel dictionary is not supported')
-        self.imp = np.zeros(D.shape[0:dimN] + (1,))
-        self.imp[(0,) * dimN] = 1.0
+        Cd = self.cri.Cd
+        if Cd > 1 and issubclass(cbpdnclass, ConvBPDNGradReg):
+            raise NotImplementedError('AddMaskSim about ConvBPDNGradReg with a multi-channel dictionary '
+                                      'is not supported')
+        # one impulse filter, or one per channel (each non-zero in its own channel) for a multi-channel
+        # dictionary (sporco/admm/cbpdn.py:2337-2345)
+        if Cd == 1:
+            self.imp = np.zeros(D.shape[0:dimN] + (1,))
+            self.imp[(0,) * dimN] = 1.0
+        else:
+            self.imp = np.zeros(D.shape[0:dimN] + (Cd,) * 2)
+            for c in range(Cd):
+                self.imp[(0,) * dimN + (c, c)] = 1.0
         Di = np.concatenate((D, self.imp.astype(D.dtype)), axis=D.ndim - 1)
         self.cbpdn = cbpdnclass(Di, S, *args, **kwargs)
         self.IterationStats = self.cbpdn.IterationStats
         inner = self.cbpdn
         self.W = np.asarray(np.asarray(W).reshape(cr.mskWshape(np.asarray(W), self.cri)),
                             dtype=inner.dtype)
-        # positions of the impulse map that are forced to zero: exactly the reference's
-        # ``Yi[np.where(self.W.astype(bool))] = 0.0`` on Yi of shape (N0, N1, Cx, K, 1)
+        # a mask with a channel axis applies channel c to the map of impulse c (:2361-2362)
+        if Cd > 1 and self.W.shape[self.cri.dimN] > 1:
+            self.W = np.swapaxes(self.W, self.cri.axisC, self.cri.axisM)
+        # positions of the impulse maps that are forced to zero: exactly the reference's
+        # ``Yi[np.where(self.W.astype(bool))] = 0.0`` on Yi of shape (N0, N1, Cx, K, Cd)
         icri = inner.cri
         kdim = icri.K if self.W.shape[icri.axisK] > 1 else 1
         cdim = icri.shpX[icri.axisC] if self.W.shape[icri.axisC] > 1 else 1
-        on = np.zeros(icri.Nv + (cdim, kdim, 1), dtype=bool)
+        on = np.zeros(icri.Nv + (cdim, kdim, Cd), dtype=bool)
+        # (index arrays, not broadcasting: a mask without a channel axis reaches the first impulse map only --
+        # the reference's behaviour, kept)
         on[np.where(self.W.astype(bool))] = True
         # combined l1 weight: the inner object's own weight on the primary maps ...
         w1 = inner.wl1
         shp = tuple(max(a, b) for a, b in zip(w1.shape[:4], on.shape[:4])) + (icri.M,)
         wfull = np.empty(shp, dtype=inner.dtype)
         wfull[...] = np.broadcast_to(w1, shp)
-        # ... and the mask on the impulse map
+        # ... and the mask on the impulse maps
         huge = inner.dtype.type(1e30 if inner.dtype == np.float32 else 1e300)
-        wfull[..., -1] = np.where(np.broadcast_to(on[..., 0], shp[:4]), huge, inner.dtype.type(0))
-        inner._ams_maps = 1
+        for c in range(Cd):
+            wfull[..., icri.M - Cd + c] = np.where(np.broadcast_to(on[..., c], shp[:4]), huge,
+                                                  inner.dtype.type(0))
+        inner._ams_maps = Cd
         inner.wl1 = wfull
         inner._after_open()
         self.timer = inner.timer
@@ -495,7 +511,7 @@ class AddMaskSim(object):
         if X is None:
             X = inner.Y[self.index_primary()]
         X = np.asarray(X, dtype=inner.dtype)
-        Xi = np.concatenate((X, np.zeros(X.shape[:-1] + (1,), dtype=inner.dtype)), axis=X.ndim - 1)
+        Xi = np.concatenate((X, np.zeros(X.shape[:-1] + (self.cri.Cd,), dtype=inner.dtype)), axis=X.ndim - 1)
         return inner.reconstruct(Xi)
 
     def getitstat(self):

@@ -1562,7 +1562,6 @@ class Engine : public spcsc_handle {
     int pgm_set_mask(const void* W, const int64_t* shape) override {
         if (poisoned) return SPCSC_ERR_CUDA;
         if (!W) { pgm_mask = false; return SPCSC_OK; }
-        if (Cd != 1) FAIL(SPCSC_ERR_UNSUPPORTED, "masked PGM with a multi-channel dictionary");
         const int64_t full[4] = {N0, N1, C, K};
         for (int i = 0; i < 4; ++i)
             if (shape[i] != 1 && shape[i] != full[i]) FAIL(SPCSC_ERR_INVALID, "mask shape is not broadcastable to (N0,N1,C,K)");

@@ -210,13 +210,11 @@ class ConvBPDNMask(ConvBPDN):
 
     The gradient, the backtracking functional and DFid take the residual through the signal
     domain (``rfft(W^2 irfft(.))``); on the device these are transforms of the K*C residual
-    planes only, next to the M-times larger coefficient arrays.  Single-channel dictionaries.
+    planes only, next to the M-times larger coefficient arrays.
     """
 
     def __init__(self, D, S, lmbda, W=None, opt=None, dimK=None, dimN=2, device=0):
         super(ConvBPDNMask, self).__init__(D, S, lmbda, opt, dimK=dimK, dimN=dimN, device=device)
-        if self.cri.Cd != 1:
-            raise NotImplementedError('ConvBPDNMask with a multi-channel dictionary is not supported')
         if W is None:
             W = np.array([1.0], dtype=self.dtype)
         W = np.asarray(W)

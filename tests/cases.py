@@ -526,7 +526,9 @@ AMS_CASES = {'ams_gry': ({'MaxMainIter': 30, 'RelStopTol': 0.0}, None),
              'ams_grd': ({'MaxMainIter': 30, 'RelStopTol': 0.0, 'rho': 3.0, 'AutoRho': {'Enabled': False},
                           'GradWeight': 'ams7'}, None),
              'ams_k3': ({'MaxMainIter': 20, 'RelStopTol': 0.0, 'NonNegCoef': True, 'NoBndryCross': True,
-                         'AuxVarObj': True}, 1)}
+                         'AuxVarObj': True}, 1),
+             # multi-channel dictionary: one impulse filter per channel, the mask's channels on the impulse maps
+             'ams_c3': ({'MaxMainIter': 20, 'RelStopTol': 0.0}, None)}
 
 
 def run_ams_case(tag, sfx):
@@ -573,15 +575,17 @@ def run_tikhonov_cases():
             assert np.allclose(sl + sh, s, atol=1e-6 if sfx == 'f32' else 1e-14)
 
 
-def run_pgm_mask_case(sfx):
-    """pgm.cbpdn.ConvBPDNMask with backtracking against the reference's outputs."""
+def run_pgm_mask_case(sfx, tag='pgm_mask'):
+    """pgm.cbpdn.ConvBPDNMask with backtracking against the reference's outputs (`pgm_mask`: single-channel
+    dictionary, three images; `pgm_mask_c3`: multi-channel dictionary)."""
     from sporco_b200.pgm import cbpdn as pcbpdn
     from sporco_b200.pgm.backtrack import BacktrackStandard
     tol = 1e-11 if sfx == 'f64' else 5e-5
-    g = load('pgm_mask_' + sfx)
-    opt = pcbpdn.ConvBPDN.Options({'MaxMainIter': 20, 'RelStopTol': 0.0, 'L': 5.0,
+    g = load('%s_%s' % (tag, sfx))
+    c3 = tag.endswith('c3')
+    opt = pcbpdn.ConvBPDN.Options({'MaxMainIter': 15 if c3 else 20, 'RelStopTol': 0.0, 'L': 5.0,
                                    'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=8)})
-    b = pcbpdn.ConvBPDNMask(g['D'], g['S'], float(g['lmbda']), g['W'], opt, dimK=1)
+    b = pcbpdn.ConvBPDNMask(g['D'], g['S'], float(g['lmbda']), g['W'], opt, dimK=None if c3 else 1)
     X = b.solve()
     its = b.getitstat()
     assert X.dtype == g['X'].dtype and rel(X, g['X']) < tol

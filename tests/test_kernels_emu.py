@@ -138,6 +138,7 @@ def test_tikhonov_filter_golden():
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
 def test_pgm_mask_golden(sfx):
     cases.run_pgm_mask_case(sfx)
+    cases.run_pgm_mask_case(sfx, 'pgm_mask_c3')          # multi-channel dictionary
 
 
 @pytest.mark.parametrize('wave', ['1,1', '2,2', '2,1'])

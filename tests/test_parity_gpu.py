@@ -256,6 +256,7 @@ def test_tikhonov_filter_golden():
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
 def test_pgm_mask_golden(sfx):
     cases.run_pgm_mask_case(sfx)
+    cases.run_pgm_mask_case(sfx, 'pgm_mask_c3')          # multi-channel dictionary
 
 
 def test_eight_cta_clusters_admm_and_pgm():
