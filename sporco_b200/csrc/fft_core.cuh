@@ -212,7 +212,10 @@ constexpr int stage_tw_len(int N, int E) {
     return len;
 }
 
-template <typename T, int N, int E, bool INV, int Ns, int TWOFF>
+// TWR: the (single) twiddled stage of a two-stage plan takes its factors from a thread-local array laid out
+// [i][r] (see load_stage_tw_regs) instead of the shared-memory table: they depend only on the lane, so a
+// persistent kernel loads them once and keeps them in registers.
+template <typename T, int N, int E, bool INV, int Ns, int TWOFF, bool TWR = false>
 struct RegStage {
     static constexpr int REM = N / Ns;
     static constexpr int R = REM >= E ? E : REM;
@@ -237,7 +240,7 @@ struct RegStage {
                 for (int r = 0; r < R; ++r) {
                     C2<T> x = RD_FAST ? rd[r * (RS + RS / 16)] : buf[fft_pad(j + r * RS)];
                     if (r > 0) {
-                        const C2<T> w = stw[TWOFF + r * Ns + k];
+                        const C2<T> w = TWR ? stw[i * R + r] : stw[TWOFF + r * Ns + k];
                         x = INV ? mulc(x, w) : x * w;
                     }
                     v[i * R + r] = x;
@@ -268,7 +271,8 @@ struct RegStage {
                 }
             }
             __syncwarp();
-            RegStage<T, N, E, INV, Ns * R, TWOFF + (Ns > 1 ? R * Ns : 0)>::run(v, buf, stw, t);
+            static_assert(!TWR || Ns == 1, "register twiddles: two-stage plans only");
+            RegStage<T, N, E, INV, Ns * R, TWOFF + (Ns > 1 ? R * Ns : 0), TWR>::run(v, buf, stw, t);
         } else {
             // slot i*R + r holds X[t + TPF*(i + NB*r)]: rename registers into strided order
             if (NB > 1) {
@@ -387,6 +391,26 @@ template <typename T, int N, int E, bool INV>
 SPCSC_DEV void fft_regs(C2<T>* v, C2<T>* buf, const C2<T>* SPCSC_RESTRICT stw, int t) {
     static_assert(E <= N && (N / E) <= 32, "plan must fit in one warp");
     RegStage<T, N, E, INV, 1, 0>::run(v, buf, stw, t);
+}
+
+// Two-stage plans (E < N <= E*E) with the second stage's factors in registers: twr[E] is filled once per
+// thread by load_stage_tw_regs from the (N, E) table and then passed to fft_regs_twr for every transform.
+template <int N, int E>
+constexpr bool fft_two_stage() { return N > E && N <= E * E; }
+template <typename T, int N, int E>
+SPCSC_DEV void load_stage_tw_regs(C2<T>* twr, const C2<T>* SPCSC_RESTRICT stw, int t) {
+    constexpr int Ns = E, R = N / E, NB = E / R, TPF = N / E;
+    SPCSC_UNROLL
+    for (int i = 0; i < NB; ++i) {
+        const int k = (t + i * TPF) & (Ns - 1);
+        SPCSC_UNROLL
+        for (int r = 0; r < R; ++r) twr[i * R + r] = stw[r * Ns + k];
+    }
+}
+template <typename T, int N, int E, bool INV>
+SPCSC_DEV void fft_regs_twr(C2<T>* v, C2<T>* buf, const C2<T>* twr, int t) {
+    static_assert(fft_two_stage<N, E>() && (N / E) <= 32, "two-stage plan in one warp");
+    RegStage<T, N, E, INV, 1, 0, true>::run(v, buf, twr, t);
 }
 
 }  // namespace spcsc

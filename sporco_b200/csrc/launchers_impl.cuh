@@ -342,6 +342,65 @@ static bool col3_go(ColLaunch<T>& c, const C2<T>* stw, unsigned cs, cudaError_t&
     return true;
 }
 
+// k_col4 launch (single-channel dictionaries): returns false when it does not fit
+constexpr int kCol4Threads = 512;
+template <typename T, int N0, int E>
+static bool col4_go(ColLaunch<T>& c, const C2<T>* stw, cudaError_t& result) {
+    constexpr int NT = kCol4Threads, TPF = N0 / E, NG = NT / TPF;
+    if constexpr (N0 > NT || NG < 1) {
+        return false;
+    } else {
+        auto kern = k_col4<T, N0, E, NT>;
+        const unsigned cs = (unsigned)((c.a.M + NG - 1) / NG);
+        if (cs > 8) return false;
+        const size_t smem4 = col4_smem_bytes<T, N0, E, NT>((int)cs);
+        if (smem4 > 227 * 1024) return false;
+        static int resident4[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
+        if (resident4[cs] == 0) {
+            resident4[cs] = max_active_clusters(kern, dim3(NT), cs, smem4);
+            if (resident4[cs] <= 0) resident4[cs] = -1;
+        }
+        const int ncl = resident4[cs];
+        if (ncl <= 0) return false;
+        const long long total = (long long)c.a.N1f * c.nb;
+        const int use = (long long)ncl < total ? ncl : (int)total;
+        g_col_variant = 6;
+        result = launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem4, c.stream, c.in, c.out, c.Df,
+                                c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb);
+        return true;
+    }
+}
+
+// k_col5 launch (single-channel dictionaries): independent thread groups sharing the staged dictionary columns
+template <typename T, int N0, int E>
+static bool col5_go(ColLaunch<T>& c, const C2<T>* stw, cudaError_t& result) {
+    constexpr int NT = kCol4Threads, NGRP = 2, TPF = N0 / E, NGG = (NT / NGRP) / TPF;
+    if constexpr (NGG < 1) {
+        return false;
+    } else {
+        auto kern = k_col5<T, N0, E, NT, NGRP>;
+        const unsigned cs = (unsigned)((c.a.M + NGG - 1) / NGG);
+        if (cs > 8) return false;
+        const size_t smem5 = col5_smem_bytes<T, N0, E, NT, NGRP>((int)cs);
+        if (smem5 > 227 * 1024) return false;
+        static int resident5[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per cluster size
+        if (resident5[cs] == 0) {
+            resident5[cs] = max_active_clusters(kern, dim3(NT), cs, smem5);
+            if (resident5[cs] <= 0) resident5[cs] = -1;
+        }
+        const int ncl = resident5[cs];
+        if (ncl <= 0) return false;
+        const long long total = (long long)c.a.N1f * c.nb;
+        const int use = (long long)ncl < total ? ncl : (int)total;
+        static int stagger = -1;
+        if (stagger < 0) stagger = getenv("SPCSC_COL5_STAGGER") ? atoi(getenv("SPCSC_COL5_STAGGER")) : 0;
+        g_col_variant = 7;
+        result = launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem5, c.stream, c.in, c.out, c.Df,
+                                c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, stagger);
+        return true;
+    }
+}
+
 template <typename T, int N0, int CD>
 static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
     constexpr int E = col2_elems<T>(), NT = kCol2Threads, CPG = col2_cpg<T>();
@@ -370,7 +429,17 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
                               c.sumout, c.sumin, c.ref);
     if (mode != COL_ADMM) return cudaErrorInvalidValue;
     g_col_variant = 2;
-    if (c.push && !c.bulk) {
+    if constexpr (CD == 1) {
+        if (c.push == 4) {          // k_col4: slab, dictionary columns and signal row staged by bulk copies
+            cudaError_t e4 = cudaErrorInvalidValue;
+            if (col4_go<T, N0, E>(c, stw, e4)) return e4;
+        }
+        if (c.push == 5) {          // k_col5: the same with two independent thread groups per CTA
+            cudaError_t e5 = cudaErrorInvalidValue;
+            if (col5_go<T, N0, E>(c, stw, e5)) return e5;
+        }
+    }
+    if (c.push && c.push != 4 && c.push != 5 && !c.bulk) {
         // k_col3: persistent clusters over (frequency column, run of images) items; the per-frequency sums
         // travel by st.async pushes instead of cluster barriers.  push == 2 (float32): the two columns of a lane
         // group are transformed together, exchanging 16-byte elements

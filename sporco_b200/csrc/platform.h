@@ -178,6 +178,11 @@ inline void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
     memcpy(dst, src, bytes);
     mbar_complete_tx(bar, bytes);
 }
+// copy only: the bytes must have been announced with mbar_expect_tx (several copies, one arrival)
+inline void bulk_copy(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
+    memcpy(dst, src, bytes);
+    mbar_complete_tx(bar, bytes);
+}
 inline void mbar_wait(mbar_t* bar, unsigned parity) {
     while (reinterpret_cast<EmuBar*>(bar)->phase == (unsigned char)parity) emu::yield();
 }
@@ -200,6 +205,13 @@ SPCSC_DEV void bulk_load(void* dst, const void* src, unsigned bytes, mbar_t* bar
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// copy only: the bytes must have been announced with mbar_expect_tx (several copies, one arrival)
+SPCSC_DEV void bulk_copy(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
 SPCSC_DEV void mbar_wait(mbar_t* bar, unsigned parity) {
     unsigned done = 0;
     while (!done) {
@@ -216,6 +228,17 @@ SPCSC_DEV void mbar_wait(mbar_t* bar, unsigned parity) {
 // The store completes `sizeof(value)` transaction bytes on an mbarrier of the RECEIVING CTA, which waits on
 // its own barrier: no cluster-wide barrier, hence none of the cluster-scope fences (and the L1 invalidation)
 // that barrier.cluster.arrive.release / wait.acquire bring along.
+// ---- named barrier over a subset of the CTA's warps (independent thread groups inside one CTA) -------------
+#ifdef SPCSC_EMU
+inline void group_barrier(int id, int nthreads) { emu::named_barrier(id, nthreads); }
+inline void nap(unsigned) {}
+#else
+SPCSC_DEV void group_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+SPCSC_DEV void nap(unsigned ns) { __nanosleep(ns); }
+#endif
+
 #ifdef SPCSC_EMU
 typedef unsigned char* rptr_t;                       // address in a peer's shared memory
 template <typename P> inline rptr_t cluster_remote(P* p, unsigned rank) {

@@ -48,6 +48,8 @@ struct BlockCtx {
     unsigned char* smem = nullptr;
     int bar_arrive = 0;
     unsigned bar_gen = 0;
+    int nb_arrive[16] = {0};
+    unsigned nb_gen[16] = {0};
     uint3 bidx;
 };
 
@@ -90,6 +92,7 @@ void run_cluster(Worker* w, unsigned cl, dim3 grid, dim3 block, unsigned cs) {
         if ((int)B.fib.size() < n) B.fib.resize(n);
         if ((int)B.warps.size() < nwarp) B.warps.resize(nwarp);
         B.bar_arrive = 0;
+        for (int i = 0; i < 16; ++i) B.nb_arrive[i] = 0;
         for (int i = 0; i < nwarp; ++i) {
             B.warps[i].arrive = 0;
             B.warps[i].lanes = (i == nwarp - 1) ? n - 32 * i : 32;
@@ -237,6 +240,18 @@ void sync_threads() {
         return;
     }
     while (B.bar_gen == g) yield_to_sched();
+}
+
+void named_barrier(int id, int nthreads) {
+    Worker* w = t_worker;
+    BlockCtx& B = w->blk[w->cur_blk];
+    unsigned g = B.nb_gen[id];
+    if (++B.nb_arrive[id] == nthreads) {
+        B.nb_arrive[id] = 0;
+        ++B.nb_gen[id];
+        return;
+    }
+    while (B.nb_gen[id] == g) yield_to_sched();
 }
 
 void sync_warp() {

@@ -41,6 +41,7 @@ void cluster_wait();
 void* map_shared_rank(void* p, unsigned rank);
 void yield();                        // let the other fibres of the cluster run (used by emulated waits)
 void sync_threads();
+void named_barrier(int id, int nthreads);   // bar.sync id, nthreads
 void sync_warp();
 // exchange 16-byte payloads between lanes of the calling warp
 void warp_exchange(const void* mine, void* out, int src_lane, size_t nbytes);

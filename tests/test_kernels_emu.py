@@ -197,14 +197,28 @@ def test_setting_y_between_solves_is_seen_by_the_fused_schedule():
 
 
 @pytest.mark.parametrize('case', cases.FRESH_CASES + [(64, 64, 8, 5, None, None, None)])
-@pytest.mark.parametrize('pair', [False, True, 'cpg1'])
+@pytest.mark.parametrize('pair', [False, True, 'cpg1', 'col4', 'col5'])
 def test_push_exchange_column_kernel_vs_oracle(case, pair, monkeypatch):
     """k_col3 (SPCSC_COL3=1): persistent clusters over (frequency column, run of images) items, the
     per-frequency sums pushed into the peers' shared memory and awaited on an mbarrier."""
-    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3'}[pair])
+    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3', 'col4': '4', 'col5': '5'}[pair])
     N0, N1, M, K, C, mu, extra = case
     b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
-    assert b._h.admm_schedule_info()['col_kernel'] == {False: 3, True: 4, 'cpg1': 5}[pair]
+    want = {False: 3, True: 4, 'cpg1': 5, 'col4': 6, 'col5': 7}[pair]
+    if pair == 'col5' and N0 > 256:
+        want = 2        # 512-point columns do not fit two groups' stages: k_col2 takes over
+    assert b._h.admm_schedule_info()['col_kernel'] == want
+
+
+@pytest.mark.parametrize('case', cases.FRESH_CASES_F64[:2])
+def test_staged_column_kernel_float64(case, monkeypatch):
+    """k_col4 (SPCSC_COL3=4: slab, dictionary columns and signal row staged by bulk copies) in float64:
+    8 elements per lane, 16 columns per CTA, clusters of up to 8."""
+    monkeypatch.setenv('SPCSC_COL3', '4')
+    N0, N1, M, K, C, mu, extra = case
+    b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra, dt=np.float64, tol=1e-9)
+    # 256-point float64 columns do not fit the staged layout (239 KB): k_col2 takes over
+    assert b._h.admm_schedule_info()['col_kernel'] == (6 if N0 <= 128 else 2)
 
 
 def test_push_exchange_column_kernel_float64_and_colour_dictionary(monkeypatch):

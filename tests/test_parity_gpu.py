@@ -150,13 +150,27 @@ def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
 
 
 @pytest.mark.parametrize('case', [cases.FRESH_CASES[0], cases.FRESH_CASES[2], (64, 64, 8, 5, None, None, None)])
-@pytest.mark.parametrize('pair', [False, True, 'cpg1'])
+@pytest.mark.parametrize('pair', [False, True, 'cpg1', 'col4', 'col5'])
 def test_push_exchange_column_kernel_vs_oracle(case, pair, monkeypatch):
     """k_col3 (persistent clusters, sums pushed over DSMEM) against the oracle and against k_col2."""
-    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3'}[pair])
+    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3', 'col4': '4', 'col5': '5'}[pair])
     N0, N1, M, K, C, mu, extra = case
     b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
-    assert b._h.admm_schedule_info()['col_kernel'] == {False: 3, True: 4, 'cpg1': 5}[pair]
+    want = {False: 3, True: 4, 'cpg1': 5, 'col4': 6, 'col5': 7}[pair]
+    if pair == 'col5' and N0 > 256:
+        want = 2        # 512-point columns do not fit two groups' stages: k_col2 takes over
+    assert b._h.admm_schedule_info()['col_kernel'] == want
+
+
+@pytest.mark.parametrize('case', cases.FRESH_CASES_F64[:2])
+def test_staged_column_kernel_float64(case, monkeypatch):
+    """k_col4 (SPCSC_COL3=4: slab, dictionary columns and signal row staged by bulk copies) in float64:
+    8 elements per lane, 16 columns per CTA, clusters of up to 8."""
+    monkeypatch.setenv('SPCSC_COL3', '4')
+    N0, N1, M, K, C, mu, extra = case
+    b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra, dt=np.float64, tol=1e-9)
+    # 256-point float64 columns do not fit the staged layout (239 KB): k_col2 takes over
+    assert b._h.admm_schedule_info()['col_kernel'] == (6 if N0 <= 128 else 2)
 
 
 @pytest.mark.parametrize('wave', ['2,2', 'f:2,2'])
