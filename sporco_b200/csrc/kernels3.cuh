@@ -317,12 +317,12 @@ constexpr size_t col4_smem_bytes(int cs) {
            32 * sizeof(double) + 4 * sizeof(mbar_t);
 }
 
-template <typename T, int N0, int E, int NT>
+template <typename T, int N0, int E, int NT, bool DBG = false>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 1)
 k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
        const AdmmState<T>* SPCSC_RESTRICT st, double* SPCSC_RESTRICT acc,
-       const C2<T>* SPCSC_RESTRICT stw, ColArgs a, int nb) {
+       const C2<T>* SPCSC_RESTRICT stw, ColArgs a, int nb, unsigned* dbg = nullptr) {
     if (st->stopped) return;                                   // same value in every CTA of the cluster
     SPCSC_DYN_SMEM(smem_raw);
     constexpr int TPF = N0 / E, NG = NT / TPF;
@@ -373,12 +373,23 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     }
     int cur_wf = -1;
     unsigned nslab = 0, ndf = 0;
+    // DBG: cycles per phase, summed over the slabs, for two probe threads (a reducer and a non-reducer)
+    unsigned ph_c[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned tk = 0;
+#ifndef SPCSC_EMU
+#define SPCSC_MARK(i) if constexpr (DBG) { const unsigned now_ = (unsigned)clock64(); ph_c[i] += now_ - tk; tk = now_; }
+#else
+#define SPCSC_MARK(i)
+#endif
     for (int L = lo; L < hi; ++L, ++nslab) {
         const int wf = L / nb, b = L - wf * nb;
         const unsigned par = nslab & 1u, ph = (nslab >> 1) & 1u;
         const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
         const double wgt_wf = (wf == 0 || (a.even_n1 && wf == a.N1f - 1)) ? 1.0 : 2.0;
         bool df_wait = false;
+#ifndef SPCSC_EMU
+        if constexpr (DBG) tk = (unsigned)clock64();
+#endif
         if (wf != cur_wf) {                                    // the same decision in every CTA of the cluster
             cur_wf = wf;
             __syncthreads();                                   // everyone has used the previous column's slice
@@ -390,7 +401,9 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             df_wait = true;
         }
         if (cs > 1 && tid == 0) mbar_expect_tx(bar + par, rbytes);
+        SPCSC_MARK(0)
         mbar_wait(bar + 2, par);                               // the slab's columns and signal row have landed
+        SPCSC_MARK(1)
         C2<T> v[E];
         if (have) {
             SPCSC_UNROLL
@@ -401,6 +414,7 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
         }
         fft_regs<T, N0, E, false>(v, xbuf + g * XP, stw_s, t);
         __syncwarp();
+        SPCSC_MARK(2)
         if (df_wait) {
             mbar_wait(bar + 3, ndf & 1u);
             ++ndf;
@@ -411,7 +425,9 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             const int h = t + TPF * p;
             xbuf[g * XP + h] = have ? dfs[g * N0 + h] * v[p] : mk<T>(0, 0);
         }
+        SPCSC_MARK(3)
         __syncthreads();
+        SPCSC_MARK(4)
         if (tid == 0 && L + 1 < hi) {                          // the stage is free: fetch the next slab now
             const int wfn = (L + 1) / nb, bn = (L + 1) - wfn * nb;
             const int kn = bn / a.Cx, cxn = bn - kn * a.Cx;
@@ -440,7 +456,9 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             }
             mine[i] = s0;
         }
+        SPCSC_MARK(5)
         if (cs > 1) mbar_wait(bar + par, ph);
+        SPCSC_MARK(6)
         const T rho = st->rho;
         double dsum[1] = {0.0};
         SPCSC_UNROLL
@@ -457,7 +475,9 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 qbuf[h] = q;
             }
         }
+        SPCSC_MARK(7)
         __syncthreads();
+        SPCSC_MARK(8)
         if (a.dfid_on) block_accumulate<1>(dsum, red, acc + ACC_DFID);
         if (have) {
             SPCSC_UNROLL
@@ -466,16 +486,27 @@ k_col4(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 v[p] = v[p] + mulc(qbuf[h], dfs[g * N0 + h]);
             }
         }
+        SPCSC_MARK(9)
         fft_regs<T, N0, E, true>(v, xbuf + g * XP, stw_s, t);
         __syncwarp();
+        SPCSC_MARK(10)
         if (have) {
             C2<T>* dst = out + slab + (size_t)(col0 + g) * N0;
             SPCSC_UNROLL
             for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[p];
         }
+        SPCSC_MARK(11)
         // xbuf rows, qbuf and recv[par] are next written after barriers every thread passes only once it is
         // done with them here (see k_col3); the stage and pre[par ^ 1] are being refilled meanwhile
     }
+    if constexpr (DBG) {
+        if (dbg && (tid == 0 || tid == NT / 2)) {
+            unsigned* o = dbg + ((size_t)blockIdx.x * 2 + (tid ? 1 : 0)) * 13;
+            for (int i = 0; i < 12; ++i) o[i] = ph_c[i];
+            o[12] = nslab;
+        }
+    }
+#undef SPCSC_MARK
 }
 
 // ------------------------------------------------------------------------------------
@@ -509,7 +540,10 @@ constexpr size_t col5_smem_bytes(int cs) {
            32 * sizeof(double) + (3 * NGRP + 1) * sizeof(mbar_t);
 }
 
-template <typename T, int N0, int E, int NT, int NGRP>
+// TST: the result leaves through the exchange regions and bulk copies shared -> global instead of 16 stores per
+// thread (measured 3 % slower at the metric configuration -- the extra pass through shared memory costs more than the
+// store queue it relieves -- so it stays an experiment).
+template <typename T, int N0, int E, int NT, int NGRP, bool TST = false>
 SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS2(NT, 1)
 k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* SPCSC_RESTRICT Df,
        const C2<T>* SPCSC_RESTRICT Sf, const C2<T>* SPCSC_RESTRICT G,
@@ -595,6 +629,10 @@ k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 SPCSC_UNROLL
                 for (int p = 0; p < E; ++p) v[p] = mk<T>(0, 0);
             }
+            if constexpr (TST) {                               // the previous slab's result has left this region
+                if (t == 0) bulk_store_wait_read();
+                __syncwarp();
+            }
             if constexpr (TWR)
                 fft_regs_twr<T, N0, E, false>(v, xbuf + g * XP, twr, t);
             else
@@ -617,6 +655,7 @@ k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 bulk_copy(pre + (par ^ 1u) * N0, Sf + (((size_t)kn * a.Cs + cxn) * a.N1f + wf) * N0, rowbytes,
                           bar + 2);
             }
+            const T rho = st->rho;
             C2<T> mine[HPT];
             SPCSC_UNROLL
             for (int i = 0; i < HPT; ++i) {
@@ -638,7 +677,6 @@ k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 mine[i] = s0;
             }
             if (cs > 1) mbar_wait(bar + par, ph);
-            const T rho = st->rho;
             SPCSC_UNROLL
             for (int i = 0; i < HPT; ++i) {
                 const int h = tg + NTG * i;
@@ -647,8 +685,8 @@ k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                     for (unsigned rk = 0; rk < cs; ++rk)
                         s = s + ((rk == cr) ? mine[i] : recv[((size_t)par * cs + rk) * N0 + h]);
                     const C2<T> d = pre[par * N0 + h] - s;
-                    const T den = gram[h].re + rho;
-                    const C2<T> q = mk<T>(d.re / den, d.im / den);
+                    const T inv = (T)1 / (gram[h].re + rho);
+                    const C2<T> q = mk<T>(d.re * inv, d.im * inv);
                     if (a.dfid_on && cr == 0) dsum[0] += wgt_wf * (double)abs2(q);
                     qbuf[h] = q;
                 }
@@ -666,7 +704,18 @@ k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
             else
                 fft_regs<T, N0, E, true>(v, xbuf + g * XP, stw_s, t);
             __syncwarp();
-            if (have) {
+            if constexpr (TST) {
+                if (have) {
+                    SPCSC_UNROLL
+                    for (int p = 0; p < E; ++p) xbuf[g * XP + t + TPF * p] = v[p];
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (have && t == 0) {
+                    bulk_store(out + slab + (size_t)(col0 + g) * N0, xbuf + g * XP, (unsigned)(N0 * sizeof(C2<T>)));
+                    bulk_store_commit();
+                }
+            } else if (have) {
                 C2<T>* dst = out + slab + (size_t)(col0 + g) * N0;
                 SPCSC_UNROLL
                 for (int p = 0; p < E; ++p) dst[t + TPF * p] = v[p];
@@ -676,6 +725,7 @@ k_col5(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
         ++ndf;
         L = segend;
     }
+    if constexpr (TST) bulk_store_wait_all();
     if (a.dfid_on) block_accumulate<1>(dsum, red, acc + ACC_DFID);
 }
 

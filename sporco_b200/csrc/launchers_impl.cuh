@@ -5,6 +5,8 @@
 
 #include <cstdlib>
 #include <string>
+#include <vector>
+#include <cstdio>
 
 namespace spcsc {
 
@@ -365,20 +367,55 @@ static bool col4_go(ColLaunch<T>& c, const C2<T>* stw, cudaError_t& result) {
         const long long total = (long long)c.a.N1f * c.nb;
         const int use = (long long)ncl < total ? ncl : (int)total;
         g_col_variant = 6;
+#ifndef SPCSC_EMU
+        if constexpr (N0 == 256 && sizeof(T) == 4) {
+            // diagnosis only (SPCSC_COL4_DBG=1): cycles per phase of two probe threads per CTA, printed once
+            static int dbg_left = getenv("SPCSC_COL4_DBG") ? atoi(getenv("SPCSC_COL4_DBG")) : 0;
+            if (dbg_left > 0) {
+                --dbg_left;
+                auto kd = k_col4<T, N0, E, NT, true>;
+                cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+                unsigned* dbg = nullptr;
+                const size_t nw = (size_t)use * cs * 2 * 13;
+                cudaMalloc(&dbg, nw * sizeof(unsigned));
+                cudaMemset(dbg, 0, nw * sizeof(unsigned));
+                result = launch_cluster(kd, dim3(use * cs, 1), dim3(NT), cs, smem4, c.stream, c.in, c.out, c.Df,
+                                        c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, dbg);
+                cudaStreamSynchronize(c.stream);
+                std::vector<unsigned> hbuf(nw);
+                cudaMemcpy(hbuf.data(), dbg, nw * sizeof(unsigned), cudaMemcpyDeviceToHost);
+                cudaFree(dbg);
+                for (int probe = 0; probe < 2; ++probe) {
+                    double tot[12] = {0};
+                    double ns = 0;
+                    for (int bk = 0; bk < (int)(use * cs); ++bk) {
+                        const unsigned* o = hbuf.data() + ((size_t)bk * 2 + probe) * 13;
+                        for (int i = 0; i < 12; ++i) tot[i] += o[i];
+                        ns += o[12];
+                    }
+                    fprintf(stderr, "k_col4 phases (probe %d, cycles per slab, %g slabs):", probe, ns);
+                    double sum = 0;
+                    for (int i = 0; i < 12; ++i) { fprintf(stderr, " %.0f", tot[i] / ns); sum += tot[i] / ns; }
+                    fprintf(stderr, " | total %.0f\n", sum);
+                }
+                return true;
+            }
+        }
+#endif
         result = launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem4, c.stream, c.in, c.out, c.Df,
-                                c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb);
+                                c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, (unsigned*)nullptr);
         return true;
     }
 }
 
 // k_col5 launch (single-channel dictionaries): independent thread groups sharing the staged dictionary columns
-template <typename T, int N0, int E>
+template <typename T, int N0, int E, int NGRP, bool TST = false>
 static bool col5_go(ColLaunch<T>& c, const C2<T>* stw, cudaError_t& result) {
-    constexpr int NT = kCol4Threads, NGRP = 2, TPF = N0 / E, NGG = (NT / NGRP) / TPF;
+    constexpr int NT = kCol4Threads, TPF = N0 / E, NGG = (NT / NGRP) / TPF;
     if constexpr (NGG < 1) {
         return false;
     } else {
-        auto kern = k_col5<T, N0, E, NT, NGRP>;
+        auto kern = k_col5<T, N0, E, NT, NGRP, TST>;
         const unsigned cs = (unsigned)((c.a.M + NGG - 1) / NGG);
         if (cs > 8) return false;
         const size_t smem5 = col5_smem_bytes<T, N0, E, NT, NGRP>((int)cs);
@@ -394,7 +431,7 @@ static bool col5_go(ColLaunch<T>& c, const C2<T>* stw, cudaError_t& result) {
         const int use = (long long)ncl < total ? ncl : (int)total;
         static int stagger = -1;
         if (stagger < 0) stagger = getenv("SPCSC_COL5_STAGGER") ? atoi(getenv("SPCSC_COL5_STAGGER")) : 0;
-        g_col_variant = 7;
+        g_col_variant = NGRP == 1 ? 8 + (TST ? 1 : 0) : 7;
         result = launch_cluster(kern, dim3(use * cs, 1), dim3(NT), cs, smem5, c.stream, c.in, c.out, c.Df,
                                 c.Sf, c.G, c.st, c.acc, stw, c.a, c.nb, stagger);
         return true;
@@ -436,10 +473,18 @@ static cudaError_t col2_go(int mode, ColLaunch<T>& c, const C2<T>* stw) {
         }
         if (c.push == 5) {          // k_col5: the same with two independent thread groups per CTA
             cudaError_t e5 = cudaErrorInvalidValue;
-            if (col5_go<T, N0, E>(c, stw, e5)) return e5;
+            if (col5_go<T, N0, E, 2>(c, stw, e5)) return e5;
+        }
+        if (c.push == 6) {          // one group: k_col4's shape with the stage twiddles in registers
+            cudaError_t e5 = cudaErrorInvalidValue;
+            if (col5_go<T, N0, E, 1>(c, stw, e5)) return e5;
+        }
+        if (c.push == 7) {          // ... and the result leaving by bulk copies (TMA stores)
+            cudaError_t e5 = cudaErrorInvalidValue;
+            if (col5_go<T, N0, E, 1, true>(c, stw, e5)) return e5;
         }
     }
-    if (c.push && c.push != 4 && c.push != 5 && !c.bulk) {
+    if (c.push && (c.push < 4 || c.push > 7) && !c.bulk) {
         // k_col3: persistent clusters over (frequency column, run of images) items; the per-frequency sums
         // travel by st.async pushes instead of cluster barriers.  push == 2 (float32): the two columns of a lane
         // group are transformed together, exchanging 16-byte elements

@@ -186,6 +186,12 @@ inline void bulk_copy(void* dst, const void* src, unsigned bytes, mbar_t* bar) {
 inline void mbar_wait(mbar_t* bar, unsigned parity) {
     while (reinterpret_cast<EmuBar*>(bar)->phase == (unsigned char)parity) emu::yield();
 }
+// bulk copy shared -> global (TMA store), tracked by the issuing thread's bulk group
+inline void fence_async_smem() {}
+inline void bulk_store(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
+inline void bulk_store_commit() {}
+inline void bulk_store_wait_read() {}
+inline void bulk_store_wait_all() {}
 #else
 SPCSC_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 SPCSC_DEV void mbar_init(mbar_t* bar, unsigned count) {
@@ -212,6 +218,19 @@ SPCSC_DEV void bulk_copy(void* dst, const void* src, unsigned bytes, mbar_t* bar
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// ---- bulk copy shared -> global (TMA store), tracked by the issuing thread's bulk group -----------------
+// generic-proxy writes to shared memory become visible to the asynchronous proxy (call before the barrier that
+// precedes bulk_store)
+SPCSC_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+SPCSC_DEV void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+SPCSC_DEV void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's stores have finished READING shared memory (the source may be overwritten)
+SPCSC_DEV void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+SPCSC_DEV void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 SPCSC_DEV void mbar_wait(mbar_t* bar, unsigned parity) {
     unsigned done = 0;
     while (!done) {

@@ -557,7 +557,11 @@ class Engine : public spcsc_handle {
         // persistent clusters + bulk-copy prefetch: measured no faster than one slab per cluster
         // (the kernel is issue-bound, not load-bound), so it stays opt-in
         c.bulk = (getenv("SPCSC_COLBULK") && atoi(getenv("SPCSC_COLBULK")) == 1) ? 1 : 0;
-        c.push = getenv("SPCSC_COL3") ? atoi(getenv("SPCSC_COL3")) : 0;     // 1: k_col3, 2: with paired transforms
+        // ADMM column kernel: 6 (default) k_col5 with one thread group -- slab, dictionary columns and signal row
+        // staged by bulk copies, stage twiddles in registers; falls back to k_col2 (0) when the staged layout does
+        // not fit or the dictionary has several channels.  1/2/3/11/12 k_col3 variants, 4 k_col4, 5 k_col5 with
+        // two independent groups, 7 with bulk-copy stores
+        c.push = getenv("SPCSC_COL3") ? atoi(getenv("SPCSC_COL3")) : 6;
         c.prefetch = getenv("SPCSC_COL3_PF") ? atoi(getenv("SPCSC_COL3_PF")) : 0;
         return c;
     }

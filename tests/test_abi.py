@@ -73,6 +73,7 @@ def test_hot_kernels_do_not_spill():
     out = subprocess.run([cuobjdump, '-res-usage', build.build()], stdout=subprocess.PIPE,
                          stderr=subprocess.DEVNULL, text=True).stdout.splitlines()
     hot = {'k_col2IfLi256ELi16ELi2ELi256ELi1ELb1ELi1ELb1ELb0': 128,        # 2 CTAs of 256 threads per SM
+           'k_col5IfLi256ELi16ELi512ELi1ELb0E': 128,                       # 1 CTA of 512 threads per SM
            'k_row_inv_prox3IfLi128ELi16ELi1ELi128ELb1': 128}               # 4 CTAs of 128 threads per SM
     seen = set()
     for i, line in enumerate(out):

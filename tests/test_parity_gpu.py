@@ -150,13 +150,13 @@ def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
 
 
 @pytest.mark.parametrize('case', [cases.FRESH_CASES[0], cases.FRESH_CASES[2], (64, 64, 8, 5, None, None, None)])
-@pytest.mark.parametrize('pair', [False, True, 'cpg1', 'col4', 'col5'])
+@pytest.mark.parametrize('pair', [False, True, 'cpg1', 'col4', 'col5', 'col6', 'col7'])
 def test_push_exchange_column_kernel_vs_oracle(case, pair, monkeypatch):
     """k_col3 (persistent clusters, sums pushed over DSMEM) against the oracle and against k_col2."""
-    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3', 'col4': '4', 'col5': '5'}[pair])
+    monkeypatch.setenv('SPCSC_COL3', {False: '1', True: '2', 'cpg1': '3', 'col4': '4', 'col5': '5', 'col6': '6', 'col7': '7'}[pair])
     N0, N1, M, K, C, mu, extra = case
     b, _ = cases.run_fresh_case(N0, N1, M, K, C=C, mu=mu, extra=extra)
-    want = {False: 3, True: 4, 'cpg1': 5, 'col4': 6, 'col5': 7}[pair]
+    want = {False: 3, True: 4, 'cpg1': 5, 'col4': 6, 'col5': 7, 'col6': 8, 'col7': 9}[pair]
     if pair == 'col5' and N0 > 256:
         want = 2        # 512-point columns do not fit two groups' stages: k_col2 takes over
     assert b._h.admm_schedule_info()['col_kernel'] == want
