@@ -235,6 +235,22 @@ int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out);
 /* xstep.setdict(dstep.getdict()) on the device (dictlrn.py:386-389): Df <- Xf. */
 int spcsc_ccmod_push_dict(spcsc_handle* h);
 
+/* ---- consensus dictionary update: sporco.admm.ccmod.ConvCnstrMOD_Consensus (sporco/admm/ccmod.py:613-911 over
+   ADMMConsensus, sporco/admm/admm.py:1419-1707) on the same handle and the same dictionary / coefficient state as
+   the PGM update above (spcsc_ccmod_reset sets Y0, spcsc_ccmod_setcoef* the coefficient maps, spcsc_ccmod_get_dict /
+   _push_dict read the consensus variable Y).  One block per (image, coefficient channel).
+   spcsc_ccmod_cns_init: U_i = Y0 / rho when a Y0 was given, else 0 (ccmod.py:739-750); nb_global = number of
+   blocks over all ranks when the images are sharded (0: this handle holds them all).
+   spcsc_ccmod_cns_step: one iteration -- xstep (:787-813: solvedbi_sm per block against its coefficient spectra),
+   relax_AX (admm.py:1608-1616, rlx = RelaxParam), ystep (admm.py:1585-1591 with prox_g = Pcn, ccmod.py:842-846),
+   ustep -- with U read as U / udiv (the lazy form of U /= rsf after a change of rho, admm.py:549-575).
+   out[]: [0] DFid on Y (ccmod.py:884-892 with fEvalX False), [1] Cnstr = ||Pcn(Y) - Y|| (:895-902),
+   [2] ||X||^2, [3] ||X - Y||^2, [4] ||U||^2, [5] ||Y||^2, [6] ||Yprev - Y||^2 (the host forms the residuals of
+   admm.py:1673-1707 from them), [7] reserved.  flags as for spcsc_ccmod_step.  With images sharded over ranks the
+   filter supports of the block mean and the norms are summed over the ranks (peer memory / NCCL). */
+int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global);
+int spcsc_ccmod_cns_step(spcsc_handle* h, double rho, double udiv, double rlx, int32_t flags, double out[8]);
+
 /* ---- multi-GPU: images are sharded over ranks (one process per GPU); the only exchange of
    the path is the all-reduce of the residual / objective sums that drive the shared rho and the
    stopping test (admm/admm.py:462-486 are global over all K images).  NCCL is resolved at run

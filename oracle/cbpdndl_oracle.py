@@ -200,3 +200,169 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
     out['X'] = Y
     out['time'] = time.perf_counter() - t0
     return out
+
+
+# =====================================================================================
+# Consensus dictionary update: sporco.admm.ccmod.ConvCnstrMOD_Consensus (sporco/admm/ccmod.py:613-911)
+# on ADMMConsensus / ADMM (sporco/admm/admm.py:293-389, 434-486, 549-575, 1419-1707).
+# =====================================================================================
+CNS_DEFAULTS = {
+    'MaxMainIter': 1000, 'rho': None, 'RelaxParam': 1.8, 'ZeroMean': False, 'Y0': None,
+    'RelStopTol': 1e-3, 'AbsStopTol': 0.0,
+    'AutoRho': {'Enabled': False, 'Period': 10, 'Scaling': 2.0, 'RsdlRatio': 10.0, 'RsdlTarget': 1.0,
+                'AutoScaling': False, 'StdResiduals': False},
+}
+
+
+class ConsensusCCMOD(object):
+    """State and iteration of ConvCnstrMOD_Consensus (objective on the consensus variable: AuxVarObj True,
+    the class default).  S: (N0, N1, K) or (N0, N1, C, K); coefficient maps Z: (N0, N1, Cx, K, M); dsz =
+    (h, w, M) or (h, w, Cd, M).  `reduce`, if given, maps a float64 array of local sums to global sums (blocks
+    sharded over ranks: the supports of the block mean and the squared norms are summed)."""
+
+    def __init__(self, S, dsz, opt=None, fft=None, reduce=None, nb_global=None):
+        self.fft = fft or co.FFTBackend()
+        o = {k: (dict(v) if isinstance(v, dict) else v) for k, v in CNS_DEFAULTS.items()}
+        for k, v in (opt or {}).items():
+            if k == 'AutoRho':
+                o[k].update(v)
+            else:
+                o[k] = v
+        self.o = o
+        self.reduce = reduce
+        self.dtype = np.dtype(S.dtype)
+        self.rdt = co._rdt(self.dtype)
+        self.dsz = dsz
+        self.Cd = dsz[2] if len(dsz) == 4 else 1
+        self.C = S.shape[2] if S.ndim == 4 else 1
+        self.N0, self.N1, self.K = S.shape[0], S.shape[1], S.shape[-1]
+        self.M = dsz[-1]
+        self.Nv = (self.N0, self.N1)
+        N0, N1, C, K, Cd, M = self.N0, self.N1, self.C, self.K, self.Cd, self.M
+        self.Nb = (K if C == Cd else C * K)                      # local blocks (ccmod.py:684-686)
+        self.NbG = self.Nb if nb_global is None else int(nb_global)     # blocks over all ranks
+        Sm = np.asarray(S.reshape(N0, N1, C, K, 1), dtype=self.dtype)
+        if Cd == 1 and C > 1:
+            Sm = Sm.reshape(N0, N1, 1, C * K, 1)
+        self.S = Sm
+        self.Sf = self.fft.rfftn(Sm, None, (0, 1))
+        # NB the reference means the number of images as default (ccmod.py:691-692) but ADMM.__init__ has already
+        # set rho = 1 (admm.py:247) and set_attr keeps a value that is set: the effective default is 1
+        self.rho = self.rdt.type(1.0 if o['rho'] is None else o['rho'])
+        self.rlx = self.rdt.type(o['RelaxParam'])
+        yshape = (N0, N1, Cd, 1, M)
+        self.Nx = self.NbG * int(np.prod(yshape))
+        self.Nc = self.Nx
+        if o['Y0'] is None:
+            self.Y = np.zeros(yshape, self.dtype)
+            self.U = np.zeros(yshape + (self.Nb,), self.dtype)
+        else:
+            self.Y = np.asarray(o['Y0'], dtype=self.dtype).reshape(yshape)
+            self.U = (np.repeat(self.Y[..., np.newaxis], self.Nb, axis=-1) / self.rho).astype(self.dtype)
+        self.k = 0
+        self.itstat = []
+
+    def setcoef(self, Z):
+        N0, N1, C, K, Cd, M = self.N0, self.N1, self.C, self.K, self.Cd, self.M
+        Cx = C - Cd + 1
+        Z = np.asarray(Z, dtype=self.dtype).reshape(N0, N1, Cx, K, M)
+        if Cd == 1 and C > 1:
+            Z = Z.reshape(N0, N1, 1, Cx * K, M)
+        self.Zf = self.fft.rfftn(Z, self.Nv, (0, 1))
+        self.ZSf = np.conj(self.Zf) * self.Sf
+
+    def _pcn(self, x):
+        return pcn(x, self.dsz, self.Nv, zm=self.o['ZeroMean'])
+
+    def step(self):
+        """One pass of the loop body of ADMM.solve (admm.py:331-377).  Returns True when the stopping
+        test fires."""
+        fft, o, ar = self.fft, self.o, self.o['AutoRho']
+        rdt, Nb = self.rdt, self.Nb
+        axN, axK, axM = (0, 1), 3, 4
+        Yprev = self.Y.copy()
+        # xstep (ccmod.py:787-813; the per-block form of xistep :825-838 is the same arithmetic)
+        YU = self.Y[..., np.newaxis] - self.U
+        X = np.empty_like(self.U)
+        for i in range(Nb):
+            b = np.take(self.ZSf, [i], axis=axK) + self.rho * fft.rfftn(YU[..., i], None, axN)
+            Xf = co.solvedbi_sm(np.take(self.Zf, [i], axis=axK), self.rho, b, axM)
+            X[..., i] = fft.irfftn(Xf, self.Nv, axN)
+        # relax_AX (admm.py:1608-1616)
+        AX = X if self.rlx == 1.0 else self.rlx * X + (1 - self.rlx) * self.Y[..., np.newaxis]
+        # ystep (admm.py:1585-1591) with prox_g = Pcn
+        if self.reduce is None:
+            mAXU = np.mean(AX + self.U, axis=-1)
+        else:       # blocks sharded over ranks: only the filter supports of the mean are exchanged
+            loc = np.sum((AX + self.U).astype(np.float64), axis=-1) / self.NbG
+            h, w = self.dsz[0], self.dsz[1]
+            supp = self.reduce(loc[0:h, 0:w].copy())
+            mAXU = np.zeros(self.Y.shape, self.dtype)
+            mAXU[0:h, 0:w] = supp.astype(self.dtype)
+        self.Y = self._pcn(np.asarray(mAXU, dtype=self.dtype))
+        # ustep (admm.py:434-437)
+        self.U = self.U + (AX - self.Y[..., np.newaxis])
+        # compute_residuals (admm.py:462-486 with ADMMConsensus.rsdl_* :1673-1707)
+        if self.reduce is None:
+            nX, nU = np.linalg.norm(X), np.linalg.norm(self.U)
+            nR = np.linalg.norm(X - self.Y[..., np.newaxis])
+        else:
+            g = self.reduce(np.array([np.sum(a.astype(np.float64) ** 2)
+                                      for a in (X, self.U, X - self.Y[..., np.newaxis])]))
+            nX, nU, nR = [rdt.type(np.sqrt(v)) for v in g]
+        nY = np.linalg.norm(self.Y)
+        sNb = np.sqrt(self.NbG)
+        r = nR
+        s = np.linalg.norm(sNb * self.rho * (Yprev - self.Y))
+        rn = max(nX, sNb * nY)
+        sn = self.rho * nU
+        if ar['StdResiduals']:
+            epri = np.sqrt(self.Nc) * o['AbsStopTol'] + rn * o['RelStopTol']
+            edua = np.sqrt(self.Nx) * o['AbsStopTol'] + sn * o['RelStopTol']
+        else:
+            rn = 1.0 if rn == 0.0 else rn
+            sn = 1.0 if sn == 0.0 else sn
+            r = r / rn
+            s = s / sn
+            epri = np.sqrt(self.Nc) * o['AbsStopTol'] / rn + o['RelStopTol']
+            edua = np.sqrt(self.Nx) * o['AbsStopTol'] / sn + o['RelStopTol']
+        # objective on Y (ccmod.py:861-902 with fEvalX False, gEvalY True)
+        Yf = fft.rfftn(self.Y, None, axN)
+        Ef = co.inner(self.Zf, Yf, axM) - self.Sf
+        dfd = co.rfl2norm2(Ef, self.S.shape, axis=axN) / 2.0
+        if self.reduce is not None:
+            dfd = self.reduce(np.array([dfd], dtype=np.float64))[0]
+        cns = np.linalg.norm(self._pcn(self.Y) - self.Y)
+        self.itstat.append((self.k, float(dfd), float(cns), float(r), float(s), float(epri), float(edua),
+                            float(self.rho)))
+        # update_rho (admm.py:549-575)
+        if ar['Enabled'] and self.k != 0 and np.mod(self.k + 1, ar['Period']) == 0:
+            tau, mu, xi = rdt.type(ar['Scaling']), rdt.type(ar['RsdlRatio']), rdt.type(ar['RsdlTarget'])
+            if ar['AutoScaling']:
+                if s == 0.0 or r == 0.0:
+                    mlt = tau
+                else:
+                    mlt = np.sqrt(r / (s * xi) if r > s * xi else (s * xi) / r)
+                    if mlt > tau:
+                        mlt = tau
+            else:
+                mlt = tau
+            rsf = 1.0
+            if r > xi * mu * s:
+                rsf = mlt
+            elif s > (mu / xi) * r:
+                rsf = 1.0 / mlt
+            self.rho = self.rho * rdt.type(rsf)
+            self.U = (self.U / rsf).astype(self.dtype, copy=False)
+        stop = bool(r < epri and s < edua)
+        self.k += 1
+        return stop
+
+    def solve(self):
+        for _ in range(self.o['MaxMainIter']):
+            if self.step():
+                break
+        return self.Y
+
+    def getdict(self):
+        return self.Y[0:self.dsz[0], 0:self.dsz[1]]

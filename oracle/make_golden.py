@@ -148,6 +148,7 @@ CDL_OPT_ZM = {'MaxMainIter': 20, 'CBPDN': {'NonNegCoef': True},
 
 CDL_OPT_CLR = {'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}},
                'CCMOD': {'L': 60.0, 'ZeroMean': True}}
+CDL_OPT_CNS = {'MaxMainIter': 15, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}
 CDL_OPT_PGMX = {'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}
 
 
@@ -168,11 +169,11 @@ def cdl_case(tag, dt, D0, S, lmbda, opt):
     print('wrote', tag)
 
 
-def cdl_ref_case(tag, dt, D0, S, lmbda, opt, xmethod):
-    """Variants the numpy oracle does not restate (PGM X step, AccurateDFid): the fixture holds
-    the reference's own outputs."""
+def cdl_ref_case(tag, dt, D0, S, lmbda, opt, xmethod, dmethod='pgm'):
+    """Variants the numpy oracle does not restate as a whole (PGM X step, AccurateDFid, consensus D step -- whose
+    D step alone is pinned by cns_case): the fixture holds the reference's own outputs."""
     b = rcbpdndl.ConvBPDNDictLearn(D0, S, lmbda, rcbpdndl.ConvBPDNDictLearn.Options(
-        opt, xmethod=xmethod, dmethod='pgm'), xmethod=xmethod, dmethod='pgm', dimK=1)
+        opt, xmethod=xmethod, dmethod=dmethod), xmethod=xmethod, dmethod=dmethod, dimK=1)
     D1 = b.solve()
     its = b.getitstat()
     out = dict(D0=D0, S=S, lmbda=np.float64(lmbda), D=D1, X=b.getcoef())
@@ -181,6 +182,29 @@ def cdl_ref_case(tag, dt, D0, S, lmbda, opt, xmethod):
             out[name] = stat(its, name)
     np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
     print('wrote', tag, sorted(out))
+
+
+def cns_case(tag, dt, Z, S, dsz, opt):
+    """admm.ccmod.ConvCnstrMOD_Consensus with given coefficient maps (ccmod.py:613-911)."""
+    from sporco.admm import ccmod as rccmod
+    c = rccmod.ConvCnstrMOD_Consensus(Z, S, dsz, rccmod.ConvCnstrMOD_Consensus.Options(dict(opt, Verbose=False)))
+    c.solve()
+    r = orcdl.ConsensusCCMOD(S, dsz, opt)
+    r.setcoef(Z)
+    r.solve()
+    same(c.Y, r.Y, tag + ' Y')
+    its = c.getitstat()
+    ref = np.array(r.itstat, dtype=np.float64)
+    cols = ('DFid', 'Cnstr', 'PrimalRsdl', 'DualRsdl', 'EpsPrimal', 'EpsDual', 'Rho')
+    for i, name in enumerate(cols):
+        same(stat(its, name), ref[:, i + 1], tag + ' ' + name)
+    out = dict(Z=Z, S=S, dsz=np.array(dsz), Y=c.Y)
+    out.update({name: stat(its, name) for name in cols})
+    for k, v in opt.items():
+        if k == 'Y0':
+            out['Y0'] = v
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag)
 
 
 def tikhonov():
@@ -247,6 +271,15 @@ def level1():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = [a[7:] for a in sys.argv[1:] if a.startswith('--only=')]
+    if only:        # every case still runs (the random stream stays the same); only matching fixtures are written
+        prefixes = tuple(only[0].split(','))
+        real_save = np.savez_compressed
+
+        def filtered(path, **kw):
+            if os.path.basename(path).startswith(prefixes):
+                real_save(path, **kw)
+        np.savez_compressed = filtered
     level1()
     tikhonov()
     for dt, sfx in ((np.float64, 'f64'), (np.float32, 'f32')):
@@ -321,6 +354,16 @@ def main():
         cdl_case('cdl_clr3_' + sfx, dt, D0c, Sc, 0.1, CDL_OPT_CLR)     # colour dictionary
         cdl_ref_case('cdl_accdfid_' + sfx, dt, D0, S4, 0.1, dict(CDL_OPT, AccurateDFid=True), 'admm')
         cdl_ref_case('cdl_pgmx_' + sfx, dt, D0, S4, 0.1, CDL_OPT_PGMX, 'pgm')
+        # consensus dictionary update: alone (oracle pinned) and as the D step of dictionary learning
+        Zc = rng.standard_normal((32, 32, 1, 3, 6)).astype(dt)
+        Zc[np.abs(Zc) < 1.0] = 0
+        Sc3 = rng.standard_normal((32, 32, 3)).astype(dt)
+        cns_case('cns_zm_' + sfx, dt, Zc, Sc3, (5, 5, 6), {'MaxMainIter': 15, 'ZeroMean': True})
+        cns_case('cns_arho_' + sfx, dt, Zc, Sc3, (5, 5, 6),
+                 {'MaxMainIter': 15, 'rho': 2.0, 'AutoRho': {'Enabled': True, 'Period': 3, 'AutoScaling': True,
+                                                              'Scaling': 10.0}})
+        cdl_ref_case('cdl_cns_' + sfx, dt, D0, S4, 0.1, CDL_OPT_CNS, 'admm', 'cns')
+        cdl_ref_case('cdl_cns_clr1_' + sfx, dt, D0, Sc, 0.1, CDL_OPT_CNS, 'admm', 'cns')
 
 
 if __name__ == '__main__':

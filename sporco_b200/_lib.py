@@ -32,6 +32,7 @@ SYMBOLS = (
     'spcsc_pgm_accept', 'spcsc_pgm_policy_stats', 'spcsc_pgm_combine_y', 'spcsc_pgm_finish', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
     'spcsc_p2p_attach', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
+    'spcsc_ccmod_cns_init', 'spcsc_ccmod_cns_step',
 )
 
 
@@ -126,6 +127,9 @@ def _declare(lib):
     lib.spcsc_ccmod_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, i32, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_ccmod_get_dict.argtypes = [vp, vp]
     lib.spcsc_ccmod_push_dict.argtypes = [vp]
+    lib.spcsc_ccmod_cns_init.argtypes = [vp, ctypes.c_double, i32, ctypes.c_int64]
+    lib.spcsc_ccmod_cns_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, i32,
+                                         ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
     lib.spcsc_comm_create.argtypes = [ctypes.c_char_p, vp, i32, i32, i32, ctypes.POINTER(vp)]
     lib.spcsc_comm_destroy.argtypes = [vp]
@@ -408,6 +412,14 @@ class Handle(object):
 
     def ccmod_push_dict(self):
         self._c(self.lib.spcsc_ccmod_push_dict(self.h))
+
+    def ccmod_cns_init(self, rho, y0_given, nb_global=0):
+        self._c(self.lib.spcsc_ccmod_cns_init(self.h, float(rho), 1 if y0_given else 0, int(nb_global)))
+
+    def ccmod_cns_step(self, rho, udiv, rlx, flags=3):
+        out = (ctypes.c_double * 8)()
+        self._c(self.lib.spcsc_ccmod_cns_step(self.h, float(rho), float(udiv), float(rlx), int(flags), out))
+        return [float(x) for x in out]
 
     def p2p_export(self):
         buf = ctypes.create_string_buffer(64)

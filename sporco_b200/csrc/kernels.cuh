@@ -334,6 +334,11 @@ struct ColArgs {
     int gradreg;           // k_col SOLVE 1 / 4: ConvBPDNGradReg (G.im = GHG, sumin[m] = (mu w_m, w_m))
     int pgm_mask;          // k_col SOLVE 2 / 4: masked data fidelity (pgm.ConvBPDNMask): the residual spectra
                            // W^2-filtered in the signal domain arrive ready made (SOLVE 2: sumin, SOLVE 4: G)
+    // consensus dictionary update (admm.ccmod.ConvCnstrMOD_Consensus): every slab b has its OWN "dictionary" --
+    // the coefficient spectra of block b / df_bdiv -- and Gram row: Df + (b / df_bdiv) df_bstride, likewise G.
+    // 0: one dictionary shared by all slabs (ConvBPDN)
+    long long df_bstride, g_bstride;
+    int df_bdiv;
 };
 
 template <typename T, int MAXCD>
@@ -481,6 +486,11 @@ SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(sizeof(T) == 4 ? 1024 : 512) k_col(const C
     const int tid = threadIdx.x, nt = blockDim.x;
     const int wf = blockIdx.x, b = blockIdx.y;
     const int M = a.M, Cd = a.Cd, MC = a.MC;
+    if (a.df_bstride) {                      // per-slab dictionary (consensus dictionary update)
+        const size_t ib = (size_t)(b / a.df_bdiv);
+        Df += ib * (size_t)a.df_bstride;
+        G += ib * (size_t)a.g_bstride;
+    }
     C2<T>* buf = reinterpret_cast<C2<T>*>(smem_raw);                 // [MC][N0]
     C2<T>* buf2 = buf + (size_t)MC * N0;                              // [MC][N0], direct-DFT path only
     C2<T>* spart = buf + (size_t)MC * N0 * (GEN ? 2 : 1);             // [Cd][parts][N0]

@@ -852,14 +852,17 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
     for (; tile < a.ntiles; tile += tstep) {
     const int wf = tile % a.N1f, b = tile / a.N1f;
     const size_t slab = (((size_t)b * a.N1f + wf) * M) * N0;
-    const C2<T>* dfw = Df + ((size_t)wf * M) * N0;
+    // per-slab dictionary and Gram row (consensus dictionary update), else shared by all slabs
+    const C2<T>* Dfb = a.df_bstride ? Df + (size_t)(b / a.df_bdiv) * (size_t)a.df_bstride : Df;
+    const C2<T>* Gb = a.df_bstride ? G + (size_t)(b / a.df_bdiv) * (size_t)a.g_bstride : G;
+    const C2<T>* dfw = Dfb + ((size_t)wf * M) * N0;
     if constexpr (SOLVE != 0 && CD == 1) {
         // the solve needs one signal and one Gram value per frequency: start fetching them now, so
         // that their L2 latency is not exposed between the two cluster barriers
         const int kk = b / a.Cx, cxx = b - kk * a.Cx;
         for (int h = tid; h < N0; h += NT) {
             cp_async<sizeof(C2<T>)>(pre + h, Sf + (((size_t)kk * a.Cs + cxx) * a.N1f + wf) * N0 + h);
-            if (SOLVE == 1) cp_async<sizeof(C2<T>)>(pre + N0 + h, G + (size_t)wf * N0 + h);
+            if (SOLVE == 1) cp_async<sizeof(C2<T>)>(pre + N0 + h, Gb + (size_t)wf * N0 + h);
         }
         cp_async_commit();
     }
@@ -967,7 +970,7 @@ k_col2(const C2<T>* SPCSC_RESTRICT in, C2<T>* SPCSC_RESTRICT out, const C2<T>* S
                 dv[0] = mk<T>(dv[0].re / den, dv[0].im / den);
             } else {
                 C2<T> A[CD][CD];
-                const C2<T>* Gp = G + ((size_t)wf * N0 + h) * CD * CD;
+                const C2<T>* Gp = Gb + ((size_t)wf * N0 + h) * CD * CD;
                 SPCSC_UNROLL
                 for (int i = 0; i < CD; ++i) {
                     SPCSC_UNROLL

@@ -195,4 +195,97 @@ SPCSC_GLOBAL void k_crop_dict(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT D, in
     }
 }
 
+// =====================================================================================
+// Consensus dictionary update: sporco.admm.ccmod.ConvCnstrMOD_Consensus (sporco/admm/ccmod.py:613-911 over
+// sporco/admm/admm.py:1419-1707).  One block i per (image, coefficient channel) with its own copy X_i of the
+// dictionary, dual U_i, and the consensus variable Y = the constrained dictionary:
+//   x step   Xf_i = solvedbi_sm(Zf_i, rho, conj(Zf_i) Sf_i + rho rfftn(Y - U_i))      ccmod.py:787-813
+//            = the ConvBPDN column kernel with the coefficient spectra of block i as its "dictionary"
+//              (ColArgs::df_bstride), i.e. the roles of the images and the filters swapped
+//   relax    AX_i = alpha X_i + (1 - alpha) Y                                          admm.py:1608-1616
+//   y step   Y = Pcn(mean_i (AX_i + U_i))                                              admm.py:1585-1591
+//            Pcn = normalise . zpad . bcrop (cnvrep.py:953-1033) and bcrop is linear: only the filter SUPPORTS of
+//            the mean are formed (k_cns_support_mean) -- with images sharded over GPUs that is also all that is
+//            exchanged
+//   u step   U_i += AX_i - Y                                                           admm.py:434-437
+//   norms    ||X||, ||X - Y||, ||U||, ||Y||, ||Yprev - Y|| for rsdl_r / rsdl_s / rsdl_rn / rsdl_sn  admm.py:1673-1707
+// Device layout: X, U [NB][M][N0][N1] with batch index bb = (image, channel); Y [Cd][M][N0][N1] (bb % Cd is the
+// dictionary channel of batch bb; Cd == 1: the signal channels count as further blocks, ccmod.py:697-705).
+// =====================================================================================
+enum { ACC_CNS_X2 = 8, ACC_CNS_R2 = 9, ACC_CNS_U2 = 10, ACC_CNS_Y2 = 11, ACC_CNS_S2 = 12 };
+
+// W[bb] = Y[bb % Cd] - U[bb] * uinv     (U /= rsf of a change of rho is applied lazily: uinv = 1 / udiv)
+template <typename T>
+SPCSC_GLOBAL void k_cns_yu(const T* SPCSC_RESTRICT Y, const T* SPCSC_RESTRICT U, T* SPCSC_RESTRICT W, int NB,
+                           int Cd, size_t plane, T uinv) {
+    const size_t n = (size_t)NB * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bb = i / plane, o = i - bb * plane;
+        W[i] = Y[(bb % Cd) * plane + o] - U[i] * uinv;
+    }
+}
+
+// U[bb] = Y[bb % Cd] * s   (uinit with a given Y0: U = Y / rho for every block, ccmod.py:739-750)
+template <typename T>
+SPCSC_GLOBAL void k_cns_uinit(const T* SPCSC_RESTRICT Y, T* SPCSC_RESTRICT U, int NB, int Cd, size_t plane, T s) {
+    const size_t n = (size_t)NB * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bb = i / plane, o = i - bb * plane;
+        U[i] = Y[(bb % Cd) * plane + o] * s;
+    }
+}
+
+// Filter supports of  sum_{bb = c mod Cd} (alpha X[bb] + U[bb] uinv) * wsum  +  ymul (1 - alpha) Y[c]  written into the
+// supports of V [Cd][M][N0][N1]; wsum = 1 / (number of blocks over all ranks), ymul = 1 / (number of ranks)
+// so that the rank sum of the supports is the global mean.  One CTA per (m, c).
+template <typename T>
+SPCSC_GLOBAL void k_cns_support_mean(const T* SPCSC_RESTRICT X, const T* SPCSC_RESTRICT U, const T* SPCSC_RESTRICT Y,
+                                     T* SPCSC_RESTRICT V, int NB, int Cd, int M, int N0, int N1, int hd, int wd,
+                                     T alpha, T uinv, T wsum, T ymul) {
+    const int m = blockIdx.x, c = blockIdx.y;
+    const size_t img = (size_t)N0 * N1, plane = (size_t)M * img;
+    for (int e = threadIdx.x; e < hd * wd; e += blockDim.x) {
+        const size_t o = (size_t)m * img + (size_t)(e / wd) * N1 + (e % wd);
+        T acc = 0;
+        for (int bb = c; bb < NB; bb += Cd) acc += alpha * X[(size_t)bb * plane + o] + U[(size_t)bb * plane + o] * uinv;
+        V[(size_t)c * plane + o] = acc * wsum + ymul * ((T)1 - alpha) * Y[(size_t)c * plane + o];
+    }
+}
+
+// U[bb] <- U[bb] uinv + alpha X[bb] + (1 - alpha) Yold[c] - Ynew[c], and the sums of X^2, (X - Ynew)^2, Unew^2
+template <typename T>
+SPCSC_GLOBAL void k_cns_update(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT U, const T* SPCSC_RESTRICT Yold,
+                               const T* SPCSC_RESTRICT Ynew, double* SPCSC_RESTRICT acc, int NB, int Cd,
+                               size_t plane, T alpha, T uinv) {
+    __shared__ double red[3 * 32];
+    const size_t n = (size_t)NB * plane;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bb = i / plane, o = (bb % Cd) * plane + (i - bb * plane);
+        const T x = X[i], y0 = Yold[o], y1 = Ynew[o];
+        const T ax = alpha * x + ((T)1 - alpha) * y0;
+        const T u = U[i] * uinv + (ax - y1);
+        U[i] = u;
+        const T r = x - y1;
+        s[0] += (double)x * (double)x;
+        s[1] += (double)r * (double)r;
+        s[2] += (double)u * (double)u;
+    }
+    block_accumulate<3>(s, red, acc + ACC_CNS_X2);
+}
+
+// sums of Ynew^2 and (Yold - Ynew)^2 over the dictionary planes
+template <typename T>
+SPCSC_GLOBAL void k_cns_ynorms(const T* SPCSC_RESTRICT Yold, const T* SPCSC_RESTRICT Ynew, double* SPCSC_RESTRICT acc,
+                               size_t n) {
+    __shared__ double red[2 * 32];
+    double s[2] = {0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const T a = Yold[i], b = Ynew[i];
+        s[0] += (double)b * (double)b;
+        s[1] += (double)(a - b) * (double)(a - b);
+    }
+    block_accumulate<2>(s, red, acc + ACC_CNS_Y2);
+}
+
 }  // namespace spcsc

@@ -315,6 +315,8 @@ struct spcsc_handle {
     virtual int ccmod_step(double L, double coef, int flags, double* out) = 0;
     virtual int ccmod_get_dict(void* out) = 0;
     virtual int ccmod_push_dict() = 0;
+    virtual int ccmod_cns_init(double rho, int y0_given, long long nb_global) = 0;
+    virtual int ccmod_cns_step(double rho, double udiv, double rlx, int flags, double* out) = 0;
 };
 
 namespace {
@@ -403,6 +405,13 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> cdZf;                             // coefficient spectra, slab layout [K][N1f][M][N0]
     bool cd_ready = false, cd_have_coef = false;
     int cd_zero_mean = 0;
+    // consensus dictionary update (admm.ccmod.ConvCnstrMOD_Consensus): per-block copies of the dictionary and
+    // duals [K*C][M][N0][N1], their row/column spectra, the Gram rows of the coefficient spectra, the new Y
+    DevBuf<T> cnsX, cnsU, cnsYn;
+    DevBuf<C2<T>> cnsZ, cnsG;
+    DevBuf<AdmmState<T>> cns_st;
+    bool cns_ready = false, cns_gram_stale = true;
+    long long cns_nb_global = 0;             // blocks over all ranks (the mean of the y step runs over them)
     bool pgm_ready = false, pgm_have_cand = false;
     bool v2_rowf = false, v2_rowp = false, v2_col = false;
     bool gen_rows = false, gen_cols = false;   // any-size direct-DFT path for this axis
@@ -459,6 +468,7 @@ class Engine : public spcsc_handle {
         pgA.release(); pgB.release(); Zt2.release();
         pgZ.release(); pgYp.release(); pg_sx.release(); pg_rprev.release(); pg_sxprev.release();
         cd_supp.release(); cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
+        cnsX.release(); cnsU.release(); cnsYn.release(); cnsZ.release(); cnsG.release(); cns_st.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
 #ifndef SPCSC_EMU
 #endif
@@ -1396,6 +1406,7 @@ class Engine : public spcsc_handle {
         CK(cudaStreamSynchronize(stream));
         cd_zero_mean = zero_mean;
         cd_ready = true;
+        cns_ready = false;
         return SPCSC_OK;
     }
     int ccmod_setcoef_device(int source) override {
@@ -1413,6 +1424,7 @@ class Engine : public spcsc_handle {
             FAIL(SPCSC_ERR_INVALID, "unknown coefficient source");
         }
         cd_have_coef = true;
+        cns_gram_stale = true;
         return SPCSC_OK;
     }
     int ccmod_setcoef(const void* Z) override {
@@ -1427,6 +1439,7 @@ class Engine : public spcsc_handle {
         if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
         cd_have_coef = true;
+        cns_gram_stale = true;
         return SPCSC_OK;
     }
     template <bool GRAD>
@@ -1534,6 +1547,135 @@ class Engine : public spcsc_handle {
         out[1] = std::sqrt(ha[3]);
         out[2] = ha[2] * inv_n;
         out[3] = 0.5 * hF;
+        return SPCSC_OK;
+    }
+    // ---- consensus dictionary update (sporco/admm/ccmod.py:613-911): state and one iteration
+    int ccmod_cns_init(double rho, int y0_given, long long nb_global) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cd_ready) FAIL(SPCSC_ERR_STATE, "ccmod_cns_init before ccmod_reset");
+        if (Cd != 1 && Cd != C) FAIL(SPCSC_ERR_UNSUPPORTED, "dictionary channels must be 1 or the signal's");
+        if (!(rho > 0.0)) FAIL(SPCSC_ERR_INVALID, "rho must be positive");
+        CK(cudaSetDevice(pb.device));
+        const int NB = K * C;
+        const size_t plane = (size_t)M * N0 * N1, nb_real = (size_t)NB * plane;
+        CK(cnsX.ensure(nb_real));
+        CK(cnsU.ensure(nb_real));
+        CK(cnsYn.ensure((size_t)Cd * plane));
+        CK(cnsZ.ensure((size_t)NB * N1f * M * N0));
+        CK(cnsG.ensure((size_t)K * Cx * N1f * N0));
+        CK(cns_st.ensure(1));
+        CK(cudaMemsetAsync(cnsYn.p, 0, (size_t)Cd * plane * sizeof(T), stream));
+        if (y0_given)       // U_i = Y0 / rho for every block (ccmod.py:739-750)
+            CK(launch(k_cns_uinit<T>, dim3(1184), dim3(256), 0, stream, (const T*)cdX.p, cnsU.p, NB, Cd, plane,
+                      (T)(1.0 / rho)));
+        else
+            CK(cudaMemsetAsync(cnsU.p, 0, nb_real * sizeof(T), stream));
+        CK(cudaStreamSynchronize(stream));
+        cns_nb_global = nb_global > 0 ? nb_global : (long long)(NB / Cd);
+        cns_ready = true;
+        return SPCSC_OK;
+    }
+    // out: [0] DFid (on Y), [1] Cnstr (on Y), [2] ||X||^2, [3] ||X - Y||^2, [4] ||U||^2, [5] ||Y||^2, [6] ||Yprev - Y||^2
+    int ccmod_cns_step(double rho, double udiv, double rlx, int flags, double* out) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cns_ready || !cd_have_coef) FAIL(SPCSC_ERR_STATE, "ccmod_cns_step before ccmod_cns_init / setcoef");
+        if (!(rho > 0.0) || !(udiv > 0.0)) FAIL(SPCSC_ERR_INVALID, "rho and udiv must be positive");
+        CK(cudaSetDevice(pb.device));
+        const int NB = K * C;
+        const size_t plane = (size_t)M * N0 * N1, nb_real = (size_t)NB * plane;
+        const T uinv = (T)(1.0 / udiv), alpha = (T)rlx;
+        if (cns_gram_stale) {       // g_i = sum_m |Zf_i,m|^2 for every block's coefficient spectra
+            CK(launch(k_gram<T>, dim3(1024), dim3(128), 0, stream, (const C2<T>*)cdZf.p, cnsG.p, K * Cx * N1f, N0,
+                      M, 1));
+            cns_gram_stale = false;
+        }
+        AdmmState<T> hs;
+        memset(&hs, 0, sizeof(hs));
+        hs.rho = (T)rho; hs.udiv = (T)1; hs.k = 0; hs.stopped = 0; hs.zt_stale = 1; hs.emit = 0;
+        CK(cudaMemcpyAsync(cns_st.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, stream));
+        // x step: rfftn(Y - U_i), the column solve against block i's coefficient spectra, irfftn
+        CK(launch(k_cns_yu<T>, dim3(1184), dim3(256), 0, stream, (const T*)cdX.p, (const T*)cnsU.p, cnsX.p, NB, Cd,
+                  plane, uinv));
+        ColLaunch<T> c = colargs(M, NB);
+        c.in = cnsZ.p; c.out = cnsZ.p;
+        c.Df = cdZf.p; c.G = cnsG.p; c.Sf = Sf.p;
+        c.st = cns_st.p; c.acc = acc.p;
+        c.a.Cd = 1; c.a.Cx = C; c.a.Cs = C;
+        c.a.df_bstride = (long long)N1f * M * N0;
+        c.a.g_bstride = (long long)N1f * N0;
+        c.a.df_bdiv = Cd;
+        c.push = 0; c.bulk = 0;
+        c.Lstep = 0;
+        if (v2_rowf && v2_col && col2_ok<T>(N0, M, 1)) {
+            CK(row_fwd2<T>(H, rowargs(M, NB, 1), (const T*)cnsX.p, (const T*)nullptr,
+                           (const AdmmState<T>*)nullptr, cnsZ.p, (const C2<T>*)stw_row1.p, 0));
+            CK(col2<T>(N0, COL_ADMM, c, (const C2<T>*)stw_col.p));
+        } else {
+            CK(row_fwd<T>(H, rowargs(M, NB, 1), (const T*)cnsX.p, (const T*)nullptr,
+                          (const AdmmState<T>*)nullptr, cnsZ.p));
+            CK(col<T>(N0, COL_ADMM, c));
+        }
+        CK(row_inv<T>(H, rowargs(M, NB, 1), (const C2<T>*)cnsZ.p, cnsX.p, (T)(1.0 / ((double)N0 * (double)N1))));
+        // y step: supports of the mean over all blocks (of all ranks), then the constraint projection
+        const double nb_glob = (double)cns_nb_global;
+        CK(tmp_real.ensure((size_t)Cd * plane));
+        CK(launch(k_cns_support_mean<T>, dim3(M, Cd), dim3(64), 0, stream, (const T*)cnsX.p, (const T*)cnsU.p,
+                  (const T*)cdX.p, tmp_real.p, NB, Cd, M, N0, N1, pb.hd, pb.wd, alpha, uinv, (T)(1.0 / nb_glob),
+                  (T)(1.0 / (double)nranks)));
+        if (nccl_comm) {
+            const int nsupp = pb.hd * pb.wd * Cd * M;
+            CK(cd_supp.ensure((size_t)nsupp + 4));
+            CK(launch(k_support_copy<T>, dim3(64), dim3(256), 0, stream, tmp_real.p, cd_supp.p, Cd * M, N0, N1,
+                      pb.hd, pb.wd, 0));
+            if (p2p_on && nsupp <= kP2pVecMax) {
+                CK(launch(k_p2p_allreduce_vec<T>, dim3(1), dim3(1024), 0, stream, p2p, cd_supp.p, nsupp,
+                          &st.p->stopped));
+            } else {
+                int nr = nccl->AllReduce(cd_supp.p, cd_supp.p, (size_t)nsupp, sizeof(T) == 4 ? 7 : 8, 0, nccl_comm, stream);
+                if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+            }
+            CK(launch(k_support_copy<T>, dim3(64), dim3(256), 0, stream, tmp_real.p, cd_supp.p, Cd * M, N0, N1,
+                      pb.hd, pb.wd, 1));
+        }
+        CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, cnsYn.p, acc.p, Cd, M,
+                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 0));
+        // u step and the norms of the residuals
+        CK(cudaMemsetAsync(acc.p + ACC_CNS_X2, 0, 5 * sizeof(double), stream));
+        CK(launch(k_cns_update<T>, dim3(1184), dim3(256), 0, stream, (const T*)cnsX.p, cnsU.p, (const T*)cdX.p,
+                  (const T*)cnsYn.p, acc.p, NB, Cd, plane, alpha, uinv));
+        rc = reduce_acc_over_ranks();
+        if (rc) return rc;
+        CK(launch(k_cns_ynorms<T>, dim3(296), dim3(256), 0, stream, (const T*)cdX.p, (const T*)cnsYn.p, acc.p,
+                  (size_t)Cd * plane));
+        double hn[5];
+        CK(cudaMemcpyAsync(hn, acc.p + ACC_CNS_X2, 5 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemsetAsync(acc.p + ACC_CNS_X2, 0, 5 * sizeof(double), stream));
+        std::swap(cdX.p, cnsYn.p);
+        std::swap(cdX.n, cnsYn.n);
+        // the new dictionary's spectrum (hand-over to the X step, data fidelity)
+        rc = forward2d(cdX.p, cdXf.p, M, Cd);
+        if (rc) return rc;
+        double ha[4] = {0.0, 0.0, 0.0, 0.0};
+        if (flags & (SPCSC_CCMOD_DFID | SPCSC_CCMOD_CNSTR)) {
+            if (flags & SPCSC_CCMOD_DFID) CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
+            if (nccl_comm && (flags & SPCSC_CCMOD_DFID)) {
+                rc = reduce_acc_over_ranks();
+                if (rc) return rc;
+            }
+            if (flags & SPCSC_CCMOD_CNSTR)
+                CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
+                          N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
+            CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        const double inv_n = 1.0 / ((double)N0 * (double)N1);
+        out[0] = 0.5 * ha[1] * inv_n;
+        out[1] = std::sqrt(ha[3]);
+        out[2] = hn[0]; out[3] = hn[1]; out[4] = hn[2]; out[5] = hn[3]; out[6] = hn[4];
+        out[7] = 0.0;
         return SPCSC_OK;
     }
     int ccmod_get_dict(void* out) override {
@@ -2081,6 +2223,8 @@ int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z) { H_CALL(Z ? h->ccmod_se
 int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]) { H_CALL(out ? h->ccmod_step(L, coef, flags, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
+int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global) { H_CALL(h->ccmod_cns_init(rho, y0_given, (long long)nb_global)); }
+int spcsc_ccmod_cns_step(spcsc_handle* h, double rho, double udiv, double rlx, int32_t flags, double out[8]) { H_CALL(out ? h->ccmod_cns_step(rho, udiv, rlx, flags, out) : SPCSC_ERR_INVALID); }
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {
     if (!id128) { g_last_error = "null id buffer"; return SPCSC_ERR_INVALID; }
     NcclApi& api = nccl_api(nccl_lib);

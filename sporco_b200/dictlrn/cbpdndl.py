@@ -2,13 +2,13 @@
 
 Counterpart of ``sporco.dictlrn.cbpdndl.ConvBPDNDictLearn`` (sporco/dictlrn/cbpdndl.py:231-524):
 alternation of a convolutional sparse coding step (``xmethod`` 'admm' or 'pgm': the ConvBPDN
-solvers of this package) and a PGM dictionary update (``dmethod`` 'pgm':
-:class:`sporco_b200.pgm.ccmod.ConvCnstrMOD`), same constructor, ``Options`` tree
+solvers of this package) and a dictionary update (``dmethod`` 'pgm':
+:class:`sporco_b200.pgm.ccmod.ConvCnstrMOD`, or 'cns': the consensus ADMM update
+:class:`sporco_b200.admm.ccmod.ConvCnstrMOD_Consensus`), same constructor, ``Options`` tree
 (``CBPDN`` / ``CCMOD`` sub-trees, ``DictSize``, ``AccurateDFid``) and ``IterationStats`` fields.
 Both steps share one engine handle: the coefficient maps go from the X step to the D step, and
 the dictionary spectrum back, as device arrays; per outer iteration the host sees the two
-records of scalars only.  The ADMM dictionary updates (``dmethod`` 'ism', 'cg', 'cns') are not
-provided.
+records of scalars only.  The ADMM dictionary updates ``dmethod`` 'ism' and 'cg' are not provided.
 """
 
 import copy
@@ -17,6 +17,7 @@ import numpy as np
 
 from .. import _lib, cdict, cnvrep as cr
 from ..admm import cbpdn as admm_cbpdn
+from ..admm import ccmod as admm_ccmod
 from ..pgm import cbpdn as pgm_cbpdn
 from ..pgm import ccmod as pgm_ccmod
 from . import common as dc
@@ -33,7 +34,9 @@ def cbpdn_class_label_lookup(label):
 def ccmod_class_label_lookup(label):
     if label == 'pgm':
         return pgm_ccmod.ConvCnstrMOD
-    if label in ('ism', 'cg', 'cns'):
+    if label == 'cns':
+        return admm_ccmod.ConvCnstrMOD_Consensus
+    if label in ('ism', 'cg'):
         raise NotImplementedError("dictionary update method '%s' is not provided; use 'pgm'"
                                   % label)
     raise ValueError('Unknown ConvCnstrMOD solver method %s' % label)
@@ -73,14 +76,26 @@ def ConvBPDN(*args, **kwargs):
     return cbpdn_class_label_lookup(method)(*args, **kwargs)
 
 
+_D_OVERRIDES = {
+    'pgm': {'MaxMainIter': 1},
+    'cns': {'MaxMainIter': 1, 'AutoRho': {'Period': 10, 'AutoScaling': False, 'RsdlRatio': 10.0,
+                                          'Scaling': 2.0, 'RsdlTarget': 1.0}},
+}
+
+
 def ConvCnstrMODOptionsDefaults(method='pgm'):
+    """Defaults of the D step inside dictionary learning (dictlrn/cbpdndl.py:139-152)."""
     dflt = copy.deepcopy(ccmod_class_label_lookup(method).Options.defaults)
-    dflt.update({'MaxMainIter': 1})
+    for k, v in _D_OVERRIDES[method].items():
+        if isinstance(v, dict):
+            dflt[k].update(v)
+        else:
+            dflt[k] = v
     return dflt
 
 
 def ConvCnstrMODOptions(opt=None, method='pgm'):
-    o = ccmod_class_label_lookup(method).Options({'MaxMainIter': 1})
+    o = ccmod_class_label_lookup(method).Options(copy.deepcopy(_D_OVERRIDES[method]))
     if opt is not None:
         o.update(cdict._plain(opt))
     return o
@@ -138,7 +153,8 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
         # normalised initial dictionary, also the first iterate of the D step  (cbpdndl.py:448-454)
         D0 = cr.Pcn(np.asarray(D0), dsz, cri.Nv, dimN, cri.dimCd, crp=True,
                     zm=opt['CCMOD', 'ZeroMean'])
-        opt['CCMOD'].update({'X0': cr.zpad(cr.stdformD(D0, cri.Cd, cri.M, dimN), cri.Nv)})
+        optname = 'X0' if dmethod == 'pgm' else 'Y0'
+        opt['CCMOD'].update({optname: cr.zpad(cr.stdformD(D0, cri.Cd, cri.M, dimN), cri.Nv)})
         xstep = ConvBPDN(D0, S, lmbda, opt['CBPDN'], method=xmethod, dimK=dimK, dimN=dimN,
                          device=device)
         dstep = ConvCnstrMOD(None, S, dsz, opt['CCMOD'], method=dmethod, dimK=dimK, dimN=dimN,
@@ -219,6 +235,8 @@ class ConvBPDNDictLearn(dictlrn.DictLearn):
         data-fidelity value, on the device over peer memory (NCCL where peers cannot be mapped), so all
         ranks hold the same dictionary."""
         self.xstep.attach_process_group(dist, group)
+        if self.dmethod == 'cns':       # the block mean of the consensus update runs over all ranks' images
+            self.dstep.attach_process_group(dist, group)
         self._dist = (dist, group)
 
 

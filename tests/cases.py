@@ -411,6 +411,10 @@ CDL_CASES = {
     'cdl_clr3': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}},
                   'CCMOD': {'L': 60.0, 'ZeroMean': True}}, 'admm', 0.1),       # colour dictionary
     'cdl_pgmx': ({'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}, 'pgm', 0.1),
+    # consensus ADMM dictionary update (dmethod 'cns'): greyscale; colour signals with a greyscale dictionary
+    'cdl_cns': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}, 'admm', 0.1, 'cns'),
+    'cdl_cns_clr1': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}, 'admm', 0.1,
+                     'cns'),
 }
 
 
@@ -418,13 +422,14 @@ def run_cdl_case(tag, sfx):
     """Learn the golden dictionary with sporco_b200 and compare with the reference's outputs."""
     from sporco_b200.dictlrn import cbpdndl
     g = load('%s_%s' % (tag, sfx))
-    o, xmethod, lmbda = CDL_CASES[tag]
+    o, xmethod, lmbda = CDL_CASES[tag][:3]
+    dmethod = CDL_CASES[tag][3] if len(CDL_CASES[tag]) > 3 else 'pgm'
     assert float(g['lmbda']) == lmbda
-    # float32: north_star's rtol 1e-4, except the PGM X step case, where the reference's own
-    # float32 and float64 runs drift apart by 2.1e-4 (D) over these 20 alternations
-    tol = 1e-10 if sfx == 'f64' else (1e-3 if tag == 'cdl_pgmx' else 1e-4)
-    opt = cbpdndl.ConvBPDNDictLearn.Options(o, xmethod=xmethod, dmethod='pgm')
-    b = cbpdndl.ConvBPDNDictLearn(g['D0'], g['S'], lmbda, opt, xmethod=xmethod, dmethod='pgm')
+    # float32: north_star's rtol 1e-4, except the PGM X step and the consensus D step cases, where the
+    # reference's own float32 and float64 runs drift apart by 2e-4 ... 4e-4 (D) over these alternations
+    tol = 1e-10 if sfx == 'f64' else (1e-3 if (tag == 'cdl_pgmx' or dmethod == 'cns') else 1e-4)
+    opt = cbpdndl.ConvBPDNDictLearn.Options(o, xmethod=xmethod, dmethod=dmethod)
+    b = cbpdndl.ConvBPDNDictLearn(g['D0'], g['S'], lmbda, opt, xmethod=xmethod, dmethod=dmethod)
     D = b.solve()
     its = b.getitstat()
     assert D.dtype == g['D'].dtype and D.shape == g['D'].shape
@@ -433,6 +438,8 @@ def run_cdl_case(tag, sfx):
     assert X.shape == g['X'].shape and rel(X, g['X']) <= 3 * tol, 'X: %.3e' % rel(X, g['X'])
     names = [f for f in its._fields if f in g.files and f != 'Cnstr']
     assert len(names) >= 6
+    if dmethod == 'cns':
+        assert 'DPrRsdl' in names and 'DDlRsdl' in names and 'DRho' in names
     for f in names:
         assert len(getattr(its, f)) == len(g[f])
         assert rel(getattr(its, f), g[f]) <= 10 * tol, '%s: %.3e' % (f, rel(getattr(its, f), g[f]))
@@ -595,3 +602,88 @@ def run_pgm_mask_case(sfx, tag='pgm_mask'):
     assert rel(its.ObjFun, g['ObjFun']) < 10 * tol and rel(its.DFid, g['DFid']) < 10 * tol
     assert rel(its.Rsdl, g['Rsdl']) < 10 * tol
     return b
+
+
+# ---- consensus dictionary update (admm.ccmod.ConvCnstrMOD_Consensus) against the pinned oracle
+CNS_CASES = [
+    # N0, N1, C, Cd, K, M, h, options
+    (32, 32, 1, 1, 3, 6, 5, {'MaxMainIter': 12, 'ZeroMean': True}),
+    (32, 64, 3, 1, 2, 5, 4, {'MaxMainIter': 10, 'rho': 2.0,
+                             'AutoRho': {'Enabled': True, 'Period': 3, 'AutoScaling': True, 'Scaling': 10.0}}),
+    (64, 32, 3, 3, 2, 6, 5, {'MaxMainIter': 10, 'Y0': 'pcn', 'AutoRho': {'StdResiduals': True}}),
+    (16, 17, 1, 1, 4, 4, 3, {'MaxMainIter': 8, 'rho': 0.5, 'RelaxParam': 1.0}),      # any-size transforms
+]
+
+
+def run_cns_case(case, dt=np.float32):
+    """ConvCnstrMOD_Consensus on the device against oracle/cbpdndl_oracle.ConsensusCCMOD (bit-identical to
+    the reference): dictionary, residual / penalty / objective trajectories."""
+    from oracle import cbpdndl_oracle as dlo
+    from sporco_b200 import cnvrep as cr
+    from sporco_b200.admm import ccmod
+    N0, N1, C, Cd, K, M, h, o = case
+    o = dict(o)
+    rng = np.random.default_rng(11)
+    Cx = C - Cd + 1
+    Z = rng.standard_normal((N0, N1, Cx, K, M)).astype(dt)
+    Z[np.abs(Z) < 1.0] = 0
+    S = rng.standard_normal((N0, N1, C, K) if C > 1 else (N0, N1, K)).astype(dt)
+    dsz = (h, h, M) if Cd == 1 else (h, h, Cd, M)
+    if o.get('Y0') == 'pcn':
+        D0 = rng.standard_normal(dsz).astype(dt)
+        cri = cr.CDU_ConvRepIndexing(dsz, S, 1, 2)
+        o['Y0'] = cr.zpad(cr.stdformD(cr.Pcn(D0, dsz, cri.Nv, 2, cri.dimCd, crp=True), cri.Cd, cri.M, 2), cri.Nv)
+    c = ccmod.ConvCnstrMOD_Consensus(Z, S, dsz, ccmod.ConvCnstrMOD_Consensus.Options(o))
+    Y = c.solve()
+    r = dlo.ConsensusCCMOD(S, dsz, o)
+    r.setcoef(Z)
+    r.solve()
+    its = c.getitstat()
+    tol = 1e-9
+    if dt == np.float32:
+        # The reference's own float32 run drifts from its float64 run by 1e-4 ... 6e-4 on these problems (the
+        # block solves amplify rounding); the device must agree with the float64 oracle on the same inputs much
+        # better than that, and with the float32 oracle within that drift.
+        o64 = dict(o)
+        if o64.get('Y0') is not None:
+            o64['Y0'] = np.asarray(o64['Y0'], dtype=np.float64)
+        r64 = dlo.ConsensusCCMOD(S.astype(np.float64), dsz, o64)
+        r64.setcoef(Z.astype(np.float64))
+        r64.solve()
+        drift = rel(r.Y, r64.Y)
+        assert rel(Y, r64.Y) < 5e-5, rel(Y, r64.Y)
+        tol = max(2e-4, 1.5 * drift)
+    ref = np.array(r.itstat, dtype=np.float64)
+    assert len(its.Iter) == len(ref)
+    assert rel(Y, r.Y) < tol, rel(Y, r.Y)
+    for name, col in (('DFid', 1), ('PrimalRsdl', 3), ('DualRsdl', 4), ('EpsPrimal', 5), ('EpsDual', 6), ('Rho', 7)):
+        e = rel(getattr(its, name), ref[:, col])
+        assert e < 5 * tol, (name, e)
+    assert np.all(np.asarray(its.Cnstr) < 1e-5)
+    assert rel(c.getdict(), r.getdict()) < tol
+    return c
+
+
+def run_cns_golden(tag, sfx):
+    """ConvCnstrMOD_Consensus on the fixture's inputs against the reference's own outputs."""
+    from sporco_b200.admm import ccmod
+    g = load('%s_%s' % (tag, sfx))
+    o = dict(CNS_GOLDEN[tag])
+    dsz = tuple(int(x) for x in g['dsz'])
+    c = ccmod.ConvCnstrMOD_Consensus(g['Z'], g['S'], dsz, ccmod.ConvCnstrMOD_Consensus.Options(o))
+    Y = c.solve()
+    its = c.getitstat()
+    # float32: the reference's float32 run is itself 3e-4 ... 6e-4 away from its float64 run here
+    tol = 1e-9 if sfx == 'f64' else 1e-3
+    assert Y.shape == g['Y'].shape and rel(Y, g['Y']) < tol, rel(Y, g['Y'])
+    for name in ('DFid', 'PrimalRsdl', 'DualRsdl', 'EpsPrimal', 'EpsDual', 'Rho'):
+        assert len(getattr(its, name)) == len(g[name])
+        assert rel(getattr(its, name), g[name]) < 10 * tol, (name, rel(getattr(its, name), g[name]))
+    return c
+
+
+CNS_GOLDEN = {
+    'cns_zm': {'MaxMainIter': 15, 'ZeroMean': True},
+    'cns_arho': {'MaxMainIter': 15, 'rho': 2.0,
+                 'AutoRho': {'Enabled': True, 'Period': 3, 'AutoScaling': True, 'Scaling': 10.0}},
+}

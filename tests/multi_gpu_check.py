@@ -74,6 +74,43 @@ def main():
     print('rank %d: pgm X err %.3e backtracking counts equal %s L err %.3e obj err %.3e'
           % (rank, x_err, bt_same, l_err, pobj_err), flush=True)
     ok = ok and x_err < 1e-4 and bt_same and l_err < 1e-4 and pobj_err < 1e-4
+    # consensus dictionary update, blocks (images) sharded: supports of the block mean + norms summed over ranks
+    from sporco_b200.admm import ccmod
+    Zc = rng.standard_normal((64, 64, 1, 2 * world, 6)).astype(np.float32)
+    Zc[np.abs(Zc) < 1.0] = 0
+    Sc = rng.standard_normal((64, 64, 2 * world)).astype(np.float32)
+    cm = [2 * rank, 2 * rank + 1]
+    co_ = {'MaxMainIter': 12, 'rho': 2.0, 'AutoRho': {'Enabled': True, 'Period': 3, 'AutoScaling': True, 'Scaling': 10.0}}
+    cc = ccmod.ConvCnstrMOD_Consensus(Zc[:, :, :, cm, :], Sc[:, :, cm], (5, 5, 6), ccmod.ConvCnstrMOD_Consensus.Options(co_),
+                                      device=local)
+    cc.attach_process_group(dist)
+    Yc = cc.solve()
+    rc = ocdl.ConsensusCCMOD(Sc.astype(np.float64), (5, 5, 6), co_)
+    rc.setcoef(Zc.astype(np.float64))
+    rc.solve()
+    cref = np.array(rc.itstat, dtype=np.float64)
+    cits = cc.getitstat()
+    cy_err = np.linalg.norm((Yc - rc.Y).ravel()) / np.linalg.norm(rc.Y.ravel())
+    crho_err = np.abs(np.array(cits.Rho, dtype=np.float64) - cref[:, 7]).max() / np.abs(cref[:, 7]).max()
+    cr_err = np.abs(np.array(cits.PrimalRsdl, dtype=np.float64) - cref[:, 3]).max() / np.abs(cref[:, 3]).max()
+    print('rank %d: consensus ccmod Y err (vs float64 oracle) %.3e rho err %.3e r err %.3e' % (rank, cy_err, crho_err, cr_err),
+          flush=True)
+    ok = ok and cy_err < 1e-4 and crho_err < 1e-4 and cr_err < 1e-3
+    # ... and as the D step of dictionary learning with the training images sharded
+    o2 = {'MaxMainIter': 12, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}
+    d1 = cbpdndl.ConvBPDNDictLearn(D0, S[:, :, mine], 0.1, cbpdndl.ConvBPDNDictLearn.Options(o2, dmethod='cns'),
+                                   dmethod='cns', device=local)
+    d1.attach_process_group(dist)
+    D1 = d1.solve().squeeze()
+    if rank == 0:
+        d2 = cbpdndl.ConvBPDNDictLearn(D0, S, 0.1, cbpdndl.ConvBPDNDictLearn.Options(o2, dmethod='cns'),
+                                       dmethod='cns', device=local)
+        D2 = d2.solve().squeeze()
+        dd_err = np.linalg.norm((D1 - D2).ravel()) / np.linalg.norm(D2.ravel())
+        do_err = np.abs(np.array(d1.getitstat().ObjFun) - np.array(d2.getitstat().ObjFun)).max() / \
+            np.abs(np.array(d2.getitstat().ObjFun)).max()
+        print('rank 0: dictlearn (consensus D step) sharded vs one GPU: D err %.3e obj err %.3e' % (dd_err, do_err), flush=True)
+        ok = ok and dd_err < 3e-4 and do_err < 1e-4
     print('rank %d: schedule %s, peer-memory exchange %s' % (rank, b._h.admm_schedule_info(), b._p2p), flush=True)
     t = torch.tensor([1.0 if ok else 0.0], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -247,3 +247,15 @@ def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
 
 def test_level1_entry_points():
     cases.run_level1_cases()
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64])
+@pytest.mark.parametrize('case', cases.CNS_CASES)
+def test_consensus_dictionary_update_vs_oracle(case, dt):
+    cases.run_cns_case(case, dt)
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.CNS_GOLDEN))
+def test_consensus_dictionary_update_golden(tag, sfx):
+    cases.run_cns_golden(tag, sfx)

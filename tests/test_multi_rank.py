@@ -75,6 +75,50 @@ def _gloo_cdl_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_cns_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import cbpdndl_oracle as ocdl
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = cases.load('cns_arho_f64')
+    mine = [0, 1] if rank == 0 else [2]          # uneven shards on purpose
+
+    def reduce(v):
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
+        dist.all_reduce(t)
+        return t.numpy()
+
+    r = ocdl.ConsensusCCMOD(g['S'][:, :, mine], tuple(int(x) for x in g['dsz']), cases.CNS_GOLDEN['cns_arho'],
+                            reduce=reduce, nb_global=3)
+    r.setcoef(g['Z'][:, :, :, mine, :])
+    r.solve()
+    ref = np.array(r.itstat, dtype=np.float64)
+    q.put((rank, cases.rel(r.Y, g['Y']), cases.rel(ref[:, 7], g['Rho']), cases.rel(ref[:, 3], g['PrimalRsdl']),
+           cases.rel(ref[:, 1], g['DFid'])))
+    dist.destroy_process_group()
+
+
+def test_sharded_consensus_dictionary_update_gloo_world2():
+    """Consensus dictionary update with the blocks (images) sharded over two ranks: only the filter
+    supports of the block mean and the squared norms are summed over ranks, and the run reproduces the
+    reference's unsharded trajectory."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_cns_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, y_err, rho_err, r_err, d_err in res:
+        assert y_err < 1e-9 and rho_err < 1e-12 and r_err < 1e-9 and d_err < 1e-10, (rank, y_err, rho_err, r_err, d_err)
+
+
 def test_sharded_dictionary_learning_gloo_world2():
     """Dictionary learning with the training images sharded over two ranks (gradient, norms and
     objective terms summed over ranks) follows the single-object reference trajectory."""

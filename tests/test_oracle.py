@@ -79,6 +79,21 @@ def test_oracle_reproduces_golden_addmasksim(tag, sfx):
     assert np.array_equal(np.array([row[9 if gm else 8] for row in r.itstat], dtype=np.float64), g['Rho'])
 
 
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.CNS_GOLDEN))
+def test_oracle_reproduces_golden_consensus_ccmod(tag, sfx):
+    """oracle/cbpdndl_oracle.ConsensusCCMOD against the reference's outputs (bit for bit)."""
+    from oracle import cbpdndl_oracle as ocdl
+    g = cases.load('%s_%s' % (tag, sfx))
+    r = ocdl.ConsensusCCMOD(g['S'], tuple(int(x) for x in g['dsz']), cases.CNS_GOLDEN[tag])
+    r.setcoef(g['Z'])
+    r.solve()
+    assert np.array_equal(r.Y, g['Y'])
+    ref = np.array(r.itstat, dtype=np.float64)
+    for i, name in enumerate(('DFid', 'Cnstr', 'PrimalRsdl', 'DualRsdl', 'EpsPrimal', 'EpsDual', 'Rho')):
+        assert np.array_equal(ref[:, i + 1], g[name]), name
+
+
 def test_oracle_reproduces_golden_tikhonov():
     from oracle import signal_oracle as sorc
     g = cases.load('tikhonov')

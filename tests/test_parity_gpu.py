@@ -302,3 +302,17 @@ def test_eight_cta_clusters_admm_and_pgm():
 
 def test_level1_entry_points():
     cases.run_level1_cases()
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64])
+@pytest.mark.parametrize('case', cases.CNS_CASES + [(256, 256, 1, 1, 4, 16, 8, {'MaxMainIter': 6})])
+def test_consensus_dictionary_update_vs_oracle(case, dt):
+    """admm.ccmod.ConvCnstrMOD_Consensus: block solves on the column kernel with per-block coefficient spectra,
+    support means, Pcn, duals and residual norms on the device."""
+    cases.run_cns_case(case, dt)
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('tag', sorted(cases.CNS_GOLDEN))
+def test_consensus_dictionary_update_golden(tag, sfx):
+    cases.run_cns_golden(tag, sfx)
