@@ -375,7 +375,7 @@ def run_b200(args):
         sys.path.insert(0, os.path.join(ROOT, 'tools'))
         import bench_configs
         cfgs = {}
-        for name in ('cfg2', 'cfg3a', 'cfg3b', 'cfg4', 'cfg5'):
+        for name in ('cfg2', 'cfg3a', 'cfg3b', 'cfg4', 'cfg5', 'cfg5_cns'):
             try:
                 cfgs[name] = bench_configs.measure(name, peak, quick=True)
             except Exception as e:        # a configuration must not take the headline line down

@@ -1545,7 +1545,10 @@ class Engine : public spcsc_handle {
         const double inv_n = 1.0 / ((double)N0 * (double)N1);
         out[0] = 0.5 * ha[1] * inv_n;
         out[1] = std::sqrt(ha[3]);
-        out[2] = ha[2] * inv_n;
+        // the residual is computed from the (rank-identical) dictionary on every rank; the peer-memory exchange
+        // above sums all accumulator slots, this one included
+        const bool rsdl_summed = nccl_comm && p2p_on && (flags & SPCSC_CCMOD_DFID);
+        out[2] = ha[2] * inv_n / (rsdl_summed ? (double)nranks : 1.0);
         out[3] = 0.5 * hF;
         return SPCSC_OK;
     }

@@ -136,6 +136,34 @@ def measure(name, peak_gbs, quick=True):
         out = {'ms': dt / n * 1e3, 'it_per_s': n / dt, 'algorithmic_GB': per_iter / 1e9,
                'workload': 'dictlrn.cbpdndl.ConvBPDNDictLearn 16 images 256x256, 8x8x64, ADMM X step / PGM D step, f32',
                'ObjFun_first_last': [float(its.ObjFun[0]), float(its.ObjFun[-1])]}
+    elif name == 'cfg5_cns':
+        # the same problem with the consensus ADMM dictionary update (dmethod 'cns'): per outer iteration the D step
+        # runs Y - U_i (R U W W: 2 B), forward rows (R W W Z: B + Zt), block solves in place against the block's
+        # coefficient spectra (R W Z + R Zf: 3 Zt), inverse rows (Zt + B), dual update and norms (R X U W U: 3 B),
+        # data fidelity on Y (R Zf: Zt); the X step and the hand-over as in cfg5
+        from sporco_b200.dictlrn import cbpdndl
+        D0 = rng.standard_normal((8, 8, 64)).astype(f32)
+        S = rng.standard_normal((256, 256, 16)).astype(f32)
+        o = cbpdndl.ConvBPDNDictLearn.Options({'MaxMainIter': 10, 'CCMOD': {'rho': 16.0}}, dmethod='cns')
+        b = cbpdndl.ConvBPDNDictLearn(D0, S, 0.1, o, dmethod='cns')
+        b.solve()
+        n = 40 if quick else 100
+        b.opt['MaxMainIter'] = n
+        b.xstep._h.synchronize()
+        t0 = time.perf_counter()
+        b.solve()
+        b.xstep._h.synchronize()
+        dt = time.perf_counter() - t0
+        its = b.getitstat()
+        b_r = 4.0 * 256 * 256 * 16 * 64
+        zt = 8.0 * 256 * 129 * 16 * 64
+        xstep = (2 * b_r + zt) + 2 * zt + (zt + 4 * b_r) + (b_r + zt) + 2 * zt
+        dstep = 2 * b_r + (b_r + zt) + 3 * zt + (zt + b_r) + 3 * b_r + zt
+        out = {'ms': dt / n * 1e3, 'it_per_s': n / dt, 'algorithmic_GB': (xstep + dstep) / 1e9,
+               'workload': 'dictlrn.cbpdndl.ConvBPDNDictLearn 16 images 256x256, 8x8x64, ADMM X step / consensus ADMM D step '
+                           '(dmethod cns), f32',
+               'ObjFun_first_last': [float(its.ObjFun[0]), float(its.ObjFun[-1])],
+               'DPrRsdl_last': float(its.DPrRsdl[-1])}
     else:
         raise ValueError(name)
     out['GBps'] = out['algorithmic_GB'] / (out['ms'] / 1e3)
