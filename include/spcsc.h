@@ -228,7 +228,7 @@ int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z);
 /* One PGM iteration with step 1/L and momentum coefficient coef = (t_prev - 1)/t  (pgm/pgm.py:779-831).
    flags select the statistics that cost a pass of their own (the reference computes both unless
    FastSolve is set, pgm/pgm.py:347-356): out[0] needs SPCSC_CCMOD_DFID, out[1] SPCSC_CCMOD_CNSTR. */
-enum { SPCSC_CCMOD_DFID = 1, SPCSC_CCMOD_CNSTR = 2 };
+enum { SPCSC_CCMOD_DFID = 1, SPCSC_CCMOD_CNSTR = 2, SPCSC_CCMOD_LINSOLVE = 4 };
 int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]);
 /* getdict(crop=True): (hd, wd, Cd, M).                                     pgm/ccmod.py:283-291 */
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out);
@@ -246,10 +246,14 @@ int spcsc_ccmod_push_dict(spcsc_handle* h);
    ustep -- with U read as U / udiv (the lazy form of U /= rsf after a change of rho, admm.py:549-575).
    out[]: [0] DFid on Y (ccmod.py:884-892 with fEvalX False), [1] Cnstr = ||Pcn(Y) - Y|| (:895-902),
    [2] ||X||^2, [3] ||X - Y||^2, [4] ||U||^2, [5] ||Y||^2, [6] ||Yprev - Y||^2 (the host forms the residuals of
-   admm.py:1673-1707 from them), [7] reserved.  flags as for spcsc_ccmod_step.  With images sharded over ranks the
-   filter supports of the block mean and the norms are summed over the ranks (peer memory / NCCL). */
+   admm.py:1673-1707 from them), [7] XSlvRelRes with SPCSC_CCMOD_LINSOLVE (LinSolveCheck, ccmod.py:815-824: the solve then
+   runs out of place), else -1.  Other flags as for spcsc_ccmod_step.  With images sharded over ranks the filter supports of
+   the block mean and the norms are summed over the ranks (peer memory / NCCL).
+   spcsc_ccmod_cns_get: the block variables X (which = 0, after the last step) or U (1) in device order
+   [K*C][M][N0][N1], batch index (image, channel). */
 int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global);
 int spcsc_ccmod_cns_step(spcsc_handle* h, double rho, double udiv, double rlx, int32_t flags, double out[8]);
+int spcsc_ccmod_cns_get(spcsc_handle* h, int32_t which, void* out);
 
 /* ---- multi-GPU: images are sharded over ranks (one process per GPU); the only exchange of
    the path is the all-reduce of the residual / objective sums that drive the shared rho and the

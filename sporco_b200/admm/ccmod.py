@@ -13,9 +13,10 @@ reference does.
 
 Supported: greyscale and multi-channel signals with a single-channel dictionary (channels become
 further blocks, ccmod.py:697-705) or a dictionary with the signal's channels; the objective on the
-consensus variable (``AuxVarObj`` True, the class default).  ``LinSolveCheck`` and the objective on
-the block variables (``AuxVarObj`` False) raise ``NotImplementedError``; the ``ism`` and ``cg``
-solvers are not provided.
+consensus variable (``AuxVarObj`` True, the class default), ``LinSolveCheck``.  The objective on the
+block variables (``AuxVarObj`` False) raises ``NotImplementedError``; the ``ism`` and ``cg`` solvers
+are not provided (the factory functions ``ConvCnstrMOD`` / ``ConvCnstrMODOptions`` accept ``method='cns'``,
+their default in the reference).
 """
 
 import copy
@@ -61,8 +62,6 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
         if not (np.isrealobj(S) and (Z is None or np.isrealobj(Z))):
             raise NotImplementedError('complex-valued data is not supported')
         opt = self._coerce_options(opt)
-        if opt['LinSolveCheck']:
-            raise NotImplementedError('LinSolveCheck is not implemented for the device consensus update')
         if opt['fEvalX'] or not opt['gEvalY']:
             raise NotImplementedError('the objective is evaluated on the consensus variable '
                                       '(AuxVarObj True, the class default) only')
@@ -135,6 +134,23 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
     def var_y(self):
         return self.Y
 
+    def _blocks(self, which):
+        """Block variables in the reference's layout (N0, N1, Cd, 1, M, Nb) (ccmod.py:728-735)."""
+        cri = self.cri
+        a = self._h.ccmod_cns_get(which, cri.K * cri.C, cri.M)            # (K*C, M, N0, N1), batch = (k, c)
+        nbl = (cri.K * cri.C) // cri.Cd
+        a = a.reshape(nbl, cri.Cd, cri.M, cri.Nv[0], cri.Nv[1])
+        return np.ascontiguousarray(a.transpose(3, 4, 1, 2, 0))[:, :, :, np.newaxis, :, :]
+
+    @property
+    def X(self):
+        return self._blocks(0)
+
+    @property
+    def U(self):
+        u = self._blocks(1)
+        return u if self._udiv == 1.0 else (u / self.dtype.type(self._udiv)).astype(self.dtype)
+
     def getmin(self):
         return self.Y
 
@@ -147,7 +163,7 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
         rdt = common.real_dtype(self.dtype).type
         ar = opt['AutoRho']
         need_rsdl = ar['Enabled'] or not opt['FastSolve']
-        flags = 0 if opt['FastSolve'] else 3
+        flags = (0 if opt['FastSolve'] else 3) | (4 if opt['LinSolveCheck'] else 0)
         rows, done, stopped = [], 0, False
         for _ in range(n):
             k = self.k + done
@@ -179,7 +195,7 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
                 epri = np.sqrt(self.Nc) * opt['AbsStopTol'] / rn + opt['RelStopTol']
                 edua = np.sqrt(self.Nx) * opt['AbsStopTol'] / sn + opt['RelStopTol']
             if want_rows:
-                rows.append((k, st[0], st[1], r, s, epri, edua, rho))
+                rows.append((k, st[0], st[1], r, s, epri, edua, rho, st[7] if st[7] >= 0.0 else None))
             # update_rho (admm.py:549-575); U /= rsf is applied by the next reads of U on the device
             if ar['Enabled'] and k != 0 and np.mod(k + 1, ar['Period']) == 0:
                 tau, mu, xi = self.rho_tau, self.rho_mu, self.rho_xi
@@ -205,8 +221,8 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
         return rows, done, stopped
 
     def _make_itstat(self, row, t):
-        k, dfd, cns, r, s, epri, edua, rho = row
-        return type(self).IterationStats(int(k), dfd, cns, r, s, epri, edua, rho, None, t)
+        k, dfd, cns, r, s, epri, edua, rho, xrrs = row
+        return type(self).IterationStats(int(k), dfd, cns, r, s, epri, edua, rho, xrrs, t)
 
     def attach_process_group(self, dist, group=None):
         """Shard the blocks (images) over the ranks of a ``torch.distributed`` group: every rank owns
@@ -229,3 +245,18 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
         h = getattr(self, '_h', None)
         if h is not None and getattr(self, '_owns_handle', False):
             h.close()
+
+
+def ConvCnstrMODOptions(opt=None, method='cns'):
+    """Options object of the selected dictionary update (sporco/admm/ccmod.py:970-1001)."""
+    if method != 'cns':
+        raise NotImplementedError("dictionary update method '%s' is not provided; use 'cns' (or pgm.ccmod)" % method)
+    return ConvCnstrMOD_Consensus.Options(opt)
+
+
+def ConvCnstrMOD(*args, **kwargs):
+    """Dictionary update object of the selected class (sporco/admm/ccmod.py:914-966; default 'cns')."""
+    method = kwargs.pop('method', 'cns')
+    if method != 'cns':
+        raise NotImplementedError("dictionary update method '%s' is not provided; use 'cns' (or pgm.ccmod)" % method)
+    return ConvCnstrMOD_Consensus(*args, **kwargs)

@@ -288,4 +288,62 @@ SPCSC_GLOBAL void k_cns_ynorms(const T* SPCSC_RESTRICT Yold, const T* SPCSC_REST
     block_accumulate<2>(s, red, acc + ACC_CNS_Y2);
 }
 
+// LinSolveCheck of the consensus x step (ccmod.py:815-824): relative residual of the block solves SUMMED over the
+// blocks,  ax = sum_i [conj(Zf_i) (sum_m Zf_i,m Xf_i,m) + rho Xf_i],  b = sum_i [conj(Zf_i) Sf_i + rho rfftn(Y - U_i)],
+// XSlvRelRes = ||ax - b|| / ||b|| (plain norms over the stored half spectra).  One CTA per (wf, tile of 32 frequencies):
+// 32 h-lanes x 8 filter groups, loop over the batches bb = c, c + Cd, ... of dictionary channel c with ax, b in registers.
+enum { ACC_CNS_LSR = 13, ACC_CNS_LSB = 14 };
+template <typename T, int MI>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(256)
+k_cns_linsolve(const C2<T>* SPCSC_RESTRICT Zf, const C2<T>* SPCSC_RESTRICT Xf, const C2<T>* SPCSC_RESTRICT Zin,
+               const C2<T>* SPCSC_RESTRICT Sf, double* SPCSC_RESTRICT acc, int NB, int Cd, int c, int N1f, int M,
+               int N0, T rho) {
+    __shared__ C2<T> red[8][33];
+    __shared__ double dred[2 * 32];
+    const int lane = threadIdx.x & 31, mg = threadIdx.x >> 5;
+    const int wf = blockIdx.x, h = blockIdx.y * 32 + lane;
+    const bool hv = h < N0;
+    C2<T> ax[MI], bv[MI];
+    SPCSC_UNROLL
+    for (int i = 0; i < MI; ++i) ax[i] = bv[i] = mk<T>(0, 0);
+    for (int bb = c; bb < NB; bb += Cd) {
+        const C2<T>* zk = Zf + (((size_t)(bb / Cd) * N1f + wf) * M) * N0;
+        const size_t slab = (((size_t)bb * N1f + wf) * M) * N0;
+        C2<T> z[MI], x[MI];
+        C2<T> part = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int i = 0; i < MI; ++i) {
+            const int m = mg + 8 * i;
+            const bool ok = hv && m < M;
+            z[i] = ok ? zk[(size_t)m * N0 + h] : mk<T>(0, 0);
+            x[i] = ok ? Xf[slab + (size_t)m * N0 + h] : mk<T>(0, 0);
+            part = part + z[i] * x[i];
+        }
+        red[mg][lane] = part;
+        __syncthreads();
+        C2<T> sx = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int q = 0; q < 8; ++q) sx = sx + red[q][lane];
+        const C2<T> sf = hv ? Sf[((size_t)bb * N1f + wf) * N0 + h] : mk<T>(0, 0);
+        __syncthreads();
+        SPCSC_UNROLL
+        for (int i = 0; i < MI; ++i) {
+            const int m = mg + 8 * i;
+            if (hv && m < M) {
+                const C2<T> zi = Zin[slab + (size_t)m * N0 + h];
+                ax[i] = ax[i] + mulc(sx, z[i]) + mk<T>(rho * x[i].re, rho * x[i].im);
+                bv[i] = bv[i] + mulc(sf, z[i]) + mk<T>(rho * zi.re, rho * zi.im);
+            }
+        }
+    }
+    double s1[1] = {0.0}, s2[1] = {0.0};
+    SPCSC_UNROLL
+    for (int i = 0; i < MI; ++i) {
+        s1[0] += (double)abs2(ax[i] - bv[i]);
+        s2[0] += (double)abs2(bv[i]);
+    }
+    block_accumulate<1>(s1, dred, acc + ACC_CNS_LSR);
+    block_accumulate<1>(s2, dred, acc + ACC_CNS_LSB);
+}
+
 }  // namespace spcsc

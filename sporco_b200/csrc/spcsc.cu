@@ -317,6 +317,7 @@ struct spcsc_handle {
     virtual int ccmod_push_dict() = 0;
     virtual int ccmod_cns_init(double rho, int y0_given, long long nb_global) = 0;
     virtual int ccmod_cns_step(double rho, double udiv, double rlx, int flags, double* out) = 0;
+    virtual int ccmod_cns_get(int which, void* out) = 0;
 };
 
 namespace {
@@ -408,7 +409,7 @@ class Engine : public spcsc_handle {
     // consensus dictionary update (admm.ccmod.ConvCnstrMOD_Consensus): per-block copies of the dictionary and
     // duals [K*C][M][N0][N1], their row/column spectra, the Gram rows of the coefficient spectra, the new Y
     DevBuf<T> cnsX, cnsU, cnsYn;
-    DevBuf<C2<T>> cnsZ, cnsG;
+    DevBuf<C2<T>> cnsZ, cnsZ2, cnsG;            // cnsZ2: the solve's output when LinSolveCheck needs its input too
     DevBuf<AdmmState<T>> cns_st;
     bool cns_ready = false, cns_gram_stale = true;
     long long cns_nb_global = 0;             // blocks over all ranks (the mean of the y step runs over them)
@@ -468,7 +469,7 @@ class Engine : public spcsc_handle {
         pgA.release(); pgB.release(); Zt2.release();
         pgZ.release(); pgYp.release(); pg_sx.release(); pg_rprev.release(); pg_sxprev.release();
         cd_supp.release(); cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
-        cnsX.release(); cnsU.release(); cnsYn.release(); cnsZ.release(); cnsG.release(); cns_st.release();
+        cnsX.release(); cnsU.release(); cnsYn.release(); cnsZ.release(); cnsZ2.release(); cnsG.release(); cns_st.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
 #ifndef SPCSC_EMU
 #endif
@@ -1601,6 +1602,8 @@ class Engine : public spcsc_handle {
         // x step: rfftn(Y - U_i), the column solve against block i's coefficient spectra, irfftn
         CK(launch(k_cns_yu<T>, dim3(1184), dim3(256), 0, stream, (const T*)cdX.p, (const T*)cnsU.p, cnsX.p, NB, Cd,
                   plane, uinv));
+        const bool lscheck = (flags & SPCSC_CCMOD_LINSOLVE) != 0;
+        C2<T>* xf = cnsZ.p;
         ColLaunch<T> c = colargs(M, NB);
         c.in = cnsZ.p; c.out = cnsZ.p;
         c.Df = cdZf.p; c.G = cnsG.p; c.Sf = Sf.p;
@@ -1611,7 +1614,43 @@ class Engine : public spcsc_handle {
         c.a.df_bdiv = Cd;
         c.push = 0; c.bulk = 0;
         c.Lstep = 0;
-        if (v2_rowf && v2_col && col2_ok<T>(N0, M, 1)) {
+        double hls[2] = {0.0, 0.0};
+        if (lscheck) {
+            // LinSolveCheck: forward columns, solve and inverse columns as separate launches of the general kernel, so
+            // that the solve's input and output exist side by side in the 2-D frequency domain for the check
+            const size_t nsp = (size_t)NB * N1f * M * N0;
+            CK(cnsZ2.ensure(2 * nsp));
+            C2<T>* zf2 = cnsZ2.p;
+            C2<T>* xf2 = cnsZ2.p + nsp;
+            if (v2_rowf)
+                CK(row_fwd2<T>(H, rowargs(M, NB, 1), (const T*)cnsX.p, (const T*)nullptr,
+                               (const AdmmState<T>*)nullptr, cnsZ.p, (const C2<T>*)stw_row1.p, 0));
+            else
+                CK(row_fwd<T>(H, rowargs(M, NB, 1), (const T*)cnsX.p, (const T*)nullptr,
+                              (const AdmmState<T>*)nullptr, cnsZ.p));
+            ColLaunch<T> c1 = c;
+            c1.in = cnsZ.p; c1.out = zf2;
+            CK(col<T>(N0, COL_FWD, c1));
+            ColLaunch<T> c2 = c;
+            c2.in = zf2; c2.out = xf2;
+            CK(col<T>(N0, COL_ADMM_NOFFT, c2));
+            CK(cudaMemsetAsync(acc.p + ACC_CNS_LSR, 0, 2 * sizeof(double), stream));
+            dim3 grid(N1f, (N0 + 31) / 32);
+            for (int cc = 0; cc < Cd; ++cc) {
+                if (M <= 64)
+                    CK(launch(k_cns_linsolve<T, 8>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p, (const C2<T>*)xf2,
+                              (const C2<T>*)zf2, (const C2<T>*)Sf.p, acc.p, NB, Cd, cc, N1f, M, N0, (T)rho));
+                else
+                    CK(launch(k_cns_linsolve<T, 16>, grid, dim3(256), 0, stream, (const C2<T>*)cdZf.p, (const C2<T>*)xf2,
+                              (const C2<T>*)zf2, (const C2<T>*)Sf.p, acc.p, NB, Cd, cc, N1f, M, N0, (T)rho));
+            }
+            // (with the blocks sharded over ranks this is the residual of the rank's own blocks)
+            CK(cudaMemcpyAsync(hls, acc.p + ACC_CNS_LSR, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemsetAsync(acc.p + ACC_CNS_LSR, 0, 2 * sizeof(double), stream));
+            ColLaunch<T> c3 = c;
+            c3.in = xf2; c3.out = cnsZ.p;
+            CK(col<T>(N0, COL_INV, c3));
+        } else if (v2_rowf && v2_col && col2_ok<T>(N0, M, 1)) {
             CK(row_fwd2<T>(H, rowargs(M, NB, 1), (const T*)cnsX.p, (const T*)nullptr,
                            (const AdmmState<T>*)nullptr, cnsZ.p, (const C2<T>*)stw_row1.p, 0));
             CK(col2<T>(N0, COL_ADMM, c, (const C2<T>*)stw_col.p));
@@ -1620,7 +1659,7 @@ class Engine : public spcsc_handle {
                           (const AdmmState<T>*)nullptr, cnsZ.p));
             CK(col<T>(N0, COL_ADMM, c));
         }
-        CK(row_inv<T>(H, rowargs(M, NB, 1), (const C2<T>*)cnsZ.p, cnsX.p, (T)(1.0 / ((double)N0 * (double)N1))));
+        CK(row_inv<T>(H, rowargs(M, NB, 1), (const C2<T>*)xf, cnsX.p, (T)(1.0 / ((double)N0 * (double)N1))));
         // y step: supports of the mean over all blocks (of all ranks), then the constraint projection
         const double nb_glob = (double)cns_nb_global;
         CK(tmp_real.ensure((size_t)Cd * plane));
@@ -1678,7 +1717,18 @@ class Engine : public spcsc_handle {
         out[0] = 0.5 * ha[1] * inv_n;
         out[1] = std::sqrt(ha[3]);
         out[2] = hn[0]; out[3] = hn[1]; out[4] = hn[2]; out[5] = hn[3]; out[6] = hn[4];
-        out[7] = 0.0;
+        out[7] = lscheck ? (hls[1] > 0.0 ? std::sqrt(hls[0] / hls[1]) : std::sqrt(hls[0])) : -1.0;
+        return SPCSC_OK;
+    }
+    // block variables in device order [K*C][M][N0][N1]: which 0 = X (after the last step), 1 = U
+    int ccmod_cns_get(int which, void* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!cns_ready) FAIL(SPCSC_ERR_STATE, "ccmod_cns_get before ccmod_cns_init");
+        if (which != 0 && which != 1) FAIL(SPCSC_ERR_INVALID, "which must be 0 (X) or 1 (U)");
+        CK(cudaSetDevice(pb.device));
+        const size_t n = (size_t)K * C * M * N0 * N1;
+        CK(cudaMemcpyAsync(out, which == 0 ? cnsX.p : cnsU.p, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
         return SPCSC_OK;
     }
     int ccmod_get_dict(void* out) override {
@@ -2227,6 +2277,7 @@ int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, doub
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
 int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global) { H_CALL(h->ccmod_cns_init(rho, y0_given, (long long)nb_global)); }
+int spcsc_ccmod_cns_get(spcsc_handle* h, int32_t which, void* out) { H_CALL(out ? h->ccmod_cns_get(which, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_cns_step(spcsc_handle* h, double rho, double udiv, double rlx, int32_t flags, double out[8]) { H_CALL(out ? h->ccmod_cns_step(rho, udiv, rlx, flags, out) : SPCSC_ERR_INVALID); }
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {
     if (!id128) { g_last_error = "null id buffer"; return SPCSC_ERR_INVALID; }

@@ -27,7 +27,13 @@ OTHER_CLASSES = ('ConvBPDNProjL1', 'ConvMinL1InL2Ball',
 NOT_IMPLEMENTED = {
     'admm': {'test_10cplx': 'complex-valued data'},
     'pgm': {'test_10cplx': 'complex-valued data'},
+    # tests/admm/test_ccmod.py with ConvCnstrMOD_Consensus and the factory functions replaced (default method 'cns')
+    'ccmod': {'test_03cplx': 'complex-valued data', 'test_05': 'multi-scale dictionary (dsz a tuple of tuples)',
+              'test_13': 'multi-channel coefficient maps together with a multi-channel dictionary (runs in the '
+                         'reference through numpy broadcasting only; not a documented configuration)'},
 }
+# tests of the reference's other dictionary-update classes / its own option classes in that file
+CCMOD_OTHER = ('ConvCnstrMOD_IterSM', 'ConvCnstrMOD_CG', 'ConvCnstrMODBase')
 
 
 def _load(kind):
@@ -38,6 +44,17 @@ def _load(kind):
     from sporco_b200.admm import cbpdn as my_admm
     from sporco_b200.pgm import cbpdn as my_pgm
     proxy = types.ModuleType('cbpdn_proxy')
+    if kind == 'ccmod':
+        import sporco.admm.ccmod as ref_ccmod
+        from sporco_b200.admm import ccmod as my_ccmod
+        proxy.__dict__.update(ref_ccmod.__dict__)
+        for name in ('ConvCnstrMOD_Consensus', 'ConvCnstrMOD', 'ConvCnstrMODOptions'):
+            setattr(proxy, name, getattr(my_ccmod, name))
+        path = os.path.join(REF, 'tests', 'admm', 'test_ccmod.py')
+        src = open(path).read().replace('from sporco.admm import ccmod', 'ccmod = __proxy__')
+        ns = {'__proxy__': proxy, '__name__': 'ref_tests_ccmod'}
+        exec(compile(src, path, 'exec'), ns)
+        return ns['TestSet01']
     if kind == 'admm':
         proxy.__dict__.update(ref_admm.__dict__)
         for name in ('GenericConvBPDN', 'ConvBPDN', 'ConvBPDNJoint', 'ConvElasticNet', 'ConvBPDNGradReg',
@@ -72,7 +89,7 @@ def _cases(kind):
         if not name.startswith('test_'):
             continue
         body = inspect.getsource(fn)
-        if any(c in body for c in OTHER_CLASSES):
+        if any(c in body for c in (CCMOD_OTHER if kind == 'ccmod' else OTHER_CLASSES)):
             continue                                      # a test of another reference class
         out.append(name)
     return out
@@ -97,7 +114,7 @@ def test_reference_admm_suite(name):
 
 # 2000-iteration recovery tests: ~1 min each under emulation; they pass (run them with
 # SPCSC_LONG_TESTS=1) but are kept out of the default CPU suite to keep it short
-LONG = {'pgm': ('test_10', 'test_11')}
+LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03',)}       # test_03: up to 500 iterations, ~20 min emulated
 
 
 @pytest.mark.parametrize('name', _cases('pgm'))
@@ -107,6 +124,19 @@ def test_reference_pgm_suite(name):
     if name in NOT_IMPLEMENTED['pgm']:
         pytest.xfail('not implemented: ' + NOT_IMPLEMENTED['pgm'][name])
     cls = _load('pgm')
+    obj = cls()
+    obj.setup_method(None)
+    getattr(obj, name)()
+
+
+@pytest.mark.parametrize('name', _cases('ccmod'))
+def test_reference_ccmod_suite(name):
+    """/root/reference/tests/admm/test_ccmod.py: the consensus dictionary update and the factory functions."""
+    if name in LONG['ccmod'] and not os.environ.get('SPCSC_LONG_TESTS'):
+        pytest.skip('long emulated run; set SPCSC_LONG_TESTS=1')
+    if name in NOT_IMPLEMENTED['ccmod']:
+        pytest.xfail('not implemented: ' + NOT_IMPLEMENTED['ccmod'][name])
+    cls = _load('ccmod')
     obj = cls()
     obj.setup_method(None)
     getattr(obj, name)()
