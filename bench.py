@@ -189,21 +189,33 @@ def multi_gpu_parity(dist, rank, world, device):
     b.attach_process_group(dist)
     Y = b.solve()
     its = b.getitstat()
+    # The check is against the float64 oracle on the same (float32) inputs: over these 60 AutoRho iterations the
+    # reference's own float32 run drifts 3e-4 from its float64 run, so agreement with the float32 oracle to 1e-4
+    # is not a property any float32 implementation has; the rho trajectory and the stop iteration are compared
+    # with the float32 oracle (they are decided in float32).
     r = orc.admm_convbpdn(Dp, Sp, 0.05, opt=opt, dimK=1)
-    Yr = r.Y[:, :, :, 2 * rank:2 * rank + 2, :].reshape(Y.shape)
-    rel_y = float(np.linalg.norm((Y - Yr).ravel()) / max(np.linalg.norm(Yr.ravel()), 1e-30))
+    opt64 = dict(opt, MaxMainIter=len(r.itstat), RelStopTol=0.0)        # the same number of iterations
+    r64 = orc.admm_convbpdn(Dp.astype(np.float64), Sp.astype(np.float64), 0.05, opt=opt64, dimK=1)
+    sl = (slice(None), slice(None), slice(None), slice(2 * rank, 2 * rank + 2), slice(None))
+    Yr = r.Y[sl].reshape(Y.shape)
+    Y64 = r64.Y[sl].reshape(Y.shape)
+    rel_y = float(np.linalg.norm((Y - Y64).ravel()) / max(np.linalg.norm(Y64.ravel()), 1e-30))
+    rel_y32 = float(np.linalg.norm((Y - Yr).ravel()) / max(np.linalg.norm(Yr.ravel()), 1e-30))
+    drift = float(np.linalg.norm((r.Y - r64.Y).ravel()) / max(np.linalg.norm(r64.Y.ravel()), 1e-30))
     rho_ref = np.array([row[8] for row in r.itstat], dtype=np.float64)
     rho_own = np.asarray(its.Rho, dtype=np.float64)
     same_n = len(rho_own) == len(rho_ref)
     rho_rel = float(np.max(np.abs(rho_own - rho_ref) / rho_ref)) if same_n else float('inf')
-    t = torch.tensor([rel_y, rho_rel, 0.0 if same_n else 1.0], dtype=torch.float64, device='cuda')
+    t = torch.tensor([rel_y, rho_rel, 0.0 if same_n else 1.0, rel_y32], dtype=torch.float64, device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    rel_y, rho_rel, bad_n = (float(x) for x in t.tolist())
+    rel_y, rho_rel, bad_n, rel_y32 = (float(x) for x in t.tolist())
     ok = bool(rel_y < 1e-4 and rho_rel < 1e-4 and bad_n == 0.0)
     del b
     return {'n': world, 'problem': '64x64, 6x6x8 dictionary, %d images (2 per rank), AutoRho, stop at RelStopTol 4e-3'
             % (2 * world), 'iterations': int(len(rho_ref)), 'stop_iteration_equal': bad_n == 0.0,
-            'rel_Y': rel_y, 'rho_rel': rho_rel, 'tol': 1e-4, 'ok': ok}
+            'rel_Y': rel_y, 'rel_Y_reference': 'float64 oracle on the same inputs',
+            'rel_Y_vs_float32_oracle': rel_y32, 'oracle_float32_vs_float64': drift,
+            'rho_rel': rho_rel, 'tol': 1e-4, 'ok': ok}
 
 
 def recorded_traffic(kernel):
