@@ -215,13 +215,27 @@ SPCSC_GLOBAL void k_crop_dict(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT D, in
 enum { ACC_CNS_X2 = 8, ACC_CNS_R2 = 9, ACC_CNS_U2 = 10, ACC_CNS_Y2 = 11, ACC_CNS_S2 = 12 };
 
 // W[bb] = Y[bb % Cd] - U[bb] * uinv     (U /= rsf of a change of rho is applied lazily: uinv = 1 / udiv)
+// grid (x, NB): blockIdx.y is the batch index, so no per-element division; 4 values per thread and step where the
+// plane size allows (the first version divided per element and ran at 2.4 TB/s, profiles/r02_configs_ncu.md)
 template <typename T>
 SPCSC_GLOBAL void k_cns_yu(const T* SPCSC_RESTRICT Y, const T* SPCSC_RESTRICT U, T* SPCSC_RESTRICT W, int NB,
                            int Cd, size_t plane, T uinv) {
-    const size_t n = (size_t)NB * plane;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t bb = i / plane, o = i - bb * plane;
-        W[i] = Y[(bb % Cd) * plane + o] - U[i] * uinv;
+    const size_t bb = blockIdx.y;
+    if (bb >= (size_t)NB) return;
+    const T* y = Y + (bb % Cd) * plane;
+    const T* u = U + bb * plane;
+    T* w = W + bb * plane;
+    const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    if (plane % 4 == 0) {
+        for (size_t i = start * 4; i < plane; i += step * 4) {
+            T a[4], b[4];
+            SPCSC_UNROLL
+            for (int q = 0; q < 4; ++q) { a[q] = y[i + q]; b[q] = u[i + q]; }
+            SPCSC_UNROLL
+            for (int q = 0; q < 4; ++q) w[i + q] = a[q] - b[q] * uinv;
+        }
+    } else {
+        for (size_t i = start; i < plane; i += step) w[i] = y[i] - u[i] * uinv;
     }
 }
 
@@ -253,23 +267,37 @@ SPCSC_GLOBAL void k_cns_support_mean(const T* SPCSC_RESTRICT X, const T* SPCSC_R
 }
 
 // U[bb] <- U[bb] uinv + alpha X[bb] + (1 - alpha) Yold[c] - Ynew[c], and the sums of X^2, (X - Ynew)^2, Unew^2
+// grid (x, NB) as k_cns_yu
 template <typename T>
 SPCSC_GLOBAL void k_cns_update(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT U, const T* SPCSC_RESTRICT Yold,
                                const T* SPCSC_RESTRICT Ynew, double* SPCSC_RESTRICT acc, int NB, int Cd,
                                size_t plane, T alpha, T uinv) {
     __shared__ double red[3 * 32];
-    const size_t n = (size_t)NB * plane;
+    const size_t bb = blockIdx.y;
     double s[3] = {0.0, 0.0, 0.0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t bb = i / plane, o = (bb % Cd) * plane + (i - bb * plane);
-        const T x = X[i], y0 = Yold[o], y1 = Ynew[o];
-        const T ax = alpha * x + ((T)1 - alpha) * y0;
-        const T u = U[i] * uinv + (ax - y1);
-        U[i] = u;
-        const T r = x - y1;
-        s[0] += (double)x * (double)x;
-        s[1] += (double)r * (double)r;
-        s[2] += (double)u * (double)u;
+    if (bb < (size_t)NB) {
+        const T* x = X + bb * plane;
+        T* u = U + bb * plane;
+        const T* y0 = Yold + (bb % Cd) * plane;
+        const T* y1 = Ynew + (bb % Cd) * plane;
+        const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+        const int V = (plane % 4 == 0) ? 4 : 1;
+        float fs[3] = {0.f, 0.f, 0.f};                       // per-thread partial sums of a few hundred terms at most
+        for (size_t i = start * V; i < plane; i += step * V) {
+            for (int q = 0; q < V; ++q) {
+                const T xv = x[i + q], a = y0[i + q], b = y1[i + q];
+                const T ax = alpha * xv + ((T)1 - alpha) * a;
+                const T un = u[i + q] * uinv + (ax - b);
+                u[i + q] = un;
+                const T r = xv - b;
+                if (sizeof(T) == 4) {
+                    fs[0] += (float)(xv * xv); fs[1] += (float)(r * r); fs[2] += (float)(un * un);
+                } else {
+                    s[0] += (double)xv * (double)xv; s[1] += (double)r * (double)r; s[2] += (double)un * (double)un;
+                }
+            }
+        }
+        if (sizeof(T) == 4) { s[0] = fs[0]; s[1] = fs[1]; s[2] = fs[2]; }
     }
     block_accumulate<3>(s, red, acc + ACC_CNS_X2);
 }

@@ -1600,7 +1600,7 @@ class Engine : public spcsc_handle {
         hs.rho = (T)rho; hs.udiv = (T)1; hs.k = 0; hs.stopped = 0; hs.zt_stale = 1; hs.emit = 0;
         CK(cudaMemcpyAsync(cns_st.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, stream));
         // x step: rfftn(Y - U_i), the column solve against block i's coefficient spectra, irfftn
-        CK(launch(k_cns_yu<T>, dim3(1184), dim3(256), 0, stream, (const T*)cdX.p, (const T*)cnsU.p, cnsX.p, NB, Cd,
+        CK(launch(k_cns_yu<T>, dim3(148, NB), dim3(256), 0, stream, (const T*)cdX.p, (const T*)cnsU.p, cnsX.p, NB, Cd,
                   plane, uinv));
         const bool lscheck = (flags & SPCSC_CCMOD_LINSOLVE) != 0;
         C2<T>* xf = cnsZ.p;
@@ -1685,7 +1685,7 @@ class Engine : public spcsc_handle {
                   N0, N1, pb.hd, pb.wd, cd_zero_mean, 0));
         // u step and the norms of the residuals
         CK(cudaMemsetAsync(acc.p + ACC_CNS_X2, 0, 5 * sizeof(double), stream));
-        CK(launch(k_cns_update<T>, dim3(1184), dim3(256), 0, stream, (const T*)cnsX.p, cnsU.p, (const T*)cdX.p,
+        CK(launch(k_cns_update<T>, dim3(148, NB), dim3(256), 0, stream, (const T*)cnsX.p, cnsU.p, (const T*)cdX.p,
                   (const T*)cnsYn.p, acc.p, NB, Cd, plane, alpha, uinv));
         rc = reduce_acc_over_ranks();
         if (rc) return rc;

@@ -132,10 +132,18 @@ def test_dictionary_learning_options_tree():
     p = cbpdndl.ConvBPDNDictLearn.Options(xmethod='pgm')
     assert p.xmethod == 'pgm' and 'Backtrack' in p['CBPDN'] and 'AutoRho' not in p['CBPDN']
     with pytest.raises(NotImplementedError):
-        cbpdndl.ccmod_class_label_lookup('cns')
+        cbpdndl.ccmod_class_label_lookup('ism')
+    from sporco_b200.admm import ccmod as accmod
+    assert cbpdndl.ccmod_class_label_lookup('cns') is accmod.ConvCnstrMOD_Consensus
+    q = cbpdndl.ConvBPDNDictLearn.Options({'CCMOD': {'rho': 3.0}}, dmethod='cns')
+    assert isinstance(q['CCMOD'], accmod.ConvCnstrMOD_Consensus.Options) and q['CCMOD', 'MaxMainIter'] == 1
+    assert q['CCMOD', 'AutoRho', 'Period'] == 10 and q['CCMOD', 'AutoRho', 'Enabled'] is False
+    assert q['CCMOD', 'RelaxParam'] == 1.8 and q['CCMOD', 'AuxVarObj'] is True and q['CCMOD', 'rho'] == 3.0
     from sporco_b200.dictlrn import common as dc
     assert dc.isfld('admm', 'pgm', o) == ['Iter', 'ObjFun', 'DFid', 'RegL1', 'Cnstr', 'XPrRsdl', 'XDlRsdl',
                                           'XRho', 'D_L', 'D_Rsdl', 'Time']
+    assert dc.isfld('admm', 'cns', q) == ['Iter', 'ObjFun', 'DFid', 'RegL1', 'Cnstr', 'XPrRsdl', 'XDlRsdl',
+                                          'XRho', 'DPrRsdl', 'DDlRsdl', 'DRho', 'Time']
     assert dc.isfld('pgm', 'pgm', p) == ['Iter', 'ObjFun', 'DFid', 'RegL1', 'Cnstr', 'X_L', 'X_Rsdl', 'D_L',
                                          'D_Rsdl', 'Time']
 
