@@ -196,8 +196,18 @@ def test_setting_y_between_solves_is_seen_by_the_fused_schedule():
     assert np.array_equal(sol[0], sol[1])
 
 
-@pytest.mark.parametrize('case', cases.FRESH_CASES + [(64, 64, 8, 5, None, None, None)])
-@pytest.mark.parametrize('pair', [False, True, 'cpg1', 'col4', 'col5', 'col6', 'col7'])
+def _column_variant_cases():
+    """The default column kernel (col6 = k_col5 with one thread group) on every fresh case; the opt-in variants
+    on the cases that exercise their cluster / ragged / multi-channel-signal paths (keeps the CPU suite short)."""
+    every = cases.FRESH_CASES + [(64, 64, 8, 5, None, None, None)]
+    few = [cases.FRESH_CASES[0], cases.FRESH_CASES[6], (64, 64, 8, 5, None, None, None)]
+    out = [pytest.param(c, 'col6', id='col6-case%d' % i) for i, c in enumerate(every)]
+    for v in (False, True, 'cpg1', 'col4', 'col5', 'col7'):
+        out += [pytest.param(c, v, id='%s-case%d' % (v, every.index(c))) for c in few]
+    return out
+
+
+@pytest.mark.parametrize('case,pair', _column_variant_cases())
 def test_push_exchange_column_kernel_vs_oracle(case, pair, monkeypatch):
     """k_col3 (SPCSC_COL3=1): persistent clusters over (frequency column, run of images) items, the
     per-frequency sums pushed into the peers' shared memory and awaited on an mbarrier."""

@@ -114,7 +114,7 @@ def test_reference_admm_suite(name):
 
 # 2000-iteration recovery tests: ~1 min each under emulation; they pass (run them with
 # SPCSC_LONG_TESTS=1) but are kept out of the default CPU suite to keep it short
-LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03',)}       # test_03: up to 500 iterations, ~20 min emulated
+LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03', 'test_04')}       # test_03 / test_04: up to 500 / 1000 iterations, 4-8 min emulated
 
 
 @pytest.mark.parametrize('name', _cases('pgm'))
