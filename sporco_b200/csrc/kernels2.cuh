@@ -266,8 +266,12 @@ struct Prox3Plan {
     static constexpr bool REMAP = (sizeof(C2<T>) == 8 && TPF == 8 && E == 16 && TR % 16 == 0);
     static constexpr int YS = TR * H + (REMAP ? TR : 0);       // one channel of a Y / U tile
     static constexpr int TWLEN = stage_tw_len(H, E);
+    // TWG: with three or more coefficient channels the tiles alone are 75 KB; the two twiddle tables (2.5 KB) are then
+    // read from global memory through L1 instead of being staged, which is what lets a third CTA fit on the SM
+    // (profiles/r02_configs_ncu.md: the joint prox of cfg3a ran at 12 % warp occupancy with two)
+    static constexpr bool TWG = (CX >= 3);
     static constexpr size_t smem_bytes =
-        ((size_t)CX * (2 * YS + TR * P) + TWLEN + N1f) * sizeof(C2<T>);
+        ((size_t)CX * (2 * YS + TR * P) + (TWG ? 0 : TWLEN + N1f)) * sizeof(C2<T>);
     static SPCSC_HD int row_of_group(int gi) {
         return REMAP ? ((gi & ~15) | ((gi & 1) << 3) | ((gi & 15) >> 1)) : gi;
     }
@@ -293,8 +297,9 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     C2<T>* ybuf = reinterpret_cast<C2<T>*>(smem_raw);          // [CX][YS]  (rows of H complex pairs)
     C2<T>* ubuf = ybuf + CX * YS;                              // [CX][YS]
     C2<T>* reg = ubuf + CX * YS;                               // [CX][TR][P]
-    C2<T>* stw_s = reg + CX * TR * P;                          // [TWLEN] stage twiddles
-    C2<T>* tw_s = stw_s + TWLEN;                               // [N1f] split twiddles
+    C2<T>* tab_s = reg + CX * TR * P;                          // [TWLEN] stage twiddles, [N1f] split twiddles
+    const C2<T>* stw_s = PL::TWG ? stw : tab_s;                // (TWG: read from global memory, not staged)
+    const C2<T>* tw_s = PL::TWG ? tw : tab_s + TWLEN;
     const int tid = threadIdx.x;
     const int h0 = blockIdx.x * TR, m = blockIdx.y, k = blockIdx.z;
     const bool ams = m >= prm.ams_m0;   // additive-mask-simulation map: no clipping, not part of RegL1
@@ -302,8 +307,10 @@ k_row_inv_prox3(const C2<T>* SPCSC_RESTRICT Zt, C2<T>* SPCSC_RESTRICT Znext, T* 
     const int gr = tid % TR, wf0 = tid / TR;                   // this thread's row / first wf in tile loops
     // group 0: the twiddle tables (asynchronous as well: the profile of the synchronous copy showed 16 % of
     // the kernel's stall samples on the stores that waited for these loads) ...
-    for (int i = tid; i < TWLEN; i += NT) cp_async<sizeof(C2<T>)>(stw_s + i, stw + i);
-    for (int i = tid; i < N1f; i += NT) cp_async<sizeof(C2<T>)>(tw_s + i, tw + i);
+    if constexpr (!PL::TWG) {
+        for (int i = tid; i < TWLEN; i += NT) cp_async<sizeof(C2<T>)>(tab_s + i, stw + i);
+        for (int i = tid; i < N1f; i += NT) cp_async<sizeof(C2<T>)>(tab_s + TWLEN + i, tw + i);
+    }
     SPCSC_UNROLL
     for (int c = 0; c < CX; ++c) {   // ... and the Zt tiles, transposed on the fly
         const C2<T>* src = Zt + (((size_t)(k * CX + c) * N1f) * M + m) * N0 + h0 +
