@@ -3,6 +3,8 @@ tests/emu, driven through the same C ABI and Python classes as on the GPU, and c
 with the reference's outputs.  This is how `-m "not gpu"` covers the kernels' index
 arithmetic and control flow; performance and the real hardware are the GPU tests' job."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -15,6 +17,12 @@ def _use_emulated_kernels(emu_library):
     _lib.use_library(emu_library)
     yield
     _lib.use_library(None)
+
+
+# Both precisions of every case run on the GPU (tests/test_parity_gpu.py).  Under emulation the float32 instantiations of
+# the heavier families are opt-in (SPCSC_LONG_TESTS=1) so that the CPU suite stays short; the kernel source is the same template.
+_BOTH = ['f64', 'f32'] if os.environ.get('SPCSC_LONG_TESTS') else ['f64']
+_BOTH_DT = [np.float64, np.float32] if os.environ.get('SPCSC_LONG_TESTS') else [np.float64]
 
 
 @pytest.mark.parametrize('dt', [np.float32, np.float64])
@@ -114,8 +122,8 @@ def test_option_paths(capsys):
     cases.run_option_cases(capsys)
 
 
-@pytest.mark.parametrize('sfx', ['f64', 'f32'])
-@pytest.mark.parametrize('tag', sorted(cases.CDL_CASES))
+@pytest.mark.parametrize('tag,sfx', [(t, 'f64') for t in sorted(cases.CDL_CASES)] +
+                         [(t, 'f32') for t in sorted(cases.CDL_CASES) if t in ('cdl', 'cdl_cns') or os.environ.get('SPCSC_LONG_TESTS')])
 def test_dictionary_learning_golden(tag, sfx):
     cases.run_cdl_case(tag, sfx)
 
@@ -135,13 +143,13 @@ def test_tikhonov_filter_golden():
     cases.run_tikhonov_cases()
 
 
-@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('sfx', _BOTH)
 def test_pgm_mask_golden(sfx):
     cases.run_pgm_mask_case(sfx)
     cases.run_pgm_mask_case(sfx, 'pgm_mask_c3')          # multi-channel dictionary
 
 
-@pytest.mark.parametrize('wave', ['1,1', '2,2', '2,1'])
+@pytest.mark.parametrize('wave', ['1,1', '2,2', '2,1'] if os.environ.get('SPCSC_LONG_TESTS') else ['2,2'])
 @pytest.mark.parametrize('keep', ['0', '1', 'fused'])
 def test_wavefront_schedule_vs_oracle(wave, keep, monkeypatch):
     """The wavefront schedule (groups of images through an L2-sized scratch, SPCSC_WAVE=g,s): ragged
@@ -203,7 +211,8 @@ def _column_variant_cases():
     few = [cases.FRESH_CASES[0], cases.FRESH_CASES[6], (64, 64, 8, 5, None, None, None)]
     out = [pytest.param(c, 'col6', id='col6-case%d' % i) for i, c in enumerate(every)]
     for v in (False, True, 'cpg1', 'col4', 'col5', 'col7'):
-        out += [pytest.param(c, v, id='%s-case%d' % (v, every.index(c))) for c in few]
+        sel = few if (v in (False, 'col4', 'col5') or os.environ.get('SPCSC_LONG_TESTS')) else few[:1]
+        out += [pytest.param(c, v, id='%s-case%d' % (v, every.index(c))) for c in sel]
     return out
 
 
@@ -249,7 +258,7 @@ def test_push_exchange_column_kernel_float64_and_colour_dictionary(monkeypatch):
     assert cases.rel(b.getitstat().ObjFun, [x[1] for x in r.itstat]) < 3e-4
 
 
-@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+@pytest.mark.parametrize('sfx', _BOTH)
 @pytest.mark.parametrize('name', cases.PGM_VARIANTS)
 def test_pgm_step_size_policies_monotone_and_robust_backtracking(name, sfx):
     cases.run_pgm_variant_case(name, sfx)
