@@ -419,6 +419,111 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_cfg5(args):
+    """`--config cfg5 | cfg5_cns`: BASELINE.json's configuration 5 -- dictlrn.cbpdndl.ConvBPDNDictLearn on 16 images
+    256x256 with an 8x8x64 dictionary, ADMM X step and PGM (`cfg5`) or consensus ADMM (`cfg5_cns`: "alternating X/D
+    ADMM" as the configuration is written) D step -- with the 16 training images sharded over the ranks (strong
+    scaling: 16 / N images per GPU).  A "step" is one outer iteration; wall clock around `solve()` with device
+    synchronisation and a barrier on both sides, max over ranks.  At N > 1 an untimed small sharded run is compared
+    with the same run on one GPU (all images) and the run fails if they disagree."""
+    import torch
+    from sporco_b200.dictlrn import cbpdndl
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dmethod = 'cns' if args.config == 'cfg5_cns' else 'pgm'
+    ccmod = {'rho': 16.0} if dmethod == 'cns' else {}
+    rng = np.random.default_rng(2024)
+    D0 = rng.standard_normal((8, 8, 64)).astype(np.float32)
+    S = rng.standard_normal((256, 256, 16)).astype(np.float32)
+    if 16 % world:
+        raise SystemExit('the 16 training images must divide over the ranks')
+    per = 16 // world
+    mine = list(range(rank * per, (rank + 1) * per))
+
+    def learner(D0_, S_, iters, dev):
+        o = cbpdndl.ConvBPDNDictLearn.Options({'MaxMainIter': iters, 'CCMOD': dict(ccmod)}, dmethod=dmethod)
+        return cbpdndl.ConvBPDNDictLearn(D0_, S_, 0.1, o, dmethod=dmethod, device=dev)
+
+    parity = None
+    if world > 1:
+        Ds = rng.standard_normal((6, 6, 8)).astype(np.float32)
+        Ss = rng.standard_normal((64, 64, 2 * world)).astype(np.float32)
+        ps = learner(Ds, np.ascontiguousarray(Ss[:, :, 2 * rank:2 * rank + 2]), 12, local_rank)
+        ps.attach_process_group(dist)
+        Dsh = ps.solve().squeeze()
+        obj_sh = np.array(ps.getitstat().ObjFun, dtype=np.float64)
+        res = torch.zeros(2, dtype=torch.float64, device='cuda')
+        if rank == 0:
+            p1 = learner(Ds, Ss, 12, local_rank)
+            D1 = p1.solve().squeeze()
+            obj1 = np.array(p1.getitstat().ObjFun, dtype=np.float64)
+            res[0] = float(np.linalg.norm((Dsh - D1).ravel()) / np.linalg.norm(D1.ravel()))
+            res[1] = float(np.max(np.abs(obj_sh - obj1) / np.abs(obj1)))
+            del p1
+        dist.broadcast(res, src=0)
+        rel_d, rel_obj = float(res[0].item()), float(res[1].item())
+        parity = {'n': world, 'problem': '64x64, 6x6x8 dictionary, %d images (2 per rank), 12 outer iterations, sharded '
+                  'against one GPU holding all images' % (2 * world), 'rel_D': rel_d, 'rel_ObjFun': rel_obj,
+                  'tol': 3e-4, 'ok': bool(rel_d < 3e-4 and rel_obj < 1e-4)}
+        del ps
+    b = learner(D0, np.ascontiguousarray(S[:, :, mine]), max(args.warmup, 3), local_rank)
+    if world > 1:
+        b.attach_process_group(dist)
+    b.solve()
+    b.opt['MaxMainIter'] = args.steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t0 = time.perf_counter()
+    b.solve()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    sec = float(te.item())
+    its = b.getitstat()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    if parity is not None and not parity['ok']:
+        print(json.dumps({'error': 'multi-GPU parity check failed', 'parity_check': parity}))
+        raise SystemExit(3)
+    out = {'metric': 'ConvBPDNDictLearn outer iterations/sec (16 images 256x256, 8x8x64 dictionary, float32)',
+           'value': args.steps / sec, 'unit': 'iterations/s', 'n_gpus': world, 'steps': args.steps,
+           'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * sec / args.steps, 'higher_is_better': True,
+           'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'dictlrn.cbpdndl.ConvBPDNDictLearn, ADMM X step / %s D step, 16 training images '
+                                  'sharded %d per GPU; per outer iteration the ranks exchange the 8x8x64 filter supports '
+                                  '(16 KB) and the residual / objective sums over peer memory'
+                                  % ('consensus ADMM' if dmethod == 'cns' else 'PGM', per),
+                      'timing': 'wall clock around solve() with device synchronisation, max over ranks (the host loop '
+                                'reads one record of scalars per outer iteration: part of the algorithm)',
+                      'ObjFun_first_last': [float(its.ObjFun[0]), float(its.ObjFun[-1])]},
+           'clocks': clocks}
+    if parity is not None:
+        out['parity_check'] = parity
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -427,11 +532,16 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-configs', action='store_true', help='skip the configs block (cfg2..cfg5)')
+    ap.add_argument('--config', default='metric', choices=['metric', 'cfg5', 'cfg5_cns'],
+                    help="'metric' (default): the headline ConvBPDN benchmark; cfg5 / cfg5_cns: dictionary learning with "
+                         "the training images sharded over the GPUs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config != 'metric':
+        run_cfg5(args)
     else:
         run_b200(args)
 
