@@ -234,6 +234,10 @@ int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, doub
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out);
 /* xstep.setdict(dstep.getdict()) on the device (dictlrn.py:386-389): Df <- Xf. */
 int spcsc_ccmod_push_dict(spcsc_handle* h);
+/* Multi-scale dictionaries (dsz a tuple of blocks, sporco/cnvrep.py:277-360, 609-668, 894-950): hw[2 m], hw[2 m + 1] is the
+   support of filter m inside the handle's hd x wd (the largest support); the constraint projection Pcn of both dictionary
+   updates then crops / zero-means / normalises every filter over its own support.  NULL: one support for all filters. */
+int spcsc_ccmod_set_supports(spcsc_handle* h, const int32_t* hw);
 
 /* ---- consensus dictionary update: sporco.admm.ccmod.ConvCnstrMOD_Consensus (sporco/admm/ccmod.py:613-911 over
    ADMMConsensus, sporco/admm/admm.py:1419-1707) on the same handle and the same dictionary / coefficient state as

@@ -19,14 +19,28 @@ import numpy as np
 from . import cbpdn_oracle as co
 
 
+def dsz_blocks(dsz):
+    """Blocks [(h, w, [Cd,] Mb), ...] of a single- or multi-scale dictionary size (cnvrep.py:277-360)."""
+    return [tuple(b) for b in dsz] if isinstance(dsz[0], (tuple, list)) else [tuple(dsz)]
+
+
+def dsz_max(dsz):
+    """(max h, max w, [Cd,] M): the support that holds every filter."""
+    bl = dsz_blocks(dsz)
+    return (max(b[0] for b in bl), max(b[1] for b in bl)) + tuple(bl[0][2:-1]) + (sum(b[-1] for b in bl),)
+
+
 def pcn(x, dsz, Nv, zm=False):
-    """normalise(zeromean(zpad(bcrop(x)))) for x of shape (N0, N1, Cd, 1, M)  (cnvrep.py:953-1033)."""
-    h, w = dsz[0], dsz[1]
-    c = x[0:h, 0:w]
+    """normalise(zeromean(zpad(bcrop(x)))) for x of shape (N0, N1, Cd, 1, M)  (cnvrep.py:953-1033); every block of
+    a multi-scale dictionary over its own support (cnvrep.py:609-668, 894-950)."""
     p = np.zeros(x.shape, dtype=x.dtype)
-    p[0:h, 0:w] = c
-    if zm:
-        p[0:h, 0:w] -= np.mean(p[0:h, 0:w], (0, 1))
+    m0 = 0
+    for b in dsz_blocks(dsz):
+        h, w, mb = b[0], b[1], b[-1]
+        p[0:h, 0:w, ..., m0:m0 + mb] = x[0:h, 0:w, ..., m0:m0 + mb]
+        if zm:
+            p[0:h, 0:w, ..., m0:m0 + mb] -= np.mean(p[0:h, 0:w, ..., m0:m0 + mb], (0, 1))
+        m0 += mb
     vn = np.sqrt(np.sum(p ** 2, (0, 1, 2), keepdims=True))
     vn[vn == 0] = 1.0
     return np.asarray(p / vn, dtype=x.dtype)
@@ -66,7 +80,8 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
     ar = xo['AutoRho']
     dtype = np.dtype(S.dtype)
     rdt = co._rdt(dtype)
-    dsz = D0.shape
+    dsz = o.get('DictSize') or D0.shape                     # possibly multi-scale; D0 holds the largest support
+    mxd = dsz_max(dsz)
     Cd = D0.shape[2] if D0.ndim == 4 else 1
     C = S.shape[2] if S.ndim == 4 else 1
     N0, N1, K = S.shape[0], S.shape[1], S.shape[-1]
@@ -76,15 +91,9 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
     axN, axC, axK, axM = (0, 1), 2, 3, 4
 
     # ---- initial dictionary: cropped + normalised (cbpdndl.py:448-454)
-    Dn = np.zeros((dsz[0], dsz[1], Cd, 1, M), dtype=D0.dtype)
-    Dn[...] = D0.reshape(dsz[0], dsz[1], Cd, 1, M)
-    if do['ZeroMean']:
-        Dn = Dn - np.mean(Dn, (0, 1))
-    vn = np.sqrt(np.sum(Dn ** 2, (0, 1, 2), keepdims=True))
-    vn[vn == 0] = 1.0
-    Dn = np.asarray(Dn / vn, dtype=D0.dtype)
+    Dn = pcn(np.asarray(D0.reshape(mxd[0], mxd[1], Cd, 1, M)), dsz, (mxd[0], mxd[1]), zm=do['ZeroMean'])
     X0d = np.zeros((N0, N1, Cd, 1, M), dtype=D0.dtype)
-    X0d[0:dsz[0], 0:dsz[1]] = Dn
+    X0d[0:mxd[0], 0:mxd[1]] = Dn
 
     # ---- X-step state (admm/cbpdn.py ctor)
     Sm = np.asarray(S.reshape(N0, N1, C, K, 1), dtype=dtype)
@@ -190,13 +199,13 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
         drsdl = co.rfl2norm2(Xdf - Ydfprv, Xd.shape, axis=axN)
         cns = np.linalg.norm((pcn(Xd, dsz, Nv, zm=do['ZeroMean']) - Xd))
         # ================= book-keeping (dictlrn/dictlrn.py:327-363) =================
-        Dcur = np.asarray(Xd[0:dsz[0], 0:dsz[1]], dtype=dtype)
+        Dcur = np.asarray(Xd[0:mxd[0], 0:mxd[1]], dtype=dtype)
         for name, val in (('ObjFun', dfd + lm * rl1), ('DFid', dfd), ('RegL1', rl1), ('Cnstr', cns),
                           ('XPrRsdl', r), ('XDlRsdl', s), ('XRho', xrho), ('D_L', L),
                           ('D_Rsdl', drsdl)):
             cols[name].append(float(val))
     out = {k: np.array(v, dtype=np.float64) for k, v in cols.items()}
-    out['D'] = Dcur.reshape(dsz)
+    out['D'] = Dcur.reshape(mxd)
     out['X'] = Y
     out['time'] = time.perf_counter() - t0
     return out
@@ -233,10 +242,11 @@ class ConsensusCCMOD(object):
         self.dtype = np.dtype(S.dtype)
         self.rdt = co._rdt(self.dtype)
         self.dsz = dsz
-        self.Cd = dsz[2] if len(dsz) == 4 else 1
+        self.mxd = dsz_max(dsz)
+        self.Cd = self.mxd[2] if len(self.mxd) == 4 else 1
         self.C = S.shape[2] if S.ndim == 4 else 1
         self.N0, self.N1, self.K = S.shape[0], S.shape[1], S.shape[-1]
-        self.M = dsz[-1]
+        self.M = self.mxd[-1]
         self.Nv = (self.N0, self.N1)
         N0, N1, C, K, Cd, M = self.N0, self.N1, self.C, self.K, self.Cd, self.M
         self.Nb = (K if C == Cd else C * K)                      # local blocks (ccmod.py:684-686)
@@ -295,7 +305,7 @@ class ConsensusCCMOD(object):
             mAXU = np.mean(AX + self.U, axis=-1)
         else:       # blocks sharded over ranks: only the filter supports of the mean are exchanged
             loc = np.sum((AX + self.U).astype(np.float64), axis=-1) / self.NbG
-            h, w = self.dsz[0], self.dsz[1]
+            h, w = self.mxd[0], self.mxd[1]
             supp = self.reduce(loc[0:h, 0:w].copy())
             mAXU = np.zeros(self.Y.shape, self.dtype)
             mAXU[0:h, 0:w] = supp.astype(self.dtype)
@@ -365,4 +375,4 @@ class ConsensusCCMOD(object):
         return self.Y
 
     def getdict(self):
-        return self.Y[0:self.dsz[0], 0:self.dsz[1]]
+        return self.Y[0:self.mxd[0], 0:self.mxd[1]]

@@ -148,6 +148,9 @@ CDL_OPT_ZM = {'MaxMainIter': 20, 'CBPDN': {'NonNegCoef': True},
 
 CDL_OPT_CLR = {'MaxMainIter': 15, 'CBPDN': {'rho': 5.0, 'AutoRho': {'Period': 4}},
                'CCMOD': {'L': 60.0, 'ZeroMean': True}}
+MS_DSZ = ((4, 4, 3), (7, 6, 2))
+CDL_OPT_MS = {'MaxMainIter': 15, 'DictSize': MS_DSZ, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'L': 50.0, 'ZeroMean': True}}
+CDL_OPT_MS_CNS = {'MaxMainIter': 15, 'DictSize': MS_DSZ, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}
 CDL_OPT_CNS = {'MaxMainIter': 15, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}
 CDL_OPT_PGMX = {'MaxMainIter': 20, 'CBPDN': {'L': 80.0}, 'CCMOD': {'L': 40.0}}
 
@@ -364,6 +367,10 @@ def main():
                                                               'Scaling': 10.0}})
         cdl_ref_case('cdl_cns_' + sfx, dt, D0, S4, 0.1, CDL_OPT_CNS, 'admm', 'cns')
         cdl_ref_case('cdl_cns_clr1_' + sfx, dt, D0, Sc, 0.1, CDL_OPT_CNS, 'admm', 'cns')
+        # multi-scale dictionaries (DictSize a tuple of blocks): PGM and consensus D steps
+        D0m = rng.standard_normal((7, 6, 5)).astype(dt)
+        cdl_case('cdl_ms_' + sfx, dt, D0m, S4, 0.1, CDL_OPT_MS)
+        cdl_ref_case('cdl_ms_cns_' + sfx, dt, D0m, S4, 0.1, CDL_OPT_MS_CNS, 'admm', 'cns')
 
 
 if __name__ == '__main__':

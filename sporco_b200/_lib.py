@@ -32,7 +32,7 @@ SYMBOLS = (
     'spcsc_pgm_accept', 'spcsc_pgm_policy_stats', 'spcsc_pgm_combine_y', 'spcsc_pgm_finish', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
     'spcsc_p2p_attach', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
-    'spcsc_ccmod_cns_init', 'spcsc_ccmod_cns_step', 'spcsc_ccmod_cns_get',
+    'spcsc_ccmod_cns_init', 'spcsc_ccmod_cns_step', 'spcsc_ccmod_cns_get', 'spcsc_ccmod_set_supports',
 )
 
 
@@ -129,6 +129,7 @@ def _declare(lib):
     lib.spcsc_ccmod_push_dict.argtypes = [vp]
     lib.spcsc_ccmod_cns_init.argtypes = [vp, ctypes.c_double, i32, ctypes.c_int64]
     lib.spcsc_ccmod_cns_get.argtypes = [vp, i32, vp]
+    lib.spcsc_ccmod_set_supports.argtypes = [vp, vp]
     lib.spcsc_ccmod_cns_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, i32,
                                          ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
@@ -416,6 +417,14 @@ class Handle(object):
 
     def ccmod_cns_init(self, rho, y0_given, nb_global=0):
         self._c(self.lib.spcsc_ccmod_cns_init(self.h, float(rho), 1 if y0_given else 0, int(nb_global)))
+
+    def ccmod_set_supports(self, hw):
+        """Per-filter supports (M, 2) of a multi-scale dictionary, or None for one support."""
+        if hw is None:
+            self._c(self.lib.spcsc_ccmod_set_supports(self.h, None))
+            return
+        a = np.ascontiguousarray(hw, dtype=np.int32)
+        self._c(self.lib.spcsc_ccmod_set_supports(self.h, a.ctypes.data_as(ctypes.c_void_p)))
 
     def ccmod_cns_get(self, which, nb, m):
         """Block variables X (which 0) or U (1) of the consensus update in device order (nb, m, N0, N1)."""

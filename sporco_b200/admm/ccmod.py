@@ -90,6 +90,8 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
                                  cri.dsz[0], cri.dsz[1], self.dtype, device)
             handle.set_signal(self.S[..., 0])
         self._h = handle
+        # multi-scale dictionary: every filter is projected over its own support (cnvrep.py:277-360)
+        self._h.ccmod_set_supports(cr.filter_supports(dsz) if cri.multiscale else None)
         y0 = opt['Y0']
         if y0 is None:
             d0 = np.zeros((cri.dsz[0], cri.dsz[1], cri.Cd, cri.M), dtype=self.dtype)

@@ -62,20 +62,52 @@ def l1Wshape(W, cri):
     return W.shape[:-1] + (1,) * (2 - cri.dimC - cri.dimK) + W.shape[-1:]
 
 
-# ---- dictionary-update side (sporco/cnvrep.py:277-470, 868-1074), single filter-support size ----
+# ---- dictionary-update side (sporco/cnvrep.py:277-470, 868-1074) ----
+# `dsz` is (hd, wd, M) or (hd, wd, Cd, M), or -- a multi-scale dictionary -- a tuple of such tuples, one per block of
+# equally sized filters (cnvrep.py:277-360; blocks that differ in their channel count are not supported).
+
+def _is_multiscale(dsz):
+    return isinstance(dsz[0], (tuple, list))
+
+
+def _blocks(dsz, dimN):
+    """Normalised list of blocks [(hd, wd, [Cd,] Mb), ...] of a (single- or multi-scale) specification."""
+    if not _is_multiscale(dsz):
+        dsz = (dsz,)
+    out = []
+    for b in dsz:
+        if isinstance(b[0], (tuple, list)):
+            raise NotImplementedError('dictionary blocks that differ in their channel structure are not supported')
+        if len(b) not in (dimN + 1, dimN + 2):
+            raise ValueError('dsz must have dimN+1 or dimN+2 entries (per block)')
+        out.append(tuple(int(v) for v in b))
+    if len(set(len(b) for b in out)) != 1 or (len(out[0]) == dimN + 2 and len(set(b[dimN] for b in out)) != 1):
+        raise NotImplementedError('all blocks of a multi-scale dictionary must have the same number of channels')
+    return out
+
 
 def _single_support(dsz, dimN):
-    if isinstance(dsz[0], (tuple, list)):
-        raise NotImplementedError('multi-scale dictionary size specifications are not supported')
-    if len(dsz) not in (dimN + 1, dimN + 2):
-        raise ValueError('dsz must have dimN+1 or dimN+2 entries')
-    return tuple(int(v) for v in dsz)
+    """(max hd, max wd, [Cd,] M) of the specification: the support that holds every filter."""
+    bl = _blocks(dsz, dimN)
+    mx = tuple(max(b[i] for b in bl) for i in range(dimN))
+    return mx + tuple(bl[0][dimN:-1]) + (sum(b[-1] for b in bl),)
+
+
+def filter_supports(dsz, dimN=2):
+    """Per filter: its support size, as an (M, dimN) integer array."""
+    rows = []
+    for b in _blocks(dsz, dimN):
+        rows += [list(b[:dimN])] * b[-1]
+    return np.array(rows, dtype=np.int32)
 
 
 class CDU_ConvRepIndexing(object):
-    """Array roles for the dictionary update: `dsz` is (hd, wd, M) or (hd, wd, Cd, M)."""
+    """Array roles for the dictionary update: `dsz` is (hd, wd, M) or (hd, wd, Cd, M) or a tuple of such blocks;
+    `self.dsz` is the support that holds every filter, `self.dsz_spec` what was given."""
 
     def __init__(self, dsz, S, dimK=None, dimN=2):
+        self.dsz_spec = dsz
+        self.multiscale = _is_multiscale(dsz)
         dsz = _single_support(dsz, dimN)
         self.dsz = dsz
         self.dimCd = len(dsz) - dimN - 1
@@ -121,17 +153,31 @@ def zpad(x, Nv):
 
 
 def bcrop(x, dsz, dimN=2):
-    """Crop the leading (spatial) axes to the filter support (cnvrep.py:894-932)."""
-    dsz = _single_support(dsz, dimN)
-    return x[tuple(slice(0, n) for n in dsz[:dimN])]
+    """Crop the leading (spatial) axes to the filter support; with a multi-scale specification to the largest
+    support, every block of filters zero outside its own (cnvrep.py:894-950)."""
+    mx = _single_support(dsz, dimN)
+    out = x[tuple(slice(0, n) for n in mx[:dimN])]
+    if not _is_multiscale(dsz):
+        return out
+    out = np.array(out)
+    m0 = 0
+    for b in _blocks(dsz, dimN):
+        keep = np.zeros(mx[:dimN], dtype=bool)
+        keep[tuple(slice(0, n) for n in b[:dimN])] = True
+        blk = out[..., m0:m0 + b[-1]]
+        blk[~keep] = 0
+        m0 += b[-1]
+    return out
 
 
 def zeromean(v, dsz, dimN=2):
-    """Subtract, per filter and channel, the mean over the filter support (cnvrep.py:779-820)."""
-    dsz = _single_support(dsz, dimN)
+    """Subtract, per filter and channel, the mean over the filter's own support (cnvrep.py:609-668)."""
     vz = v.copy()
-    sl = tuple(slice(0, n) for n in dsz[:dimN])
-    vz[sl] -= np.mean(v[sl], axis=tuple(range(dimN)))
+    m0 = 0
+    for b in _blocks(dsz, dimN):
+        sl = tuple(slice(0, n) for n in b[:dimN]) + (Ellipsis, slice(m0, m0 + b[-1]))
+        vz[sl] -= np.mean(v[sl], axis=tuple(range(dimN)))
+        m0 += b[-1]
     return vz
 
 

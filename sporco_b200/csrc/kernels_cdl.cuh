@@ -102,11 +102,14 @@ SPCSC_GLOBAL void k_ccmod_step(const C2<T>* SPCSC_RESTRICT Yf, const C2<T>* SPCS
 // support) is accumulated instead of writing X.
 template <typename T>
 SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* SPCSC_RESTRICT acc,
-                        int Cd, int M, int N0, int N1, int hd, int wd, int zero_mean, int check) {
+                        int Cd, int M, int N0, int N1, int hd, int wd, int zero_mean, int check,
+                        const int* SPCSC_RESTRICT supp = nullptr) {
     __shared__ double red[4 * 32];
     __shared__ double bc[8];
     const int m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int ns = hd * wd;
+    // multi-scale dictionaries (cnvrep.py:277-360): filter m has its own support hm x wm <= hd x wd
+    const int hm = supp ? supp[2 * m] : hd, wm = supp ? supp[2 * m + 1] : wd;
+    const int ns = hm * wm;
     // per-channel means over the support, then the norm of the (mean-free) support
     double nrm2 = 0.0;
     for (int c = 0; c < Cd; ++c) {
@@ -114,7 +117,7 @@ SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* 
         double mean = 0.0;
         if (zero_mean) {
             double s[1] = {0.0};
-            for (int e = tid; e < ns; e += nt) s[0] += (double)v[(size_t)(e / wd) * N1 + (e % wd)];
+            for (int e = tid; e < ns; e += nt) s[0] += (double)v[(size_t)(e / wm) * N1 + (e % wm)];
             if (tid == 0) bc[0] = 0.0;
             __syncthreads();
             block_accumulate<1>(s, red, bc);
@@ -124,7 +127,7 @@ SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* 
         }
         double s2[1] = {0.0};
         for (int e = tid; e < ns; e += nt) {
-            const double x = (double)((T)((double)v[(size_t)(e / wd) * N1 + (e % wd)] - (T)mean));
+            const double x = (double)((T)((double)v[(size_t)(e / wm) * N1 + (e % wm)] - (T)mean));
             s2[0] += x * x;
         }
         if (tid == 0) bc[1] = 0.0;
@@ -146,13 +149,22 @@ SPCSC_GLOBAL void k_pcn(const T* SPCSC_RESTRICT V, T* SPCSC_RESTRICT X, double* 
         const T* v = V + ((size_t)c * M + m) * N0 * N1;
         T* x = X ? X + ((size_t)c * M + m) * N0 * N1 : nullptr;
         for (int e = tid; e < ns; e += nt) {
-            const size_t o = (size_t)(e / wd) * N1 + (e % wd);
+            const size_t o = (size_t)(e / wm) * N1 + (e % wm);
             const T p = (v[o] - mean) / vn;
             if (check) {
                 const double d = (double)(p - v[o]);
                 d2[0] += d * d;
             } else {
                 x[o] = p;
+            }
+        }
+        if (supp) {       // the part of the largest support that lies outside this filter's own
+            for (int e = tid; e < hd * wd; e += nt) {
+                const int y = e / wd, xx = e % wd;
+                if (y < hm && xx < wm) continue;
+                const size_t o = (size_t)y * N1 + xx;
+                if (check) d2[0] += (double)v[o] * (double)v[o];
+                else x[o] = (T)0;
             }
         }
     }

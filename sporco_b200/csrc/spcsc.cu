@@ -318,6 +318,7 @@ struct spcsc_handle {
     virtual int ccmod_cns_init(double rho, int y0_given, long long nb_global) = 0;
     virtual int ccmod_cns_step(double rho, double udiv, double rlx, int flags, double* out) = 0;
     virtual int ccmod_cns_get(int which, void* out) = 0;
+    virtual int ccmod_set_supports(const int32_t* hw) = 0;
 };
 
 namespace {
@@ -406,6 +407,7 @@ class Engine : public spcsc_handle {
     DevBuf<C2<T>> cdZf;                             // coefficient spectra, slab layout [K][N1f][M][N0]
     bool cd_ready = false, cd_have_coef = false;
     int cd_zero_mean = 0;
+    DevBuf<int> cd_fsupp;                           // multi-scale dictionaries: (h_m, w_m) per filter, else unallocated
     // consensus dictionary update (admm.ccmod.ConvCnstrMOD_Consensus): per-block copies of the dictionary and
     // duals [K*C][M][N0][N1], their row/column spectra, the Gram rows of the coefficient spectra, the new Y
     DevBuf<T> cnsX, cnsU, cnsYn;
@@ -469,7 +471,7 @@ class Engine : public spcsc_handle {
         pgA.release(); pgB.release(); Zt2.release();
         pgZ.release(); pgYp.release(); pg_sx.release(); pg_rprev.release(); pg_sxprev.release();
         cd_supp.release(); cdX.release(); cdXf.release(); cdYf.release(); cdV.release(); cdG.release(); cdZf.release(); ghg_buf.release(); gw_buf.release();
-        cnsX.release(); cnsU.release(); cnsYn.release(); cnsZ.release(); cnsZ2.release(); cnsG.release(); cns_st.release();
+        cnsX.release(); cnsU.release(); cnsYn.release(); cd_fsupp.release(); cnsZ.release(); cnsZ2.release(); cnsG.release(); cns_st.release();
         mk_W.release(); mk_r.release(); mk_wr.release(); mk_w2r.release(); mk_f.release(); mk_grad.release(); mk_sx.release();
 #ifndef SPCSC_EMU
 #endif
@@ -1513,7 +1515,7 @@ class Engine : public spcsc_handle {
         }
         // X = Pcn(V) ; Xf = rfftn(X)  (into cdV, the old Xf stays in cdXf as Xfprv)
         CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, cdX.p, acc.p, Cd, M,
-                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 0));
+                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 0, (const int*)cd_fsupp.p));
         rc = forward2d(cdX.p, cdV.p, M, Cd);
         if (rc) return rc;
         // residual against Yfprv (= Yf before the momentum step), then the momentum step
@@ -1536,7 +1538,7 @@ class Engine : public spcsc_handle {
         }
         if (flags & SPCSC_CCMOD_CNSTR)
             CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
-                      N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
+                      N0, N1, pb.hd, pb.wd, cd_zero_mean, 1, (const int*)cd_fsupp.p));
         double ha[4];
         CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
         // slots ACC_CDL_* alias ADMM accumulators (ACC_AX2 ...: LinSolveCheck sums of the X step that shares
@@ -1682,7 +1684,7 @@ class Engine : public spcsc_handle {
                       pb.hd, pb.wd, 1));
         }
         CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, cnsYn.p, acc.p, Cd, M,
-                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 0));
+                  N0, N1, pb.hd, pb.wd, cd_zero_mean, 0, (const int*)cd_fsupp.p));
         // u step and the norms of the residuals
         CK(cudaMemsetAsync(acc.p + ACC_CNS_X2, 0, 5 * sizeof(double), stream));
         CK(launch(k_cns_update<T>, dim3(148, NB), dim3(256), 0, stream, (const T*)cnsX.p, cnsU.p, (const T*)cdX.p,
@@ -1708,7 +1710,7 @@ class Engine : public spcsc_handle {
             }
             if (flags & SPCSC_CCMOD_CNSTR)
                 CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
-                          N0, N1, pb.hd, pb.wd, cd_zero_mean, 1));
+                          N0, N1, pb.hd, pb.wd, cd_zero_mean, 1, (const int*)cd_fsupp.p));
             CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
             CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
         }
@@ -1718,6 +1720,19 @@ class Engine : public spcsc_handle {
         out[1] = std::sqrt(ha[3]);
         out[2] = hn[0]; out[3] = hn[1]; out[4] = hn[2]; out[5] = hn[3]; out[6] = hn[4];
         out[7] = lscheck ? (hls[1] > 0.0 ? std::sqrt(hls[0] / hls[1]) : std::sqrt(hls[0])) : -1.0;
+        return SPCSC_OK;
+    }
+    // multi-scale dictionaries: the support (h_m, w_m) of every filter; NULL: all filters use the handle's hd x wd
+    int ccmod_set_supports(const int32_t* hw) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        CK(cudaSetDevice(pb.device));
+        if (!hw) { cd_fsupp.release(); return SPCSC_OK; }
+        for (int m = 0; m < M; ++m)
+            if (hw[2 * m] < 1 || hw[2 * m] > pb.hd || hw[2 * m + 1] < 1 || hw[2 * m + 1] > pb.wd)
+                FAIL(SPCSC_ERR_INVALID, "filter support outside the handle's hd x wd");
+        CK(cd_fsupp.ensure((size_t)2 * M));
+        CK(cudaMemcpyAsync(cd_fsupp.p, hw, (size_t)2 * M * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
         return SPCSC_OK;
     }
     // block variables in device order [K*C][M][N0][N1]: which 0 = X (after the last step), 1 = U
@@ -2277,6 +2292,7 @@ int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, doub
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
 int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global) { H_CALL(h->ccmod_cns_init(rho, y0_given, (long long)nb_global)); }
+int spcsc_ccmod_set_supports(spcsc_handle* h, const int32_t* hw) { H_CALL(h->ccmod_set_supports(hw)); }
 int spcsc_ccmod_cns_get(spcsc_handle* h, int32_t which, void* out) { H_CALL(out ? h->ccmod_cns_get(which, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_cns_step(spcsc_handle* h, double rho, double udiv, double rlx, int32_t flags, double out[8]) { H_CALL(out ? h->ccmod_cns_step(rho, udiv, rlx, flags, out) : SPCSC_ERR_INVALID); }
 int spcsc_comm_unique_id(const char* nccl_lib, void* id128) {

@@ -10,7 +10,7 @@ sequence, as the reference does.  When the object is built by
 coefficient maps and dictionary pass between the two steps without leaving the GPU.
 
 Supported: greyscale and multi-channel signals with a single-channel or a multi-channel
-dictionary, one filter-support size, fixed step 1/L with Nesterov (or linear) momentum.  Backtracking, ``Monotone`` and ``StepSizePolicy`` raise
+dictionary, single- or multi-scale filter supports, fixed step 1/L with Nesterov (or linear) momentum.  Backtracking, ``Monotone`` and ``StepSizePolicy`` raise
 ``NotImplementedError``.
 """
 
@@ -62,6 +62,8 @@ class ConvCnstrMOD(pgm.PGMDFT):
                                  cri.dsz[0], cri.dsz[1], self.dtype, device)
             handle.set_signal(self.S[..., 0])
         self._h = handle
+        # multi-scale dictionary: every filter is projected over its own support (cnvrep.py:277-360)
+        self._h.ccmod_set_supports(cr.filter_supports(dsz) if cri.multiscale else None)
         x0 = opt['X0']
         if x0 is None:
             d0 = np.zeros((cri.dsz[0], cri.dsz[1], cri.Cd, cri.M), dtype=self.dtype)

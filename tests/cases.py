@@ -415,6 +415,11 @@ CDL_CASES = {
     'cdl_cns': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}, 'admm', 0.1, 'cns'),
     'cdl_cns_clr1': ({'MaxMainIter': 15, 'CBPDN': {'rho': 5.0}, 'CCMOD': {'rho': 2.0, 'ZeroMean': True}}, 'admm', 0.1,
                      'cns'),
+    # multi-scale dictionary (DictSize a tuple of blocks: three 4x4 and two 7x6 filters), PGM and consensus D steps
+    'cdl_ms': ({'MaxMainIter': 15, 'DictSize': ((4, 4, 3), (7, 6, 2)), 'CBPDN': {'rho': 5.0},
+                'CCMOD': {'L': 50.0, 'ZeroMean': True}}, 'admm', 0.1),
+    'cdl_ms_cns': ({'MaxMainIter': 15, 'DictSize': ((4, 4, 3), (7, 6, 2)), 'CBPDN': {'rho': 5.0},
+                    'CCMOD': {'rho': 2.0, 'ZeroMean': True}}, 'admm', 0.1, 'cns'),
 }
 
 
@@ -452,6 +457,11 @@ def run_cdl_case(tag, sfx):
     full = b.getdict(crop=False)
     assert full.shape[:2] == g['S'].shape[:2] and not np.any(full[D.shape[0]:]) \
         and not np.any(full[:, D.shape[1]:])
+    if o.get('DictSize') is not None:                   # every block zero outside its own support
+        m0 = 0
+        for blk in o['DictSize']:
+            assert not np.any(D[blk[0]:, ..., m0:m0 + blk[-1]]) and not np.any(D[:, blk[1]:, ..., m0:m0 + blk[-1]])
+            m0 += blk[-1]
     rec = b.reconstruct()
     assert rec.shape[:2] == g['S'].shape[:2]
     assert rel(b.xstep.D.squeeze(), D.squeeze()) == 0.0

@@ -67,7 +67,7 @@ def _gloo_cdl_worker(rank, world, port, q):
         dist.all_reduce(t)
         return t.numpy()
 
-    o, _, lmbda = cases.CDL_CASES['cdl']
+    o, _, lmbda = cases.CDL_CASES['cdl'][:3]
     r = ocdl.cbpdndl(g['D0'], S[:, :, mine], lmbda, o, reduce=reduce)
     q.put((rank, cases.rel(r['D'], g['D'].squeeze()), cases.rel(r['X'], g['X'][:, :, :, mine, :]),
            cases.rel(r['ObjFun'], g['ObjFun']), cases.rel(r['XRho'], g['XRho']),

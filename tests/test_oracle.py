@@ -52,11 +52,11 @@ def test_oracle_reproduces_golden_pgm(sfx):
 
 
 @pytest.mark.parametrize('sfx', ['f64', 'f32'])
-@pytest.mark.parametrize('tag', ['cdl', 'cdl_zm', 'cdl_clr1', 'cdl_clr3'])
+@pytest.mark.parametrize('tag', ['cdl', 'cdl_zm', 'cdl_clr1', 'cdl_clr3', 'cdl_ms'])
 def test_oracle_reproduces_golden_dictionary_learning(tag, sfx):
     from oracle import cbpdndl_oracle as ocdl
     g = cases.load('%s_%s' % (tag, sfx))
-    o, _, lmbda = cases.CDL_CASES[tag]
+    o, _, lmbda = cases.CDL_CASES[tag][:3]
     r = ocdl.cbpdndl(g['D0'], g['S'], lmbda, o)
     assert np.array_equal(r['D'], g['D'].squeeze())
     assert np.array_equal(r['X'], g['X'])

@@ -28,7 +28,7 @@ NOT_IMPLEMENTED = {
     'admm': {'test_10cplx': 'complex-valued data'},
     'pgm': {'test_10cplx': 'complex-valued data'},
     # tests/admm/test_ccmod.py with ConvCnstrMOD_Consensus and the factory functions replaced (default method 'cns')
-    'ccmod': {'test_03cplx': 'complex-valued data', 'test_05': 'multi-scale dictionary (dsz a tuple of tuples)',
+    'ccmod': {'test_03cplx': 'complex-valued data',
               'test_13': 'multi-channel coefficient maps together with a multi-channel dictionary (runs in the '
                          'reference through numpy broadcasting only; not a documented configuration)'},
 }
@@ -114,7 +114,7 @@ def test_reference_admm_suite(name):
 
 # 2000-iteration recovery tests: ~1 min each under emulation; they pass (run them with
 # SPCSC_LONG_TESTS=1) but are kept out of the default CPU suite to keep it short
-LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03', 'test_04')}       # test_03 / test_04: up to 500 / 1000 iterations, 4-8 min emulated
+LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03', 'test_04', 'test_05')}       # up to 500 / 1000 / 1000 iterations, 4-8 min emulated each
 
 
 @pytest.mark.parametrize('name', _cases('pgm'))
