@@ -230,6 +230,13 @@ int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z);
    FastSolve is set, pgm/pgm.py:347-356): out[0] needs SPCSC_CCMOD_DFID, out[1] SPCSC_CCMOD_CNSTR. */
 enum { SPCSC_CCMOD_DFID = 1, SPCSC_CCMOD_CNSTR = 2, SPCSC_CCMOD_LINSOLVE = 4 };
 int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]);
+/* The same iteration in two parts for a backtracking search over L (sporco/pgm/backtrack.py:74-107 on
+   pgm/ccmod.py:295-318, 379-393, pgm/pgm.py:850-894).  spcsc_ccmod_trial: proximal step at 1/L from the current
+   momentum point (the gradient is computed once per iteration and kept across trials); out = { f(X) = obfn_f of the
+   candidate, f(Y), <grad f(Y), X - Y>, ||X - Y||^2 }, plain sums over the stored half spectra and over all ranks.
+   spcsc_ccmod_accept: ystep, residual, objective of the last candidate; out as spcsc_ccmod_step. */
+int spcsc_ccmod_trial(spcsc_handle* h, double L, double out[4]);
+int spcsc_ccmod_accept(spcsc_handle* h, double coef, int32_t flags, double out[4]);
 /* getdict(crop=True): (hd, wd, Cd, M).                                     pgm/ccmod.py:283-291 */
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out);
 /* xstep.setdict(dstep.getdict()) on the device (dictlrn.py:386-389): Df <- Xf. */

@@ -210,6 +210,19 @@ def cns_case(tag, dt, Z, S, dsz, opt):
     print('wrote', tag)
 
 
+def ccmod_bt_case(tag, dt, Z, S, dsz, opt_ref):
+    """pgm.ccmod.ConvCnstrMOD with BacktrackStandard (pgm/backtrack.py:74-107): the fixture holds the reference's outputs."""
+    from sporco.pgm import ccmod as rpccmod
+    c = rpccmod.ConvCnstrMOD(Z, S, dsz, rpccmod.ConvCnstrMOD.Options(dict(opt_ref, Verbose=False)))
+    c.solve()
+    its = c.getitstat()
+    out = dict(Z=Z, S=S, dsz=np.array(dsz), D=c.getdict())
+    for name in ('DFid', 'Cnstr', 'Rsdl', 'F_Btrack', 'Q_Btrack', 'IterBTrack', 'L'):
+        out[name] = stat(its, name)
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), **out)
+    print('wrote', tag)
+
+
 def tikhonov():
     """sporco.signal.tikhonov_filter on a few shapes (padded sizes: power of two, composite, odd)."""
     from sporco import signal as rsignal
@@ -367,6 +380,18 @@ def main():
                                                               'Scaling': 10.0}})
         cdl_ref_case('cdl_cns_' + sfx, dt, D0, S4, 0.1, CDL_OPT_CNS, 'admm', 'cns')
         cdl_ref_case('cdl_cns_clr1_' + sfx, dt, D0, Sc, 0.1, CDL_OPT_CNS, 'admm', 'cns')
+        # backtracking in the D step, alone and inside dictionary learning (PGM X step with backtracking, colour,
+        # multi-scale: the configuration of examples/scripts/cdl/cbpdndl_pgm_clr.py in small)
+        Zb = (rng.standard_normal((16, 32, 1, 3, 5)) * (rng.random((16, 32, 1, 3, 5)) < 0.2)).astype(dt)
+        Sb = rng.standard_normal((16, 32, 3)).astype(dt)
+        ccmod_bt_case('ccmod_bt_' + sfx, dt, Zb, Sb, (4, 6, 5),
+                      {'MaxMainIter': 12, 'L': 2.0, 'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=10),
+                       'RelStopTol': 0.0, 'ZeroMean': True})
+        D0e = rng.standard_normal((7, 6, 3, 5)).astype(dt)
+        cdl_ref_case('cdl_bt_clr_ms_' + sfx, dt, D0e, Sc, 0.1,
+                     {'MaxMainIter': 12, 'DictSize': ((4, 4, 3, 3), (7, 6, 3, 2)),
+                      'CBPDN': {'Backtrack': BacktrackStandard(gamma_u=1.1), 'L': 10.0},
+                      'CCMOD': {'Backtrack': BacktrackStandard(), 'L': 5.0}}, 'pgm')
         # multi-scale dictionaries (DictSize a tuple of blocks): PGM and consensus D steps
         D0m = rng.standard_normal((7, 6, 5)).astype(dt)
         cdl_case('cdl_ms_' + sfx, dt, D0m, S4, 0.1, CDL_OPT_MS)

@@ -31,7 +31,7 @@ SYMBOLS = (
     'spcsc_trim_pools', 'spcsc_pgm_configure', 'spcsc_pgm_reset', 'spcsc_pgm_trial',
     'spcsc_pgm_accept', 'spcsc_pgm_policy_stats', 'spcsc_pgm_combine_y', 'spcsc_pgm_finish', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
     'spcsc_p2p_attach', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
-    'spcsc_ccmod_step', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
+    'spcsc_ccmod_step', 'spcsc_ccmod_trial', 'spcsc_ccmod_accept', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
     'spcsc_ccmod_cns_init', 'spcsc_ccmod_cns_step', 'spcsc_ccmod_cns_get', 'spcsc_ccmod_set_supports',
 )
 
@@ -125,6 +125,8 @@ def _declare(lib):
     lib.spcsc_ccmod_setcoef_device.argtypes = [vp, i32]
     lib.spcsc_ccmod_setcoef.argtypes = [vp, vp]
     lib.spcsc_ccmod_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.spcsc_ccmod_trial.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    lib.spcsc_ccmod_accept.argtypes = [vp, ctypes.c_double, i32, ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_ccmod_get_dict.argtypes = [vp, vp]
     lib.spcsc_ccmod_push_dict.argtypes = [vp]
     lib.spcsc_ccmod_cns_init.argtypes = [vp, ctypes.c_double, i32, ctypes.c_int64]
@@ -414,6 +416,16 @@ class Handle(object):
 
     def ccmod_push_dict(self):
         self._c(self.lib.spcsc_ccmod_push_dict(self.h))
+
+    def ccmod_trial(self, L):
+        out = (ctypes.c_double * 4)()
+        self._c(self.lib.spcsc_ccmod_trial(self.h, float(L), out))
+        return [float(x) for x in out]
+
+    def ccmod_accept(self, coef, flags=3):
+        out = (ctypes.c_double * 4)()
+        self._c(self.lib.spcsc_ccmod_accept(self.h, float(coef), int(flags), out))
+        return [float(x) for x in out]
 
     def ccmod_cns_init(self, rho, y0_given, nb_global=0):
         self._c(self.lib.spcsc_ccmod_cns_init(self.h, float(rho), 1 if y0_given else 0, int(nb_global)))

@@ -191,6 +191,21 @@ SPCSC_GLOBAL void k_spec_diffnorm(const C2<T>* SPCSC_RESTRICT A, const C2<T>* SP
     block_accumulate<1>(s, red, acc + ACC_CDL_RSDL);
 }
 
+// Backtracking terms of the dictionary update over spectra in slab order: sum Re(conj(X - Y) g)  (eval_linear_approx,
+// pgm/pgm.py:886-894) and sum |X - Y|^2, plain sums over the stored half spectrum.
+template <typename T>
+SPCSC_GLOBAL void k_spec_lin(const C2<T>* SPCSC_RESTRICT X, const C2<T>* SPCSC_RESTRICT Y, const C2<T>* SPCSC_RESTRICT G,
+                             double* SPCSC_RESTRICT acc, size_t n) {
+    __shared__ double red[2 * 32];
+    double s[2] = {0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const C2<T> d = X[i] - Y[i], g = G[i];
+        s[0] += (double)d.re * (double)g.re + (double)d.im * (double)g.im;
+        s[1] += (double)abs2(d);
+    }
+    block_accumulate<2>(s, red, acc + ACC_CDL_RSDL);
+}
+
 // Cropped dictionary in the reference's order (hd, wd, Cd, M) from the device order [Cd][M][N0][N1].
 template <typename T>
 SPCSC_GLOBAL void k_crop_dict(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT D, int hd, int wd, int Cd,

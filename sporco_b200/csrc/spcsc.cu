@@ -313,6 +313,8 @@ struct spcsc_handle {
     virtual int ccmod_setcoef_device(int source) = 0;
     virtual int ccmod_setcoef(const void* Z) = 0;
     virtual int ccmod_step(double L, double coef, int flags, double* out) = 0;
+    virtual int ccmod_trial(double L, double* out) = 0;
+    virtual int ccmod_accept(double coef, int flags, double* out) = 0;
     virtual int ccmod_get_dict(void* out) = 0;
     virtual int ccmod_push_dict() = 0;
     virtual int ccmod_cns_init(double rho, int y0_given, long long nb_global) = 0;
@@ -1409,6 +1411,7 @@ class Engine : public spcsc_handle {
         CK(cudaStreamSynchronize(stream));
         cd_zero_mean = zero_mean;
         cd_ready = true;
+        cd_grad_valid = false;
         cns_ready = false;
         return SPCSC_OK;
     }
@@ -1427,6 +1430,7 @@ class Engine : public spcsc_handle {
             FAIL(SPCSC_ERR_INVALID, "unknown coefficient source");
         }
         cd_have_coef = true;
+        cd_grad_valid = false;
         cns_gram_stale = true;
         return SPCSC_OK;
     }
@@ -1442,6 +1446,7 @@ class Engine : public spcsc_handle {
         if (rc) return rc;
         CK(cudaStreamSynchronize(stream));
         cd_have_coef = true;
+        cd_grad_valid = false;
         cns_gram_stale = true;
         return SPCSC_OK;
     }
@@ -1465,31 +1470,40 @@ class Engine : public spcsc_handle {
         }
         return cudaSuccess;
     }
-    int ccmod_step(double L, double coef, int flags, double* out) override {
-        int rc = ccmod_check();
-        if (rc) return rc;
-        if (!cd_ready || !cd_have_coef) FAIL(SPCSC_ERR_STATE, "ccmod_step before ccmod_reset / setcoef");
-        if (!(L > 0.0)) FAIL(SPCSC_ERR_INVALID, "L must be positive");
-        CK(cudaSetDevice(pb.device));
+    // ---- one PGM iteration of the dictionary update = proximal trial(s) at step 1/L + acceptance.
+    // Part A (sporco/pgm/pgm.py:779-811 PGMDFT.xstep with pgm/ccmod.py:295-318 grad_f): gradient at Yf (once per
+    // iteration: kept in cdG across the trials of a backtracking search), Vf = Yf - g/L, V = irfftn(Vf), X = Pcn(V)
+    // into cdX, Xf = rfftn(X) into cdV (the accepted iterate stays in cdXf).
+    bool cd_grad_valid = false;
+    double cd_fY = 0.0;                              // obfn_f(Yf) = sum |R(Yf)|^2 / 2 over the stored half spectrum (all ranks)
+    int ccmod_part_a(double L) {
         const size_t nsp = (size_t)Cd * N1f * M * N0;
-        const int even = (N1 % 2 == 0) ? 1 : 0;
-        double hF = 0.0;
-        CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
-        // gradient at Yf (one pass over the coefficient spectra)
-        CK(launch_grad<true>((const C2<T>*)cdYf.p, cdG.p));
+        const int nsupp = pb.hd * pb.wd * Cd * M;
         // Images sharded over ranks: the gradient is a sum over all of them.  Pcn only looks at the filter
         // supports and cropping is linear (cnvrep.py:953-981), so instead of all-reducing the 2 N0 N1f Cd M values of
         // the spectral gradient every rank forms V_r = irfftn(Yf / R - g_r / L), and only the hd x wd supports of
         // V = sum_r V_r are exchanged (hd wd Cd M values: 16 KB at 8x8x64) -- over the peer-memory block when the
         // ranks have mapped each other, else by one small NCCL call.
-        const int nsupp = pb.hd * pb.wd * Cd * M;
         const bool crop_reduce = nccl_comm && (p2p_on ? nsupp <= kP2pVecMax : true) &&
                                  !(getenv("SPCSC_CDL_FULLREDUCE") && atoi(getenv("SPCSC_CDL_FULLREDUCE")) == 1);
-        if (nccl_comm && !crop_reduce) {
-            int nr = nccl->AllReduce(cdG.p, cdG.p, 2 * nsp, sizeof(T) == 4 ? 7 : 8, 0, nccl_comm, stream);
-            if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+        if (!cd_grad_valid) {
+            double hF = 0.0;
+            CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+            CK(launch_grad<true>((const C2<T>*)cdYf.p, cdG.p));     // one pass over the coefficient spectra
+            if (nccl_comm && !crop_reduce) {
+                int nr = nccl->AllReduce(cdG.p, cdG.p, 2 * nsp, sizeof(T) == 4 ? 7 : 8, 0, nccl_comm, stream);
+                if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
+            }
+            if (nccl_comm) {                                         // f(Yf) of all images
+                int rc = reduce_acc_over_ranks();
+                if (rc) return rc;
+            }
+            CK(cudaMemcpyAsync(&hF, acc.p + ACC_CDL_F, sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+            CK(cudaStreamSynchronize(stream));
+            cd_fY = 0.5 * hF;
+            cd_grad_valid = true;
         }
-        CK(cudaMemcpyAsync(&hF, acc.p + ACC_CDL_F, sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(launch(k_ccmod_step<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)cdYf.p,
                   (const C2<T>*)cdG.p, cdV.p, (T)L, crop_reduce ? (T)(1.0 / (double)nranks) : (T)1, nsp));
         // V = irfftn(Vf): inverse columns, inverse rows
@@ -1516,25 +1530,26 @@ class Engine : public spcsc_handle {
         // X = Pcn(V) ; Xf = rfftn(X)  (into cdV, the old Xf stays in cdXf as Xfprv)
         CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, cdX.p, acc.p, Cd, M,
                   N0, N1, pb.hd, pb.wd, cd_zero_mean, 0, (const int*)cd_fsupp.p));
-        rc = forward2d(cdX.p, cdV.p, M, Cd);
-        if (rc) return rc;
-        // residual against Yfprv (= Yf before the momentum step), then the momentum step
+        return forward2d(cdX.p, cdV.p, M, Cd);
+    }
+    // Part B (pgm/pgm.py:815-831 ystep, pgm/ccmod.py:341-376): residual against Yfprv, momentum step, the candidate
+    // becomes the iterate, objective terms.
+    int ccmod_part_b(double coef, int flags, double* out) {
+        const size_t nsp = (size_t)Cd * N1f * M * N0;
+        const int even = (N1 % 2 == 0) ? 1 : 0;
         CK(launch(k_spec_diffnorm<T>, dim3(296), dim3(256), 0, stream, (const C2<T>*)cdV.p,
                   (const C2<T>*)cdYf.p, acc.p, Cd, N1f, (size_t)M * N0, even));
         CK(launch(k_pgm_momentum<T>, dim3(592), dim3(256), 0, stream, (const C2<T>*)cdV.p,
                   (const C2<T>*)cdXf.p, cdYf.p, (T)coef, nsp));
         std::swap(cdXf.p, cdV.p);
         std::swap(cdXf.n, cdV.n);
+        cd_grad_valid = false;
         // objective terms of the new iterate: data fidelity (second pass over Zf), constraint violation
         CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 2 * sizeof(double), stream));
         if (flags & SPCSC_CCMOD_DFID) CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
         if (nccl_comm && (flags & SPCSC_CCMOD_DFID)) {
-            if (p2p_on) {       // the 16 accumulators over the peer block, as in the ADMM iteration
-                CK(launch(k_p2p_allreduce_acc<0>, dim3(1), dim3(256), 0, stream, p2p, acc.p, &st.p->stopped));
-            } else {
-                int nr = nccl->AllReduce(acc.p + ACC_CDL_DFID, acc.p + ACC_CDL_DFID, 1, 8, 0, nccl_comm, stream);
-                if (nr != 0) { err = std::string("ncclAllReduce: ") + nccl->GetErrorString(nr); poisoned = true; return SPCSC_ERR_NCCL; }
-            }
+            int rc = reduce_acc_over_ranks();       // the 16 accumulators over the peer block (or one small NCCL call)
+            if (rc) return rc;
         }
         if (flags & SPCSC_CCMOD_CNSTR)
             CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)cdX.p, (T*)nullptr, acc.p, Cd, M,
@@ -1548,12 +1563,65 @@ class Engine : public spcsc_handle {
         const double inv_n = 1.0 / ((double)N0 * (double)N1);
         out[0] = 0.5 * ha[1] * inv_n;
         out[1] = std::sqrt(ha[3]);
-        // the residual is computed from the (rank-identical) dictionary on every rank; the peer-memory exchange
-        // above sums all accumulator slots, this one included
-        const bool rsdl_summed = nccl_comm && p2p_on && (flags & SPCSC_CCMOD_DFID);
+        // the residual is computed from the (rank-identical) dictionary on every rank; the exchange above sums all
+        // accumulator slots, this one included
+        const bool rsdl_summed = nccl_comm && (flags & SPCSC_CCMOD_DFID);
         out[2] = ha[2] * inv_n / (rsdl_summed ? (double)nranks : 1.0);
-        out[3] = 0.5 * hF;
+        out[3] = cd_fY;
         return SPCSC_OK;
+    }
+    int ccmod_step_check(double L) {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cd_ready || !cd_have_coef) FAIL(SPCSC_ERR_STATE, "dictionary update step before ccmod_reset / setcoef");
+        if (!(L > 0.0)) FAIL(SPCSC_ERR_INVALID, "L must be positive");
+        CK(cudaSetDevice(pb.device));
+        return SPCSC_OK;
+    }
+    int ccmod_step(double L, double coef, int flags, double* out) override {
+        int rc = ccmod_step_check(L);
+        if (rc) return rc;
+        rc = ccmod_part_a(L);
+        if (rc) return rc;
+        return ccmod_part_b(coef, flags, out);
+    }
+    // One trial of a backtracking search (sporco/pgm/backtrack.py:74-107): out = { f(X) = obfn_f of the candidate,
+    // f(Y), <grad f(Y), X - Y> (eval_linear_approx, pgm/pgm.py:886-894), ||X - Y||^2 } over the stored half spectra;
+    // the host forms Q = f(Y) + <.,.> + (L/2) ||X - Y||^2 and decides.  spcsc_ccmod_accept then completes the iteration.
+    int ccmod_trial(double L, double* out) override {
+        int rc = ccmod_step_check(L);
+        if (rc) return rc;
+        rc = ccmod_part_a(L);
+        if (rc) return rc;
+        const size_t nsp = (size_t)Cd * N1f * M * N0;
+        CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+        CK(launch_grad<false>((const C2<T>*)cdV.p, (C2<T>*)nullptr));             // f(X): pass over the coefficient spectra
+        CK(launch(k_spec_lin<T>, dim3(296), dim3(256), 0, stream, (const C2<T>*)cdV.p, (const C2<T>*)cdYf.p,
+                  (const C2<T>*)cdG.p, acc.p, nsp));
+        if (nccl_comm) {
+            rc = reduce_acc_over_ranks();
+            if (rc) return rc;
+        }
+        double ha[4];
+        CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+        CK(cudaStreamSynchronize(stream));
+        // with the gradient summed over ranks before use (no crop-before-reduce) the linear term is already global
+        const bool crop_reduce = nccl_comm && (p2p_on ? pb.hd * pb.wd * Cd * M <= kP2pVecMax : true) &&
+                                 !(getenv("SPCSC_CDL_FULLREDUCE") && atoi(getenv("SPCSC_CDL_FULLREDUCE")) == 1);
+        const double rk = nccl_comm ? (double)nranks : 1.0;
+        out[0] = 0.5 * ha[0];
+        out[1] = cd_fY;
+        out[2] = (nccl_comm && !crop_reduce) ? ha[2] / rk : ha[2];
+        out[3] = ha[3] / rk;
+        return SPCSC_OK;
+    }
+    int ccmod_accept(double coef, int flags, double* out) override {
+        int rc = ccmod_check();
+        if (rc) return rc;
+        if (!cd_ready || !cd_grad_valid) FAIL(SPCSC_ERR_STATE, "ccmod_accept without a preceding ccmod_trial");
+        CK(cudaSetDevice(pb.device));
+        return ccmod_part_b(coef, flags, out);
     }
     // ---- consensus dictionary update (sporco/admm/ccmod.py:613-911): state and one iteration
     int ccmod_cns_init(double rho, int y0_given, long long nb_global) override {
@@ -2289,6 +2357,8 @@ int spcsc_ccmod_reset(spcsc_handle* h, const void* D0, int32_t zm) { H_CALL(D0 ?
 int spcsc_ccmod_setcoef_device(spcsc_handle* h, int32_t source) { H_CALL(h->ccmod_setcoef_device(source)); }
 int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z) { H_CALL(Z ? h->ccmod_setcoef(Z) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]) { H_CALL(out ? h->ccmod_step(L, coef, flags, out) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_trial(spcsc_handle* h, double L, double out[4]) { H_CALL(out ? h->ccmod_trial(L, out) : SPCSC_ERR_INVALID); }
+int spcsc_ccmod_accept(spcsc_handle* h, double coef, int32_t flags, double out[4]) { H_CALL(out ? h->ccmod_accept(coef, flags, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
 int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global) { H_CALL(h->ccmod_cns_init(rho, y0_given, (long long)nb_global)); }

@@ -10,8 +10,8 @@ sequence, as the reference does.  When the object is built by
 coefficient maps and dictionary pass between the two steps without leaving the GPU.
 
 Supported: greyscale and multi-channel signals with a single-channel or a multi-channel
-dictionary, single- or multi-scale filter supports, fixed step 1/L with Nesterov (or linear) momentum.  Backtracking, ``Monotone`` and ``StepSizePolicy`` raise
-``NotImplementedError``.
+dictionary, single- or multi-scale filter supports, step 1/L fixed or found by ``BacktrackStandard``, Nesterov (or
+linear) momentum.  ``BacktrackRobust``, ``Monotone`` and ``StepSizePolicy`` raise ``NotImplementedError``.
 """
 
 import copy
@@ -40,13 +40,17 @@ class ConvCnstrMOD(pgm.PGMDFT):
         opt = self._coerce_options(opt)
         self.cri = cr.CDU_ConvRepIndexing(dsz, S, dimK=dimK, dimN=dimN)
         cri = self.cri
-        if opt['Backtrack'] is not None:
-            raise NotImplementedError('backtracking is not implemented for the device '
-                                      'dictionary update')
+        from .backtrack import BacktrackStandard
+        if opt['Backtrack'] is not None and not (isinstance(opt['Backtrack'], BacktrackStandard) or
+                                                  type(opt['Backtrack']).__name__ == 'BacktrackStandard'):
+            raise NotImplementedError('only BacktrackStandard is implemented for the device dictionary update')
         if opt['Monotone'] or opt['StepSizePolicy'] is not None:
             raise NotImplementedError('Monotone / StepSizePolicy are not implemented for the device '
                                       'dictionary update')
         super(ConvCnstrMOD, self).__init__(cri.shpD, cri.Nv, cri.axisN, S.dtype, opt)
+        if self.backtrack is not None and not isinstance(self.backtrack, BacktrackStandard):
+            # a parameter holder of the same name built by the reference package
+            self.backtrack = BacktrackStandard(gamma_u=self.backtrack.gamma_u, maxiter=self.backtrack.maxiter)
         # NB the reference passes dval = 14 K here (pgm/ccmod.py:218) but PGM.__init__ has already
         # set L = 1 (pgm/pgm.py:242) and set_attr keeps a value that is set: the effective
         # default is 1, which is what this class reproduces.
@@ -108,15 +112,26 @@ class ConvCnstrMOD(pgm.PGMDFT):
 
     # ---- one PGM iteration: PGMDFT.xstep + ystep of pgm/pgm.py:779-831 in one device call
     def _trial(self):
-        return None
+        """One proximal trial at the current L (backtracking only): F = f(X) and the quadratic model
+        Q = f(Y) + <grad f(Y), X - Y> + (L / 2) ||X - Y||^2 in the DFT scaling (pgm/backtrack.py:88-97)."""
+        if self.backtrack is None:
+            return None
+        f, fy, lin, dxy2 = self._h.ccmod_trial(float(self.L))
+        self._tried = True
+        rdt = self.dtype.type
+        return rdt(f), rdt(fy) + rdt(lin) + (self.L / 2.) * rdt(dxy2)
 
     def ystep(self):
         tprv = self.t
         self.t = self.momentum.update(self.var_momentum())
         # FastSolve: no iteration record is built (pgm/pgm.py:347), so the two statistics that
         # need a pass of their own are skipped
-        self._stats = self._h.ccmod_step(float(self.L), (tprv - 1.) / self.t,
-                                         0 if self.opt['FastSolve'] else 3)
+        flags = 0 if self.opt['FastSolve'] else 3
+        if self.backtrack is not None and getattr(self, '_tried', False):
+            self._stats = self._h.ccmod_accept((tprv - 1.) / self.t, flags)
+            self._tried = False
+        else:
+            self._stats = self._h.ccmod_step(float(self.L), (tprv - 1.) / self.t, flags)
         self._cache.clear()
 
     def rsdl(self):

@@ -420,6 +420,11 @@ CDL_CASES = {
                 'CCMOD': {'L': 50.0, 'ZeroMean': True}}, 'admm', 0.1),
     'cdl_ms_cns': ({'MaxMainIter': 15, 'DictSize': ((4, 4, 3), (7, 6, 2)), 'CBPDN': {'rho': 5.0},
                     'CCMOD': {'rho': 2.0, 'ZeroMean': True}}, 'admm', 0.1, 'cns'),
+    # backtracking in both steps, colour signals, multi-scale colour dictionary (examples/scripts/cdl/cbpdndl_pgm_clr.py
+    # in small); the Backtrack objects are filled in by run_cdl_case
+    'cdl_bt_clr_ms': ({'MaxMainIter': 12, 'DictSize': ((4, 4, 3, 3), (7, 6, 3, 2)),
+                       'CBPDN': {'Backtrack': ('std', 1.1), 'L': 10.0}, 'CCMOD': {'Backtrack': ('std', 1.2), 'L': 5.0}},
+                      'pgm', 0.1),
 }
 
 
@@ -429,10 +434,17 @@ def run_cdl_case(tag, sfx):
     g = load('%s_%s' % (tag, sfx))
     o, xmethod, lmbda = CDL_CASES[tag][:3]
     dmethod = CDL_CASES[tag][3] if len(CDL_CASES[tag]) > 3 else 'pgm'
+    if any(isinstance(o.get(k, {}).get('Backtrack'), tuple) for k in ('CBPDN', 'CCMOD')):
+        from sporco_b200.pgm.backtrack import BacktrackStandard
+        o = {k: (dict(v) if isinstance(v, dict) else v) for k, v in o.items()}
+        for k in ('CBPDN', 'CCMOD'):
+            bt = o[k].get('Backtrack')
+            if isinstance(bt, tuple):
+                o[k]['Backtrack'] = BacktrackStandard(gamma_u=bt[1])
     assert float(g['lmbda']) == lmbda
     # float32: north_star's rtol 1e-4, except the PGM X step and the consensus D step cases, where the
     # reference's own float32 and float64 runs drift apart by 2e-4 ... 4e-4 (D) over these alternations
-    tol = 1e-10 if sfx == 'f64' else (1e-3 if (tag == 'cdl_pgmx' or dmethod == 'cns') else 1e-4)
+    tol = 1e-10 if sfx == 'f64' else (1e-3 if (xmethod == 'pgm' or dmethod == 'cns') else 1e-4)
     opt = cbpdndl.ConvBPDNDictLearn.Options(o, xmethod=xmethod, dmethod=dmethod)
     b = cbpdndl.ConvBPDNDictLearn(g['D0'], g['S'], lmbda, opt, xmethod=xmethod, dmethod=dmethod)
     D = b.solve()
@@ -697,3 +709,22 @@ CNS_GOLDEN = {
     'cns_arho': {'MaxMainIter': 15, 'rho': 2.0,
                  'AutoRho': {'Enabled': True, 'Period': 3, 'AutoScaling': True, 'Scaling': 10.0}},
 }
+
+
+def run_ccmod_bt(sfx):
+    """pgm.ccmod.ConvCnstrMOD with BacktrackStandard against the reference's outputs: dictionary, L trajectory,
+    backtracking counts, F, Q, residual, data fidelity."""
+    from sporco_b200.pgm import ccmod
+    from sporco_b200.pgm.backtrack import BacktrackStandard
+    g = load('ccmod_bt_' + sfx)
+    opt = ccmod.ConvCnstrMOD.Options({'MaxMainIter': 12, 'L': 2.0, 'Backtrack': BacktrackStandard(gamma_u=1.3, maxiter=10),
+                                      'RelStopTol': 0.0, 'ZeroMean': True})
+    c = ccmod.ConvCnstrMOD(g['Z'], g['S'], tuple(int(x) for x in g['dsz']), opt)
+    c.solve()
+    its = c.getitstat()
+    tol = 1e-10 if sfx == 'f64' else 2e-5
+    assert rel(c.getdict(), g['D']) < tol, rel(c.getdict(), g['D'])
+    assert np.array_equal(np.asarray(its.IterBTrack, dtype=np.float64), g['IterBTrack'])
+    for name in ('L', 'F_Btrack', 'Q_Btrack', 'Rsdl', 'DFid'):
+        assert rel(getattr(its, name), g[name]) < 10 * tol, (name, rel(getattr(its, name), g[name]))
+    return c

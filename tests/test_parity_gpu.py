@@ -316,3 +316,9 @@ def test_consensus_dictionary_update_vs_oracle(case, dt):
 @pytest.mark.parametrize('tag', sorted(cases.CNS_GOLDEN))
 def test_consensus_dictionary_update_golden(tag, sfx):
     cases.run_cns_golden(tag, sfx)
+
+
+@pytest.mark.parametrize('sfx', ['f64', 'f32'])
+def test_dictionary_update_backtracking_golden(sfx):
+    """pgm.ccmod.ConvCnstrMOD with BacktrackStandard (trial / accept on the device, F <= Q on the host)."""
+    cases.run_ccmod_bt(sfx)
