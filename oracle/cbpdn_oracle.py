@@ -345,7 +345,7 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         emu = dtype.type(enet_mu)
     grd = grad_mu is not None
     if grd:
-        assert not joint and not enet and dims.Cd == 1
+        assert not joint and not enet
         gmu = dtype.type(grad_mu)
         gw = o.get('GradWeight', 1.0)
         if hasattr(gw, 'ndim'):
@@ -389,7 +389,10 @@ def admm_convbpdn(D, S, lmbda=None, mu=None, opt=None, dimK=None, fft=None,
         rho_x = (emu + rho) if enet else rho           # admm/cbpdn.py:948-955
         if grd:                                         # admm/cbpdn.py:1173-1201
             rho_x = gmu * GHGf + rho
-            Xf = solvedbd_sm(Df, rho_x, b, axM)
+            if dims.Cd == 1:
+                Xf = solvedbd_sm(Df, rho_x, b, axM)
+            else:                                       # admm/cbpdn.py:1181-1184: the diagonal goes in as "rho"
+                Xf = solvemdbi_ism(Df, rho_x, b, axM, axC)
         elif dims.Cd == 1:
             Xf = solvedbi_sm(Df, rho_x, b, axM)
         else:

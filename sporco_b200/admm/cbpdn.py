@@ -374,7 +374,9 @@ class ConvBPDNGradReg(ConvBPDN):
                  + (mu/2) sum_i sum_m w_m || G_i x_m ||_2^2
 
     The x-step system has the diagonal ``mu w_m GHG + rho`` (linalg.solvedbd_sm) instead of
-    ``rho``; ``IterationStats`` gains ``RegGrad``.  Single-channel dictionaries.
+    ``rho``; ``IterationStats`` gains ``RegGrad``.  With a multi-channel dictionary the system is the
+    rank-C update of that diagonal (``linalg.solvemdbi_ism`` in the reference, one C x C solve per frequency
+    here); ``LinSolveCheck`` / ``AuxVarObj`` are then not available.
     """
 
     class Options(ConvBPDN.Options):
@@ -392,8 +394,9 @@ class ConvBPDNGradReg(ConvBPDN):
     def __init__(self, D, S, lmbda=None, mu=0.0, opt=None, dimK=None, dimN=2, device=0):
         opt = self._coerce_options(opt)
         self.cri = cr.CSC_ConvRepIndexing(D, S, dimK=dimK, dimN=dimN)
-        if self.cri.Cd != 1:
-            raise NotImplementedError('ConvBPDNGradReg with a multi-channel dictionary is not supported')
+        if self.cri.Cd != 1 and (opt['LinSolveCheck'] or opt['AuxVarObj']):
+            raise NotImplementedError('ConvBPDNGradReg with a multi-channel dictionary: LinSolveCheck and '
+                                      'AuxVarObj are not supported')
         self.set_dtype(opt, S.dtype)
         self.mu = self.dtype.type(mu)
         gw = opt['GradWeight']

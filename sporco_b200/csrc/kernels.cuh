@@ -1499,6 +1499,111 @@ SPCSC_GLOBAL void k_set_ghg(C2<T>* SPCSC_RESTRICT G, const T* SPCSC_RESTRICT ghg
         G[i].im = ghg[i];
 }
 
+// ConvBPDNGradReg with a multi-channel dictionary (sporco/admm/cbpdn.py:1181-1184: solvemdbi_ism with the diagonal
+// d_m = mu w_m GHG + rho in place of rho; linalg.py:370-444).  Closed form per frequency, A = [conj(Df_c,m)] (M x C):
+//   sigma_c = sum_m Df_c,m z_m / d_m ,  Gamma_cc' = sum_m Df_c,m conj(Df_c',m) / d_m ,
+//   q = (I + Gamma)^-1 (Sf - rho sigma) ,  x_m = (rho z_m + sum_c conj(Df_c,m) q_c) / d_m ,  sum_m Df_c,m x_m - Sf_c = -q_c
+// (the Cd = 1 case of this is in k_col).  Works in place on slabs that are ALREADY in the 2-D frequency domain (the engine
+// brackets it with the forward / inverse column passes of k_col).  One CTA per (wf, 32 frequencies h, slab): 32 h-lanes x
+// 8 filter groups; general path, not tuned.
+template <typename T, int CD>
+SPCSC_GLOBAL void SPCSC_LAUNCH_BOUNDS(256)
+k_gradreg_mc(C2<T>* SPCSC_RESTRICT Zf, const C2<T>* SPCSC_RESTRICT Df, const C2<T>* SPCSC_RESTRICT Sf,
+             const T* SPCSC_RESTRICT ghg, const C2<T>* SPCSC_RESTRICT gw, const AdmmState<T>* SPCSC_RESTRICT st,
+             double* SPCSC_RESTRICT acc, int N1f, int M, int N0, int Cs, int even_n1, int stats) {
+    if (st->stopped) return;
+    __shared__ C2<T> red[8][33];
+    __shared__ C2<T> qs[CD][32];
+    __shared__ double dred[2 * 32];
+    const int lane = threadIdx.x & 31, mg = threadIdx.x >> 5;
+    const int wf = blockIdx.x, h = blockIdx.y * 32 + lane, b = blockIdx.z;
+    const bool hv = h < N0;
+    const T rho = st->rho;
+    const T g = hv ? ghg[(size_t)wf * N0 + h] : (T)0;
+    const size_t slab = (((size_t)b * N1f + wf) * M) * N0;
+    const size_t dfc = (size_t)N1f * M * N0;
+    C2<T> sig[CD], gam[CD][CD];
+    SPCSC_UNROLL
+    for (int c = 0; c < CD; ++c) {
+        sig[c] = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int d = 0; d < CD; ++d) gam[c][d] = mk<T>(0, 0);
+    }
+    if (hv) {
+        for (int m = mg; m < M; m += 8) {
+            const C2<T> z = Zf[slab + (size_t)m * N0 + h];
+            const T inv = (T)1 / (gw[m].re * g + rho);
+            C2<T> df[CD];
+            SPCSC_UNROLL
+            for (int c = 0; c < CD; ++c) df[c] = Df[(size_t)c * dfc + ((size_t)wf * M + m) * N0 + h];
+            SPCSC_UNROLL
+            for (int c = 0; c < CD; ++c) {
+                sig[c] = sig[c] + inv * (df[c] * z);
+                SPCSC_UNROLL
+                for (int d = 0; d < CD; ++d) gam[c][d] = gam[c][d] + inv * mulc(df[c], df[d]);
+            }
+        }
+    }
+    // sums over the 8 filter groups, one quantity at a time through a small shared array
+    auto group_sum = [&](C2<T> v) -> C2<T> {
+        red[mg][lane] = v;
+        __syncthreads();
+        C2<T> s = mk<T>(0, 0);
+        SPCSC_UNROLL
+        for (int q = 0; q < 8; ++q) s = s + red[q][lane];
+        __syncthreads();
+        return s;
+    };
+    SPCSC_UNROLL
+    for (int c = 0; c < CD; ++c) {
+        sig[c] = group_sum(sig[c]);
+        SPCSC_UNROLL
+        for (int d = 0; d < CD; ++d) gam[c][d] = group_sum(gam[c][d]);
+    }
+    double dsum[1] = {0.0};
+    if (mg == 0) {
+        C2<T> A[CD][CD], rhs[CD];
+        SPCSC_UNROLL
+        for (int c = 0; c < CD; ++c) {
+            const C2<T> sf = hv ? Sf[(((size_t)b * Cs + c) * N1f + wf) * N0 + h] : mk<T>(0, 0);
+            rhs[c] = sf - rho * sig[c];
+            SPCSC_UNROLL
+            for (int d = 0; d < CD; ++d) {
+                A[c][d] = gam[c][d];
+                if (c == d) A[c][d].re += (T)1;
+            }
+        }
+        hpd_solve<T, CD>(A, rhs, CD);
+        const double wg = (wf == 0 || (even_n1 && wf == N1f - 1)) ? 1.0 : 2.0;
+        SPCSC_UNROLL
+        for (int c = 0; c < CD; ++c) {
+            qs[c][lane] = rhs[c];
+            if (hv) dsum[0] += wg * (double)abs2(rhs[c]);
+        }
+    }
+    __syncthreads();
+    double rg[1] = {0.0};
+    if (hv) {
+        const double wg = (wf == 0 || (even_n1 && wf == N1f - 1)) ? 1.0 : 2.0;
+        for (int m = mg; m < M; m += 8) {
+            const C2<T> z = Zf[slab + (size_t)m * N0 + h];
+            const C2<T> gwm = gw[m];
+            const T inv = (T)1 / (gwm.re * g + rho);
+            C2<T> x = rho * z;
+            SPCSC_UNROLL
+            for (int c = 0; c < CD; ++c)
+                x = x + mulc(qs[c][lane], Df[(size_t)c * dfc + ((size_t)wf * M + m) * N0 + h]);
+            x = inv * x;
+            Zf[slab + (size_t)m * N0 + h] = x;
+            rg[0] += wg * (double)(gwm.im * g * abs2(x));
+        }
+    }
+    if (stats) {
+        block_accumulate<1>(dsum, dred, acc + ACC_DFID);
+        block_accumulate<1>(rg, dred, acc + ACC_RGRAD);
+    }
+}
+
 // Gram of the dictionary per frequency: G[wf][h][c][c'] = sum_m Df_c[m] conj(Df_c'[m]).
 template <typename T>
 SPCSC_GLOBAL void k_gram(const C2<T>* SPCSC_RESTRICT Df, C2<T>* SPCSC_RESTRICT G, int N1f, int N0,

@@ -679,14 +679,14 @@ class Engine : public spcsc_handle {
     }
 
     int install_ghg() {
-        if (!gradreg) return SPCSC_OK;
+        if (!gradreg || Cd != 1) return SPCSC_OK;        // multi-channel dictionaries: k_gradreg_mc reads ghg_buf
         CK(launch(k_set_ghg<T>, dim3(128), dim3(256), 0, stream, G.p, (const T*)ghg_buf.p, (size_t)N1f * N0));
         return SPCSC_OK;
     }
     int set_gradreg(const void* ghg, const void* wgrd) override {
         if (poisoned) return SPCSC_ERR_CUDA;
         if (!ghg) { gradreg = false; return SPCSC_OK; }
-        if (Cd != 1) FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with a multi-channel dictionary");
+        if (Cd > 4) FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with more than 4 dictionary channels");
         if (!wgrd) FAIL(SPCSC_ERR_INVALID, "wgrd is NULL");
         CK(cudaSetDevice(pb.device));
         const T* g = (const T*)ghg;
@@ -733,6 +733,9 @@ class Engine : public spcsc_handle {
         prm.emit_policy = (getenv("SPCSC_EMIT") && atoi(getenv("SPCSC_EMIT")) == 0) ? 0 : 1;
         if (gradreg) {
             if (o->joint || o->l2_weight != 0.0) FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with the joint or l2 penalty");
+            if (Cd > 1 && (o->linsolve_check || (o->aux_var_obj && !o->fast_solve) || o->ams_maps > 0))
+                FAIL(SPCSC_ERR_UNSUPPORTED, "gradient regularisation with a multi-channel dictionary: LinSolveCheck, "
+                                            "AuxVarObj and AddMaskSim are not available");
             std::vector<C2<T>> gw(M);
             for (int m = 0; m < M; ++m) gw[m] = mk<T>((T)o->mu * gr_w[m], gr_w[m]);
             CK(gw_buf.ensure(M));
@@ -1036,6 +1039,21 @@ class Engine : public spcsc_handle {
                 if (v2_col && !prm.enet && !prm.gradreg) {  // l2 / gradient terms: general kernel only
                     CK(col2<T>(N0, COL_ADMM, cs, (const C2<T>*)stw_col.p));
                     last_col_kernel = g_col_variant;
+                } else if (prm.gradreg && Cd > 1) {
+                    // ConvBPDNGradReg with a multi-channel dictionary: forward columns, the C x C solve with the
+                    // diagonal mu w_m GHG + rho, inverse columns
+                    ColLaunch<T> c1 = cs;
+                    c1.a.gradreg = 0;
+                    CK(col<T>(N0, COL_FWD, c1));
+                    dim3 gg(N1f, (N0 + 31) / 32, K * Cx);
+                    const int even = (N1 % 2 == 0) ? 1 : 0;
+                    cudaError_t ge = cudaErrorInvalidValue;
+                    if (Cd == 2) ge = launch(k_gradreg_mc<T, 2>, gg, dim3(256), 0, stream, zin, (const C2<T>*)Df.p, (const C2<T>*)Sf.p, (const T*)ghg_buf.p, (const C2<T>*)gw_buf.p, (const AdmmState<T>*)st.p, acc.p, N1f, M, N0, C, even, cs.a.dfid_on);
+                    if (Cd == 3) ge = launch(k_gradreg_mc<T, 3>, gg, dim3(256), 0, stream, zin, (const C2<T>*)Df.p, (const C2<T>*)Sf.p, (const T*)ghg_buf.p, (const C2<T>*)gw_buf.p, (const AdmmState<T>*)st.p, acc.p, N1f, M, N0, C, even, cs.a.dfid_on);
+                    if (Cd == 4) ge = launch(k_gradreg_mc<T, 4>, gg, dim3(256), 0, stream, zin, (const C2<T>*)Df.p, (const C2<T>*)Sf.p, (const T*)ghg_buf.p, (const C2<T>*)gw_buf.p, (const AdmmState<T>*)st.p, acc.p, N1f, M, N0, C, even, cs.a.dfid_on);
+                    CK(ge);
+                    CK(col<T>(N0, COL_INV, c1));
+                    last_col_kernel = 0;
                 } else {
                     CK(col<T>(N0, COL_ADMM, cs));
                     last_col_kernel = 0;

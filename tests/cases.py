@@ -728,3 +728,25 @@ def run_ccmod_bt(sfx):
     for name in ('L', 'F_Btrack', 'Q_Btrack', 'Rsdl', 'DFid'):
         assert rel(getattr(its, name), g[name]) < 10 * tol, (name, rel(getattr(its, name), g[name]))
     return c
+
+
+def run_gradreg_multichannel_dict(dt=np.float32):
+    """ConvBPDNGradReg with a 3-channel dictionary (C x C solve with the diagonal mu w_m GHG + rho per frequency)
+    against the oracle (pinned to the reference: solvemdbi_ism with the diagonal as rho)."""
+    from oracle import cbpdn_oracle as orc
+    from sporco_b200.admm import cbpdn
+    rng = np.random.default_rng(4)
+    D = rng.standard_normal((5, 5, 3, 6)).astype(dt)
+    S = rng.standard_normal((32, 32, 3, 2)).astype(dt)
+    gw = np.linspace(0.2, 2.0, 6).astype(dt)
+    for extra in ({}, {'rho': 3.0, 'AutoRho': {'Enabled': False}, 'NonNegCoef': True}):
+        opt = dict({'MaxMainIter': 15, 'RelStopTol': 0.0, 'GradWeight': gw}, **extra)
+        b = cbpdn.ConvBPDNGradReg(D, S, 0.1, 0.4, cbpdn.ConvBPDNGradReg.Options(opt))
+        Y = b.solve()
+        r = orc.admm_convbpdn(D, S, 0.1, opt=opt, grad_mu=0.4)
+        tol = 1e-9 if dt == np.float64 else 3e-4
+        assert rel(Y, r.Y) < tol, rel(Y, r.Y)
+        its = b.getitstat()
+        assert rel(its.ObjFun, [x[1] for x in r.itstat]) < tol
+        assert rel(its.RegGrad, [x[4] for x in r.itstat]) < tol
+        assert rel(its.Rho, [x[9] for x in r.itstat]) < tol

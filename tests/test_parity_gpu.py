@@ -322,3 +322,8 @@ def test_consensus_dictionary_update_golden(tag, sfx):
 def test_dictionary_update_backtracking_golden(sfx):
     """pgm.ccmod.ConvCnstrMOD with BacktrackStandard (trial / accept on the device, F <= Q on the host)."""
     cases.run_ccmod_bt(sfx)
+
+
+@pytest.mark.parametrize('dt', [np.float64, np.float32])
+def test_gradient_regularisation_with_a_multichannel_dictionary(dt):
+    cases.run_gradreg_multichannel_dict(dt)
