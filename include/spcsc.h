@@ -245,6 +245,9 @@ int spcsc_ccmod_push_dict(spcsc_handle* h);
    support of filter m inside the handle's hd x wd (the largest support); the constraint projection Pcn of both dictionary
    updates then crops / zero-means / normalises every filter over its own support.  NULL: one support for all filters. */
 int spcsc_ccmod_set_supports(spcsc_handle* h, const int32_t* hw);
+/* ConvCnstrMOD.Xf / .Yf (pgm/ccmod.py:139-261): spectrum of the dictionary iterate (which = 0) or of the momentum point (1),
+   complex, device order [Cd][N1f][M][N0]. */
+int spcsc_ccmod_get_spectrum(spcsc_handle* h, int32_t which, void* out);
 
 /* ---- consensus dictionary update: sporco.admm.ccmod.ConvCnstrMOD_Consensus (sporco/admm/ccmod.py:613-911 over
    ADMMConsensus, sporco/admm/admm.py:1419-1707) on the same handle and the same dictionary / coefficient state as

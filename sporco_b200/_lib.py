@@ -32,7 +32,7 @@ SYMBOLS = (
     'spcsc_pgm_accept', 'spcsc_pgm_policy_stats', 'spcsc_pgm_combine_y', 'spcsc_pgm_finish', 'spcsc_set_gradreg', 'spcsc_tikhonov_filter', 'spcsc_pgm_set_mask', 'spcsc_p2p_export',
     'spcsc_p2p_attach', 'spcsc_ccmod_reset', 'spcsc_ccmod_setcoef_device', 'spcsc_ccmod_setcoef',
     'spcsc_ccmod_step', 'spcsc_ccmod_trial', 'spcsc_ccmod_accept', 'spcsc_ccmod_get_dict', 'spcsc_ccmod_push_dict',
-    'spcsc_ccmod_cns_init', 'spcsc_ccmod_cns_step', 'spcsc_ccmod_cns_get', 'spcsc_ccmod_set_supports',
+    'spcsc_ccmod_cns_init', 'spcsc_ccmod_cns_step', 'spcsc_ccmod_cns_get', 'spcsc_ccmod_set_supports', 'spcsc_ccmod_get_spectrum',
 )
 
 
@@ -132,6 +132,7 @@ def _declare(lib):
     lib.spcsc_ccmod_cns_init.argtypes = [vp, ctypes.c_double, i32, ctypes.c_int64]
     lib.spcsc_ccmod_cns_get.argtypes = [vp, i32, vp]
     lib.spcsc_ccmod_set_supports.argtypes = [vp, vp]
+    lib.spcsc_ccmod_get_spectrum.argtypes = [vp, i32, vp]
     lib.spcsc_ccmod_cns_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, i32,
                                          ctypes.POINTER(ctypes.c_double)]
     lib.spcsc_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
@@ -429,6 +430,14 @@ class Handle(object):
 
     def ccmod_cns_init(self, rho, y0_given, nb_global=0):
         self._c(self.lib.spcsc_ccmod_cns_init(self.h, float(rho), 1 if y0_given else 0, int(nb_global)))
+
+    def ccmod_get_spectrum(self, which):
+        """Xf (which 0) or Yf (1) of the PGM dictionary update as (N0, N1f, Cd, 1, M)."""
+        d = self.dims
+        n1f = d['N1'] // 2 + 1
+        out = np.empty((d['Cd'], n1f, d['M'], d['N0']), dtype=self.cdtype)
+        self._c(self.lib.spcsc_ccmod_get_spectrum(self.h, int(which), out.ctypes.data_as(ctypes.c_void_p)))
+        return np.ascontiguousarray(out.transpose(3, 1, 0, 2))[:, :, :, np.newaxis, :]
 
     def ccmod_set_supports(self, hw):
         """Per-filter supports (M, 2) of a multi-scale dictionary, or None for one support."""

@@ -321,6 +321,7 @@ struct spcsc_handle {
     virtual int ccmod_cns_step(double rho, double udiv, double rlx, int flags, double* out) = 0;
     virtual int ccmod_cns_get(int which, void* out) = 0;
     virtual int ccmod_set_supports(const int32_t* hw) = 0;
+    virtual int ccmod_get_spectrum(int which, void* out) = 0;
 };
 
 namespace {
@@ -1808,6 +1809,17 @@ class Engine : public spcsc_handle {
         out[7] = lscheck ? (hls[1] > 0.0 ? std::sqrt(hls[0] / hls[1]) : std::sqrt(hls[0])) : -1.0;
         return SPCSC_OK;
     }
+    // spectra of the PGM dictionary update in device order [Cd][N1f][M][N0]: which 0 = Xf (iterate), 1 = Yf (momentum point)
+    int ccmod_get_spectrum(int which, void* out) override {
+        if (poisoned) return SPCSC_ERR_CUDA;
+        if (!cd_ready) FAIL(SPCSC_ERR_STATE, "ccmod_get_spectrum before ccmod_reset");
+        if (which != 0 && which != 1) FAIL(SPCSC_ERR_INVALID, "which must be 0 (Xf) or 1 (Yf)");
+        CK(cudaSetDevice(pb.device));
+        const size_t nsp = (size_t)Cd * N1f * M * N0;
+        CK(cudaMemcpyAsync(out, which == 0 ? cdXf.p : cdYf.p, nsp * sizeof(C2<T>), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPCSC_OK;
+    }
     // multi-scale dictionaries: the support (h_m, w_m) of every filter; NULL: all filters use the handle's hd x wd
     int ccmod_set_supports(const int32_t* hw) override {
         if (poisoned) return SPCSC_ERR_CUDA;
@@ -2380,6 +2392,7 @@ int spcsc_ccmod_accept(spcsc_handle* h, double coef, int32_t flags, double out[4
 int spcsc_ccmod_get_dict(spcsc_handle* h, void* D_out) { H_CALL(D_out ? h->ccmod_get_dict(D_out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_push_dict(spcsc_handle* h) { H_CALL(h->ccmod_push_dict()); }
 int spcsc_ccmod_cns_init(spcsc_handle* h, double rho, int32_t y0_given, int64_t nb_global) { H_CALL(h->ccmod_cns_init(rho, y0_given, (long long)nb_global)); }
+int spcsc_ccmod_get_spectrum(spcsc_handle* h, int32_t which, void* out) { H_CALL(out ? h->ccmod_get_spectrum(which, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_set_supports(spcsc_handle* h, const int32_t* hw) { H_CALL(h->ccmod_set_supports(hw)); }
 int spcsc_ccmod_cns_get(spcsc_handle* h, int32_t which, void* out) { H_CALL(out ? h->ccmod_cns_get(which, out) : SPCSC_ERR_INVALID); }
 int spcsc_ccmod_cns_step(spcsc_handle* h, double rho, double udiv, double rlx, int32_t flags, double out[8]) { H_CALL(out ? h->ccmod_cns_step(rho, udiv, rlx, flags, out) : SPCSC_ERR_INVALID); }

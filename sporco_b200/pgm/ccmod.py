@@ -104,6 +104,14 @@ class ConvCnstrMOD(pgm.PGMDFT):
     def X(self):
         return self.getdict(crop=False)
 
+    @property
+    def Xf(self):
+        return self._h.ccmod_get_spectrum(0)
+
+    @property
+    def Yf(self):
+        return self._h.ccmod_get_spectrum(1)
+
     def getmin(self):
         return self.getdict(crop=False)
 

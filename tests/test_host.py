@@ -106,8 +106,19 @@ def test_cnvrep_dictionary_helpers_match_the_oracle():
     assert (cri.Cd, cri.C, cri.Cx, cri.K, cri.M) == (3, 3, 1, 7, 4) and cri.shpD == (16, 12, 3, 1, 4)
     cri = cr.CDU_ConvRepIndexing((5, 4, 4), np.zeros((16, 12, 3, 7)), dimK=1)
     assert (cri.Cd, cri.C, cri.Cx) == (1, 3, 3) and cri.shpX == (16, 12, 3, 7, 4)
+    # multi-scale specification: the largest support, the filters of all blocks, per-filter supports; projection
+    # of every block over its own support, equal to the oracle's restatement
+    ms = ((5, 5, 2), (3, 4, 3))
+    cri = cr.CDU_ConvRepIndexing(ms, np.zeros((16, 12, 7)))
+    assert cri.multiscale and cri.dsz == (5, 5, 5) and cri.M == 5 and cri.shpD == (16, 12, 1, 1, 5)
+    assert cr.filter_supports(ms).tolist() == [[5, 5], [5, 5], [3, 4], [3, 4], [3, 4]]
+    xm = rng.standard_normal((16, 12, 1, 1, 5))
+    for zm in (False, True):
+        pm = cr.Pcn(xm, ms, (16, 12), dimN=2, dimC=1, crp=False, zm=zm)
+        assert np.allclose(pm, ocdl.pcn(xm, ms, (16, 12), zm=zm), atol=1e-15)
+        assert not np.any(pm[3:, :, :, :, 2:]) and not np.any(pm[:, 4:, :, :, 2:]) and np.any(pm[3:5, :5, :, :, :2])
     with pytest.raises(NotImplementedError):
-        cr.CDU_ConvRepIndexing(((5, 5, 2), (3, 3, 2)), np.zeros((16, 12, 7)))
+        cr.CDU_ConvRepIndexing((((5, 5, 1, 2), (5, 5, 2, 2)), (3, 3, 3, 2)), np.zeros((16, 12, 3, 7)))
     # mask shapes: same decisions as the oracle's restatement of cnvrep.mskWshape
     for S, W in ((np.zeros((8, 8)), np.zeros((8, 8))), (np.zeros((8, 8, 3)), np.zeros((8, 8, 3))),
                  (np.zeros((8, 8, 3, 2)), np.zeros((8, 8, 1, 2))), (np.zeros((8, 8, 3, 2)), np.zeros((8, 8, 3)))):

@@ -31,6 +31,13 @@ NOT_IMPLEMENTED = {
     'ccmod': {'test_03cplx': 'complex-valued data',
               'test_13': 'multi-channel coefficient maps together with a multi-channel dictionary (runs in the '
                          'reference through numpy broadcasting only; not a documented configuration)'},
+    # tests/pgm/test_ccmod.py with pgm.ccmod.ConvCnstrMOD replaced
+    'pgmccmod': {'test_10': 'multi-channel coefficient maps together with a multi-channel dictionary (numpy broadcasting '
+                            'only; not a documented configuration)',
+                 'test_13': 'BacktrackRobust in the dictionary update',
+                 'test_16': 'StepSizePolicyBB in the dictionary update',
+                 'test_17': 'StepSizePolicyCauchy in the dictionary update',
+                 'test_18': 'Monotone in the dictionary update'},
 }
 # tests of the reference's other dictionary-update classes / its own option classes in that file
 CCMOD_OTHER = ('ConvCnstrMOD_IterSM', 'ConvCnstrMOD_CG', 'ConvCnstrMODBase')
@@ -53,6 +60,19 @@ def _load(kind):
         path = os.path.join(REF, 'tests', 'admm', 'test_ccmod.py')
         src = open(path).read().replace('from sporco.admm import ccmod', 'ccmod = __proxy__')
         ns = {'__proxy__': proxy, '__name__': 'ref_tests_ccmod'}
+        exec(compile(src, path, 'exec'), ns)
+        return ns['TestSet01']
+    if kind == 'pgmccmod':
+        import sporco.pgm.ccmod as ref_pccmod
+        from sporco_b200.pgm import ccmod as my_pccmod
+        proxy.__dict__.update(ref_pccmod.__dict__)
+        proxy.ConvCnstrMOD = my_pccmod.ConvCnstrMOD
+        path = os.path.join(REF, 'tests', 'pgm', 'test_ccmod.py')
+        src = open(path).read().replace('from sporco.pgm import ccmod', 'ccmod = __proxy__')
+        src = src.replace('from sporco.pgm.momentum import', 'from sporco_b200.pgm.momentum import')
+        src = src.replace('from sporco.pgm.backtrack import', 'from sporco_b200.pgm.backtrack import')
+        src = src.replace('from sporco.pgm.stepsize import', 'from sporco_b200.pgm.stepsize import')
+        ns = {'__proxy__': proxy, '__name__': 'ref_tests_pgmccmod'}
         exec(compile(src, path, 'exec'), ns)
         return ns['TestSet01']
     if kind == 'admm':
@@ -89,7 +109,8 @@ def _cases(kind):
         if not name.startswith('test_'):
             continue
         body = inspect.getsource(fn)
-        if any(c in body for c in (CCMOD_OTHER if kind == 'ccmod' else OTHER_CLASSES)):
+        if any(c in body for c in (CCMOD_OTHER if kind == 'ccmod' else (('ConvCnstrMODMask',) if kind == 'pgmccmod'
+                                                                         else OTHER_CLASSES))):
             continue                                      # a test of another reference class
         out.append(name)
     return out
@@ -114,7 +135,9 @@ def test_reference_admm_suite(name):
 
 # 2000-iteration recovery tests: ~1 min each under emulation; they pass (run them with
 # SPCSC_LONG_TESTS=1) but are kept out of the default CPU suite to keep it short
-LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03', 'test_04', 'test_05')}       # up to 500 / 1000 / 1000 iterations, 4-8 min emulated each
+LONG = {'pgm': ('test_10', 'test_11'), 'ccmod': ('test_03', 'test_04', 'test_05'),
+        # default MaxMainIter (1000) or 3000-iteration recovery runs
+        'pgmccmod': ('test_01', 'test_02', 'test_11', 'test_12', 'test_14', 'test_15')}       # up to 500 / 1000 / 1000 iterations, 4-8 min emulated each
 
 
 @pytest.mark.parametrize('name', _cases('pgm'))
@@ -137,6 +160,20 @@ def test_reference_ccmod_suite(name):
     if name in NOT_IMPLEMENTED['ccmod']:
         pytest.xfail('not implemented: ' + NOT_IMPLEMENTED['ccmod'][name])
     cls = _load('ccmod')
+    obj = cls()
+    obj.setup_method(None)
+    getattr(obj, name)()
+
+
+@pytest.mark.parametrize('name', _cases('pgmccmod'))
+def test_reference_pgm_ccmod_suite(name):
+    """/root/reference/tests/pgm/test_ccmod.py: the PGM dictionary update (fixed step and BacktrackStandard, linear /
+    generalised-linear momentum, multi-scale and multi-channel dictionaries, DataType)."""
+    if name in LONG['pgmccmod'] and not os.environ.get('SPCSC_LONG_TESTS'):
+        pytest.skip('long emulated run; set SPCSC_LONG_TESTS=1')
+    if name in NOT_IMPLEMENTED['pgmccmod']:
+        pytest.xfail('not implemented: ' + NOT_IMPLEMENTED['pgmccmod'][name])
+    cls = _load('pgmccmod')
     obj = cls()
     obj.setup_method(None)
     getattr(obj, name)()
