@@ -228,7 +228,7 @@ int spcsc_ccmod_setcoef(spcsc_handle* h, const void* Z);
 /* One PGM iteration with step 1/L and momentum coefficient coef = (t_prev - 1)/t  (pgm/pgm.py:779-831).
    flags select the statistics that cost a pass of their own (the reference computes both unless
    FastSolve is set, pgm/pgm.py:347-356): out[0] needs SPCSC_CCMOD_DFID, out[1] SPCSC_CCMOD_CNSTR. */
-enum { SPCSC_CCMOD_DFID = 1, SPCSC_CCMOD_CNSTR = 2, SPCSC_CCMOD_LINSOLVE = 4 };
+enum { SPCSC_CCMOD_DFID = 1, SPCSC_CCMOD_CNSTR = 2, SPCSC_CCMOD_LINSOLVE = 4, SPCSC_CCMOD_OBJ_X = 8 };
 int spcsc_ccmod_step(spcsc_handle* h, double L, double coef, int32_t flags, double out[4]);
 /* The same iteration in two parts for a backtracking search over L (sporco/pgm/backtrack.py:74-107 on
    pgm/ccmod.py:295-318, 379-393, pgm/pgm.py:850-894).  spcsc_ccmod_trial: proximal step at 1/L from the current
@@ -258,7 +258,8 @@ int spcsc_ccmod_get_spectrum(spcsc_handle* h, int32_t which, void* out);
    spcsc_ccmod_cns_step: one iteration -- xstep (:787-813: solvedbi_sm per block against its coefficient spectra),
    relax_AX (admm.py:1608-1616, rlx = RelaxParam), ystep (admm.py:1585-1591 with prox_g = Pcn, ccmod.py:842-846),
    ustep -- with U read as U / udiv (the lazy form of U /= rsf after a change of rho, admm.py:549-575).
-   out[]: [0] DFid on Y (ccmod.py:884-892 with fEvalX False), [1] Cnstr = ||Pcn(Y) - Y|| (:895-902),
+   out[]: [0] DFid on Y (ccmod.py:884-892 with fEvalX False), [1] Cnstr = ||Pcn(Y) - Y|| (:895-902) -- with
+   SPCSC_CCMOD_OBJ_X (AuxVarObj False) DFid of every block with its own X_i and Cnstr of the block mean of X instead --,
    [2] ||X||^2, [3] ||X - Y||^2, [4] ||U||^2, [5] ||Y||^2, [6] ||Yprev - Y||^2 (the host forms the residuals of
    admm.py:1673-1707 from them), [7] XSlvRelRes with SPCSC_CCMOD_LINSOLVE (LinSolveCheck, ccmod.py:815-824: the solve then
    runs out of place), else -1.  Other flags as for spcsc_ccmod_step.  With images sharded over ranks the filter supports of

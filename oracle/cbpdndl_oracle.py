@@ -217,7 +217,7 @@ def cbpdndl(D0, S, lmbda, opt=None, fft=None, reduce=None):
 # =====================================================================================
 CNS_DEFAULTS = {
     'MaxMainIter': 1000, 'rho': None, 'RelaxParam': 1.8, 'ZeroMean': False, 'Y0': None,
-    'RelStopTol': 1e-3, 'AbsStopTol': 0.0,
+    'RelStopTol': 1e-3, 'AbsStopTol': 0.0, 'AuxVarObj': True,
     'AutoRho': {'Enabled': False, 'Period': 10, 'Scaling': 2.0, 'RsdlRatio': 10.0, 'RsdlTarget': 1.0,
                 'AutoScaling': False, 'StdResiduals': False},
 }
@@ -294,9 +294,11 @@ class ConsensusCCMOD(object):
         # xstep (ccmod.py:787-813; the per-block form of xistep :825-838 is the same arithmetic)
         YU = self.Y[..., np.newaxis] - self.U
         X = np.empty_like(self.U)
+        Xfs = []
         for i in range(Nb):
             b = np.take(self.ZSf, [i], axis=axK) + self.rho * fft.rfftn(YU[..., i], None, axN)
             Xf = co.solvedbi_sm(np.take(self.Zf, [i], axis=axK), self.rho, b, axM)
+            Xfs.append(Xf)
             X[..., i] = fft.irfftn(Xf, self.Nv, axN)
         # relax_AX (admm.py:1608-1616)
         AX = X if self.rlx == 1.0 else self.rlx * X + (1 - self.rlx) * self.Y[..., np.newaxis]
@@ -336,13 +338,23 @@ class ConsensusCCMOD(object):
             s = s / sn
             epri = np.sqrt(self.Nc) * o['AbsStopTol'] / rn + o['RelStopTol']
             edua = np.sqrt(self.Nx) * o['AbsStopTol'] / sn + o['RelStopTol']
-        # objective on Y (ccmod.py:861-902 with fEvalX False, gEvalY True)
-        Yf = fft.rfftn(self.Y, None, axN)
-        Ef = co.inner(self.Zf, Yf, axM) - self.Sf
-        dfd = co.rfl2norm2(Ef, self.S.shape, axis=axN) / 2.0
-        if self.reduce is not None:
-            dfd = self.reduce(np.array([dfd], dtype=np.float64))[0]
-        cns = np.linalg.norm(self._pcn(self.Y) - self.Y)
+        if o['AuxVarObj']:
+            # objective on Y (ccmod.py:861-902 with fEvalX False, gEvalY True)
+            Yf = fft.rfftn(self.Y, None, axN)
+            Ef = co.inner(self.Zf, Yf, axM) - self.Sf
+            dfd = co.rfl2norm2(Ef, self.S.shape, axis=axN) / 2.0
+            if self.reduce is not None:
+                dfd = self.reduce(np.array([dfd], dtype=np.float64))[0]
+            cns = np.linalg.norm(self._pcn(self.Y) - self.Y)
+        else:
+            # objective on the block variables (fEvalX True, gEvalY False): data fidelity of every block with its own
+            # X_i (obfn_fvarf = swapaxes(Xf), ccmod.py:872-892), constraint violation of the block mean (admm.py:1641-1646)
+            assert self.reduce is None
+            Xfb = np.concatenate(Xfs, axis=axK)                  # (N0, N1f, Cd, Nb, M): block i on the image axis
+            Ef = co.inner(self.Zf, Xfb, axM) - self.Sf
+            dfd = co.rfl2norm2(Ef, self.S.shape, axis=axN) / 2.0
+            Yg = np.mean(X, axis=-1)
+            cns = np.linalg.norm(self._pcn(Yg) - Yg)
         self.itstat.append((self.k, float(dfd), float(cns), float(r), float(s), float(epri), float(edua),
                             float(self.rho)))
         # update_rho (admm.py:549-575)

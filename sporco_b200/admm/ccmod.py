@@ -13,8 +13,8 @@ reference does.
 
 Supported: greyscale and multi-channel signals with a single-channel dictionary (channels become
 further blocks, ccmod.py:697-705) or a dictionary with the signal's channels; the objective on the
-consensus variable (``AuxVarObj`` True, the class default), ``LinSolveCheck``.  The objective on the
-block variables (``AuxVarObj`` False) raises ``NotImplementedError``; the ``ism`` and ``cg`` solvers
+consensus variable (``AuxVarObj`` True, the class default) or on the block variables (``AuxVarObj`` False; one GPU),
+``LinSolveCheck``.  The ``ism`` and ``cg`` solvers
 are not provided (the factory functions ``ConvCnstrMOD`` / ``ConvCnstrMODOptions`` accept ``method='cns'``,
 their default in the reference).
 """
@@ -62,9 +62,8 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
         if not (np.isrealobj(S) and (Z is None or np.isrealobj(Z))):
             raise NotImplementedError('complex-valued data is not supported')
         opt = self._coerce_options(opt)
-        if opt['fEvalX'] or not opt['gEvalY']:
-            raise NotImplementedError('the objective is evaluated on the consensus variable '
-                                      '(AuxVarObj True, the class default) only')
+        if bool(opt['fEvalX']) == bool(opt['gEvalY']):
+            raise NotImplementedError('fEvalX / gEvalY must be set together through AuxVarObj')
         self.cri = cr.CDU_ConvRepIndexing(dsz, S, dimK=dimK, dimN=dimN)
         cri = self.cri
         # a single-channel dictionary with a multi-channel signal: the channels are further blocks
@@ -165,7 +164,7 @@ class ConvCnstrMOD_Consensus(admm.ADMM):
         rdt = common.real_dtype(self.dtype).type
         ar = opt['AutoRho']
         need_rsdl = ar['Enabled'] or not opt['FastSolve']
-        flags = (0 if opt['FastSolve'] else 3) | (4 if opt['LinSolveCheck'] else 0)
+        flags = (0 if opt['FastSolve'] else 3) | (4 if opt['LinSolveCheck'] else 0) | (8 if opt['fEvalX'] else 0)
         rows, done, stopped = [], 0, False
         for _ in range(n):
             k = self.k + done

@@ -343,6 +343,28 @@ SPCSC_GLOBAL void k_cns_ynorms(const T* SPCSC_RESTRICT Yold, const T* SPCSC_REST
     block_accumulate<2>(s, red, acc + ACC_CNS_Y2);
 }
 
+// Objective on the block variables (AuxVarObj False: gEvalY False, admm.py:1641-1646): G[c] = mean over the blocks bb = c
+// mod Cd of X[bb], full planes; and the part of ||Pcn(G) - G||^2 that lies outside the largest filter support (there
+// Pcn(G) = 0), added to the slot k_pcn's check mode uses for the part inside.
+template <typename T>
+SPCSC_GLOBAL void k_cns_mean_x(const T* SPCSC_RESTRICT X, T* SPCSC_RESTRICT Gm, double* SPCSC_RESTRICT acc, int NB, int Cd,
+                               int M, int N0, int N1, int hd, int wd, T winv) {
+    __shared__ double red[32];
+    const size_t img = (size_t)N0 * N1, plane = (size_t)M * img, n = (size_t)Cd * plane;
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / plane, o = i - c * plane;
+        T a = 0;
+        for (int bb = (int)c; bb < NB; bb += Cd) a += X[(size_t)bb * plane + o];
+        a *= winv;
+        Gm[i] = a;
+        const size_t px = o % img;
+        const int y = (int)(px / N1), x = (int)(px % N1);
+        if (y >= hd || x >= wd) s[0] += (double)a * (double)a;
+    }
+    block_accumulate<1>(s, red, acc + ACC_CDL_CNS);
+}
+
 // LinSolveCheck of the consensus x step (ccmod.py:815-824): relative residual of the block solves SUMMED over the
 // blocks,  ax = sum_i [conj(Zf_i) (sum_m Zf_i,m Xf_i,m) + rho Xf_i],  b = sum_i [conj(Zf_i) Sf_i + rho rfftn(Y - U_i)],
 // XSlvRelRes = ||ax - b|| / ||b|| (plain norms over the stored half spectra).  One CTA per (wf, tile of 32 frequencies):

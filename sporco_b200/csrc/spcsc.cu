@@ -1692,6 +1692,11 @@ class Engine : public spcsc_handle {
         CK(launch(k_cns_yu<T>, dim3(148, NB), dim3(256), 0, stream, (const T*)cdX.p, (const T*)cnsU.p, cnsX.p, NB, Cd,
                   plane, uinv));
         const bool lscheck = (flags & SPCSC_CCMOD_LINSOLVE) != 0;
+        // objective on the block variables (AuxVarObj False): the data fidelity falls out of the block solves
+        // (sum_m Zf_i,m Xf_i,m - Sf_i = -rho q_i, as in ConvBPDN), the constraint term is taken on the block mean of X
+        const bool obj_x = (flags & SPCSC_CCMOD_OBJ_X) != 0 && (flags & (SPCSC_CCMOD_DFID | SPCSC_CCMOD_CNSTR)) != 0;
+        if (obj_x && nccl_comm) FAIL(SPCSC_ERR_UNSUPPORTED, "AuxVarObj False with the blocks sharded over ranks");
+        if (obj_x) CK(cudaMemsetAsync(acc.p + ACC_DFID, 0, sizeof(double), stream));
         C2<T>* xf = cnsZ.p;
         ColLaunch<T> c = colargs(M, NB);
         c.in = cnsZ.p; c.out = cnsZ.p;
@@ -1703,6 +1708,7 @@ class Engine : public spcsc_handle {
         c.a.df_bdiv = Cd;
         c.push = 0; c.bulk = 0;
         c.Lstep = 0;
+        c.a.dfid_on = obj_x ? 1 : 0;
         double hls[2] = {0.0, 0.0};
         if (lscheck) {
             // LinSolveCheck: forward columns, solve and inverse columns as separate launches of the general kernel, so
@@ -1789,7 +1795,18 @@ class Engine : public spcsc_handle {
         rc = forward2d(cdX.p, cdXf.p, M, Cd);
         if (rc) return rc;
         double ha[4] = {0.0, 0.0, 0.0, 0.0};
-        if (flags & (SPCSC_CCMOD_DFID | SPCSC_CCMOD_CNSTR)) {
+        double hq = 0.0;
+        if (obj_x) {
+            CK(cudaMemcpyAsync(&hq, acc.p + ACC_DFID, sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemsetAsync(acc.p + ACC_DFID, 0, sizeof(double), stream));
+            CK(tmp_real.ensure((size_t)Cd * plane));
+            CK(launch(k_cns_mean_x<T>, dim3(592), dim3(256), 0, stream, (const T*)cnsX.p, tmp_real.p, acc.p, NB, Cd, M, N0, N1,
+                      pb.hd, pb.wd, (T)(1.0 / (double)(NB / Cd))));
+            CK(launch(k_pcn<T>, dim3(M), dim3(128), 0, stream, (const T*)tmp_real.p, (T*)nullptr, acc.p, Cd, M,
+                      N0, N1, pb.hd, pb.wd, cd_zero_mean, 1, (const int*)cd_fsupp.p));
+            CK(cudaMemcpyAsync(ha, acc.p + ACC_CDL_F, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemsetAsync(acc.p + ACC_CDL_F, 0, 4 * sizeof(double), stream));
+        } else if (flags & (SPCSC_CCMOD_DFID | SPCSC_CCMOD_CNSTR)) {
             if (flags & SPCSC_CCMOD_DFID) CK(launch_grad<false>((const C2<T>*)cdXf.p, (C2<T>*)nullptr));
             if (nccl_comm && (flags & SPCSC_CCMOD_DFID)) {
                 rc = reduce_acc_over_ranks();
@@ -1803,7 +1820,7 @@ class Engine : public spcsc_handle {
         }
         CK(cudaStreamSynchronize(stream));
         const double inv_n = 1.0 / ((double)N0 * (double)N1);
-        out[0] = 0.5 * ha[1] * inv_n;
+        out[0] = obj_x ? 0.5 * rho * rho * hq * inv_n : 0.5 * ha[1] * inv_n;
         out[1] = std::sqrt(ha[3]);
         out[2] = hn[0]; out[3] = hn[1]; out[4] = hn[2]; out[5] = hn[3]; out[6] = hn[4];
         out[7] = lscheck ? (hls[1] > 0.0 ? std::sqrt(hls[0] / hls[1]) : std::sqrt(hls[0])) : -1.0;
