@@ -13,7 +13,9 @@ resident in HBM, max over ranks); `e2e` = the same through the public class with
 arrays in and the coefficient maps back out; `roofline` = the dominant kernel's algorithmic
 bytes / its event-timed duration against MEASURED_PEAKS.json; `cpu_baseline` = the numpy
 oracle (a restatement of the reference, bit-identical to it here) on the full 32-image batch for a
-few iterations; `configs` = short runs of BASELINE.json's other configurations; at N > 1
+few iterations; `configs` = short runs of BASELINE.json's other configurations plus `modes` (the metric
+configuration in the other two timing modes of SURVEY.md section 8d: class defaults with statistics every iteration, and
+FastSolve without AutoRho); at N > 1
 `parity_check` = a small sharded solve against the oracle on the whole batch (the run fails if
 it disagrees).  Reference arm (`--impl reference`): the oracle on the host cores, full batch, the
 same warm-up / timed iterations of one solve as the device arm.
@@ -392,6 +394,10 @@ def run_b200(args):
                 cfgs[name] = bench_configs.measure(name, peak, quick=True)
             except Exception as e:        # a configuration must not take the headline line down
                 cfgs[name] = {'error': '%s: %s' % (type(e).__name__, e)}
+        try:
+            cfgs['modes'] = measure_modes(local_rank, steps=min(args.steps, 50), warm=max(args.warmup, 3))
+        except Exception as e:
+            cfgs['modes'] = {'error': '%s: %s' % (type(e).__name__, e)}
 
     out = {
         'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
@@ -417,6 +423,30 @@ def run_b200(args):
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measure_modes(device, steps=20, warm=5):
+    """The other two timing modes of SURVEY.md section 8(d) at the metric configuration (the headline is mode B:
+    FastSolve with AutoRho): (A) the class defaults -- residuals, AutoRho and the objective / iteration record every
+    iteration (sporco/admm/admm.py:350-377) --, (C) FastSolve without AutoRho -- pure x / y / u steps, no reductions.
+    Device time (CUDA events on the library's stream) of `steps` iterations after `warm`."""
+    from sporco_b200.admm import cbpdn
+    out = {}
+    for name, o, rows in (('A_default', {'RelStopTol': 0.0, 'AutoRho': {'Enabled': True}}, True),
+                          ('C_fastsolve_fixed_rho', {'RelStopTol': 0.0, 'FastSolve': True,
+                                                     'AutoRho': {'Enabled': False}}, False)):
+        D, S = make_inputs(K_PER_GPU)
+        opt = dict(o)
+        opt['MaxMainIter'] = steps
+        b = cbpdn.ConvBPDN(D, S, LMBDA, cbpdn.ConvBPDN.Options(opt), dimK=1, device=device)
+        h = b._h
+        h.admm_configure(**b._admm_config())
+        h.admm_iterate(warm, rows)
+        _, done, _ = h.admm_iterate(steps, rows)
+        ms, _ = h.admm_last_timing()
+        out[name] = {'ms_per_step': ms / max(done, 1), 'it_per_s': done / (ms / 1e3), 'steps': int(done), 'warmup': warm}
+        del b, h
+    return out
 
 
 def run_cfg5(args):

@@ -289,3 +289,17 @@ def test_dictionary_update_backtracking_golden(sfx):
 @pytest.mark.parametrize('dt', [np.float64, np.float32])
 def test_gradient_regularisation_with_a_multichannel_dictionary(dt):
     cases.run_gradreg_multichannel_dict(dt)
+
+
+def test_bench_mode_helper_runs_on_a_small_problem(monkeypatch):
+    """bench.measure_modes (timing modes A and C of SURVEY.md section 8d) with the problem shrunk for the emulation."""
+    import bench
+    monkeypatch.setattr(bench, 'N0', 32)
+    monkeypatch.setattr(bench, 'N1', 32)
+    monkeypatch.setattr(bench, 'M', 4)
+    monkeypatch.setattr(bench, 'HD', 5)
+    monkeypatch.setattr(bench, 'K_PER_GPU', 2)
+    r = bench.measure_modes(0, steps=4, warm=3)
+    assert set(r) == {'A_default', 'C_fastsolve_fixed_rho'}
+    for v in r.values():
+        assert v['steps'] == 4 and v['it_per_s'] > 0
